@@ -1,0 +1,90 @@
+"""CPU: the oracle restatement (oracle/dbsr_oracle.py) against vectors produced by the reference's own
+modules (oracle/make_golden.py -> tests/golden/*.npz).  fp32 tolerance: the oracle re-associates a few
+sums (explicit gathers vs ATen kernels), so 2e-5 abs on pred in [0, 0.13] and 1e-4 px on the flow."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import dbsr_oracle as O
+
+
+def _load(golden_dir, name):
+    return np.load(os.path.join(golden_dir, name + '.npz'))
+
+
+def test_state_dict_contract(golden_dir):
+    lines = open(os.path.join(golden_dir, 'state_dict_keys.txt')).read().split('\n')
+    ref = [l.split(' ') for l in lines if l]
+    spec = O.state_dict_spec()
+    assert len(spec) == len(ref) == 231
+    for (k, s), (rk, rs) in zip(spec, ref):
+        assert k == rk
+        assert 'x'.join(map(str, s)) == rs
+    sd = O.make_state_dict(0)
+    assert sum(v.numel() for v in sd.values()) == 13011237  # SURVEY.md 8c parameter count
+
+
+def test_ops_against_reference(golden_dir):
+    g = _load(golden_dir, 'ops')
+    feat = torch.from_numpy(g['feat'])
+    flow = torch.from_numpy(g['flow'])
+    assert np.abs(O.warp(feat, flow).numpy() - g['warp']).max() < 2e-5
+    assert np.abs(O.backwarp(feat, flow).numpy() - g['backwarp']).max() < 2e-5
+    assert np.abs(O.resize_bilinear(feat, 64, 64).numpy() - g['interp_up']).max() < 1e-5
+    assert np.abs(O.resize_bilinear(feat, 5, 7).numpy() - g['interp_down']).max() < 1e-5
+    f1 = torch.from_numpy(g['corr_f1'])
+    f2 = torch.from_numpy(g['corr_f2'])
+    assert np.abs(O.correlation81(f1, f2).numpy() - g['corr']).max() < 1e-6
+    assert np.abs(O.correlation81_bruteforce(f1[:1, :, :3, :4], f2[:1, :, :3, :4]).numpy()
+                  - O.correlation81(f1[:1, :, :3, :4], f2[:1, :, :3, :4]).numpy()).max() < 1e-6
+    m = torch.remainder(torch.tensor([-0.25, 1.75, -1e-9, 0.0, 3.0]), 1.0).numpy()
+    assert np.array_equal(m, g['mod'])
+
+
+def test_semantic_kats():
+    """SURVEY.md Appendix D(7)."""
+    g = torch.Generator().manual_seed(3)
+    img = torch.rand(1, 2, 6, 7, generator=g)
+    # integer flow == shift
+    flow = torch.zeros(1, 2, 6, 7)
+    flow[:, 0] = 1.0
+    w = O.warp(img, flow)
+    assert torch.allclose(w[..., :-1], img[..., 1:], atol=1e-6) and float(w[..., -1].abs().max()) == 0.0
+    # backwarp: flow (W-1)/W shifts by exactly one pixel
+    flow[:, 0] = (7 - 1.0) / 7
+    bw = O.backwarp(img, flow)
+    assert torch.allclose(bw[..., :-1], img[..., 1:], atol=1e-5)
+    # pixel shuffle index map
+    x = torch.arange(64 * 2 * 3, dtype=torch.float32).view(1, 64, 2, 3)
+    ps = O.pixel_shuffle(x, 8)
+    assert torch.equal(ps, torch.nn.functional.pixel_shuffle(x, 8))
+    assert ps[0, 0, 8 * 1 + 3, 8 * 2 + 5] == x[0, 3 * 8 + 5, 1, 2]
+    # deconv restatement
+    xin = torch.randn(2, 5, 3, 4, generator=g)
+    wt = torch.randn(5, 2, 4, 4, generator=g)
+    b = torch.randn(2, generator=g)
+    ref = torch.nn.functional.conv_transpose2d(xin, wt, b, stride=2, padding=1)
+    assert torch.allclose(O.deconv4x4s2(xin, wt, b), ref, atol=1e-5)
+    K = O.gauss_kernel3()
+    assert abs(float(K[1, 1]) - 0.2042) < 1e-4 and abs(float(K[0, 0]) - 0.0751) < 1e-4
+
+
+@pytest.mark.parametrize('name', ['tiny_b1n3_16x16', 'rect_b2n4_24x40', 'stress_b1n5_32x32', 'cfg1_b1n14_48x48'])
+def test_forward_against_reference(golden_dir, name):
+    g = _load(golden_dir, name)
+    wseed, bseed, B, N, H, W = [int(v) for v in g['meta']]
+    sd = O.make_state_dict(wseed, pwc_gain=float(g['pwc_gain'][0]))
+    burst = O.make_burst(bseed, B, N, H, W)
+    pred, aux = O.dbsr_forward(burst, sd)
+    flow_tol = 1e-4 if float(g['pwc_gain'][0]) == 1.0 else 5e-3
+    assert np.abs(aux['offsets'].numpy() - g['offsets']).max() < flow_tol
+    if 'pred' in g:
+        assert np.abs(pred.numpy() - g['pred']).max() < 2e-5
+    else:
+        assert np.abs(pred[:, :, ::2, ::2].numpy() - g['pred_sub']).max() < 2e-5
+        assert abs(pred.double().sum().item() - g['pred_sum'][0]) < 1e-3 * abs(g['pred_sum'][0])
+    fw = aux['fusion_weights']
+    assert np.abs(fw[:, :, ::37, ::3, ::3].numpy() - g['fusion_weights_sub']).max() < 2e-5
+    assert np.abs(fw.mean(dim=(2, 3, 4)).numpy() - g['fusion_weights_mean']).max() < 1e-5
