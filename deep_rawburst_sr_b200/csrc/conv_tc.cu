@@ -1,0 +1,515 @@
+// tcgen05 / TMEM implicit-GEMM convolution for sm_100a (bf16 operands, fp32 accumulation in tensor memory).
+//
+// Replaces the cuDNN fp32 convs + separate ReLU / residual-add kernels of the DBSR encoder, fusion weight
+// predictor and decoder (reference models/layers/blocks.py:46-96, models/dbsr/{encoders,merging,decoders}.py).
+//
+// GEMM view:  D[pixels, Cout] = sum_{tap, cin} X[pixel + tap, cin] * W[tap, cout, cin]
+//   M tile   : 128 output pixels = 16 rows x 8 columns of one image (one TMEM lane per pixel)
+//   N tile   : BLOCK_N output channels (32 / 64 / 128) = TMEM columns, double buffered
+//   K loop   : for kx in 0..2 : for cin chunk of CK (64 -> SWIZZLE_128B rows, 32 -> SWIZZLE_64B rows):
+//                one TMA box {CK ch, 8 px, 16 + 2*dil rows} of the NHWC input at (x0 + (kx-1)*dil, y0 - dil)
+//                -- out-of-image coordinates are zero-filled by TMA, which IS the conv zero padding --
+//                serves the three ky taps: 8 pixels x CK channels is exactly one swizzle atom, so the tap
+//                (ky) view of the tile is the same smem at a +ky*dil*atom byte offset (1024 B / 512 B aligned).
+//                The three [BLOCK_N x CK] weight tiles of (ky, kx) ride in the same pipeline stage.
+//   Roles    : warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread tcgen05.mma issuer,
+//              warps 2..5 = epilogue (tcgen05.ld -> +bias, +residual, activation -> bf16/fp32 global stores).
+//   Persistent: grid = min(#work items, #SMs); work item = (pixel tile, N tile), N tile fastest.
+//   Pixel-shuffle (upsampling.py:57) is folded into the store addressing: the packed weight rows are
+//   permuted to (i, j, c) order so an N tile of 128 channels is 4 adjacent HR pixels x 32 channels, contiguous.
+#include "common.cuh"
+
+#include <cuda.h>
+
+namespace dbsr {
+
+// ---------------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// bounded wait: a protocol bug traps (with a message) instead of hanging the GPU
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int tag) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if (++spins > (1u << 26)) {
+      printf("conv_tc: mbarrier timeout tag=%d block=%d thread=%d parity=%u\n", tag, (int)blockIdx.x, (int)threadIdx.x,
+             parity);
+      __trap();
+    }
+  }
+}
+
+__device__ __forceinline__ void tma_load_4d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, int c2,
+                                            int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(cols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
+}
+
+// D[tmem] (+)= A[smem desc] * B[smem desc], bf16 x bf16 -> fp32, M = 128, issued by one thread
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive on an mbarrier when all previously issued tcgen05.mma of this thread have completed
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// K-major shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout):
+//   [0,14) start>>4 | [16,30) LBO>>4 (unused for swizzled K-major, canonical value 1) | [32,46) SBO>>4
+//   [46,48) version = 1 (sm_100) | [61,64) layout: 2 = SWIZZLE_128B, 4 = SWIZZLE_64B
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t sbo_bytes, uint32_t layout) {
+  return (uint64_t)((saddr >> 4) & 0x3FFFu) | (1ull << 16) | ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) |
+         (1ull << 46) | ((uint64_t)layout << 61);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// kernel
+// ---------------------------------------------------------------------------------------------------------
+constexpr int TILE_H = 16, TILE_W = 8;
+constexpr int TC_THREADS = 192;
+
+struct ConvTcParams {
+  int n, H, W;          // input == output spatial size (stride 1, "same" padding)
+  int ksize, dil;
+  int nchunks;          // Cin_pad / CK
+  int cout_pad;         // rows per tap in the packed weight matrix
+  int ntiles_n;         // Cout / BLOCK_N
+  int tiles_x, tiles_y;
+  long long total_items;
+  int stages;
+  int a_bytes, b_tap_bytes;  // per stage
+  // output
+  void* y; int y_dtype; int y_pitch; int y_coff; int yH, yW;
+  const void* res; int r_pitch; int r_coff;   // bf16 residual with the geometry of y
+  const float* bias;
+  int act;
+  int shuffle_r;        // 8: pixel shuffle addressing (y is the (8H, 8W, 32) map)
+};
+
+template <int BLOCK_N, int CK>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
+               const ConvTcParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // carve: [stages x (A | B taps)] then barriers
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int taps_per_stage = p.ksize;  // 3 (ky) for 3x3, 1 for 1x1
+  const int stage_bytes = p.a_bytes + taps_per_stage * p.b_tap_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * stage_bytes);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + p.stages;
+  uint64_t* tfull_bar = bars + 2 * p.stages;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr uint32_t TMEM_COLS = (2 * BLOCK_N < 32) ? 32 : 2 * BLOCK_N;
+  constexpr uint32_t ROW_BYTES = CK * 2;                 // bytes per pixel row of a K chunk
+  constexpr uint32_t ATOM_BYTES = 8 * ROW_BYTES;         // 8 rows: 1024 (SW128) / 512 (SW64)
+  constexpr uint32_t LAYOUT = (CK == 64) ? 2u : 4u;
+  constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BLOCK_N >> 3) << 17) | ((128u >> 4) << 24);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    tma_prefetch_desc(&tmap_x);
+    tma_prefetch_desc(&tmap_w);
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int ksteps = (p.ksize == 3 ? 3 : 1) * p.nchunks;
+  const int tiles_per_img = p.tiles_x * p.tiles_y;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (long long item = blockIdx.x; item < p.total_items; item += gridDim.x) {
+        const int nt = (int)(item % p.ntiles_n);
+        const long long tm = item / p.ntiles_n;
+        const int img = (int)(tm / tiles_per_img);
+        const int trem = (int)(tm - (long long)img * tiles_per_img);
+        const int y0 = (trem / p.tiles_x) * TILE_H, x0 = (trem % p.tiles_x) * TILE_W;
+        for (int ks = 0; ks < ksteps; ++ks) {
+          const int kx = (p.ksize == 3) ? ks / p.nchunks : 0;
+          const int ch = ks - kx * p.nchunks;
+          mbar_wait(&empty_bar[stage], phase ^ 1, 100 + stage);
+          uint8_t* sa = smem + (size_t)stage * stage_bytes;
+          mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)stage_bytes);
+          if (p.ksize == 3) {
+            tma_load_4d(&tmap_x, &full_bar[stage], sa, ch * CK, x0 + (kx - 1) * p.dil, y0 - p.dil, img);
+            for (int ky = 0; ky < 3; ++ky)
+              tma_load_2d(&tmap_w, &full_bar[stage], sa + p.a_bytes + ky * p.b_tap_bytes, ch * CK,
+                          (ky * 3 + kx) * p.cout_pad + nt * BLOCK_N);
+          } else {
+            tma_load_4d(&tmap_x, &full_bar[stage], sa, ch * CK, x0, y0, img);
+            tma_load_2d(&tmap_w, &full_bar[stage], sa + p.a_bytes, ch * CK, nt * BLOCK_N);
+          }
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      int acc = 0; uint32_t acc_phase = 0;
+      for (long long item = blockIdx.x; item < p.total_items; item += gridDim.x) {
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1, 200 + acc);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BLOCK_N);
+        for (int ks = 0; ks < ksteps; ++ks) {
+          mbar_wait(&full_bar[stage], phase, 300 + stage);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
+          const uint32_t sb = sa + (uint32_t)p.a_bytes;
+          for (int ky = 0; ky < taps_per_stage; ++ky) {
+            const uint32_t a_tap = sa + (uint32_t)(ky * p.dil) * ATOM_BYTES;
+            const uint32_t b_tap = sb + (uint32_t)(ky * p.b_tap_bytes);
+#pragma unroll
+            for (int k16 = 0; k16 < CK / 16; ++k16) {
+              const uint64_t adesc = make_smem_desc(a_tap + k16 * 32, ATOM_BYTES, LAYOUT);
+              const uint64_t bdesc = make_smem_desc(b_tap + k16 * 32, ATOM_BYTES, LAYOUT);
+              umma_bf16(d_tmem, adesc, bdesc, IDESC, (ks | ky | k16) != 0 ? 1u : 0u);
+            }
+          }
+          umma_commit(&empty_bar[stage]);  // frees the smem stage when these MMAs retire
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tfull_bar[acc]);      // accumulator ready for the epilogue
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else {
+    // ===================== epilogue (warps 2..5) =====================
+    const int quarter = warp & 3;                  // TMEM lane quarter this warp may access
+    const int m = quarter * 32 + lane;             // pixel within the tile
+    const int ty = m >> 3, tx = m & 7;
+    int acc = 0; uint32_t acc_phase = 0;
+    for (long long item = blockIdx.x; item < p.total_items; item += gridDim.x) {
+      const int nt = (int)(item % p.ntiles_n);
+      const long long tm = item / p.ntiles_n;
+      const int img = (int)(tm / tiles_per_img);
+      const int trem = (int)(tm - (long long)img * tiles_per_img);
+      const int y = (trem / p.tiles_x) * TILE_H + ty, x = (trem % p.tiles_x) * TILE_W + tx;
+      const bool valid = (y < p.H) && (x < p.W);
+      long long off;   // element offset of this thread's first output channel
+      if (p.shuffle_r > 1) {
+        // packed channel co' = i*256 + j*32 + c ; N tile = 128 -> i = nt / 2, j0 = (nt & 1) * 4
+        const int per_i = p.shuffle_r * 32;        // channels per HR row phase
+        const int co0 = nt * BLOCK_N;
+        const int si = co0 / per_i, j0 = (co0 - si * per_i) / 32;
+        off = (((long long)img * p.yH + (y * p.shuffle_r + si)) * p.yW + (x * p.shuffle_r + j0)) * p.y_pitch + p.y_coff;
+      } else {
+        off = (((long long)img * p.yH + y) * p.yW + x) * p.y_pitch + p.y_coff + nt * BLOCK_N;
+      }
+      const long long roff = (((long long)img * p.yH + y) * p.yW + x) * p.r_pitch + p.r_coff + nt * BLOCK_N;
+
+      mbar_wait(&tfull_bar[acc], acc_phase, 400 + acc);
+      tc_fence_after();
+#pragma unroll 1
+      for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+        uint32_t r[32];
+        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BLOCK_N + c0);
+        tmem_ld32(taddr, r);
+        if (valid) {
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+          if (p.bias) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + nt * BLOCK_N + c0 + j));
+              v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+            }
+          }
+          if (p.res) {
+            const __nv_bfloat16* rp = reinterpret_cast<const __nv_bfloat16*>(p.res) + roff + c0;
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              const uint4 q = __ldg(reinterpret_cast<const uint4*>(rp + j));
+              const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&q);
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const float2 f = __bfloat1622float2(h[k]);
+                v[j + 2 * k] += f.x; v[j + 2 * k + 1] += f.y;
+              }
+            }
+          }
+          if (p.act == DBSR_ACT_RELU) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.0f);
+          } else if (p.act == DBSR_ACT_LRELU) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = v[j] > 0.0f ? v[j] : 0.1f * v[j];
+          }
+          if (p.y_dtype == DBSR_BF16) {
+            __nv_bfloat16* yp = reinterpret_cast<__nv_bfloat16*>(p.y) + off + c0;
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              uint4 q;
+              __nv_bfloat162 h0 = __floats2bfloat162_rn(v[j], v[j + 1]);
+              __nv_bfloat162 h1 = __floats2bfloat162_rn(v[j + 2], v[j + 3]);
+              __nv_bfloat162 h2 = __floats2bfloat162_rn(v[j + 4], v[j + 5]);
+              __nv_bfloat162 h3 = __floats2bfloat162_rn(v[j + 6], v[j + 7]);
+              q.x = *reinterpret_cast<uint32_t*>(&h0); q.y = *reinterpret_cast<uint32_t*>(&h1);
+              q.z = *reinterpret_cast<uint32_t*>(&h2); q.w = *reinterpret_cast<uint32_t*>(&h3);
+              *reinterpret_cast<uint4*>(yp + j) = q;
+            }
+          } else {
+            float* yp = reinterpret_cast<float*>(p.y) + off + c0;
+#pragma unroll
+            for (int j = 0; j < 32; j += 4)
+              *reinterpret_cast<float4*>(yp + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+          }
+        }
+      }
+      // all TMEM reads of this warp are complete (tcgen05.wait::ld inside tmem_ld32): release the accumulator
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  }
+  return fn;
+}
+
+struct TcConfig {
+  int block_n, ck, nchunks, cout_pad, stages, a_bytes, b_tap_bytes, smem_bytes;
+};
+
+static int tc_plan(const dbsr_conv_t* c, TcConfig* cfg, bool set_err) {
+#define TC_REQ(cond, ...) do { if (!(cond)) { if (set_err) set_error(__VA_ARGS__); return 1; } } while (0)
+  TC_REQ(c && view_ok(&c->x) && view_ok(&c->y) && c->w, "conv2d_tc: bad descriptor");
+  TC_REQ(c->x.dtype == DBSR_BF16, "conv2d_tc: input must be bf16");
+  TC_REQ(c->ksize == 1 || c->ksize == 3, "conv2d_tc: ksize must be 1 or 3");
+  TC_REQ(c->stride == 1, "conv2d_tc: stride must be 1");
+  TC_REQ(c->dilation >= 1 && c->dilation <= 16, "conv2d_tc: dilation out of range");
+  const int r = c->shuffle_r > 1 ? c->shuffle_r : 1;
+  const int cout = c->y.c * r * r;
+  TC_REQ(c->y.n == c->x.n && c->y.h == c->x.h * r && c->y.w == c->x.w * r, "conv2d_tc: output geometry mismatch");
+  TC_REQ((c->x.c_off % 8) == 0 && (c->x.c_pitch % 8) == 0 && ((uintptr_t)c->x.data % 16) == 0,
+         "conv2d_tc: input view must be 16-byte aligned (c_off, c_pitch multiples of 8)");
+  int bn;
+  if (r > 1) {
+    TC_REQ(r == 8 && c->y.c == 32 && c->y.c_pitch == 32 && c->y.c_off == 0 && cout % 128 == 0,
+           "conv2d_tc: pixel-shuffle mode needs r=8 and a dense 32-channel output map");
+    bn = 128;
+  } else if (cout % 128 == 0) bn = 128;
+  else if (cout % 64 == 0) bn = 64;
+  else if (cout % 32 == 0) bn = 32;
+  else { TC_REQ(false, "conv2d_tc: Cout=%d must be a multiple of 32", cout); }
+  const size_t yes = elem_size(c->y.dtype);
+  TC_REQ(((c->y.c_off * yes) % 16) == 0 && ((c->y.c_pitch * yes) % 16) == 0 && ((uintptr_t)c->y.data % 16) == 0,
+         "conv2d_tc: output view must be 16-byte aligned");
+  if (c->residual.data) {
+    TC_REQ(r == 1 && c->residual.dtype == DBSR_BF16 && c->residual.n == c->y.n && c->residual.h == c->y.h &&
+               c->residual.w == c->y.w && c->residual.c == c->y.c && (c->residual.c_off % 8) == 0 &&
+               (c->residual.c_pitch % 8) == 0 && ((uintptr_t)c->residual.data % 16) == 0,
+           "conv2d_tc: residual must be an aligned bf16 view with the geometry of y");
+  }
+  if (c->bias) TC_REQ(((uintptr_t)c->bias % 16) == 0, "conv2d_tc: bias must be 16-byte aligned");
+  const int cin = c->x.c;
+  const int ck = (cin % 64 == 0) ? 64 : 32;
+  cfg->block_n = bn;
+  cfg->ck = ck;
+  cfg->nchunks = (cin + ck - 1) / ck;
+  cfg->cout_pad = cout;
+  const int rows = (c->ksize == 3) ? TILE_H + 2 * c->dilation : TILE_H;
+  cfg->a_bytes = rows * TILE_W * ck * 2;
+  cfg->b_tap_bytes = bn * ck * 2;
+  const int stage = cfg->a_bytes + c->ksize * cfg->b_tap_bytes;
+  const int budget = 227 * 1024 - 2048;
+  int stages = budget / stage;
+  if (stages > 6) stages = 6;
+  TC_REQ(stages >= 2, "conv2d_tc: pipeline stage of %d bytes does not fit twice in shared memory", stage);
+  cfg->stages = stages;
+  cfg->smem_bytes = stages * stage + 1024 /*align slack*/ + 256 /*barriers*/;
+  return 0;
+#undef TC_REQ
+}
+
+template <int BN, int CK>
+static int launch_tc(const CUtensorMap& mx, const CUtensorMap& mw, const ConvTcParams& p, int smem, cudaStream_t st) {
+  static int configured_smem = 0;
+  if (smem > configured_smem) {
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BN, CK>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) {
+      set_error("conv2d_tc: cudaFuncSetAttribute(%d) failed: %s", smem, cudaGetErrorString(e));
+      return 2;
+    }
+    configured_smem = smem;
+  }
+  static int num_sms = 0;
+  if (!num_sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+  }
+  const int grid = (int)(p.total_items < num_sms ? p.total_items : num_sms);
+  conv_tc_kernel<BN, CK><<<grid, TC_THREADS, smem, st>>>(mx, mw, p);
+  return check_launch("conv2d_tc");
+}
+
+}  // namespace dbsr
+
+using namespace dbsr;
+
+extern "C" int dbsr_conv2d_tc_supported(const dbsr_conv_t* c) {
+  TcConfig cfg;
+  return tc_plan(c, &cfg, false) == 0 ? 1 : 0;
+}
+
+extern "C" int dbsr_conv2d_tc(const dbsr_conv_t* c, void* stream) {
+  TcConfig cfg;
+  if (tc_plan(c, &cfg, true)) return 1;
+  EncodeTiledFn encode = get_encode();
+  DBSR_REQUIRE(encode != nullptr, "conv2d_tc: cuTensorMapEncodeTiled entry point not available");
+
+  const int r = c->shuffle_r > 1 ? c->shuffle_r : 1;
+  const int rows = (c->ksize == 3) ? TILE_H + 2 * c->dilation : TILE_H;
+  const CUtensorMapSwizzle swz = cfg.ck == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+
+  alignas(64) CUtensorMap mx, mw;
+  {
+    cuuint64_t dims[4] = {(cuuint64_t)c->x.c, (cuuint64_t)c->x.w, (cuuint64_t)c->x.h, (cuuint64_t)c->x.n};
+    cuuint64_t strides[3] = {(cuuint64_t)c->x.c_pitch * 2, (cuuint64_t)c->x.w * c->x.c_pitch * 2,
+                             (cuuint64_t)c->x.h * c->x.w * c->x.c_pitch * 2};
+    cuuint32_t box[4] = {(cuuint32_t)cfg.ck, (cuuint32_t)TILE_W, (cuuint32_t)rows, 1};
+    cuuint32_t es[4] = {1, 1, 1, 1};
+    void* base = reinterpret_cast<__nv_bfloat16*>(c->x.data) + c->x.c_off;
+    CUresult rc = encode(&mx, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, base, dims, strides, box, es,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    DBSR_REQUIRE(rc == CUDA_SUCCESS, "conv2d_tc: cuTensorMapEncodeTiled(x) failed with %d", (int)rc);
+  }
+  {
+    const int taps = c->ksize * c->ksize;
+    const int kpad = cfg.nchunks * cfg.ck;
+    cuuint64_t dims[2] = {(cuuint64_t)kpad, (cuuint64_t)taps * cfg.cout_pad};
+    cuuint64_t strides[1] = {(cuuint64_t)kpad * 2};
+    cuuint32_t box[2] = {(cuuint32_t)cfg.ck, (cuuint32_t)cfg.block_n};
+    cuuint32_t es[2] = {1, 1};
+    CUresult rc = encode(&mw, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(c->w), dims, strides, box, es,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    DBSR_REQUIRE(rc == CUDA_SUCCESS, "conv2d_tc: cuTensorMapEncodeTiled(w) failed with %d", (int)rc);
+  }
+
+  ConvTcParams p;
+  p.n = c->x.n; p.H = c->x.h; p.W = c->x.w;
+  p.ksize = c->ksize; p.dil = c->dilation;
+  p.nchunks = cfg.nchunks; p.cout_pad = cfg.cout_pad;
+  p.ntiles_n = cfg.cout_pad / cfg.block_n;
+  p.tiles_x = ceil_div(p.W, TILE_W); p.tiles_y = ceil_div(p.H, TILE_H);
+  p.total_items = (long long)p.n * p.tiles_x * p.tiles_y * p.ntiles_n;
+  p.stages = cfg.stages; p.a_bytes = cfg.a_bytes; p.b_tap_bytes = cfg.b_tap_bytes;
+  p.y = c->y.data; p.y_dtype = c->y.dtype; p.y_pitch = c->y.c_pitch; p.y_coff = c->y.c_off;
+  p.yH = c->y.h; p.yW = c->y.w;
+  p.res = c->residual.data; p.r_pitch = c->residual.c_pitch; p.r_coff = c->residual.c_off;
+  p.bias = c->bias; p.act = c->act; p.shuffle_r = r;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (cfg.block_n == 128 && cfg.ck == 64) return launch_tc<128, 64>(mx, mw, p, cfg.smem_bytes, st);
+  if (cfg.block_n == 64 && cfg.ck == 64) return launch_tc<64, 64>(mx, mw, p, cfg.smem_bytes, st);
+  if (cfg.block_n == 32 && cfg.ck == 64) return launch_tc<32, 64>(mx, mw, p, cfg.smem_bytes, st);
+  if (cfg.block_n == 128 && cfg.ck == 32) return launch_tc<128, 32>(mx, mw, p, cfg.smem_bytes, st);
+  if (cfg.block_n == 64 && cfg.ck == 32) return launch_tc<64, 32>(mx, mw, p, cfg.smem_bytes, st);
+  if (cfg.block_n == 32 && cfg.ck == 32) return launch_tc<32, 32>(mx, mw, p, cfg.smem_bytes, st);
+  set_error("conv2d_tc: no kernel instance for BLOCK_N=%d CK=%d", cfg.block_n, cfg.ck);
+  return 1;
+}

@@ -1,0 +1,172 @@
+// PWC-Net cost volume (81 displacements, mean over channels), shared-memory tiled.
+//
+// Replaces the three cupy launches + two zero-padded NHWC temporaries of the reference
+// (external/pwcnet/correlation/correlation.py:8-103, 280-330), the LeakyReLU that follows it
+// (models/alignment/pwcnet.py:161,169) and -- when a flow is given -- `backwarp` of the second feature map
+// (pwcnet.py:16-38), which is fused into the staging of the f2 halo tile so the warped map never touches HBM.
+//
+// Work decomposition: one CTA = one pair x one 8x16 output tile.  288 threads = 9 (dy) x 8 (rows) x 4 (strips
+// of 4 pixels); a thread owns 4 pixels x 9 dx = 36 accumulators for its dy.  Channels are walked in chunks
+// of 32 staged in smem as [pixel][32] fp32; inside a chunk each lane walks the 8 float4 groups in a rotated
+// order ((j + lane) & 7) so that the 8 lanes of an LDS.128 phase hit 8 distinct 16-byte bank groups.
+#include "common.cuh"
+
+namespace dbsr {
+
+constexpr int CT_H = 8, CT_W = 16, C_CH = 32;
+constexpr int HALO_H = CT_H + 8, HALO_W = CT_W + 8;
+constexpr int CORR_THREADS = 288;
+constexpr int CORR_SMEM = (HALO_H * HALO_W + CT_H * CT_W) * C_CH * (int)sizeof(float);
+
+struct CorrParams {
+  View f1, f2, flow, out;
+  float flow_scale;
+  int group, act;
+  int tiles_x;
+};
+
+__global__ void __launch_bounds__(CORR_THREADS) corr81_kernel(const CorrParams p) {
+  extern __shared__ __align__(16) float smem[];
+  float* f2_s = smem;                                // [HALO_H*HALO_W][32]
+  float* f1_s = smem + HALO_H * HALO_W * C_CH;       // [CT_H*CT_W][32]
+
+  const int t = threadIdx.x;
+  const int lane = t & 31;
+  const int strip = t & 3, row = (t >> 2) & 7, dy = t >> 5;
+  const int pair = blockIdx.y;
+  const int ty0 = (blockIdx.x / p.tiles_x) * CT_H, tx0 = (blockIdx.x % p.tiles_x) * CT_W;
+  const int H = p.f1.h, W = p.f1.w, C = p.f1.c;
+  int i1 = pair, i2 = pair;
+  if (p.group > 0) {
+    const int b = pair / p.group;
+    i1 = b * (p.group + 1);
+    i2 = i1 + 1 + (pair - b * p.group);
+  }
+  const long long base1 = (long long)i1 * H * W, base2 = (long long)i2 * H * W, basef = (long long)pair * H * W;
+  const bool warp2 = p.flow.data != nullptr;
+  const float sxw = warp2 ? p.flow_scale * (float)W / (float)(W - 1) : 0.0f;  // pwcnet.py:28 + linspace grid :20
+  const float syh = warp2 ? p.flow_scale * (float)H / (float)(H - 1) : 0.0f;
+
+  float acc[4][9];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int d = 0; d < 9; ++d) acc[i][d] = 0.0f;
+
+  for (int c0 = 0; c0 < C; c0 += C_CH) {
+    // ---- stage f1 tile
+    for (int e = t; e < CT_H * CT_W * C_CH; e += CORR_THREADS) {
+      const int ch = e & (C_CH - 1), pix = e >> 5;
+      const int y = ty0 + pix / CT_W, x = tx0 + pix % CT_W;
+      float v = 0.0f;
+      if (y < H && x < W && c0 + ch < C) v = view_ld(p.f1, base1 + (long long)y * W + x, c0 + ch);
+      f1_s[e] = v;
+    }
+    // ---- stage f2 halo tile (optionally backwarped)
+    for (int e = t; e < HALO_H * HALO_W * C_CH; e += CORR_THREADS) {
+      const int ch = e & (C_CH - 1), pix = e >> 5;
+      const int y = ty0 - 4 + pix / HALO_W, x = tx0 - 4 + pix % HALO_W;
+      float v = 0.0f;
+      if (y >= 0 && y < H && x >= 0 && x < W && c0 + ch < C) {
+        if (!warp2) {
+          v = view_ld(p.f2, base2 + (long long)y * W + x, c0 + ch);
+        } else {
+          const long long fp = basef + (long long)y * W + x;
+          const float u = (float)x + view_ld(p.flow, fp, 0) * sxw;
+          const float w = (float)y + view_ld(p.flow, fp, 1) * syh;
+          const float fu = floorf(u), fv = floorf(w);
+          const float ax = u - fu, ay = w - fv;
+          const int xa = (int)fu, ya = (int)fv;
+          float s = 0.0f, m = 0.0f;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const int xx = xa + (k & 1), yy = ya + (k >> 1);
+            const float wt = ((k & 1) ? ax : 1.0f - ax) * ((k >> 1) ? ay : 1.0f - ay);
+            if (xx >= 0 && xx < W && yy >= 0 && yy < H) {
+              s = fmaf(view_ld(p.f2, base2 + (long long)yy * W + xx, c0 + ch), wt, s);
+              m += wt;
+            }
+          }
+          v = (m > 0.999f) ? s : 0.0f;  // pwcnet.py:34-38
+        }
+      }
+      f2_s[e] = v;
+    }
+    __syncthreads();
+
+    // ---- accumulate
+#pragma unroll 2
+    for (int j = 0; j < 8; ++j) {
+      const int jj = ((j + lane) & 7) * 4;
+      float4 a[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        a[i] = *reinterpret_cast<const float4*>(&f1_s[(row * CT_W + strip * 4 + i) * C_CH + jj]);
+#pragma unroll
+      for (int k = 0; k < 12; ++k) {
+        const float4 b = *reinterpret_cast<const float4*>(&f2_s[((row + dy) * HALO_W + strip * 4 + k) * C_CH + jj]);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int dx = k - i;
+          if (dx >= 0 && dx <= 8) {
+            float s = acc[i][dx];
+            s = fmaf(a[i].x, b.x, s); s = fmaf(a[i].y, b.y, s); s = fmaf(a[i].z, b.z, s); s = fmaf(a[i].w, b.w, s);
+            acc[i][dx] = s;
+          }
+        }
+      }
+    }
+    __syncthreads();
+  }
+
+  // ---- epilogue: scale, activation, transpose through smem for coalesced 81-channel rows
+  float* out_s = smem;  // [128][81]
+  const float invC = 1.0f / (float)C;
+  (void)invC;
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int d = 0; d < 9; ++d)
+      out_s[(row * CT_W + strip * 4 + i) * 81 + dy * 9 + d] = apply_act(acc[i][d] / (float)C, p.act);
+  __syncthreads();
+  for (int e = t; e < CT_H * CT_W * 81; e += CORR_THREADS) {
+    const int pix = e / 81, ch = e - pix * 81;
+    const int y = ty0 + pix / CT_W, x = tx0 + pix % CT_W;
+    if (y < H && x < W) view_st(p.out, (long long)pair * H * W + (long long)y * W + x, ch, out_s[e]);
+  }
+}
+
+}  // namespace dbsr
+
+using namespace dbsr;
+
+extern "C" int dbsr_corr81(const dbsr_nhwc_t* f1, const dbsr_nhwc_t* f2, const dbsr_nhwc_t* flow, float flow_scale,
+                           const dbsr_nhwc_t* out, int32_t pairs, int32_t group, int32_t act, void* stream) {
+  DBSR_REQUIRE(view_ok(f1) && view_ok(f2) && view_ok(out), "corr81: bad views");
+  DBSR_REQUIRE(f1->h == f2->h && f1->w == f2->w && f1->c == f2->c && out->h == f1->h && out->w == f1->w &&
+                   out->c == 81 && out->n == pairs, "corr81: geometry mismatch");
+  const bool has_flow = flow && flow->data;
+  if (has_flow) {
+    DBSR_REQUIRE(view_ok(flow) && flow->n == pairs && flow->h == f1->h && flow->w == f1->w && flow->c == 2,
+                 "corr81: flow geometry mismatch");
+    DBSR_REQUIRE(f1->h > 1 && f1->w > 1, "corr81: backwarp needs maps larger than 1x1 (reference divides by W-1)");
+  }
+  if (group > 0)
+    DBSR_REQUIRE(pairs % group == 0 && f1->n >= (pairs / group) * (group + 1) && f2->n >= (pairs / group) * (group + 1),
+                 "corr81: pair->image mapping out of range");
+  else
+    DBSR_REQUIRE(f1->n >= pairs && f2->n >= pairs, "corr81: not enough images");
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(corr81_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CORR_SMEM);
+    DBSR_REQUIRE(e == cudaSuccess, "corr81: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
+    attr_set = true;
+  }
+  CorrParams p;
+  p.f1 = make_view(f1); p.f2 = make_view(f2); p.flow = make_view(has_flow ? flow : nullptr); p.out = make_view(out);
+  p.flow_scale = flow_scale; p.group = group; p.act = act;
+  p.tiles_x = ceil_div(f1->w, CT_W);
+  dim3 grid(p.tiles_x * ceil_div(f1->h, CT_H), pairs);
+  corr81_kernel<<<grid, CORR_THREADS, CORR_SMEM, (cudaStream_t)stream>>>(p);
+  return check_launch("corr81");
+}

@@ -1,0 +1,441 @@
+// Error plumbing, probes, layout converters and the small HBM-bound kernels of the DBSR forward path
+// (burst preparation, transposed conv, flow head, offsets modulo, weight-predictor input, blur, predictor).
+#include "common.cuh"
+
+#include <string.h>
+
+namespace dbsr {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int check_launch(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_error("%s: CUDA launch failed: %s", what, cudaGetErrorString(e));
+    return 2;
+  }
+  return 0;
+}
+
+// -------------------------------------------------------------------------------------------------------
+// NCHW fp32 <-> NHWC view.  Tiled transpose through shared memory so both sides stay coalesced.
+// -------------------------------------------------------------------------------------------------------
+__global__ void nchw_to_nhwc_kernel(const float* __restrict__ src, View dst) {
+  __shared__ float tile[32][33];
+  const int HW = dst.h * dst.w;
+  const int n = blockIdx.z;
+  const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int c = c0 + i, p = p0 + threadIdx.x;
+    tile[i][threadIdx.x] = (c < dst.c && p < HW) ? __ldg(src + ((long long)n * dst.c + c) * HW + p) : 0.0f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int p = p0 + i, c = c0 + threadIdx.x;
+    if (c < dst.c && p < HW) view_st(dst, (long long)n * HW + p, c, tile[threadIdx.x][i]);
+  }
+}
+
+__global__ void nhwc_to_nchw_kernel(View src, float* __restrict__ dst) {
+  __shared__ float tile[32][33];
+  const int HW = src.h * src.w;
+  const int n = blockIdx.z;
+  const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int p = p0 + i, c = c0 + threadIdx.x;
+    tile[i][threadIdx.x] = (c < src.c && p < HW) ? view_ld(src, (long long)n * HW + p, c) : 0.0f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int c = c0 + i, p = p0 + threadIdx.x;
+    if (c < src.c && p < HW) dst[((long long)n * src.c + c) * HW + p] = tile[threadIdx.x][i];
+  }
+}
+
+__global__ void copy_channels_kernel(View src, View dst, int group, int src_group, int src_first) {
+  const long long total = (long long)dst.n * dst.h * dst.w * dst.c;
+  const int HW = dst.h * dst.w;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % dst.c);
+    const long long pix = i / dst.c;
+    const int n = (int)(pix / HW);
+    const int rem = (int)(pix - (long long)n * HW);
+    const int sn = group > 0 ? (n / group) * src_group + src_first : n;
+    view_st(dst, pix, c, view_ld(src, (long long)sn * HW + rem, c));
+  }
+}
+
+// -------------------------------------------------------------------------------------------------------
+// Burst preparation.  One thread per output pixel of either destination.
+//   enc_in: channels-last copy of the packed RAW frame (zero-padded channels)
+//   pwc_in: RGGB->RGB (encoders.py:52) then bilinear resize to (Hp, Wp), align_corners=False
+//           (pwcnet.py:266-271): src = (dst + 0.5) * in/out - 0.5, clamped at 0, neighbour clamped.
+// -------------------------------------------------------------------------------------------------------
+__global__ void prep_burst_kernel(const float* __restrict__ burst, int H, int W, View enc_in, View pwc_in) {
+  const int HW = H * W;
+  const long long n_enc = (long long)enc_in.n * HW;
+  const long long n_pwc = (long long)pwc_in.n * pwc_in.h * pwc_in.w;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_enc + n_pwc;
+       i += (long long)gridDim.x * blockDim.x) {
+    if (i < n_enc) {
+      const int f = (int)(i / HW);
+      const int rem = (int)(i - (long long)f * HW);
+      const float* b = burst + (long long)f * 4 * HW + rem;
+      for (int c = 0; c < enc_in.c; ++c) view_st(enc_in, i, c, c < 4 ? __ldg(b + (long long)c * HW) : 0.0f);
+    } else {
+      const long long j = i - n_enc;
+      const int Hp = pwc_in.h, Wp = pwc_in.w;
+      const int f = (int)(j / ((long long)Hp * Wp));
+      const int rem = (int)(j - (long long)f * Hp * Wp);
+      const int oy = rem / Wp, ox = rem - oy * Wp;
+      const float sy = (float)H / (float)Hp, sx = (float)W / (float)Wp;
+      float fy = fmaxf((oy + 0.5f) * sy - 0.5f, 0.0f);
+      float fx = fmaxf((ox + 0.5f) * sx - 0.5f, 0.0f);
+      int y0 = min((int)fy, H - 1), x0 = min((int)fx, W - 1);
+      const int y1 = min(y0 + 1, H - 1), x1 = min(x0 + 1, W - 1);
+      const float wy = fy - (float)y0, wx = fx - (float)x0;
+      const float* b = burst + (long long)f * 4 * HW;
+      float rgb[3];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        float v[4];
+        const int ys[2] = {y0, y1}, xs[2] = {x0, x1};
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          const int pix = ys[t >> 1] * W + xs[t & 1];
+          if (c == 0) v[t] = __ldg(b + pix);
+          else if (c == 1) v[t] = (__ldg(b + HW + pix) + __ldg(b + 2 * HW + pix)) / 2.0f;
+          else v[t] = __ldg(b + 3 * HW + pix);
+        }
+        // same association as ATen's upsample_bilinear2d: rows first (wy), then columns (wx)
+        const float top = v[0] * (1.0f - wx) + v[1] * wx;
+        const float bot = v[2] * (1.0f - wx) + v[3] * wx;
+        rgb[c] = top * (1.0f - wy) + bot * wy;
+      }
+      for (int c = 0; c < pwc_in.c; ++c) view_st(pwc_in, j, c, c < 3 ? rgb[c] : 0.0f);
+    }
+  }
+}
+
+// -------------------------------------------------------------------------------------------------------
+// ConvTranspose2d(k=4, s=2, p=1), Cout = 2 (pwcnet.py:119-120).  One warp per output pixel; lanes stride
+// over input channels (coalesced NHWC reads), 2x2 valid taps per output parity, shuffle reduction.
+//   out[oy,ox,oc] = b[oc] + sum_{ic} sum_{ky = (oy+1)&1 (+2)} sum_{kx} x[(oy+1-ky)/2, (ox+1-kx)/2, ic] w[ky][kx][oc][ic]
+// -------------------------------------------------------------------------------------------------------
+__global__ void deconv4x4s2_kernel(View x, const float* __restrict__ w, const float* __restrict__ bias, View y,
+                                   View y2) {
+  const int lane = threadIdx.x & 31;
+  const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int Ho = 2 * x.h, Wo = 2 * x.w;
+  const long long total = (long long)x.n * Ho * Wo;
+  if (warp >= total) return;
+  const int n = (int)(warp / ((long long)Ho * Wo));
+  const int rem = (int)(warp - (long long)n * Ho * Wo);
+  const int oy = rem / Wo, ox = rem - oy * Wo;
+  float acc0 = 0.0f, acc1 = 0.0f;
+  const int Cin = x.c;
+#pragma unroll
+  for (int a = 0; a < 2; ++a) {
+    const int ky = ((oy + 1) & 1) + 2 * a;
+    const int iy2 = oy + 1 - ky;
+    if (iy2 < 0) continue;
+    const int iy = iy2 >> 1;
+    if (iy >= x.h) continue;
+#pragma unroll
+    for (int b = 0; b < 2; ++b) {
+      const int kx = ((ox + 1) & 1) + 2 * b;
+      const int ix2 = ox + 1 - kx;
+      if (ix2 < 0) continue;
+      const int ix = ix2 >> 1;
+      if (ix >= x.w) continue;
+      const long long pix = ((long long)n * x.h + iy) * x.w + ix;
+      const float* w0 = w + ((ky * 4 + kx) * 2 + 0) * (long long)Cin;
+      const float* w1 = w0 + Cin;
+      for (int ic = lane; ic < Cin; ic += 32) {
+        const float v = view_ld(x, pix, ic);
+        acc0 = fmaf(v, __ldg(w0 + ic), acc0);
+        acc1 = fmaf(v, __ldg(w1 + ic), acc1);
+      }
+    }
+  }
+#pragma unroll
+  for (int s = 16; s > 0; s >>= 1) {
+    acc0 += __shfl_xor_sync(0xffffffffu, acc0, s);
+    acc1 += __shfl_xor_sync(0xffffffffu, acc1, s);
+  }
+  if (lane == 0) {
+    acc0 += bias[0];
+    acc1 += bias[1];
+    view_st(y, warp, 0, acc0);
+    view_st(y, warp, 1, acc1);
+    if (y2.data) {
+      view_st(y2, warp, 0, acc0);
+      view_st(y2, warp, 1, acc1);
+    }
+  }
+}
+
+// -------------------------------------------------------------------------------------------------------
+// Flow head (pwcnet.py:274-279): bilinear resize of the quarter-resolution flow to (H, W) with
+// align_corners=False, x20, x(W/Wp, H/Hp).  Output NCHW fp32 (the public `offsets`).
+// -------------------------------------------------------------------------------------------------------
+__global__ void flow_head_kernel(View f4, float* __restrict__ offsets, int H, int W, float mulx, float muly) {
+  const long long total = (long long)f4.n * H * W;
+  const int h4 = f4.h, w4 = f4.w;
+  const float sy = (float)h4 / (float)H, sx = (float)w4 / (float)W;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int n = (int)(i / ((long long)H * W));
+    const int rem = (int)(i - (long long)n * H * W);
+    const int oy = rem / W, ox = rem - oy * W;
+    const float fy = fmaxf((oy + 0.5f) * sy - 0.5f, 0.0f);
+    const float fx = fmaxf((ox + 0.5f) * sx - 0.5f, 0.0f);
+    const int y0 = min((int)fy, h4 - 1), x0 = min((int)fx, w4 - 1);
+    const int y1 = min(y0 + 1, h4 - 1), x1 = min(x0 + 1, w4 - 1);
+    const float wy = fy - (float)y0, wx = fx - (float)x0;
+    const long long base = (long long)n * h4 * w4;
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      const float v00 = view_ld(f4, base + y0 * w4 + x0, c), v01 = view_ld(f4, base + y0 * w4 + x1, c);
+      const float v10 = view_ld(f4, base + y1 * w4 + x0, c), v11 = view_ld(f4, base + y1 * w4 + x1, c);
+      const float top = v00 * (1.0f - wx) + v01 * wx;
+      const float bot = v10 * (1.0f - wx) + v11 * wx;
+      const float v = 20.0f * (top * (1.0f - wy) + bot * wy);
+      offsets[((long long)n * 2 + c) * H * W + rem] = v * (c == 0 ? mulx : muly);
+    }
+  }
+}
+
+// merging.py:91-105: zeros for the reference frame, floor-mod for the others
+__global__ void offsets_mod_kernel(const float* __restrict__ offsets, View out, int frames, float modulo) {
+  const int HW = out.h * out.w;
+  const long long total = (long long)out.n * HW;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int img = (int)(i / HW);
+    const int rem = (int)(i - (long long)img * HW);
+    const int b = img / frames, f = img - b * frames;
+    float v[2] = {0.0f, 0.0f};
+    if (f > 0) {
+      const long long p = (long long)b * (frames - 1) + (f - 1);
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        const float a = __ldg(offsets + (p * 2 + c) * HW + rem);
+        float r = a;
+        if (modulo > 0.0f) {
+          r = fmodf(a, modulo);               // torch.remainder: fmod, then fix the sign
+          if (r != 0.0f && r < 0.0f) r += modulo;
+        }
+        v[c] = r;
+      }
+    }
+    for (int c = 0; c < out.c; ++c) view_st(out, i, c, c < 2 ? v[c] : 0.0f);
+  }
+}
+
+// merging.py:79-89: [base | diff] channels of the weight-predictor input
+__global__ void build_wp_input_kernel(View proj, View wp_in, int frames) {
+  const int C = proj.c;
+  const int HW = proj.h * proj.w;
+  const long long total = (long long)proj.n * HW * C;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    const long long pix = i / C;
+    const int img = (int)(pix / HW);
+    const int rem = (int)(pix - (long long)img * HW);
+    const int b = img / frames;
+    const float base = view_ld(proj, (long long)b * frames * HW + rem, c);
+    const float mine = view_ld(proj, pix, c);
+    view_st(wp_in, pix, c, base);
+    view_st(wp_in, pix, C + c, mine - base);
+  }
+}
+
+// upsampling.py:59-65: per-channel 3x3 blur with zero padding
+__global__ void blur3x3_kernel(View x, View y, float k0, float k1, float k2, float k3, float k4, float k5, float k6,
+                               float k7, float k8) {
+  const float k[9] = {k0, k1, k2, k3, k4, k5, k6, k7, k8};
+  const int C = x.c;
+  const long long total = (long long)x.n * x.h * x.w * C;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    const long long pix = i / C;
+    const int n = (int)(pix / ((long long)x.h * x.w));
+    const int rem = (int)(pix - (long long)n * x.h * x.w);
+    const int py = rem / x.w, px = rem - py * x.w;
+    float acc = 0.0f;
+#pragma unroll
+    for (int dy = -1; dy <= 1; ++dy)
+#pragma unroll
+      for (int dx = -1; dx <= 1; ++dx) {
+        const int yy = py + dy, xx = px + dx;
+        if (yy >= 0 && yy < x.h && xx >= 0 && xx < x.w)
+          acc = fmaf(view_ld(x, ((long long)n * x.h + yy) * x.w + xx, c), k[(dy + 1) * 3 + (dx + 1)], acc);
+      }
+    view_st(y, pix, c, acc);
+  }
+}
+
+// decoders.py:52,60: 1x1 conv to `cout` (<= 4) channels + ReLU, NCHW fp32 output
+__global__ void predictor_kernel(View x, const float* __restrict__ w, const float* __restrict__ bias, int cout,
+                                 float* __restrict__ pred) {
+  extern __shared__ float ws[];  // [cout][C] + [cout]
+  const int C = x.c;
+  for (int i = threadIdx.x; i < cout * C; i += blockDim.x) ws[i] = w[i];
+  for (int i = threadIdx.x; i < cout; i += blockDim.x) ws[cout * C + i] = bias ? bias[i] : 0.0f;
+  __syncthreads();
+  const int HW = x.h * x.w;
+  const long long total = (long long)x.n * HW;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int c = 0; c < C; ++c) {
+      const float v = view_ld(x, i, c);
+#pragma unroll
+      for (int o = 0; o < 4; ++o)
+        if (o < cout) acc[o] = fmaf(v, ws[o * C + c], acc[o]);
+    }
+    const int n = (int)(i / HW);
+    const int rem = (int)(i - (long long)n * HW);
+#pragma unroll
+    for (int o = 0; o < 4; ++o)
+      if (o < cout) pred[((long long)n * cout + o) * HW + rem] = fmaxf(acc[o] + ws[cout * C + o], 0.0f);
+  }
+}
+
+static inline int grid_for(long long total, int block) {
+  long long g = (total + block - 1) / block;
+  const long long cap = 148LL * 16;
+  return (int)(g < 1 ? 1 : (g > cap ? cap : g));
+}
+
+}  // namespace dbsr
+
+using namespace dbsr;
+
+extern "C" int dbsr_version(void) { return DBSR_B200_VERSION; }
+extern "C" const char* dbsr_last_error(void) { return g_err; }
+
+extern "C" int dbsr_device_check(int device) {
+  cudaDeviceProp prop;
+  cudaError_t e = cudaGetDeviceProperties(&prop, device);
+  if (e != cudaSuccess) {
+    set_error("device_check: cudaGetDeviceProperties(%d) failed: %s", device, cudaGetErrorString(e));
+    return 2;
+  }
+  DBSR_REQUIRE(prop.major == 10, "device_check: device %d is sm_%d%d; libdbsr_b200 runs on sm_100 (B200) only", device,
+               prop.major, prop.minor);
+  return 0;
+}
+
+extern "C" int dbsr_nchw_to_nhwc(const float* src, const dbsr_nhwc_t* dst, void* stream) {
+  DBSR_REQUIRE(src && view_ok(dst), "nchw_to_nhwc: bad arguments");
+  dim3 grid(ceil_div((long long)dst->h * dst->w, 32), ceil_div(dst->c, 32), dst->n), block(32, 8);
+  nchw_to_nhwc_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(src, make_view(dst));
+  return check_launch("nchw_to_nhwc");
+}
+
+extern "C" int dbsr_nhwc_to_nchw(const dbsr_nhwc_t* src, float* dst, void* stream) {
+  DBSR_REQUIRE(dst && view_ok(src), "nhwc_to_nchw: bad arguments");
+  dim3 grid(ceil_div((long long)src->h * src->w, 32), ceil_div(src->c, 32), src->n), block(32, 8);
+  nhwc_to_nchw_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(make_view(src), dst);
+  return check_launch("nhwc_to_nchw");
+}
+
+extern "C" int dbsr_copy_channels(const dbsr_nhwc_t* src, const dbsr_nhwc_t* dst, int32_t group, int32_t src_group,
+                                  int32_t src_first, void* stream) {
+  DBSR_REQUIRE(view_ok(src) && view_ok(dst), "copy_channels: bad views");
+  DBSR_REQUIRE(src->h == dst->h && src->w == dst->w && src->c == dst->c, "copy_channels: geometry mismatch");
+  if (group > 0)
+    DBSR_REQUIRE(dst->n % group == 0 && (dst->n / group - 1) * src_group + src_first < src->n,
+                 "copy_channels: group mapping out of range");
+  else
+    DBSR_REQUIRE(src->n == dst->n, "copy_channels: image count mismatch");
+  const long long total = (long long)dst->n * dst->h * dst->w * dst->c;
+  copy_channels_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(make_view(src), make_view(dst), group,
+                                                                                src_group, src_first);
+  return check_launch("copy_channels");
+}
+
+extern "C" int dbsr_prep_burst(const float* burst, int32_t frames, int32_t H, int32_t W, const dbsr_nhwc_t* enc_in,
+                               const dbsr_nhwc_t* pwc_in, void* stream) {
+  DBSR_REQUIRE(burst && view_ok(enc_in) && view_ok(pwc_in), "prep_burst: bad arguments");
+  DBSR_REQUIRE(enc_in->n == frames && pwc_in->n == frames && enc_in->h == H && enc_in->w == W && enc_in->c >= 4 &&
+                   pwc_in->c >= 3, "prep_burst: geometry mismatch");
+  const long long total = (long long)frames * H * W + (long long)frames * pwc_in->h * pwc_in->w;
+  prep_burst_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(burst, H, W, make_view(enc_in),
+                                                                             make_view(pwc_in));
+  return check_launch("prep_burst");
+}
+
+extern "C" int dbsr_deconv4x4s2(const dbsr_nhwc_t* x, const float* w, const float* bias, const dbsr_nhwc_t* y,
+                                const dbsr_nhwc_t* y2, void* stream) {
+  DBSR_REQUIRE(view_ok(x) && view_ok(y) && w && bias, "deconv4x4s2: bad arguments");
+  DBSR_REQUIRE(y->n == x->n && y->h == 2 * x->h && y->w == 2 * x->w && y->c == 2, "deconv4x4s2: output geometry");
+  const bool has2 = y2 && y2->data;
+  if (has2) DBSR_REQUIRE(view_ok(y2) && y2->n == y->n && y2->h == y->h && y2->w == y->w && y2->c == 2,
+                         "deconv4x4s2: second output geometry");
+  const long long warps = (long long)x->n * y->h * y->w;
+  const int block = 256;
+  const long long blocks = (warps * 32 + block - 1) / block;
+  deconv4x4s2_kernel<<<(unsigned)blocks, block, 0, (cudaStream_t)stream>>>(make_view(x), w, bias, make_view(y),
+                                                                            make_view(has2 ? y2 : nullptr));
+  return check_launch("deconv4x4s2");
+}
+
+extern "C" int dbsr_flow_head(const dbsr_nhwc_t* flow4, float* offsets, int32_t H, int32_t W, int32_t Hp, int32_t Wp,
+                              void* stream) {
+  DBSR_REQUIRE(view_ok(flow4) && offsets && flow4->c == 2, "flow_head: bad arguments");
+  const long long total = (long long)flow4->n * H * W;
+  flow_head_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(make_view(flow4), offsets, H, W,
+                                                                            (float)W / (float)Wp, (float)H / (float)Hp);
+  return check_launch("flow_head");
+}
+
+extern "C" int dbsr_offsets_mod(const float* offsets, const dbsr_nhwc_t* out, int32_t bursts, int32_t frames,
+                                float modulo, void* stream) {
+  DBSR_REQUIRE(offsets && view_ok(out) && out->n == bursts * frames && out->c >= 2 && frames >= 2,
+               "offsets_mod: bad arguments");
+  const long long total = (long long)out->n * out->h * out->w;
+  offsets_mod_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(offsets, make_view(out), frames, modulo);
+  return check_launch("offsets_mod");
+}
+
+extern "C" int dbsr_build_wp_input(const dbsr_nhwc_t* proj, const dbsr_nhwc_t* wp_in, int32_t frames, void* stream) {
+  DBSR_REQUIRE(view_ok(proj) && view_ok(wp_in) && proj->n == wp_in->n && proj->h == wp_in->h &&
+                   proj->w == wp_in->w && wp_in->c >= 2 * proj->c && proj->n % frames == 0,
+               "build_wp_input: bad arguments");
+  const long long total = (long long)proj->n * proj->h * proj->w * proj->c;
+  build_wp_input_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(make_view(proj), make_view(wp_in),
+                                                                                 frames);
+  return check_launch("build_wp_input");
+}
+
+extern "C" int dbsr_blur3x3(const dbsr_nhwc_t* x, const dbsr_nhwc_t* y, const float* k9, void* stream) {
+  DBSR_REQUIRE(view_ok(x) && view_ok(y) && k9 && x->n == y->n && x->h == y->h && x->w == y->w && x->c == y->c,
+               "blur3x3: bad arguments");
+  const long long total = (long long)x->n * x->h * x->w * x->c;
+  blur3x3_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(make_view(x), make_view(y), k9[0], k9[1],
+                                                                          k9[2], k9[3], k9[4], k9[5], k9[6], k9[7],
+                                                                          k9[8]);
+  return check_launch("blur3x3");
+}
+
+extern "C" int dbsr_predictor(const dbsr_nhwc_t* x, const float* w, const float* bias, int32_t cout, float* pred,
+                              void* stream) {
+  DBSR_REQUIRE(view_ok(x) && w && pred && cout >= 1 && cout <= 4, "predictor: bad arguments");
+  const long long total = (long long)x->n * x->h * x->w;
+  const size_t smem = (size_t)(cout * x->c + cout) * sizeof(float);
+  predictor_kernel<<<grid_for(total, 256), 256, smem, (cudaStream_t)stream>>>(make_view(x), w, bias, cout, pred);
+  return check_launch("predictor");
+}

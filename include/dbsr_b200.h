@@ -1,0 +1,155 @@
+/*
+ * dbsr_b200.h -- C ABI of libdbsr_b200.so: hand-written sm_100a kernels for the DBSR burst forward pass.
+ *
+ * Drop-in boundary.  The reference (Tony-Tseng/deep-rawburst-sr) has no FFI of its own: its only native
+ * code are CUDA-C strings launched through cupy with raw `data_ptr()` integers
+ * (external/pwcnet/correlation/correlation.py:293-322).  This header is the compiled replacement for that
+ * seam and for every library op on the hot path `DBSRNet.forward` (models/dbsr/dbsrnet.py:33-38).  Host
+ * code (Python, `deep_rawburst_sr_b200/`) allocates all device memory with torch and passes raw pointers,
+ * sizes and the current `cudaStream_t`; nothing in here allocates device memory or synchronises.
+ *
+ * Conventions
+ *  - Every entry point returns 0 on success, non-zero on error; `dbsr_last_error()` returns the message of
+ *    the last failing call on the calling thread.
+ *  - Activations inside the path are NHWC ("channels-last") views described by `dbsr_nhwc_t`; a view may
+ *    be a channel slice [c_off, c_off + c) of a wider buffer (c_pitch channels per pixel).  That is how
+ *    the PWC-Net dense concatenations (models/alignment/pwcnet.py:171-177) are written in place.
+ *  - The module seams of the reference are NCHW fp32; `dbsr_nchw_to_nhwc` / `dbsr_nhwc_to_nchw` convert.
+ *  - `stream` is a `cudaStream_t` passed as `void*`.
+ *  - No entry point falls back to the CPU: on a device that is not sm_100 `dbsr_device_check` fails and
+ *    the Python layer refuses to run.
+ */
+#ifndef DBSR_B200_H_
+#define DBSR_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DBSR_B200_VERSION 100
+
+enum { DBSR_F32 = 0, DBSR_BF16 = 1 };
+enum { DBSR_ACT_NONE = 0, DBSR_ACT_RELU = 1, DBSR_ACT_LRELU = 2 /* slope 0.1 */ };
+
+/* NHWC activation view (element (n,y,x,ch) at data[((n*h + y)*w + x)*c_pitch + c_off + ch]). */
+typedef struct dbsr_nhwc {
+  void*   data;
+  int32_t n, h, w;
+  int32_t c;        /* channels in the view                          */
+  int32_t c_off;    /* first channel of the view inside a pixel      */
+  int32_t c_pitch;  /* channels per pixel of the underlying buffer   */
+  int32_t dtype;    /* DBSR_F32 | DBSR_BF16                          */
+} dbsr_nhwc_t;
+
+/* -------------------------------------------------------------------------------------------------- */
+/* probes                                                                                             */
+/* -------------------------------------------------------------------------------------------------- */
+int         dbsr_version(void);
+const char* dbsr_last_error(void);
+/* 0 iff `device` is a compute-capability 10.x part (B200); anything else is refused (no fallback).   */
+int         dbsr_device_check(int device);
+
+/* -------------------------------------------------------------------------------------------------- */
+/* layout converters (module seams; NCHW fp32 <-> NHWC view)                                          */
+/* -------------------------------------------------------------------------------------------------- */
+int dbsr_nchw_to_nhwc(const float* src, const dbsr_nhwc_t* dst, void* stream);
+int dbsr_nhwc_to_nchw(const dbsr_nhwc_t* src, float* dst, void* stream);
+/* dst[p] = src[map(p)]: map(p) = p if group == 0, else (p / group) * src_group  (reference frame of the
+ * burst replicated over its pairs; replaces `x_rgb[:, :1].repeat(...)`, models/dbsr/encoders.py:53).  */
+int dbsr_copy_channels(const dbsr_nhwc_t* src, const dbsr_nhwc_t* dst, int32_t group, int32_t src_group,
+                       int32_t src_first, void* stream);
+
+/* -------------------------------------------------------------------------------------------------- */
+/* burst preparation: replaces encoders.py:52 (RGGB->RGB) + pwcnet.py:262-271 (bilinear resize to x64) */
+/*   burst  [B*N, 4, H, W] fp32 NCHW                                                                  */
+/*   enc_in [B*N, H, W, >=4]  packed RAW, channels-last, extra channels zero-filled                   */
+/*   pwc_in [B*N, Hp, Wp, >=3] RGB resized to (Hp, Wp), extra channels zero-filled                    */
+/* -------------------------------------------------------------------------------------------------- */
+int dbsr_prep_burst(const float* burst, int32_t frames, int32_t H, int32_t W, const dbsr_nhwc_t* enc_in,
+                    const dbsr_nhwc_t* pwc_in, void* stream);
+
+/* -------------------------------------------------------------------------------------------------- */
+/* convolution, CUDA-core path (exact fp32 accumulate; any Cin/Cout/stride/dilation)                   */
+/* replaces nn.Conv2d + activation + residual of models/layers/blocks.py:46-96 and pwcnet.py:49-204    */
+/*   w: fp32 [k*k][Cin][Cout]  (tap-major, Cout contiguous) -- see dbsr_pack_conv_weight_direct         */
+/*   y = act(conv(x) + bias (+ residual))                                                              */
+/*   shuffle_r > 1: output channel co = (c*r + i)*r + j is written to pixel (r*y+i, r*x+j), channel c   */
+/*   of the (r*H, r*W) output view (nn.PixelShuffle folded in, models/layers/upsampling.py:57).         */
+/* -------------------------------------------------------------------------------------------------- */
+typedef struct dbsr_conv {
+  dbsr_nhwc_t x, y;
+  dbsr_nhwc_t residual;      /* data == NULL: none; same geometry as y                              */
+  const void* w;             /* packed weights (layout depends on the entry point)                  */
+  const float* bias;         /* NULL: none                                                          */
+  int32_t ksize;             /* 1 or 3                                                              */
+  int32_t stride, dilation;  /* padding is dilation*(ksize-1)/2 ("same" for stride 1)               */
+  int32_t act;
+  int32_t shuffle_r;         /* 0/1: plain; 8: pixel-shuffle scatter                                */
+} dbsr_conv_t;
+int dbsr_conv2d_direct(const dbsr_conv_t* p, void* stream);
+
+/* tcgen05 / TMEM implicit-GEMM path (bf16 operands, fp32 accumulate in tensor memory).
+ *   x, y (and residual): bf16 NHWC; x.c and x.c_off multiples of 32 (pad with zero channels), stride 1.
+ *   w: bf16 [Cout_pad][k*k][Cin_pad] K-major, see dbsr_pack_conv_weight_tc; Cout_pad multiple of 16.
+ *   y may be fp32 (logits).  Returns non-zero for shapes it does not cover (caller must not fall back
+ *   silently; the Python engine decides per layer at plan time).                                      */
+int dbsr_conv2d_tc(const dbsr_conv_t* p, void* stream);
+/* smem bytes / tile shape chosen for a conv, for reporting */
+int dbsr_conv2d_tc_supported(const dbsr_conv_t* p);
+
+/* ConvTranspose2d(k=4, s=2, p=1), Cout = 2 (pwcnet.py:119-120 netUpflow / netUpfeat).
+ *   w: fp32 [4][4][2][Cin]; y, y2: [n, 2h, 2w, 2] views (y2 optional second destination, data NULL ok) */
+int dbsr_deconv4x4s2(const dbsr_nhwc_t* x, const float* w, const float* bias, const dbsr_nhwc_t* y,
+                     const dbsr_nhwc_t* y2, void* stream);
+
+/* -------------------------------------------------------------------------------------------------- */
+/* PWC-Net cost volume: replaces correlation.FunctionCorrelation (correlation.py:280-330, 3 launches +  */
+/* 2 padded temporaries), the LeakyReLU after it (pwcnet.py:161,169) and, when flow != NULL, backwarp   */
+/* (pwcnet.py:16-38) of the second feature map fused into the halo staging.                            */
+/*   out[p, 9*(dy+4)+(dx+4), y, x] = act( (1/C) sum_c f1[i1(p),c,y,x] * f2w[i2(p),c,y+dy,x+dx] )        */
+/*   pair -> image mapping: group == 0: i1 = i2 = p; else burst b = p / group, i1 = b*(group+1),        */
+/*   i2 = b*(group+1) + 1 + p % group  (frame 0 of each burst is the reference).                        */
+/*   flow: [pairs, h, w, 2] fp32 view or data NULL; flow_scale = fltBackwarp (pwcnet.py:121)            */
+/* -------------------------------------------------------------------------------------------------- */
+int dbsr_corr81(const dbsr_nhwc_t* f1, const dbsr_nhwc_t* f2, const dbsr_nhwc_t* flow, float flow_scale,
+                const dbsr_nhwc_t* out, int32_t pairs, int32_t group, int32_t act, void* stream);
+
+/* flow head: replaces pwcnet.py:274-279.  flow4 [P, h4, w4, 2] fp32 -> offsets [P, 2, H, W] fp32 NCHW  */
+/*   offsets = 20 * bilinear_resize(flow4 -> (H, W)) * (W/Wp, H/Hp)                                     */
+int dbsr_flow_head(const dbsr_nhwc_t* flow4, float* offsets, int32_t H, int32_t W, int32_t Hp, int32_t Wp,
+                   void* stream);
+
+/* -------------------------------------------------------------------------------------------------- */
+/* fusion                                                                                              */
+/* -------------------------------------------------------------------------------------------------- */
+/* warp (models/layers/warp.py:19-46): out[p] = bilinear(feat[img(p)], (x + fx, y + fy)), zeros outside.
+ *   offsets: [P, 2, H, W] fp32 NCHW; img(p) as in dbsr_corr81's i2 mapping.                            */
+int dbsr_warp(const dbsr_nhwc_t* feat, const float* offsets, const dbsr_nhwc_t* out, int32_t pairs,
+              int32_t group, void* stream);
+/* merging.py:91-105: [B*N, H, W, >=2] <- (frame 0: zeros; others: offsets mod 1.0, floor-mod)          */
+int dbsr_offsets_mod(const float* offsets, const dbsr_nhwc_t* out, int32_t bursts, int32_t frames,
+                     float modulo, void* stream);
+/* merging.py:79-89: wp_in[:, 0:C] = proj[b, 0]; wp_in[:, C:2C] = proj[b, n] - proj[b, 0]               */
+int dbsr_build_wp_input(const dbsr_nhwc_t* proj, const dbsr_nhwc_t* wp_in, int32_t frames, void* stream);
+/* merging.py:117-124 fused with the warp: fused[b] = sum_n softmax_n(logits[b,n]) * A[b,n] where
+ *   A[b,0] = feat[b*N], A[b,n>0] = bilinear(feat[b*N+n], (x,y) + offsets[b*(N-1)+n-1]) gathered on the fly
+ *   (offsets == NULL: `feat` already holds the aligned maps).  weights_out (optional, may be NULL):
+ *   [B, N, C, H, W] fp32 NCHW -- the reference's `fusion_weights`.                                     */
+int dbsr_softmax_wsum(const dbsr_nhwc_t* feat, const dbsr_nhwc_t* logits, const float* offsets,
+                      const dbsr_nhwc_t* fused, float* weights_out, int32_t frames, void* stream);
+
+/* -------------------------------------------------------------------------------------------------- */
+/* decoder tail                                                                                        */
+/* -------------------------------------------------------------------------------------------------- */
+/* per-channel 3x3 blur, zero padding (upsampling.py:59-65); k: 9 floats on the host                    */
+int dbsr_blur3x3(const dbsr_nhwc_t* x, const dbsr_nhwc_t* y, const float* k9, void* stream);
+/* predictor (decoders.py:52,60): pred[n, co, y, x] = relu(b[co] + sum_c w[co][c] x[n,y,x,c]), NCHW fp32 */
+int dbsr_predictor(const dbsr_nhwc_t* x, const float* w, const float* bias, int32_t cout, float* pred,
+                   void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DBSR_B200_H_ */
