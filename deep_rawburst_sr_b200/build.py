@@ -55,7 +55,7 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
             objs.append(obj)
             if verbose:
                 sys.stderr.write(log)
-    cmd = [nvcc, '-shared', '-o', LIB] + objs + ['-lcudart']
+    cmd = [nvcc, '-shared', '-o', LIB] + objs + ['-cudart', 'static']
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f'link failed:\n{r.stdout}\n{r.stderr}')
