@@ -1,0 +1,260 @@
+#!/usr/bin/env python
+"""Benchmark of the DBSR burst forward pass (BASELINE.json metric: bursts/sec, 14-frame, 4x SR).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+One step = one forward of a batch of synthetic bursts (BASELINE.json configs[1]: 32 bursts of 14x4x48x48 per GPU,
+bf16 tensor cores, random-init weights).  Bursts are independent, so ranks shard bursts with no data-path
+collective (weak scaling: the per-GPU batch is fixed); NCCL is used only for the barrier / max-over-ranks timing.
+Prints ONE JSON line (rank 0).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+FRAMES = 14
+CONV_GFLOP_PER_BURST = {48: 223.28, 80: 644.10}   # SURVEY.md App. B (2*MAC, all 134 conv calls as the reference runs them)
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--batch', type=int, default=32, help='bursts per GPU per step')
+    ap.add_argument('--size', type=int, default=48, help='packed RAW height = width')
+    ap.add_argument('--precision', default='bf16', choices=['bf16', 'fp32'])
+    ap.add_argument('--cpu-baseline-seconds', type=float, default=15.0)
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    return ap.parse_args()
+
+
+def peaks():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {'hbm_gbs': d['hbm_gbs'], 'tflops': d.get('bf16_tflops_sustained', d['bf16_tflops']), 'src': 'measured'}
+    return {'hbm_gbs': 6650.0, 'tflops': 1400.0, 'src': 'fallback'}
+
+
+class ClockSampler(threading.Thread):
+    """samples nvidia-smi SM clocks / throttle reasons during the timed region"""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.stop_flag = False
+        self.samples = []
+        self.reasons = set()
+        self.max_mhz = None
+
+    def run(self):
+        q = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+             'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(['nvidia-smi', f'--query-gpu={q}', '--format=csv,noheader,nounits', '-i', str(self.index)],
+                                     capture_output=True, text=True, timeout=5).stdout.strip().split('\n')[0]
+                f = [v.strip() for v in out.split(',')]
+                self.samples.append(float(f[0]))
+                self.max_mhz = float(f[1])
+                for n, v in zip(names, f[2:]):
+                    if v.lower().startswith('active'):
+                        self.reasons.add(n)
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        s = sorted(self.samples)
+        med = s[len(s) // 2] if s else None
+        return {'sm_mhz': med, 'sm_max_mhz': self.max_mhz, 'reasons': sorted(self.reasons), 'samples': len(s)}
+
+
+def cpu_reference_arm(args, rank):
+    """--impl reference: the reference algorithm on the host cores (oracle port of the Python reference: the
+    reference is a Python toolkit that cannot travel to the GPU box)."""
+    if rank != 0:
+        return
+    from oracle import dbsr_oracle as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sd = O.make_state_dict(0)
+    burst = O.make_burst(0, 1, FRAMES, args.size, args.size)
+    for _ in range(max(1, min(args.warmup, 2))):
+        O.dbsr_forward(burst, sd)
+    steps = max(1, min(args.steps, 10))
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        O.dbsr_forward(burst, sd)
+    dt = (time.perf_counter() - t0) / steps
+    val = 1.0 / dt
+    sample = f'1 burst of {FRAMES}x4x{args.size}x{args.size} per step, fp32, {steps} steps'
+    print(json.dumps({
+        'impl': 'reference', 'metric': 'bursts/sec (14-frame, 4x SR)', 'value': val, 'unit': 'bursts/s',
+        'n_gpus': args.gpus, 'steps': steps, 'warmup': args.warmup, 'ms_per_step': dt * 1e3, 'higher_is_better': True,
+        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': f'DBSRNet forward, bursts of {FRAMES}x4x{args.size}x{args.size} -> 3x{8 * args.size}x{8 * args.size}, random-init weights'},
+        'cpu_baseline': {'value': val, 'unit': 'bursts/s', 'cores': cores, 'kind': 'port', 'sample': sample},
+        'e2e': {'value': val, 'unit': 'bursts/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+    }))
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    if args.impl == 'reference':
+        cpu_reference_arm(args, rank)
+        return
+    import torch.distributed as dist
+    dev = torch.device('cuda', local_rank)
+    torch.cuda.set_device(dev)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+
+    from oracle import dbsr_oracle as O   # weight recipe only (random-init weights of the reference architecture)
+    from deep_rawburst_sr_b200.models.dbsr.dbsrnet import dbsrnet_default_synthetic
+    net = dbsrnet_default_synthetic()
+    net.load_state_dict(O.make_state_dict(0), strict=True)
+    net = net.to(dev).eval().set_precision(args.precision)
+    eng = net.engine(dev)
+
+    B, S = args.batch, args.size
+    gen = torch.Generator().manual_seed(1000 + rank)
+    host_in = torch.rand(B, FRAMES, 4, S, S, generator=gen).pin_memory()
+    dev_in = host_in.to(dev)
+    host_out = torch.empty(B, 3, 8 * S, 8 * S).pin_memory()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+        return ms
+
+    # ---- device-resident throughput ("value")
+    for _ in range(args.warmup):
+        net(dev_in)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    eng.launches = 0
+    eng.flops = {}
+    eng.timers = {}
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        pred, _aux = net(dev_in)
+    e1.record()
+    barrier()
+    ms_total = max_over_ranks(e0.elapsed_time(e1))
+    launches = eng.launches
+    fam = eng.timer_summary()
+    flops = dict(eng.flops)
+    eng.timers = None
+    value = world * B * args.steps / (ms_total / 1e3)
+
+    # ---- end to end through the public module with HOST buffers (H2D of the burst + D2H of pred inside the region)
+    for _ in range(2):
+        p, _ = net(host_in.to(dev, non_blocking=True))
+        host_out.copy_(p, non_blocking=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        p, _ = net(host_in.to(dev, non_blocking=True))
+        host_out.copy_(p, non_blocking=True)
+    e1.record()
+    barrier()
+    ms_e2e = max_over_ranks(e0.elapsed_time(e1))
+    e2e = world * B * args.steps / (ms_e2e / 1e3)
+    if rank == 0:
+        sampler.stop_flag = True
+        sampler.join(timeout=3)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    pk = peaks()
+    # dominant kernel family by measured device time inside the timed region
+    dom = max(fam.items(), key=lambda kv: kv[1][0])[0] if fam else None
+    roofline = None
+    if dom in ('conv_tc', 'conv_direct'):
+        ms, n = fam[dom]
+        ach = flops.get(dom, 0) / (ms / 1e3) / 1e12
+        roofline = {'kernel': dom, 'bound': 'tensor', 'achieved': ach, 'peak': pk['tflops'], 'unit': 'TFLOP/s',
+                    'frac': ach / pk['tflops'], 'traffic': None, 'peak_source': pk['src'],
+                    'launches': n, 'kernel_ms_per_step': ms / args.steps}
+    elif dom is not None:
+        ms, n = fam[dom]
+        roofline = {'kernel': dom, 'bound': 'hbm', 'achieved': None, 'peak': pk['hbm_gbs'], 'unit': 'GB/s', 'frac': None,
+                    'traffic': None, 'peak_source': pk['src'], 'launches': n, 'kernel_ms_per_step': ms / args.steps}
+    families = {k: {'ms_per_step': v[0] / args.steps, 'launches_per_step': v[1] / args.steps,
+                    'tflops': (flops.get(k, 0) / (v[0] / 1e3) / 1e12) if k in flops and v[0] > 0 else None}
+                for k, v in fam.items()}
+
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        torch.set_num_threads(cores)
+        sd = O.make_state_dict(0)
+        b1 = O.make_burst(0, 1, FRAMES, S, S)
+        O.dbsr_forward(b1, sd)
+        t0 = time.perf_counter()
+        n = 0
+        while True:
+            O.dbsr_forward(b1, sd)
+            n += 1
+            if time.perf_counter() - t0 > args.cpu_baseline_seconds or n >= 20:
+                break
+        dt = (time.perf_counter() - t0) / n
+        cpu = {'value': 1.0 / dt, 'unit': 'bursts/s', 'cores': cores, 'kind': 'port',
+               'sample': f'{n} forwards of 1 burst {FRAMES}x4x{S}x{S}, fp32, torch CPU threads={cores}'}
+
+    gf = CONV_GFLOP_PER_BURST.get(S)
+    line = {
+        'metric': 'bursts/sec (14-frame, 4x SR)', 'value': value, 'unit': 'bursts/s', 'n_gpus': world,
+        'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_total / args.steps, 'higher_is_better': True,
+        'scaling': 'weak', 'vs_baseline': None, 'dtype': args.precision, 'data': 'synthetic',
+        'config': {'workload': f'DBSRNet forward, {B} bursts/GPU of {FRAMES}x4x{S}x{S} packed RAW -> 3x{8 * S}x{8 * S}, '
+                               f'random-init weights (BASELINE.json configs[1])',
+                   'global_batch': B * world, 'parallelism': f'burst-sharded x{world}, no data-path collective',
+                   'l2': 'per-step activation working set (~GBs) >> 126 MB L2; no explicit flush'},
+        'e2e': {'value': e2e, 'unit': 'bursts/s', 'ms_per_step': ms_e2e / args.steps,
+                'h2d_bytes_per_step': host_in.numel() * 4, 'd2h_bytes_per_step': host_out.numel() * 4},
+        'gpu_launches': launches,
+        'roofline': roofline,
+        'kernel_families': families,
+        'cpu_baseline': cpu,
+        'clocks': sampler.summary(),
+        'model_tflops': (gf * value / 1e3) if gf else None,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

@@ -58,7 +58,7 @@ __device__ __forceinline__ Vec4 gather4(const T* base, int c_pitch, int H, int W
 }
 
 template <typename TI, typename TO>
-__global__ void __launch_bounds__(256) warp_kernel(View feat, const float* __restrict__ offsets, View out, int group) {
+__global__ void __launch_bounds__(256) warp_kernel(View feat, const float* __restrict__ offsets, View out, int frames) {
   const int H = out.h, W = out.w, C4 = out.c >> 2;
   const long long HW = (long long)H * W;
   const long long total = (long long)out.n * HW * C4;
@@ -68,17 +68,24 @@ __global__ void __launch_bounds__(256) warp_kernel(View feat, const float* __res
        i += (long long)gridDim.x * blockDim.x) {
     const int c4 = (int)(i % C4);
     const long long pix = i / C4;
-    const int p = (int)(pix / HW);
-    const int rem = (int)(pix - (long long)p * HW);
+    const int f = (int)(pix / HW);
+    const int rem = (int)(pix - (long long)f * HW);
     const int y = rem / W, x = rem - y * W;
-    int img = p;
-    if (group > 0) {
-      const int b = p / group;
-      img = b * (group + 1) + 1 + (p - b * group);
+    long long p = f;        // index into offsets
+    bool identity = false;  // burst mode: frame 0 of every burst is the reference (copied)
+    if (frames > 0) {
+      const int b = f / frames, n = f - b * frames;
+      identity = (n == 0);
+      p = (long long)b * (frames - 1) + (n - 1);
     }
-    const float fx = __ldg(offsets + ((long long)p * 2 + 0) * HW + rem);
-    const float fy = __ldg(offsets + ((long long)p * 2 + 1) * HW + rem);
-    const Vec4 r = gather4<TI>(fbase, feat.c_pitch, H, W, (long long)img * HW, (float)x + fx, (float)y + fy, c4 * 4);
+    Vec4 r;
+    if (identity) {
+      r = ld4<TI>(fbase + pix * feat.c_pitch + c4 * 4);
+    } else {
+      const float fx = __ldg(offsets + (p * 2 + 0) * HW + rem);
+      const float fy = __ldg(offsets + (p * 2 + 1) * HW + rem);
+      r = gather4<TI>(fbase, feat.c_pitch, H, W, (long long)f * HW, (float)x + fx, (float)y + fy, c4 * 4);
+    }
     st4<TO>(obase + pix * out.c_pitch + c4 * 4, r);
   }
 }
@@ -172,23 +179,22 @@ static bool vec4_ok(const dbsr_nhwc_t* v) {
 
 using namespace dbsr;
 
-extern "C" int dbsr_warp(const dbsr_nhwc_t* feat, const float* offsets, const dbsr_nhwc_t* out, int32_t pairs,
-                         int32_t group, void* stream) {
+extern "C" int dbsr_warp(const dbsr_nhwc_t* feat, const float* offsets, const dbsr_nhwc_t* out, int32_t frames,
+                         void* stream) {
   DBSR_REQUIRE(view_ok(feat) && view_ok(out) && offsets, "warp: bad arguments");
-  DBSR_REQUIRE(out->n == pairs && out->h == feat->h && out->w == feat->w && out->c == feat->c, "warp: geometry");
+  DBSR_REQUIRE(out->n == feat->n && out->h == feat->h && out->w == feat->w && out->c == feat->c, "warp: geometry");
   DBSR_REQUIRE(vec4_ok(feat) && vec4_ok(out), "warp: channel count/offset/pitch must be multiples of 4 and aligned");
-  if (group > 0) DBSR_REQUIRE(pairs % group == 0 && feat->n >= (pairs / group) * (group + 1), "warp: mapping range");
-  else DBSR_REQUIRE(feat->n >= pairs, "warp: not enough images");
-  const long long total = (long long)pairs * out->h * out->w * (out->c / 4);
+  DBSR_REQUIRE(frames == 0 || (frames >= 2 && out->n % frames == 0), "warp: image count is not a multiple of frames");
+  const long long total = (long long)out->n * out->h * out->w * (out->c / 4);
   const int g = grid_cap(total, 256);
   cudaStream_t st = (cudaStream_t)stream;
   View f = make_view(feat), o = make_view(out);
-  if (feat->dtype == DBSR_F32 && out->dtype == DBSR_F32) warp_kernel<float, float><<<g, 256, 0, st>>>(f, offsets, o, group);
+  if (feat->dtype == DBSR_F32 && out->dtype == DBSR_F32) warp_kernel<float, float><<<g, 256, 0, st>>>(f, offsets, o, frames);
   else if (feat->dtype == DBSR_BF16 && out->dtype == DBSR_BF16)
-    warp_kernel<__nv_bfloat16, __nv_bfloat16><<<g, 256, 0, st>>>(f, offsets, o, group);
+    warp_kernel<__nv_bfloat16, __nv_bfloat16><<<g, 256, 0, st>>>(f, offsets, o, frames);
   else if (feat->dtype == DBSR_F32 && out->dtype == DBSR_BF16)
-    warp_kernel<float, __nv_bfloat16><<<g, 256, 0, st>>>(f, offsets, o, group);
-  else warp_kernel<__nv_bfloat16, float><<<g, 256, 0, st>>>(f, offsets, o, group);
+    warp_kernel<float, __nv_bfloat16><<<g, 256, 0, st>>>(f, offsets, o, frames);
+  else warp_kernel<__nv_bfloat16, float><<<g, 256, 0, st>>>(f, offsets, o, frames);
   return check_launch("warp");
 }
 

@@ -1,0 +1,512 @@
+"""Execution engine of the DBSR burst forward pass on B200.
+
+Owns (i) the weights re-packed once for the kernels, (ii) per-shape channels-last workspaces in HBM, (iii) the
+launch sequence that replaces `DBSRNet.forward` (reference models/dbsr/dbsrnet.py:33-38, call stack in
+SURVEY.md 3.1).  The Python modules in `deep_rawburst_sr_b200.models` keep the reference's interfaces and
+parameters and delegate here.  Every op is a hand-written sm_100a kernel behind the C ABI (`ops.py`); there is
+no eager-PyTorch fallback for any of them.
+
+Data layout in HBM: every activation is NHWC.  `precision='bf16'`: DBSR activations are bf16 and the 3x3 / 1x1
+convolutions run on tcgen05 tensor cores with fp32 accumulation in TMEM; PWC-Net (flow) stays fp32.
+`precision='fp32'`: everything fp32 on CUDA cores (exact path, <= 1e-4 on the output).
+PWC-Net dense concatenations (pwcnet.py:171-177) are channel slices of one buffer per pyramid level, segments
+aligned to 8 channels: [o5 32 | o4 64 | o3 96 | o2 128 | o1 128 | V 81(+7) | f1 C | upflow 2(+6) | upfeat 2(+6)].
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, Optional
+
+import torch
+
+from . import ops
+from .ops import ACT_LRELU, ACT_NONE, ACT_RELU, Act
+
+PWC_NAMES = ['One', 'Two', 'Thr', 'Fou', 'Fiv', 'Six']
+PWC_EXT_CH = [3, 16, 32, 64, 96, 128, 196]
+PWC_DEC_OUT = [128, 128, 96, 64, 32]           # netOne..netFiv outputs (netSix -> 2 flow channels)
+PWC_BACKWARP = {5: 0.625, 4: 1.25, 3: 2.5, 2: 5.0}   # reference pwcnet.py:121
+PWC_REFINER_DIL = [1, 2, 4, 8, 16, 1, 1]
+
+
+def _align8(v: int) -> int:
+    return (v + 7) // 8 * 8
+
+
+class PwcLayout:
+    """Channel layout of the level-l concat buffer (new channels in FRONT, reference pwcnet.py:173-177)."""
+
+    def __init__(self, level: int):
+        segs = [('o5', 32), ('o4', 64), ('o3', 96), ('o2', 128), ('o1', 128), ('V', 81)]
+        if level < 6:
+            segs += [('f1', PWC_EXT_CH[level]), ('upflow', 2), ('upfeat', 2)]
+        self.level = level
+        self.names = [s[0] for s in segs]
+        self.sizes = {s[0]: s[1] for s in segs}
+        self.off = {}
+        o = 0
+        for name, sz in segs:
+            self.off[name] = o
+            o += _align8(sz)
+        self.total = o
+
+    def chmap_from(self, first_seg: str):
+        """buffer channel (relative to the slice start) of every original input channel of a conv that reads
+        `cat[first_seg:]`; and the slice (start, length)."""
+        i0 = self.names.index(first_seg)
+        start = self.off[first_seg]
+        cm = []
+        for name in self.names[i0:]:
+            cm += list(range(self.off[name] - start, self.off[name] - start + self.sizes[name]))
+        return cm, start, self.total - start
+
+
+def pack_direct(w: torch.Tensor, chmap=None, cin_buf: Optional[int] = None) -> torch.Tensor:
+    """[Cout, Cin, k, k] -> fp32 [k*k, Cin_buf, Cout] (rows of padded channels are zero)."""
+    cout, cin, kh, kw = w.shape
+    cin_buf = cin if cin_buf is None else cin_buf
+    out = torch.zeros((kh * kw, cin_buf, cout), dtype=torch.float32, device=w.device)
+    src = w.float().permute(2, 3, 1, 0).reshape(kh * kw, cin, cout)
+    if chmap is None:
+        out[:, :cin] = src
+    else:
+        out[:, torch.as_tensor(chmap, device=w.device)] = src
+    return out.contiguous()
+
+
+def pack_tc(w: torch.Tensor, shuffle_r: int = 0) -> torch.Tensor:
+    """[Cout, Cin, k, k] -> bf16 [k*k, Cout, Kpad] K-major (Kpad = Cin rounded up to the kernel's K chunk: 64
+    when Cin % 64 == 0 else 32).  shuffle_r = 8: rows permuted to (i, j, c) order so that an N tile is contiguous
+    in the pixel-shuffled output (nn.PixelShuffle: co = c*r*r + i*r + j)."""
+    cout, cin, kh, kw = w.shape
+    ck = 64 if cin % 64 == 0 else 32
+    kpad = (cin + ck - 1) // ck * ck
+    src = w.float()
+    if shuffle_r and shuffle_r > 1:
+        r = shuffle_r
+        c = cout // (r * r)
+        src = src.view(c, r, r, cin, kh, kw).permute(1, 2, 0, 3, 4, 5).reshape(cout, cin, kh, kw)
+    out = torch.zeros((kh * kw, cout, kpad), dtype=torch.float32, device=w.device)
+    out[:, :, :cin] = src.permute(2, 3, 0, 1).reshape(kh * kw, cout, cin)
+    return out.to(torch.bfloat16).contiguous()
+
+
+def pack_deconv(w: torch.Tensor, chmap=None, cin_buf: Optional[int] = None) -> torch.Tensor:
+    """ConvTranspose2d weight [Cin, 2, 4, 4] -> fp32 [4, 4, 2, Cin_buf]."""
+    cin = w.shape[0]
+    cin_buf = cin if cin_buf is None else cin_buf
+    out = torch.zeros((4, 4, 2, cin_buf), dtype=torch.float32, device=w.device)
+    src = w.float().permute(2, 3, 1, 0)
+    if chmap is None:
+        out[..., :cin] = src
+    else:
+        out[..., torch.as_tensor(chmap, device=w.device)] = src
+    return out.contiguous()
+
+
+class ConvW:
+    __slots__ = ('direct', 'tc', 'bias', 'ksize', 'cout', 'cin', 'shuffle_r')
+
+    def __init__(self, direct, tc, bias, ksize, cout, cin, shuffle_r=0):
+        self.direct, self.tc, self.bias, self.ksize, self.cout, self.cin, self.shuffle_r = \
+            direct, tc, bias, ksize, cout, cin, shuffle_r
+
+
+class DBSREngine:
+    def __init__(self, state_dict: Dict[str, torch.Tensor], device, precision: str = 'bf16', offset_modulo: float = 1.0,
+                 gauss_kernel=None, logits_fp32: bool = False,
+                 pwc_prefix: str = 'encoder.alignment_net.net.', parts=('pwc', 'encoder', 'merging', 'decoder')):
+        assert precision in ('bf16', 'fp32')
+        self.device = torch.device(device)
+        ops.require_device(torch.empty(1, device=self.device))
+        self.precision = precision
+        self.bf16 = precision == 'bf16'
+        self.act_dtype = torch.bfloat16 if self.bf16 else torch.float32
+        self.logits_dtype = torch.float32 if (logits_fp32 or not self.bf16) else torch.bfloat16
+        self.offset_modulo = float(offset_modulo) if offset_modulo is not None else 0.0
+        self.pwc_prefix = pwc_prefix
+        self.W: Dict[str, ConvW] = {}
+        self.D: Dict[str, tuple] = {}
+        self._ws: Dict[tuple, dict] = {}
+        self.launches = 0
+        self.timers = None   # when a dict: family -> list of (start, end) CUDA events on the launching stream
+        self.flops = {}      # family -> algorithmic FLOPs (2*MAC, real channel counts) launched since reset
+        sd = {k: v.detach().to(self.device) for k, v in state_dict.items()}
+        if 'pwc' in parts:
+            self._pack_pwc(sd)
+        if 'encoder' in parts or 'merging' in parts or 'decoder' in parts:
+            self._pack_dbsr(sd, parts)
+        if gauss_kernel is False:
+            gauss_kernel = None
+        elif gauss_kernel is None:
+            k = torch.arange(-1.0, 2.0)
+            g = torch.exp(-0.5 * k ** 2) / math.sqrt(2 * math.pi)
+            K = g.view(1, -1) * g.view(-1, 1)
+            gauss_kernel = K / K.sum()
+        self.gauss = [float(v) for v in gauss_kernel.reshape(-1).tolist()] if gauss_kernel is not None else None
+
+    # ------------------------------------------------------------------------------------------------
+    # weight packing
+    # ------------------------------------------------------------------------------------------------
+    def _add(self, key, w, b, tc=False, chmap=None, cin_buf=None, shuffle_r=0):
+        direct = pack_direct(w, chmap, cin_buf)
+        tcw = pack_tc(w, shuffle_r) if (tc and self.bf16) else None
+        self.W[key] = ConvW(direct, tcw, None if b is None else b.float().contiguous(), w.shape[2], w.shape[0], w.shape[1],
+                             shuffle_r)
+
+    def _pack_pwc(self, sd):
+        pre = self.pwc_prefix
+        for name in PWC_NAMES:
+            for idx in (0, 2, 4):
+                k = f'{pre}netExtractor.net{name}.{idx}'
+                self._add(k, sd[k + '.weight'], sd[k + '.bias'])
+        self.pwc_layouts = {l: PwcLayout(l) for l in (2, 3, 4, 5, 6)}
+        segs = ['V', 'o1', 'o2', 'o3', 'o4', 'o5']   # input of netOne..netSix starts at this segment
+        for lvl in (6, 5, 4, 3, 2):
+            lay = self.pwc_layouts[lvl]
+            lname = PWC_NAMES[lvl - 1]
+            for j, sub in enumerate(PWC_NAMES):
+                k = f'{pre}net{lname}.net{sub}.0'
+                cm, _start, length = lay.chmap_from(segs[j])
+                self._add(k, sd[k + '.weight'], sd[k + '.bias'], chmap=cm, cin_buf=length)
+            if lvl < 6:
+                prev = self.pwc_layouts[lvl + 1]
+                cm, _s, length = prev.chmap_from('o5')
+                k = f'{pre}net{lname}.netUpfeat'
+                self.D[k] = (pack_deconv(sd[k + '.weight'], cm, length), sd[k + '.bias'].float().contiguous())
+                k = f'{pre}net{lname}.netUpflow'
+                self.D[k] = (pack_deconv(sd[k + '.weight']), sd[k + '.bias'].float().contiguous())
+        cm, _s, length = self.pwc_layouts[2].chmap_from('o5')
+        for j in range(7):
+            k = f'{pre}netRefiner.netMain.{2 * j}'
+            if j == 0:
+                self._add(k, sd[k + '.weight'], sd[k + '.bias'], chmap=cm, cin_buf=length)
+            else:
+                self._add(k, sd[k + '.weight'], sd[k + '.bias'])
+
+    def _pack_dbsr(self, sd, parts):
+        def add(k, tc=True, bias=True, shuffle_r=0):
+            self._add(k, sd[k + '.weight'], sd.get(k + '.bias') if bias else None, tc=tc, shuffle_r=shuffle_r)
+
+        if 'encoder' in parts:
+            add('encoder.init_layer.0')
+            self.enc_res = len([k for k in sd if k.startswith('encoder.res_layers.') and k.endswith('conv1.0.weight')])
+            for i in range(self.enc_res):
+                add(f'encoder.res_layers.{i}.conv1.0')
+                add(f'encoder.res_layers.{i}.conv2.0')
+            add('encoder.out_layer.0')
+            self.enc_dim = sd['encoder.init_layer.0.weight'].shape[0]
+            self.feat_dim = sd['encoder.out_layer.0.weight'].shape[0]
+        if 'merging' in parts:
+            add('merging.feat_project_layer.0')
+            add('merging.offset_feat_extractor.0.0')
+            self.off_res = len([k for k in sd if k.startswith('merging.offset_feat_extractor.') and k.endswith('conv1.0.weight')])
+            for i in range(self.off_res):
+                add(f'merging.offset_feat_extractor.{i + 1}.conv1.0')
+                add(f'merging.offset_feat_extractor.{i + 1}.conv2.0')
+            self.wp_res = len([k for k in sd if k.startswith('merging.weight_predictor.') and k.endswith('conv1.0.weight')])
+            add('merging.weight_predictor.0.0')
+            for i in range(self.wp_res):
+                add(f'merging.weight_predictor.{i + 1}.conv1.0')
+                add(f'merging.weight_predictor.{i + 1}.conv2.0')
+            add(f'merging.weight_predictor.{self.wp_res + 1}.0')
+            self.proj_dim = sd['merging.feat_project_layer.0.weight'].shape[0]
+            self.offf_dim = sd['merging.offset_feat_extractor.0.0.weight'].shape[0]
+            self.wp_dim = sd['merging.weight_predictor.0.0.weight'].shape[0]
+            self.feat_dim = sd['merging.feat_project_layer.0.weight'].shape[1]
+        if 'decoder' in parts:
+            add('decoder.init_layer.0')
+            self.dec_pre = len([k for k in sd if k.startswith('decoder.pre_res_layers.') and k.endswith('conv1.0.weight')])
+            for i in range(self.dec_pre):
+                add(f'decoder.pre_res_layers.{i}.conv1.0')
+                add(f'decoder.pre_res_layers.{i}.conv2.0')
+            up_w = sd['decoder.upsample_layer.conv_layer.0.weight']
+            self.dec_dim = sd['decoder.init_layer.0.weight'].shape[0]
+            self.post_dim = sd['decoder.predictor.0.weight'].shape[1]
+            self.up_r = int(round(math.sqrt(up_w.shape[0] // self.post_dim)))
+            self._add('decoder.upsample_layer.conv_layer.0', up_w, sd.get('decoder.upsample_layer.conv_layer.0.bias'),
+                      tc=True, shuffle_r=self.up_r)
+            self.dec_post = len([k for k in sd if k.startswith('decoder.post_res_layers.') and k.endswith('conv1.0.weight')])
+            for i in range(self.dec_post):
+                add(f'decoder.post_res_layers.{i}.conv1.0')
+                add(f'decoder.post_res_layers.{i}.conv2.0')
+            self.pred_w = sd['decoder.predictor.0.weight'].float().reshape(sd['decoder.predictor.0.weight'].shape[0], -1).contiguous()
+            self.pred_b = sd['decoder.predictor.0.bias'].float().contiguous()
+            self.feat_dim = sd['decoder.init_layer.0.weight'].shape[1]
+
+    # ------------------------------------------------------------------------------------------------
+    # helpers
+    # ------------------------------------------------------------------------------------------------
+    def _conv(self, key: str, x: Act, y: Act, act: int, stride: int = 1, dilation: int = 1,
+              residual: Optional[Act] = None, force_direct: bool = False) -> Act:
+        cw = self.W[key]
+        use_tc = (cw.tc is not None and not force_direct and x.dtype == torch.bfloat16 and stride == 1)
+        if use_tc:
+            use_tc = ops.conv2d_tc_supported(x, cw.tc, cw.bias, y, cw.ksize, stride, dilation, residual, cw.shuffle_r)
+        self.launches += 1
+        fam = 'conv_tc' if use_tc else 'conv_direct'
+        ho, wo = (y.h, y.w) if cw.shuffle_r <= 1 else (y.h // cw.shuffle_r, y.w // cw.shuffle_r)
+        self.flops[fam] = self.flops.get(fam, 0) + 2 * x.n * ho * wo * cw.cout * cw.cin * cw.ksize * cw.ksize
+        ev = self._tic(fam)
+        if use_tc:
+            ops.conv2d(x, cw.tc, cw.bias, y, cw.ksize, stride, dilation, act, residual, cw.shuffle_r, tensor_core=True)
+        else:
+            ops.conv2d(x, cw.direct, cw.bias, y, cw.ksize, stride, dilation, act, residual, cw.shuffle_r)
+        self._toc(ev)
+        return y
+
+    def _tic(self, family: str):
+        if self.timers is None:
+            return None
+        a = torch.cuda.Event(enable_timing=True)
+        b = torch.cuda.Event(enable_timing=True)
+        a.record()
+        self.timers.setdefault(family, []).append((a, b))
+        return b
+
+    @staticmethod
+    def _toc(ev):
+        if ev is not None:
+            ev.record()
+
+    def timer_summary(self) -> dict:
+        """family -> (total ms, launches); call after a synchronize."""
+        out = {}
+        for fam, evs in (self.timers or {}).items():
+            out[fam] = (sum(a.elapsed_time(b) for a, b in evs), len(evs))
+        return out
+
+    def _resblock(self, key: str, x: Act, tmp: Act, y: Act) -> Act:
+        """reference models/layers/blocks.py:84-96: relu(x + conv2(relu(conv1(x))))"""
+        self._conv(key + '.conv1.0', x, tmp, ACT_RELU)
+        return self._conv(key + '.conv2.0', tmp, y, ACT_RELU, residual=x)
+
+    def _buf(self, ws: dict, name: str, n, h, w, c, dtype, zero=False) -> Act:
+        a = ws.get(name)
+        if a is None:
+            a = Act.empty(n, h, w, c, dtype, self.device, zero=zero)
+            ws[name] = a
+        return a
+
+    def workspace(self, key: tuple) -> dict:
+        ws = self._ws.get(key)
+        if ws is None:
+            ws = {}
+            self._ws[key] = ws
+        return ws
+
+    # ------------------------------------------------------------------------------------------------
+    # PWC-Net  (reference models/alignment/pwcnet.py)
+    # ------------------------------------------------------------------------------------------------
+    def pwc_extract(self, ws: dict, pwc_in: Act) -> list:
+        """Extractor pyramid (pwcnet.py:45-111) on every image of `pwc_in` [n, Hp, Wp, >=3]."""
+        pre = self.pwc_prefix
+        n = pwc_in.n
+        x = pwc_in.slice(0, 3)
+        h, w = pwc_in.h, pwc_in.w
+        feats = []
+        for l, name in enumerate(PWC_NAMES):
+            c = PWC_EXT_CH[l + 1]
+            h, w = (h + 1) // 2, (w + 1) // 2
+            t1 = self._buf(ws, f'ext{l}_a', n, h, w, c, torch.float32)
+            t2 = self._buf(ws, f'ext{l}_b', n, h, w, c, torch.float32)
+            f = self._buf(ws, f'ext{l}_f', n, h, w, c, torch.float32)
+            self._conv(f'{pre}netExtractor.net{name}.0', x, t1, ACT_LRELU, stride=2)
+            self._conv(f'{pre}netExtractor.net{name}.2', t1, t2, ACT_LRELU)
+            self._conv(f'{pre}netExtractor.net{name}.4', t2, f, ACT_LRELU)
+            feats.append(f)
+            x = f
+        return feats
+
+    def pwc_decode(self, ws: dict, first: list, second: list, pairs: int, group: int, src_group: int) -> Act:
+        """Decoders 6..2 + refiner (pwcnet.py:113-231).  `first`/`second`: per-level feature Acts.  group > 0: burst
+        mode (both lists are the same per-frame pyramid, frame 0 of each burst is the reference)."""
+        pre = self.pwc_prefix
+        segs = ['V', 'o1', 'o2', 'o3', 'o4', 'o5']
+        prev_cat = None
+        prev_flow = None
+        for lvl in (6, 5, 4, 3, 2):
+            lay = self.pwc_layouts[lvl]
+            lname = PWC_NAMES[lvl - 1]
+            f1, f2 = first[lvl - 1], second[lvl - 1]
+            h, w = f1.h, f1.w
+            cat = self._buf(ws, f'cat{lvl}', pairs, h, w, lay.total, torch.float32, zero=True)
+            flow = self._buf(ws, f'flow{lvl}', pairs, h, w, 2, torch.float32)
+            vol = cat.slice(lay.off['V'], 81)
+            if prev_cat is None:
+                ev = self._tic('corr81')
+                ops.corr81(f1, f2, vol, pairs, group, act=ACT_LRELU)
+                self._toc(ev)
+                self.launches += 1
+            else:
+                upflow = self._buf(ws, f'upflow{lvl}', pairs, h, w, 2, torch.float32)
+                wf, bf = self.D[f'{pre}net{lname}.netUpflow']
+                ops.deconv4x4s2(prev_flow, wf, bf, cat.slice(lay.off['upflow'], 2), upflow)
+                wt, bt = self.D[f'{pre}net{lname}.netUpfeat']
+                ops.deconv4x4s2(prev_cat, wt, bt, cat.slice(lay.off['upfeat'], 2))
+                ops.copy_channels(f1, cat.slice(lay.off['f1'], lay.sizes['f1']), group, src_group, 0)
+                ev = self._tic('corr81')
+                ops.corr81(f1, f2, vol, pairs, group, flow=upflow, flow_scale=PWC_BACKWARP[lvl], act=ACT_LRELU)
+                self._toc(ev)
+                self.launches += 4
+            for j, sub in enumerate(PWC_NAMES[:5]):
+                _cm, start, length = lay.chmap_from(segs[j])
+                out_name = 'o%d' % (j + 1)
+                self._conv(f'{pre}net{lname}.net{sub}.0', cat.slice(start, length),
+                           cat.slice(lay.off[out_name], lay.sizes[out_name]), ACT_LRELU)
+            self._conv(f'{pre}net{lname}.netSix.0', cat, flow, ACT_NONE)
+            prev_cat, prev_flow = cat, flow
+        # refiner (dilated convs), result added to the level-2 flow (pwcnet.py:231)
+        h, w = prev_cat.h, prev_cat.w
+        chans = [128, 128, 128, 96, 64, 32]
+        x = prev_cat
+        for j in range(6):
+            y = self._buf(ws, f'ref{j}', pairs, h, w, chans[j], torch.float32)
+            self._conv(f'{pre}netRefiner.netMain.{2 * j}', x, y, ACT_LRELU, dilation=PWC_REFINER_DIL[j])
+            x = y
+        flow4 = self._buf(ws, 'flow_quarter', pairs, h, w, 2, torch.float32)
+        self._conv(f'{pre}netRefiner.netMain.12', x, flow4, ACT_NONE, dilation=1, residual=prev_flow)
+        return flow4
+
+    def pwc_burst(self, ws: dict, pwc_in: Act, B: int, N: int, H: int, W: int, offsets: torch.Tensor) -> torch.Tensor:
+        """PWCNet.forward (pwcnet.py:248-281) for a burst batch: frame 0 of every burst is the target; the pyramid of
+        each frame is computed once (the reference recomputes the reference frame's pyramid N-1 times)."""
+        feats = self.pwc_extract(ws, pwc_in)
+        flow4 = self.pwc_decode(ws, feats, feats, B * (N - 1), N - 1, N)
+        ops.flow_head(flow4, offsets, H, W, pwc_in.h, pwc_in.w)
+        self.launches += 1
+        return offsets
+
+    # ------------------------------------------------------------------------------------------------
+    # DBSR stages
+    # ------------------------------------------------------------------------------------------------
+    def encode(self, ws: dict, enc_in: Act) -> Act:
+        """conv stack of ResEncoderWarpAlignnet (reference models/dbsr/encoders.py:66-72) on all B*N frames."""
+        F_, H, W = enc_in.n, enc_in.h, enc_in.w
+        dt = self.act_dtype
+        xa = self._buf(ws, 'enc_a', F_, H, W, self.enc_dim, dt)
+        xb = self._buf(ws, 'enc_b', F_, H, W, self.enc_dim, dt)
+        xt = self._buf(ws, 'enc_t', F_, H, W, self.enc_dim, dt)
+        feat = self._buf(ws, 'feat', F_, H, W, self.feat_dim, dt)
+        self._conv('encoder.init_layer.0', enc_in.slice(0, 4), xa, ACT_RELU)
+        cur, nxt = xa, xb
+        for i in range(self.enc_res):
+            self._resblock(f'encoder.res_layers.{i}', cur, xt, nxt)
+            cur, nxt = nxt, cur
+        self._conv('encoder.out_layer.0', cur, feat, ACT_RELU)
+        return feat
+
+    def merge(self, ws: dict, all_feat: Act, offsets: torch.Tensor, B: int, N: int,
+              weights_out: Optional[torch.Tensor] = None) -> Act:
+        """WeightedSum.forward (reference models/dbsr/merging.py:61-127).  `all_feat` [B*N, H, W, C]: reference frame +
+        aligned other frames; offsets [B*(N-1), 2, H, W]."""
+        F_, H, W = all_feat.n, all_feat.h, all_feat.w
+        dt = self.act_dtype
+        pd, od, wd = self.proj_dim, self.offf_dim, self.wp_dim
+        proj = self._buf(ws, 'proj', F_, H, W, pd, dt)
+        self._conv('merging.feat_project_layer.0', all_feat, proj, ACT_RELU)
+        wp_in = self._buf(ws, 'wp_in', F_, H, W, 2 * pd + od, dt)
+        ops.build_wp_input(proj, wp_in, N)
+        offm = self._buf(ws, 'offm', F_, H, W, 8, dt)
+        ops.offsets_mod(offsets, offm, B, N, self.offset_modulo)
+        self.launches += 2
+        oa = self._buf(ws, 'off_a', F_, H, W, od, dt)
+        ob = self._buf(ws, 'off_b', F_, H, W, od, dt)
+        ot = self._buf(ws, 'off_t', F_, H, W, od, dt)
+        self._conv('merging.offset_feat_extractor.0.0', offm.slice(0, 2), oa, ACT_RELU)
+        cur, nxt = oa, ob
+        for i in range(self.off_res):
+            last = i == self.off_res - 1
+            dst = wp_in.slice(2 * pd, od) if last else nxt
+            self._resblock(f'merging.offset_feat_extractor.{i + 1}', cur, ot, dst)
+            cur, nxt = dst, cur
+        if self.off_res == 0:
+            ops.copy_channels(oa, wp_in.slice(2 * pd, od))
+            self.launches += 1
+        wa = self._buf(ws, 'wp_a', F_, H, W, wd, dt)
+        wb = self._buf(ws, 'wp_b', F_, H, W, wd, dt)
+        wt = self._buf(ws, 'wp_t', F_, H, W, wd, dt)
+        self._conv('merging.weight_predictor.0.0', wp_in, wa, ACT_RELU)
+        cur, nxt = wa, wb
+        for i in range(self.wp_res):
+            self._resblock(f'merging.weight_predictor.{i + 1}', cur, wt, nxt)
+            cur, nxt = nxt, cur
+        logits = self._buf(ws, 'logits', F_, H, W, self.feat_dim, self.logits_dtype)
+        self._conv(f'merging.weight_predictor.{self.wp_res + 1}.0', cur, logits, ACT_NONE)
+        fused = self._buf(ws, 'fused', B, H, W, self.feat_dim, dt)
+        ev = self._tic('softmax_wsum')
+        ops.softmax_wsum(all_feat, logits, fused, N, offsets=None, weights_out=weights_out)
+        self._toc(ev)
+        self.launches += 1 + (1 if weights_out is not None else 0)
+        return fused
+
+    def decode(self, ws: dict, fused: Act, pred: torch.Tensor) -> torch.Tensor:
+        """ResPixShuffleConv.forward (reference models/dbsr/decoders.py:54-62, models/layers/upsampling.py:51-66)."""
+        B, H, W = fused.n, fused.h, fused.w
+        dt = self.act_dtype
+        r = self.up_r
+        da = self._buf(ws, 'dec_a', B, H, W, self.dec_dim, dt)
+        db = self._buf(ws, 'dec_b', B, H, W, self.dec_dim, dt)
+        dtmp = self._buf(ws, 'dec_t', B, H, W, self.dec_dim, dt)
+        self._conv('decoder.init_layer.0', fused, da, ACT_RELU)
+        cur, nxt = da, db
+        for i in range(self.dec_pre):
+            self._resblock(f'decoder.pre_res_layers.{i}', cur, dtmp, nxt)
+            cur, nxt = nxt, cur
+        ha = self._buf(ws, 'hr_a', B, H * r, W * r, self.post_dim, dt)
+        hb = self._buf(ws, 'hr_b', B, H * r, W * r, self.post_dim, dt)
+        ht = self._buf(ws, 'hr_t', B, H * r, W * r, self.post_dim, dt)
+        self._conv('decoder.upsample_layer.conv_layer.0', cur, ha, ACT_RELU)      # 1x1 conv + ReLU + PixelShuffle
+        if self.gauss is not None:
+            ops.blur3x3(ha, hb, self.gauss)
+            self.launches += 1
+            cur, nxt = hb, ha
+        else:
+            cur, nxt = ha, hb
+        for i in range(self.dec_post):
+            self._resblock(f'decoder.post_res_layers.{i}', cur, ht, nxt)
+            cur, nxt = nxt, cur
+        ops.predictor(cur, self.pred_w, self.pred_b, pred)
+        self.launches += 1
+        return pred
+
+    # ------------------------------------------------------------------------------------------------
+    # whole forward
+    # ------------------------------------------------------------------------------------------------
+    @torch.no_grad()
+    def forward(self, burst: torch.Tensor, return_weights: bool = False, out: Optional[dict] = None):
+        """DBSRNet.forward: burst [B, N, 4, H, W] fp32 CUDA -> pred [B, 3, 8H, 8W], offsets [B, N-1, 2, H, W],
+        fusion_weights [B, N, C, H, W] (only when return_weights)."""
+        assert burst.dim() == 5 and burst.shape[2] == 4, 'burst must be [B, N, 4, H, W]'
+        ops.require_device(burst)
+        burst = burst.contiguous().float()
+        B, N, _, H, W = burst.shape
+        assert N >= 2, 'a burst needs at least 2 frames'
+        Hp, Wp = int(math.ceil(H / 64.0) * 64), int(math.ceil(W / 64.0) * 64)
+        ws = self.workspace((B, N, H, W))
+        F_ = B * N
+        enc_in = self._buf(ws, 'enc_in', F_, H, W, 8, self.act_dtype)
+        pwc_in = self._buf(ws, 'pwc_in', F_, Hp, Wp, 4, torch.float32)
+        ops.prep_burst(burst, enc_in, pwc_in)
+        self.launches += 1
+        if out is None:
+            out = {}
+        offsets = out.get('offsets')
+        if offsets is None:
+            offsets = torch.empty((B * (N - 1), 2, H, W), dtype=torch.float32, device=self.device)
+        self.pwc_burst(ws, pwc_in, B, N, H, W, offsets)
+        feat = self.encode(ws, enc_in)
+        all_feat = self._buf(ws, 'all_feat', F_, H, W, self.feat_dim, self.act_dtype)
+        ev = self._tic('warp')
+        ops.warp(feat, offsets, all_feat, frames=N)
+        self._toc(ev)
+        self.launches += 1
+        weights = None
+        if return_weights:
+            weights = torch.empty((B, N, self.feat_dim, H, W), dtype=torch.float32, device=self.device)
+        fused = self.merge(ws, all_feat, offsets, B, N, weights)
+        pred = out.get('pred')
+        if pred is None:
+            pred = torch.empty((B, 3, H * self.up_r, W * self.up_r), dtype=torch.float32, device=self.device)
+        self.decode(ws, fused, pred)
+        return pred, offsets.view(B, N - 1, 2, H, W), weights

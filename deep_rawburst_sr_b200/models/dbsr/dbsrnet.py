@@ -1,0 +1,122 @@
+"""DBSRNet and its factory with the reference's interface (models/dbsr/dbsrnet.py:24-82).
+
+`DBSRNet(encoder, merging, decoder).forward(im [B, N, 4, H, W]) -> (pred [B, 3, 8H, 8W], {'offsets', 'fusion_weights'})`.
+When the three sub-modules are the B200 ones, the whole forward runs inside one `DBSREngine` in channels-last
+layout with no NCHW round trips between the stages; `state_dict()` keys equal the reference's.
+`fusion_weights` (a [B, N, 512, H, W] fp32 tensor no caller of the reference reads) is materialised only when
+`net.return_fusion_weights` is True (default False -> the key is present with value None).
+"""
+import os
+
+import torch
+import torch.nn as nn
+
+from ... import ops
+from ...admin.environment import env_settings
+from ...admin.model_constructor import model_constructor
+from ...engine import DBSREngine
+from ..alignment.pwcnet import PWCNet
+from . import decoders as dbsr_decoders
+from . import encoders as dbsr_encoders
+from . import merging as dbsr_merging
+
+
+class DBSRNet(nn.Module):
+    """ Deep Burst Super-Resolution model"""
+
+    def __init__(self, encoder, merging, decoder):
+        super().__init__()
+        self.encoder = encoder      # Encodes input images and performs alignment
+        self.merging = merging      # Merges the input embeddings to obtain a single feature map
+        self.decoder = decoder      # Decodes the merged embeddings to generate HR RGB image
+        self.precision = os.environ.get('DBSR_B200_PRECISION', 'bf16')
+        self.logits_fp32 = False
+        self.return_fusion_weights = False
+        self._engine = None
+
+    def _apply(self, fn, *a, **k):
+        self._engine = None
+        return super()._apply(fn, *a, **k)
+
+    def load_state_dict(self, *a, **k):
+        self._engine = None
+        return super().load_state_dict(*a, **k)
+
+    def set_precision(self, precision: str):
+        assert precision in ('bf16', 'fp32')
+        self.precision = precision
+        self._engine = None
+        return self
+
+    def _fused_path(self):
+        return (isinstance(self.encoder, dbsr_encoders.ResEncoderWarpAlignnet) and
+                isinstance(self.merging, dbsr_merging.WeightedSum) and
+                isinstance(self.decoder, dbsr_decoders.ResPixShuffleConv))
+
+    def engine(self, device):
+        e = self._engine
+        if e is None or e.device != torch.device(device) or e.precision != self.precision:
+            self._engine = DBSREngine(self.state_dict(), device, precision=self.precision,
+                                      offset_modulo=self.merging.offset_modulo,
+                                      gauss_kernel=self.decoder.gauss_taps(), logits_fp32=self.logits_fp32)
+        return self._engine
+
+    @torch.no_grad()
+    def forward(self, im):
+        if not self._fused_path():
+            out_enc = self.encoder(im)
+            out_merge = self.merging(out_enc)
+            out_dec = self.decoder(out_merge)
+            return out_dec['pred'], {'offsets': out_enc['offsets'], 'fusion_weights': out_merge['fusion_weights']}
+        ops.require_device(im)
+        pred, offsets, weights = self.engine(im.device).forward(im, return_weights=self.return_fusion_weights)
+        return pred, {'offsets': offsets, 'fusion_weights': weights}
+
+
+@model_constructor
+def dbsrnet_cvpr2021(enc_init_dim, enc_num_res_blocks, enc_out_dim,
+                     dec_init_conv_dim, dec_num_pre_res_blocks, dec_post_conv_dim, dec_num_post_res_blocks,
+                     upsample_factor=2, activation='relu', train_alignmentnet=False,
+                     offset_feat_dim=64,
+                     weight_pred_proj_dim=32,
+                     num_offset_feat_extractor_res=1,
+                     num_weight_predictor_res=1,
+                     offset_modulo=1.0,
+                     use_offset=True,
+                     ref_offset_noise=0.0,
+                     softmax=True,
+                     use_base_frame=True,
+                     icnrinit=False,
+                     gauss_blur_sd=None,
+                     gauss_ksz=3,
+                     load_pretrained_alignment=True,
+                     ):
+    """Same arguments as the reference factory (dbsrnet.py:41-82).  `load_pretrained_alignment=False` (extension)
+    skips loading `<pretrained_nets_dir>/pwcnet-network-default.pth` for random-init / checkpoint-restore use."""
+    if load_pretrained_alignment:
+        alignment_net = PWCNet(load_pretrained=True,
+                               weights_path='{}/pwcnet-network-default.pth'.format(env_settings().pretrained_nets_dir))
+    else:
+        alignment_net = PWCNet(load_pretrained=False)
+    encoder = dbsr_encoders.ResEncoderWarpAlignnet(enc_init_dim, enc_num_res_blocks, enc_out_dim, alignment_net,
+                                                   activation=activation, train_alignmentnet=train_alignmentnet)
+    merging = dbsr_merging.WeightedSum(enc_out_dim, weight_pred_proj_dim, offset_feat_dim,
+                                       num_offset_feat_extractor_res=num_offset_feat_extractor_res,
+                                       num_weight_predictor_res=num_weight_predictor_res,
+                                       offset_modulo=offset_modulo, use_offset=use_offset,
+                                       ref_offset_noise=ref_offset_noise, softmax=softmax,
+                                       use_base_frame=use_base_frame)
+    decoder = dbsr_decoders.ResPixShuffleConv(enc_out_dim, dec_init_conv_dim, dec_num_pre_res_blocks,
+                                              dec_post_conv_dim, dec_num_post_res_blocks,
+                                              upsample_factor=upsample_factor, activation=activation,
+                                              gauss_blur_sd=gauss_blur_sd, icnrinit=icnrinit, gauss_ksz=gauss_ksz)
+    return DBSRNet(encoder=encoder, merging=merging, decoder=decoder)
+
+
+def dbsrnet_default_synthetic(load_pretrained_alignment=False):
+    """The architecture of train_settings/dbsr/default_synthetic.py:73-82 (the only configuration of the path)."""
+    return dbsrnet_cvpr2021(enc_init_dim=64, enc_num_res_blocks=9, enc_out_dim=512, dec_init_conv_dim=64,
+                            dec_num_pre_res_blocks=5, dec_post_conv_dim=32, dec_num_post_res_blocks=4,
+                            upsample_factor=8, offset_feat_dim=64, weight_pred_proj_dim=64,
+                            num_weight_predictor_res=3, gauss_blur_sd=1.0, icnrinit=True,
+                            load_pretrained_alignment=load_pretrained_alignment)

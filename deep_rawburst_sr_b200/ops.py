@@ -1,0 +1,193 @@
+"""Thin torch-tensor wrappers over the C ABI (include/dbsr_b200.h).  PyTorch is used for device memory and
+streams only; every op below launches a hand-written sm_100a kernel from libdbsr_b200.so on the current
+torch stream.  Nothing here has a CPU / eager-PyTorch fallback: CPU tensors raise.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Optional
+
+import torch
+
+from . import _lib
+from ._lib import ACT_LRELU, ACT_NONE, ACT_RELU, DBSR_BF16, DBSR_F32, ConvDesc, NhwcView  # noqa: F401
+
+_checked_devices = set()
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def require_device(t: torch.Tensor) -> None:
+    """Fail loudly on anything but a CUDA tensor on an sm_100 device (reference behaviour for the cost volume on
+    CPU input is NotImplementedError, external/pwcnet/correlation/correlation.py:324-325)."""
+    if not t.is_cuda:
+        raise NotImplementedError('deep_rawburst_sr_b200 runs on CUDA (sm_100a) tensors only; there is no CPU path')
+    idx = t.device.index if t.device.index is not None else torch.cuda.current_device()
+    if idx not in _checked_devices:
+        _lib.check(_lib.load_library().dbsr_device_check(idx), 'dbsr_device_check')
+        _checked_devices.add(idx)
+
+
+class Act:
+    """Channels-last activation view: a channel slice [c_off, c_off + c) of a [n, h, w, c_pitch] torch buffer."""
+
+    __slots__ = ('buf', 'n', 'h', 'w', 'c', 'c_off')
+
+    def __init__(self, buf: torch.Tensor, c_off: int = 0, c: Optional[int] = None):
+        assert buf.dim() == 4 and buf.is_contiguous(), 'Act needs a contiguous [n,h,w,c] buffer'
+        assert buf.dtype in (torch.float32, torch.bfloat16)
+        self.buf = buf
+        self.n, self.h, self.w = buf.shape[0], buf.shape[1], buf.shape[2]
+        self.c_off = c_off
+        self.c = buf.shape[3] - c_off if c is None else c
+        assert 0 <= self.c_off and self.c_off + self.c <= buf.shape[3]
+
+    @staticmethod
+    def empty(n, h, w, c, dtype, device, zero: bool = False):
+        f = torch.zeros if zero else torch.empty
+        return Act(f((n, h, w, c), dtype=dtype, device=device))
+
+    def slice(self, c_off: int, c: int) -> 'Act':
+        return Act(self.buf, self.c_off + c_off, c)
+
+    def images(self, start: int, count: int) -> 'Act':
+        return Act(self.buf[start:start + count], self.c_off, self.c)
+
+    @property
+    def dtype(self):
+        return self.buf.dtype
+
+    def view(self) -> NhwcView:
+        return NhwcView(self.buf.data_ptr(), self.n, self.h, self.w, self.c, self.c_off, self.buf.shape[3],
+                        DBSR_F32 if self.buf.dtype == torch.float32 else DBSR_BF16)
+
+    def to_nchw(self) -> torch.Tensor:
+        out = torch.empty((self.n, self.c, self.h, self.w), dtype=torch.float32, device=self.buf.device)
+        v = self.view()
+        _lib.check(_lib.load_library().dbsr_nhwc_to_nchw(ctypes.byref(v), out.data_ptr(), _stream()), 'nhwc_to_nchw')
+        return out
+
+    def from_nchw(self, src: torch.Tensor) -> 'Act':
+        assert src.dtype == torch.float32 and src.is_contiguous() and tuple(src.shape) == (self.n, self.c, self.h, self.w)
+        v = self.view()
+        _lib.check(_lib.load_library().dbsr_nchw_to_nhwc(src.data_ptr(), ctypes.byref(v), _stream()), 'nchw_to_nhwc')
+        return self
+
+
+_NULL_VIEW = NhwcView(None, 0, 0, 0, 0, 0, 0, 0)
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def conv2d(x: Act, w: torch.Tensor, bias: Optional[torch.Tensor], y: Act, ksize: int, stride: int = 1, dilation: int = 1,
+           act: int = ACT_NONE, residual: Optional[Act] = None, shuffle_r: int = 0, tensor_core: bool = False) -> Act:
+    d = ConvDesc(x.view(), y.view(), residual.view() if residual is not None else _NULL_VIEW, w.data_ptr(),
+                 _ptr(bias), ksize, stride, dilation, act, shuffle_r)
+    lib = _lib.load_library()
+    if tensor_core:
+        _lib.check(lib.dbsr_conv2d_tc(ctypes.byref(d), _stream()), 'dbsr_conv2d_tc')
+    else:
+        _lib.check(lib.dbsr_conv2d_direct(ctypes.byref(d), _stream()), 'dbsr_conv2d_direct')
+    return y
+
+
+def conv2d_tc_supported(x: Act, w: torch.Tensor, bias, y: Act, ksize: int, stride: int = 1, dilation: int = 1,
+                        residual: Optional[Act] = None, shuffle_r: int = 0) -> bool:
+    d = ConvDesc(x.view(), y.view(), residual.view() if residual is not None else _NULL_VIEW, w.data_ptr(),
+                 _ptr(bias), ksize, stride, dilation, 0, shuffle_r)
+    return bool(_lib.load_library().dbsr_conv2d_tc_supported(ctypes.byref(d)))
+
+
+def deconv4x4s2(x: Act, w: torch.Tensor, bias: torch.Tensor, y: Act, y2: Optional[Act] = None) -> Act:
+    xv, yv = x.view(), y.view()
+    y2v = y2.view() if y2 is not None else _NULL_VIEW
+    _lib.check(_lib.load_library().dbsr_deconv4x4s2(ctypes.byref(xv), w.data_ptr(), bias.data_ptr(), ctypes.byref(yv),
+                                                    ctypes.byref(y2v), _stream()), 'dbsr_deconv4x4s2')
+    return y
+
+
+def corr81(f1: Act, f2: Act, out: Act, pairs: int, group: int = 0, flow: Optional[Act] = None, flow_scale: float = 0.0,
+           act: int = ACT_NONE) -> Act:
+    a, b, o = f1.view(), f2.view(), out.view()
+    fl = flow.view() if flow is not None else _NULL_VIEW
+    _lib.check(_lib.load_library().dbsr_corr81(ctypes.byref(a), ctypes.byref(b), ctypes.byref(fl), float(flow_scale),
+                                               ctypes.byref(o), pairs, group, act, _stream()), 'dbsr_corr81')
+    return out
+
+
+def copy_channels(src: Act, dst: Act, group: int = 0, src_group: int = 0, src_first: int = 0) -> Act:
+    s, d = src.view(), dst.view()
+    _lib.check(_lib.load_library().dbsr_copy_channels(ctypes.byref(s), ctypes.byref(d), group, src_group, src_first,
+                                                      _stream()), 'dbsr_copy_channels')
+    return dst
+
+
+def prep_burst(burst: torch.Tensor, enc_in: Act, pwc_in: Act) -> None:
+    assert burst.dtype == torch.float32 and burst.is_contiguous() and burst.dim() == 5 and burst.shape[2] == 4
+    frames = burst.shape[0] * burst.shape[1]
+    e, p = enc_in.view(), pwc_in.view()
+    _lib.check(_lib.load_library().dbsr_prep_burst(burst.data_ptr(), frames, burst.shape[3], burst.shape[4],
+                                                   ctypes.byref(e), ctypes.byref(p), _stream()), 'dbsr_prep_burst')
+
+
+def flow_head(flow4: Act, offsets: torch.Tensor, H: int, W: int, Hp: int, Wp: int) -> torch.Tensor:
+    assert offsets.dtype == torch.float32 and offsets.is_contiguous() and tuple(offsets.shape) == (flow4.n, 2, H, W)
+    v = flow4.view()
+    _lib.check(_lib.load_library().dbsr_flow_head(ctypes.byref(v), offsets.data_ptr(), H, W, Hp, Wp, _stream()),
+               'dbsr_flow_head')
+    return offsets
+
+
+def warp(feat: Act, offsets: torch.Tensor, out: Act, frames: int = 0) -> Act:
+    assert offsets.dtype == torch.float32 and offsets.is_contiguous()
+    f, o = feat.view(), out.view()
+    _lib.check(_lib.load_library().dbsr_warp(ctypes.byref(f), offsets.data_ptr(), ctypes.byref(o), frames, _stream()),
+               'dbsr_warp')
+    return out
+
+
+def offsets_mod(offsets: torch.Tensor, out: Act, bursts: int, frames: int, modulo: float) -> Act:
+    assert offsets.dtype == torch.float32 and offsets.is_contiguous()
+    o = out.view()
+    _lib.check(_lib.load_library().dbsr_offsets_mod(offsets.data_ptr(), ctypes.byref(o), bursts, frames, float(modulo),
+                                                    _stream()), 'dbsr_offsets_mod')
+    return out
+
+
+def build_wp_input(proj: Act, wp_in: Act, frames: int) -> Act:
+    p, w = proj.view(), wp_in.view()
+    _lib.check(_lib.load_library().dbsr_build_wp_input(ctypes.byref(p), ctypes.byref(w), frames, _stream()),
+               'dbsr_build_wp_input')
+    return wp_in
+
+
+def softmax_wsum(feat: Act, logits: Act, fused: Act, frames: int, offsets: Optional[torch.Tensor] = None,
+                 weights_out: Optional[torch.Tensor] = None) -> Act:
+    if offsets is not None:
+        assert offsets.dtype == torch.float32 and offsets.is_contiguous()
+    if weights_out is not None:
+        assert weights_out.dtype == torch.float32 and weights_out.is_contiguous()
+    f, l, o = feat.view(), logits.view(), fused.view()
+    _lib.check(_lib.load_library().dbsr_softmax_wsum(ctypes.byref(f), ctypes.byref(l), _ptr(offsets), ctypes.byref(o),
+                                                     _ptr(weights_out), frames, _stream()), 'dbsr_softmax_wsum')
+    return fused
+
+
+def blur3x3(x: Act, y: Act, k9) -> Act:
+    arr = (ctypes.c_float * 9)(*[float(v) for v in k9])
+    xv, yv = x.view(), y.view()
+    _lib.check(_lib.load_library().dbsr_blur3x3(ctypes.byref(xv), ctypes.byref(yv), arr, _stream()), 'dbsr_blur3x3')
+    return y
+
+
+def predictor(x: Act, w: torch.Tensor, bias: Optional[torch.Tensor], pred: torch.Tensor) -> torch.Tensor:
+    cout = w.shape[0]
+    assert pred.dtype == torch.float32 and pred.is_contiguous() and tuple(pred.shape) == (x.n, cout, x.h, x.w)
+    v = x.view()
+    _lib.check(_lib.load_library().dbsr_predictor(ctypes.byref(v), w.data_ptr(), _ptr(bias), cout, pred.data_ptr(),
+                                                  _stream()), 'dbsr_predictor')
+    return pred

@@ -124,10 +124,11 @@ int dbsr_flow_head(const dbsr_nhwc_t* flow4, float* offsets, int32_t H, int32_t 
 /* -------------------------------------------------------------------------------------------------- */
 /* fusion                                                                                              */
 /* -------------------------------------------------------------------------------------------------- */
-/* warp (models/layers/warp.py:19-46): out[p] = bilinear(feat[img(p)], (x + fx, y + fy)), zeros outside.
- *   offsets: [P, 2, H, W] fp32 NCHW; img(p) as in dbsr_corr81's i2 mapping.                            */
-int dbsr_warp(const dbsr_nhwc_t* feat, const float* offsets, const dbsr_nhwc_t* out, int32_t pairs,
-              int32_t group, void* stream);
+/* warp (models/layers/warp.py:19-46): out[f] = bilinear(feat[f], (x + fx, y + fy)), zeros outside.
+ *   offsets: [P, 2, H, W] fp32 NCHW.  frames == 0: plain mode, image f uses offsets[f].
+ *   frames = N > 0: burst mode over B*N images: frame 0 of each burst is copied (the reference frame,
+ *   models/dbsr/merging.py:72 `cat(ref_feat, oth_feat)`), frame n > 0 uses offsets[b*(N-1) + n-1].       */
+int dbsr_warp(const dbsr_nhwc_t* feat, const float* offsets, const dbsr_nhwc_t* out, int32_t frames, void* stream);
 /* merging.py:91-105: [B*N, H, W, >=2] <- (frame 0: zeros; others: offsets mod 1.0, floor-mod)          */
 int dbsr_offsets_mod(const float* offsets, const dbsr_nhwc_t* out, int32_t bursts, int32_t frames,
                      float modulo, void* stream);

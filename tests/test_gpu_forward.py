@@ -1,0 +1,132 @@
+"""GPU: end-to-end parity of the B200 path (through the drop-in DBSRNet module -> DBSREngine -> C ABI) against the
+CPU oracle and against the golden vectors produced by the reference's own modules.
+
+Tolerances (BASELINE.json north_star): fp32 path max-abs <= 1e-4 on pred in [0,1]; bf16 tensor-core path
+max-abs <= 1e-2 and |PSNR(new, gt) - PSNR(ref, gt)| <= 0.02 dB against a seeded pseudo ground truth."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import dbsr_oracle as O  # noqa: E402
+
+
+@pytest.fixture(scope='module')
+def dev():
+    if not torch.cuda.is_available():
+        pytest.skip('needs a CUDA device')
+    return torch.device('cuda:0')
+
+
+def _net(sd, dev, precision):
+    from deep_rawburst_sr_b200.models.dbsr.dbsrnet import dbsrnet_default_synthetic
+    net = dbsrnet_default_synthetic()
+    net.load_state_dict(sd, strict=True)
+    net = net.to(dev).eval()
+    net.set_precision(precision)
+    net.return_fusion_weights = True
+    return net
+
+
+GOLDEN = ['tiny_b1n3_16x16', 'rect_b2n4_24x40', 'cfg1_b1n14_48x48']
+
+
+@pytest.mark.parametrize('name', GOLDEN)
+def test_fp32_path_against_reference_golden(dev, golden_dir, name):
+    g = np.load(os.path.join(golden_dir, name + '.npz'))
+    wseed, bseed, B, N, H, W = [int(v) for v in g['meta']]
+    sd = O.make_state_dict(wseed, pwc_gain=float(g['pwc_gain'][0]))
+    net = _net(sd, dev, 'fp32')
+    burst = O.make_burst(bseed, B, N, H, W)
+    pred, aux = net(burst.to(dev))
+    pred = pred.cpu()
+    assert tuple(pred.shape) == (B, 3, 8 * H, 8 * W)
+    assert np.abs(aux['offsets'].cpu().numpy() - g['offsets']).max() < 1e-3      # pixels
+    if 'pred' in g:
+        assert np.abs(pred.numpy() - g['pred']).max() <= 1e-4
+    else:
+        assert np.abs(pred[:, :, ::2, ::2].numpy() - g['pred_sub']).max() <= 1e-4
+    fw = aux['fusion_weights'].cpu()
+    assert np.abs(fw[:, :, ::37, ::3, ::3].numpy() - g['fusion_weights_sub']).max() < 1e-4
+
+
+def test_fp32_path_stress_flows_against_oracle(dev):
+    """multi-pixel flows (PWC weights x2.2): exercises out-of-bounds taps, the backwarp mask and the modulo"""
+    sd = O.make_state_dict(2, pwc_gain=2.2)
+    burst = O.make_burst(2, 1, 5, 32, 32)
+    ref_pred, ref_aux = O.dbsr_forward(burst, sd)
+    net = _net(sd, dev, 'fp32')
+    pred, aux = net(burst.to(dev))
+    flow_err = (aux['offsets'].cpu() - ref_aux['offsets']).abs().max().item()
+    assert float(ref_aux['offsets'].abs().max()) > 2.0
+    assert flow_err < 2e-2, flow_err
+    # `offsets % 1.0` is discontinuous: compare away from pixels whose flow sits within flow_err of an integer
+    err = (pred.cpu() - ref_pred).abs()
+    assert err.mean().item() < 1e-5 and (err > 1e-4).float().mean().item() < 2e-3, (err.max().item(), err.mean().item())
+
+
+@pytest.mark.parametrize('shape', [(1, 14, 48, 48), (2, 5, 16, 24), (1, 2, 24, 24)])
+def test_bf16_path_tolerance(dev, shape):
+    B, N, H, W = shape
+    sd = O.make_state_dict(0)
+    burst = O.make_burst(7, B, N, H, W)
+    ref_pred, ref_aux = O.dbsr_forward(burst, sd)
+    net = _net(sd, dev, 'bf16')
+    pred, aux = net(burst.to(dev))
+    pred = pred.cpu()
+    max_abs = (pred - ref_pred).abs().max().item()
+    assert max_abs <= 1e-2, max_abs
+    gt = torch.rand(ref_pred.shape, generator=torch.Generator().manual_seed(99))
+    bi = 40 if min(8 * H, 8 * W) > 100 else 0
+    d_psnr = abs(O.psnr(pred, gt, bi) - O.psnr(ref_pred, gt, bi))
+    assert d_psnr <= 0.02, d_psnr
+    assert (aux['offsets'].cpu() - ref_aux['offsets']).abs().max().item() < 1e-3   # PWC-Net stays fp32
+    frac = ((pred - ref_pred).abs() <= 1e-2).float().mean().item()
+    assert frac >= 0.95
+
+
+def test_batch_invariance_and_reuse(dev):
+    """burst i gives bit-identical output alone, in a batch and on a second call (workspace reuse)"""
+    sd = O.make_state_dict(0)
+    net = _net(sd, dev, 'bf16')
+    net.return_fusion_weights = False
+    burst = O.make_burst(5, 3, 4, 16, 16).to(dev)
+    p_all, aux = net(burst)
+    assert aux['fusion_weights'] is None
+    p_all = p_all.clone()
+    p_again, _ = net(burst)
+    assert torch.equal(p_all, p_again)
+    for i in range(3):
+        p_i, _ = net(burst[i:i + 1])
+        assert torch.equal(p_i[0], p_all[i])
+
+
+def test_module_seams_match_fused_path(dev):
+    """encoder -> merging -> decoder called one by one (NCHW dict seams of the reference) == fused engine path"""
+    sd = O.make_state_dict(1)
+    net = _net(sd, dev, 'fp32')
+    burst = O.make_burst(3, 1, 3, 16, 16).to(dev)
+    pred, aux = net(burst)
+    for m in (net.encoder, net.merging, net.decoder):
+        m.precision = 'fp32'
+    enc = net.encoder(burst)
+    assert tuple(enc['oth_feat'].shape) == (1, 2, 512, 16, 16) and tuple(enc['ref_feat'].shape) == (1, 2, 512, 16, 16)
+    mer = net.merging(enc)
+    dec = net.decoder(mer)
+    assert (dec['pred'] - pred).abs().max().item() < 1e-5
+    assert (enc['offsets'] - aux['offsets']).abs().max().item() < 1e-6
+    # PWCNet seam: flow target->source
+    x_rgb = O.rggb_to_rgb(burst.cpu())
+    ref_flow = O.pwcnet_forward(x_rgb[:, 1:].reshape(-1, 3, 16, 16), x_rgb[:, :1].repeat(1, 2, 1, 1, 1).reshape(-1, 3, 16, 16), sd)
+    flow = net.encoder.alignment_net(x_rgb[:, 1:].reshape(-1, 3, 16, 16).to(dev),
+                                     x_rgb[:, :1].repeat(1, 2, 1, 1, 1).reshape(-1, 3, 16, 16).to(dev))
+    assert (flow.cpu() - ref_flow).abs().max().item() < 1e-4
+
+
+def test_cpu_input_is_refused(dev):
+    net = _net(O.make_state_dict(0), dev, 'bf16')
+    with pytest.raises(NotImplementedError):
+        net(O.make_burst(0, 1, 2, 16, 16))

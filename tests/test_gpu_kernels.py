@@ -1,0 +1,290 @@
+"""GPU: per-kernel parity of the C-ABI entry points against the CPU oracle (oracle/dbsr_oracle.py) on seeded
+inputs.  fp32 kernels: tolerance is fp32 round-off of a re-associated sum (stated per test)."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+from oracle import dbsr_oracle as O  # noqa: E402
+
+
+@pytest.fixture(scope='module')
+def dev():
+    if not torch.cuda.is_available():
+        pytest.skip('needs a CUDA device')
+    from deep_rawburst_sr_b200 import ops
+    ops.require_device(torch.empty(1, device='cuda:0'))
+    return torch.device('cuda:0')
+
+
+def _gen(seed):
+    return torch.Generator().manual_seed(seed)
+
+
+def _act_from(x_nchw, dev, dtype=torch.float32, pitch=None, c_off=0):
+    from deep_rawburst_sr_b200.ops import Act
+    n, c, h, w = x_nchw.shape
+    pitch = pitch or c
+    buf = Act(torch.zeros((n, h, w, pitch), dtype=dtype, device=dev))
+    v = buf.slice(c_off, c)
+    v.from_nchw(x_nchw.to(dev).contiguous())
+    return v
+
+
+def test_layout_roundtrip(dev):
+    x = torch.randn(3, 37, 9, 11, generator=_gen(0))
+    for dtype, tol in ((torch.float32, 0.0), (torch.bfloat16, 2e-2)):
+        v = _act_from(x, dev, dtype=dtype, pitch=48, c_off=8)
+        back = v.to_nchw().cpu()
+        assert (back - x).abs().max() <= tol
+        assert float(v.buf[..., :8].float().abs().max()) == 0.0 and float(v.buf[..., 45:].float().abs().max()) == 0.0
+
+
+CONV_CASES = [
+    # cin, cout, k, stride, dil, n, h, w, act, residual
+    (3, 16, 3, 2, 1, 2, 64, 64, 2, False),
+    (16, 16, 3, 1, 1, 2, 32, 32, 2, False),
+    (81, 128, 3, 1, 1, 5, 2, 2, 2, False),
+    (117, 128, 3, 1, 1, 2, 16, 16, 2, False),
+    (565, 2, 3, 1, 1, 2, 16, 16, 0, True),
+    (128, 128, 3, 1, 2, 2, 16, 16, 2, False),
+    (96, 64, 3, 1, 16, 1, 16, 16, 2, False),
+    (64, 64, 3, 1, 1, 2, 24, 40, 1, True),
+    (512, 64, 1, 1, 1, 2, 12, 12, 1, False),
+    (4, 64, 3, 1, 1, 3, 16, 16, 1, False),
+    (196, 196, 3, 1, 1, 3, 1, 1, 2, False),
+    (32, 3, 1, 1, 1, 1, 16, 16, 1, False),
+]
+
+
+@pytest.mark.parametrize('case', CONV_CASES)
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
+def test_conv2d_direct(dev, case, dtype):
+    from deep_rawburst_sr_b200 import ops
+    from deep_rawburst_sr_b200.engine import pack_direct
+    cin, cout, k, stride, dil, n, h, w, act, use_res = case
+    g = _gen(hash(case) % 1000)
+    x = torch.randn(n, cin, h, w, generator=g)
+    wt = torch.randn(cout, cin, k, k, generator=g) / (cin * k * k) ** 0.5
+    b = torch.randn(cout, generator=g)
+    if dtype == torch.bfloat16:
+        x = x.bfloat16().float()
+    pad = dil * (k - 1) // 2
+    ref = F.conv2d(x, wt, b, stride=stride, padding=pad, dilation=dil)
+    res = torch.randn(ref.shape, generator=g) if use_res else None
+    if res is not None:
+        if dtype == torch.bfloat16:
+            res = res.bfloat16().float()
+        ref = ref + res
+    ref = torch.relu(ref) if act == 1 else (O.lrelu(ref) if act == 2 else ref)
+    xa = _act_from(x, dev, dtype=dtype, pitch=cin + 5, c_off=3)      # unaligned slice on purpose
+    ya = ops.Act(torch.zeros((n, ref.shape[2], ref.shape[3], cout + 8), dtype=torch.float32, device=dev)).slice(8, cout)
+    ra = _act_from(res, dev, dtype=dtype) if res is not None else None
+    ops.conv2d(xa, pack_direct(wt.to(dev)), b.to(dev), ya, k, stride, dil, act, ra)
+    got = ya.to_nchw().cpu()
+    assert (got - ref).abs().max() < 2e-4 * max(1.0, float(ref.abs().max()))
+    assert float(ya.buf[..., :8].abs().max()) == 0.0   # neighbours of the slice untouched
+
+
+def test_conv2d_direct_pixel_shuffle(dev):
+    from deep_rawburst_sr_b200 import ops
+    from deep_rawburst_sr_b200.engine import pack_direct
+    g = _gen(5)
+    x = torch.randn(2, 64, 6, 5, generator=g)
+    wt = torch.randn(2048, 64, 1, 1, generator=g) / 8
+    ref = O.pixel_shuffle(torch.relu(F.conv2d(x, wt)), 8)
+    xa = _act_from(x, dev)
+    ya = ops.Act.empty(2, 48, 40, 32, torch.float32, dev)
+    ops.conv2d(xa, pack_direct(wt.to(dev)), None, ya, 1, 1, 1, ops.ACT_RELU, None, shuffle_r=8)
+    assert (ya.to_nchw().cpu() - ref).abs().max() < 1e-5
+
+
+@pytest.mark.parametrize('cin,h,w', [(2, 4, 4), (529, 1, 1), (661, 2, 3), (597, 8, 8)])
+def test_deconv4x4s2(dev, cin, h, w):
+    from deep_rawburst_sr_b200 import ops
+    from deep_rawburst_sr_b200.engine import pack_deconv
+    g = _gen(cin)
+    x = torch.randn(3, cin, h, w, generator=g)
+    wt = torch.randn(cin, 2, 4, 4, generator=g) / (cin * 4) ** 0.5
+    b = torch.randn(2, generator=g)
+    ref = F.conv_transpose2d(x, wt, b, stride=2, padding=1)
+    assert torch.allclose(O.deconv4x4s2(x, wt, b), ref, atol=1e-5)
+    xa = _act_from(x, dev)
+    ya = ops.Act.empty(3, 2 * h, 2 * w, 16, torch.float32, dev, zero=True).slice(8, 2)
+    y2 = ops.Act.empty(3, 2 * h, 2 * w, 2, torch.float32, dev)
+    ops.deconv4x4s2(xa, pack_deconv(wt.to(dev)), b.to(dev), ya, y2)
+    assert (ya.to_nchw().cpu() - ref).abs().max() < 1e-4
+    assert (y2.to_nchw().cpu() - ref).abs().max() < 1e-4
+
+
+CORR_SHAPES = [(196, 1, 1), (128, 2, 2), (96, 4, 4), (64, 8, 8), (32, 16, 16), (32, 48, 48), (6, 5, 7), (64, 20, 33),
+               (196, 3, 3), (128, 6, 6)]
+
+
+@pytest.mark.parametrize('c,h,w', CORR_SHAPES)
+def test_corr81_plain(dev, c, h, w):
+    """every PWC level shape of the 48^2 / 80^2 / 96^2 / 160^2 / 256^2 configs incl. C=196, h=1"""
+    from deep_rawburst_sr_b200 import ops
+    g = _gen(c * 100 + h)
+    f1 = torch.randn(3, c, h, w, generator=g)
+    f2 = torch.randn(3, c, h, w, generator=g)
+    ref = O.correlation81(f1, f2)
+    out = ops.Act.empty(3, h, w, 96, torch.float32, dev, zero=True).slice(8, 81)
+    ops.corr81(_act_from(f1, dev), _act_from(f2, dev), out, pairs=3, group=0)
+    assert (out.to_nchw().cpu() - ref).abs().max() < 2e-5
+    ref_l = O.lrelu(ref)
+    ops.corr81(_act_from(f1, dev), _act_from(f2, dev), out, pairs=3, group=0, act=ops.ACT_LRELU)
+    assert (out.to_nchw().cpu() - ref_l).abs().max() < 2e-5
+
+
+def test_corr81_golden_reference_vector(dev, golden_dir):
+    """the vector produced by the reference module's own code path (tests/golden/ops.npz)"""
+    import os
+    from deep_rawburst_sr_b200.external.pwcnet.correlation import correlation
+    gold = np.load(os.path.join(golden_dir, 'ops.npz'))
+    f1 = torch.from_numpy(gold['corr_f1']).to(dev)
+    f2 = torch.from_numpy(gold['corr_f2']).to(dev)
+    got = correlation.FunctionCorrelation(tenFirst=f1, tenSecond=f2).cpu().numpy()
+    assert got.shape == gold['corr'].shape and np.abs(got - gold['corr']).max() < 2e-6
+    with pytest.raises(NotImplementedError):
+        correlation.FunctionCorrelation(tenFirst=f1.cpu(), tenSecond=f2.cpu())
+
+
+@pytest.mark.parametrize('c,h,w,mag', [(32, 16, 16, 3.0), (64, 8, 8, 6.0), (128, 2, 2, 1.0), (96, 4, 5, 30.0), (32, 32, 24, 6.0)])
+def test_corr81_backwarp_burst_mapping(dev, c, h, w, mag):
+    """fused backwarp (flows up to +-mag px, incl. all taps out of bounds) + burst pair->image mapping"""
+    from deep_rawburst_sr_b200 import ops
+    g = _gen(c + h)
+    B, N = 2, 4
+    feats = torch.randn(B * N, c, h, w, generator=g)
+    flow = (torch.rand(B * (N - 1), 2, h, w, generator=g) * 2 - 1) * mag
+    scale = 1.25
+    f1 = feats.view(B, N, c, h, w)[:, :1].expand(-1, N - 1, -1, -1, -1).reshape(-1, c, h, w)
+    f2 = feats.view(B, N, c, h, w)[:, 1:].reshape(-1, c, h, w)
+    ref = O.lrelu(O.correlation81(f1, O.backwarp(f2, flow * scale)))
+    fa = _act_from(feats, dev)
+    out = ops.Act.empty(B * (N - 1), h, w, 81, torch.float32, dev)
+    ops.corr81(fa, fa, out, pairs=B * (N - 1), group=N - 1, flow=_act_from(flow, dev), flow_scale=scale,
+               act=ops.ACT_LRELU)
+    got = out.to_nchw().cpu()
+    err = (got - ref).abs()
+    # the 0.999 mask is a discontinuity: allow a handful of pixels to flip, everything else to fp32 round-off
+    bad = (err > 5e-5).any(dim=1).float().mean()
+    assert bad < 0.01, float(err.max())
+
+
+def test_prep_burst_and_flow_head(dev):
+    from deep_rawburst_sr_b200 import ops
+    g = _gen(11)
+    burst = torch.rand(2, 3, 4, 24, 40, generator=g)
+    enc_in = ops.Act.empty(6, 24, 40, 8, torch.float32, dev)
+    pwc_in = ops.Act.empty(6, 64, 64, 4, torch.float32, dev)
+    ops.prep_burst(burst.to(dev), enc_in, pwc_in)
+    assert (enc_in.slice(0, 4).to_nchw().cpu() - burst.view(6, 4, 24, 40)).abs().max() == 0
+    assert float(enc_in.buf[..., 4:].abs().max()) == 0
+    ref = O.resize_bilinear(O.rggb_to_rgb(burst).view(6, 3, 24, 40), 64, 64)
+    assert (pwc_in.slice(0, 3).to_nchw().cpu() - ref).abs().max() < 1e-6
+    flow4 = torch.randn(5, 2, 16, 16, generator=g)
+    offsets = torch.empty(5, 2, 24, 40, device=dev)
+    ops.flow_head(_act_from(flow4, dev), offsets, 24, 40, 64, 64)
+    ref = 20.0 * O.resize_bilinear(flow4, 24, 40)
+    ref = torch.stack((ref[:, 0] * (40 / 64.0), ref[:, 1] * (24 / 64.0)), 1)
+    assert (offsets.cpu() - ref).abs().max() < 1e-5
+
+
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
+def test_warp(dev, dtype, golden_dir):
+    import os
+    from deep_rawburst_sr_b200 import ops
+    from deep_rawburst_sr_b200.models.layers.warp import warp as warp_b200
+    gold = np.load(os.path.join(golden_dir, 'ops.npz'))
+    if dtype == torch.float32:
+        got = warp_b200(torch.from_numpy(gold['feat']).to(dev), torch.from_numpy(gold['flow']).to(dev)).cpu().numpy()
+        assert np.abs(got - gold['warp']).max() < 2e-5
+    g = _gen(3)
+    B, N, C, H, W = 2, 3, 64, 12, 20
+    feat = torch.randn(B * N, C, H, W, generator=g)
+    if dtype == torch.bfloat16:
+        feat = feat.bfloat16().float()
+    offs = (torch.rand(B * (N - 1), 2, H, W, generator=g) * 2 - 1) * 6.0
+    offs[0, :, 0, 0] = torch.tensor([-100.0, 50.0])
+    fa = _act_from(feat, dev, dtype=dtype)
+    out = ops.Act.empty(B * N, H, W, C, dtype, dev)
+    ops.warp(fa, offs.to(dev), out, frames=N)
+    f5 = feat.view(B, N, C, H, W)
+    ref = torch.cat([f5[:, :1], O.warp(f5[:, 1:].reshape(-1, C, H, W), offs).view(B, N - 1, C, H, W)], 1)
+    tol = 2e-5 if dtype == torch.float32 else 3e-2
+    assert (out.to_nchw().cpu() - ref.reshape(-1, C, H, W)).abs().max() < tol
+
+
+def test_offsets_mod_and_wp_input(dev):
+    from deep_rawburst_sr_b200 import ops
+    g = _gen(4)
+    B, N, H, W = 2, 3, 5, 7
+    offs = (torch.rand(B * (N - 1), 2, H, W, generator=g) * 2 - 1) * 3
+    offs[0, 0, 0, :5] = torch.tensor([-0.25, 1.75, -1e-9, 0.0, 3.0])
+    out = ops.Act.empty(B * N, H, W, 8, torch.float32, dev)
+    ops.offsets_mod(offs.to(dev), out, B, N, 1.0)
+    ref = torch.cat([torch.zeros(B, 1, 2, H, W), torch.remainder(offs, 1.0).view(B, N - 1, 2, H, W)], 1).view(-1, 2, H, W)
+    got = out.slice(0, 2).to_nchw().cpu()
+    assert torch.equal(got, ref), (got - ref).abs().max()
+    assert float(out.buf[..., 2:].abs().max()) == 0
+    proj = torch.randn(B * N, 16, H, W, generator=g)
+    wp = ops.Act.empty(B * N, H, W, 48, torch.float32, dev, zero=True)
+    ops.build_wp_input(_act_from(proj, dev), wp, N)
+    p5 = proj.view(B, N, 16, H, W)
+    refw = torch.cat([p5[:, :1].expand(-1, N, -1, -1, -1), p5 - p5[:, :1]], 2).reshape(B * N, 32, H, W)
+    assert torch.equal(wp.slice(0, 32).to_nchw().cpu(), refw)
+
+
+@pytest.mark.parametrize('with_offsets', [False, True])
+def test_softmax_wsum(dev, with_offsets):
+    from deep_rawburst_sr_b200 import ops
+    g = _gen(9)
+    B, N, C, H, W = 2, 5, 64, 6, 9
+    feat = torch.rand(B * N, C, H, W, generator=g)
+    logits = torch.randn(B * N, C, H, W, generator=g) * 3
+    logits[0, :, 0, 0] = 30.0
+    logits[1, :, 0, 0] = -30.0     # overflow guard
+    offs = (torch.rand(B * (N - 1), 2, H, W, generator=g) * 2 - 1) * 4
+    f5 = feat.view(B, N, C, H, W)
+    if with_offsets:
+        a5 = torch.cat([f5[:, :1], O.warp(f5[:, 1:].reshape(-1, C, H, W), offs).view(B, N - 1, C, H, W)], 1)
+    else:
+        a5 = f5
+    w = torch.softmax(logits.view(B, N, C, H, W), dim=1)
+    ref = (a5 * w).sum(1)
+    fused = ops.Act.empty(B, H, W, C, torch.float32, dev)
+    wout = torch.empty(B, N, C, H, W, device=dev)
+    ops.softmax_wsum(_act_from(feat, dev), _act_from(logits, dev), fused, N,
+                     offsets=offs.to(dev) if with_offsets else None, weights_out=wout)
+    assert (fused.to_nchw().cpu() - ref).abs().max() < 1e-5
+    assert (wout.cpu() - w).abs().max() < 1e-6
+
+
+def test_blur_and_predictor(dev):
+    from deep_rawburst_sr_b200 import ops
+    g = _gen(2)
+    x = torch.rand(2, 32, 16, 24, generator=g)
+    K = O.gauss_kernel3()
+    ref = F.conv2d(x.view(-1, 1, 16, 24), K.view(1, 1, 3, 3), padding=1).view(2, 32, 16, 24)
+    y = ops.Act.empty(2, 16, 24, 32, torch.float32, dev)
+    ops.blur3x3(_act_from(x, dev), y, K.reshape(-1).tolist())
+    assert (y.to_nchw().cpu() - ref).abs().max() < 1e-6
+    wt = torch.randn(3, 32, generator=g)
+    b = torch.randn(3, generator=g)
+    pred = torch.empty(2, 3, 16, 24, device=dev)
+    ops.predictor(_act_from(x, dev), wt.to(dev), b.to(dev), pred)
+    refp = torch.relu(F.conv2d(x, wt.view(3, 32, 1, 1), b))
+    assert (pred.cpu() - refp).abs().max() < 1e-5
+
+
+def test_backwarp_seam(dev, golden_dir):
+    import os
+    from deep_rawburst_sr_b200.models.alignment.pwcnet import backwarp
+    gold = np.load(os.path.join(golden_dir, 'ops.npz'))
+    got = backwarp(torch.from_numpy(gold['feat']).to(dev), torch.from_numpy(gold['flow']).to(dev)).cpu().numpy()
+    err = np.abs(got - gold['backwarp'])
+    assert (err > 5e-5).mean() < 0.01

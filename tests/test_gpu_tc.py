@@ -1,0 +1,83 @@
+"""GPU: the tcgen05 / TMEM implicit-GEMM convolution (dbsr_conv2d_tc) against a CPU fp32 convolution of the SAME
+bf16-rounded operands (so the only differences are fp32 accumulation order and the bf16 rounding of the output).
+Tolerance: 2^-8 relative to the output scale for bf16 outputs, 1e-4 for fp32 outputs."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+from oracle import dbsr_oracle as O  # noqa: E402
+
+# name: cin, cout, k, dil, n, h, w, act, residual, out_fp32, shuffle
+TC_CASES = {
+    'enc_res_64x64': (64, 64, 3, 1, 3, 48, 48, 1, True, False, 0),
+    'enc_init_4x64': (4, 64, 3, 1, 2, 16, 16, 1, False, False, 0),
+    'enc_out_64x512': (64, 512, 3, 1, 2, 16, 24, 1, False, False, 0),
+    'proj_1x1_512x64': (512, 64, 1, 1, 2, 16, 16, 1, False, False, 0),
+    'wp0_192x128': (192, 128, 3, 1, 2, 16, 16, 1, False, False, 0),
+    'wp_res_128x128': (128, 128, 3, 1, 2, 24, 40, 1, True, False, 0),
+    'wp_out_128x512_f32': (128, 512, 3, 1, 1, 16, 16, 0, False, True, 0),
+    'dec_init_512x64': (512, 64, 3, 1, 1, 16, 16, 1, False, False, 0),
+    'post_res_32x32': (32, 32, 3, 1, 1, 64, 64, 1, True, False, 0),
+    'ragged_20x13': (64, 64, 3, 1, 2, 20, 13, 2, False, False, 0),
+    'offset_2x64': (2, 64, 3, 1, 2, 16, 16, 1, False, False, 0),
+    'upsample_shuffle': (64, 2048, 1, 1, 2, 6, 5, 1, False, False, 8),
+    'dilated_d2': (128, 128, 3, 2, 1, 32, 32, 2, False, False, 0),
+}
+
+
+def run_case(name, dev):
+    from deep_rawburst_sr_b200 import ops
+    from deep_rawburst_sr_b200.engine import pack_tc
+    cin, cout, k, dil, n, h, w, act, use_res, out_f32, shuffle = TC_CASES[name]
+    g = torch.Generator().manual_seed(sum(map(ord, name)))
+    x = torch.randn(n, cin, h, w, generator=g).bfloat16().float()
+    wt = (torch.randn(cout, cin, k, k, generator=g) / (cin * k * k) ** 0.5).bfloat16().float()
+    b = torch.randn(cout, generator=g)
+    ref = F.conv2d(x, wt, b, padding=dil * (k - 1) // 2, dilation=dil)
+    res = None
+    if use_res:
+        res = torch.randn(ref.shape, generator=g).bfloat16().float()
+        ref = ref + res
+    ref = torch.relu(ref) if act == 1 else (O.lrelu(ref) if act == 2 else ref)
+    if shuffle:
+        ref = O.pixel_shuffle(ref, shuffle)
+    pitch = max(8, (cin + 7) // 8 * 8)
+    xa = ops.Act(torch.zeros((n, h, w, pitch), dtype=torch.bfloat16, device=dev)).slice(0, cin)
+    xa.from_nchw(x.to(dev))
+    ydt = torch.float32 if out_f32 else torch.bfloat16
+    if shuffle:
+        ya = ops.Act.empty(n, h * shuffle, w * shuffle, cout // shuffle ** 2, ydt, dev)
+    else:
+        ya = ops.Act(torch.zeros((n, h, w, cout + 16), dtype=ydt, device=dev)).slice(16, cout)
+    ra = None
+    if res is not None:
+        ra = ops.Act.empty(n, h, w, cout, torch.bfloat16, dev).from_nchw(res.to(dev))
+    wp = pack_tc(wt.to(dev), shuffle)
+    assert ops.conv2d_tc_supported(xa, wp, b.to(dev), ya, k, 1, dil, ra, shuffle)
+    ops.conv2d(xa, wp, b.to(dev), ya, k, 1, dil, act, ra, shuffle, tensor_core=True)
+    torch.cuda.synchronize()
+    got = ya.to_nchw().cpu()
+    err = (got - ref).abs().max().item()
+    scale = max(1.0, ref.abs().max().item())
+    tol = 1e-4 * scale if out_f32 else scale * 2.0 ** -8
+    return err, tol
+
+
+@pytest.mark.parametrize('name', list(TC_CASES))
+def test_conv2d_tc(name):
+    if not torch.cuda.is_available():
+        pytest.skip('needs a CUDA device')
+    err, tol = run_case(name, torch.device('cuda:0'))
+    assert err <= tol, f'{name}: max abs err {err} > {tol}'
+
+
+if __name__ == '__main__':
+    # probe mode: `python tests/test_gpu_tc.py <case>` prints the error of one case (one process per case so a
+    # device fault in one variant does not hide the others)
+    import sys
+    sys.path.insert(0, '.')
+    nm = sys.argv[1]
+    e, t = run_case(nm, torch.device('cuda:0'))
+    print(f'TC_CASE {nm} err={e:.3e} tol={t:.3e} {"OK" if e <= t else "FAIL"}')

@@ -1,0 +1,93 @@
+"""CPU: host-side logic of the package -- interface / state_dict contract of the drop-in modules, weight packing
+(checked numerically against torch convs of the original weights), unsupported-flag and CPU-input behaviour."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import dbsr_oracle as O
+from deep_rawburst_sr_b200.engine import PwcLayout, pack_deconv, pack_direct, pack_tc
+from deep_rawburst_sr_b200.models.dbsr import dbsrnet as D
+from deep_rawburst_sr_b200.models.dbsr.merging import WeightedSum
+from deep_rawburst_sr_b200.models.alignment.pwcnet import PWCNet
+
+
+def test_state_dict_contract_and_constructor():
+    net = D.dbsrnet_default_synthetic()
+    spec = O.state_dict_spec()
+    sd = net.state_dict()
+    assert list(sd.keys()) == [k for k, _ in spec]
+    assert all(tuple(sd[k].shape) == tuple(s) for k, s in spec)
+    assert len(list(net.buffers())) == 0
+    net.load_state_dict(O.make_state_dict(0), strict=True)
+    assert net.constructor.fun_name == 'dbsrnet_cvpr2021' and net.constructor.fun_module.endswith('models.dbsr.dbsrnet')
+    assert hasattr(net, 'encoder') and hasattr(net, 'merging') and hasattr(net, 'decoder')
+    assert isinstance(net.encoder.alignment_net, PWCNet) and hasattr(net.encoder.alignment_net, 'net')
+    # ICNR structure of the freshly initialised upsampler (reference initializations.py:21-38)
+    w = D.dbsrnet_default_synthetic().state_dict()['decoder.upsample_layer.conv_layer.0.weight']
+    assert torch.equal(w[0], w[63]) and not torch.equal(w[0], w[64])
+
+
+def test_unsupported_flags_raise():
+    for kw in (dict(softmax=False), dict(use_base_frame=False), dict(ref_offset_noise=0.1), dict(use_bn=True),
+               dict(activation='lrelu'), dict(use_offset=False)):
+        base = dict(softmax=True, use_base_frame=True)
+        base.update(kw)
+        with pytest.raises(NotImplementedError):
+            WeightedSum(512, 64, 64, **base)
+    with pytest.raises(Exception):
+        PWCNet(load_pretrained=True, weights_path=None)
+
+
+def test_cpu_tensors_raise_not_implemented():
+    from deep_rawburst_sr_b200.external.pwcnet.correlation import correlation
+    with pytest.raises(NotImplementedError):
+        correlation.FunctionCorrelation(tenFirst=torch.zeros(1, 4, 3, 3), tenSecond=torch.zeros(1, 4, 3, 3))
+    net = D.dbsrnet_default_synthetic()
+    with pytest.raises(NotImplementedError):
+        net(torch.zeros(1, 2, 4, 16, 16))
+
+
+def test_pwc_layout_and_packing_equivalence():
+    """conv over the padded in-place concat layout with packed weights == conv over the reference's torch.cat"""
+    g = torch.Generator().manual_seed(0)
+    lay = PwcLayout(3)
+    assert lay.total % 8 == 0 and all(v % 8 == 0 for v in lay.off.values())
+    assert lay.off['V'] == 448 and lay.sizes['f1'] == 64
+    cm, start, length = lay.chmap_from('o2')
+    cin = 128 + 128 + 81 + 64 + 2 + 2
+    assert len(cm) == cin and start == lay.off['o2'] and length == lay.total - start
+    w = torch.randn(96, cin, 3, 3, generator=g)
+    x_orig = torch.randn(2, cin, 5, 6, generator=g)
+    buf = torch.zeros(2, length, 5, 6)
+    buf[:, cm] = x_orig
+    packed = pack_direct(w, cm, length)                       # [9, length, 96]
+    w_buf = packed.view(3, 3, length, 96).permute(3, 2, 0, 1)  # back to [Cout, Cin_buf, k, k]
+    assert torch.allclose(F.conv2d(buf, w_buf, padding=1), F.conv2d(x_orig, w, padding=1), atol=1e-4)
+    # deconv packing
+    wd = torch.randn(cin, 2, 4, 4, generator=g)
+    pd = pack_deconv(wd, cm, length)                          # [4,4,2,length]
+    wd_buf = pd.permute(3, 2, 0, 1)
+    assert torch.allclose(F.conv_transpose2d(buf, wd_buf, stride=2, padding=1),
+                          F.conv_transpose2d(x_orig, wd, stride=2, padding=1), atol=1e-4)
+
+
+def test_pack_tc_layout_and_shuffle_permutation():
+    g = torch.Generator().manual_seed(1)
+    w = torch.randn(64, 4, 3, 3, generator=g)
+    p = pack_tc(w)
+    assert p.dtype == torch.bfloat16 and tuple(p.shape) == (9, 64, 32)
+    assert torch.equal(p[4, :, :4].float(), w[:, :, 1, 1].bfloat16().float()) and float(p[:, :, 4:].float().abs().max()) == 0
+    assert tuple(pack_tc(torch.randn(128, 192, 3, 3, generator=g)).shape) == (9, 128, 192)
+    wu = torch.randn(2048, 64, 1, 1, generator=g)
+    pu = pack_tc(wu, shuffle_r=8)
+    # packed row i*256 + j*32 + c holds original output channel c*64 + i*8 + j
+    for (c, i, j) in ((0, 0, 0), (5, 3, 7), (31, 7, 1)):
+        assert torch.equal(pu[0, i * 256 + j * 32 + c].float(), wu[c * 64 + i * 8 + j, :, 0, 0].bfloat16().float())
+
+
+def test_icnr_matches_reference_structure():
+    from deep_rawburst_sr_b200.models.layers.initializations import ICNR
+    torch.manual_seed(0)
+    k = ICNR(torch.zeros(2048, 64, 1, 1), 8)
+    assert tuple(k.shape) == (2048, 64, 1, 1)
+    assert torch.equal(k[0], k[63]) and torch.equal(k[64], k[127]) and not torch.equal(k[0], k[64])

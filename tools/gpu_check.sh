@@ -1,0 +1,16 @@
+#!/bin/bash
+# Round of GPU checks (run under gpurun): per-kernel parity, tcgen05 conv probes (one process per case so a device
+# fault in one variant cannot hide the others), end-to-end parity, smoke, short bench.  Logs -> gpurun_out/.
+mkdir -p gpurun_out
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/gpu.txt 2>&1
+python -c "import __graft_entry__ as g; g.build()" > gpurun_out/build.log 2>&1 || { tail -20 gpurun_out/build.log; exit 1; }
+echo "== kernels"; timeout 900 python -m pytest tests/test_gpu_kernels.py -q -m gpu --tb=short -p no:cacheprovider > gpurun_out/kernels.log 2>&1; tail -15 gpurun_out/kernels.log
+echo "== tc probes"
+: > gpurun_out/tc.log
+for c in enc_res_64x64 enc_init_4x64 enc_out_64x512 proj_1x1_512x64 wp0_192x128 wp_res_128x128 wp_out_128x512_f32 dec_init_512x64 post_res_32x32 ragged_20x13 offset_2x64 upsample_shuffle dilated_d2; do
+  timeout 120 python tests/test_gpu_tc.py $c >> gpurun_out/tc.log 2>&1 || echo "TC_CASE $c EXIT=$?" >> gpurun_out/tc.log
+done
+grep -E "TC_CASE|timeout|rror" gpurun_out/tc.log | head -40
+echo "== forward"; timeout 1200 python -m pytest tests/test_gpu_forward.py -q -m gpu --tb=short -p no:cacheprovider > gpurun_out/forward.log 2>&1; tail -25 gpurun_out/forward.log
+echo "== smoke"; timeout 600 python __graft_entry__.py smoke > gpurun_out/smoke.log 2>&1; tail -5 gpurun_out/smoke.log
+echo "== bench"; timeout 900 python bench.py --steps 3 --warmup 3 --batch ${BENCH_BATCH:-8} > gpurun_out/bench.log 2>&1; tail -3 gpurun_out/bench.log
