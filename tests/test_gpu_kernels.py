@@ -191,7 +191,7 @@ def test_prep_burst_and_flow_head(dev):
     ops.flow_head(_act_from(flow4, dev), offsets, 24, 40, 64, 64)
     ref = 20.0 * O.resize_bilinear(flow4, 24, 40)
     ref = torch.stack((ref[:, 0] * (40 / 64.0), ref[:, 1] * (24 / 64.0)), 1)
-    assert (offsets.cpu() - ref).abs().max() < 1e-5
+    assert (offsets.cpu() - ref).abs().max() < 2e-6 * max(1.0, float(ref.abs().max()))   # fp32 round-off, |flow| ~ 20
 
 
 @pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])

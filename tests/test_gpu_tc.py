@@ -1,9 +1,14 @@
 """GPU: the tcgen05 / TMEM implicit-GEMM convolution (dbsr_conv2d_tc) against a CPU fp32 convolution of the SAME
 bf16-rounded operands (so the only differences are fp32 accumulation order and the bf16 rounding of the output).
 Tolerance: 2^-8 relative to the output scale for bf16 outputs, 1e-4 for fp32 outputs."""
+import os
+import sys
+
 import pytest
 import torch
 import torch.nn.functional as F
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
 pytestmark = pytest.mark.gpu
 
