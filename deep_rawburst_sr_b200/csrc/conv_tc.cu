@@ -5,13 +5,13 @@
 //
 // GEMM view:  D[pixels, Cout] = sum_{tap, cin} X[pixel + tap, cin] * W[tap, cout, cin]
 //   M tile   : 128 output pixels = 16 rows x 8 columns of one image (one TMEM lane per pixel)
-//   N tile   : BLOCK_N output channels (32 / 64 / 128) = TMEM columns, double buffered
+//   N tile   : n_tile output channels (any multiple of 16 up to 128) = TMEM columns, double buffered
 //   K loop   : for kx in 0..2 : for cin chunk of CK (64 -> SWIZZLE_128B rows, 32 -> SWIZZLE_64B rows):
 //                one TMA box {CK ch, 8 px, 16 + 2*dil rows} of the NHWC input at (x0 + (kx-1)*dil, y0 - dil)
 //                -- out-of-image coordinates are zero-filled by TMA, which IS the conv zero padding --
 //                serves the three ky taps: 8 pixels x CK channels is exactly one swizzle atom, so the tap
 //                (ky) view of the tile is the same smem at a +ky*dil*atom byte offset (1024 B / 512 B aligned).
-//                The three [BLOCK_N x CK] weight tiles of (ky, kx) ride in the same pipeline stage.
+//                The three [n_tile x CK] weight tiles of (ky, kx) ride in the same pipeline stage.
 //   Roles    : warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread tcgen05.mma issuer,
 //              warps 2..5 = epilogue (tcgen05.ld -> +bias, +residual, activation -> bf16/fp32 global stores).
 //   Persistent: grid = min(#work items, #SMs); work item = (pixel tile, N tile), N tile fastest.
@@ -118,6 +118,16 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
 // K-major shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout):
 //   [0,14) start>>4 | [16,30) LBO>>4 (unused for swizzled K-major, canonical value 1) | [32,46) SBO>>4
 //   [46,48) version = 1 (sm_100) | [61,64) layout: 2 = SWIZZLE_128B, 4 = SWIZZLE_64B
@@ -135,22 +145,94 @@ constexpr int TC_THREADS = 192;
 struct ConvTcParams {
   int n, H, W;          // input == output spatial size (stride 1, "same" padding)
   int ksize, dil;
-  int nchunks;          // Cin_pad / CK
-  int cout_pad;         // rows per tap in the packed weight matrix
-  int ntiles_n;         // Cout / BLOCK_N
+  int nchunks;          // Kpad / CK
+  int cout_pad;         // rows per tap in the packed weight matrix (= ntiles_n * n_tile)
+  int cout;             // real output channels (stores are masked beyond it)
+  int n_tile;           // UMMA N (multiple of 16, <= 128)
+  int tmem_cols;        // power of two >= max(32, 2 * n_tile)
+  int vec_ok;           // 1: aligned fast path (16-byte accesses, every 32-column chunk fully inside cout)
+  int ntiles_n;         // cout_pad / n_tile
   int tiles_x, tiles_y;
   long long total_items;
   int stages;
   int a_bytes, b_tap_bytes;  // per stage
   // output
   void* y; int y_dtype; int y_pitch; int y_coff; int yH, yW;
-  const void* res; int r_pitch; int r_coff;   // bf16 residual with the geometry of y
+  const void* res; int r_dtype; int r_pitch; int r_coff;   // residual with the geometry of y
   const float* bias;
   int act;
   int shuffle_r;        // 8: pixel shuffle addressing (y is the (8H, 8W, 32) map)
 };
 
-template <int BLOCK_N, int CK>
+// epilogue of NC (32 or 16) accumulator columns held by one thread (= one output pixel)
+template <int NC>
+__device__ __forceinline__ void epilogue_chunk(const ConvTcParams& p, const uint32_t (&r)[32], int co, long long off,
+                                               long long roff) {
+  // co: first output channel of the chunk; off / roff: element offsets of that channel in y / residual
+  float v[NC];
+#pragma unroll
+  for (int j = 0; j < NC; ++j) v[j] = __uint_as_float(r[j]);
+  if (p.vec_ok) {
+    if (p.bias) {
+#pragma unroll
+      for (int j = 0; j < NC; j += 4) {
+        const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + co + j));
+        v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+      }
+    }
+    if (p.res) {   // bf16 on the fast path
+      const __nv_bfloat16* rp = reinterpret_cast<const __nv_bfloat16*>(p.res) + roff;
+#pragma unroll
+      for (int j = 0; j < NC; j += 8) {
+        const uint4 q = __ldg(reinterpret_cast<const uint4*>(rp + j));
+        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&q);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float2 f = __bfloat1622float2(h[k]);
+          v[j + 2 * k] += f.x; v[j + 2 * k + 1] += f.y;
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < NC; ++j) v[j] = apply_act(v[j], p.act);
+    if (p.y_dtype == DBSR_BF16) {
+      __nv_bfloat16* yp = reinterpret_cast<__nv_bfloat16*>(p.y) + off;
+#pragma unroll
+      for (int j = 0; j < NC; j += 8) {
+        uint4 q;
+        __nv_bfloat162 h0 = __floats2bfloat162_rn(v[j], v[j + 1]);
+        __nv_bfloat162 h1 = __floats2bfloat162_rn(v[j + 2], v[j + 3]);
+        __nv_bfloat162 h2 = __floats2bfloat162_rn(v[j + 4], v[j + 5]);
+        __nv_bfloat162 h3 = __floats2bfloat162_rn(v[j + 6], v[j + 7]);
+        q.x = *reinterpret_cast<uint32_t*>(&h0); q.y = *reinterpret_cast<uint32_t*>(&h1);
+        q.z = *reinterpret_cast<uint32_t*>(&h2); q.w = *reinterpret_cast<uint32_t*>(&h3);
+        *reinterpret_cast<uint4*>(yp + j) = q;
+      }
+    } else {
+      float* yp = reinterpret_cast<float*>(p.y) + off;
+#pragma unroll
+      for (int j = 0; j < NC; j += 4) *reinterpret_cast<float4*>(yp + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+    }
+  } else {
+    // generic path: any channel count / alignment / residual dtype, masked at cout
+#pragma unroll
+    for (int j = 0; j < NC; ++j) {
+      if (co + j < p.cout) {
+        float t = v[j];
+        if (p.bias) t += __ldg(p.bias + co + j);
+        if (p.res) {
+          t += (p.r_dtype == DBSR_F32) ? __ldg(reinterpret_cast<const float*>(p.res) + roff + j)
+                                       : __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p.res)[roff + j]);
+        }
+        t = apply_act(t, p.act);
+        if (p.y_dtype == DBSR_BF16) reinterpret_cast<__nv_bfloat16*>(p.y)[off + j] = __float2bfloat16_rn(t);
+        else reinterpret_cast<float*>(p.y)[off + j] = t;
+      }
+    }
+  }
+}
+
+template <int CK>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
                const ConvTcParams p) {
@@ -167,11 +249,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  constexpr uint32_t TMEM_COLS = (2 * BLOCK_N < 32) ? 32 : 2 * BLOCK_N;
   constexpr uint32_t ROW_BYTES = CK * 2;                 // bytes per pixel row of a K chunk
   constexpr uint32_t ATOM_BYTES = 8 * ROW_BYTES;         // 8 rows: 1024 (SW128) / 512 (SW64)
   constexpr uint32_t LAYOUT = (CK == 64) ? 2u : 4u;
-  constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BLOCK_N >> 3) << 17) | ((128u >> 4) << 24);
+  // cute::UMMA::InstrDescriptor: c_format F32 [4,6) | a,b format BF16 [7,10),[10,13) | K-major | N>>3 [17,23) | M>>4 [24,29)
+  const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.n_tile >> 3) << 17) | ((128u >> 4) << 24);
+  const int NT = p.n_tile;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
@@ -181,7 +264,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
     tma_prefetch_desc(&tmap_x);
     tma_prefetch_desc(&tmap_w);
   }
-  if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
+  if (warp == 1) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -210,10 +293,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
             tma_load_4d(&tmap_x, &full_bar[stage], sa, ch * CK, x0 + (kx - 1) * p.dil, y0 - p.dil, img);
             for (int ky = 0; ky < 3; ++ky)
               tma_load_2d(&tmap_w, &full_bar[stage], sa + p.a_bytes + ky * p.b_tap_bytes, ch * CK,
-                          (ky * 3 + kx) * p.cout_pad + nt * BLOCK_N);
+                          (ky * 3 + kx) * p.cout_pad + nt * NT);
           } else {
             tma_load_4d(&tmap_x, &full_bar[stage], sa, ch * CK, x0, y0, img);
-            tma_load_2d(&tmap_w, &full_bar[stage], sa + p.a_bytes, ch * CK, nt * BLOCK_N);
+            tma_load_2d(&tmap_w, &full_bar[stage], sa + p.a_bytes, ch * CK, nt * NT);
           }
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
@@ -227,7 +310,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
       for (long long item = blockIdx.x; item < p.total_items; item += gridDim.x) {
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1, 200 + acc);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BLOCK_N);
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * NT);
         for (int ks = 0; ks < ksteps; ++ks) {
           mbar_wait(&full_bar[stage], phase, 300 + stage);
           tc_fence_after();
@@ -240,7 +323,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
             for (int k16 = 0; k16 < CK / 16; ++k16) {
               const uint64_t adesc = make_smem_desc(a_tap + k16 * 32, ATOM_BYTES, LAYOUT);
               const uint64_t bdesc = make_smem_desc(b_tap + k16 * 32, ATOM_BYTES, LAYOUT);
-              umma_bf16(d_tmem, adesc, bdesc, IDESC, (ks | ky | k16) != 0 ? 1u : 0u);
+              umma_bf16(d_tmem, adesc, bdesc, idesc, (ks | ky | k16) != 0 ? 1u : 0u);
             }
           }
           umma_commit(&empty_bar[stage]);  // frees the smem stage when these MMAs retire
@@ -263,78 +346,34 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
       const int trem = (int)(tm - (long long)img * tiles_per_img);
       const int y = (trem / p.tiles_x) * TILE_H + ty, x = (trem % p.tiles_x) * TILE_W + tx;
       const bool valid = (y < p.H) && (x < p.W);
-      long long off;   // element offset of this thread's first output channel
+      const int co0 = nt * NT;
+      long long off;   // element offset of this thread's first output channel of the tile
       if (p.shuffle_r > 1) {
         // packed channel co' = i*256 + j*32 + c ; N tile = 128 -> i = nt / 2, j0 = (nt & 1) * 4
         const int per_i = p.shuffle_r * 32;        // channels per HR row phase
-        const int co0 = nt * BLOCK_N;
         const int si = co0 / per_i, j0 = (co0 - si * per_i) / 32;
         off = (((long long)img * p.yH + (y * p.shuffle_r + si)) * p.yW + (x * p.shuffle_r + j0)) * p.y_pitch + p.y_coff;
       } else {
-        off = (((long long)img * p.yH + y) * p.yW + x) * p.y_pitch + p.y_coff + nt * BLOCK_N;
+        off = (((long long)img * p.yH + y) * p.yW + x) * p.y_pitch + p.y_coff + co0;
       }
-      const long long roff = (((long long)img * p.yH + y) * p.yW + x) * p.r_pitch + p.r_coff + nt * BLOCK_N;
+      const long long roff = (((long long)img * p.yH + y) * p.yW + x) * p.r_pitch + p.r_coff + co0;
 
       mbar_wait(&tfull_bar[acc], acc_phase, 400 + acc);
       tc_fence_after();
+      const uint32_t tbase = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * NT);
+      int c0 = 0;
 #pragma unroll 1
-      for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+      for (; c0 + 32 <= NT; c0 += 32) {
         uint32_t r[32];
-        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BLOCK_N + c0);
-        tmem_ld32(taddr, r);
-        if (valid) {
-          float v[32];
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-          if (p.bias) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + nt * BLOCK_N + c0 + j));
-              v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
-            }
-          }
-          if (p.res) {
-            const __nv_bfloat16* rp = reinterpret_cast<const __nv_bfloat16*>(p.res) + roff + c0;
-#pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-              const uint4 q = __ldg(reinterpret_cast<const uint4*>(rp + j));
-              const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&q);
-#pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                const float2 f = __bfloat1622float2(h[k]);
-                v[j + 2 * k] += f.x; v[j + 2 * k + 1] += f.y;
-              }
-            }
-          }
-          if (p.act == DBSR_ACT_RELU) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.0f);
-          } else if (p.act == DBSR_ACT_LRELU) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = v[j] > 0.0f ? v[j] : 0.1f * v[j];
-          }
-          if (p.y_dtype == DBSR_BF16) {
-            __nv_bfloat16* yp = reinterpret_cast<__nv_bfloat16*>(p.y) + off + c0;
-#pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-              uint4 q;
-              __nv_bfloat162 h0 = __floats2bfloat162_rn(v[j], v[j + 1]);
-              __nv_bfloat162 h1 = __floats2bfloat162_rn(v[j + 2], v[j + 3]);
-              __nv_bfloat162 h2 = __floats2bfloat162_rn(v[j + 4], v[j + 5]);
-              __nv_bfloat162 h3 = __floats2bfloat162_rn(v[j + 6], v[j + 7]);
-              q.x = *reinterpret_cast<uint32_t*>(&h0); q.y = *reinterpret_cast<uint32_t*>(&h1);
-              q.z = *reinterpret_cast<uint32_t*>(&h2); q.w = *reinterpret_cast<uint32_t*>(&h3);
-              *reinterpret_cast<uint4*>(yp + j) = q;
-            }
-          } else {
-            float* yp = reinterpret_cast<float*>(p.y) + off + c0;
-#pragma unroll
-            for (int j = 0; j < 32; j += 4)
-              *reinterpret_cast<float4*>(yp + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-          }
-        }
+        tmem_ld32(tbase + (uint32_t)c0, r);
+        if (valid) epilogue_chunk<32>(p, r, co0 + c0, off + c0, roff + c0);
       }
-      // all TMEM reads of this warp are complete (tcgen05.wait::ld inside tmem_ld32): release the accumulator
+      if (c0 < NT) {   // 16-column tail (n_tile is a multiple of 16)
+        uint32_t r[32];
+        tmem_ld16(tbase + (uint32_t)c0, r);
+        if (valid) epilogue_chunk<16>(p, r, co0 + c0, off + c0, roff + c0);
+      }
+      // all TMEM reads of this warp are complete (tcgen05.wait::ld inside the loads): release the accumulator
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[acc]);
@@ -346,7 +385,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, TMEM_COLS);
+    tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
   }
 }
 
@@ -369,8 +408,30 @@ static EncodeTiledFn get_encode() {
   return fn;
 }
 
+static inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
+
+// Tiling rule shared with the Python weight packer through dbsr_conv2d_tc_geometry().
+static void tc_geometry(int cin, int cout, int* ck, int* kpad, int* n_tile, int* cout_pad) {
+  const int k32 = round_up(cin, 32), k64 = round_up(cin, 64);
+  *ck = (k64 <= k32) ? 64 : 32;          // smallest padded K; ties go to the wider chunk
+  *kpad = (*ck == 64) ? k64 : k32;
+  int nt;
+  if (cout % 128 == 0) nt = 128;
+  else if (cout % 64 == 0) nt = 64;
+  else {
+    const int c16 = round_up(cout, 16);
+    if (c16 <= 128) nt = c16;
+    else {
+      const int parts = (c16 + 127) / 128;
+      nt = round_up((c16 + parts - 1) / parts, 16);
+    }
+  }
+  *n_tile = nt;
+  *cout_pad = round_up(cout, nt);
+}
+
 struct TcConfig {
-  int block_n, ck, nchunks, cout_pad, stages, a_bytes, b_tap_bytes, smem_bytes;
+  int n_tile, ck, nchunks, cout, cout_pad, stages, a_bytes, b_tap_bytes, smem_bytes, tmem_cols, vec_ok;
 };
 
 static int tc_plan(const dbsr_conv_t* c, TcConfig* cfg, bool set_err) {
@@ -385,38 +446,40 @@ static int tc_plan(const dbsr_conv_t* c, TcConfig* cfg, bool set_err) {
   TC_REQ(c->y.n == c->x.n && c->y.h == c->x.h * r && c->y.w == c->x.w * r, "conv2d_tc: output geometry mismatch");
   TC_REQ((c->x.c_off % 8) == 0 && (c->x.c_pitch % 8) == 0 && ((uintptr_t)c->x.data % 16) == 0,
          "conv2d_tc: input view must be 16-byte aligned (c_off, c_pitch multiples of 8)");
-  int bn;
-  if (r > 1) {
-    TC_REQ(r == 8 && c->y.c == 32 && c->y.c_pitch == 32 && c->y.c_off == 0 && cout % 128 == 0,
+  int ck, kpad, nt, cpad;
+  tc_geometry(c->x.c, cout, &ck, &kpad, &nt, &cpad);
+  if (r > 1)
+    TC_REQ(r == 8 && c->y.c == 32 && c->y.c_pitch == 32 && c->y.c_off == 0 && nt == 128,
            "conv2d_tc: pixel-shuffle mode needs r=8 and a dense 32-channel output map");
-    bn = 128;
-  } else if (cout % 128 == 0) bn = 128;
-  else if (cout % 64 == 0) bn = 64;
-  else if (cout % 32 == 0) bn = 32;
-  else { TC_REQ(false, "conv2d_tc: Cout=%d must be a multiple of 32", cout); }
   const size_t yes = elem_size(c->y.dtype);
-  TC_REQ(((c->y.c_off * yes) % 16) == 0 && ((c->y.c_pitch * yes) % 16) == 0 && ((uintptr_t)c->y.data % 16) == 0,
-         "conv2d_tc: output view must be 16-byte aligned");
+  // fast path: no channel padding (every accumulator chunk lies inside cout) and 16-byte aligned rows
+  bool vec = cout == cpad && ((c->y.c_off * yes) % 16) == 0 && ((c->y.c_pitch * yes) % 16) == 0 &&
+             ((uintptr_t)c->y.data % 16) == 0;
   if (c->residual.data) {
-    TC_REQ(r == 1 && c->residual.dtype == DBSR_BF16 && c->residual.n == c->y.n && c->residual.h == c->y.h &&
-               c->residual.w == c->y.w && c->residual.c == c->y.c && (c->residual.c_off % 8) == 0 &&
-               (c->residual.c_pitch % 8) == 0 && ((uintptr_t)c->residual.data % 16) == 0,
-           "conv2d_tc: residual must be an aligned bf16 view with the geometry of y");
+    TC_REQ(r == 1 && view_ok(&c->residual) && c->residual.n == c->y.n && c->residual.h == c->y.h &&
+               c->residual.w == c->y.w && c->residual.c == c->y.c,
+           "conv2d_tc: residual must have the geometry of y");
+    vec = vec && c->residual.dtype == DBSR_BF16 && (c->residual.c_off % 8) == 0 && (c->residual.c_pitch % 8) == 0 &&
+          ((uintptr_t)c->residual.data % 16) == 0;
   }
-  if (c->bias) TC_REQ(((uintptr_t)c->bias % 16) == 0, "conv2d_tc: bias must be 16-byte aligned");
-  const int cin = c->x.c;
-  const int ck = (cin % 64 == 0) ? 64 : 32;
-  cfg->block_n = bn;
+  if (c->bias) vec = vec && ((uintptr_t)c->bias % 16) == 0;
+  cfg->vec_ok = vec ? 1 : 0;
+  cfg->n_tile = nt;
   cfg->ck = ck;
-  cfg->nchunks = (cin + ck - 1) / ck;
-  cfg->cout_pad = cout;
+  cfg->nchunks = kpad / ck;
+  cfg->cout = cout;
+  cfg->cout_pad = cpad;
+  int tc = 32;
+  while (tc < 2 * nt) tc <<= 1;
+  cfg->tmem_cols = tc;
   const int rows = (c->ksize == 3) ? TILE_H + 2 * c->dilation : TILE_H;
   cfg->a_bytes = rows * TILE_W * ck * 2;
-  cfg->b_tap_bytes = bn * ck * 2;
+  cfg->b_tap_bytes = nt * ck * 2;
+  TC_REQ(cfg->b_tap_bytes % 1024 == 0 && cfg->a_bytes % 1024 == 0, "conv2d_tc: internal: unaligned stage layout");
   const int stage = cfg->a_bytes + c->ksize * cfg->b_tap_bytes;
   const int budget = 227 * 1024 - 2048;
   int stages = budget / stage;
-  if (stages > 6) stages = 6;
+  if (stages > 8) stages = 8;
   TC_REQ(stages >= 2, "conv2d_tc: pipeline stage of %d bytes does not fit twice in shared memory", stage);
   cfg->stages = stages;
   cfg->smem_bytes = stages * stage + 1024 /*align slack*/ + 256 /*barriers*/;
@@ -424,11 +487,11 @@ static int tc_plan(const dbsr_conv_t* c, TcConfig* cfg, bool set_err) {
 #undef TC_REQ
 }
 
-template <int BN, int CK>
+template <int CK>
 static int launch_tc(const CUtensorMap& mx, const CUtensorMap& mw, const ConvTcParams& p, int smem, cudaStream_t st) {
   static int configured_smem = 0;
   if (smem > configured_smem) {
-    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BN, CK>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<CK>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) {
       set_error("conv2d_tc: cudaFuncSetAttribute(%d) failed: %s", smem, cudaGetErrorString(e));
       return 2;
@@ -442,13 +505,22 @@ static int launch_tc(const CUtensorMap& mx, const CUtensorMap& mw, const ConvTcP
     cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
   }
   const int grid = (int)(p.total_items < num_sms ? p.total_items : num_sms);
-  conv_tc_kernel<BN, CK><<<grid, TC_THREADS, smem, st>>>(mx, mw, p);
+  conv_tc_kernel<CK><<<grid, TC_THREADS, smem, st>>>(mx, mw, p);
   return check_launch("conv2d_tc");
 }
 
 }  // namespace dbsr
 
 using namespace dbsr;
+
+extern "C" int dbsr_conv2d_tc_geometry(int32_t cin, int32_t cout, int32_t* ck, int32_t* kpad, int32_t* n_tile,
+                                       int32_t* cout_pad) {
+  DBSR_REQUIRE(cin > 0 && cout > 0 && ck && kpad && n_tile && cout_pad, "conv2d_tc_geometry: bad arguments");
+  int a, b, c, d;
+  tc_geometry(cin, cout, &a, &b, &c, &d);
+  *ck = a; *kpad = b; *n_tile = c; *cout_pad = d;
+  return 0;
+}
 
 extern "C" int dbsr_conv2d_tc_supported(const dbsr_conv_t* c) {
   TcConfig cfg;
@@ -483,7 +555,7 @@ extern "C" int dbsr_conv2d_tc(const dbsr_conv_t* c, void* stream) {
     const int kpad = cfg.nchunks * cfg.ck;
     cuuint64_t dims[2] = {(cuuint64_t)kpad, (cuuint64_t)taps * cfg.cout_pad};
     cuuint64_t strides[1] = {(cuuint64_t)kpad * 2};
-    cuuint32_t box[2] = {(cuuint32_t)cfg.ck, (cuuint32_t)cfg.block_n};
+    cuuint32_t box[2] = {(cuuint32_t)cfg.ck, (cuuint32_t)cfg.n_tile};
     cuuint32_t es[2] = {1, 1};
     CUresult rc = encode(&mw, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(c->w), dims, strides, box, es,
                          CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -494,22 +566,17 @@ extern "C" int dbsr_conv2d_tc(const dbsr_conv_t* c, void* stream) {
   ConvTcParams p;
   p.n = c->x.n; p.H = c->x.h; p.W = c->x.w;
   p.ksize = c->ksize; p.dil = c->dilation;
-  p.nchunks = cfg.nchunks; p.cout_pad = cfg.cout_pad;
-  p.ntiles_n = cfg.cout_pad / cfg.block_n;
+  p.nchunks = cfg.nchunks; p.cout_pad = cfg.cout_pad; p.cout = cfg.cout; p.n_tile = cfg.n_tile;
+  p.tmem_cols = cfg.tmem_cols; p.vec_ok = cfg.vec_ok;
+  p.ntiles_n = cfg.cout_pad / cfg.n_tile;
   p.tiles_x = ceil_div(p.W, TILE_W); p.tiles_y = ceil_div(p.H, TILE_H);
   p.total_items = (long long)p.n * p.tiles_x * p.tiles_y * p.ntiles_n;
   p.stages = cfg.stages; p.a_bytes = cfg.a_bytes; p.b_tap_bytes = cfg.b_tap_bytes;
   p.y = c->y.data; p.y_dtype = c->y.dtype; p.y_pitch = c->y.c_pitch; p.y_coff = c->y.c_off;
   p.yH = c->y.h; p.yW = c->y.w;
-  p.res = c->residual.data; p.r_pitch = c->residual.c_pitch; p.r_coff = c->residual.c_off;
+  p.res = c->residual.data; p.r_dtype = c->residual.dtype; p.r_pitch = c->residual.c_pitch; p.r_coff = c->residual.c_off;
   p.bias = c->bias; p.act = c->act; p.shuffle_r = r;
   cudaStream_t st = (cudaStream_t)stream;
-  if (cfg.block_n == 128 && cfg.ck == 64) return launch_tc<128, 64>(mx, mw, p, cfg.smem_bytes, st);
-  if (cfg.block_n == 64 && cfg.ck == 64) return launch_tc<64, 64>(mx, mw, p, cfg.smem_bytes, st);
-  if (cfg.block_n == 32 && cfg.ck == 64) return launch_tc<32, 64>(mx, mw, p, cfg.smem_bytes, st);
-  if (cfg.block_n == 128 && cfg.ck == 32) return launch_tc<128, 32>(mx, mw, p, cfg.smem_bytes, st);
-  if (cfg.block_n == 64 && cfg.ck == 32) return launch_tc<64, 32>(mx, mw, p, cfg.smem_bytes, st);
-  if (cfg.block_n == 32 && cfg.ck == 32) return launch_tc<32, 32>(mx, mw, p, cfg.smem_bytes, st);
-  set_error("conv2d_tc: no kernel instance for BLOCK_N=%d CK=%d", cfg.block_n, cfg.ck);
-  return 1;
+  if (cfg.ck == 64) return launch_tc<64>(mx, mw, p, cfg.smem_bytes, st);
+  return launch_tc<32>(mx, mw, p, cfg.smem_bytes, st);
 }

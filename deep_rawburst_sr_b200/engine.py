@@ -74,20 +74,25 @@ def pack_direct(w: torch.Tensor, chmap=None, cin_buf: Optional[int] = None) -> t
     return out.contiguous()
 
 
-def pack_tc(w: torch.Tensor, shuffle_r: int = 0) -> torch.Tensor:
-    """[Cout, Cin, k, k] -> bf16 [k*k, Cout, Kpad] K-major (Kpad = Cin rounded up to the kernel's K chunk: 64
-    when Cin % 64 == 0 else 32).  shuffle_r = 8: rows permuted to (i, j, c) order so that an N tile is contiguous
-    in the pixel-shuffled output (nn.PixelShuffle: co = c*r*r + i*r + j)."""
+def pack_tc(w: torch.Tensor, shuffle_r: int = 0, chmap=None, cin_buf: Optional[int] = None) -> torch.Tensor:
+    """[Cout, Cin, k, k] -> bf16 [k*k, cout_pad, kpad] K-major for dbsr_conv2d_tc; (kpad, cout_pad) come from the
+    kernel's own tiling rule (dbsr_conv2d_tc_geometry).  Padded rows / columns are zero.  `chmap`/`cin_buf`: input
+    channel -> position inside a padded concat slice.  shuffle_r = 8: rows permuted to (i, j, c) order so that an N
+    tile is contiguous in the pixel-shuffled output (nn.PixelShuffle: co = c*r*r + i*r + j)."""
     cout, cin, kh, kw = w.shape
-    ck = 64 if cin % 64 == 0 else 32
-    kpad = (cin + ck - 1) // ck * ck
+    cin_buf = cin if cin_buf is None else cin_buf
+    _ck, kpad, _nt, cout_pad = ops.conv2d_tc_geometry(cin_buf, cout)
     src = w.float()
     if shuffle_r and shuffle_r > 1:
         r = shuffle_r
         c = cout // (r * r)
         src = src.view(c, r, r, cin, kh, kw).permute(1, 2, 0, 3, 4, 5).reshape(cout, cin, kh, kw)
-    out = torch.zeros((kh * kw, cout, kpad), dtype=torch.float32, device=w.device)
-    out[:, :, :cin] = src.permute(2, 3, 0, 1).reshape(kh * kw, cout, cin)
+    out = torch.zeros((kh * kw, cout_pad, kpad), dtype=torch.float32, device=w.device)
+    src = src.permute(2, 3, 0, 1).reshape(kh * kw, cout, cin)
+    if chmap is None:
+        out[:, :cout, :cin] = src
+    else:
+        out[:, :cout, torch.as_tensor(chmap, device=w.device)] = src
     return out.to(torch.bfloat16).contiguous()
 
 
@@ -114,7 +119,7 @@ class ConvW:
 
 class DBSREngine:
     def __init__(self, state_dict: Dict[str, torch.Tensor], device, precision: str = 'bf16', offset_modulo: float = 1.0,
-                 gauss_kernel=None, logits_fp32: bool = False,
+                 gauss_kernel=None, logits_fp32: bool = False, pwc_precision: Optional[str] = None,
                  pwc_prefix: str = 'encoder.alignment_net.net.', parts=('pwc', 'encoder', 'merging', 'decoder')):
         assert precision in ('bf16', 'fp32')
         self.device = torch.device(device)
@@ -123,6 +128,10 @@ class DBSREngine:
         self.bf16 = precision == 'bf16'
         self.act_dtype = torch.bfloat16 if self.bf16 else torch.float32
         self.logits_dtype = torch.float32 if (logits_fp32 or not self.bf16) else torch.bfloat16
+        # PWC-Net activations: bf16 + tensor cores with the bf16 path unless pwc_precision='fp32' (flows stay fp32)
+        self.pwc_precision = pwc_precision or precision
+        assert self.pwc_precision in ('bf16', 'fp32')
+        self.pwc_dtype = torch.bfloat16 if self.pwc_precision == 'bf16' else torch.float32
         self.offset_modulo = float(offset_modulo) if offset_modulo is not None else 0.0
         self.pwc_prefix = pwc_prefix
         self.W: Dict[str, ConvW] = {}
@@ -150,16 +159,17 @@ class DBSREngine:
     # ------------------------------------------------------------------------------------------------
     def _add(self, key, w, b, tc=False, chmap=None, cin_buf=None, shuffle_r=0):
         direct = pack_direct(w, chmap, cin_buf)
-        tcw = pack_tc(w, shuffle_r) if (tc and self.bf16) else None
+        tcw = pack_tc(w, shuffle_r, chmap, cin_buf) if tc else None
         self.W[key] = ConvW(direct, tcw, None if b is None else b.float().contiguous(), w.shape[2], w.shape[0], w.shape[1],
                              shuffle_r)
 
     def _pack_pwc(self, sd):
         pre = self.pwc_prefix
+        ptc = self.pwc_precision == 'bf16'
         for name in PWC_NAMES:
             for idx in (0, 2, 4):
                 k = f'{pre}netExtractor.net{name}.{idx}'
-                self._add(k, sd[k + '.weight'], sd[k + '.bias'])
+                self._add(k, sd[k + '.weight'], sd[k + '.bias'], tc=ptc and idx != 0)   # idx 0 is the stride-2 conv
         self.pwc_layouts = {l: PwcLayout(l) for l in (2, 3, 4, 5, 6)}
         segs = ['V', 'o1', 'o2', 'o3', 'o4', 'o5']   # input of netOne..netSix starts at this segment
         for lvl in (6, 5, 4, 3, 2):
@@ -168,7 +178,7 @@ class DBSREngine:
             for j, sub in enumerate(PWC_NAMES):
                 k = f'{pre}net{lname}.net{sub}.0'
                 cm, _start, length = lay.chmap_from(segs[j])
-                self._add(k, sd[k + '.weight'], sd[k + '.bias'], chmap=cm, cin_buf=length)
+                self._add(k, sd[k + '.weight'], sd[k + '.bias'], tc=ptc, chmap=cm, cin_buf=length)
             if lvl < 6:
                 prev = self.pwc_layouts[lvl + 1]
                 cm, _s, length = prev.chmap_from('o5')
@@ -180,13 +190,13 @@ class DBSREngine:
         for j in range(7):
             k = f'{pre}netRefiner.netMain.{2 * j}'
             if j == 0:
-                self._add(k, sd[k + '.weight'], sd[k + '.bias'], chmap=cm, cin_buf=length)
+                self._add(k, sd[k + '.weight'], sd[k + '.bias'], tc=ptc, chmap=cm, cin_buf=length)
             else:
-                self._add(k, sd[k + '.weight'], sd[k + '.bias'])
+                self._add(k, sd[k + '.weight'], sd[k + '.bias'], tc=ptc)
 
     def _pack_dbsr(self, sd, parts):
-        def add(k, tc=True, bias=True, shuffle_r=0):
-            self._add(k, sd[k + '.weight'], sd.get(k + '.bias') if bias else None, tc=tc, shuffle_r=shuffle_r)
+        def add(k, bias=True, shuffle_r=0):
+            self._add(k, sd[k + '.weight'], sd.get(k + '.bias') if bias else None, tc=self.bf16, shuffle_r=shuffle_r)
 
         if 'encoder' in parts:
             add('encoder.init_layer.0')
@@ -225,7 +235,7 @@ class DBSREngine:
             self.post_dim = sd['decoder.predictor.0.weight'].shape[1]
             self.up_r = int(round(math.sqrt(up_w.shape[0] // self.post_dim)))
             self._add('decoder.upsample_layer.conv_layer.0', up_w, sd.get('decoder.upsample_layer.conv_layer.0.bias'),
-                      tc=True, shuffle_r=self.up_r)
+                      tc=self.bf16 and self.up_r == 8 and self.post_dim == 32, shuffle_r=self.up_r)
             self.dec_post = len([k for k in sd if k.startswith('decoder.post_res_layers.') and k.endswith('conv1.0.weight')])
             for i in range(self.dec_post):
                 add(f'decoder.post_res_layers.{i}.conv1.0')
@@ -282,9 +292,11 @@ class DBSREngine:
         return self._conv(key + '.conv2.0', tmp, y, ACT_RELU, residual=x)
 
     def _buf(self, ws: dict, name: str, n, h, w, c, dtype, zero=False) -> Act:
+        """workspace buffer; the pixel pitch is rounded up to 8 channels (16-byte rows for TMA / vector access)"""
         a = ws.get(name)
         if a is None:
-            a = Act.empty(n, h, w, c, dtype, self.device, zero=zero)
+            pitch = _align8(c)
+            a = Act.empty(n, h, w, pitch, dtype, self.device, zero=zero or pitch != c).slice(0, c)
             ws[name] = a
         return a
 
@@ -308,9 +320,9 @@ class DBSREngine:
         for l, name in enumerate(PWC_NAMES):
             c = PWC_EXT_CH[l + 1]
             h, w = (h + 1) // 2, (w + 1) // 2
-            t1 = self._buf(ws, f'ext{l}_a', n, h, w, c, torch.float32)
-            t2 = self._buf(ws, f'ext{l}_b', n, h, w, c, torch.float32)
-            f = self._buf(ws, f'ext{l}_f', n, h, w, c, torch.float32)
+            t1 = self._buf(ws, f'ext{l}_a', n, h, w, c, self.pwc_dtype)
+            t2 = self._buf(ws, f'ext{l}_b', n, h, w, c, self.pwc_dtype)
+            f = self._buf(ws, f'ext{l}_f', n, h, w, c, self.pwc_dtype)
             self._conv(f'{pre}netExtractor.net{name}.0', x, t1, ACT_LRELU, stride=2)
             self._conv(f'{pre}netExtractor.net{name}.2', t1, t2, ACT_LRELU)
             self._conv(f'{pre}netExtractor.net{name}.4', t2, f, ACT_LRELU)
@@ -330,7 +342,7 @@ class DBSREngine:
             lname = PWC_NAMES[lvl - 1]
             f1, f2 = first[lvl - 1], second[lvl - 1]
             h, w = f1.h, f1.w
-            cat = self._buf(ws, f'cat{lvl}', pairs, h, w, lay.total, torch.float32, zero=True)
+            cat = self._buf(ws, f'cat{lvl}', pairs, h, w, lay.total, self.pwc_dtype, zero=True)
             flow = self._buf(ws, f'flow{lvl}', pairs, h, w, 2, torch.float32)
             vol = cat.slice(lay.off['V'], 81)
             if prev_cat is None:
@@ -361,7 +373,7 @@ class DBSREngine:
         chans = [128, 128, 128, 96, 64, 32]
         x = prev_cat
         for j in range(6):
-            y = self._buf(ws, f'ref{j}', pairs, h, w, chans[j], torch.float32)
+            y = self._buf(ws, f'ref{j}', pairs, h, w, chans[j], self.pwc_dtype)
             self._conv(f'{pre}netRefiner.netMain.{2 * j}', x, y, ACT_LRELU, dilation=PWC_REFINER_DIL[j])
             x = y
         flow4 = self._buf(ws, 'flow_quarter', pairs, h, w, 2, torch.float32)

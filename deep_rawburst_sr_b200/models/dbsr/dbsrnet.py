@@ -31,6 +31,7 @@ class DBSRNet(nn.Module):
         self.decoder = decoder      # Decodes the merged embeddings to generate HR RGB image
         self.precision = os.environ.get('DBSR_B200_PRECISION', 'bf16')
         self.logits_fp32 = False
+        self.pwc_precision = None      # None: follow `precision`; 'fp32' keeps PWC-Net (flow) on the exact CUDA-core path
         self.return_fusion_weights = False
         self._engine = None
 
@@ -55,8 +56,10 @@ class DBSRNet(nn.Module):
 
     def engine(self, device):
         e = self._engine
-        if e is None or e.device != torch.device(device) or e.precision != self.precision:
+        if (e is None or e.device != torch.device(device) or e.precision != self.precision or
+                e.pwc_precision != (self.pwc_precision or self.precision)):
             self._engine = DBSREngine(self.state_dict(), device, precision=self.precision,
+                                      pwc_precision=self.pwc_precision,
                                       offset_modulo=self.merging.offset_modulo,
                                       gauss_kernel=self.decoder.gauss_taps(), logits_fp32=self.logits_fp32)
         return self._engine

@@ -102,6 +102,15 @@ def conv2d_tc_supported(x: Act, w: torch.Tensor, bias, y: Act, ksize: int, strid
     return bool(_lib.load_library().dbsr_conv2d_tc_supported(ctypes.byref(d)))
 
 
+def conv2d_tc_geometry(cin: int, cout: int):
+    """(ck, kpad, n_tile, cout_pad) the tcgen05 kernel uses for a Cin -> Cout convolution (single source of truth for
+    the weight packer)."""
+    a, b, c, d = ctypes.c_int32(), ctypes.c_int32(), ctypes.c_int32(), ctypes.c_int32()
+    _lib.check(_lib.load_library().dbsr_conv2d_tc_geometry(cin, cout, ctypes.byref(a), ctypes.byref(b), ctypes.byref(c),
+                                                           ctypes.byref(d)), 'dbsr_conv2d_tc_geometry')
+    return a.value, b.value, c.value, d.value
+
+
 def deconv4x4s2(x: Act, w: torch.Tensor, bias: torch.Tensor, y: Act, y2: Optional[Act] = None) -> Act:
     xv, yv = x.view(), y.view()
     y2v = y2.view() if y2 is not None else _NULL_VIEW

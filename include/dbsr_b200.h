@@ -90,14 +90,20 @@ typedef struct dbsr_conv {
 } dbsr_conv_t;
 int dbsr_conv2d_direct(const dbsr_conv_t* p, void* stream);
 
-/* tcgen05 / TMEM implicit-GEMM path (bf16 operands, fp32 accumulate in tensor memory).
- *   x, y (and residual): bf16 NHWC; x.c and x.c_off multiples of 32 (pad with zero channels), stride 1.
- *   w: bf16 [Cout_pad][k*k][Cin_pad] K-major, see dbsr_pack_conv_weight_tc; Cout_pad multiple of 16.
- *   y may be fp32 (logits).  Returns non-zero for shapes it does not cover (caller must not fall back
- *   silently; the Python engine decides per layer at plan time).                                      */
+/* tcgen05 / TMEM implicit-GEMM path (bf16 operands, fp32 accumulate in tensor memory), stride 1.
+ *   x: bf16 NHWC view, c_off and c_pitch multiples of 8 (16-byte rows for TMA); channels beyond x.c are
+ *      zero-filled by TMA, so Cin needs no padding in memory.
+ *   y: bf16 or fp32 view (any channel count / offset; aligned multiples of 16 channels take a vector path)
+ *   residual: bf16 or fp32 view with the geometry of y.
+ *   w: bf16 [k*k][cout_pad][kpad] K-major with (ck, kpad, n_tile, cout_pad) = dbsr_conv2d_tc_geometry(Cin, Cout);
+ *      rows >= Cout and columns >= Cin are zero.  shuffle_r = 8: rows permuted to (i, j, c) order.
+ *   Returns non-zero for shapes it does not cover; the Python engine decides per layer at plan time
+ *   (dbsr_conv2d_tc_supported) and never falls back silently inside a call.                              */
 int dbsr_conv2d_tc(const dbsr_conv_t* p, void* stream);
-/* smem bytes / tile shape chosen for a conv, for reporting */
 int dbsr_conv2d_tc_supported(const dbsr_conv_t* p);
+/* tiling chosen for (Cin, Cout): K chunk (64 -> SWIZZLE_128B, 32 -> SWIZZLE_64B), padded K, UMMA N, padded Cout */
+int dbsr_conv2d_tc_geometry(int32_t cin, int32_t cout, int32_t* ck, int32_t* kpad, int32_t* n_tile,
+                            int32_t* cout_pad);
 
 /* ConvTranspose2d(k=4, s=2, p=1), Cout = 2 (pwcnet.py:119-120 netUpflow / netUpfeat).
  *   w: fp32 [4][4][2][Cin]; y, y2: [n, 2h, 2w, 2] views (y2 optional second destination, data NULL ok) */

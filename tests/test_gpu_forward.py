@@ -68,13 +68,15 @@ def test_fp32_path_stress_flows_against_oracle(dev):
     assert err.mean().item() < 1e-5 and (err > 1e-4).float().mean().item() < 2e-3, (err.max().item(), err.mean().item())
 
 
+@pytest.mark.parametrize('pwc_precision', [None, 'fp32'])
 @pytest.mark.parametrize('shape', [(1, 14, 48, 48), (2, 5, 16, 24), (1, 2, 24, 24)])
-def test_bf16_path_tolerance(dev, shape):
+def test_bf16_path_tolerance(dev, shape, pwc_precision):
     B, N, H, W = shape
     sd = O.make_state_dict(0)
     burst = O.make_burst(7, B, N, H, W)
     ref_pred, ref_aux = O.dbsr_forward(burst, sd)
     net = _net(sd, dev, 'bf16')
+    net.pwc_precision = pwc_precision
     pred, aux = net(burst.to(dev))
     pred = pred.cpu()
     max_abs = (pred - ref_pred).abs().max().item()
@@ -83,7 +85,10 @@ def test_bf16_path_tolerance(dev, shape):
     bi = 40 if min(8 * H, 8 * W) > 100 else 0
     d_psnr = abs(O.psnr(pred, gt, bi) - O.psnr(ref_pred, gt, bi))
     assert d_psnr <= 0.02, d_psnr
-    assert (aux['offsets'].cpu() - ref_aux['offsets']).abs().max().item() < 1e-3   # PWC-Net stays fp32
+    flow_err = (aux['offsets'].cpu() - ref_aux['offsets']).abs().max().item()
+    # PWC-Net on bf16 tensor cores: ~1e-2 px (SURVEY.md 7 measured 8.7e-3 px for bf16 autocast); fp32 PWC: round-off
+    assert flow_err < (1e-3 if pwc_precision == 'fp32' else 5e-2), flow_err
+    print(f'bf16 path {shape} pwc={pwc_precision}: max_abs={max_abs:.3e} dPSNR={d_psnr:.4f} flow_err={flow_err:.3e}')
     frac = ((pred - ref_pred).abs() <= 1e-2).float().mean().item()
     assert frac >= 0.95
 

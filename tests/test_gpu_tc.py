@@ -29,6 +29,14 @@ TC_CASES = {
     'offset_2x64': (2, 64, 3, 1, 2, 16, 16, 1, False, False, 0),
     'upsample_shuffle': (64, 2048, 1, 1, 2, 6, 5, 1, False, False, 8),
     'dilated_d2': (128, 128, 3, 2, 1, 32, 32, 2, False, False, 0),
+    # PWC-Net long tail: odd channel counts (masked / padded N tiles), tiny maps, fp32 flow outputs, big dilations
+    'pwc_flow_565x2_f32res': (565, 2, 3, 1, 3, 16, 16, 0, True, True, 0),
+    'pwc_ext_196x196_1x1map': (196, 196, 3, 1, 5, 1, 1, 2, False, False, 0),
+    'pwc_dec_136x128': (136, 128, 3, 1, 3, 8, 8, 2, False, False, 0),
+    'pwc_dec_440x96': (440, 96, 3, 1, 3, 4, 4, 2, False, False, 0),
+    'pwc_ext_16x16': (16, 16, 3, 1, 2, 32, 32, 2, False, False, 0),
+    'pwc_ref_d8_128x96': (128, 96, 3, 8, 1, 16, 16, 2, False, False, 0),
+    'pwc_ref_d16_96x64': (96, 64, 3, 16, 1, 32, 32, 2, False, False, 0),
 }
 
 
@@ -49,7 +57,10 @@ def run_case(name, dev):
     if shuffle:
         ref = O.pixel_shuffle(ref, shuffle)
     pitch = max(8, (cin + 7) // 8 * 8)
-    xa = ops.Act(torch.zeros((n, h, w, pitch), dtype=torch.bfloat16, device=dev)).slice(0, cin)
+    c_off = 0
+    if name.startswith('pwc_dec'):       # a channel slice of a wider concat buffer
+        c_off, pitch = 448, 448 + pitch + 16
+    xa = ops.Act(torch.full((n, h, w, pitch), 7.0, dtype=torch.bfloat16, device=dev)).slice(c_off, cin)
     xa.from_nchw(x.to(dev))
     ydt = torch.float32 if out_f32 else torch.bfloat16
     if shuffle:
@@ -58,7 +69,7 @@ def run_case(name, dev):
         ya = ops.Act(torch.zeros((n, h, w, cout + 16), dtype=ydt, device=dev)).slice(16, cout)
     ra = None
     if res is not None:
-        ra = ops.Act.empty(n, h, w, cout, torch.bfloat16, dev).from_nchw(res.to(dev))
+        ra = ops.Act.empty(n, h, w, cout, ydt, dev).from_nchw(res.to(dev))
     wp = pack_tc(wt.to(dev), shuffle)
     assert ops.conv2d_tc_supported(xa, wp, b.to(dev), ya, k, 1, dil, ra, shuffle)
     ops.conv2d(xa, wp, b.to(dev), ya, k, 1, dil, act, ra, shuffle, tensor_core=True)

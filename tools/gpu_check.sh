@@ -7,7 +7,7 @@ python -c "import __graft_entry__ as g; g.build()" > gpurun_out/build.log 2>&1 |
 echo "== kernels"; timeout 900 python -m pytest tests/test_gpu_kernels.py -q -m gpu --tb=short -p no:cacheprovider > gpurun_out/kernels.log 2>&1; tail -15 gpurun_out/kernels.log
 echo "== tc probes"
 : > gpurun_out/tc.log
-for c in enc_res_64x64 enc_init_4x64 enc_out_64x512 proj_1x1_512x64 wp0_192x128 wp_res_128x128 wp_out_128x512_f32 dec_init_512x64 post_res_32x32 ragged_20x13 offset_2x64 upsample_shuffle dilated_d2; do
+for c in $(python -c "import sys; sys.path.insert(0,\"tests\"); import test_gpu_tc as t; print(\" \".join(t.TC_CASES))"); do
   timeout 120 python tests/test_gpu_tc.py $c >> gpurun_out/tc.log 2>&1 || echo "TC_CASE $c EXIT=$?" >> gpurun_out/tc.log
 done
 grep -E "TC_CASE|timeout|rror" gpurun_out/tc.log | head -40
