@@ -37,6 +37,7 @@ def parse():
     ap.add_argument('--precision', default='bf16', choices=['bf16', 'fp32'])
     ap.add_argument('--cpu-baseline-seconds', type=float, default=15.0)
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-graph', action='store_true', help='launch eagerly instead of replaying a CUDA graph')
     return ap.parse_args()
 
 
@@ -94,11 +95,11 @@ def cpu_reference_arm(args, rank):
     sd = O.make_state_dict(0)
     burst = O.make_burst(0, 1, FRAMES, args.size, args.size)
     for _ in range(max(1, min(args.warmup, 2))):
-        O.dbsr_forward(burst, sd)
+        O.dbsr_forward_fast(burst, sd)
     steps = max(1, min(args.steps, 10))
     t0 = time.perf_counter()
     for _ in range(steps):
-        O.dbsr_forward(burst, sd)
+        O.dbsr_forward_fast(burst, sd)
     dt = (time.perf_counter() - t0) / steps
     val = 1.0 / dt
     sample = f'1 burst of {FRAMES}x4x{args.size}x{args.size} per step, fp32, {steps} steps'
@@ -151,7 +152,9 @@ def main():
             return float(t.item())
         return ms
 
-    # ---- device-resident throughput ("value")
+    net.use_cuda_graph = not args.no_graph
+
+    # ---- device-resident throughput ("value"): K forwards, inputs already in HBM
     for _ in range(args.warmup):
         net(dev_in)
     barrier()
@@ -159,8 +162,6 @@ def main():
     if rank == 0:
         sampler.start()
     eng.launches = 0
-    eng.flops = {}
-    eng.timers = {}
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
@@ -170,9 +171,6 @@ def main():
     barrier()
     ms_total = max_over_ranks(e0.elapsed_time(e1))
     launches = eng.launches
-    fam = eng.timer_summary()
-    flops = dict(eng.flops)
-    eng.timers = None
     value = world * B * args.steps / (ms_total / 1e3)
 
     # ---- end to end through the public module with HOST buffers (H2D of the burst + D2H of pred inside the region)
@@ -191,6 +189,19 @@ def main():
     if rank == 0:
         sampler.stop_flag = True
         sampler.join(timeout=3)
+
+    # ---- instrumented pass (same K steps, eager launches bracketed by CUDA events on the launching stream): per
+    #      kernel-family device time for the roofline; kept out of the timed regions above because creating ~800 events
+    #      per step makes the step CPU-bound
+    net.use_cuda_graph = False
+    eng.flops = {}
+    eng.timers = {}
+    for _ in range(args.steps):
+        net(dev_in)
+    torch.cuda.synchronize()
+    fam = eng.timer_summary()
+    flops = dict(eng.flops)
+    eng.timers = None
 
     if rank != 0:
         if world > 1:
@@ -211,9 +222,22 @@ def main():
         ms, n = fam[dom]
         roofline = {'kernel': dom, 'bound': 'hbm', 'achieved': None, 'peak': pk['hbm_gbs'], 'unit': 'GB/s', 'frac': None,
                     'traffic': None, 'peak_source': pk['src'], 'launches': n, 'kernel_ms_per_step': ms / args.steps}
+    # algorithmic bytes per step of the two HBM-bound fusion kernels (SURVEY.md 8d formulas, element size s)
+    es = 2 if args.precision == 'bf16' else 4
+    C, HW = 512, S * S
+    hbm_bytes = {
+        'warp': B * ((FRAMES * C * es) * 2 + (FRAMES - 1) * 2 * 4) * HW,                 # read 14 maps, write 14 maps, flow
+        'softmax_wsum': B * (2 * FRAMES * C * es + C * es) * HW,                          # 14 feat + 14 logit maps, fused out
+    }
     families = {k: {'ms_per_step': v[0] / args.steps, 'launches_per_step': v[1] / args.steps,
-                    'tflops': (flops.get(k, 0) / (v[0] / 1e3) / 1e12) if k in flops and v[0] > 0 else None}
+                    'tflops': (flops.get(k, 0) / (v[0] / 1e3) / 1e12) if k in flops and v[0] > 0 else None,
+                    'hbm_gbs': (hbm_bytes[k] * args.steps / (v[0] / 1e3) / 1e9) if k in hbm_bytes and v[0] > 0 else None}
                 for k, v in fam.items()}
+    for k in families:
+        if families[k]['hbm_gbs'] is not None:
+            families[k]['hbm_frac'] = families[k]['hbm_gbs'] / pk['hbm_gbs']
+        if families[k]['tflops'] is not None and k == 'conv_tc':
+            families[k]['tensor_frac'] = families[k]['tflops'] / pk['tflops']
 
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
@@ -221,11 +245,11 @@ def main():
         torch.set_num_threads(cores)
         sd = O.make_state_dict(0)
         b1 = O.make_burst(0, 1, FRAMES, S, S)
-        O.dbsr_forward(b1, sd)
+        O.dbsr_forward_fast(b1, sd)
         t0 = time.perf_counter()
         n = 0
         while True:
-            O.dbsr_forward(b1, sd)
+            O.dbsr_forward_fast(b1, sd)
             n += 1
             if time.perf_counter() - t0 > args.cpu_baseline_seconds or n >= 20:
                 break
@@ -244,7 +268,7 @@ def main():
                    'l2': 'per-step activation working set (~GBs) >> 126 MB L2; no explicit flush'},
         'e2e': {'value': e2e, 'unit': 'bursts/s', 'ms_per_step': ms_e2e / args.steps,
                 'h2d_bytes_per_step': host_in.numel() * 4, 'd2h_bytes_per_step': host_out.numel() * 4},
-        'gpu_launches': launches,
+        'gpu_launches': launches, 'cuda_graph': not args.no_graph,
         'roofline': roofline,
         'kernel_families': families,
         'cpu_baseline': cpu,

@@ -20,6 +20,7 @@
 #include "common.cuh"
 
 #include <cuda.h>
+#include <stdlib.h>
 
 namespace dbsr {
 
@@ -131,9 +132,10 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[32]) {
 // K-major shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout):
 //   [0,14) start>>4 | [16,30) LBO>>4 (unused for swizzled K-major, canonical value 1) | [32,46) SBO>>4
 //   [46,48) version = 1 (sm_100) | [61,64) layout: 2 = SWIZZLE_128B, 4 = SWIZZLE_64B
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t sbo_bytes, uint32_t layout) {
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t sbo_bytes, uint32_t layout,
+                                                   uint32_t base_offset = 0) {
   return (uint64_t)((saddr >> 4) & 0x3FFFu) | (1ull << 16) | ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) |
-         (1ull << 46) | ((uint64_t)layout << 61);
+         (1ull << 46) | ((uint64_t)(base_offset & 7u) << 49) | ((uint64_t)layout << 61);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -155,13 +157,16 @@ struct ConvTcParams {
   int tiles_x, tiles_y;
   long long total_items;
   int stages;
-  int a_bytes, b_tap_bytes;  // per stage
+  int a_bytes, b_tap_bytes;  // per stage (a_bytes rounded up to 1024)
+  int a_tx_bytes;            // bytes the A box actually transfers
   // output
   void* y; int y_dtype; int y_pitch; int y_coff; int yH, yW;
   const void* res; int r_dtype; int r_pitch; int r_coff;   // residual with the geometry of y
   const float* bias;
   int act;
   int shuffle_r;        // 8: pixel shuffle addressing (y is the (8H, 8W, 32) map)
+  int halo_mode;        // experiment: 0 = one 8-wide box per kx; 1/2 = one (8+2d)-wide halo box, taps addressed at
+                        // 128-byte granularity inside it (2: descriptor base_offset = (addr >> 7) & 7)
 };
 
 // epilogue of NC (32 or 16) accumulator columns held by one thread (= one output pixel)
@@ -288,9 +293,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
           const int ch = ks - kx * p.nchunks;
           mbar_wait(&empty_bar[stage], phase ^ 1, 100 + stage);
           uint8_t* sa = smem + (size_t)stage * stage_bytes;
-          mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)stage_bytes);
+          mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)(p.a_tx_bytes + taps_per_stage * p.b_tap_bytes));
           if (p.ksize == 3) {
-            tma_load_4d(&tmap_x, &full_bar[stage], sa, ch * CK, x0 + (kx - 1) * p.dil, y0 - p.dil, img);
+            tma_load_4d(&tmap_x, &full_bar[stage], sa, ch * CK, p.halo_mode ? x0 - p.dil : x0 + (kx - 1) * p.dil,
+                        y0 - p.dil, img);
             for (int ky = 0; ky < 3; ++ky)
               tma_load_2d(&tmap_w, &full_bar[stage], sa + p.a_bytes + ky * p.b_tap_bytes, ch * CK,
                           (ky * 3 + kx) * p.cout_pad + nt * NT);
@@ -316,12 +322,20 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
           const uint32_t sb = sa + (uint32_t)p.a_bytes;
+          const int kx_h = (p.ksize == 3) ? ks / p.nchunks : 0;
+          const uint32_t halo_w = (uint32_t)(TILE_W + 2 * p.dil);
           for (int ky = 0; ky < taps_per_stage; ++ky) {
-            const uint32_t a_tap = sa + (uint32_t)(ky * p.dil) * ATOM_BYTES;
+            uint32_t a_tap = sa + (uint32_t)(ky * p.dil) * ATOM_BYTES;
+            uint32_t a_sbo = ATOM_BYTES, a_bo = 0;
+            if (p.halo_mode && p.ksize == 3) {   // tap (ky, kx) = pixel offset inside the halo box
+              a_tap = sa + ((uint32_t)(ky * p.dil) * halo_w + (uint32_t)(kx_h * p.dil)) * ROW_BYTES;
+              a_sbo = halo_w * ROW_BYTES;
+              if (p.halo_mode == 2) a_bo = (a_tap >> 7) & 7u;
+            }
             const uint32_t b_tap = sb + (uint32_t)(ky * p.b_tap_bytes);
 #pragma unroll
             for (int k16 = 0; k16 < CK / 16; ++k16) {
-              const uint64_t adesc = make_smem_desc(a_tap + k16 * 32, ATOM_BYTES, LAYOUT);
+              const uint64_t adesc = make_smem_desc(a_tap + k16 * 32, a_sbo, LAYOUT, a_bo);
               const uint64_t bdesc = make_smem_desc(b_tap + k16 * 32, ATOM_BYTES, LAYOUT);
               umma_bf16(d_tmem, adesc, bdesc, idesc, (ks | ky | k16) != 0 ? 1u : 0u);
             }
@@ -430,8 +444,13 @@ static void tc_geometry(int cin, int cout, int* ck, int* kpad, int* n_tile, int*
   *cout_pad = round_up(cout, nt);
 }
 
+static int tc_halo_mode() {
+  const char* e = getenv("DBSR_TC_HALO");
+  return e ? atoi(e) : 0;
+}
+
 struct TcConfig {
-  int n_tile, ck, nchunks, cout, cout_pad, stages, a_bytes, b_tap_bytes, smem_bytes, tmem_cols, vec_ok;
+  int n_tile, ck, nchunks, cout, cout_pad, stages, a_bytes, a_tx_bytes, b_tap_bytes, smem_bytes, tmem_cols, vec_ok;
 };
 
 static int tc_plan(const dbsr_conv_t* c, TcConfig* cfg, bool set_err) {
@@ -473,7 +492,10 @@ static int tc_plan(const dbsr_conv_t* c, TcConfig* cfg, bool set_err) {
   while (tc < 2 * nt) tc <<= 1;
   cfg->tmem_cols = tc;
   const int rows = (c->ksize == 3) ? TILE_H + 2 * c->dilation : TILE_H;
-  cfg->a_bytes = rows * TILE_W * ck * 2;
+  const int halo = tc_halo_mode();
+  const int cols = (halo && c->ksize == 3) ? TILE_W + 2 * c->dilation : TILE_W;
+  cfg->a_tx_bytes = rows * cols * ck * 2;
+  cfg->a_bytes = round_up(cfg->a_tx_bytes, 1024);
   cfg->b_tap_bytes = nt * ck * 2;
   TC_REQ(cfg->b_tap_bytes % 1024 == 0 && cfg->a_bytes % 1024 == 0, "conv2d_tc: internal: unaligned stage layout");
   const int stage = cfg->a_bytes + c->ksize * cfg->b_tap_bytes;
@@ -542,7 +564,8 @@ extern "C" int dbsr_conv2d_tc(const dbsr_conv_t* c, void* stream) {
     cuuint64_t dims[4] = {(cuuint64_t)c->x.c, (cuuint64_t)c->x.w, (cuuint64_t)c->x.h, (cuuint64_t)c->x.n};
     cuuint64_t strides[3] = {(cuuint64_t)c->x.c_pitch * 2, (cuuint64_t)c->x.w * c->x.c_pitch * 2,
                              (cuuint64_t)c->x.h * c->x.w * c->x.c_pitch * 2};
-    cuuint32_t box[4] = {(cuuint32_t)cfg.ck, (cuuint32_t)TILE_W, (cuuint32_t)rows, 1};
+    const int cols = (tc_halo_mode() && c->ksize == 3) ? TILE_W + 2 * c->dilation : TILE_W;
+    cuuint32_t box[4] = {(cuuint32_t)cfg.ck, (cuuint32_t)cols, (cuuint32_t)rows, 1};
     cuuint32_t es[4] = {1, 1, 1, 1};
     void* base = reinterpret_cast<__nv_bfloat16*>(c->x.data) + c->x.c_off;
     CUresult rc = encode(&mx, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, base, dims, strides, box, es,
@@ -571,11 +594,12 @@ extern "C" int dbsr_conv2d_tc(const dbsr_conv_t* c, void* stream) {
   p.ntiles_n = cfg.cout_pad / cfg.n_tile;
   p.tiles_x = ceil_div(p.W, TILE_W); p.tiles_y = ceil_div(p.H, TILE_H);
   p.total_items = (long long)p.n * p.tiles_x * p.tiles_y * p.ntiles_n;
-  p.stages = cfg.stages; p.a_bytes = cfg.a_bytes; p.b_tap_bytes = cfg.b_tap_bytes;
+  p.stages = cfg.stages; p.a_bytes = cfg.a_bytes; p.a_tx_bytes = cfg.a_tx_bytes; p.b_tap_bytes = cfg.b_tap_bytes;
   p.y = c->y.data; p.y_dtype = c->y.dtype; p.y_pitch = c->y.c_pitch; p.y_coff = c->y.c_off;
   p.yH = c->y.h; p.yW = c->y.w;
   p.res = c->residual.data; p.r_dtype = c->residual.dtype; p.r_pitch = c->residual.c_pitch; p.r_coff = c->residual.c_off;
   p.bias = c->bias; p.act = c->act; p.shuffle_r = r;
+  p.halo_mode = tc_halo_mode();
   cudaStream_t st = (cudaStream_t)stream;
   if (cfg.ck == 64) return launch_tc<64>(mx, mw, p, cfg.smem_bytes, st);
   return launch_tc<32>(mx, mw, p, cfg.smem_bytes, st);

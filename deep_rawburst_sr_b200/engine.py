@@ -96,6 +96,12 @@ def pack_tc(w: torch.Tensor, shuffle_r: int = 0, chmap=None, cin_buf: Optional[i
     return out.to(torch.bfloat16).contiguous()
 
 
+def permute_shuffle_rows(t: torch.Tensor, r: int) -> torch.Tensor:
+    """reorder dim 0 from PixelShuffle order (c, i, j) to the tensor-core kernel's (i, j, c) order"""
+    c = t.shape[0] // (r * r)
+    return t.reshape(c, r, r, *t.shape[1:]).permute(1, 2, 0, *range(3, t.dim() + 2)).reshape(t.shape).contiguous()
+
+
 def pack_deconv(w: torch.Tensor, chmap=None, cin_buf: Optional[int] = None) -> torch.Tensor:
     """ConvTranspose2d weight [Cin, 2, 4, 4] -> fp32 [4, 4, 2, Cin_buf]."""
     cin = w.shape[0]
@@ -110,11 +116,14 @@ def pack_deconv(w: torch.Tensor, chmap=None, cin_buf: Optional[int] = None) -> t
 
 
 class ConvW:
-    __slots__ = ('direct', 'tc', 'bias', 'ksize', 'cout', 'cin', 'shuffle_r')
+    __slots__ = ('direct', 'tc', 'bias', 'bias_tc', 'ksize', 'cout', 'cin', 'shuffle_r')
 
     def __init__(self, direct, tc, bias, ksize, cout, cin, shuffle_r=0):
         self.direct, self.tc, self.bias, self.ksize, self.cout, self.cin, self.shuffle_r = \
             direct, tc, bias, ksize, cout, cin, shuffle_r
+        self.bias_tc = bias
+        if bias is not None and shuffle_r and shuffle_r > 1:   # the tensor-core path stores in (i, j, c) row order
+            self.bias_tc = permute_shuffle_rows(bias, shuffle_r)
 
 
 class DBSREngine:
@@ -137,6 +146,7 @@ class DBSREngine:
         self.W: Dict[str, ConvW] = {}
         self.D: Dict[str, tuple] = {}
         self._ws: Dict[tuple, dict] = {}
+        self._graphs: Dict[tuple, tuple] = {}
         self.launches = 0
         self.timers = None   # when a dict: family -> list of (start, end) CUDA events on the launching stream
         self.flops = {}      # family -> algorithmic FLOPs (2*MAC, real channel counts) launched since reset
@@ -252,18 +262,26 @@ class DBSREngine:
         cw = self.W[key]
         use_tc = (cw.tc is not None and not force_direct and x.dtype == torch.bfloat16 and stride == 1)
         if use_tc:
-            use_tc = ops.conv2d_tc_supported(x, cw.tc, cw.bias, y, cw.ksize, stride, dilation, residual, cw.shuffle_r)
+            use_tc = ops.conv2d_tc_supported(x, cw.tc, cw.bias_tc, y, cw.ksize, stride, dilation, residual, cw.shuffle_r)
         self.launches += 1
         fam = 'conv_tc' if use_tc else 'conv_direct'
         ho, wo = (y.h, y.w) if cw.shuffle_r <= 1 else (y.h // cw.shuffle_r, y.w // cw.shuffle_r)
         self.flops[fam] = self.flops.get(fam, 0) + 2 * x.n * ho * wo * cw.cout * cw.cin * cw.ksize * cw.ksize
         ev = self._tic(fam)
         if use_tc:
-            ops.conv2d(x, cw.tc, cw.bias, y, cw.ksize, stride, dilation, act, residual, cw.shuffle_r, tensor_core=True)
+            ops.conv2d(x, cw.tc, cw.bias_tc, y, cw.ksize, stride, dilation, act, residual, cw.shuffle_r, tensor_core=True)
         else:
             ops.conv2d(x, cw.direct, cw.bias, y, cw.ksize, stride, dilation, act, residual, cw.shuffle_r)
         self._toc(ev)
         return y
+
+    def _run(self, family: str, fn, *args, **kw):
+        """launch one kernel through ops.*, counted and (optionally) timed under `family`"""
+        ev = self._tic(family)
+        r = fn(*args, **kw)
+        self._toc(ev)
+        self.launches += 1
+        return r
 
     def _tic(self, family: str):
         if self.timers is None:
@@ -346,21 +364,16 @@ class DBSREngine:
             flow = self._buf(ws, f'flow{lvl}', pairs, h, w, 2, torch.float32)
             vol = cat.slice(lay.off['V'], 81)
             if prev_cat is None:
-                ev = self._tic('corr81')
-                ops.corr81(f1, f2, vol, pairs, group, act=ACT_LRELU)
-                self._toc(ev)
-                self.launches += 1
+                self._run('corr81', ops.corr81, f1, f2, vol, pairs, group, act=ACT_LRELU)
             else:
                 upflow = self._buf(ws, f'upflow{lvl}', pairs, h, w, 2, torch.float32)
                 wf, bf = self.D[f'{pre}net{lname}.netUpflow']
-                ops.deconv4x4s2(prev_flow, wf, bf, cat.slice(lay.off['upflow'], 2), upflow)
+                self._run('deconv', ops.deconv4x4s2, prev_flow, wf, bf, cat.slice(lay.off['upflow'], 2), upflow)
                 wt, bt = self.D[f'{pre}net{lname}.netUpfeat']
-                ops.deconv4x4s2(prev_cat, wt, bt, cat.slice(lay.off['upfeat'], 2))
-                ops.copy_channels(f1, cat.slice(lay.off['f1'], lay.sizes['f1']), group, src_group, 0)
-                ev = self._tic('corr81')
-                ops.corr81(f1, f2, vol, pairs, group, flow=upflow, flow_scale=PWC_BACKWARP[lvl], act=ACT_LRELU)
-                self._toc(ev)
-                self.launches += 4
+                self._run('deconv', ops.deconv4x4s2, prev_cat, wt, bt, cat.slice(lay.off['upfeat'], 2))
+                self._run('copy', ops.copy_channels, f1, cat.slice(lay.off['f1'], lay.sizes['f1']), group, src_group, 0)
+                self._run('corr81', ops.corr81, f1, f2, vol, pairs, group, flow=upflow, flow_scale=PWC_BACKWARP[lvl],
+                          act=ACT_LRELU)
             for j, sub in enumerate(PWC_NAMES[:5]):
                 _cm, start, length = lay.chmap_from(segs[j])
                 out_name = 'o%d' % (j + 1)
@@ -385,8 +398,7 @@ class DBSREngine:
         each frame is computed once (the reference recomputes the reference frame's pyramid N-1 times)."""
         feats = self.pwc_extract(ws, pwc_in)
         flow4 = self.pwc_decode(ws, feats, feats, B * (N - 1), N - 1, N)
-        ops.flow_head(flow4, offsets, H, W, pwc_in.h, pwc_in.w)
-        self.launches += 1
+        self._run('flow_head', ops.flow_head, flow4, offsets, H, W, pwc_in.h, pwc_in.w)
         return offsets
 
     # ------------------------------------------------------------------------------------------------
@@ -418,10 +430,9 @@ class DBSREngine:
         proj = self._buf(ws, 'proj', F_, H, W, pd, dt)
         self._conv('merging.feat_project_layer.0', all_feat, proj, ACT_RELU)
         wp_in = self._buf(ws, 'wp_in', F_, H, W, 2 * pd + od, dt)
-        ops.build_wp_input(proj, wp_in, N)
+        self._run('build_wp_input', ops.build_wp_input, proj, wp_in, N)
         offm = self._buf(ws, 'offm', F_, H, W, 8, dt)
-        ops.offsets_mod(offsets, offm, B, N, self.offset_modulo)
-        self.launches += 2
+        self._run('offsets_mod', ops.offsets_mod, offsets, offm, B, N, self.offset_modulo)
         oa = self._buf(ws, 'off_a', F_, H, W, od, dt)
         ob = self._buf(ws, 'off_b', F_, H, W, od, dt)
         ot = self._buf(ws, 'off_t', F_, H, W, od, dt)
@@ -433,8 +444,7 @@ class DBSREngine:
             self._resblock(f'merging.offset_feat_extractor.{i + 1}', cur, ot, dst)
             cur, nxt = dst, cur
         if self.off_res == 0:
-            ops.copy_channels(oa, wp_in.slice(2 * pd, od))
-            self.launches += 1
+            self._run('copy', ops.copy_channels, oa, wp_in.slice(2 * pd, od))
         wa = self._buf(ws, 'wp_a', F_, H, W, wd, dt)
         wb = self._buf(ws, 'wp_b', F_, H, W, wd, dt)
         wt = self._buf(ws, 'wp_t', F_, H, W, wd, dt)
@@ -446,10 +456,8 @@ class DBSREngine:
         logits = self._buf(ws, 'logits', F_, H, W, self.feat_dim, self.logits_dtype)
         self._conv(f'merging.weight_predictor.{self.wp_res + 1}.0', cur, logits, ACT_NONE)
         fused = self._buf(ws, 'fused', B, H, W, self.feat_dim, dt)
-        ev = self._tic('softmax_wsum')
-        ops.softmax_wsum(all_feat, logits, fused, N, offsets=None, weights_out=weights_out)
-        self._toc(ev)
-        self.launches += 1 + (1 if weights_out is not None else 0)
+        self._run('softmax_wsum', ops.softmax_wsum, all_feat, logits, fused, N, offsets=None, weights_out=weights_out)
+        self.launches += (1 if weights_out is not None else 0)
         return fused
 
     def decode(self, ws: dict, fused: Act, pred: torch.Tensor) -> torch.Tensor:
@@ -470,16 +478,14 @@ class DBSREngine:
         ht = self._buf(ws, 'hr_t', B, H * r, W * r, self.post_dim, dt)
         self._conv('decoder.upsample_layer.conv_layer.0', cur, ha, ACT_RELU)      # 1x1 conv + ReLU + PixelShuffle
         if self.gauss is not None:
-            ops.blur3x3(ha, hb, self.gauss)
-            self.launches += 1
+            self._run('blur3x3', ops.blur3x3, ha, hb, self.gauss)
             cur, nxt = hb, ha
         else:
             cur, nxt = ha, hb
         for i in range(self.dec_post):
             self._resblock(f'decoder.post_res_layers.{i}', cur, ht, nxt)
             cur, nxt = nxt, cur
-        ops.predictor(cur, self.pred_w, self.pred_b, pred)
-        self.launches += 1
+        self._run('predictor', ops.predictor, cur, self.pred_w, self.pred_b, pred)
         return pred
 
     # ------------------------------------------------------------------------------------------------
@@ -499,8 +505,7 @@ class DBSREngine:
         F_ = B * N
         enc_in = self._buf(ws, 'enc_in', F_, H, W, 8, self.act_dtype)
         pwc_in = self._buf(ws, 'pwc_in', F_, Hp, Wp, 4, torch.float32)
-        ops.prep_burst(burst, enc_in, pwc_in)
-        self.launches += 1
+        self._run('prep_burst', ops.prep_burst, burst, enc_in, pwc_in)
         if out is None:
             out = {}
         offsets = out.get('offsets')
@@ -509,10 +514,7 @@ class DBSREngine:
         self.pwc_burst(ws, pwc_in, B, N, H, W, offsets)
         feat = self.encode(ws, enc_in)
         all_feat = self._buf(ws, 'all_feat', F_, H, W, self.feat_dim, self.act_dtype)
-        ev = self._tic('warp')
-        ops.warp(feat, offsets, all_feat, frames=N)
-        self._toc(ev)
-        self.launches += 1
+        self._run('warp', ops.warp, feat, offsets, all_feat, frames=N)
         weights = None
         if return_weights:
             weights = torch.empty((B, N, self.feat_dim, H, W), dtype=torch.float32, device=self.device)
@@ -522,3 +524,35 @@ class DBSREngine:
             pred = torch.empty((B, 3, H * self.up_r, W * self.up_r), dtype=torch.float32, device=self.device)
         self.decode(ws, fused, pred)
         return pred, offsets.view(B, N - 1, 2, H, W), weights
+
+    # ------------------------------------------------------------------------------------------------
+    # CUDA-graph replay of the whole forward (launch-bound at small batch: ~400 launches per forward)
+    # ------------------------------------------------------------------------------------------------
+    @torch.no_grad()
+    def forward_graphed(self, burst: torch.Tensor, return_weights: bool = False):
+        """Same as forward(), but the launch sequence is captured once per input shape into a CUDA graph and replayed.
+        The returned tensors are the graph's static outputs: they are overwritten by the next call of the same shape."""
+        ops.require_device(burst)
+        burst = burst.contiguous().float()
+        key = (tuple(burst.shape), bool(return_weights))
+        entry = self._graphs.get(key)
+        if entry is None:
+            assert self.timers is None, 'per-kernel timers cannot be recorded inside a graph capture'
+            static_in = torch.empty_like(burst)
+            static_in.copy_(burst)
+            side = torch.cuda.Stream(device=self.device)
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):          # warm-up outside capture: workspaces, smem attributes, tensor maps
+                self.forward(static_in, return_weights)
+            torch.cuda.current_stream().wait_stream(side)
+            launches0 = self.launches
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                outs = self.forward(static_in, return_weights)
+            entry = (graph, static_in, outs, self.launches - launches0)
+            self._graphs[key] = entry
+        graph, static_in, outs, n_launch = entry
+        static_in.copy_(burst, non_blocking=True)
+        graph.replay()
+        self.launches += n_launch + 1
+        return outs

@@ -33,6 +33,8 @@ class DBSRNet(nn.Module):
         self.logits_fp32 = False
         self.pwc_precision = None      # None: follow `precision`; 'fp32' keeps PWC-Net (flow) on the exact CUDA-core path
         self.return_fusion_weights = False
+        self.use_cuda_graph = False    # True: capture the launch sequence per input shape and replay it (outputs are
+                                       # static buffers, overwritten by the next call with the same shape)
         self._engine = None
 
     def _apply(self, fn, *a, **k):
@@ -72,7 +74,9 @@ class DBSRNet(nn.Module):
             out_dec = self.decoder(out_merge)
             return out_dec['pred'], {'offsets': out_enc['offsets'], 'fusion_weights': out_merge['fusion_weights']}
         ops.require_device(im)
-        pred, offsets, weights = self.engine(im.device).forward(im, return_weights=self.return_fusion_weights)
+        eng = self.engine(im.device)
+        run = eng.forward_graphed if (self.use_cuda_graph and eng.timers is None) else eng.forward
+        pred, offsets, weights = run(im, return_weights=self.return_fusion_weights)
         return pred, {'offsets': offsets, 'fusion_weights': weights}
 
 

@@ -503,3 +503,107 @@ def psnr(pred, gt, boundary_ignore: int = 40, max_value: float = 1.0):
         mse = ((p.double() - g.double()) ** 2).mean()
         vals.append(20 * math.log10(max_value) - 10.0 * math.log10(float(mse)))
     return sum(vals) / len(vals)
+
+
+# ----------------------------------------------------------------------------------------------------
+# Library-op restatement: the SAME op sequence the reference modules execute (ATen grid_sample /
+# interpolate / conv_transpose2d / pixel_shuffle / softmax), used as the timed CPU arm of bench.py
+# (`cpu_baseline`, `--impl reference`) so that the baseline runs at the reference's own speed rather than
+# at the speed of the explicit-gather restatement above.  tests/test_oracle.py pins it to the explicit one.
+# ----------------------------------------------------------------------------------------------------
+def _ref_backwarp(f2, flow):
+    """pwcnet.py:16-38 verbatim op sequence."""
+    n, c, H, W = f2.shape
+    hor = torch.linspace(-1.0 + 1.0 / W, 1.0 - 1.0 / W, W).view(1, 1, 1, -1).expand(-1, -1, H, -1)
+    ver = torch.linspace(-1.0 + 1.0 / H, 1.0 - 1.0 / H, H).view(1, 1, -1, 1).expand(-1, -1, -1, W)
+    grid = torch.cat([hor, ver], 1)
+    flow = torch.cat([flow[:, 0:1] / ((W - 1.0) / 2.0), flow[:, 1:2] / ((H - 1.0) / 2.0)], 1)
+    inp = torch.cat([f2, f2.new_ones(n, 1, H, W)], 1)
+    out = F.grid_sample(inp, (grid + flow).permute(0, 2, 3, 1), mode='bilinear', padding_mode='zeros', align_corners=False)
+    mask = out[:, -1:]
+    mask = (mask > 0.999).to(out.dtype)
+    return out[:, :-1] * mask
+
+
+def _ref_corr(f1, f2):
+    n, c, H, W = f1.shape
+    f2p = F.pad(f2, (4, 4, 4, 4))
+    return torch.cat([(f1 * f2p[:, :, dy:dy + H, dx:dx + W]).mean(1, keepdim=True) for dy in range(9) for dx in range(9)], 1)
+
+
+def _ref_warp(feat, flow):
+    """models/layers/warp.py:19-46 verbatim op sequence."""
+    B, C, H, W = feat.shape
+    rowv, colv = torch.meshgrid([torch.arange(0.5, H + 0.5), torch.arange(0.5, W + 0.5)], indexing='ij')
+    grid = torch.stack((colv, rowv), dim=0).unsqueeze(0).float() + flow
+    gn = torch.stack((2.0 * grid[:, 0] / W - 1.0, 2.0 * grid[:, 1] / H - 1.0), dim=1).permute(0, 2, 3, 1)
+    return F.grid_sample(feat, gn, mode='bilinear', padding_mode='zeros', align_corners=False)
+
+
+@torch.no_grad()
+def dbsr_forward_fast(im, sd):
+    """DBSRNet.forward with the reference's own library-op sequence (CPU timing arm)."""
+    B, N, _, H, W = im.shape
+    pre = 'encoder.alignment_net.net.'
+    x_rgb = torch.stack((im[:, :, 0], im[:, :, 1:3].mean(dim=2), im[:, :, 3]), dim=2)
+    x_ref = x_rgb[:, :1].repeat(1, N - 1, 1, 1, 1).contiguous().view(-1, 3, H, W)
+    x_oth = x_rgb[:, 1:].contiguous().view(-1, 3, H, W)
+    Hp = int(math.floor(math.ceil(H / 64.0) * 64.0))
+    Wp = int(math.floor(math.ceil(W / 64.0) * 64.0))
+    src_re = F.interpolate(x_oth, size=(Hp, Wp), mode='bilinear', align_corners=False)
+    tgt_re = F.interpolate(x_ref, size=(Hp, Wp), mode='bilinear', align_corners=False)
+    f1 = pwc_extractor(tgt_re, sd, pre)
+    f2 = pwc_extractor(src_re, sd, pre)
+    est = None
+    for lvl in (6, 5, 4, 3, 2):
+        name = PWC_LEVEL_NAMES[lvl - 1]
+        k = f'{pre}net{name}'
+        a, b = f1[lvl - 1], f2[lvl - 1]
+        if est is None:
+            feat = F.leaky_relu(_ref_corr(a, b), 0.1)
+        else:
+            upflow = F.conv_transpose2d(est['flow'], sd[k + '.netUpflow.weight'], sd[k + '.netUpflow.bias'], stride=2, padding=1)
+            upfeat = F.conv_transpose2d(est['feat'], sd[k + '.netUpfeat.weight'], sd[k + '.netUpfeat.bias'], stride=2, padding=1)
+            vol = F.leaky_relu(_ref_corr(a, _ref_backwarp(b, upflow * PWC_BACKWARP_SCALE[lvl])), 0.1)
+            feat = torch.cat([vol, a, upflow, upfeat], 1)
+        for sub in PWC_LEVEL_NAMES[:5]:
+            feat = torch.cat([F.leaky_relu(conv(feat, sd, f'{k}.net{sub}.0'), 0.1), feat], 1)
+        est = {'flow': conv(feat, sd, f'{k}.netSix.0'), 'feat': feat}
+    x = est['feat']
+    for j, (_ci, _co, d) in enumerate(PWC_REFINER):
+        x = conv(x, sd, f'{pre}netRefiner.netMain.{2 * j}', padding=d, dilation=d)
+        if j < len(PWC_REFINER) - 1:
+            x = F.leaky_relu(x, 0.1)
+    flow = 20.0 * F.interpolate(est['flow'] + x, size=(H, W), mode='bilinear', align_corners=False)
+    offsets = torch.stack((flow[:, 0] * (float(W) / Wp), flow[:, 1] * (float(H) / Hp)), dim=1)
+    out = torch.relu(conv(im.view(-1, 4, H, W), sd, 'encoder.init_layer.0'))
+    for i in range(ENC_NUM_RES):
+        out = resblock(out, sd, f'encoder.res_layers.{i}')
+    feat = torch.relu(conv(out, sd, 'encoder.out_layer.0')).view(B, N, ENC_OUT_DIM, H, W)
+    oth = _ref_warp(feat[:, 1:].contiguous().view(-1, ENC_OUT_DIM, H, W), offsets).view(B, N - 1, ENC_OUT_DIM, H, W)
+    offsets = offsets.view(B, N - 1, 2, H, W)
+    all_feat = torch.cat((feat[:, :1].contiguous(), oth), dim=1)
+    proj = torch.relu(conv(all_feat.view(-1, ENC_OUT_DIM, H, W), sd, 'merging.feat_project_layer.0', padding=0)).view(B, N, -1, H, W)
+    base = proj[:, :1].contiguous()
+    diff = (proj - base).view(-1, PROJ_DIM, H, W)
+    base = base.expand(-1, N, -1, -1, -1).contiguous().view(-1, PROJ_DIM, H, W)
+    offs = torch.cat((torch.zeros(B, 1, 2, H, W), offsets), dim=1).view(-1, 2, H, W) % OFFSET_MODULO
+    of = torch.relu(conv(offs, sd, 'merging.offset_feat_extractor.0.0'))
+    for i in range(NUM_OFFSET_RES):
+        of = resblock(of, sd, f'merging.offset_feat_extractor.{i + 1}')
+    wp = torch.relu(conv(torch.cat([base, diff, of], dim=1), sd, 'merging.weight_predictor.0.0'))
+    for i in range(NUM_WP_RES):
+        wp = resblock(wp, sd, f'merging.weight_predictor.{i + 1}')
+    logits = conv(wp, sd, f'merging.weight_predictor.{NUM_WP_RES + 1}.0').view(B, N, ENC_OUT_DIM, H, W)
+    w = F.softmax(logits, dim=1)
+    fused = (all_feat * w).sum(dim=1)
+    out = torch.relu(conv(fused, sd, 'decoder.init_layer.0'))
+    for i in range(DEC_NUM_PRE_RES):
+        out = resblock(out, sd, f'decoder.pre_res_layers.{i}')
+    up = F.pixel_shuffle(torch.relu(F.conv2d(out, sd['decoder.upsample_layer.conv_layer.0.weight'])), UPSAMPLE)
+    shp = up.shape
+    up = F.conv2d(up.view(-1, 1, *shp[-2:]), gauss_kernel3().view(1, 1, 3, 3), padding=1).view(shp)
+    for i in range(DEC_NUM_POST_RES):
+        up = resblock(up, sd, f'decoder.post_res_layers.{i}')
+    pred = torch.relu(conv(up, sd, 'decoder.predictor.0', padding=0))
+    return pred, {'offsets': offsets, 'fusion_weights': w}

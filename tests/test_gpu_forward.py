@@ -135,3 +135,18 @@ def test_cpu_input_is_refused(dev):
     net = _net(O.make_state_dict(0), dev, 'bf16')
     with pytest.raises(NotImplementedError):
         net(O.make_burst(0, 1, 2, 16, 16))
+
+
+def test_cuda_graph_replay_matches_eager(dev):
+    sd = O.make_state_dict(0)
+    net = _net(sd, dev, 'bf16')
+    net.return_fusion_weights = False
+    b1 = O.make_burst(11, 2, 4, 16, 16).to(dev)
+    b2 = O.make_burst(12, 2, 4, 16, 16).to(dev)
+    e1 = net(b1)[0].clone()
+    e2 = net(b2)[0].clone()
+    net.use_cuda_graph = True
+    g1 = net(b1)[0].clone()
+    g2 = net(b2)[0].clone()     # replay of the graph captured for b1's shape
+    g1b = net(b1)[0].clone()
+    assert torch.equal(e1, g1) and torch.equal(e2, g2) and torch.equal(g1, g1b)

@@ -42,7 +42,7 @@ TC_CASES = {
 
 def run_case(name, dev):
     from deep_rawburst_sr_b200 import ops
-    from deep_rawburst_sr_b200.engine import pack_tc
+    from deep_rawburst_sr_b200.engine import pack_tc, permute_shuffle_rows
     cin, cout, k, dil, n, h, w, act, use_res, out_f32, shuffle = TC_CASES[name]
     g = torch.Generator().manual_seed(sum(map(ord, name)))
     x = torch.randn(n, cin, h, w, generator=g).bfloat16().float()
@@ -71,8 +71,9 @@ def run_case(name, dev):
     if res is not None:
         ra = ops.Act.empty(n, h, w, cout, ydt, dev).from_nchw(res.to(dev))
     wp = pack_tc(wt.to(dev), shuffle)
-    assert ops.conv2d_tc_supported(xa, wp, b.to(dev), ya, k, 1, dil, ra, shuffle)
-    ops.conv2d(xa, wp, b.to(dev), ya, k, 1, dil, act, ra, shuffle, tensor_core=True)
+    bd = b.to(dev) if not shuffle else permute_shuffle_rows(b.to(dev), shuffle)   # bias follows the packed row order
+    assert ops.conv2d_tc_supported(xa, wp, bd, ya, k, 1, dil, ra, shuffle)
+    ops.conv2d(xa, wp, bd, ya, k, 1, dil, act, ra, shuffle, tensor_core=True)
     torch.cuda.synchronize()
     got = ya.to_nchw().cpu()
     err = (got - ref).abs().max().item()

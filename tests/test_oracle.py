@@ -88,3 +88,13 @@ def test_forward_against_reference(golden_dir, name):
     fw = aux['fusion_weights']
     assert np.abs(fw[:, :, ::37, ::3, ::3].numpy() - g['fusion_weights_sub']).max() < 2e-5
     assert np.abs(fw.mean(dim=(2, 3, 4)).numpy() - g['fusion_weights_mean']).max() < 1e-5
+
+
+def test_library_op_restatement_matches_explicit_oracle():
+    """the timed CPU arm (same library-op sequence as the reference) == the explicit-arithmetic oracle"""
+    sd = O.make_state_dict(1)
+    burst = O.make_burst(4, 1, 3, 16, 24)
+    p0, a0 = O.dbsr_forward(burst, sd)
+    p1, a1 = O.dbsr_forward_fast(burst, sd)
+    assert (p0 - p1).abs().max().item() < 2e-5
+    assert (a0['offsets'] - a1['offsets']).abs().max().item() < 1e-4
