@@ -1,22 +1,27 @@
 // tcgen05 / TMEM implicit-GEMM convolution for sm_100a (bf16 operands, fp32 accumulation in tensor memory).
 //
-// Replaces the cuDNN fp32 convs + separate ReLU / residual-add kernels of the DBSR encoder, fusion weight
-// predictor and decoder (reference models/layers/blocks.py:46-96, models/dbsr/{encoders,merging,decoders}.py).
+// Replaces the cuDNN fp32 convs + separate ReLU / LeakyReLU / residual-add / concat kernels of the DBSR encoder, fusion
+// weight predictor, decoder and of PWC-Net (reference models/layers/blocks.py:46-96, models/dbsr/*.py,
+// models/alignment/pwcnet.py:49-204).
 //
 // GEMM view:  D[pixels, Cout] = sum_{tap, cin} X[pixel + tap, cin] * W[tap, cout, cin]
-//   M tile   : 128 output pixels = 16 rows x 8 columns of one image (one TMEM lane per pixel)
-//   N tile   : n_tile output channels (any multiple of 16 up to 128) = TMEM columns, double buffered
-//   K loop   : for kx in 0..2 : for cin chunk of CK (64 -> SWIZZLE_128B rows, 32 -> SWIZZLE_64B rows):
-//                one TMA box {CK ch, 8 px, 16 + 2*dil rows} of the NHWC input at (x0 + (kx-1)*dil, y0 - dil)
-//                -- out-of-image coordinates are zero-filled by TMA, which IS the conv zero padding --
-//                serves the three ky taps: 8 pixels x CK channels is exactly one swizzle atom, so the tap
-//                (ky) view of the tile is the same smem at a +ky*dil*atom byte offset (1024 B / 512 B aligned).
-//                The three [n_tile x CK] weight tiles of (ky, kx) ride in the same pipeline stage.
-//   Roles    : warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread tcgen05.mma issuer,
-//              warps 2..5 = epilogue (tcgen05.ld -> +bias, +residual, activation -> bf16/fp32 global stores).
-//   Persistent: grid = min(#work items, #SMs); work item = (pixel tile, N tile), N tile fastest.
-//   Pixel-shuffle (upsampling.py:57) is folded into the store addressing: the packed weight rows are
-//   permuted to (i, j, c) order so an N tile of 128 channels is 4 adjacent HR pixels x 32 channels, contiguous.
+//   work item: 16 x (8*mt) output pixels of one image (mt = 1 or 2 side-by-side 16x8 tiles, one M=128 accumulator
+//              each, sharing every weight tile) x one N tile (n_tile = any multiple of 16 up to 128 = TMEM columns).
+//   A operand: per K chunk (CK = 64 channels -> SWIZZLE_128B rows, 32 -> SWIZZLE_64B) ONE TMA box
+//              {CK ch, 8*mt + 2*dil px, 16 + 2*dil rows} of the NHWC input, i.e. the tile plus its halo.  Coordinates
+//              outside the image are zero-filled by TMA, which IS the conv zero padding.  All 9 taps read this box in
+//              place: the UMMA descriptor of tap (ky, kx) starts (ky*dil*halo_w + kx*dil) pixel rows (128/64 B each)
+//              into the box with SBO = halo_w pixel rows.  (Swizzling is a function of the absolute smem address, so
+//              a 128 B-granular start inside a TMA-written box is consistent -- verified on B200.)
+//   B operand: [n_tile x CK] weight tile per (chunk, tap).  Streamed through its own mbarrier ring, or -- when all
+//              taps x chunks fit next to the A ring (e.g. 64->64: 72 KB) -- loaded once per CTA and kept resident.
+//   roles    : warp 0 = A (activation) TMA producer, warp 2 = B (weight) TMA producer, warp 1 = TMEM allocator +
+//              single-thread tcgen05.mma issuer, warps 3..6 = epilogue (tcgen05.ld -> +bias, +residual, activation ->
+//              bf16 / fp32 stores; masked generic path for odd channel counts).  TMEM accumulators are double
+//              buffered so the epilogue of item i overlaps the MMAs of item i+1.
+//   persistent: grid = min(#items, #SMs); static round-robin over items, N tile fastest.
+//   Pixel-shuffle (upsampling.py:57) is folded into the store addressing: the packed weight rows are permuted to
+//   (i, j, c) order so an N tile of 128 channels is 4 adjacent HR pixels x 32 channels, contiguous.
 #include "common.cuh"
 
 #include <cuda.h>
@@ -142,7 +147,7 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t sbo_
 // kernel
 // ---------------------------------------------------------------------------------------------------------
 constexpr int TILE_H = 16, TILE_W = 8;
-constexpr int TC_THREADS = 192;
+constexpr int TC_THREADS = 224;
 
 struct ConvTcParams {
   int n, H, W;          // input == output spatial size (stride 1, "same" padding)
@@ -151,22 +156,21 @@ struct ConvTcParams {
   int cout_pad;         // rows per tap in the packed weight matrix (= ntiles_n * n_tile)
   int cout;             // real output channels (stores are masked beyond it)
   int n_tile;           // UMMA N (multiple of 16, <= 128)
-  int tmem_cols;        // power of two >= max(32, 2 * n_tile)
+  int mt;               // 16x8 tiles per item (1 or 2, side by side along x)
+  int tmem_cols;        // power of two >= max(32, 2 * mt * n_tile)
   int vec_ok;           // 1: aligned fast path (16-byte accesses, every 32-column chunk fully inside cout)
   int ntiles_n;         // cout_pad / n_tile
-  int tiles_x, tiles_y;
+  int items_x, tiles_y;
   long long total_items;
-  int stages;
-  int a_bytes, b_tap_bytes;  // per stage (a_bytes rounded up to 1024)
-  int a_tx_bytes;            // bytes the A box actually transfers
+  int a_slots, b_stages, b_resident;
+  int a_bytes, a_tx_bytes, b_bytes;
+  int halo_w;           // pixels per row of the A box
   // output
   void* y; int y_dtype; int y_pitch; int y_coff; int yH, yW;
   const void* res; int r_dtype; int r_pitch; int r_coff;   // residual with the geometry of y
   const float* bias;
   int act;
   int shuffle_r;        // 8: pixel shuffle addressing (y is the (8H, 8W, 32) map)
-  int halo_mode;        // experiment: 0 = one 8-wide box per kx; 1/2 = one (8+2d)-wide halo box, taps addressed at
-                        // 128-byte granularity inside it (2: descriptor base_offset = (addr >> 7) & 7)
 };
 
 // epilogue of NC (32 or 16) accumulator columns held by one thread (= one output pixel)
@@ -178,6 +182,12 @@ __device__ __forceinline__ void epilogue_chunk(const ConvTcParams& p, const uint
 #pragma unroll
   for (int j = 0; j < NC; ++j) v[j] = __uint_as_float(r[j]);
   if (p.vec_ok) {
+    uint4 rq[NC / 8];
+    if (p.res) {   // bf16 on the fast path; issue the loads first so they overlap the bias math
+      const __nv_bfloat16* rp = reinterpret_cast<const __nv_bfloat16*>(p.res) + roff;
+#pragma unroll
+      for (int j = 0; j < NC / 8; ++j) rq[j] = __ldg(reinterpret_cast<const uint4*>(rp + 8 * j));
+    }
     if (p.bias) {
 #pragma unroll
       for (int j = 0; j < NC; j += 4) {
@@ -185,16 +195,14 @@ __device__ __forceinline__ void epilogue_chunk(const ConvTcParams& p, const uint
         v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
       }
     }
-    if (p.res) {   // bf16 on the fast path
-      const __nv_bfloat16* rp = reinterpret_cast<const __nv_bfloat16*>(p.res) + roff;
+    if (p.res) {
 #pragma unroll
-      for (int j = 0; j < NC; j += 8) {
-        const uint4 q = __ldg(reinterpret_cast<const uint4*>(rp + j));
-        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&q);
+      for (int j = 0; j < NC / 8; ++j) {
+        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&rq[j]);
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
           const float2 f = __bfloat1622float2(h[k]);
-          v[j + 2 * k] += f.x; v[j + 2 * k + 1] += f.y;
+          v[8 * j + 2 * k] += f.x; v[8 * j + 2 * k + 1] += f.y;
         }
       }
     }
@@ -237,32 +245,48 @@ __device__ __forceinline__ void epilogue_chunk(const ConvTcParams& p, const uint
   }
 }
 
+struct ItemCoord { int nt, img, y0, x0; };
+__device__ __forceinline__ ItemCoord decode_item(const ConvTcParams& p, long long item) {
+  ItemCoord c;
+  c.nt = (int)(item % p.ntiles_n);
+  const long long tm = item / p.ntiles_n;
+  const int per_img = p.items_x * p.tiles_y;
+  c.img = (int)(tm / per_img);
+  const int rem = (int)(tm - (long long)c.img * per_img);
+  c.y0 = (rem / p.items_x) * TILE_H;
+  c.x0 = (rem % p.items_x) * (TILE_W * p.mt);
+  return c;
+}
+
 template <int CK>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
                const ConvTcParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  // carve: [stages x (A | B taps)] then barriers
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  const int taps_per_stage = p.ksize;  // 3 (ky) for 3x3, 1 for 1x1
-  const int stage_bytes = p.a_bytes + taps_per_stage * p.b_tap_bytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * stage_bytes);
-  uint64_t* full_bar = bars;
-  uint64_t* empty_bar = bars + p.stages;
-  uint64_t* tfull_bar = bars + 2 * p.stages;
+  uint8_t* smem_a = smem;                                         // [a_slots][a_bytes]
+  uint8_t* smem_b = smem + (size_t)p.a_slots * p.a_bytes;         // [b_stages][b_bytes]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_b + (size_t)p.b_stages * p.b_bytes);
+  uint64_t* a_full = bars;
+  uint64_t* a_empty = a_full + p.a_slots;
+  uint64_t* b_full = a_empty + p.a_slots;
+  uint64_t* b_empty = b_full + p.b_stages;
+  uint64_t* tfull_bar = b_empty + p.b_stages;
   uint64_t* tempty_bar = tfull_bar + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  constexpr uint32_t ROW_BYTES = CK * 2;                 // bytes per pixel row of a K chunk
-  constexpr uint32_t ATOM_BYTES = 8 * ROW_BYTES;         // 8 rows: 1024 (SW128) / 512 (SW64)
+  constexpr uint32_t ROW_BYTES = CK * 2;                 // bytes per pixel of a K chunk
   constexpr uint32_t LAYOUT = (CK == 64) ? 2u : 4u;
   // cute::UMMA::InstrDescriptor: c_format F32 [4,6) | a,b format BF16 [7,10),[10,13) | K-major | N>>3 [17,23) | M>>4 [24,29)
   const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.n_tile >> 3) << 17) | ((128u >> 4) << 24);
   const int NT = p.n_tile;
+  const int taps = p.ksize * p.ksize;
+  const int pad = (p.ksize == 3) ? p.dil : 0;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < p.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < p.a_slots; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
+    for (int s = 0; s < p.b_stages; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -275,119 +299,135 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const int ksteps = (p.ksize == 3 ? 3 : 1) * p.nchunks;
-  const int tiles_per_img = p.tiles_x * p.tiles_y;
-
   if (warp == 0) {
-    // ===================== TMA producer =====================
+    // ===================== A producer: one halo box per (item, K chunk) =====================
     if (lane == 0) {
-      int stage = 0; uint32_t phase = 0;
+      int slot = 0; uint32_t phase = 0;
       for (long long item = blockIdx.x; item < p.total_items; item += gridDim.x) {
-        const int nt = (int)(item % p.ntiles_n);
-        const long long tm = item / p.ntiles_n;
-        const int img = (int)(tm / tiles_per_img);
-        const int trem = (int)(tm - (long long)img * tiles_per_img);
-        const int y0 = (trem / p.tiles_x) * TILE_H, x0 = (trem % p.tiles_x) * TILE_W;
-        for (int ks = 0; ks < ksteps; ++ks) {
-          const int kx = (p.ksize == 3) ? ks / p.nchunks : 0;
-          const int ch = ks - kx * p.nchunks;
-          mbar_wait(&empty_bar[stage], phase ^ 1, 100 + stage);
-          uint8_t* sa = smem + (size_t)stage * stage_bytes;
-          mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)(p.a_tx_bytes + taps_per_stage * p.b_tap_bytes));
-          if (p.ksize == 3) {
-            tma_load_4d(&tmap_x, &full_bar[stage], sa, ch * CK, p.halo_mode ? x0 - p.dil : x0 + (kx - 1) * p.dil,
-                        y0 - p.dil, img);
-            for (int ky = 0; ky < 3; ++ky)
-              tma_load_2d(&tmap_w, &full_bar[stage], sa + p.a_bytes + ky * p.b_tap_bytes, ch * CK,
-                          (ky * 3 + kx) * p.cout_pad + nt * NT);
-          } else {
-            tma_load_4d(&tmap_x, &full_bar[stage], sa, ch * CK, x0, y0, img);
-            tma_load_2d(&tmap_w, &full_bar[stage], sa + p.a_bytes, ch * CK, nt * NT);
+        const ItemCoord c = decode_item(p, item);
+        for (int ch = 0; ch < p.nchunks; ++ch) {
+          mbar_wait(&a_empty[slot], phase ^ 1, 100 + slot);
+          mbar_arrive_expect_tx(&a_full[slot], (uint32_t)p.a_tx_bytes);
+          tma_load_4d(&tmap_x, &a_full[slot], smem_a + (size_t)slot * p.a_bytes, ch * CK, c.x0 - pad, c.y0 - pad, c.img);
+          if (++slot == p.a_slots) { slot = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 2) {
+    // ===================== B producer: weight tiles =====================
+    if (lane == 0) {
+      if (p.b_resident) {
+        // every item uses the same tiles (ntiles_n == 1): load each (chunk, tap) tile once and keep it
+        for (int t = 0; t < p.nchunks * taps; ++t) {
+          const int ch = t / taps, tap = t - ch * taps;
+          mbar_arrive_expect_tx(&b_full[t], (uint32_t)p.b_bytes);
+          tma_load_2d(&tmap_w, &b_full[t], smem_b + (size_t)t * p.b_bytes, ch * CK, tap * p.cout_pad);
+        }
+      } else {
+        int stage = 0; uint32_t phase = 0;
+        for (long long item = blockIdx.x; item < p.total_items; item += gridDim.x) {
+          const int nt = (int)(item % p.ntiles_n);
+          for (int ch = 0; ch < p.nchunks; ++ch) {
+            for (int tap = 0; tap < taps; ++tap) {
+              mbar_wait(&b_empty[stage], phase ^ 1, 150 + stage);
+              mbar_arrive_expect_tx(&b_full[stage], (uint32_t)p.b_bytes);
+              tma_load_2d(&tmap_w, &b_full[stage], smem_b + (size_t)stage * p.b_bytes, ch * CK,
+                          tap * p.cout_pad + nt * NT);
+              if (++stage == p.b_stages) { stage = 0; phase ^= 1; }
+            }
           }
-          if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
-      int stage = 0; uint32_t phase = 0;
+      int aslot = 0; uint32_t aphase = 0;
+      int bstage = 0; uint32_t bphase = 0;
       int acc = 0; uint32_t acc_phase = 0;
+      bool first_item = true;
+      const uint32_t a_sbo = (uint32_t)p.halo_w * ROW_BYTES;
+      const uint32_t b_sbo = 8u * ROW_BYTES;
       for (long long item = blockIdx.x; item < p.total_items; item += gridDim.x) {
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1, 200 + acc);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * NT);
-        for (int ks = 0; ks < ksteps; ++ks) {
-          mbar_wait(&full_bar[stage], phase, 300 + stage);
-          tc_fence_after();
-          const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
-          const uint32_t sb = sa + (uint32_t)p.a_bytes;
-          const int kx_h = (p.ksize == 3) ? ks / p.nchunks : 0;
-          const uint32_t halo_w = (uint32_t)(TILE_W + 2 * p.dil);
-          for (int ky = 0; ky < taps_per_stage; ++ky) {
-            uint32_t a_tap = sa + (uint32_t)(ky * p.dil) * ATOM_BYTES;
-            uint32_t a_sbo = ATOM_BYTES, a_bo = 0;
-            if (p.halo_mode && p.ksize == 3) {   // tap (ky, kx) = pixel offset inside the halo box
-              a_tap = sa + ((uint32_t)(ky * p.dil) * halo_w + (uint32_t)(kx_h * p.dil)) * ROW_BYTES;
-              a_sbo = halo_w * ROW_BYTES;
-              if (p.halo_mode == 2) a_bo = (a_tap >> 7) & 7u;
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.mt * NT);
+        for (int ch = 0; ch < p.nchunks; ++ch) {
+          mbar_wait(&a_full[aslot], aphase, 300 + aslot);
+          const uint32_t sa = smem_u32(smem_a + (size_t)aslot * p.a_bytes);
+          for (int tap = 0; tap < taps; ++tap) {
+            uint32_t sb;
+            if (p.b_resident) {
+              const int t = ch * taps + tap;
+              if (first_item) mbar_wait(&b_full[t], 0, 350 + (t & 31));
+              sb = smem_u32(smem_b + (size_t)t * p.b_bytes);
+            } else {
+              mbar_wait(&b_full[bstage], bphase, 350 + bstage);
+              sb = smem_u32(smem_b + (size_t)bstage * p.b_bytes);
             }
-            const uint32_t b_tap = sb + (uint32_t)(ky * p.b_tap_bytes);
+            tc_fence_after();
+            const int ky = (p.ksize == 3) ? tap / 3 : 0, kx = (p.ksize == 3) ? tap - 3 * ky : 0;
+            const uint32_t a_tap = sa + (uint32_t)((ky * p.dil) * p.halo_w + kx * p.dil) * ROW_BYTES;
+            for (int t = 0; t < p.mt; ++t) {
 #pragma unroll
-            for (int k16 = 0; k16 < CK / 16; ++k16) {
-              const uint64_t adesc = make_smem_desc(a_tap + k16 * 32, a_sbo, LAYOUT, a_bo);
-              const uint64_t bdesc = make_smem_desc(b_tap + k16 * 32, ATOM_BYTES, LAYOUT);
-              umma_bf16(d_tmem, adesc, bdesc, idesc, (ks | ky | k16) != 0 ? 1u : 0u);
+              for (int k16 = 0; k16 < CK / 16; ++k16) {
+                const uint64_t adesc = make_smem_desc(a_tap + (uint32_t)(t * TILE_W) * ROW_BYTES + k16 * 32, a_sbo, LAYOUT);
+                const uint64_t bdesc = make_smem_desc(sb + k16 * 32, b_sbo, LAYOUT);
+                umma_bf16(d_tmem + (uint32_t)(t * NT), adesc, bdesc, idesc, (ch | tap | k16) != 0 ? 1u : 0u);
+              }
+            }
+            if (!p.b_resident) {
+              umma_commit(&b_empty[bstage]);   // weight stage free once these MMAs retire
+              if (++bstage == p.b_stages) { bstage = 0; bphase ^= 1; }
             }
           }
-          umma_commit(&empty_bar[stage]);  // frees the smem stage when these MMAs retire
-          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+          umma_commit(&a_empty[aslot]);        // halo box free once every tap of this chunk retired
+          if (++aslot == p.a_slots) { aslot = 0; aphase ^= 1; }
         }
-        umma_commit(&tfull_bar[acc]);      // accumulator ready for the epilogue
+        umma_commit(&tfull_bar[acc]);          // accumulators ready for the epilogue
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        first_item = false;
       }
     }
   } else {
-    // ===================== epilogue (warps 2..5) =====================
+    // ===================== epilogue (warps 3..6) =====================
     const int quarter = warp & 3;                  // TMEM lane quarter this warp may access
-    const int m = quarter * 32 + lane;             // pixel within the tile
+    const int m = quarter * 32 + lane;             // pixel within a 16x8 tile
     const int ty = m >> 3, tx = m & 7;
     int acc = 0; uint32_t acc_phase = 0;
     for (long long item = blockIdx.x; item < p.total_items; item += gridDim.x) {
-      const int nt = (int)(item % p.ntiles_n);
-      const long long tm = item / p.ntiles_n;
-      const int img = (int)(tm / tiles_per_img);
-      const int trem = (int)(tm - (long long)img * tiles_per_img);
-      const int y = (trem / p.tiles_x) * TILE_H + ty, x = (trem % p.tiles_x) * TILE_W + tx;
-      const bool valid = (y < p.H) && (x < p.W);
-      const int co0 = nt * NT;
-      long long off;   // element offset of this thread's first output channel of the tile
-      if (p.shuffle_r > 1) {
-        // packed channel co' = i*256 + j*32 + c ; N tile = 128 -> i = nt / 2, j0 = (nt & 1) * 4
-        const int per_i = p.shuffle_r * 32;        // channels per HR row phase
-        const int si = co0 / per_i, j0 = (co0 - si * per_i) / 32;
-        off = (((long long)img * p.yH + (y * p.shuffle_r + si)) * p.yW + (x * p.shuffle_r + j0)) * p.y_pitch + p.y_coff;
-      } else {
-        off = (((long long)img * p.yH + y) * p.yW + x) * p.y_pitch + p.y_coff + co0;
-      }
-      const long long roff = (((long long)img * p.yH + y) * p.yW + x) * p.r_pitch + p.r_coff + co0;
-
+      const ItemCoord c = decode_item(p, item);
+      const int co0 = c.nt * NT;
       mbar_wait(&tfull_bar[acc], acc_phase, 400 + acc);
       tc_fence_after();
-      const uint32_t tbase = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * NT);
-      int c0 = 0;
+      for (int t = 0; t < p.mt; ++t) {
+        const int y = c.y0 + ty, x = c.x0 + t * TILE_W + tx;
+        const bool valid = (y < p.H) && (x < p.W);
+        long long off;   // element offset of this thread's first output channel of the N tile
+        if (p.shuffle_r > 1) {
+          // packed channel co' = i*256 + j*32 + c ; N tile = 128 -> i = nt / 2, j0 = (nt & 1) * 4
+          const int per_i = p.shuffle_r * 32;
+          const int si = co0 / per_i, j0 = (co0 - si * per_i) / 32;
+          off = (((long long)c.img * p.yH + (y * p.shuffle_r + si)) * p.yW + (x * p.shuffle_r + j0)) * p.y_pitch + p.y_coff;
+        } else {
+          off = (((long long)c.img * p.yH + y) * p.yW + x) * p.y_pitch + p.y_coff + co0;
+        }
+        const long long roff = (((long long)c.img * p.yH + y) * p.yW + x) * p.r_pitch + p.r_coff + co0;
+        const uint32_t tbase = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)((acc * p.mt + t) * NT);
+        int c0 = 0;
 #pragma unroll 1
-      for (; c0 + 32 <= NT; c0 += 32) {
-        uint32_t r[32];
-        tmem_ld32(tbase + (uint32_t)c0, r);
-        if (valid) epilogue_chunk<32>(p, r, co0 + c0, off + c0, roff + c0);
+        for (; c0 + 32 <= NT; c0 += 32) {
+          uint32_t r[32];
+          tmem_ld32(tbase + (uint32_t)c0, r);
+          if (valid) epilogue_chunk<32>(p, r, co0 + c0, off + c0, roff + c0);
+        }
+        if (c0 < NT) {   // 16-column tail (n_tile is a multiple of 16)
+          uint32_t r[32];
+          tmem_ld16(tbase + (uint32_t)c0, r);
+          if (valid) epilogue_chunk<16>(p, r, co0 + c0, off + c0, roff + c0);
+        }
       }
-      if (c0 < NT) {   // 16-column tail (n_tile is a multiple of 16)
-        uint32_t r[32];
-        tmem_ld16(tbase + (uint32_t)c0, r);
-        if (valid) epilogue_chunk<16>(p, r, co0 + c0, off + c0, roff + c0);
-      }
-      // all TMEM reads of this warp are complete (tcgen05.wait::ld inside the loads): release the accumulator
+      // all TMEM reads of this warp are complete (tcgen05.wait::ld inside the loads): release the accumulators
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[acc]);
@@ -444,13 +484,9 @@ static void tc_geometry(int cin, int cout, int* ck, int* kpad, int* n_tile, int*
   *cout_pad = round_up(cout, nt);
 }
 
-static int tc_halo_mode() {
-  const char* e = getenv("DBSR_TC_HALO");
-  return e ? atoi(e) : 0;
-}
-
 struct TcConfig {
-  int n_tile, ck, nchunks, cout, cout_pad, stages, a_bytes, a_tx_bytes, b_tap_bytes, smem_bytes, tmem_cols, vec_ok;
+  int n_tile, ck, nchunks, cout, cout_pad, mt, halo_w, rows, a_slots, b_stages, b_resident, a_bytes, a_tx_bytes, b_bytes,
+      smem_bytes, tmem_cols, vec_ok;
 };
 
 static int tc_plan(const dbsr_conv_t* c, TcConfig* cfg, bool set_err) {
@@ -488,23 +524,46 @@ static int tc_plan(const dbsr_conv_t* c, TcConfig* cfg, bool set_err) {
   cfg->nchunks = kpad / ck;
   cfg->cout = cout;
   cfg->cout_pad = cpad;
+  const int tiles_x = ceil_div(c->x.w, TILE_W);
+  const int pad = (c->ksize == 3) ? c->dilation : 0;
+  const int budget = 227 * 1024 - 4096;
+  const int taps = c->ksize * c->ksize;
+  cfg->b_bytes = nt * ck * 2;
+  TC_REQ(cfg->b_bytes % 1024 == 0, "conv2d_tc: internal: unaligned weight stage");
+  cfg->rows = TILE_H + 2 * pad;
+  // item width (mt tiles) and depth of the activation ring: prefer 2 tiles x 3 slots, shrink until the halo boxes
+  // leave room for at least two weight stages (large dilations have large halos)
+  bool found = false;
+  for (int mt = (tiles_x >= 2 ? 2 : 1); mt >= 1 && !found; --mt) {
+    for (int slots = (kpad / ck == 1 ? 2 : 3); slots >= 1 && !found; --slots) {
+      const int hw = TILE_W * mt + 2 * pad;
+      const int ab = round_up(cfg->rows * hw * ck * 2, 1024);
+      if (slots * ab + 2 * cfg->b_bytes <= budget && (slots * ab <= budget / 2 || slots <= 2)) {
+        cfg->mt = mt; cfg->a_slots = slots; cfg->halo_w = hw; cfg->a_bytes = ab;
+        cfg->a_tx_bytes = cfg->rows * hw * ck * 2;
+        found = true;
+      }
+    }
+  }
+  TC_REQ(found, "conv2d_tc: activation halo box does not fit in shared memory (dilation %d)", c->dilation);
   int tc = 32;
-  while (tc < 2 * nt) tc <<= 1;
+  while (tc < 2 * cfg->mt * nt) tc <<= 1;
   cfg->tmem_cols = tc;
-  const int rows = (c->ksize == 3) ? TILE_H + 2 * c->dilation : TILE_H;
-  const int halo = tc_halo_mode();
-  const int cols = (halo && c->ksize == 3) ? TILE_W + 2 * c->dilation : TILE_W;
-  cfg->a_tx_bytes = rows * cols * ck * 2;
-  cfg->a_bytes = round_up(cfg->a_tx_bytes, 1024);
-  cfg->b_tap_bytes = nt * ck * 2;
-  TC_REQ(cfg->b_tap_bytes % 1024 == 0 && cfg->a_bytes % 1024 == 0, "conv2d_tc: internal: unaligned stage layout");
-  const int stage = cfg->a_bytes + c->ksize * cfg->b_tap_bytes;
-  const int budget = 227 * 1024 - 2048;
-  int stages = budget / stage;
-  if (stages > 8) stages = 8;
-  TC_REQ(stages >= 2, "conv2d_tc: pipeline stage of %d bytes does not fit twice in shared memory", stage);
-  cfg->stages = stages;
-  cfg->smem_bytes = stages * stage + 1024 /*align slack*/ + 256 /*barriers*/;
+  const int b_total = cfg->nchunks * taps * cfg->b_bytes;
+  if (cpad == nt && cfg->a_slots * cfg->a_bytes + b_total <= budget && cfg->nchunks * taps <= 64) {
+    cfg->b_resident = 1;
+    cfg->b_stages = cfg->nchunks * taps;
+  } else {
+    cfg->b_resident = 0;
+    int st = (budget - cfg->a_slots * cfg->a_bytes) / cfg->b_bytes;
+    if (st > 12) st = 12;
+    TC_REQ(st >= 2, "conv2d_tc: no room for the weight pipeline");
+    cfg->b_stages = st;
+  }
+  int smem = cfg->a_slots * cfg->a_bytes + cfg->b_stages * cfg->b_bytes + 1024 /*align slack*/ + 2048 /*barriers*/;
+  // a CTA that owns more than half of TMEM must be alone on its SM: make its smem footprint exclusive too
+  if (cfg->tmem_cols > 256 && smem < 120 * 1024) smem = 120 * 1024;
+  cfg->smem_bytes = smem;
   return 0;
 #undef TC_REQ
 }
@@ -556,7 +615,6 @@ extern "C" int dbsr_conv2d_tc(const dbsr_conv_t* c, void* stream) {
   DBSR_REQUIRE(encode != nullptr, "conv2d_tc: cuTensorMapEncodeTiled entry point not available");
 
   const int r = c->shuffle_r > 1 ? c->shuffle_r : 1;
-  const int rows = (c->ksize == 3) ? TILE_H + 2 * c->dilation : TILE_H;
   const CUtensorMapSwizzle swz = cfg.ck == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
 
   alignas(64) CUtensorMap mx, mw;
@@ -564,8 +622,7 @@ extern "C" int dbsr_conv2d_tc(const dbsr_conv_t* c, void* stream) {
     cuuint64_t dims[4] = {(cuuint64_t)c->x.c, (cuuint64_t)c->x.w, (cuuint64_t)c->x.h, (cuuint64_t)c->x.n};
     cuuint64_t strides[3] = {(cuuint64_t)c->x.c_pitch * 2, (cuuint64_t)c->x.w * c->x.c_pitch * 2,
                              (cuuint64_t)c->x.h * c->x.w * c->x.c_pitch * 2};
-    const int cols = (tc_halo_mode() && c->ksize == 3) ? TILE_W + 2 * c->dilation : TILE_W;
-    cuuint32_t box[4] = {(cuuint32_t)cfg.ck, (cuuint32_t)cols, (cuuint32_t)rows, 1};
+    cuuint32_t box[4] = {(cuuint32_t)cfg.ck, (cuuint32_t)cfg.halo_w, (cuuint32_t)cfg.rows, 1};
     cuuint32_t es[4] = {1, 1, 1, 1};
     void* base = reinterpret_cast<__nv_bfloat16*>(c->x.data) + c->x.c_off;
     CUresult rc = encode(&mx, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, base, dims, strides, box, es,
@@ -589,17 +646,17 @@ extern "C" int dbsr_conv2d_tc(const dbsr_conv_t* c, void* stream) {
   ConvTcParams p;
   p.n = c->x.n; p.H = c->x.h; p.W = c->x.w;
   p.ksize = c->ksize; p.dil = c->dilation;
-  p.nchunks = cfg.nchunks; p.cout_pad = cfg.cout_pad; p.cout = cfg.cout; p.n_tile = cfg.n_tile;
+  p.nchunks = cfg.nchunks; p.cout_pad = cfg.cout_pad; p.cout = cfg.cout; p.n_tile = cfg.n_tile; p.mt = cfg.mt;
   p.tmem_cols = cfg.tmem_cols; p.vec_ok = cfg.vec_ok;
   p.ntiles_n = cfg.cout_pad / cfg.n_tile;
-  p.tiles_x = ceil_div(p.W, TILE_W); p.tiles_y = ceil_div(p.H, TILE_H);
-  p.total_items = (long long)p.n * p.tiles_x * p.tiles_y * p.ntiles_n;
-  p.stages = cfg.stages; p.a_bytes = cfg.a_bytes; p.a_tx_bytes = cfg.a_tx_bytes; p.b_tap_bytes = cfg.b_tap_bytes;
+  p.items_x = ceil_div(p.W, TILE_W * cfg.mt); p.tiles_y = ceil_div(p.H, TILE_H);
+  p.total_items = (long long)p.n * p.items_x * p.tiles_y * p.ntiles_n;
+  p.a_slots = cfg.a_slots; p.b_stages = cfg.b_stages; p.b_resident = cfg.b_resident;
+  p.a_bytes = cfg.a_bytes; p.a_tx_bytes = cfg.a_tx_bytes; p.b_bytes = cfg.b_bytes; p.halo_w = cfg.halo_w;
   p.y = c->y.data; p.y_dtype = c->y.dtype; p.y_pitch = c->y.c_pitch; p.y_coff = c->y.c_off;
   p.yH = c->y.h; p.yW = c->y.w;
   p.res = c->residual.data; p.r_dtype = c->residual.dtype; p.r_pitch = c->residual.c_pitch; p.r_coff = c->residual.c_off;
   p.bias = c->bias; p.act = c->act; p.shuffle_r = r;
-  p.halo_mode = tc_halo_mode();
   cudaStream_t st = (cudaStream_t)stream;
   if (cfg.ck == 64) return launch_tc<64>(mx, mw, p, cfg.smem_bytes, st);
   return launch_tc<32>(mx, mw, p, cfg.smem_bytes, st);

@@ -13,5 +13,4 @@ done
 grep -E "TC_CASE|timeout|rror" gpurun_out/tc.log | head -40
 echo "== forward"; timeout 1200 python -m pytest tests/test_gpu_forward.py -q -m gpu --tb=short -p no:cacheprovider > gpurun_out/forward.log 2>&1; tail -25 gpurun_out/forward.log
 echo "== smoke"; timeout 600 python __graft_entry__.py smoke > gpurun_out/smoke.log 2>&1; tail -5 gpurun_out/smoke.log
-echo "== halo probes"; for m in 1 2; do for c in enc_res_64x64 wp_res_128x128 post_res_32x32 dilated_d2; do DBSR_TC_HALO=$m timeout 120 python tests/test_gpu_tc.py $c 2>&1 | grep -E "TC_CASE|timeout|rror" | sed "s/^/halo=$m /"; done; done
 echo "== bench"; timeout 900 python bench.py --steps ${BENCH_STEPS:-5} --warmup 3 --batch ${BENCH_BATCH:-8} > gpurun_out/bench.log 2>&1; tail -3 gpurun_out/bench.log
