@@ -37,6 +37,7 @@ def parse():
     ap.add_argument('--precision', default='bf16', choices=['bf16', 'fp32'])
     ap.add_argument('--cpu-baseline-seconds', type=float, default=15.0)
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--layers-out', default='', help='write the per-conv-layer time table of the instrumented pass here')
     ap.add_argument('--no-graph', action='store_true', help='launch eagerly instead of replaying a CUDA graph')
     return ap.parse_args()
 
@@ -196,10 +197,17 @@ def main():
     net.use_cuda_graph = False
     eng.flops = {}
     eng.timers = {}
+    eng.layer_events = {}
     for _ in range(args.steps):
         net(dev_in)
     torch.cuda.synchronize()
     fam = eng.timer_summary()
+    if rank == 0 and args.layers_out:
+        rows = eng.layer_summary()
+        with open(args.layers_out, 'w') as f:
+            for key, family, shape, n, ms, tf in rows:
+                f.write(f'{ms / args.steps:9.4f} ms/step {tf:8.1f} TFLOP/s {family:12s} n,h,w,cin,cout={shape} x{n // args.steps} {key}\n')
+    eng.layer_events = None
     flops = dict(eng.flops)
     eng.timers = None
 

@@ -56,6 +56,7 @@ PROTOTYPES = {
     'dbsr_warp': (_I, [_PV, _VP, _PV, _I, _VP]),
     'dbsr_offsets_mod': (_I, [_VP, _PV, _I, _I, _F, _VP]),
     'dbsr_build_wp_input': (_I, [_PV, _PV, _I, _VP]),
+    'dbsr_warp_proj': (_I, [_PV, _VP, _VP, _PV, _I, _VP]),
     'dbsr_softmax_wsum': (_I, [_PV, _PV, _VP, _PV, _VP, _I, _VP]),
     'dbsr_blur3x3': (_I, [_PV, _PV, ctypes.POINTER(ctypes.c_float), _VP]),
     'dbsr_predictor': (_I, [_PV, _VP, _VP, _I, _VP, _VP]),

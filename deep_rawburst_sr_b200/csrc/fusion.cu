@@ -163,6 +163,216 @@ __global__ void fusion_weights_kernel(View logits, float* __restrict__ wout, int
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------
+// 8-channel (16-byte for bf16, 2 x 16-byte for fp32) vector helpers for the bandwidth-bound kernels
+// ---------------------------------------------------------------------------------------------------------
+struct Vec8 { float v[8]; };
+
+template <typename T> __device__ __forceinline__ Vec8 ld8(const T* p);
+template <> __device__ __forceinline__ Vec8 ld8<float>(const float* p) {
+  const float4 a = __ldg(reinterpret_cast<const float4*>(p));
+  const float4 b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+  return Vec8{{a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w}};
+}
+template <> __device__ __forceinline__ Vec8 ld8<__nv_bfloat16>(const __nv_bfloat16* p) {
+  const uint4 q = __ldg(reinterpret_cast<const uint4*>(p));
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&q);
+  Vec8 r;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const float2 f = __bfloat1622float2(h[k]);
+    r.v[2 * k] = f.x; r.v[2 * k + 1] = f.y;
+  }
+  return r;
+}
+template <typename T> __device__ __forceinline__ void st8(T* p, const Vec8& v);
+template <> __device__ __forceinline__ void st8<float>(float* p, const Vec8& v) {
+  reinterpret_cast<float4*>(p)[0] = make_float4(v.v[0], v.v[1], v.v[2], v.v[3]);
+  reinterpret_cast<float4*>(p)[1] = make_float4(v.v[4], v.v[5], v.v[6], v.v[7]);
+}
+template <> __device__ __forceinline__ void st8<__nv_bfloat16>(__nv_bfloat16* p, const Vec8& v) {
+  uint4 q;
+  __nv_bfloat162 h0 = __floats2bfloat162_rn(v.v[0], v.v[1]), h1 = __floats2bfloat162_rn(v.v[2], v.v[3]);
+  __nv_bfloat162 h2 = __floats2bfloat162_rn(v.v[4], v.v[5]), h3 = __floats2bfloat162_rn(v.v[6], v.v[7]);
+  q.x = *reinterpret_cast<uint32_t*>(&h0); q.y = *reinterpret_cast<uint32_t*>(&h1);
+  q.z = *reinterpret_cast<uint32_t*>(&h2); q.w = *reinterpret_cast<uint32_t*>(&h3);
+  *reinterpret_cast<uint4*>(p) = q;
+}
+
+struct Taps {  // bilinear taps of one sample position (zeros outside the image)
+  int off[4];   // pixel offset inside the image, -1 when out of bounds
+  float w[4];
+};
+__device__ __forceinline__ Taps make_taps(float u, float v, int H, int W) {
+  const float fu = floorf(u), fv = floorf(v);
+  const float ax = u - fu, ay = v - fv;
+  const int x0 = (int)fu, y0 = (int)fv;
+  Taps t;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int xx = x0 + (k & 1), yy = y0 + (k >> 1);
+    t.w[k] = ((k & 1) ? ax : 1.0f - ax) * ((k >> 1) ? ay : 1.0f - ay);
+    t.off[k] = (xx >= 0 && xx < W && yy >= 0 && yy < H) ? yy * W + xx : -1;
+  }
+  return t;
+}
+template <typename T>
+__device__ __forceinline__ Vec8 gather8(const T* img_base, int c_pitch, const Taps& t, int ch) {
+  Vec8 r;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) r.v[i] = 0.0f;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    if (t.off[k] >= 0) {
+      const Vec8 a = ld8<T>(img_base + (long long)t.off[k] * c_pitch + ch);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) r.v[i] = fmaf(a.v[i], t.w[k], r.v[i]);
+    }
+  }
+  return r;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// warp_proj: the 1x1 projection (merging.py:75) commutes with the bilinear warp (both linear, the warp acts per
+// channel), so the engine projects the UNWARPED embeddings first (512 -> 64 channels, tensor cores, no bias / act)
+// and this kernel warps the 64-channel result instead of the 512-channel one:
+//   p_n = relu(warp(q_n, flow_n) + bias)      (n = 0: no warp)       merging.py:72-75 + encoders.py:80
+//   wp_in[:, 0:C] = p_0 ; wp_in[:, C:2C] = p_n - p_0                  merging.py:79-89
+// ---------------------------------------------------------------------------------------------------------
+template <typename TQ, typename TO>
+__global__ void __launch_bounds__(256)
+warp_proj_kernel(View q, const float* __restrict__ bias, const float* __restrict__ offsets, View wp_in, int frames) {
+  const int H = q.h, W = q.w, C = q.c, C8 = C >> 3;
+  const int HW = H * W;
+  const long long total = (long long)q.n * HW * C8;
+  const TQ* qbase = reinterpret_cast<const TQ*>(q.data) + q.c_off;
+  TO* obase = reinterpret_cast<TO*>(wp_in.data) + wp_in.c_off;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c8 = (int)(i % C8);
+    const long long pix = i / C8;
+    const int f = (int)(pix / HW);
+    const int rem = (int)(pix - (long long)f * HW);
+    const int b = f / frames, n = f - b * frames;
+    const int ch = c8 * 8;
+    Vec8 bv = ld8<float>(bias + ch);
+    Vec8 p0 = ld8<TQ>(qbase + ((long long)b * frames * HW + rem) * q.c_pitch + ch);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) p0.v[k] = fmaxf(p0.v[k] + bv.v[k], 0.0f);
+    Vec8 d;
+    if (n == 0) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) d.v[k] = 0.0f;
+    } else {
+      Vec8 pn;
+      if (offsets != nullptr) {
+        const long long pr = (long long)b * (frames - 1) + (n - 1);
+        const int y = rem / W, x = rem - y * W;
+        const float fx = __ldg(offsets + (pr * 2 + 0) * HW + rem);
+        const float fy = __ldg(offsets + (pr * 2 + 1) * HW + rem);
+        const Taps t = make_taps((float)x + fx, (float)y + fy, H, W);
+        pn = gather8<TQ>(qbase + (long long)f * HW * q.c_pitch, q.c_pitch, t, ch);
+      } else {
+        pn = ld8<TQ>(qbase + pix * q.c_pitch + ch);
+      }
+#pragma unroll
+      for (int k = 0; k < 8; ++k) d.v[k] = fmaxf(pn.v[k] + bv.v[k], 0.0f) - p0.v[k];
+    }
+    st8<TO>(obase + pix * wp_in.c_pitch + ch, p0);
+    st8<TO>(obase + pix * wp_in.c_pitch + C + ch, d);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// softmax over the burst + weighted sum, 8 channels per thread, warp of the embeddings recomputed on the fly
+// ---------------------------------------------------------------------------------------------------------
+template <typename TF, typename TL, typename TO>
+__global__ void __launch_bounds__(256)
+softmax_wsum8_kernel(View feat, View logits, const float* __restrict__ offsets, View fused, int frames) {
+  const int H = fused.h, W = fused.w, C8 = fused.c >> 3;
+  const int HW = H * W;
+  const long long total = (long long)fused.n * HW * C8;
+  const TF* fbase = reinterpret_cast<const TF*>(feat.data) + feat.c_off;
+  const TL* lbase = reinterpret_cast<const TL*>(logits.data) + logits.c_off;
+  TO* obase = reinterpret_cast<TO*>(fused.data) + fused.c_off;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c8 = (int)(i % C8);
+    const long long pix = i / C8;
+    const int b = (int)(pix / HW);
+    const int rem = (int)(pix - (long long)b * HW);
+    const int y = rem / W, x = rem - y * W;
+    const int ch = c8 * 8;
+    float m[8], s[8], acc[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { m[k] = -INFINITY; s[k] = 0.0f; acc[k] = 0.0f; }
+#pragma unroll 2
+    for (int n = 0; n < frames; ++n) {
+      const long long img = (long long)b * frames + n;
+      const Vec8 l = ld8<TL>(lbase + (img * HW + rem) * logits.c_pitch + ch);
+      Vec8 a;
+      if (n == 0 || offsets == nullptr) {
+        a = ld8<TF>(fbase + (img * HW + rem) * feat.c_pitch + ch);
+      } else {
+        const long long pr = (long long)b * (frames - 1) + (n - 1);
+        const float fx = __ldg(offsets + (pr * 2 + 0) * HW + rem);
+        const float fy = __ldg(offsets + (pr * 2 + 1) * HW + rem);
+        const Taps t = make_taps((float)x + fx, (float)y + fy, H, W);
+        a = gather8<TF>(fbase + img * HW * feat.c_pitch, feat.c_pitch, t, ch);
+      }
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const float mn = fmaxf(m[k], l.v[k]);
+        const float sc = expf(m[k] - mn);   // exp(-inf) = 0 on the first frame
+        const float e = expf(l.v[k] - mn);
+        s[k] = fmaf(s[k], sc, e);
+        acc[k] = fmaf(acc[k], sc, a.v[k] * e);
+        m[k] = mn;
+      }
+    }
+    Vec8 r;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) r.v[k] = acc[k] / s[k];
+    st8<TO>(obase + pix * fused.c_pitch + ch, r);
+  }
+}
+
+// upsampling.py:59-65: per-channel 3x3 blur with zero padding, 8 channels per thread
+template <typename T>
+__global__ void __launch_bounds__(256) blur3x3_v8_kernel(View x, View y, float k0, float k1, float k2, float k3, float k4,
+                                                         float k5, float k6, float k7, float k8) {
+  const float kk[9] = {k0, k1, k2, k3, k4, k5, k6, k7, k8};
+  const int H = x.h, W = x.w, C8 = x.c >> 3;
+  const long long total = (long long)x.n * H * W * C8;
+  const T* xb = reinterpret_cast<const T*>(x.data) + x.c_off;
+  T* yb = reinterpret_cast<T*>(y.data) + y.c_off;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c8 = (int)(i % C8);
+    const long long pix = i / C8;
+    const int n = (int)(pix / ((long long)H * W));
+    const int rem = (int)(pix - (long long)n * H * W);
+    const int py = rem / W, px = rem - py * W;
+    Vec8 acc;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc.v[k] = 0.0f;
+#pragma unroll
+    for (int dy = -1; dy <= 1; ++dy)
+#pragma unroll
+      for (int dx = -1; dx <= 1; ++dx) {
+        const int yy = py + dy, xx = px + dx;
+        if (yy >= 0 && yy < H && xx >= 0 && xx < W) {
+          const Vec8 a = ld8<T>(xb + (((long long)n * H + yy) * W + xx) * x.c_pitch + c8 * 8);
+          const float w = kk[(dy + 1) * 3 + (dx + 1)];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) acc.v[k] = fmaf(a.v[k], w, acc.v[k]);
+        }
+      }
+    st8<T>(yb + pix * y.c_pitch + c8 * 8, acc);
+  }
+}
+
 static inline int grid_cap(long long total, int block) {
   long long g = (total + block - 1) / block;
   const long long cap = 148LL * 32;
@@ -173,6 +383,11 @@ static bool vec4_ok(const dbsr_nhwc_t* v) {
   const size_t es = elem_size(v->dtype);
   const size_t al = 4 * es;  // 16 B for fp32, 8 B for bf16
   return v->c % 4 == 0 && (v->c_off * es) % al == 0 && (v->c_pitch * es) % al == 0 && ((uintptr_t)v->data % al) == 0;
+}
+
+static bool vec8_ok(const dbsr_nhwc_t* v) {
+  const size_t es = elem_size(v->dtype);
+  return v->c % 8 == 0 && (v->c_off * es) % 16 == 0 && (v->c_pitch * es) % 16 == 0 && ((uintptr_t)v->data % 16) == 0;
 }
 
 }  // namespace dbsr
@@ -206,11 +421,17 @@ extern "C" int dbsr_softmax_wsum(const dbsr_nhwc_t* feat, const dbsr_nhwc_t* log
                "softmax_wsum: geometry mismatch");
   DBSR_REQUIRE(vec4_ok(feat) && vec4_ok(logits) && vec4_ok(fused),
                "softmax_wsum: channel count/offset/pitch must be multiples of 4 and aligned");
-  const long long total = (long long)fused->n * fused->h * fused->w * (fused->c / 4);
-  const int g = grid_cap(total, 256);
   cudaStream_t st = (cudaStream_t)stream;
   View f = make_view(feat), l = make_view(logits), o = make_view(fused);
   const int key = feat->dtype * 4 + logits->dtype * 2 + fused->dtype;
+  const bool v8 = vec8_ok(feat) && vec8_ok(logits) && vec8_ok(fused) && (key == 0 || key == 7 || key == 5);
+  const long long total = (long long)fused->n * fused->h * fused->w * (fused->c / (v8 ? 8 : 4));
+  const int g = grid_cap(total, 256);
+  if (v8) {
+    if (key == 0) softmax_wsum8_kernel<float, float, float><<<g, 256, 0, st>>>(f, l, offsets, o, frames);
+    else if (key == 7) softmax_wsum8_kernel<__nv_bfloat16, __nv_bfloat16, __nv_bfloat16><<<g, 256, 0, st>>>(f, l, offsets, o, frames);
+    else softmax_wsum8_kernel<__nv_bfloat16, float, __nv_bfloat16><<<g, 256, 0, st>>>(f, l, offsets, o, frames);
+  } else
   switch (key) {
     case 0: softmax_wsum_kernel<float, float, float><<<g, 256, 0, st>>>(f, l, offsets, o, frames); break;
     case 7: softmax_wsum_kernel<__nv_bfloat16, __nv_bfloat16, __nv_bfloat16><<<g, 256, 0, st>>>(f, l, offsets, o, frames); break;
@@ -229,4 +450,33 @@ extern "C" int dbsr_softmax_wsum(const dbsr_nhwc_t* feat, const dbsr_nhwc_t* log
     rc = check_launch("fusion_weights");
   }
   return rc;
+}
+
+extern "C" int dbsr_warp_proj(const dbsr_nhwc_t* q, const float* bias, const float* offsets, const dbsr_nhwc_t* wp_in,
+                              int32_t frames, void* stream) {
+  DBSR_REQUIRE(view_ok(q) && view_ok(wp_in) && bias && frames >= 2, "warp_proj: bad arguments");
+  DBSR_REQUIRE(q->n == wp_in->n && q->h == wp_in->h && q->w == wp_in->w && wp_in->c >= 2 * q->c && q->n % frames == 0,
+               "warp_proj: geometry mismatch");
+  DBSR_REQUIRE(vec8_ok(q) && vec8_ok(wp_in) && ((uintptr_t)bias % 16) == 0 && q->dtype == wp_in->dtype,
+               "warp_proj: channels must be multiples of 8, 16-byte aligned, same dtype in and out");
+  const long long total = (long long)q->n * q->h * q->w * (q->c / 8);
+  const int g = grid_cap(total, 256);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (q->dtype == DBSR_F32) warp_proj_kernel<float, float><<<g, 256, 0, st>>>(make_view(q), bias, offsets, make_view(wp_in), frames);
+  else warp_proj_kernel<__nv_bfloat16, __nv_bfloat16><<<g, 256, 0, st>>>(make_view(q), bias, offsets, make_view(wp_in), frames);
+  return check_launch("warp_proj");
+}
+
+extern "C" int dbsr_blur3x3(const dbsr_nhwc_t* x, const dbsr_nhwc_t* y, const float* k9, void* stream) {
+  DBSR_REQUIRE(view_ok(x) && view_ok(y) && k9 && x->n == y->n && x->h == y->h && x->w == y->w && x->c == y->c &&
+                   x->dtype == y->dtype, "blur3x3: bad arguments");
+  DBSR_REQUIRE(vec8_ok(x) && vec8_ok(y), "blur3x3: channels must be multiples of 8 and 16-byte aligned");
+  const long long total = (long long)x->n * x->h * x->w * (x->c / 8);
+  const int g = grid_cap(total, 256);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (x->dtype == DBSR_F32)
+    blur3x3_v8_kernel<float><<<g, 256, 0, st>>>(make_view(x), make_view(y), k9[0], k9[1], k9[2], k9[3], k9[4], k9[5], k9[6], k9[7], k9[8]);
+  else
+    blur3x3_v8_kernel<__nv_bfloat16><<<g, 256, 0, st>>>(make_view(x), make_view(y), k9[0], k9[1], k9[2], k9[3], k9[4], k9[5], k9[6], k9[7], k9[8]);
+  return check_launch("blur3x3");
 }

@@ -260,32 +260,6 @@ __global__ void build_wp_input_kernel(View proj, View wp_in, int frames) {
   }
 }
 
-// upsampling.py:59-65: per-channel 3x3 blur with zero padding
-__global__ void blur3x3_kernel(View x, View y, float k0, float k1, float k2, float k3, float k4, float k5, float k6,
-                               float k7, float k8) {
-  const float k[9] = {k0, k1, k2, k3, k4, k5, k6, k7, k8};
-  const int C = x.c;
-  const long long total = (long long)x.n * x.h * x.w * C;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    const int c = (int)(i % C);
-    const long long pix = i / C;
-    const int n = (int)(pix / ((long long)x.h * x.w));
-    const int rem = (int)(pix - (long long)n * x.h * x.w);
-    const int py = rem / x.w, px = rem - py * x.w;
-    float acc = 0.0f;
-#pragma unroll
-    for (int dy = -1; dy <= 1; ++dy)
-#pragma unroll
-      for (int dx = -1; dx <= 1; ++dx) {
-        const int yy = py + dy, xx = px + dx;
-        if (yy >= 0 && yy < x.h && xx >= 0 && xx < x.w)
-          acc = fmaf(view_ld(x, ((long long)n * x.h + yy) * x.w + xx, c), k[(dy + 1) * 3 + (dx + 1)], acc);
-      }
-    view_st(y, pix, c, acc);
-  }
-}
-
 // decoders.py:52,60: 1x1 conv to `cout` (<= 4) channels + ReLU, NCHW fp32 output
 __global__ void predictor_kernel(View x, const float* __restrict__ w, const float* __restrict__ bias, int cout,
                                  float* __restrict__ pred) {
@@ -419,16 +393,6 @@ extern "C" int dbsr_build_wp_input(const dbsr_nhwc_t* proj, const dbsr_nhwc_t* w
   build_wp_input_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(make_view(proj), make_view(wp_in),
                                                                                  frames);
   return check_launch("build_wp_input");
-}
-
-extern "C" int dbsr_blur3x3(const dbsr_nhwc_t* x, const dbsr_nhwc_t* y, const float* k9, void* stream) {
-  DBSR_REQUIRE(view_ok(x) && view_ok(y) && k9 && x->n == y->n && x->h == y->h && x->w == y->w && x->c == y->c,
-               "blur3x3: bad arguments");
-  const long long total = (long long)x->n * x->h * x->w * x->c;
-  blur3x3_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(make_view(x), make_view(y), k9[0], k9[1],
-                                                                          k9[2], k9[3], k9[4], k9[5], k9[6], k9[7],
-                                                                          k9[8]);
-  return check_launch("blur3x3");
 }
 
 extern "C" int dbsr_predictor(const dbsr_nhwc_t* x, const float* w, const float* bias, int32_t cout, float* pred,

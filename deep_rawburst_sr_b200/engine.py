@@ -148,6 +148,7 @@ class DBSREngine:
         self._ws: Dict[tuple, dict] = {}
         self._graphs: Dict[tuple, tuple] = {}
         self.launches = 0
+        self.layer_events = None   # when a dict (and timers is on): conv layer key -> [(events, flops, family, shape)]
         self.timers = None   # when a dict: family -> list of (start, end) CUDA events on the launching stream
         self.flops = {}      # family -> algorithmic FLOPs (2*MAC, real channel counts) launched since reset
         sd = {k: v.detach().to(self.device) for k, v in state_dict.items()}
@@ -258,20 +259,24 @@ class DBSREngine:
     # helpers
     # ------------------------------------------------------------------------------------------------
     def _conv(self, key: str, x: Act, y: Act, act: int, stride: int = 1, dilation: int = 1,
-              residual: Optional[Act] = None, force_direct: bool = False) -> Act:
+              residual: Optional[Act] = None, force_direct: bool = False, no_bias: bool = False) -> Act:
         cw = self.W[key]
+        bias, bias_tc = (None, None) if no_bias else (cw.bias, cw.bias_tc)
         use_tc = (cw.tc is not None and not force_direct and x.dtype == torch.bfloat16 and stride == 1)
         if use_tc:
-            use_tc = ops.conv2d_tc_supported(x, cw.tc, cw.bias_tc, y, cw.ksize, stride, dilation, residual, cw.shuffle_r)
+            use_tc = ops.conv2d_tc_supported(x, cw.tc, bias_tc, y, cw.ksize, stride, dilation, residual, cw.shuffle_r)
         self.launches += 1
         fam = 'conv_tc' if use_tc else 'conv_direct'
         ho, wo = (y.h, y.w) if cw.shuffle_r <= 1 else (y.h // cw.shuffle_r, y.w // cw.shuffle_r)
         self.flops[fam] = self.flops.get(fam, 0) + 2 * x.n * ho * wo * cw.cout * cw.cin * cw.ksize * cw.ksize
         ev = self._tic(fam)
+        if ev is not None and self.layer_events is not None:
+            fl = 2 * x.n * ho * wo * cw.cout * cw.cin * cw.ksize * cw.ksize
+            self.layer_events.setdefault(key, []).append((self.timers[fam][-1], fl, fam, (x.n, x.h, x.w, cw.cin, cw.cout)))
         if use_tc:
-            ops.conv2d(x, cw.tc, cw.bias_tc, y, cw.ksize, stride, dilation, act, residual, cw.shuffle_r, tensor_core=True)
+            ops.conv2d(x, cw.tc, bias_tc, y, cw.ksize, stride, dilation, act, residual, cw.shuffle_r, tensor_core=True)
         else:
-            ops.conv2d(x, cw.direct, cw.bias, y, cw.ksize, stride, dilation, act, residual, cw.shuffle_r)
+            ops.conv2d(x, cw.direct, bias, y, cw.ksize, stride, dilation, act, residual, cw.shuffle_r)
         self._toc(ev)
         return y
 
@@ -296,6 +301,15 @@ class DBSREngine:
     def _toc(ev):
         if ev is not None:
             ev.record()
+
+    def layer_summary(self) -> list:
+        """per conv layer: (key, family, shape, launches, total ms, TFLOP/s), sorted by time; call after a synchronize"""
+        rows = []
+        for key, evs in (self.layer_events or {}).items():
+            ms = sum(a.elapsed_time(b) for (a, b), _f, _fam, _s in evs)
+            fl = sum(f for _e, f, _fam, _s in evs)
+            rows.append((key, evs[0][2], evs[0][3], len(evs), ms, fl / (ms / 1e3) / 1e12 if ms > 0 else 0.0))
+        return sorted(rows, key=lambda r: -r[4])
 
     def timer_summary(self) -> dict:
         """family -> (total ms, launches); call after a synchronize."""
@@ -420,17 +434,21 @@ class DBSREngine:
         self._conv('encoder.out_layer.0', cur, feat, ACT_RELU)
         return feat
 
-    def merge(self, ws: dict, all_feat: Act, offsets: torch.Tensor, B: int, N: int,
-              weights_out: Optional[torch.Tensor] = None) -> Act:
-        """WeightedSum.forward (reference models/dbsr/merging.py:61-127).  `all_feat` [B*N, H, W, C]: reference frame +
-        aligned other frames; offsets [B*(N-1), 2, H, W]."""
-        F_, H, W = all_feat.n, all_feat.h, all_feat.w
+    def merge(self, ws: dict, feat: Act, offsets: torch.Tensor, B: int, N: int,
+              weights_out: Optional[torch.Tensor] = None, aligned: bool = False) -> Act:
+        """WeightedSum.forward (reference models/dbsr/merging.py:61-127) with the warp of encoders.py:80 folded in.
+        `feat` [B*N, H, W, C]: the frame embeddings -- unwarped (aligned=False: the kernels gather through `offsets`
+        on the fly, the warped 512-channel tensor is never materialised) or already aligned (aligned=True, the
+        WeightedSum module seam).  offsets [B*(N-1), 2, H, W]."""
+        F_, H, W = feat.n, feat.h, feat.w
         dt = self.act_dtype
         pd, od, wd = self.proj_dim, self.offf_dim, self.wp_dim
-        proj = self._buf(ws, 'proj', F_, H, W, pd, dt)
-        self._conv('merging.feat_project_layer.0', all_feat, proj, ACT_RELU)
+        gather = None if aligned else offsets
+        # 1x1 projection commutes with the bilinear warp: project first (tensor cores), warp 64 channels instead of 512
+        q = self._buf(ws, 'proj_q', F_, H, W, pd, dt)
+        self._conv('merging.feat_project_layer.0', feat, q, ACT_NONE, no_bias=True)
         wp_in = self._buf(ws, 'wp_in', F_, H, W, 2 * pd + od, dt)
-        self._run('build_wp_input', ops.build_wp_input, proj, wp_in, N)
+        self._run('warp_proj', ops.warp_proj, q, self.W['merging.feat_project_layer.0'].bias, wp_in, N, gather)
         offm = self._buf(ws, 'offm', F_, H, W, 8, dt)
         self._run('offsets_mod', ops.offsets_mod, offsets, offm, B, N, self.offset_modulo)
         oa = self._buf(ws, 'off_a', F_, H, W, od, dt)
@@ -456,7 +474,7 @@ class DBSREngine:
         logits = self._buf(ws, 'logits', F_, H, W, self.feat_dim, self.logits_dtype)
         self._conv(f'merging.weight_predictor.{self.wp_res + 1}.0', cur, logits, ACT_NONE)
         fused = self._buf(ws, 'fused', B, H, W, self.feat_dim, dt)
-        self._run('softmax_wsum', ops.softmax_wsum, all_feat, logits, fused, N, offsets=None, weights_out=weights_out)
+        self._run('softmax_wsum', ops.softmax_wsum, feat, logits, fused, N, offsets=gather, weights_out=weights_out)
         self.launches += (1 if weights_out is not None else 0)
         return fused
 
@@ -513,12 +531,10 @@ class DBSREngine:
             offsets = torch.empty((B * (N - 1), 2, H, W), dtype=torch.float32, device=self.device)
         self.pwc_burst(ws, pwc_in, B, N, H, W, offsets)
         feat = self.encode(ws, enc_in)
-        all_feat = self._buf(ws, 'all_feat', F_, H, W, self.feat_dim, self.act_dtype)
-        self._run('warp', ops.warp, feat, offsets, all_feat, frames=N)
         weights = None
         if return_weights:
             weights = torch.empty((B, N, self.feat_dim, H, W), dtype=torch.float32, device=self.device)
-        fused = self.merge(ws, all_feat, offsets, B, N, weights)
+        fused = self.merge(ws, feat, offsets, B, N, weights, aligned=False)
         pred = out.get('pred')
         if pred is None:
             pred = torch.empty((B, 3, H * self.up_r, W * self.up_r), dtype=torch.float32, device=self.device)

@@ -80,5 +80,5 @@ class WeightedSum(nn.Module):
         weights = None
         if self.return_fusion_weights:
             weights = torch.empty((B, N, C, H, W), dtype=torch.float32, device=all_feat.device)
-        fused = eng.merge(ws, af, offsets.reshape(B * (N - 1), 2, H, W).contiguous().float(), B, N, weights)
+        fused = eng.merge(ws, af, offsets.reshape(B * (N - 1), 2, H, W).contiguous().float(), B, N, weights, aligned=True)
         return {'fused_enc': fused.to_nchw(), 'fusion_weights': weights}

@@ -174,6 +174,15 @@ def build_wp_input(proj: Act, wp_in: Act, frames: int) -> Act:
     return wp_in
 
 
+def warp_proj(q: Act, bias: torch.Tensor, wp_in: Act, frames: int, offsets: Optional[torch.Tensor] = None) -> Act:
+    if offsets is not None:
+        assert offsets.dtype == torch.float32 and offsets.is_contiguous()
+    qv, wv = q.view(), wp_in.view()
+    _lib.check(_lib.load_library().dbsr_warp_proj(ctypes.byref(qv), bias.data_ptr(), _ptr(offsets), ctypes.byref(wv),
+                                                  frames, _stream()), 'dbsr_warp_proj')
+    return wp_in
+
+
 def softmax_wsum(feat: Act, logits: Act, fused: Act, frames: int, offsets: Optional[torch.Tensor] = None,
                  weights_out: Optional[torch.Tensor] = None) -> Act:
     if offsets is not None:

@@ -140,6 +140,12 @@ int dbsr_offsets_mod(const float* offsets, const dbsr_nhwc_t* out, int32_t burst
                      float modulo, void* stream);
 /* merging.py:79-89: wp_in[:, 0:C] = proj[b, 0]; wp_in[:, C:2C] = proj[b, n] - proj[b, 0]               */
 int dbsr_build_wp_input(const dbsr_nhwc_t* proj, const dbsr_nhwc_t* wp_in, int32_t frames, void* stream);
+/* merging.py:72-89 with the warp of encoders.py:80 folded in.  The 1x1 projection commutes with the bilinear warp,
+ * so q = W_p * feat is computed on the UNWARPED embeddings (conv2d, no bias / activation) and this kernel produces
+ *   p_n = relu(warp(q_n, offsets) + bias)  (frame 0 unwarped);  wp_in[:, 0:C] = p_0,  wp_in[:, C:2C] = p_n - p_0.
+ * offsets == NULL: q is already aligned (WeightedSum called on pre-warped embeddings).                           */
+int dbsr_warp_proj(const dbsr_nhwc_t* q, const float* bias, const float* offsets, const dbsr_nhwc_t* wp_in,
+                   int32_t frames, void* stream);
 /* merging.py:117-124 fused with the warp: fused[b] = sum_n softmax_n(logits[b,n]) * A[b,n] where
  *   A[b,0] = feat[b*N], A[b,n>0] = bilinear(feat[b*N+n], (x,y) + offsets[b*(N-1)+n-1]) gathered on the fly
  *   (offsets == NULL: `feat` already holds the aligned maps).  weights_out (optional, may be NULL):

@@ -288,3 +288,30 @@ def test_backwarp_seam(dev, golden_dir):
     got = backwarp(torch.from_numpy(gold['feat']).to(dev), torch.from_numpy(gold['flow']).to(dev)).cpu().numpy()
     err = np.abs(got - gold['backwarp'])
     assert (err > 5e-5).mean() < 0.01
+
+
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize('with_offsets', [False, True])
+def test_warp_proj(dev, dtype, with_offsets):
+    """p_n = relu(warp(q_n) + b); wp_in = [p_0 | p_n - p_0]  (projection commuted with the warp)"""
+    from deep_rawburst_sr_b200 import ops
+    g = _gen(21)
+    B, N, C, H, W = 2, 4, 64, 9, 12
+    q = torch.randn(B * N, C, H, W, generator=g)
+    if dtype == torch.bfloat16:
+        q = q.bfloat16().float()
+    bias = torch.randn(C, generator=g)
+    offs = (torch.rand(B * (N - 1), 2, H, W, generator=g) * 2 - 1) * 5
+    q5 = q.view(B, N, C, H, W)
+    if with_offsets:
+        a5 = torch.cat([q5[:, :1], O.warp(q5[:, 1:].reshape(-1, C, H, W), offs).view(B, N - 1, C, H, W)], 1)
+    else:
+        a5 = q5
+    p5 = torch.relu(a5 + bias.view(1, 1, C, 1, 1))
+    ref = torch.cat([p5[:, :1].expand(-1, N, -1, -1, -1), p5 - p5[:, :1]], 2).reshape(B * N, 2 * C, H, W)
+    wp = ops.Act.empty(B * N, H, W, 3 * C, dtype, dev, zero=True)
+    ops.warp_proj(_act_from(q, dev, dtype=dtype), bias.to(dev), wp, N, offs.to(dev) if with_offsets else None)
+    got = wp.slice(0, 2 * C).to_nchw().cpu()
+    tol = 1e-5 if dtype == torch.float32 else 4e-2
+    assert (got - ref).abs().max() < tol
+    assert float(wp.buf[..., 2 * C:].float().abs().max()) == 0.0

@@ -13,4 +13,4 @@ done
 grep -E "TC_CASE|timeout|rror" gpurun_out/tc.log | head -40
 echo "== forward"; timeout 1200 python -m pytest tests/test_gpu_forward.py -q -m gpu --tb=short -p no:cacheprovider > gpurun_out/forward.log 2>&1; tail -25 gpurun_out/forward.log
 echo "== smoke"; timeout 600 python __graft_entry__.py smoke > gpurun_out/smoke.log 2>&1; tail -5 gpurun_out/smoke.log
-echo "== bench"; timeout 900 python bench.py --steps ${BENCH_STEPS:-5} --warmup 3 --batch ${BENCH_BATCH:-8} > gpurun_out/bench.log 2>&1; tail -3 gpurun_out/bench.log
+echo "== bench"; timeout 900 python bench.py --steps ${BENCH_STEPS:-5} --warmup 3 --batch ${BENCH_BATCH:-8} --layers-out gpurun_out/layers.txt > gpurun_out/bench.log 2>&1; tail -3 gpurun_out/bench.log
