@@ -38,6 +38,7 @@ def parse():
     ap.add_argument('--cpu-baseline-seconds', type=float, default=15.0)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--layers-out', default='', help='write the per-conv-layer time table of the instrumented pass here')
+    ap.add_argument('--one-forward', action='store_true', help='profiling aid: warm up, run ONE eager forward, exit')
     ap.add_argument('--no-graph', action='store_true', help='launch eagerly instead of replaying a CUDA graph')
     return ap.parse_args()
 
@@ -153,6 +154,15 @@ def main():
             return float(t.item())
         return ms
 
+    if args.one_forward:
+        for _ in range(args.warmup):
+            net(dev_in)
+        torch.cuda.synchronize()
+        eng.launches = 0
+        net(dev_in)
+        torch.cuda.synchronize()
+        print(json.dumps({'one_forward': True, 'launches': eng.launches, 'batch': B}))
+        return
     net.use_cuda_graph = not args.no_graph
 
     # ---- device-resident throughput ("value"): K forwards, inputs already in HBM

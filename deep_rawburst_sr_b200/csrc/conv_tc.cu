@@ -147,7 +147,7 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t sbo_
 // kernel
 // ---------------------------------------------------------------------------------------------------------
 constexpr int TILE_H = 16, TILE_W = 8;
-constexpr int TC_THREADS = 224;
+constexpr int TC_THREADS = 352;   // warps 0-2: A producer / MMA issuer / B producer; warps 3-10: epilogue
 
 struct ConvTcParams {
   int n, H, W;          // input == output spatial size (stride 1, "same" padding)
@@ -173,20 +173,26 @@ struct ConvTcParams {
   int shuffle_r;        // 8: pixel shuffle addressing (y is the (8H, 8W, 32) map)
 };
 
-// epilogue of NC (32 or 16) accumulator columns held by one thread (= one output pixel)
+// epilogue of NC (32 or 16) accumulator columns held by one thread (= one output pixel).
+// rq: residual values of this chunk prefetched by the caller (fast path only, nullptr = load here)
 template <int NC>
 __device__ __forceinline__ void epilogue_chunk(const ConvTcParams& p, const uint32_t (&r)[32], int co, long long off,
-                                               long long roff) {
+                                               long long roff, const uint4* rq_pref) {
   // co: first output channel of the chunk; off / roff: element offsets of that channel in y / residual
   float v[NC];
 #pragma unroll
   for (int j = 0; j < NC; ++j) v[j] = __uint_as_float(r[j]);
   if (p.vec_ok) {
     uint4 rq[NC / 8];
-    if (p.res) {   // bf16 on the fast path; issue the loads first so they overlap the bias math
-      const __nv_bfloat16* rp = reinterpret_cast<const __nv_bfloat16*>(p.res) + roff;
+    if (p.res) {   // bf16 on the fast path
+      if (rq_pref) {
 #pragma unroll
-      for (int j = 0; j < NC / 8; ++j) rq[j] = __ldg(reinterpret_cast<const uint4*>(rp + 8 * j));
+        for (int j = 0; j < NC / 8; ++j) rq[j] = rq_pref[j];
+      } else {
+        const __nv_bfloat16* rp = reinterpret_cast<const __nv_bfloat16*>(p.res) + roff;
+#pragma unroll
+        for (int j = 0; j < NC / 8; ++j) rq[j] = __ldg(reinterpret_cast<const uint4*>(rp + 8 * j));
+      }
     }
     if (p.bias) {
 #pragma unroll
@@ -287,7 +293,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.a_slots; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
     for (int s = 0; s < p.b_stages; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], 4); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], 8); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     tma_prefetch_desc(&tmap_x);
@@ -390,41 +396,59 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
       }
     }
   } else {
-    // ===================== epilogue (warps 3..6) =====================
+    // ===================== epilogue (warps 3..10) =====================
+    // two warps per TMEM lane quarter: with mt == 2 group g owns tile g of every item, with mt == 1 the groups take
+    // alternate 32-column chunks.  Residual rows are prefetched before waiting for the accumulator.
     const int quarter = warp & 3;                  // TMEM lane quarter this warp may access
+    const int group = (warp - 3) >> 2;             // 0 or 1
     const int m = quarter * 32 + lane;             // pixel within a 16x8 tile
     const int ty = m >> 3, tx = m & 7;
+    const bool pref = p.vec_ok && p.res != nullptr;
     int acc = 0; uint32_t acc_phase = 0;
     for (long long item = blockIdx.x; item < p.total_items; item += gridDim.x) {
       const ItemCoord c = decode_item(p, item);
       const int co0 = c.nt * NT;
+      const int t = (p.mt == 2) ? group : 0;
+      const int y = c.y0 + ty, x = c.x0 + t * TILE_W + tx;
+      const bool valid = (y < p.H) && (x < p.W);
+      long long off;   // element offset of this thread's first output channel of the N tile
+      if (p.shuffle_r > 1) {
+        // packed channel co' = i*256 + j*32 + c ; N tile = 128 -> i = nt / 2, j0 = (nt & 1) * 4
+        const int per_i = p.shuffle_r * 32;
+        const int si = co0 / per_i, j0 = (co0 - si * per_i) / 32;
+        off = (((long long)c.img * p.yH + (y * p.shuffle_r + si)) * p.yW + (x * p.shuffle_r + j0)) * p.y_pitch + p.y_coff;
+      } else {
+        off = (((long long)c.img * p.yH + y) * p.yW + x) * p.y_pitch + p.y_coff + co0;
+      }
+      const long long roff = (((long long)c.img * p.yH + y) * p.yW + x) * p.r_pitch + p.r_coff + co0;
+      // chunk ownership: mt == 2 -> all chunks of my tile; mt == 1 -> chunks with (index & 1) == group
+      uint4 rq[4][4];
+      if (pref && valid) {
+        const __nv_bfloat16* rp = reinterpret_cast<const __nv_bfloat16*>(p.res) + roff;
+#pragma unroll
+        for (int ci = 0; ci < 4; ++ci) {
+          if (ci * 32 < NT && (p.mt == 2 || (ci & 1) == group)) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              if (ci * 32 + j * 8 < NT) rq[ci][j] = __ldg(reinterpret_cast<const uint4*>(rp + ci * 32 + j * 8));
+          }
+        }
+      }
       mbar_wait(&tfull_bar[acc], acc_phase, 400 + acc);
       tc_fence_after();
-      for (int t = 0; t < p.mt; ++t) {
-        const int y = c.y0 + ty, x = c.x0 + t * TILE_W + tx;
-        const bool valid = (y < p.H) && (x < p.W);
-        long long off;   // element offset of this thread's first output channel of the N tile
-        if (p.shuffle_r > 1) {
-          // packed channel co' = i*256 + j*32 + c ; N tile = 128 -> i = nt / 2, j0 = (nt & 1) * 4
-          const int per_i = p.shuffle_r * 32;
-          const int si = co0 / per_i, j0 = (co0 - si * per_i) / 32;
-          off = (((long long)c.img * p.yH + (y * p.shuffle_r + si)) * p.yW + (x * p.shuffle_r + j0)) * p.y_pitch + p.y_coff;
-        } else {
-          off = (((long long)c.img * p.yH + y) * p.yW + x) * p.y_pitch + p.y_coff + co0;
-        }
-        const long long roff = (((long long)c.img * p.yH + y) * p.yW + x) * p.r_pitch + p.r_coff + co0;
-        const uint32_t tbase = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)((acc * p.mt + t) * NT);
-        int c0 = 0;
-#pragma unroll 1
-        for (; c0 + 32 <= NT; c0 += 32) {
+      const uint32_t tbase = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)((acc * p.mt + t) * NT);
+#pragma unroll
+      for (int ci = 0; ci < 4; ++ci) {
+        const int c0 = ci * 32;
+        if (c0 < NT && (p.mt == 2 || (ci & 1) == group)) {
           uint32_t r[32];
-          tmem_ld32(tbase + (uint32_t)c0, r);
-          if (valid) epilogue_chunk<32>(p, r, co0 + c0, off + c0, roff + c0);
-        }
-        if (c0 < NT) {   // 16-column tail (n_tile is a multiple of 16)
-          uint32_t r[32];
-          tmem_ld16(tbase + (uint32_t)c0, r);
-          if (valid) epilogue_chunk<16>(p, r, co0 + c0, off + c0, roff + c0);
+          if (c0 + 32 <= NT) {
+            tmem_ld32(tbase + (uint32_t)c0, r);
+            if (valid) epilogue_chunk<32>(p, r, co0 + c0, off + c0, roff + c0, pref ? rq[ci] : nullptr);
+          } else {   // 16-column tail (n_tile is a multiple of 16)
+            tmem_ld16(tbase + (uint32_t)c0, r);
+            if (valid) epilogue_chunk<16>(p, r, co0 + c0, off + c0, roff + c0, pref ? rq[ci] : nullptr);
+          }
         }
       }
       // all TMEM reads of this warp are complete (tcgen05.wait::ld inside the loads): release the accumulators
@@ -535,10 +559,13 @@ static int tc_plan(const dbsr_conv_t* c, TcConfig* cfg, bool set_err) {
   // leave room for at least two weight stages (large dilations have large halos)
   bool found = false;
   for (int mt = (tiles_x >= 2 ? 2 : 1); mt >= 1 && !found; --mt) {
-    for (int slots = (kpad / ck == 1 ? 2 : 3); slots >= 1 && !found; --slots) {
+    for (int slots = 4; slots >= 1 && !found; --slots) {
       const int hw = TILE_W * mt + 2 * pad;
       const int ab = round_up(cfg->rows * hw * ck * 2, 1024);
-      if (slots * ab + 2 * cfg->b_bytes <= budget && (slots * ab <= budget / 2 || slots <= 2)) {
+      const int b_all = (kpad / ck) * taps * cfg->b_bytes;
+      const bool want_resident = cpad == nt && (kpad / ck) * taps <= 64 && b_all <= budget / 2;
+      const int b_need = want_resident ? b_all : 4 * cfg->b_bytes;
+      if (slots * ab + b_need <= budget || (slots == 1 && ab + 2 * cfg->b_bytes <= budget)) {
         cfg->mt = mt; cfg->a_slots = slots; cfg->halo_w = hw; cfg->a_bytes = ab;
         cfg->a_tx_bytes = cfg->rows * hw * ck * 2;
         found = true;
