@@ -34,6 +34,18 @@ namespace dbsr {
 // ---------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// one elected lane of a converged warp (ptxas then knows the region is single-threaded and keeps descriptor /
+// address operands in uniform registers instead of emitting a per-instruction R2UR waterfall loop)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
@@ -307,7 +319,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
 
   if (warp == 0) {
     // ===================== A producer: one halo box per (item, K chunk) =====================
-    if (lane == 0) {
+    if (elect_one()) {
       int slot = 0; uint32_t phase = 0;
       for (long long item = blockIdx.x; item < p.total_items; item += gridDim.x) {
         const ItemCoord c = decode_item(p, item);
@@ -321,7 +333,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
     }
   } else if (warp == 2) {
     // ===================== B producer: weight tiles =====================
-    if (lane == 0) {
+    if (elect_one()) {
       if (p.b_resident) {
         // every item uses the same tiles (ntiles_n == 1): load each (chunk, tap) tile once and keep it
         for (int t = 0; t < p.nchunks * taps; ++t) {
@@ -347,7 +359,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
+    if (elect_one()) {
       int aslot = 0; uint32_t aphase = 0;
       int bstage = 0; uint32_t bphase = 0;
       int acc = 0; uint32_t acc_phase = 0;

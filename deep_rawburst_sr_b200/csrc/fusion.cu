@@ -304,15 +304,22 @@ softmax_wsum8_kernel(View feat, View logits, const float* __restrict__ offsets, 
     const int rem = (int)(pix - (long long)b * HW);
     const int y = rem / W, x = rem - y * W;
     const int ch = c8 * 8;
+    // online softmax with ONE exponential per element: d = l - m; x = exp(-|d|);
+    //   d <= 0: (scale old, weight new) = (1, x)   else: (x, 1) and the running max moves to l
     float m[8], s[8], acc[8];
+    {
+      const long long img = (long long)b * frames;
+      const Vec8 l = ld8<TL>(lbase + (img * HW + rem) * logits.c_pitch + ch);
+      const Vec8 a = ld8<TF>(fbase + (img * HW + rem) * feat.c_pitch + ch);
 #pragma unroll
-    for (int k = 0; k < 8; ++k) { m[k] = -INFINITY; s[k] = 0.0f; acc[k] = 0.0f; }
+      for (int k = 0; k < 8; ++k) { m[k] = l.v[k]; s[k] = 1.0f; acc[k] = a.v[k]; }
+    }
 #pragma unroll 2
-    for (int n = 0; n < frames; ++n) {
+    for (int n = 1; n < frames; ++n) {
       const long long img = (long long)b * frames + n;
       const Vec8 l = ld8<TL>(lbase + (img * HW + rem) * logits.c_pitch + ch);
       Vec8 a;
-      if (n == 0 || offsets == nullptr) {
+      if (offsets == nullptr) {
         a = ld8<TF>(fbase + (img * HW + rem) * feat.c_pitch + ch);
       } else {
         const long long pr = (long long)b * (frames - 1) + (n - 1);
@@ -323,12 +330,14 @@ softmax_wsum8_kernel(View feat, View logits, const float* __restrict__ offsets, 
       }
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
-        const float mn = fmaxf(m[k], l.v[k]);
-        const float sc = expf(m[k] - mn);   // exp(-inf) = 0 on the first frame
-        const float e = expf(l.v[k] - mn);
+        const float d = l.v[k] - m[k];
+        const float ex = (sizeof(TL) == 2) ? __expf(-fabsf(d)) : expf(-fabsf(d));
+        const bool up = d > 0.0f;
+        const float sc = up ? ex : 1.0f;
+        const float e = up ? 1.0f : ex;
         s[k] = fmaf(s[k], sc, e);
         acc[k] = fmaf(acc[k], sc, a.v[k] * e);
-        m[k] = mn;
+        m[k] = up ? l.v[k] : m[k];
       }
     }
     Vec8 r;
