@@ -263,6 +263,123 @@ __device__ __forceinline__ void epilogue_chunk(const ConvTcParams& p, const uint
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------
+// Coalesced bf16 epilogue of one 16x8 tile for one warp (32 pixels = 4 tile rows x 8).
+// The L1 data pipe is shared by the tensor core's smem operand reads and by LSU traffic, and a warp instruction
+// whose lanes touch 32 different 128-byte lines costs 32 wavefronts.  So results (and residuals) are transposed
+// through a padded per-warp smem staging area: thread-per-pixel rows on the TMEM side, 128-byte-line-per-8-lanes
+// on the global side (4 wavefronts per instruction instead of 32).
+// ---------------------------------------------------------------------------------------------------------
+constexpr int STG_ROW = 144;                    // 128 data bytes + 16 pad: conflict-free for both access patterns
+constexpr int STG_WARP_BYTES = 32 * STG_ROW;    // per epilogue warp
+
+struct TilePos { long long img; int y0, x0; };  // x0: first column of THIS 16x8 tile
+
+__device__ __forceinline__ long long out_pixel_off(const ConvTcParams& p, const TilePos& tp, int m, int co0, bool* valid) {
+  const int y = tp.y0 + (m >> 3), x = tp.x0 + (m & 7);
+  *valid = (y < p.H) && (x < p.W);
+  if (p.shuffle_r > 1) {
+    const int per_i = p.shuffle_r * 32;
+    const int si = co0 / per_i, j0 = (co0 - si * per_i) / 32;
+    return ((tp.img * p.yH + (y * p.shuffle_r + si)) * p.yW + (x * p.shuffle_r + j0)) * p.y_pitch + p.y_coff;
+  }
+  return ((tp.img * p.yH + y) * p.yW + x) * p.y_pitch + p.y_coff + co0;
+}
+
+template <int GW>   // group width in channels: 64, 32 or 16  (GW * 2 bytes per pixel row)
+__device__ __forceinline__ void epilogue_group_bf16(const ConvTcParams& p, uint32_t tbase, int g0, int co0, const TilePos& tp,
+                                                    int quarter, int lane, uint8_t* stg, const uint4* res_pref) {
+  constexpr int LPP = GW / 8;        // lanes (16-byte chunks) per pixel
+  constexpr int PPI = 32 / LPP;      // pixels per warp instruction
+  const int sub = lane / LPP, chunk = lane % LPP;
+  // ---- residual: coalesced global -> staging rows
+  if (p.res) {
+#pragma unroll
+    for (int it = 0; it < LPP; ++it) {
+      const int ml = it * PPI + sub;
+      uint4 q;
+      if (res_pref) {
+        q = res_pref[it];
+      } else {
+        bool valid;
+        const int m = quarter * 32 + ml;
+        const int y = tp.y0 + (m >> 3), x = tp.x0 + (m & 7);
+        valid = (y < p.H) && (x < p.W);
+        const long long roff = ((tp.img * p.yH + y) * p.yW + x) * p.r_pitch + p.r_coff + co0 + g0;
+        q = valid ? __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.res) + roff) + chunk)
+                  : make_uint4(0, 0, 0, 0);
+      }
+      *reinterpret_cast<uint4*>(stg + ml * STG_ROW + chunk * 16) = q;
+    }
+    __syncwarp();
+  }
+  // ---- accumulator -> bias / residual / activation -> bf16 -> own staging row
+  uint8_t* myrow = stg + lane * STG_ROW;
+#pragma unroll
+  for (int c0 = 0; c0 < GW; c0 += 32) {
+    constexpr int NC_MAX = 32;
+    const int nc = (GW - c0 >= 32) ? 32 : 16;
+    uint32_t r[32];
+    if (nc == 32) tmem_ld32(tbase + (uint32_t)(g0 + c0), r);
+    else tmem_ld16(tbase + (uint32_t)(g0 + c0), r);
+    float v[NC_MAX];
+#pragma unroll
+    for (int j = 0; j < NC_MAX; ++j) v[j] = (j < nc) ? __uint_as_float(r[j]) : 0.0f;
+    if (p.bias) {
+#pragma unroll
+      for (int j = 0; j < NC_MAX; j += 4) {
+        if (j < nc) {
+          const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + co0 + g0 + c0 + j));
+          v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+        }
+      }
+    }
+    if (p.res) {
+#pragma unroll
+      for (int j = 0; j < NC_MAX / 8; ++j) {
+        if (j * 8 < nc) {
+          const uint4 q = *reinterpret_cast<const uint4*>(myrow + c0 * 2 + j * 16);
+          const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&q);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const float2 f = __bfloat1622float2(h[k]);
+            v[8 * j + 2 * k] += f.x; v[8 * j + 2 * k + 1] += f.y;
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < NC_MAX; ++j) v[j] = apply_act(v[j], p.act);
+#pragma unroll
+    for (int j = 0; j < NC_MAX / 8; ++j) {
+      if (j * 8 < nc) {
+        uint4 q;
+        __nv_bfloat162 h0 = __floats2bfloat162_rn(v[8 * j], v[8 * j + 1]);
+        __nv_bfloat162 h1 = __floats2bfloat162_rn(v[8 * j + 2], v[8 * j + 3]);
+        __nv_bfloat162 h2 = __floats2bfloat162_rn(v[8 * j + 4], v[8 * j + 5]);
+        __nv_bfloat162 h3 = __floats2bfloat162_rn(v[8 * j + 6], v[8 * j + 7]);
+        q.x = *reinterpret_cast<uint32_t*>(&h0); q.y = *reinterpret_cast<uint32_t*>(&h1);
+        q.z = *reinterpret_cast<uint32_t*>(&h2); q.w = *reinterpret_cast<uint32_t*>(&h3);
+        *reinterpret_cast<uint4*>(myrow + c0 * 2 + j * 16) = q;
+      }
+    }
+  }
+  __syncwarp();
+  // ---- staging rows -> coalesced global stores (LPP lanes cover one pixel's GW*2 contiguous bytes)
+#pragma unroll
+  for (int it = 0; it < LPP; ++it) {
+    const int ml = it * PPI + sub;
+    bool valid;
+    const long long off = out_pixel_off(p, tp, quarter * 32 + ml, co0, &valid) + g0;
+    if (valid) {
+      const uint4 q = *reinterpret_cast<const uint4*>(stg + ml * STG_ROW + chunk * 16);
+      *(reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.y) + off) + chunk) = q;
+    }
+  }
+  __syncwarp();
+}
+
 struct ItemCoord { int nt, img, y0, x0; };
 __device__ __forceinline__ ItemCoord decode_item(const ConvTcParams& p, long long item) {
   ItemCoord c;
@@ -284,7 +401,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* smem_a = smem;                                         // [a_slots][a_bytes]
   uint8_t* smem_b = smem + (size_t)p.a_slots * p.a_bytes;         // [b_stages][b_bytes]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_b + (size_t)p.b_stages * p.b_bytes);
+  uint8_t* smem_stg = smem_b + (size_t)p.b_stages * p.b_bytes;    // [8 epilogue warps][STG_WARP_BYTES]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_stg + 8 * STG_WARP_BYTES);
   uint64_t* a_full = bars;
   uint64_t* a_empty = a_full + p.a_slots;
   uint64_t* b_full = a_empty + p.a_slots;
@@ -415,7 +533,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
     const int group = (warp - 3) >> 2;             // 0 or 1
     const int m = quarter * 32 + lane;             // pixel within a 16x8 tile
     const int ty = m >> 3, tx = m & 7;
-    const bool pref = p.vec_ok && p.res != nullptr;
     int acc = 0; uint32_t acc_phase = 0;
     for (long long item = blockIdx.x; item < p.total_items; item += gridDim.x) {
       const ItemCoord c = decode_item(p, item);
@@ -433,33 +550,60 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
         off = (((long long)c.img * p.yH + y) * p.yW + x) * p.y_pitch + p.y_coff + co0;
       }
       const long long roff = (((long long)c.img * p.yH + y) * p.yW + x) * p.r_pitch + p.r_coff + co0;
-      // chunk ownership: mt == 2 -> all chunks of my tile; mt == 1 -> chunks with (index & 1) == group
-      uint4 rq[4][4];
-      if (pref && valid) {
-        const __nv_bfloat16* rp = reinterpret_cast<const __nv_bfloat16*>(p.res) + roff;
+      const uint32_t tbase = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)((acc * p.mt + t) * NT);
+      if (p.vec_ok && p.y_dtype == DBSR_BF16) {
+        // ---------- coalesced path: 64/32/16-channel groups through the per-warp staging rows ----------
+        uint8_t* stg = smem_stg + (size_t)(warp - 3) * STG_WARP_BYTES;
+        TilePos tp; tp.img = c.img; tp.y0 = c.y0; tp.x0 = c.x0 + t * TILE_W;
+        // group ownership: mt == 2 -> every group of my tile; mt == 1 -> groups with (index & 1) == group id
+        const int first_gw = NT >= 64 ? 64 : (NT >= 32 ? 32 : 16);
+        uint4 rpre[8];
+        const bool mine0 = (p.mt == 2) || group == 0;
+        const bool pre = p.res != nullptr && mine0;
+        if (pre) {   // prefetch the residual of the first group (coalesced pattern) before waiting for the MMAs
+          const int lpp = first_gw / 8, ppi = 32 / lpp;
 #pragma unroll
-        for (int ci = 0; ci < 4; ++ci) {
-          if (ci * 32 < NT && (p.mt == 2 || (ci & 1) == group)) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-              if (ci * 32 + j * 8 < NT) rq[ci][j] = __ldg(reinterpret_cast<const uint4*>(rp + ci * 32 + j * 8));
+          for (int it = 0; it < 8; ++it) {
+            if (it < lpp) {
+              const int m = quarter * 32 + it * ppi + lane / lpp;
+              const int yy = tp.y0 + (m >> 3), xx = tp.x0 + (m & 7);
+              const long long ro = ((tp.img * p.yH + yy) * p.yW + xx) * p.r_pitch + p.r_coff + co0;
+              rpre[it] = (yy < p.H && xx < p.W)
+                             ? __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.res) + ro) + lane % lpp)
+                             : make_uint4(0, 0, 0, 0);
+            }
           }
         }
-      }
-      mbar_wait(&tfull_bar[acc], acc_phase, 400 + acc);
-      tc_fence_after();
-      const uint32_t tbase = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)((acc * p.mt + t) * NT);
+        mbar_wait(&tfull_bar[acc], acc_phase, 400 + acc);
+        tc_fence_after();
+        int g0 = 0, gi = 0;
+        while (g0 < NT) {
+          const int rem = NT - g0;
+          const int gw = rem >= 64 ? 64 : (rem >= 32 ? 32 : 16);
+          if (p.mt == 2 || (gi & 1) == group) {
+            const uint4* rp = (pre && g0 == 0) ? rpre : nullptr;
+            if (gw == 64) epilogue_group_bf16<64>(p, tbase, g0, co0, tp, quarter, lane, stg, rp);
+            else if (gw == 32) epilogue_group_bf16<32>(p, tbase, g0, co0, tp, quarter, lane, stg, rp);
+            else epilogue_group_bf16<16>(p, tbase, g0, co0, tp, quarter, lane, stg, rp);
+          }
+          g0 += gw; ++gi;
+        }
+      } else {
+        // ---------- generic path (fp32 outputs, odd channel counts): one thread stores its own pixel ----------
+        mbar_wait(&tfull_bar[acc], acc_phase, 400 + acc);
+        tc_fence_after();
 #pragma unroll
-      for (int ci = 0; ci < 4; ++ci) {
-        const int c0 = ci * 32;
-        if (c0 < NT && (p.mt == 2 || (ci & 1) == group)) {
-          uint32_t r[32];
-          if (c0 + 32 <= NT) {
-            tmem_ld32(tbase + (uint32_t)c0, r);
-            if (valid) epilogue_chunk<32>(p, r, co0 + c0, off + c0, roff + c0, pref ? rq[ci] : nullptr);
-          } else {   // 16-column tail (n_tile is a multiple of 16)
-            tmem_ld16(tbase + (uint32_t)c0, r);
-            if (valid) epilogue_chunk<16>(p, r, co0 + c0, off + c0, roff + c0, pref ? rq[ci] : nullptr);
+        for (int ci = 0; ci < 4; ++ci) {
+          const int c0 = ci * 32;
+          if (c0 < NT && (p.mt == 2 || (ci & 1) == group)) {
+            uint32_t r[32];
+            if (c0 + 32 <= NT) {
+              tmem_ld32(tbase + (uint32_t)c0, r);
+              if (valid) epilogue_chunk<32>(p, r, co0 + c0, off + c0, roff + c0, nullptr);
+            } else {   // 16-column tail (n_tile is a multiple of 16)
+              tmem_ld16(tbase + (uint32_t)c0, r);
+              if (valid) epilogue_chunk<16>(p, r, co0 + c0, off + c0, roff + c0, nullptr);
+            }
           }
         }
       }
@@ -562,7 +706,7 @@ static int tc_plan(const dbsr_conv_t* c, TcConfig* cfg, bool set_err) {
   cfg->cout_pad = cpad;
   const int tiles_x = ceil_div(c->x.w, TILE_W);
   const int pad = (c->ksize == 3) ? c->dilation : 0;
-  const int budget = 227 * 1024 - 4096;
+  const int budget = 227 * 1024 - 4096 - 8 * STG_WARP_BYTES;
   const int taps = c->ksize * c->ksize;
   cfg->b_bytes = nt * ck * 2;
   TC_REQ(cfg->b_bytes % 1024 == 0, "conv2d_tc: internal: unaligned weight stage");
@@ -599,7 +743,7 @@ static int tc_plan(const dbsr_conv_t* c, TcConfig* cfg, bool set_err) {
     TC_REQ(st >= 2, "conv2d_tc: no room for the weight pipeline");
     cfg->b_stages = st;
   }
-  int smem = cfg->a_slots * cfg->a_bytes + cfg->b_stages * cfg->b_bytes + 1024 /*align slack*/ + 2048 /*barriers*/;
+  int smem = cfg->a_slots * cfg->a_bytes + cfg->b_stages * cfg->b_bytes + 8 * STG_WARP_BYTES + 1024 /*align slack*/ + 2048 /*barriers*/;
   // a CTA that owns more than half of TMEM must be alone on its SM: make its smem footprint exclusive too
   if (cfg->tmem_cols > 256 && smem < 120 * 1024) smem = 120 * 1024;
   cfg->smem_bytes = smem;
