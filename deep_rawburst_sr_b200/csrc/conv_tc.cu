@@ -177,6 +177,8 @@ struct ConvTcParams {
   int a_slots, b_stages, b_resident;
   int a_bytes, a_tx_bytes, b_bytes;
   int halo_w;           // pixels per row of the A box
+  int flat;             // small-map mode: the A box holds flat_ni whole zero-bordered images, M rows = flat slots
+  int flat_s, flat_ni;  // slots per image (H+2)*(W+2); images per item
   // output
   void* y; int y_dtype; int y_pitch; int y_coff; int yH, yW;
   const void* res; int r_dtype; int r_pitch; int r_coff;   // residual with the geometry of y
@@ -385,6 +387,10 @@ __device__ __forceinline__ ItemCoord decode_item(const ConvTcParams& p, long lon
   ItemCoord c;
   c.nt = (int)(item % p.ntiles_n);
   const long long tm = item / p.ntiles_n;
+  if (p.flat) {   // item = flat_ni consecutive images
+    c.img = (int)tm * p.flat_ni; c.y0 = 0; c.x0 = 0;
+    return c;
+  }
   const int per_img = p.items_x * p.tiles_y;
   c.img = (int)(tm / per_img);
   const int rem = (int)(tm - (long long)c.img * per_img);
@@ -444,7 +450,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
         for (int ch = 0; ch < p.nchunks; ++ch) {
           mbar_wait(&a_empty[slot], phase ^ 1, 100 + slot);
           mbar_arrive_expect_tx(&a_full[slot], (uint32_t)p.a_tx_bytes);
-          tma_load_4d(&tmap_x, &a_full[slot], smem_a + (size_t)slot * p.a_bytes, ch * CK, c.x0 - pad, c.y0 - pad, c.img);
+          tma_load_4d(&tmap_x, &a_full[slot], smem_a + (size_t)slot * p.a_bytes, ch * CK, c.x0 - pad, c.y0 - pad, c.img);   // flat: (-1, -1, first image)
           if (++slot == p.a_slots) { slot = 0; phase ^= 1; }
         }
       }
@@ -482,7 +488,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
       int bstage = 0; uint32_t bphase = 0;
       int acc = 0; uint32_t acc_phase = 0;
       bool first_item = true;
-      const uint32_t a_sbo = (uint32_t)p.halo_w * ROW_BYTES;
+      // flat mode: M rows are consecutive slots of the box (dense 8-slot atoms); tap shift is still ky*halo_w + kx slots
+      const uint32_t a_sbo = (p.flat ? 8u : (uint32_t)p.halo_w) * ROW_BYTES;
       const uint32_t b_sbo = 8u * ROW_BYTES;
       for (long long item = blockIdx.x; item < p.total_items; item += gridDim.x) {
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1, 200 + acc);
@@ -538,18 +545,25 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
       const ItemCoord c = decode_item(p, item);
       const int co0 = c.nt * NT;
       const int t = (p.mt == 2) ? group : 0;
-      const int y = c.y0 + ty, x = c.x0 + t * TILE_W + tx;
-      const bool valid = (y < p.H) && (x < p.W);
+      int y = c.y0 + ty, x = c.x0 + t * TILE_W + tx;
+      long long img = c.img;
+      bool valid = (y < p.H) && (x < p.W);
+      if (p.flat) {   // M row m = flat slot: image j = m / S, padded row / column inside it
+        const int j = m / p.flat_s, rem = m - j * p.flat_s;
+        y = rem / p.halo_w; x = rem - y * p.halo_w;
+        img = c.img + j;
+        valid = (y < p.H) && (x < p.W) && (img < p.n);
+      }
       long long off;   // element offset of this thread's first output channel of the N tile
       if (p.shuffle_r > 1) {
         // packed channel co' = i*256 + j*32 + c ; N tile = 128 -> i = nt / 2, j0 = (nt & 1) * 4
         const int per_i = p.shuffle_r * 32;
         const int si = co0 / per_i, j0 = (co0 - si * per_i) / 32;
-        off = (((long long)c.img * p.yH + (y * p.shuffle_r + si)) * p.yW + (x * p.shuffle_r + j0)) * p.y_pitch + p.y_coff;
+        off = ((img * p.yH + (y * p.shuffle_r + si)) * p.yW + (x * p.shuffle_r + j0)) * p.y_pitch + p.y_coff;
       } else {
-        off = (((long long)c.img * p.yH + y) * p.yW + x) * p.y_pitch + p.y_coff + co0;
+        off = ((img * p.yH + y) * p.yW + x) * p.y_pitch + p.y_coff + co0;
       }
-      const long long roff = (((long long)c.img * p.yH + y) * p.yW + x) * p.r_pitch + p.r_coff + co0;
+      const long long roff = ((img * p.yH + y) * p.yW + x) * p.r_pitch + p.r_coff + co0;
       const uint32_t tbase = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)((acc * p.mt + t) * NT);
       if (p.vec_ok && p.y_dtype == DBSR_BF16) {
         // ---------- coalesced path: 64/32/16-channel groups through the per-warp staging rows ----------
@@ -665,6 +679,7 @@ static void tc_geometry(int cin, int cout, int* ck, int* kpad, int* n_tile, int*
 }
 
 struct TcConfig {
+  int flat, flat_s, flat_ni;
   int n_tile, ck, nchunks, cout, cout_pad, mt, halo_w, rows, a_slots, b_stages, b_resident, a_bytes, a_tx_bytes, b_bytes,
       smem_bytes, tmem_cols, vec_ok;
 };
@@ -711,9 +726,29 @@ static int tc_plan(const dbsr_conv_t* c, TcConfig* cfg, bool set_err) {
   cfg->b_bytes = nt * ck * 2;
   TC_REQ(cfg->b_bytes % 1024 == 0, "conv2d_tc: internal: unaligned weight stage");
   cfg->rows = TILE_H + 2 * pad;
-  // item width (mt tiles) and depth of the activation ring: prefer 2 tiles x 3 slots, shrink until the halo boxes
-  // leave room for at least two weight stages (large dilations have large halos)
+  // small maps: pack several whole images (with their zero borders) into one M = 128 tile -- "flat" mode
+  cfg->flat = 0; cfg->flat_s = 0; cfg->flat_ni = 1;
+  if (c->ksize == 3 && c->dilation == 1 && r == 1 && c->x.h <= 8 && c->x.w <= 8) {
+    const int S = (c->x.h + 2) * (c->x.w + 2);
+    const int last = (c->x.h - 1) * (c->x.w + 2) + (c->x.w - 1);
+    const int ni = (127 - last) / S + 1;
+    if (ni >= 2) { cfg->flat = 1; cfg->flat_s = S; cfg->flat_ni = ni; }
+  }
   bool found = false;
+  if (cfg->flat) {
+    cfg->mt = 1; cfg->halo_w = c->x.w + 2; cfg->rows = c->x.h + 2;
+    cfg->a_tx_bytes = cfg->flat_ni * cfg->flat_s * ck * 2;
+    // the MMA reads up to slot 127 + 2*halo_w + 2 (garbage rows beyond the box only feed masked outputs)
+    cfg->a_bytes = round_up((128 + 2 * cfg->halo_w + 2) * ck * 2 > cfg->a_tx_bytes ? (128 + 2 * cfg->halo_w + 2) * ck * 2
+                                                                                   : cfg->a_tx_bytes, 1024);
+    cfg->a_slots = 4;
+    while (cfg->a_slots > 1 && cfg->a_slots * cfg->a_bytes + 4 * cfg->b_bytes > budget) cfg->a_slots--;
+    found = true;
+    vec = false;   // flat slots are not contiguous pixels: per-thread masked epilogue
+    cfg->vec_ok = 0;
+  }
+  // item width (mt tiles) and depth of the activation ring: prefer 2 tiles x 4 slots, shrink until the halo boxes
+  // leave room for the weight stages (large dilations have large halos)
   for (int mt = (tiles_x >= 2 ? 2 : 1); mt >= 1 && !found; --mt) {
     for (int slots = 4; slots >= 1 && !found; --slots) {
       const int hw = TILE_W * mt + 2 * pad;
@@ -805,7 +840,8 @@ extern "C" int dbsr_conv2d_tc(const dbsr_conv_t* c, void* stream) {
     cuuint64_t dims[4] = {(cuuint64_t)c->x.c, (cuuint64_t)c->x.w, (cuuint64_t)c->x.h, (cuuint64_t)c->x.n};
     cuuint64_t strides[3] = {(cuuint64_t)c->x.c_pitch * 2, (cuuint64_t)c->x.w * c->x.c_pitch * 2,
                              (cuuint64_t)c->x.h * c->x.w * c->x.c_pitch * 2};
-    cuuint32_t box[4] = {(cuuint32_t)cfg.ck, (cuuint32_t)cfg.halo_w, (cuuint32_t)cfg.rows, 1};
+    cuuint32_t box[4] = {(cuuint32_t)cfg.ck, (cuuint32_t)cfg.halo_w, (cuuint32_t)cfg.rows,
+                         (cuuint32_t)(cfg.flat ? cfg.flat_ni : 1)};
     cuuint32_t es[4] = {1, 1, 1, 1};
     void* base = reinterpret_cast<__nv_bfloat16*>(c->x.data) + c->x.c_off;
     CUresult rc = encode(&mx, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, base, dims, strides, box, es,
@@ -834,6 +870,8 @@ extern "C" int dbsr_conv2d_tc(const dbsr_conv_t* c, void* stream) {
   p.ntiles_n = cfg.cout_pad / cfg.n_tile;
   p.items_x = ceil_div(p.W, TILE_W * cfg.mt); p.tiles_y = ceil_div(p.H, TILE_H);
   p.total_items = (long long)p.n * p.items_x * p.tiles_y * p.ntiles_n;
+  p.flat = cfg.flat; p.flat_s = cfg.flat_s; p.flat_ni = cfg.flat_ni;
+  if (cfg.flat) p.total_items = (long long)ceil_div(p.n, cfg.flat_ni) * p.ntiles_n;
   p.a_slots = cfg.a_slots; p.b_stages = cfg.b_stages; p.b_resident = cfg.b_resident;
   p.a_bytes = cfg.a_bytes; p.a_tx_bytes = cfg.a_tx_bytes; p.b_bytes = cfg.b_bytes; p.halo_w = cfg.halo_w;
   p.y = c->y.data; p.y_dtype = c->y.dtype; p.y_pitch = c->y.c_pitch; p.y_coff = c->y.c_off;

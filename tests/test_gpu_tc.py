@@ -37,6 +37,12 @@ TC_CASES = {
     'pwc_ext_16x16': (16, 16, 3, 1, 2, 32, 32, 2, False, False, 0),
     'pwc_ref_d8_128x96': (128, 96, 3, 8, 1, 16, 16, 2, False, False, 0),
     'pwc_ref_d16_96x64': (96, 64, 3, 16, 1, 32, 32, 2, False, False, 0),
+    # small maps -> "flat" mode (several whole images per M tile); image counts not multiples of the packing factor
+    'flat_1x1_196x196_n37': (196, 196, 3, 1, 37, 1, 1, 2, False, False, 0),
+    'flat_2x2_565x64_n21': (565, 64, 3, 1, 21, 2, 2, 2, False, False, 0),
+    'flat_4x4_437x96_n11': (437, 96, 3, 1, 11, 4, 4, 2, False, False, 0),
+    'flat_4x4_629x2_f32': (629, 2, 3, 1, 7, 4, 4, 0, True, True, 0),
+    'flat_2x3_128x128': (128, 128, 3, 1, 9, 2, 3, 1, True, False, 0),
 }
 
 
