@@ -552,7 +552,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
         const int j = m / p.flat_s, rem = m - j * p.flat_s;
         y = rem / p.halo_w; x = rem - y * p.halo_w;
         img = c.img + j;
-        valid = (y < p.H) && (x < p.W) && (img < p.n);
+        valid = (j < p.flat_ni) && (y < p.H) && (x < p.W) && (img < p.n);   // rows past the box belong to nobody
       }
       long long off;   // element offset of this thread's first output channel of the N tile
       if (p.shuffle_r > 1) {
@@ -732,7 +732,9 @@ static int tc_plan(const dbsr_conv_t* c, TcConfig* cfg, bool set_err) {
     const int S = (c->x.h + 2) * (c->x.w + 2);
     const int last = (c->x.h - 1) * (c->x.w + 2) + (c->x.w - 1);
     const int ni = (127 - last) / S + 1;
-    if (ni >= 2) { cfg->flat = 1; cfg->flat_s = S; cfg->flat_ni = ni; }
+    int ni_use = ni;
+    if (const char* e = getenv("DBSR_TC_FLAT_NI")) { const int v = atoi(e); if (v >= 1 && v < ni) ni_use = v; }   // debug knob
+    if (ni >= 2) { cfg->flat = 1; cfg->flat_s = S; cfg->flat_ni = ni_use; }
   }
   bool found = false;
   if (cfg->flat) {
@@ -803,7 +805,8 @@ static int launch_tc(const CUtensorMap& mx, const CUtensorMap& mw, const ConvTcP
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
   }
-  const int grid = (int)(p.total_items < num_sms ? p.total_items : num_sms);
+  int grid = (int)(p.total_items < num_sms ? p.total_items : num_sms);
+  if (const char* e = getenv("DBSR_TC_GRID")) { const int g = atoi(e); if (g > 0 && g < grid) grid = g; }   // debug knob
   conv_tc_kernel<CK><<<grid, TC_THREADS, smem, st>>>(mx, mw, p);
   return check_launch("conv2d_tc");
 }
