@@ -148,22 +148,8 @@ def main():
         torch.cuda.synchronize()
 
     def max_over_ranks(ms):
-        if world > 1:
-            t = torch.tensor([ms], device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            return float(t.item())
-        return ms
-
-    if args.one_forward:
-        for _ in range(args.warmup):
-            net(dev_in)
-        torch.cuda.synchronize()
-        eng.launches = 0
-        net(dev_in)
-        torch.cuda.synchronize()
-        print(json.dumps({'one_forward': True, 'launches': eng.launches, 'batch': B}))
-        return
-    net.use_cuda_graph = not args.no_graph
+        from deep_rawburst_sr_b200.sharding import max_over_ranks as _mx
+        return _mx(ms, dev)
 
     # ---- device-resident throughput ("value"): K forwards, inputs already in HBM
     for _ in range(args.warmup):
