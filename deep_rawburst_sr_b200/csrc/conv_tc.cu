@@ -26,6 +26,7 @@
 
 #include <cuda.h>
 #include <stdlib.h>
+#include <string.h>
 
 namespace dbsr {
 
@@ -95,6 +96,12 @@ __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
 }
 
+// 16-byte asynchronous global -> shared copy (LDGSTS); src_bytes = 0 zero-fills (out-of-image pixels)
+__device__ __forceinline__ void cp_async16(void* dst_smem, const void* src, uint32_t src_bytes) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(dst_smem)), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
@@ -136,6 +143,27 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+}
+
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
@@ -159,7 +187,8 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t sbo_
 // kernel
 // ---------------------------------------------------------------------------------------------------------
 constexpr int TILE_H = 16, TILE_W = 8;
-constexpr int TC_THREADS = 352;   // warps 0-2: A producer / MMA issuer / B producer; warps 3-10: epilogue
+constexpr int TC_THREADS = 384;   // warpgroup 0 = warps 0-2 (A producer / MMA issuer / B producer) + 1 idle warp;
+                                  // warpgroups 1-2 = warps 4-11: epilogue.
 
 struct ConvTcParams {
   int n, H, W;          // input == output spatial size (stride 1, "same" padding)
@@ -177,6 +206,10 @@ struct ConvTcParams {
   int a_slots, b_stages, b_resident;
   int a_bytes, a_tx_bytes, b_bytes;
   int halo_w;           // pixels per row of the A box
+  int res_chunks;       // > 0: the residual is accumulated on the tensor core as res_chunks extra K chunks (identity weights)
+  int r_tx_bytes;       // bytes of one residual box {CK, 8*mt px, 16 rows}
+  long long* prof;      // debug: per-role cycle counters of CTA 0 (nullptr = off)
+  int debug;            // bit 0: skip epilogue math/stores, bit 1: skip MMAs, bit 2: skip A loads, bit 3: skip B loads
   int flat;             // small-map mode: the A box holds flat_ni whole zero-bordered images, M rows = flat slots
   int flat_s, flat_ni;  // slots per image (H+2)*(W+2); images per item
   // output
@@ -276,133 +309,134 @@ __device__ __forceinline__ void epilogue_chunk(const ConvTcParams& p, const uint
 constexpr int STG_ROW = 144;                    // 128 data bytes + 16 pad: conflict-free for both access patterns
 constexpr int STG_WARP_BYTES = 32 * STG_ROW;    // per epilogue warp
 
-struct TilePos { long long img; int y0, x0; };  // x0: first column of THIS 16x8 tile
+// geometry of one 16x8 tile for the coalesced epilogue: pointers to its pixel (0,0) at the first channel of the N
+// tile, element strides between tile rows / columns (pixel-shuffle folds into these), and how many rows / columns of
+// the tile are inside the image
+struct TileGeo {
+  __nv_bfloat16* y; const __nv_bfloat16* r;
+  int y_row, y_col, r_row, r_col;   // element strides
+  int rows_in, cols_in;
+};
 
-__device__ __forceinline__ long long out_pixel_off(const ConvTcParams& p, const TilePos& tp, int m, int co0, bool* valid) {
-  const int y = tp.y0 + (m >> 3), x = tp.x0 + (m & 7);
-  *valid = (y < p.H) && (x < p.W);
-  if (p.shuffle_r > 1) {
-    const int per_i = p.shuffle_r * 32;
-    const int si = co0 / per_i, j0 = (co0 - si * per_i) / 32;
-    return ((tp.img * p.yH + (y * p.shuffle_r + si)) * p.yW + (x * p.shuffle_r + j0)) * p.y_pitch + p.y_coff;
+// one 32-column chunk: accumulator (+bias, +residual from the staging row) -> activation -> bf16 -> staging row
+template <int NC>
+__device__ __forceinline__ void finish_chunk(const ConvTcParams& p, const uint32_t (&r)[32], const float* bias, uint8_t* myrow_c,
+                                             bool has_res) {
+  float v[NC];
+#pragma unroll
+  for (int j = 0; j < NC; ++j) v[j] = __uint_as_float(r[j]);
+  if (bias) {
+#pragma unroll
+    for (int j = 0; j < NC; j += 4) {
+      const float4 b = __ldg(reinterpret_cast<const float4*>(bias + j));
+      v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+    }
   }
-  return ((tp.img * p.yH + y) * p.yW + x) * p.y_pitch + p.y_coff + co0;
+  if (has_res) {
+#pragma unroll
+    for (int j = 0; j < NC / 8; ++j) {
+      const uint4 q = *reinterpret_cast<const uint4*>(myrow_c + j * 16);
+      const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&q);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float2 f = __bfloat1622float2(h[k]);
+        v[8 * j + 2 * k] += f.x; v[8 * j + 2 * k + 1] += f.y;
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < NC; ++j) v[j] = apply_act(v[j], p.act);
+#pragma unroll
+  for (int j = 0; j < NC / 8; ++j) {
+    uint4 q;
+    __nv_bfloat162 h0 = __floats2bfloat162_rn(v[8 * j], v[8 * j + 1]);
+    __nv_bfloat162 h1 = __floats2bfloat162_rn(v[8 * j + 2], v[8 * j + 3]);
+    __nv_bfloat162 h2 = __floats2bfloat162_rn(v[8 * j + 4], v[8 * j + 5]);
+    __nv_bfloat162 h3 = __floats2bfloat162_rn(v[8 * j + 6], v[8 * j + 7]);
+    q.x = *reinterpret_cast<uint32_t*>(&h0); q.y = *reinterpret_cast<uint32_t*>(&h1);
+    q.z = *reinterpret_cast<uint32_t*>(&h2); q.w = *reinterpret_cast<uint32_t*>(&h3);
+    *reinterpret_cast<uint4*>(myrow_c + j * 16) = q;
+  }
 }
 
 template <int GW>   // group width in channels: 64, 32 or 16  (GW * 2 bytes per pixel row)
-__device__ __forceinline__ void epilogue_group_bf16(const ConvTcParams& p, uint32_t tbase, int g0, int co0, const TilePos& tp,
-                                                    int quarter, int lane, uint8_t* stg, const uint4* res_pref) {
+__device__ __forceinline__ void epilogue_group_bf16(const ConvTcParams& p, uint32_t tbase, int g0, int co0, const TileGeo& tg,
+                                                    int quarter, int lane, uint8_t* stg, bool res_inflight, bool profme) {
   constexpr int LPP = GW / 8;        // lanes (16-byte chunks) per pixel
   constexpr int PPI = 32 / LPP;      // pixels per warp instruction
   const int sub = lane / LPP, chunk = lane % LPP;
-  // ---- residual: coalesced global -> staging rows
-  if (p.res) {
+  long long tq0 = profme ? clock64() : 0;
+  // both accumulator chunks of the group in flight before anything waits on them
+  uint32_t r0[32], r1[32];
+  if (GW >= 32) tmem_ld32_nowait(tbase + (uint32_t)g0, r0); else tmem_ld16_nowait(tbase + (uint32_t)g0, r0);
+  if (GW == 64) tmem_ld32_nowait(tbase + (uint32_t)(g0 + 32), r1);
+  const bool has_res = p.res != nullptr;
+  // ---- residual: coalesced asynchronous global -> staging rows (LPP lanes cover one pixel's GW*2 contiguous bytes);
+  //      the first group of a tile was already issued before the accumulator wait (res_inflight)
+  if (has_res) {
+    if (!res_inflight) {
 #pragma unroll
-    for (int it = 0; it < LPP; ++it) {
-      const int ml = it * PPI + sub;
-      uint4 q;
-      if (res_pref) {
-        q = res_pref[it];
-      } else {
-        bool valid;
-        const int m = quarter * 32 + ml;
-        const int y = tp.y0 + (m >> 3), x = tp.x0 + (m & 7);
-        valid = (y < p.H) && (x < p.W);
-        const long long roff = ((tp.img * p.yH + y) * p.yW + x) * p.r_pitch + p.r_coff + co0 + g0;
-        q = valid ? __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.res) + roff) + chunk)
-                  : make_uint4(0, 0, 0, 0);
+      for (int it = 0; it < LPP; ++it) {
+        const int ml = it * PPI + sub;
+        const int row = quarter * 4 + (ml >> 3), col = ml & 7;
+        const bool ok = row < tg.rows_in && col < tg.cols_in;
+        cp_async16(stg + ml * STG_ROW + chunk * 16, ok ? (const void*)(tg.r + row * tg.r_row + col * tg.r_col + g0 + chunk * 8) : (const void*)tg.r,
+                   ok ? 16u : 0u);
       }
-      *reinterpret_cast<uint4*>(stg + ml * STG_ROW + chunk * 16) = q;
     }
+    cp_async_wait_all();
     __syncwarp();
   }
+  if (profme) { const long long t = clock64(); p.prof[12] += t - tq0; tq0 = t; }
   // ---- accumulator -> bias / residual / activation -> bf16 -> own staging row
   uint8_t* myrow = stg + lane * STG_ROW;
-#pragma unroll
-  for (int c0 = 0; c0 < GW; c0 += 32) {
-    constexpr int NC_MAX = 32;
-    const int nc = (GW - c0 >= 32) ? 32 : 16;
-    uint32_t r[32];
-    if (nc == 32) tmem_ld32(tbase + (uint32_t)(g0 + c0), r);
-    else tmem_ld16(tbase + (uint32_t)(g0 + c0), r);
-    float v[NC_MAX];
-#pragma unroll
-    for (int j = 0; j < NC_MAX; ++j) v[j] = (j < nc) ? __uint_as_float(r[j]) : 0.0f;
-    if (p.bias) {
-#pragma unroll
-      for (int j = 0; j < NC_MAX; j += 4) {
-        if (j < nc) {
-          const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + co0 + g0 + c0 + j));
-          v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
-        }
-      }
-    }
-    if (p.res) {
-#pragma unroll
-      for (int j = 0; j < NC_MAX / 8; ++j) {
-        if (j * 8 < nc) {
-          const uint4 q = *reinterpret_cast<const uint4*>(myrow + c0 * 2 + j * 16);
-          const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&q);
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const float2 f = __bfloat1622float2(h[k]);
-            v[8 * j + 2 * k] += f.x; v[8 * j + 2 * k + 1] += f.y;
-          }
-        }
-      }
-    }
-#pragma unroll
-    for (int j = 0; j < NC_MAX; ++j) v[j] = apply_act(v[j], p.act);
-#pragma unroll
-    for (int j = 0; j < NC_MAX / 8; ++j) {
-      if (j * 8 < nc) {
-        uint4 q;
-        __nv_bfloat162 h0 = __floats2bfloat162_rn(v[8 * j], v[8 * j + 1]);
-        __nv_bfloat162 h1 = __floats2bfloat162_rn(v[8 * j + 2], v[8 * j + 3]);
-        __nv_bfloat162 h2 = __floats2bfloat162_rn(v[8 * j + 4], v[8 * j + 5]);
-        __nv_bfloat162 h3 = __floats2bfloat162_rn(v[8 * j + 6], v[8 * j + 7]);
-        q.x = *reinterpret_cast<uint32_t*>(&h0); q.y = *reinterpret_cast<uint32_t*>(&h1);
-        q.z = *reinterpret_cast<uint32_t*>(&h2); q.w = *reinterpret_cast<uint32_t*>(&h3);
-        *reinterpret_cast<uint4*>(myrow + c0 * 2 + j * 16) = q;
-      }
-    }
-  }
+  const float* bias = p.bias ? p.bias + co0 + g0 : nullptr;
+  tmem_wait_ld();
+  if (GW >= 32) finish_chunk<32>(p, r0, bias, myrow, has_res); else finish_chunk<16>(p, r0, bias, myrow, has_res);
+  if (GW == 64) finish_chunk<32>(p, r1, bias ? bias + 32 : nullptr, myrow + 64, has_res);
   __syncwarp();
-  // ---- staging rows -> coalesced global stores (LPP lanes cover one pixel's GW*2 contiguous bytes)
+  if (profme) { const long long t = clock64(); p.prof[13] += t - tq0; tq0 = t; }
+  // ---- staging rows -> coalesced global stores
 #pragma unroll
   for (int it = 0; it < LPP; ++it) {
     const int ml = it * PPI + sub;
-    bool valid;
-    const long long off = out_pixel_off(p, tp, quarter * 32 + ml, co0, &valid) + g0;
-    if (valid) {
+    const int row = quarter * 4 + (ml >> 3), col = ml & 7;
+    if (row < tg.rows_in && col < tg.cols_in) {
       const uint4 q = *reinterpret_cast<const uint4*>(stg + ml * STG_ROW + chunk * 16);
-      *(reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.y) + off) + chunk) = q;
+      *(reinterpret_cast<uint4*>(tg.y + row * tg.y_row + col * tg.y_col + g0) + chunk) = q;
     }
   }
   __syncwarp();
+  if (profme) { const long long t = clock64(); p.prof[14] += t - tq0; }
 }
 
+#define PROF_T(var) const long long var = p.prof ? clock64() : 0
+#define PROF_ADD(idx, t0) do { if (p.prof && blockIdx.x == 0) p.prof[idx] += clock64() - (t0); } while (0)
+
 struct ItemCoord { int nt, img, y0, x0; };
-__device__ __forceinline__ ItemCoord decode_item(const ConvTcParams& p, long long item) {
+__device__ __forceinline__ ItemCoord decode_item(const ConvTcParams& p, long long item64) {
   ItemCoord c;
-  c.nt = (int)(item % p.ntiles_n);
-  const long long tm = item / p.ntiles_n;
+  const unsigned item = (unsigned)item64;            // item counts fit 32 bits (64-bit div/mod costs ~100 instr each)
+  const unsigned tm = item / (unsigned)p.ntiles_n;
+  c.nt = (int)(item - tm * (unsigned)p.ntiles_n);
   if (p.flat) {   // item = flat_ni consecutive images
     c.img = (int)tm * p.flat_ni; c.y0 = 0; c.x0 = 0;
     return c;
   }
-  const int per_img = p.items_x * p.tiles_y;
-  c.img = (int)(tm / per_img);
-  const int rem = (int)(tm - (long long)c.img * per_img);
-  c.y0 = (rem / p.items_x) * TILE_H;
-  c.x0 = (rem % p.items_x) * (TILE_W * p.mt);
+  const unsigned per_img = (unsigned)(p.items_x * p.tiles_y);
+  const unsigned img = tm / per_img;
+  const unsigned rem = tm - img * per_img;
+  const unsigned ry = rem / (unsigned)p.items_x;
+  c.img = (int)img;
+  c.y0 = (int)ry * TILE_H;
+  c.x0 = (int)(rem - ry * (unsigned)p.items_x) * (TILE_W * p.mt);
   return c;
 }
 
 template <int CK>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
-               const ConvTcParams p) {
+               const __grid_constant__ CUtensorMap tmap_r, const __grid_constant__ CUtensorMap tmap_i, const ConvTcParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* smem_a = smem;                                         // [a_slots][a_bytes]
@@ -434,6 +468,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     tma_prefetch_desc(&tmap_x);
     tma_prefetch_desc(&tmap_w);
+    if (p.res_chunks) { tma_prefetch_desc(&tmap_r); tma_prefetch_desc(&tmap_i); }
   }
   if (warp == 1) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
   tc_fence_before();
@@ -445,15 +480,31 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
     // ===================== A producer: one halo box per (item, K chunk) =====================
     if (elect_one()) {
       int slot = 0; uint32_t phase = 0;
+      PROF_T(tp0);
       for (long long item = blockIdx.x; item < p.total_items; item += gridDim.x) {
+        PROF_T(td);
         const ItemCoord c = decode_item(p, item);
+        PROF_ADD(10, td);
         for (int ch = 0; ch < p.nchunks; ++ch) {
+          PROF_T(tw);
           mbar_wait(&a_empty[slot], phase ^ 1, 100 + slot);
+          PROF_ADD(8, tw);
+          if (p.debug & 4) { mbar_arrive(&a_full[slot]); }
+          else {
           mbar_arrive_expect_tx(&a_full[slot], (uint32_t)p.a_tx_bytes);
-          tma_load_4d(&tmap_x, &a_full[slot], smem_a + (size_t)slot * p.a_bytes, ch * CK, c.x0 - pad, c.y0 - pad, c.img);   // flat: (-1, -1, first image)
+          tma_load_4d(&tmap_x, &a_full[slot], smem_a + (size_t)slot * p.a_bytes, ch * CK, c.x0 - pad, c.y0 - pad, c.img);
+          }   // flat: (-1, -1, first image)
+          if (++slot == p.a_slots) { slot = 0; phase ^= 1; }
+        }
+        // residual of this N tile as extra K chunks: plain (no halo) box of the residual tensor
+        for (int rc = 0; rc < p.res_chunks; ++rc) {
+          mbar_wait(&a_empty[slot], phase ^ 1, 120 + slot);
+          mbar_arrive_expect_tx(&a_full[slot], (uint32_t)p.r_tx_bytes);
+          tma_load_4d(&tmap_r, &a_full[slot], smem_a + (size_t)slot * p.a_bytes, c.nt * NT + rc * CK, c.x0, c.y0, c.img);
           if (++slot == p.a_slots) { slot = 0; phase ^= 1; }
         }
       }
+      PROF_ADD(9, tp0);
     }
   } else if (warp == 2) {
     // ===================== B producer: weight tiles =====================
@@ -465,6 +516,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
           mbar_arrive_expect_tx(&b_full[t], (uint32_t)p.b_bytes);
           tma_load_2d(&tmap_w, &b_full[t], smem_b + (size_t)t * p.b_bytes, ch * CK, tap * p.cout_pad);
         }
+        for (int rc = 0; rc < p.res_chunks; ++rc) {   // identity tiles of the residual chunks
+          const int t = p.nchunks * taps + rc;
+          mbar_arrive_expect_tx(&b_full[t], (uint32_t)p.b_bytes);
+          tma_load_2d(&tmap_i, &b_full[t], smem_b + (size_t)t * p.b_bytes, rc * CK, 0);
+        }
       } else {
         int stage = 0; uint32_t phase = 0;
         for (long long item = blockIdx.x; item < p.total_items; item += gridDim.x) {
@@ -472,11 +528,20 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
           for (int ch = 0; ch < p.nchunks; ++ch) {
             for (int tap = 0; tap < taps; ++tap) {
               mbar_wait(&b_empty[stage], phase ^ 1, 150 + stage);
+              if (p.debug & 8) { mbar_arrive(&b_full[stage]); }
+              else {
               mbar_arrive_expect_tx(&b_full[stage], (uint32_t)p.b_bytes);
               tma_load_2d(&tmap_w, &b_full[stage], smem_b + (size_t)stage * p.b_bytes, ch * CK,
                           tap * p.cout_pad + nt * NT);
+              }
               if (++stage == p.b_stages) { stage = 0; phase ^= 1; }
             }
+          }
+          for (int rc = 0; rc < p.res_chunks; ++rc) {
+            mbar_wait(&b_empty[stage], phase ^ 1, 170 + stage);
+            mbar_arrive_expect_tx(&b_full[stage], (uint32_t)p.b_bytes);
+            tma_load_2d(&tmap_i, &b_full[stage], smem_b + (size_t)stage * p.b_bytes, rc * CK, 0);
+            if (++stage == p.b_stages) { stage = 0; phase ^= 1; }
           }
         }
       }
@@ -488,60 +553,138 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
       int bstage = 0; uint32_t bphase = 0;
       int acc = 0; uint32_t acc_phase = 0;
       bool first_item = true;
-      // flat mode: M rows are consecutive slots of the box (dense 8-slot atoms); tap shift is still ky*halo_w + kx slots
+      // Descriptors are built incrementally: the high word (SBO | version | layout) is constant per operand, the low
+      // word is (addr >> 4) | LBO; moving inside the box / along K only adds to the low word.  The issuing thread is a
+      // single in-order instruction stream, so everything that can be hoisted out of the per-MMA path is.
+      // flat mode: M rows are consecutive slots of the box (dense 8-slot atoms); tap shift is ky*halo_w + kx slots
       const uint32_t a_sbo = (p.flat ? 8u : (uint32_t)p.halo_w) * ROW_BYTES;
       const uint32_t b_sbo = 8u * ROW_BYTES;
+      const uint32_t a_hi = ((a_sbo >> 4) & 0x3FFFu) | (1u << 14) | (LAYOUT << 29);
+      const uint32_t b_hi = ((b_sbo >> 4) & 0x3FFFu) | (1u << 14) | (LAYOUT << 29);
+      const uint32_t r_sbo = (uint32_t)(TILE_W * p.mt) * ROW_BYTES;          // residual box: 8*mt pixels per row, no halo
+      const uint32_t r_hi = ((r_sbo >> 4) & 0x3FFFu) | (1u << 14) | (LAYOUT << 29);
+      uint32_t tap_off[9];                      // 16-byte units inside the A box
+#pragma unroll
+      for (int tap = 0; tap < 9; ++tap) {
+        const int ky = tap / 3, kx = tap - 3 * (tap / 3);
+        tap_off[tap] = (p.ksize == 3) ? (uint32_t)((ky * p.dil) * p.halo_w + kx * p.dil) * (ROW_BYTES >> 4) : 0u;
+      }
+      const uint32_t tile_step = (uint32_t)TILE_W * (ROW_BYTES >> 4);   // second 16x8 tile of the item
+      const bool two_tiles = p.mt == 2;
+      PROF_T(tm0);
       for (long long item = blockIdx.x; item < p.total_items; item += gridDim.x) {
+        PROF_T(t1);
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1, 200 + acc);
+        PROF_ADD(0, t1);
+        if (p.prof && blockIdx.x == 0) p.prof[11] += 1;
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.mt * NT);
+        const uint32_t d0 = tmem_base + (uint32_t)(acc * p.mt * NT);
+        const uint32_t d1 = d0 + (uint32_t)NT;
         for (int ch = 0; ch < p.nchunks; ++ch) {
+          PROF_T(t2);
           mbar_wait(&a_full[aslot], aphase, 300 + aslot);
-          const uint32_t sa = smem_u32(smem_a + (size_t)aslot * p.a_bytes);
-          for (int tap = 0; tap < taps; ++tap) {
-            uint32_t sb;
+          PROF_ADD(1, t2);
+          tc_fence_after();
+          const uint32_t a_lo0 = ((smem_u32(smem_a + (size_t)aslot * p.a_bytes) >> 4) & 0x3FFFu) | 0x10000u;
+          auto issue_tap = [&](int tap, uint32_t first_acc) {
+            uint32_t b_lo;
             if (p.b_resident) {
               const int t = ch * taps + tap;
-              if (first_item) mbar_wait(&b_full[t], 0, 350 + (t & 31));
-              sb = smem_u32(smem_b + (size_t)t * p.b_bytes);
+              if (first_item) { mbar_wait(&b_full[t], 0, 350 + (t & 31)); tc_fence_after(); }
+              b_lo = ((smem_u32(smem_b + (size_t)t * p.b_bytes) >> 4) & 0x3FFFu) | 0x10000u;
             } else {
+              PROF_T(t3);
               mbar_wait(&b_full[bstage], bphase, 350 + bstage);
-              sb = smem_u32(smem_b + (size_t)bstage * p.b_bytes);
+              PROF_ADD(2, t3);
+              tc_fence_after();
+              b_lo = ((smem_u32(smem_b + (size_t)bstage * p.b_bytes) >> 4) & 0x3FFFu) | 0x10000u;
             }
-            tc_fence_after();
-            const int ky = (p.ksize == 3) ? tap / 3 : 0, kx = (p.ksize == 3) ? tap - 3 * ky : 0;
-            const uint32_t a_tap = sa + (uint32_t)((ky * p.dil) * p.halo_w + kx * p.dil) * ROW_BYTES;
-            for (int t = 0; t < p.mt; ++t) {
+            const uint32_t a_lo = a_lo0 + tap_off[tap];
+            if (!(p.debug & 2)) {
 #pragma unroll
               for (int k16 = 0; k16 < CK / 16; ++k16) {
-                const uint64_t adesc = make_smem_desc(a_tap + (uint32_t)(t * TILE_W) * ROW_BYTES + k16 * 32, a_sbo, LAYOUT);
-                const uint64_t bdesc = make_smem_desc(sb + k16 * 32, b_sbo, LAYOUT);
-                umma_bf16(d_tmem + (uint32_t)(t * NT), adesc, bdesc, idesc, (ch | tap | k16) != 0 ? 1u : 0u);
+                const uint64_t adesc = ((uint64_t)a_hi << 32) | (uint64_t)(a_lo + 2u * k16);
+                const uint64_t bdesc = ((uint64_t)b_hi << 32) | (uint64_t)(b_lo + 2u * k16);
+                umma_bf16(d0, adesc, bdesc, idesc, k16 == 0 ? first_acc : 1u);
+              }
+              if (two_tiles) {
+#pragma unroll
+                for (int k16 = 0; k16 < CK / 16; ++k16) {
+                  const uint64_t adesc = ((uint64_t)a_hi << 32) | (uint64_t)(a_lo + tile_step + 2u * k16);
+                  const uint64_t bdesc = ((uint64_t)b_hi << 32) | (uint64_t)(b_lo + 2u * k16);
+                  umma_bf16(d1, adesc, bdesc, idesc, k16 == 0 ? first_acc : 1u);
+                }
               }
             }
             if (!p.b_resident) {
               umma_commit(&b_empty[bstage]);   // weight stage free once these MMAs retire
               if (++bstage == p.b_stages) { bstage = 0; bphase ^= 1; }
             }
+          };
+          if (taps == 9) {
+            issue_tap(0, ch != 0 ? 1u : 0u);
+#pragma unroll
+            for (int tap = 1; tap < 9; ++tap) issue_tap(tap, 1u);
+          } else {
+            issue_tap(0, ch != 0 ? 1u : 0u);
           }
           umma_commit(&a_empty[aslot]);        // halo box free once every tap of this chunk retired
+          if (++aslot == p.a_slots) { aslot = 0; aphase ^= 1; }
+        }
+        // residual: D += R * I  (exact: identity weights, fp32 accumulation) -- the epilogue never touches it
+        for (int rc = 0; rc < p.res_chunks; ++rc) {
+          mbar_wait(&a_full[aslot], aphase, 320 + aslot);
+          tc_fence_after();
+          const uint32_t a_lo = ((smem_u32(smem_a + (size_t)aslot * p.a_bytes) >> 4) & 0x3FFFu) | 0x10000u;
+          uint32_t b_lo;
+          if (p.b_resident) {
+            const int t = p.nchunks * taps + rc;
+            if (first_item) { mbar_wait(&b_full[t], 0, 360 + (t & 31)); tc_fence_after(); }
+            b_lo = ((smem_u32(smem_b + (size_t)t * p.b_bytes) >> 4) & 0x3FFFu) | 0x10000u;
+          } else {
+            mbar_wait(&b_full[bstage], bphase, 370 + bstage);
+            tc_fence_after();
+            b_lo = ((smem_u32(smem_b + (size_t)bstage * p.b_bytes) >> 4) & 0x3FFFu) | 0x10000u;
+          }
+          if (!(p.debug & 2)) {
+#pragma unroll
+            for (int k16 = 0; k16 < CK / 16; ++k16)
+              umma_bf16(d0, ((uint64_t)r_hi << 32) | (uint64_t)(a_lo + 2u * k16), ((uint64_t)b_hi << 32) | (uint64_t)(b_lo + 2u * k16),
+                        idesc, 1u);
+            if (two_tiles) {
+#pragma unroll
+              for (int k16 = 0; k16 < CK / 16; ++k16)
+                umma_bf16(d1, ((uint64_t)r_hi << 32) | (uint64_t)(a_lo + tile_step + 2u * k16),
+                          ((uint64_t)b_hi << 32) | (uint64_t)(b_lo + 2u * k16), idesc, 1u);
+            }
+          }
+          if (!p.b_resident) {
+            umma_commit(&b_empty[bstage]);
+            if (++bstage == p.b_stages) { bstage = 0; bphase ^= 1; }
+          }
+          umma_commit(&a_empty[aslot]);
           if (++aslot == p.a_slots) { aslot = 0; aphase ^= 1; }
         }
         umma_commit(&tfull_bar[acc]);          // accumulators ready for the epilogue
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         first_item = false;
       }
+      PROF_ADD(4, tm0);
     }
-  } else {
-    // ===================== epilogue (warps 3..10) =====================
+  } else if (warp >= 4) {
+    // ===================== epilogue (warps 4..11) =====================
     // two warps per TMEM lane quarter: with mt == 2 group g owns tile g of every item, with mt == 1 the groups take
     // alternate 32-column chunks.  Residual rows are prefetched before waiting for the accumulator.
     const int quarter = warp & 3;                  // TMEM lane quarter this warp may access
-    const int group = (warp - 3) >> 2;             // 0 or 1
+    const int group = (warp - 4) >> 2;             // 0 or 1
     const int m = quarter * 32 + lane;             // pixel within a 16x8 tile
     const int ty = m >> 3, tx = m & 7;
     int acc = 0; uint32_t acc_phase = 0;
+    const bool profme = p.prof && blockIdx.x == 0 && warp == 4 && lane == 0;
+    const long long te0 = profme ? clock64() : 0;
+    long long t_wait = 0;
     for (long long item = blockIdx.x; item < p.total_items; item += gridDim.x) {
+      const long long ti0 = profme ? clock64() : 0;
       const ItemCoord c = decode_item(p, item);
       const int co0 = c.nt * NT;
       const int t = (p.mt == 2) ? group : 0;
@@ -567,38 +710,55 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
       const uint32_t tbase = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)((acc * p.mt + t) * NT);
       if (p.vec_ok && p.y_dtype == DBSR_BF16) {
         // ---------- coalesced path: 64/32/16-channel groups through the per-warp staging rows ----------
-        uint8_t* stg = smem_stg + (size_t)(warp - 3) * STG_WARP_BYTES;
-        TilePos tp; tp.img = c.img; tp.y0 = c.y0; tp.x0 = c.x0 + t * TILE_W;
+        uint8_t* stg = smem_stg + (size_t)(warp - 4) * STG_WARP_BYTES;
+        const int tx0 = c.x0 + t * TILE_W;
+        TileGeo tg;
+        if (p.shuffle_r > 1) {
+          // packed channel co' = i*256 + j*32 + c ; N tile = 128 -> HR row phase i = nt / 2, first HR column j0 = (nt & 1) * 4
+          const int per_i = p.shuffle_r * 32;
+          const int si = co0 / per_i, j0 = (co0 - si * per_i) / 32;
+          tg.y = reinterpret_cast<__nv_bfloat16*>(p.y) +
+                 (((long long)c.img * p.yH + (c.y0 * p.shuffle_r + si)) * p.yW + (tx0 * p.shuffle_r + j0)) * p.y_pitch + p.y_coff;
+          tg.y_row = p.shuffle_r * p.yW * p.y_pitch; tg.y_col = p.shuffle_r * p.y_pitch;
+        } else {
+          tg.y = reinterpret_cast<__nv_bfloat16*>(p.y) + (((long long)c.img * p.yH + c.y0) * p.yW + tx0) * p.y_pitch + p.y_coff + co0;
+          tg.y_row = p.yW * p.y_pitch; tg.y_col = p.y_pitch;
+        }
+        tg.r = reinterpret_cast<const __nv_bfloat16*>(p.res) + (((long long)c.img * p.yH + c.y0) * p.yW + tx0) * p.r_pitch + p.r_coff + co0;
+        tg.r_row = p.yW * p.r_pitch; tg.r_col = p.r_pitch;
+        tg.rows_in = min(TILE_H, p.H - c.y0); tg.cols_in = min(TILE_W, p.W - tx0);
         // group ownership: mt == 2 -> every group of my tile; mt == 1 -> groups with (index & 1) == group id
         const int first_gw = NT >= 64 ? 64 : (NT >= 32 ? 32 : 16);
-        uint4 rpre[8];
         const bool mine0 = (p.mt == 2) || group == 0;
         const bool pre = p.res != nullptr && mine0;
-        if (pre) {   // prefetch the residual of the first group (coalesced pattern) before waiting for the MMAs
+        if (pre) {   // residual of the first group: asynchronous copy into the staging rows, overlapping the MMA wait
           const int lpp = first_gw / 8, ppi = 32 / lpp;
+          const int sub = lane / lpp, chunk = lane - sub * lpp;
 #pragma unroll
           for (int it = 0; it < 8; ++it) {
             if (it < lpp) {
-              const int m = quarter * 32 + it * ppi + lane / lpp;
-              const int yy = tp.y0 + (m >> 3), xx = tp.x0 + (m & 7);
-              const long long ro = ((tp.img * p.yH + yy) * p.yW + xx) * p.r_pitch + p.r_coff + co0;
-              rpre[it] = (yy < p.H && xx < p.W)
-                             ? __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.res) + ro) + lane % lpp)
-                             : make_uint4(0, 0, 0, 0);
+              const int ml = it * ppi + sub;
+              const int row = quarter * 4 + (ml >> 3), col = ml & 7;
+              const bool ok = row < tg.rows_in && col < tg.cols_in;
+              cp_async16(stg + ml * STG_ROW + chunk * 16, ok ? (const void*)(tg.r + row * tg.r_row + col * tg.r_col + chunk * 8) : (const void*)tg.r,
+                         ok ? 16u : 0u);
             }
           }
         }
+        const long long tw0 = profme ? clock64() : 0;
+        if (profme) p.prof[15] += tw0 - ti0;
         mbar_wait(&tfull_bar[acc], acc_phase, 400 + acc);
+        if (profme) t_wait += clock64() - tw0;
         tc_fence_after();
         int g0 = 0, gi = 0;
         while (g0 < NT) {
           const int rem = NT - g0;
           const int gw = rem >= 64 ? 64 : (rem >= 32 ? 32 : 16);
-          if (p.mt == 2 || (gi & 1) == group) {
-            const uint4* rp = (pre && g0 == 0) ? rpre : nullptr;
-            if (gw == 64) epilogue_group_bf16<64>(p, tbase, g0, co0, tp, quarter, lane, stg, rp);
-            else if (gw == 32) epilogue_group_bf16<32>(p, tbase, g0, co0, tp, quarter, lane, stg, rp);
-            else epilogue_group_bf16<16>(p, tbase, g0, co0, tp, quarter, lane, stg, rp);
+          if ((p.mt == 2 || (gi & 1) == group) && !(p.debug & 1)) {
+            const bool rp = pre && g0 == 0;
+            if (gw == 64) epilogue_group_bf16<64>(p, tbase, g0, co0, tg, quarter, lane, stg, rp, profme);
+            else if (gw == 32) epilogue_group_bf16<32>(p, tbase, g0, co0, tg, quarter, lane, stg, rp, profme);
+            else epilogue_group_bf16<16>(p, tbase, g0, co0, tg, quarter, lane, stg, rp, profme);
           }
           g0 += gw; ++gi;
         }
@@ -627,6 +787,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
       if (lane == 0) mbar_arrive(&tempty_bar[acc]);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
+    if (profme) { p.prof[5] += t_wait; p.prof[7] += clock64() - te0; }
   }
 
   tc_fence_before();
@@ -678,8 +839,28 @@ static void tc_geometry(int cin, int cout, int* ck, int* kpad, int* n_tile, int*
   *cout_pad = round_up(cout, nt);
 }
 
+__global__ void fill_identity_kernel(__nv_bfloat16* w, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n * n) w[i] = __float2bfloat16_rn((i / n) == (i % n) ? 1.0f : 0.0f);
+}
+
+// [n][n] bf16 identity ("weights" of the residual K chunks), created once per n and kept for the process lifetime
+static const void* identity_weights(int n, cudaStream_t st) {
+  static void* cache[17] = {nullptr};
+  const int slot = n / 16;
+  if (slot < 1 || slot > 16) return nullptr;
+  if (!cache[slot]) {
+    void* ptr = nullptr;
+    if (cudaMalloc(&ptr, (size_t)n * n * 2) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    fill_identity_kernel<<<(n * n + 255) / 256, 256, 0, st>>>(reinterpret_cast<__nv_bfloat16*>(ptr), n);
+    if (cudaGetLastError() != cudaSuccess) return nullptr;
+    cache[slot] = ptr;
+  }
+  return cache[slot];
+}
+
 struct TcConfig {
-  int flat, flat_s, flat_ni;
+  int flat, flat_s, flat_ni, res_chunks;
   int n_tile, ck, nchunks, cout, cout_pad, mt, halo_w, rows, a_slots, b_stages, b_resident, a_bytes, a_tx_bytes, b_bytes,
       smem_bytes, tmem_cols, vec_ok;
 };
@@ -755,7 +936,7 @@ static int tc_plan(const dbsr_conv_t* c, TcConfig* cfg, bool set_err) {
     for (int slots = 4; slots >= 1 && !found; --slots) {
       const int hw = TILE_W * mt + 2 * pad;
       const int ab = round_up(cfg->rows * hw * ck * 2, 1024);
-      const int b_all = (kpad / ck) * taps * cfg->b_bytes;
+      const int b_all = ((kpad / ck) * taps + (c->residual.data ? (nt + ck - 1) / ck : 0)) * cfg->b_bytes;
       const bool want_resident = cpad == nt && (kpad / ck) * taps <= 64 && b_all <= budget / 2;
       const int b_need = want_resident ? b_all : 4 * cfg->b_bytes;
       if (slots * ab + b_need <= budget || (slots == 1 && ab + 2 * cfg->b_bytes <= budget)) {
@@ -769,10 +950,15 @@ static int tc_plan(const dbsr_conv_t* c, TcConfig* cfg, bool set_err) {
   int tc = 32;
   while (tc < 2 * cfg->mt * nt) tc <<= 1;
   cfg->tmem_cols = tc;
-  const int b_total = cfg->nchunks * taps * cfg->b_bytes;
-  if (cpad == nt && cfg->a_slots * cfg->a_bytes + b_total <= budget && cfg->nchunks * taps <= 64) {
+  // residual on the tensor core: extra K chunks with identity weights (bf16 residual, aligned, same channel chunking)
+  cfg->res_chunks = 0;
+  if (c->residual.data && !cfg->flat && c->residual.dtype == DBSR_BF16 && (c->residual.c_off % 8) == 0 &&
+      (c->residual.c_pitch % 8) == 0 && ((uintptr_t)c->residual.data % 16) == 0 && nt % ck == 0 && !getenv("DBSR_TC_NO_RESK"))
+    cfg->res_chunks = nt / ck;
+  const int b_total = (cfg->nchunks * taps + cfg->res_chunks) * cfg->b_bytes;
+  if (cpad == nt && cfg->a_slots * cfg->a_bytes + b_total <= budget && cfg->nchunks * taps + cfg->res_chunks <= 64) {
     cfg->b_resident = 1;
-    cfg->b_stages = cfg->nchunks * taps;
+    cfg->b_stages = cfg->nchunks * taps + cfg->res_chunks;
   } else {
     cfg->b_resident = 0;
     int st = (budget - cfg->a_slots * cfg->a_bytes) / cfg->b_bytes;
@@ -789,7 +975,8 @@ static int tc_plan(const dbsr_conv_t* c, TcConfig* cfg, bool set_err) {
 }
 
 template <int CK>
-static int launch_tc(const CUtensorMap& mx, const CUtensorMap& mw, const ConvTcParams& p, int smem, cudaStream_t st) {
+static int launch_tc(const CUtensorMap& mx, const CUtensorMap& mw, const CUtensorMap& mr, const CUtensorMap& mi,
+                     const ConvTcParams& p, int smem, cudaStream_t st) {
   static int configured_smem = 0;
   if (smem > configured_smem) {
     cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<CK>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
@@ -807,7 +994,7 @@ static int launch_tc(const CUtensorMap& mx, const CUtensorMap& mw, const ConvTcP
   }
   int grid = (int)(p.total_items < num_sms ? p.total_items : num_sms);
   if (const char* e = getenv("DBSR_TC_GRID")) { const int g = atoi(e); if (g > 0 && g < grid) grid = g; }   // debug knob
-  conv_tc_kernel<CK><<<grid, TC_THREADS, smem, st>>>(mx, mw, p);
+  conv_tc_kernel<CK><<<grid, TC_THREADS, smem, st>>>(mx, mw, mr, mi, p);
   return check_launch("conv2d_tc");
 }
 
@@ -865,6 +1052,35 @@ extern "C" int dbsr_conv2d_tc(const dbsr_conv_t* c, void* stream) {
     DBSR_REQUIRE(rc == CUDA_SUCCESS, "conv2d_tc: cuTensorMapEncodeTiled(w) failed with %d", (int)rc);
   }
 
+  alignas(64) CUtensorMap mr, mi;
+  memset(&mr, 0, sizeof(mr)); memset(&mi, 0, sizeof(mi));
+  if (cfg.res_chunks > 0) {
+    {
+      cuuint64_t dims[4] = {(cuuint64_t)c->residual.c, (cuuint64_t)c->residual.w, (cuuint64_t)c->residual.h, (cuuint64_t)c->residual.n};
+      cuuint64_t strides[3] = {(cuuint64_t)c->residual.c_pitch * 2, (cuuint64_t)c->residual.w * c->residual.c_pitch * 2,
+                               (cuuint64_t)c->residual.h * c->residual.w * c->residual.c_pitch * 2};
+      cuuint32_t box[4] = {(cuuint32_t)cfg.ck, (cuuint32_t)(TILE_W * cfg.mt), (cuuint32_t)TILE_H, 1};
+      cuuint32_t es[4] = {1, 1, 1, 1};
+      void* base = reinterpret_cast<__nv_bfloat16*>(c->residual.data) + c->residual.c_off;
+      CUresult rc = encode(&mr, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, base, dims, strides, box, es,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      DBSR_REQUIRE(rc == CUDA_SUCCESS, "conv2d_tc: cuTensorMapEncodeTiled(residual) failed with %d", (int)rc);
+    }
+    {
+      const void* eye = identity_weights(cfg.n_tile, (cudaStream_t)stream);
+      DBSR_REQUIRE(eye != nullptr, "conv2d_tc: could not create the identity weight tile (cudaMalloc inside a graph capture?)");
+      cuuint64_t dims[2] = {(cuuint64_t)cfg.n_tile, (cuuint64_t)cfg.n_tile};
+      cuuint64_t strides[1] = {(cuuint64_t)cfg.n_tile * 2};
+      cuuint32_t box[2] = {(cuuint32_t)cfg.ck, (cuuint32_t)cfg.n_tile};
+      cuuint32_t es[2] = {1, 1};
+      CUresult rc = encode(&mi, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(eye), dims, strides, box, es,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      DBSR_REQUIRE(rc == CUDA_SUCCESS, "conv2d_tc: cuTensorMapEncodeTiled(identity) failed with %d", (int)rc);
+    }
+  }
+
   ConvTcParams p;
   p.n = c->x.n; p.H = c->x.h; p.W = c->x.w;
   p.ksize = c->ksize; p.dil = c->dilation;
@@ -880,8 +1096,31 @@ extern "C" int dbsr_conv2d_tc(const dbsr_conv_t* c, void* stream) {
   p.y = c->y.data; p.y_dtype = c->y.dtype; p.y_pitch = c->y.c_pitch; p.y_coff = c->y.c_off;
   p.yH = c->y.h; p.yW = c->y.w;
   p.res = c->residual.data; p.r_dtype = c->residual.dtype; p.r_pitch = c->residual.c_pitch; p.r_coff = c->residual.c_off;
+  p.res_chunks = cfg.res_chunks;
+  p.r_tx_bytes = TILE_H * TILE_W * cfg.mt * cfg.ck * 2;
+  if (cfg.res_chunks > 0) p.res = nullptr;   // accumulated by the MMAs, nothing left for the epilogue
   p.bias = c->bias; p.act = c->act; p.shuffle_r = r;
+  p.debug = 0;
+  p.prof = nullptr;
+  static long long* prof_buf = nullptr;
+  const bool do_prof = getenv("DBSR_TC_PROFILE") != nullptr;
+  if (do_prof) {
+    if (!prof_buf) cudaMalloc(&prof_buf, 16 * sizeof(long long));
+    cudaMemsetAsync(prof_buf, 0, 16 * sizeof(long long), (cudaStream_t)stream);
+    p.prof = prof_buf;
+  }
+  if (const char* e = getenv("DBSR_TC_DEBUG")) p.debug = atoi(e);
   cudaStream_t st = (cudaStream_t)stream;
-  if (cfg.ck == 64) return launch_tc<64>(mx, mw, p, cfg.smem_bytes, st);
-  return launch_tc<32>(mx, mw, p, cfg.smem_bytes, st);
+  const int rc = (cfg.ck == 64) ? launch_tc<64>(mx, mw, mr, mi, p, cfg.smem_bytes, st) : launch_tc<32>(mx, mw, mr, mi, p, cfg.smem_bytes, st);
+  if (do_prof && rc == 0) {   // debug only: synchronous read-back of CTA 0's cycle counters
+    long long h[16];
+    cudaStreamSynchronize(st);
+    cudaMemcpy(h, prof_buf, sizeof(h), cudaMemcpyDeviceToHost);
+    const double it = h[11] > 0 ? (double)h[11] : 1.0;
+    fprintf(stderr, "conv_tc prof (CTA0, cycles/item over %lld items; a_slots=%d b_stages=%d resident=%d mt=%d nt=%d chunks=%d): "
+            "mma[wait_tempty=%.0f wait_afull=%.0f wait_bfull=%.0f total=%.0f] epi[wait_tfull=%.0f total=%.0f] "
+            "prodA[wait_aempty=%.0f decode=%.0f total=%.0f] epi_detail[pre_wait=%.0f res_stage=%.0f chunks=%.0f store=%.0f]\n", h[11], cfg.a_slots, cfg.b_stages, cfg.b_resident, cfg.mt, cfg.n_tile,
+            cfg.nchunks, h[0] / it, h[1] / it, h[2] / it, h[4] / it, h[5] / it, h[7] / it, h[8] / it, h[10] / it, h[9] / it, h[15] / it, h[12] / it, h[13] / it, h[14] / it);
+  }
+  return rc;
 }
