@@ -76,7 +76,7 @@ def load_library(path: str | None = None) -> ctypes.CDLL:
     with _lock:
         if _lib is not None and path is None:
             return _lib
-        p = path or LIB_PATH
+        p = path or os.environ.get('DBSR_B200_LIB') or LIB_PATH   # DBSR_B200_LIB: A/B an alternative build of the same ABI
         if not os.path.exists(p):
             raise DbsrB200Error(
                 f'{p} not found: build it with `python -m deep_rawburst_sr_b200.build` (nvcc, sm_100a). '

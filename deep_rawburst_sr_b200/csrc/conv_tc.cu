@@ -67,15 +67,17 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// bounded wait: a protocol bug traps (with a message) instead of hanging the GPU
+// bounded wait: a protocol bug traps (with a message) instead of hanging the GPU.  The diagnostic path is kept out
+// of line so that the (single-thread, latency-critical) callers stay a handful of instructions.
+__device__ __noinline__ void mbar_timeout(int tag, uint32_t parity) {
+  printf("conv_tc: mbarrier timeout tag=%d block=%d thread=%d parity=%u\n", tag, (int)blockIdx.x, (int)threadIdx.x, parity);
+  __trap();
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int tag) {
+  if (mbar_try_wait(bar, parity)) return;
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > (1u << 26)) {
-      printf("conv_tc: mbarrier timeout tag=%d block=%d thread=%d parity=%u\n", tag, (int)blockIdx.x, (int)threadIdx.x,
-             parity);
-      __trap();
-    }
+    if (++spins > (1u << 26)) mbar_timeout(tag, parity);
   }
 }
 
@@ -187,8 +189,10 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t sbo_
 // kernel
 // ---------------------------------------------------------------------------------------------------------
 constexpr int TILE_H = 16, TILE_W = 8;
-constexpr int TC_THREADS = 384;   // warpgroup 0 = warps 0-2 (A producer / MMA issuer / B producer) + 1 idle warp;
-                                  // warpgroups 1-2 = warps 4-11: epilogue.
+constexpr int TC_THREADS = 384;   // warps 0-7: epilogue; warp 8 idle; warp 9: A producer; warp 10: B producer; warp 11: TMEM
+                                  // allocator + tcgen05.mma issuer (highest warp id: the SM arbiter favours higher ids and
+                                  // the issuer must not be starved by warps that are waiting on mbarriers)
+constexpr int WARP_A = 9, WARP_B = 10, WARP_MMA = 11;
 
 struct ConvTcParams {
   int n, H, W;          // input == output spatial size (stride 1, "same" padding)
@@ -208,8 +212,6 @@ struct ConvTcParams {
   int halo_w;           // pixels per row of the A box
   int res_chunks;       // > 0: the residual is accumulated on the tensor core as res_chunks extra K chunks (identity weights)
   int r_tx_bytes;       // bytes of one residual box {CK, 8*mt px, 16 rows}
-  long long* prof;      // debug: per-role cycle counters of CTA 0 (nullptr = off)
-  int debug;            // bit 0: skip epilogue math/stores, bit 1: skip MMAs, bit 2: skip A loads, bit 3: skip B loads
   int flat;             // small-map mode: the A box holds flat_ni whole zero-bordered images, M rows = flat slots
   int flat_s, flat_ni;  // slots per image (H+2)*(W+2); images per item
   // output
@@ -361,11 +363,10 @@ __device__ __forceinline__ void finish_chunk(const ConvTcParams& p, const uint32
 
 template <int GW>   // group width in channels: 64, 32 or 16  (GW * 2 bytes per pixel row)
 __device__ __forceinline__ void epilogue_group_bf16(const ConvTcParams& p, uint32_t tbase, int g0, int co0, const TileGeo& tg,
-                                                    int quarter, int lane, uint8_t* stg, bool res_inflight, bool profme) {
+                                                    int quarter, int lane, uint8_t* stg, bool res_inflight) {
   constexpr int LPP = GW / 8;        // lanes (16-byte chunks) per pixel
   constexpr int PPI = 32 / LPP;      // pixels per warp instruction
   const int sub = lane / LPP, chunk = lane % LPP;
-  long long tq0 = profme ? clock64() : 0;
   // both accumulator chunks of the group in flight before anything waits on them
   uint32_t r0[32], r1[32];
   if (GW >= 32) tmem_ld32_nowait(tbase + (uint32_t)g0, r0); else tmem_ld16_nowait(tbase + (uint32_t)g0, r0);
@@ -387,7 +388,6 @@ __device__ __forceinline__ void epilogue_group_bf16(const ConvTcParams& p, uint3
     cp_async_wait_all();
     __syncwarp();
   }
-  if (profme) { const long long t = clock64(); p.prof[12] += t - tq0; tq0 = t; }
   // ---- accumulator -> bias / residual / activation -> bf16 -> own staging row
   uint8_t* myrow = stg + lane * STG_ROW;
   const float* bias = p.bias ? p.bias + co0 + g0 : nullptr;
@@ -395,7 +395,6 @@ __device__ __forceinline__ void epilogue_group_bf16(const ConvTcParams& p, uint3
   if (GW >= 32) finish_chunk<32>(p, r0, bias, myrow, has_res); else finish_chunk<16>(p, r0, bias, myrow, has_res);
   if (GW == 64) finish_chunk<32>(p, r1, bias ? bias + 32 : nullptr, myrow + 64, has_res);
   __syncwarp();
-  if (profme) { const long long t = clock64(); p.prof[13] += t - tq0; tq0 = t; }
   // ---- staging rows -> coalesced global stores
 #pragma unroll
   for (int it = 0; it < LPP; ++it) {
@@ -407,11 +406,7 @@ __device__ __forceinline__ void epilogue_group_bf16(const ConvTcParams& p, uint3
     }
   }
   __syncwarp();
-  if (profme) { const long long t = clock64(); p.prof[14] += t - tq0; }
 }
-
-#define PROF_T(var) const long long var = p.prof ? clock64() : 0
-#define PROF_ADD(idx, t0) do { if (p.prof && blockIdx.x == 0) p.prof[idx] += clock64() - (t0); } while (0)
 
 struct ItemCoord { int nt, img, y0, x0; };
 __device__ __forceinline__ ItemCoord decode_item(const ConvTcParams& p, long long item64) {
@@ -433,7 +428,7 @@ __device__ __forceinline__ ItemCoord decode_item(const ConvTcParams& p, long lon
   return c;
 }
 
-template <int CK>
+template <int CK, bool RESIDENT>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
                const __grid_constant__ CUtensorMap tmap_r, const __grid_constant__ CUtensorMap tmap_i, const ConvTcParams p) {
@@ -470,30 +465,22 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
     tma_prefetch_desc(&tmap_w);
     if (p.res_chunks) { tma_prefetch_desc(&tmap_r); tma_prefetch_desc(&tmap_i); }
   }
-  if (warp == 1) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+  if (warp == WARP_MMA) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 0) {
-    // ===================== A producer: one halo box per (item, K chunk) =====================
+  if (warp == WARP_A) {
+    // ===================== A producer: one halo box per (item, K chunk), then the residual boxes =====================
     if (elect_one()) {
       int slot = 0; uint32_t phase = 0;
-      PROF_T(tp0);
       for (long long item = blockIdx.x; item < p.total_items; item += gridDim.x) {
-        PROF_T(td);
         const ItemCoord c = decode_item(p, item);
-        PROF_ADD(10, td);
         for (int ch = 0; ch < p.nchunks; ++ch) {
-          PROF_T(tw);
           mbar_wait(&a_empty[slot], phase ^ 1, 100 + slot);
-          PROF_ADD(8, tw);
-          if (p.debug & 4) { mbar_arrive(&a_full[slot]); }
-          else {
           mbar_arrive_expect_tx(&a_full[slot], (uint32_t)p.a_tx_bytes);
-          tma_load_4d(&tmap_x, &a_full[slot], smem_a + (size_t)slot * p.a_bytes, ch * CK, c.x0 - pad, c.y0 - pad, c.img);
-          }   // flat: (-1, -1, first image)
+          tma_load_4d(&tmap_x, &a_full[slot], smem_a + (size_t)slot * p.a_bytes, ch * CK, c.x0 - pad, c.y0 - pad, c.img);   // flat: (-1, -1, first image)
           if (++slot == p.a_slots) { slot = 0; phase ^= 1; }
         }
         // residual of this N tile as extra K chunks: plain (no halo) box of the residual tensor
@@ -504,36 +491,29 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
           if (++slot == p.a_slots) { slot = 0; phase ^= 1; }
         }
       }
-      PROF_ADD(9, tp0);
     }
-  } else if (warp == 2) {
+  } else if (warp == WARP_B) {
     // ===================== B producer: weight tiles =====================
     if (elect_one()) {
-      if (p.b_resident) {
-        // every item uses the same tiles (ntiles_n == 1): load each (chunk, tap) tile once and keep it
-        for (int t = 0; t < p.nchunks * taps; ++t) {
+      if (RESIDENT) {
+        // every item uses the same tiles (one N tile): load each (chunk, tap) tile once, they all signal b_full[0]
+        const int n_main = p.nchunks * taps;
+        mbar_arrive_expect_tx(&b_full[0], (uint32_t)((n_main + p.res_chunks) * p.b_bytes));
+        for (int t = 0; t < n_main; ++t) {
           const int ch = t / taps, tap = t - ch * taps;
-          mbar_arrive_expect_tx(&b_full[t], (uint32_t)p.b_bytes);
-          tma_load_2d(&tmap_w, &b_full[t], smem_b + (size_t)t * p.b_bytes, ch * CK, tap * p.cout_pad);
+          tma_load_2d(&tmap_w, &b_full[0], smem_b + (size_t)t * p.b_bytes, ch * CK, tap * p.cout_pad);
         }
-        for (int rc = 0; rc < p.res_chunks; ++rc) {   // identity tiles of the residual chunks
-          const int t = p.nchunks * taps + rc;
-          mbar_arrive_expect_tx(&b_full[t], (uint32_t)p.b_bytes);
-          tma_load_2d(&tmap_i, &b_full[t], smem_b + (size_t)t * p.b_bytes, rc * CK, 0);
-        }
+        for (int rc = 0; rc < p.res_chunks; ++rc)     // identity tiles of the residual chunks
+          tma_load_2d(&tmap_i, &b_full[0], smem_b + (size_t)(n_main + rc) * p.b_bytes, rc * CK, 0);
       } else {
         int stage = 0; uint32_t phase = 0;
         for (long long item = blockIdx.x; item < p.total_items; item += gridDim.x) {
-          const int nt = (int)(item % p.ntiles_n);
+          const int nt = (int)((unsigned)item % (unsigned)p.ntiles_n);
           for (int ch = 0; ch < p.nchunks; ++ch) {
             for (int tap = 0; tap < taps; ++tap) {
               mbar_wait(&b_empty[stage], phase ^ 1, 150 + stage);
-              if (p.debug & 8) { mbar_arrive(&b_full[stage]); }
-              else {
               mbar_arrive_expect_tx(&b_full[stage], (uint32_t)p.b_bytes);
-              tma_load_2d(&tmap_w, &b_full[stage], smem_b + (size_t)stage * p.b_bytes, ch * CK,
-                          tap * p.cout_pad + nt * NT);
-              }
+              tma_load_2d(&tmap_w, &b_full[stage], smem_b + (size_t)stage * p.b_bytes, ch * CK, tap * p.cout_pad + nt * NT);
               if (++stage == p.b_stages) { stage = 0; phase ^= 1; }
             }
           }
@@ -546,22 +526,20 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
         }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == WARP_MMA) {
     // ===================== MMA issuer =====================
+    // One in-order instruction stream: everything that is not an MMA, a barrier wait or a commit is hoisted out of the
+    // per-tap path (descriptor high words, tap offsets, weight-tile addresses are plain adds on the low word).
     if (elect_one()) {
       int aslot = 0; uint32_t aphase = 0;
       int bstage = 0; uint32_t bphase = 0;
       int acc = 0; uint32_t acc_phase = 0;
-      bool first_item = true;
-      // Descriptors are built incrementally: the high word (SBO | version | layout) is constant per operand, the low
-      // word is (addr >> 4) | LBO; moving inside the box / along K only adds to the low word.  The issuing thread is a
-      // single in-order instruction stream, so everything that can be hoisted out of the per-MMA path is.
       // flat mode: M rows are consecutive slots of the box (dense 8-slot atoms); tap shift is ky*halo_w + kx slots
       const uint32_t a_sbo = (p.flat ? 8u : (uint32_t)p.halo_w) * ROW_BYTES;
       const uint32_t b_sbo = 8u * ROW_BYTES;
+      const uint32_t r_sbo = (uint32_t)(TILE_W * p.mt) * ROW_BYTES;          // residual box: 8*mt pixels per row, no halo
       const uint32_t a_hi = ((a_sbo >> 4) & 0x3FFFu) | (1u << 14) | (LAYOUT << 29);
       const uint32_t b_hi = ((b_sbo >> 4) & 0x3FFFu) | (1u << 14) | (LAYOUT << 29);
-      const uint32_t r_sbo = (uint32_t)(TILE_W * p.mt) * ROW_BYTES;          // residual box: 8*mt pixels per row, no halo
       const uint32_t r_hi = ((r_sbo >> 4) & 0x3FFFu) | (1u << 14) | (LAYOUT << 29);
       uint32_t tap_off[9];                      // 16-byte units inside the A box
 #pragma unroll
@@ -571,146 +549,107 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
       }
       const uint32_t tile_step = (uint32_t)TILE_W * (ROW_BYTES >> 4);   // second 16x8 tile of the item
       const bool two_tiles = p.mt == 2;
-      PROF_T(tm0);
+      const uint32_t b_step = (uint32_t)p.b_bytes >> 4;
+      const uint32_t a_step = (uint32_t)p.a_bytes >> 4;
+      const uint32_t a_base = ((smem_u32(smem_a) >> 4) & 0x3FFFu) | 0x10000u;
+      const uint32_t b_base = ((smem_u32(smem_b) >> 4) & 0x3FFFu) | 0x10000u;
+      if (RESIDENT) { mbar_wait(&b_full[0], 0, 350); tc_fence_after(); }   // all weight tiles landed, once per CTA
+
+      auto mma_pair = [&](uint32_t a_lo, uint32_t a_hi_w, uint32_t b_lo, uint32_t d0, uint32_t first_acc) {
+#pragma unroll
+        for (int k16 = 0; k16 < CK / 16; ++k16)
+          umma_bf16(d0, ((uint64_t)a_hi_w << 32) | (uint64_t)(a_lo + 2u * k16), ((uint64_t)b_hi << 32) | (uint64_t)(b_lo + 2u * k16),
+                    idesc, k16 == 0 ? first_acc : 1u);
+        if (two_tiles) {
+#pragma unroll
+          for (int k16 = 0; k16 < CK / 16; ++k16)
+            umma_bf16(d0 + (uint32_t)NT, ((uint64_t)a_hi_w << 32) | (uint64_t)(a_lo + tile_step + 2u * k16),
+                      ((uint64_t)b_hi << 32) | (uint64_t)(b_lo + 2u * k16), idesc, k16 == 0 ? first_acc : 1u);
+        }
+      };
+
       for (long long item = blockIdx.x; item < p.total_items; item += gridDim.x) {
-        PROF_T(t1);
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1, 200 + acc);
-        PROF_ADD(0, t1);
-        if (p.prof && blockIdx.x == 0) p.prof[11] += 1;
         tc_fence_after();
         const uint32_t d0 = tmem_base + (uint32_t)(acc * p.mt * NT);
-        const uint32_t d1 = d0 + (uint32_t)NT;
+        uint32_t b_lo_res = b_base;               // resident: running tile address
         for (int ch = 0; ch < p.nchunks; ++ch) {
-          PROF_T(t2);
           mbar_wait(&a_full[aslot], aphase, 300 + aslot);
-          PROF_ADD(1, t2);
           tc_fence_after();
-          const uint32_t a_lo0 = ((smem_u32(smem_a + (size_t)aslot * p.a_bytes) >> 4) & 0x3FFFu) | 0x10000u;
-          auto issue_tap = [&](int tap, uint32_t first_acc) {
+          const uint32_t a_lo0 = a_base + (uint32_t)aslot * a_step;
+          if (taps == 9) {
+#pragma unroll
+            for (int tap = 0; tap < 9; ++tap) {
+              uint32_t b_lo;
+              if (RESIDENT) { b_lo = b_lo_res; b_lo_res += b_step; }
+              else {
+                mbar_wait(&b_full[bstage], bphase, 350 + bstage);
+                tc_fence_after();
+                b_lo = b_base + (uint32_t)bstage * b_step;
+              }
+              mma_pair(a_lo0 + tap_off[tap], a_hi, b_lo, d0, (tap == 0 && ch == 0) ? 0u : 1u);
+              if (!RESIDENT) {
+                umma_commit(&b_empty[bstage]);   // weight stage free once these MMAs retire
+                if (++bstage == p.b_stages) { bstage = 0; bphase ^= 1; }
+              }
+            }
+          } else {
             uint32_t b_lo;
-            if (p.b_resident) {
-              const int t = ch * taps + tap;
-              if (first_item) { mbar_wait(&b_full[t], 0, 350 + (t & 31)); tc_fence_after(); }
-              b_lo = ((smem_u32(smem_b + (size_t)t * p.b_bytes) >> 4) & 0x3FFFu) | 0x10000u;
-            } else {
-              PROF_T(t3);
+            if (RESIDENT) { b_lo = b_lo_res; b_lo_res += b_step; }
+            else {
               mbar_wait(&b_full[bstage], bphase, 350 + bstage);
-              PROF_ADD(2, t3);
               tc_fence_after();
-              b_lo = ((smem_u32(smem_b + (size_t)bstage * p.b_bytes) >> 4) & 0x3FFFu) | 0x10000u;
+              b_lo = b_base + (uint32_t)bstage * b_step;
             }
-            const uint32_t a_lo = a_lo0 + tap_off[tap];
-            if (!(p.debug & 2)) {
-#pragma unroll
-              for (int k16 = 0; k16 < CK / 16; ++k16) {
-                const uint64_t adesc = ((uint64_t)a_hi << 32) | (uint64_t)(a_lo + 2u * k16);
-                const uint64_t bdesc = ((uint64_t)b_hi << 32) | (uint64_t)(b_lo + 2u * k16);
-                umma_bf16(d0, adesc, bdesc, idesc, k16 == 0 ? first_acc : 1u);
-              }
-              if (two_tiles) {
-#pragma unroll
-                for (int k16 = 0; k16 < CK / 16; ++k16) {
-                  const uint64_t adesc = ((uint64_t)a_hi << 32) | (uint64_t)(a_lo + tile_step + 2u * k16);
-                  const uint64_t bdesc = ((uint64_t)b_hi << 32) | (uint64_t)(b_lo + 2u * k16);
-                  umma_bf16(d1, adesc, bdesc, idesc, k16 == 0 ? first_acc : 1u);
-                }
-              }
-            }
-            if (!p.b_resident) {
-              umma_commit(&b_empty[bstage]);   // weight stage free once these MMAs retire
+            mma_pair(a_lo0, a_hi, b_lo, d0, ch == 0 ? 0u : 1u);
+            if (!RESIDENT) {
+              umma_commit(&b_empty[bstage]);
               if (++bstage == p.b_stages) { bstage = 0; bphase ^= 1; }
             }
-          };
-          if (taps == 9) {
-            issue_tap(0, ch != 0 ? 1u : 0u);
-#pragma unroll
-            for (int tap = 1; tap < 9; ++tap) issue_tap(tap, 1u);
-          } else {
-            issue_tap(0, ch != 0 ? 1u : 0u);
           }
-          umma_commit(&a_empty[aslot]);        // halo box free once every tap of this chunk retired
+          umma_commit(&a_empty[aslot]);          // halo box free once every tap of this chunk retired
           if (++aslot == p.a_slots) { aslot = 0; aphase ^= 1; }
         }
         // residual: D += R * I  (exact: identity weights, fp32 accumulation) -- the epilogue never touches it
         for (int rc = 0; rc < p.res_chunks; ++rc) {
           mbar_wait(&a_full[aslot], aphase, 320 + aslot);
           tc_fence_after();
-          const uint32_t a_lo = ((smem_u32(smem_a + (size_t)aslot * p.a_bytes) >> 4) & 0x3FFFu) | 0x10000u;
           uint32_t b_lo;
-          if (p.b_resident) {
-            const int t = p.nchunks * taps + rc;
-            if (first_item) { mbar_wait(&b_full[t], 0, 360 + (t & 31)); tc_fence_after(); }
-            b_lo = ((smem_u32(smem_b + (size_t)t * p.b_bytes) >> 4) & 0x3FFFu) | 0x10000u;
-          } else {
+          if (RESIDENT) { b_lo = b_lo_res; b_lo_res += b_step; }
+          else {
             mbar_wait(&b_full[bstage], bphase, 370 + bstage);
             tc_fence_after();
-            b_lo = ((smem_u32(smem_b + (size_t)bstage * p.b_bytes) >> 4) & 0x3FFFu) | 0x10000u;
+            b_lo = b_base + (uint32_t)bstage * b_step;
           }
-          if (!(p.debug & 2)) {
-#pragma unroll
-            for (int k16 = 0; k16 < CK / 16; ++k16)
-              umma_bf16(d0, ((uint64_t)r_hi << 32) | (uint64_t)(a_lo + 2u * k16), ((uint64_t)b_hi << 32) | (uint64_t)(b_lo + 2u * k16),
-                        idesc, 1u);
-            if (two_tiles) {
-#pragma unroll
-              for (int k16 = 0; k16 < CK / 16; ++k16)
-                umma_bf16(d1, ((uint64_t)r_hi << 32) | (uint64_t)(a_lo + tile_step + 2u * k16),
-                          ((uint64_t)b_hi << 32) | (uint64_t)(b_lo + 2u * k16), idesc, 1u);
-            }
-          }
-          if (!p.b_resident) {
+          mma_pair(a_base + (uint32_t)aslot * a_step, r_hi, b_lo, d0, 1u);
+          if (!RESIDENT) {
             umma_commit(&b_empty[bstage]);
             if (++bstage == p.b_stages) { bstage = 0; bphase ^= 1; }
           }
           umma_commit(&a_empty[aslot]);
           if (++aslot == p.a_slots) { aslot = 0; aphase ^= 1; }
         }
-        umma_commit(&tfull_bar[acc]);          // accumulators ready for the epilogue
+        umma_commit(&tfull_bar[acc]);            // accumulators ready for the epilogue
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
-        first_item = false;
       }
-      PROF_ADD(4, tm0);
     }
-  } else if (warp >= 4) {
-    // ===================== epilogue (warps 4..11) =====================
+  } else if (warp < 8) {
+    // ===================== epilogue (warps 0..7) =====================
     // two warps per TMEM lane quarter: with mt == 2 group g owns tile g of every item, with mt == 1 the groups take
-    // alternate 32-column chunks.  Residual rows are prefetched before waiting for the accumulator.
+    // alternate channel groups.
     const int quarter = warp & 3;                  // TMEM lane quarter this warp may access
-    const int group = (warp - 4) >> 2;             // 0 or 1
+    const int group = warp >> 2;                   // 0 or 1
     const int m = quarter * 32 + lane;             // pixel within a 16x8 tile
     const int ty = m >> 3, tx = m & 7;
+    uint8_t* stg = smem_stg + (size_t)warp * STG_WARP_BYTES;
     int acc = 0; uint32_t acc_phase = 0;
-    const bool profme = p.prof && blockIdx.x == 0 && warp == 4 && lane == 0;
-    const long long te0 = profme ? clock64() : 0;
-    long long t_wait = 0;
     for (long long item = blockIdx.x; item < p.total_items; item += gridDim.x) {
-      const long long ti0 = profme ? clock64() : 0;
       const ItemCoord c = decode_item(p, item);
       const int co0 = c.nt * NT;
       const int t = (p.mt == 2) ? group : 0;
-      int y = c.y0 + ty, x = c.x0 + t * TILE_W + tx;
-      long long img = c.img;
-      bool valid = (y < p.H) && (x < p.W);
-      if (p.flat) {   // M row m = flat slot: image j = m / S, padded row / column inside it
-        const int j = m / p.flat_s, rem = m - j * p.flat_s;
-        y = rem / p.halo_w; x = rem - y * p.halo_w;
-        img = c.img + j;
-        valid = (j < p.flat_ni) && (y < p.H) && (x < p.W) && (img < p.n);   // rows past the box belong to nobody
-      }
-      long long off;   // element offset of this thread's first output channel of the N tile
-      if (p.shuffle_r > 1) {
-        // packed channel co' = i*256 + j*32 + c ; N tile = 128 -> i = nt / 2, j0 = (nt & 1) * 4
-        const int per_i = p.shuffle_r * 32;
-        const int si = co0 / per_i, j0 = (co0 - si * per_i) / 32;
-        off = ((img * p.yH + (y * p.shuffle_r + si)) * p.yW + (x * p.shuffle_r + j0)) * p.y_pitch + p.y_coff;
-      } else {
-        off = ((img * p.yH + y) * p.yW + x) * p.y_pitch + p.y_coff + co0;
-      }
-      const long long roff = ((img * p.yH + y) * p.yW + x) * p.r_pitch + p.r_coff + co0;
       const uint32_t tbase = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)((acc * p.mt + t) * NT);
       if (p.vec_ok && p.y_dtype == DBSR_BF16) {
         // ---------- coalesced path: 64/32/16-channel groups through the per-warp staging rows ----------
-        uint8_t* stg = smem_stg + (size_t)(warp - 4) * STG_WARP_BYTES;
         const int tx0 = c.x0 + t * TILE_W;
         TileGeo tg;
         if (p.shuffle_r > 1) {
@@ -727,43 +666,32 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
         tg.r = reinterpret_cast<const __nv_bfloat16*>(p.res) + (((long long)c.img * p.yH + c.y0) * p.yW + tx0) * p.r_pitch + p.r_coff + co0;
         tg.r_row = p.yW * p.r_pitch; tg.r_col = p.r_pitch;
         tg.rows_in = min(TILE_H, p.H - c.y0); tg.cols_in = min(TILE_W, p.W - tx0);
-        // group ownership: mt == 2 -> every group of my tile; mt == 1 -> groups with (index & 1) == group id
-        const int first_gw = NT >= 64 ? 64 : (NT >= 32 ? 32 : 16);
-        const bool mine0 = (p.mt == 2) || group == 0;
-        const bool pre = p.res != nullptr && mine0;
-        if (pre) {   // residual of the first group: asynchronous copy into the staging rows, overlapping the MMA wait
-          const int lpp = first_gw / 8, ppi = 32 / lpp;
-          const int sub = lane / lpp, chunk = lane - sub * lpp;
-#pragma unroll
-          for (int it = 0; it < 8; ++it) {
-            if (it < lpp) {
-              const int ml = it * ppi + sub;
-              const int row = quarter * 4 + (ml >> 3), col = ml & 7;
-              const bool ok = row < tg.rows_in && col < tg.cols_in;
-              cp_async16(stg + ml * STG_ROW + chunk * 16, ok ? (const void*)(tg.r + row * tg.r_row + col * tg.r_col + chunk * 8) : (const void*)tg.r,
-                         ok ? 16u : 0u);
-            }
-          }
-        }
-        const long long tw0 = profme ? clock64() : 0;
-        if (profme) p.prof[15] += tw0 - ti0;
         mbar_wait(&tfull_bar[acc], acc_phase, 400 + acc);
-        if (profme) t_wait += clock64() - tw0;
         tc_fence_after();
         int g0 = 0, gi = 0;
         while (g0 < NT) {
           const int rem = NT - g0;
           const int gw = rem >= 64 ? 64 : (rem >= 32 ? 32 : 16);
-          if ((p.mt == 2 || (gi & 1) == group) && !(p.debug & 1)) {
-            const bool rp = pre && g0 == 0;
-            if (gw == 64) epilogue_group_bf16<64>(p, tbase, g0, co0, tg, quarter, lane, stg, rp, profme);
-            else if (gw == 32) epilogue_group_bf16<32>(p, tbase, g0, co0, tg, quarter, lane, stg, rp, profme);
-            else epilogue_group_bf16<16>(p, tbase, g0, co0, tg, quarter, lane, stg, rp, profme);
+          if (p.mt == 2 || (gi & 1) == group) {
+            if (gw == 64) epilogue_group_bf16<64>(p, tbase, g0, co0, tg, quarter, lane, stg, false);
+            else if (gw == 32) epilogue_group_bf16<32>(p, tbase, g0, co0, tg, quarter, lane, stg, false);
+            else epilogue_group_bf16<16>(p, tbase, g0, co0, tg, quarter, lane, stg, false);
           }
           g0 += gw; ++gi;
         }
       } else {
-        // ---------- generic path (fp32 outputs, odd channel counts): one thread stores its own pixel ----------
+        // ---------- generic path (fp32 outputs, odd channel counts, flat mode): one thread stores its own pixel ----------
+        int y = c.y0 + ty, x = c.x0 + t * TILE_W + tx;
+        long long img = c.img;
+        bool valid = (y < p.H) && (x < p.W);
+        if (p.flat) {   // M row m = flat slot: image j = m / S, padded row / column inside it
+          const int j = m / p.flat_s, rem = m - j * p.flat_s;
+          y = rem / p.halo_w; x = rem - y * p.halo_w;
+          img = c.img + j;
+          valid = (j < p.flat_ni) && (y < p.H) && (x < p.W) && (img < p.n);   // rows past the box belong to nobody
+        }
+        const long long off = ((img * p.yH + y) * p.yW + x) * p.y_pitch + p.y_coff + co0;
+        const long long roff = ((img * p.yH + y) * p.yW + x) * p.r_pitch + p.r_coff + co0;
         mbar_wait(&tfull_bar[acc], acc_phase, 400 + acc);
         tc_fence_after();
 #pragma unroll
@@ -787,12 +715,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
       if (lane == 0) mbar_arrive(&tempty_bar[acc]);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
-    if (profme) { p.prof[5] += t_wait; p.prof[7] += clock64() - te0; }
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) {
+  if (warp == WARP_MMA) {
     tc_fence_after();
     tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
   }
@@ -974,12 +901,12 @@ static int tc_plan(const dbsr_conv_t* c, TcConfig* cfg, bool set_err) {
 #undef TC_REQ
 }
 
-template <int CK>
+template <int CK, bool RESIDENT>
 static int launch_tc(const CUtensorMap& mx, const CUtensorMap& mw, const CUtensorMap& mr, const CUtensorMap& mi,
                      const ConvTcParams& p, int smem, cudaStream_t st) {
   static int configured_smem = 0;
   if (smem > configured_smem) {
-    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<CK>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<CK, RESIDENT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) {
       set_error("conv2d_tc: cudaFuncSetAttribute(%d) failed: %s", smem, cudaGetErrorString(e));
       return 2;
@@ -994,7 +921,7 @@ static int launch_tc(const CUtensorMap& mx, const CUtensorMap& mw, const CUtenso
   }
   int grid = (int)(p.total_items < num_sms ? p.total_items : num_sms);
   if (const char* e = getenv("DBSR_TC_GRID")) { const int g = atoi(e); if (g > 0 && g < grid) grid = g; }   // debug knob
-  conv_tc_kernel<CK><<<grid, TC_THREADS, smem, st>>>(mx, mw, mr, mi, p);
+  conv_tc_kernel<CK, RESIDENT><<<grid, TC_THREADS, smem, st>>>(mx, mw, mr, mi, p);
   return check_launch("conv2d_tc");
 }
 
@@ -1100,27 +1027,9 @@ extern "C" int dbsr_conv2d_tc(const dbsr_conv_t* c, void* stream) {
   p.r_tx_bytes = TILE_H * TILE_W * cfg.mt * cfg.ck * 2;
   if (cfg.res_chunks > 0) p.res = nullptr;   // accumulated by the MMAs, nothing left for the epilogue
   p.bias = c->bias; p.act = c->act; p.shuffle_r = r;
-  p.debug = 0;
-  p.prof = nullptr;
-  static long long* prof_buf = nullptr;
-  const bool do_prof = getenv("DBSR_TC_PROFILE") != nullptr;
-  if (do_prof) {
-    if (!prof_buf) cudaMalloc(&prof_buf, 16 * sizeof(long long));
-    cudaMemsetAsync(prof_buf, 0, 16 * sizeof(long long), (cudaStream_t)stream);
-    p.prof = prof_buf;
-  }
-  if (const char* e = getenv("DBSR_TC_DEBUG")) p.debug = atoi(e);
   cudaStream_t st = (cudaStream_t)stream;
-  const int rc = (cfg.ck == 64) ? launch_tc<64>(mx, mw, mr, mi, p, cfg.smem_bytes, st) : launch_tc<32>(mx, mw, mr, mi, p, cfg.smem_bytes, st);
-  if (do_prof && rc == 0) {   // debug only: synchronous read-back of CTA 0's cycle counters
-    long long h[16];
-    cudaStreamSynchronize(st);
-    cudaMemcpy(h, prof_buf, sizeof(h), cudaMemcpyDeviceToHost);
-    const double it = h[11] > 0 ? (double)h[11] : 1.0;
-    fprintf(stderr, "conv_tc prof (CTA0, cycles/item over %lld items; a_slots=%d b_stages=%d resident=%d mt=%d nt=%d chunks=%d): "
-            "mma[wait_tempty=%.0f wait_afull=%.0f wait_bfull=%.0f total=%.0f] epi[wait_tfull=%.0f total=%.0f] "
-            "prodA[wait_aempty=%.0f decode=%.0f total=%.0f] epi_detail[pre_wait=%.0f res_stage=%.0f chunks=%.0f store=%.0f]\n", h[11], cfg.a_slots, cfg.b_stages, cfg.b_resident, cfg.mt, cfg.n_tile,
-            cfg.nchunks, h[0] / it, h[1] / it, h[2] / it, h[4] / it, h[5] / it, h[7] / it, h[8] / it, h[10] / it, h[9] / it, h[15] / it, h[12] / it, h[13] / it, h[14] / it);
-  }
-  return rc;
+  if (cfg.ck == 64) return cfg.b_resident ? launch_tc<64, true>(mx, mw, mr, mi, p, cfg.smem_bytes, st)
+                                          : launch_tc<64, false>(mx, mw, mr, mi, p, cfg.smem_bytes, st);
+  return cfg.b_resident ? launch_tc<32, true>(mx, mw, mr, mi, p, cfg.smem_bytes, st)
+                        : launch_tc<32, false>(mx, mw, mr, mi, p, cfg.smem_bytes, st);
 }
