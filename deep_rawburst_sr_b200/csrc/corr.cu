@@ -52,10 +52,15 @@ __global__ void __launch_bounds__(CORR_THREADS) corr81_kernel(const CorrParams p
   for (int i = 0; i < 4; ++i)
 #pragma unroll
     for (int d = 0; d < 9; ++d) acc[i][d] = 0.0f;
+  // rows / columns of this tile that are inside the map: small pyramid levels (1x1 ... 8x8) use a fraction of the 8x16
+  // tile, and all staging / accumulation work is bounded by it
+  const int th = min(CT_H, H - ty0), tw = min(CT_W, W - tx0);
+  const int hh = th + 8, hw = tw + 8;                  // halo extent actually needed
+  const bool active = row < th && strip * 4 < tw;      // this thread owns at least one real output pixel
 
   for (int c0 = 0; c0 < C; c0 += C_CH) {
     // ---- stage f1 tile
-    for (int e = t; e < CT_H * CT_W * C_CH; e += CORR_THREADS) {
+    for (int e = t; e < th * CT_W * C_CH; e += CORR_THREADS) {      // rows >= th are never read
       const int ch = e & (C_CH - 1), pix = e >> 5;
       const int y = ty0 + pix / CT_W, x = tx0 + pix % CT_W;
       float v = 0.0f;
@@ -63,9 +68,11 @@ __global__ void __launch_bounds__(CORR_THREADS) corr81_kernel(const CorrParams p
       f1_s[e] = v;
     }
     // ---- stage f2 halo tile (optionally backwarped)
-    for (int e = t; e < HALO_H * HALO_W * C_CH; e += CORR_THREADS) {
+    for (int e = t; e < hh * HALO_W * C_CH; e += CORR_THREADS) {       // halo rows >= th + 8 are never read
       const int ch = e & (C_CH - 1), pix = e >> 5;
-      const int y = ty0 - 4 + pix / HALO_W, x = tx0 - 4 + pix % HALO_W;
+      const int hx = pix % HALO_W;
+      const int y = ty0 - 4 + pix / HALO_W, x = tx0 - 4 + hx;
+      if (hx >= ((hw + 3) & ~3) + 4) { f2_s[e] = 0.0f; continue; }         // columns past the strips that exist
       float v = 0.0f;
       if (y >= 0 && y < H && x >= 0 && x < W && c0 + ch < C) {
         if (!warp2) {
@@ -95,6 +102,7 @@ __global__ void __launch_bounds__(CORR_THREADS) corr81_kernel(const CorrParams p
     __syncthreads();
 
     // ---- accumulate
+    if (active)
 #pragma unroll 2
     for (int j = 0; j < 8; ++j) {
       const int jj = ((j + lane) & 7) * 4;
@@ -129,7 +137,7 @@ __global__ void __launch_bounds__(CORR_THREADS) corr81_kernel(const CorrParams p
     for (int d = 0; d < 9; ++d)
       out_s[(row * CT_W + strip * 4 + i) * 81 + dy * 9 + d] = apply_act(acc[i][d] / (float)C, p.act);
   __syncthreads();
-  for (int e = t; e < CT_H * CT_W * 81; e += CORR_THREADS) {
+  for (int e = t; e < th * CT_W * 81; e += CORR_THREADS) {
     const int pix = e / 81, ch = e - pix * 81;
     const int y = ty0 + pix / CT_W, x = tx0 + pix % CT_W;
     if (y < H && x < W) view_st(p.out, (long long)pair * H * W + (long long)y * W + x, ch, out_s[e]);

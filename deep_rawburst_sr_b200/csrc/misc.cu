@@ -260,9 +260,11 @@ __global__ void build_wp_input_kernel(View proj, View wp_in, int frames) {
   }
 }
 
-// decoders.py:52,60: 1x1 conv to `cout` (<= 4) channels + ReLU, NCHW fp32 output
-__global__ void predictor_kernel(View x, const float* __restrict__ w, const float* __restrict__ bias, int cout,
-                                 float* __restrict__ pred) {
+// decoders.py:52,60: 1x1 conv to `cout` (<= 4) channels + ReLU, NCHW fp32 output.  One thread per pixel: the pixel's
+// channels are read with 16-byte loads (they are contiguous in NHWC), the `cout` planes are written coalesced.
+template <typename T, bool VEC>
+__global__ void __launch_bounds__(256) predictor_kernel(View x, const float* __restrict__ w, const float* __restrict__ bias,
+                                                        int cout, float* __restrict__ pred) {
   extern __shared__ float ws[];  // [cout][C] + [cout]
   const int C = x.c;
   for (int i = threadIdx.x; i < cout * C; i += blockDim.x) ws[i] = w[i];
@@ -270,14 +272,37 @@ __global__ void predictor_kernel(View x, const float* __restrict__ w, const floa
   __syncthreads();
   const int HW = x.h * x.w;
   const long long total = (long long)x.n * HW;
+  const T* xb = reinterpret_cast<const T*>(x.data) + x.c_off;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
     float acc[4] = {0.f, 0.f, 0.f, 0.f};
-    for (int c = 0; c < C; ++c) {
-      const float v = view_ld(x, i, c);
+    const T* px = xb + i * x.c_pitch;
+    if (VEC) {
+      for (int c = 0; c < C; c += 8) {
+        float v[8];
+        if (sizeof(T) == 2) {
+          const uint4 q = __ldg(reinterpret_cast<const uint4*>(px + c));
+          const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&q);
 #pragma unroll
-      for (int o = 0; o < 4; ++o)
-        if (o < cout) acc[o] = fmaf(v, ws[o * C + c], acc[o]);
+          for (int k = 0; k < 4; ++k) { const float2 f = __bfloat1622float2(h[k]); v[2 * k] = f.x; v[2 * k + 1] = f.y; }
+        } else {
+          const float4 a = __ldg(reinterpret_cast<const float4*>(px + c));
+          const float4 b4 = __ldg(reinterpret_cast<const float4*>(px + c) + 1);
+          v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b4.x; v[5] = b4.y; v[6] = b4.z; v[7] = b4.w;
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+#pragma unroll
+          for (int o = 0; o < 4; ++o)
+            if (o < cout) acc[o] = fmaf(v[k], ws[o * C + c + k], acc[o]);
+      }
+    } else {
+      for (int c = 0; c < C; ++c) {
+        const float v = view_ld(x, i, c);
+#pragma unroll
+        for (int o = 0; o < 4; ++o)
+          if (o < cout) acc[o] = fmaf(v, ws[o * C + c], acc[o]);
+      }
     }
     const int n = (int)(i / HW);
     const int rem = (int)(i - (long long)n * HW);
@@ -400,6 +425,16 @@ extern "C" int dbsr_predictor(const dbsr_nhwc_t* x, const float* w, const float*
   DBSR_REQUIRE(view_ok(x) && w && pred && cout >= 1 && cout <= 4, "predictor: bad arguments");
   const long long total = (long long)x->n * x->h * x->w;
   const size_t smem = (size_t)(cout * x->c + cout) * sizeof(float);
-  predictor_kernel<<<grid_for(total, 256), 256, smem, (cudaStream_t)stream>>>(make_view(x), w, bias, cout, pred);
+  const size_t es = elem_size(x->dtype);
+  const bool vec = x->c % 8 == 0 && (x->c_off * es) % 16 == 0 && (x->c_pitch * es) % 16 == 0 && ((uintptr_t)x->data % 16) == 0;
+  const int g = grid_for(total, 256) * 4;   // grid_for caps at 16 blocks/SM worth; one thread per pixel here
+  cudaStream_t st = (cudaStream_t)stream;
+  if (x->dtype == DBSR_BF16) {
+    if (vec) predictor_kernel<__nv_bfloat16, true><<<g, 256, smem, st>>>(make_view(x), w, bias, cout, pred);
+    else predictor_kernel<__nv_bfloat16, false><<<g, 256, smem, st>>>(make_view(x), w, bias, cout, pred);
+  } else {
+    if (vec) predictor_kernel<float, true><<<g, 256, smem, st>>>(make_view(x), w, bias, cout, pred);
+    else predictor_kernel<float, false><<<g, 256, smem, st>>>(make_view(x), w, bias, cout, pred);
+  }
   return check_launch("predictor");
 }
