@@ -303,11 +303,29 @@ softmax_wsum8_kernel(View feat, View logits, const float* __restrict__ offsets, 
   const int g = threadIdx.x & 7, px = (threadIdx.x >> 3) & 7, py = threadIdx.x >> 6;
   const int b = blockIdx.z;
   const int ch = blockIdx.y * 64 + g * 8;
+  __shared__ float2 offs_s[32][16];
   {
-    const int y = (blockIdx.x / tiles_x) * WS_TH + py, x = (blockIdx.x % tiles_x) * WS_TW + px;
-    if (y >= H || x >= W || ch >= fused.c) return;
+    const int y_raw = (blockIdx.x / tiles_x) * WS_TH + py, x_raw = (blockIdx.x % tiles_x) * WS_TW + px;
+    const bool live = y_raw < H && x_raw < W && ch < fused.c;   // whole warps stay alive for the __syncwarp below
+    const int y = min(y_raw, H - 1), x = min(x_raw, W - 1);
+    const int ch_ld = live ? ch : 0;
+    (void)ch_ld;
     const int rem = y * W + x;
     const long long pix = (long long)b * HW + rem;
+    // the flows of all frames at this pixel first: independent loads, shared by the 8 threads (channel groups) of the
+    // pixel through smem -- one memory latency for the whole burst instead of one dependent load per frame
+    const bool hoisted = offsets != nullptr && frames <= 17;
+    if (hoisted) {
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        const int n = g + 8 * q;
+        if (n + 1 < frames) {
+          const long long pr = (long long)b * (frames - 1) + n;
+          offs_s[threadIdx.x >> 3][n] = make_float2(__ldg(offsets + (pr * 2 + 0) * HW + rem), __ldg(offsets + (pr * 2 + 1) * HW + rem));
+        }
+      }
+      __syncwarp();
+    }
     // online softmax with ONE exponential per element: d = l - m; x = exp(-|d|);
     //   d <= 0: (scale old, weight new) = (1, x)   else: (x, 1) and the running max moves to l
     float m[8], s[8], acc[8];
@@ -326,9 +344,15 @@ softmax_wsum8_kernel(View feat, View logits, const float* __restrict__ offsets, 
       if (offsets == nullptr) {
         a = ld8<TF>(fbase + (img * HW + rem) * feat.c_pitch + ch);
       } else {
-        const long long pr = (long long)b * (frames - 1) + (n - 1);
-        const float fx = __ldg(offsets + (pr * 2 + 0) * HW + rem);
-        const float fy = __ldg(offsets + (pr * 2 + 1) * HW + rem);
+        float fx, fy;
+        if (hoisted) {
+          const float2 o2 = offs_s[threadIdx.x >> 3][n - 1];
+          fx = o2.x; fy = o2.y;
+        } else {
+          const long long pr = (long long)b * (frames - 1) + (n - 1);
+          fx = __ldg(offsets + (pr * 2 + 0) * HW + rem);
+          fy = __ldg(offsets + (pr * 2 + 1) * HW + rem);
+        }
         const Taps t = make_taps((float)x + fx, (float)y + fy, H, W);
         a = gather8<TF>(fbase + img * HW * feat.c_pitch, feat.c_pitch, t, ch);
       }
@@ -351,89 +375,6 @@ softmax_wsum8_kernel(View feat, View logits, const float* __restrict__ offsets, 
   }
 }
 
-
-// Two-pass variant for bf16 logits and bursts of up to 16 frames: the N packed logit vectors of a thread (8 channels x
-// N frames = N x 16 bytes) are loaded up front (N independent 16-byte loads in flight) and kept in registers, pass 1
-// takes the per-channel maximum, pass 2 does one FFMA + one MUFU.EX2 per element.  ~2.5x fewer instructions per element
-// than the online formulation (which pays two selects, a compare and the rescale of the running sums per element).
-template <typename TF, typename TO>
-__global__ void __launch_bounds__(256)
-softmax_wsum8_twopass_kernel(View feat, View logits, const float* __restrict__ offsets, View fused, int frames) {
-  const int H = fused.h, W = fused.w;
-  const int HW = H * W;
-  const TF* fbase = reinterpret_cast<const TF*>(feat.data) + feat.c_off;
-  const __nv_bfloat16* lbase = reinterpret_cast<const __nv_bfloat16*>(logits.data) + logits.c_off;
-  TO* obase = reinterpret_cast<TO*>(fused.data) + fused.c_off;
-  const int tiles_x = (W + WS_TW - 1) / WS_TW;
-  const int g = threadIdx.x & 7, px = (threadIdx.x >> 3) & 7, py = threadIdx.x >> 6;
-  const int b = blockIdx.z;
-  const int ch = blockIdx.y * 64 + g * 8;
-  const int y = (blockIdx.x / tiles_x) * WS_TH + py, x = (blockIdx.x % tiles_x) * WS_TW + px;
-  if (y >= H || x >= W || ch >= fused.c) return;
-  const int rem = y * W + x;
-  const long long pix = (long long)b * HW + rem;
-  const long long img0 = (long long)b * frames;
-
-  uint4 lg[16];
-#pragma unroll
-  for (int n = 0; n < 16; ++n)
-    if (n < frames) lg[n] = __ldg(reinterpret_cast<const uint4*>(lbase + ((img0 + n) * HW + rem) * logits.c_pitch + ch));
-  // pass 1: per-channel maximum over the burst (packed bf16x2 max, exact)
-  __nv_bfloat162 mx[4];
-  {
-    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&lg[0]);
-#pragma unroll
-    for (int k = 0; k < 4; ++k) mx[k] = h[k];
-  }
-#pragma unroll
-  for (int n = 1; n < 16; ++n) {
-    if (n < frames) {
-      const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&lg[n]);
-#pragma unroll
-      for (int k = 0; k < 4; ++k) mx[k] = __hmax2(mx[k], h[k]);
-    }
-  }
-  const float LOG2E = 1.4426950408889634f;
-  float nm[8];   // -max * log2(e)
-#pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    const float2 f = __bfloat1622float2(mx[k]);
-    nm[2 * k] = -f.x * LOG2E; nm[2 * k + 1] = -f.y * LOG2E;
-  }
-  float s[8], acc[8];
-#pragma unroll
-  for (int k = 0; k < 8; ++k) { s[k] = 0.0f; acc[k] = 0.0f; }
-  // pass 2: e = 2^(l*log2e - max*log2e); s += e; acc += a * e
-#pragma unroll
-  for (int n = 0; n < 16; ++n) {
-    if (n < frames) {
-      Vec8 a;
-      if (n == 0 || offsets == nullptr) {
-        a = ld8<TF>(fbase + ((img0 + n) * HW + rem) * feat.c_pitch + ch);
-      } else {
-        const long long pr = (long long)b * (frames - 1) + (n - 1);
-        const float fx = __ldg(offsets + (pr * 2 + 0) * HW + rem);
-        const float fy = __ldg(offsets + (pr * 2 + 1) * HW + rem);
-        const Taps t = make_taps((float)x + fx, (float)y + fy, H, W);
-        a = gather8<TF>(fbase + (img0 + n) * HW * feat.c_pitch, feat.c_pitch, t, ch);
-      }
-      const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&lg[n]);
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const float2 l = __bfloat1622float2(h[k]);
-        const float e0 = exp2f(fmaf(l.x, LOG2E, nm[2 * k]));
-        const float e1 = exp2f(fmaf(l.y, LOG2E, nm[2 * k + 1]));
-        s[2 * k] += e0; s[2 * k + 1] += e1;
-        acc[2 * k] = fmaf(a.v[2 * k], e0, acc[2 * k]);
-        acc[2 * k + 1] = fmaf(a.v[2 * k + 1], e1, acc[2 * k + 1]);
-      }
-    }
-  }
-  Vec8 r;
-#pragma unroll
-  for (int k = 0; k < 8; ++k) r.v[k] = __fdividef(acc[k], s[k]);
-  st8<TO>(obase + pix * fused.c_pitch + ch, r);
-}
 
 // upsampling.py:59-65: per-channel 3x3 blur with zero padding, 8 channels per thread
 template <typename T>
@@ -527,8 +468,6 @@ extern "C" int dbsr_softmax_wsum(const dbsr_nhwc_t* feat, const dbsr_nhwc_t* log
   if (v8) {
     dim3 grid8(((fused->w + WS_TW - 1) / WS_TW) * ((fused->h + WS_TH - 1) / WS_TH), (fused->c + 63) / 64, fused->n);
     if (key == 0) softmax_wsum8_kernel<float, float, float><<<grid8, 256, 0, st>>>(f, l, offsets, o, frames);
-    else if (key == 7 && frames <= 16)
-      softmax_wsum8_twopass_kernel<__nv_bfloat16, __nv_bfloat16><<<grid8, 256, 0, st>>>(f, l, offsets, o, frames);
     else if (key == 7) softmax_wsum8_kernel<__nv_bfloat16, __nv_bfloat16, __nv_bfloat16><<<grid8, 256, 0, st>>>(f, l, offsets, o, frames);
     else softmax_wsum8_kernel<__nv_bfloat16, float, __nv_bfloat16><<<grid8, 256, 0, st>>>(f, l, offsets, o, frames);
   } else
