@@ -151,6 +151,19 @@ def main():
         from deep_rawburst_sr_b200.sharding import max_over_ranks as _mx
         return _mx(ms, dev)
 
+    if args.one_forward:
+        # profiling aid (ncu launch list / --set full): warm up, then exactly ONE eager forward and exit
+        net.use_cuda_graph = False
+        for _ in range(max(1, args.warmup)):
+            net(dev_in)
+        torch.cuda.synchronize()
+        torch.cuda.profiler.start()
+        net(dev_in)
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
+        print(json.dumps({'one_forward': True, 'launches_per_forward': eng.launches // (max(1, args.warmup) + 1)}))
+        return
+
     # ---- device-resident throughput ("value"): K forwards, inputs already in HBM
     for _ in range(args.warmup):
         net(dev_in)

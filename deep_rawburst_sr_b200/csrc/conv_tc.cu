@@ -207,6 +207,10 @@ struct ConvTcParams {
   int ntiles_n;         // cout_pad / n_tile
   int items_x, tiles_y;
   long long total_items;
+  // exact division by multiply-high for item -> (N tile, image, tile row, tile column): q = umulhi(n, mul) + (n & one)
+  // (host proves exactness for every n < total_items, else fastdiv = 0 and the kernel divides)
+  unsigned md_nt, md_img, md_x, one_nt, one_img, one_x; int fastdiv;
+  int bias_smem;        // bias table of cout_pad floats staged in shared memory (lean epilogue)
   int a_slots, b_stages, b_resident;
   int a_bytes, a_tx_bytes, b_bytes;
   int halo_w;           // pixels per row of the A box
@@ -310,6 +314,8 @@ __device__ __forceinline__ void epilogue_chunk(const ConvTcParams& p, const uint
 // ---------------------------------------------------------------------------------------------------------
 constexpr int STG_ROW = 144;                    // 128 data bytes + 16 pad: conflict-free for both access patterns
 constexpr int STG_WARP_BYTES = 32 * STG_ROW;    // per epilogue warp
+constexpr int BAR_BYTES = 2048;                 // mbarriers + TMEM slot (up to 64 resident weight stages)
+constexpr int BIAS_TAB_BYTES = 2048;            // bias table of the lean epilogue (cout_pad <= 512 floats)
 
 // geometry of one 16x8 tile for the coalesced epilogue: pointers to its pixel (0,0) at the first channel of the N
 // tile, element strides between tile rows / columns (pixel-shuffle folds into these), and how many rows / columns of
@@ -409,23 +415,109 @@ __device__ __forceinline__ void epilogue_group_bf16(const ConvTcParams& p, uint3
 }
 
 struct ItemCoord { int nt, img, y0, x0; };
+__device__ __forceinline__ unsigned fast_div(unsigned n, unsigned d, unsigned mul, unsigned one, int fast) {
+  return fast ? __umulhi(n, mul) + (n & one) : n / d;
+}
 __device__ __forceinline__ ItemCoord decode_item(const ConvTcParams& p, long long item64) {
   ItemCoord c;
   const unsigned item = (unsigned)item64;            // item counts fit 32 bits (64-bit div/mod costs ~100 instr each)
-  const unsigned tm = item / (unsigned)p.ntiles_n;
+  const unsigned tm = fast_div(item, (unsigned)p.ntiles_n, p.md_nt, p.one_nt, p.fastdiv);
   c.nt = (int)(item - tm * (unsigned)p.ntiles_n);
   if (p.flat) {   // item = flat_ni consecutive images
     c.img = (int)tm * p.flat_ni; c.y0 = 0; c.x0 = 0;
     return c;
   }
   const unsigned per_img = (unsigned)(p.items_x * p.tiles_y);
-  const unsigned img = tm / per_img;
+  const unsigned img = fast_div(tm, per_img, p.md_img, p.one_img, p.fastdiv);
   const unsigned rem = tm - img * per_img;
-  const unsigned ry = rem / (unsigned)p.items_x;
+  const unsigned ry = fast_div(rem, (unsigned)p.items_x, p.md_x, p.one_x, p.fastdiv);
   c.img = (int)img;
   c.y0 = (int)ry * TILE_H;
   c.x0 = (int)(rem - ry * (unsigned)p.items_x) * (TILE_W * p.mt);
   return c;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Lean coalesced bf16 epilogue (no epilogue-side residual): the 8 epilogue warps are per-warp latency bound -- one warp
+// walks accumulator -> bias -> activation -> bf16 -> staging row -> coalesced store for its 32 pixels -- so every
+// instruction that is not one of those is hoisted out of the per-item path: shared-state-space ld/st on 32-bit addresses,
+// bias from a shared-memory table, lane pointers advanced by precomputed strides, unpredicated stores for interior tiles.
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" :: "r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ float4 lds128f(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+
+// 32 (or 16) accumulator columns of this thread's pixel -> + bias -> activation -> bf16 -> own staging row
+template <int NC>
+__device__ __forceinline__ void lean_chunk(const uint32_t (&r)[32], uint32_t bias_s, bool has_bias, int act, uint32_t row_s) {
+  float v[NC];
+#pragma unroll
+  for (int j = 0; j < NC; ++j) v[j] = __uint_as_float(r[j]);
+  if (has_bias) {
+#pragma unroll
+    for (int j = 0; j < NC; j += 4) {
+      const float4 b = lds128f(bias_s + j * 4);
+      v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+    }
+  }
+  if (act == DBSR_ACT_RELU) {
+#pragma unroll
+    for (int j = 0; j < NC; ++j) v[j] = fmaxf(v[j], 0.0f);
+  } else if (act == DBSR_ACT_LRELU) {
+#pragma unroll
+    for (int j = 0; j < NC; ++j) v[j] = apply_act(v[j], DBSR_ACT_LRELU);
+  }
+#pragma unroll
+  for (int j = 0; j < NC; j += 8)
+    sts128(row_s + j * 2, pack_bf16x2(v[j], v[j + 1]), pack_bf16x2(v[j + 2], v[j + 3]), pack_bf16x2(v[j + 4], v[j + 5]),
+           pack_bf16x2(v[j + 6], v[j + 7]));
+}
+
+// one channel group (GW = 64 / 32 / 16 channels) of this warp's 32 pixels (4 tile rows x 8)
+//   ywarp: element pointer of the warp's first pixel (tile row quarter*4, column 0) at the group's first channel
+//   rows_left / cols_in: in-image extent relative to that pixel; full: all 4 x 8 pixels are inside the image
+template <int GW>
+__device__ __forceinline__ void lean_group(uint32_t taddr, uint32_t bias_s, bool has_bias, int act, uint32_t stg_s, int lane,
+                                           __nv_bfloat16* ywarp, long long y_row, long long y_col, bool full, int rows_left,
+                                           int cols_in) {
+  constexpr int LPP = GW / 8;        // lanes (16-byte chunks) per pixel
+  constexpr int PPI = 32 / LPP;      // pixels per warp instruction
+  uint32_t r0[32], r1[32];
+  if (GW >= 32) tmem_ld32_nowait(taddr, r0); else tmem_ld16_nowait(taddr, r0);
+  if (GW == 64) tmem_ld32_nowait(taddr + 32u, r1);
+  const int sub = lane / LPP, chunk = lane % LPP;
+  const int r_lane = (PPI > 8) ? (sub >> 3) : 0, c_lane = sub & 7;
+  __nv_bfloat16* yl = ywarp + r_lane * y_row + c_lane * y_col + chunk * 8;
+  const uint32_t rd_s = stg_s + (uint32_t)(sub * STG_ROW + chunk * 16);
+  const uint32_t row_s = stg_s + (uint32_t)(lane * STG_ROW);
+  tmem_wait_ld();
+  if (GW >= 32) lean_chunk<32>(r0, bias_s, has_bias, act, row_s); else lean_chunk<16>(r0, bias_s, has_bias, act, row_s);
+  if (GW == 64) lean_chunk<32>(r1, bias_s + 128u, has_bias, act, row_s + 64u);
+  __syncwarp();
+#pragma unroll
+  for (int it = 0; it < LPP; ++it) {
+    // staging row ml = it * PPI + sub  ->  tile row (ml >> 3), column (ml & 7)
+    const int r_it = (it * PPI) >> 3, c_it = (it * PPI) & 7;
+    const uint4 q = lds128(rd_s + (uint32_t)(it * PPI * STG_ROW));
+    if (full || (r_lane + r_it < rows_left && c_lane + c_it < cols_in))
+      *reinterpret_cast<uint4*>(yl + r_it * y_row + c_it * y_col) = q;
+  }
+  __syncwarp();
 }
 
 template <int CK, bool RESIDENT>
@@ -445,6 +537,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
   uint64_t* tfull_bar = b_empty + p.b_stages;
   uint64_t* tempty_bar = tfull_bar + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  float* bias_tab = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + BAR_BYTES);   // [cout_pad] when p.bias_smem
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   constexpr uint32_t ROW_BYTES = CK * 2;                 // bytes per pixel of a K chunk
@@ -466,6 +559,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
     if (p.res_chunks) { tma_prefetch_desc(&tmap_r); tma_prefetch_desc(&tmap_i); }
   }
   if (warp == WARP_MMA) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+  if (p.bias_smem && warp < 8)
+    for (int i = threadIdx.x; i < p.cout_pad; i += 256) bias_tab[i] = p.bias ? __ldg(p.bias + i) : 0.0f;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -643,6 +738,55 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
     const int ty = m >> 3, tx = m & 7;
     uint8_t* stg = smem_stg + (size_t)warp * STG_WARP_BYTES;
     int acc = 0; uint32_t acc_phase = 0;
+    if (p.bias_smem && p.vec_ok && p.y_dtype == DBSR_BF16 && p.res == nullptr) {
+      // ---------- lean coalesced path (every bf16 layer of the encoder / fusion / decoder trunks) ----------
+      const uint32_t stg_s = smem_u32(stg);
+      const uint32_t bias_s0 = smem_u32(bias_tab);
+      const bool has_bias = p.bias != nullptr;
+      const int act = p.act;
+      const int t = (p.mt == 2) ? group : 0;
+      const bool shuffle = p.shuffle_r > 1;
+      const long long y_row = shuffle ? (long long)p.shuffle_r * p.yW * p.y_pitch : (long long)p.yW * p.y_pitch;
+      const long long y_col = shuffle ? (long long)p.shuffle_r * p.y_pitch : (long long)p.y_pitch;
+      __nv_bfloat16* const ybase = reinterpret_cast<__nv_bfloat16*>(p.y) + p.y_coff + (long long)(quarter * 4) * y_row;
+      const uint32_t tq = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(t * NT);
+      const uint32_t acc_cols = (uint32_t)(p.mt * NT);
+      for (long long item = blockIdx.x; item < p.total_items; item += gridDim.x) {
+        const ItemCoord c = decode_item(p, item);
+        const int co0 = c.nt * NT;
+        const int tx0 = c.x0 + t * TILE_W;
+        __nv_bfloat16* ywarp;
+        if (shuffle) {
+          // packed channel co' = i*256 + j*32 + c ; N tile = 128 -> HR row phase i = nt / 2, first HR column j0 = (nt & 1) * 4
+          const int per_i = p.shuffle_r * 32;
+          const int si = co0 / per_i, j0 = (co0 - si * per_i) >> 5;
+          ywarp = ybase + ((long long)(c.img * p.yH + c.y0 * p.shuffle_r + si) * p.yW + (tx0 * p.shuffle_r + j0)) * p.y_pitch;
+        } else {
+          ywarp = ybase + ((long long)(c.img * p.yH + c.y0) * p.yW + tx0) * p.y_pitch + co0;
+        }
+        const int rows_left = p.H - c.y0 - quarter * 4, cols_in = p.W - tx0;
+        const bool full = rows_left >= 4 && cols_in >= TILE_W;
+        const uint32_t tbase = tq + (uint32_t)acc * acc_cols;
+        const uint32_t bias_s = bias_s0 + (uint32_t)co0 * 4u;
+        mbar_wait(&tfull_bar[acc], acc_phase, 400 + acc);
+        tc_fence_after();
+        int g0 = 0, gi = 0;
+        while (g0 < NT) {
+          const int rem = NT - g0;
+          const int gw = rem >= 64 ? 64 : (rem >= 32 ? 32 : 16);
+          if (p.mt == 2 || (gi & 1) == group) {
+            if (gw == 64) lean_group<64>(tbase + (uint32_t)g0, bias_s + (uint32_t)g0 * 4u, has_bias, act, stg_s, lane, ywarp + g0, y_row, y_col, full, rows_left, cols_in);
+            else if (gw == 32) lean_group<32>(tbase + (uint32_t)g0, bias_s + (uint32_t)g0 * 4u, has_bias, act, stg_s, lane, ywarp + g0, y_row, y_col, full, rows_left, cols_in);
+            else lean_group<16>(tbase + (uint32_t)g0, bias_s + (uint32_t)g0 * 4u, has_bias, act, stg_s, lane, ywarp + g0, y_row, y_col, full, rows_left, cols_in);
+          }
+          g0 += gw; ++gi;
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    } else
     for (long long item = blockIdx.x; item < p.total_items; item += gridDim.x) {
       const ItemCoord c = decode_item(p, item);
       const int co0 = c.nt * NT;
@@ -829,7 +973,7 @@ static int tc_plan(const dbsr_conv_t* c, TcConfig* cfg, bool set_err) {
   cfg->cout_pad = cpad;
   const int tiles_x = ceil_div(c->x.w, TILE_W);
   const int pad = (c->ksize == 3) ? c->dilation : 0;
-  const int budget = 227 * 1024 - 4096 - 8 * STG_WARP_BYTES;
+  const int budget = 227 * 1024 - (1024 + BAR_BYTES + BIAS_TAB_BYTES) - 8 * STG_WARP_BYTES;
   const int taps = c->ksize * c->ksize;
   cfg->b_bytes = nt * ck * 2;
   TC_REQ(cfg->b_bytes % 1024 == 0, "conv2d_tc: internal: unaligned weight stage");
@@ -893,7 +1037,7 @@ static int tc_plan(const dbsr_conv_t* c, TcConfig* cfg, bool set_err) {
     TC_REQ(st >= 2, "conv2d_tc: no room for the weight pipeline");
     cfg->b_stages = st;
   }
-  int smem = cfg->a_slots * cfg->a_bytes + cfg->b_stages * cfg->b_bytes + 8 * STG_WARP_BYTES + 1024 /*align slack*/ + 2048 /*barriers*/;
+  int smem = cfg->a_slots * cfg->a_bytes + cfg->b_stages * cfg->b_bytes + 8 * STG_WARP_BYTES + 1024 /*align slack*/ + BAR_BYTES + BIAS_TAB_BYTES;
   // a CTA that owns more than half of TMEM must be alone on its SM: make its smem footprint exclusive too
   if (cfg->tmem_cols > 256 && smem < 120 * 1024) smem = 120 * 1024;
   cfg->smem_bytes = smem;
@@ -1018,6 +1162,23 @@ extern "C" int dbsr_conv2d_tc(const dbsr_conv_t* c, void* stream) {
   p.total_items = (long long)p.n * p.items_x * p.tiles_y * p.ntiles_n;
   p.flat = cfg.flat; p.flat_s = cfg.flat_s; p.flat_ni = cfg.flat_ni;
   if (cfg.flat) p.total_items = (long long)ceil_div(p.n, cfg.flat_ni) * p.ntiles_n;
+  DBSR_REQUIRE(p.total_items < (1LL << 31) && (long long)c->y.n * c->y.h * c->y.w < (1LL << 31),
+               "conv2d_tc: more than 2^31 work items / output pixels");
+  {
+    // q = umulhi(n, ceil(2^32 / d)) is floor(n / d) for every n with n * d < 2^32
+    const unsigned d[3] = {(unsigned)p.ntiles_n, (unsigned)(p.items_x * p.tiles_y), (unsigned)p.items_x};
+    unsigned mul[3], one[3];
+    unsigned long long dmax = 1;
+    for (int i = 0; i < 3; ++i) {
+      if (d[i] <= 1) { mul[i] = 0u; one[i] = 0xFFFFFFFFu; }
+      else { mul[i] = (unsigned)(((1ULL << 32) + d[i] - 1) / d[i]); one[i] = 0u; }
+      if (d[i] > dmax) dmax = d[i];
+    }
+    p.md_nt = mul[0]; p.md_img = mul[1]; p.md_x = mul[2];
+    p.one_nt = one[0]; p.one_img = one[1]; p.one_x = one[2];
+    p.fastdiv = ((unsigned long long)p.total_items * dmax < (1ULL << 32)) ? 1 : 0;
+  }
+  p.bias_smem = (cfg.cout_pad * 4 <= BIAS_TAB_BYTES) ? 1 : 0;
   p.a_slots = cfg.a_slots; p.b_stages = cfg.b_stages; p.b_resident = cfg.b_resident;
   p.a_bytes = cfg.a_bytes; p.a_tx_bytes = cfg.a_tx_bytes; p.b_bytes = cfg.b_bytes; p.halo_w = cfg.halo_w;
   p.y = c->y.data; p.y_dtype = c->y.dtype; p.y_pitch = c->y.c_pitch; p.y_coff = c->y.c_off;

@@ -302,14 +302,13 @@ softmax_wsum8_kernel(View feat, View logits, const float* __restrict__ offsets, 
   const int tiles_x = (W + WS_TW - 1) / WS_TW;
   const int g = threadIdx.x & 7, px = (threadIdx.x >> 3) & 7, py = threadIdx.x >> 6;
   const int b = blockIdx.z;
-  const int ch = blockIdx.y * 64 + g * 8;
+  const int ch_raw = blockIdx.y * 64 + g * 8;
+  const int ch = min(ch_raw, fused.c - 8);   // clamped for the loads; the store is predicated on `live`
   __shared__ float2 offs_s[32][16];
   {
     const int y_raw = (blockIdx.x / tiles_x) * WS_TH + py, x_raw = (blockIdx.x % tiles_x) * WS_TW + px;
-    const bool live = y_raw < H && x_raw < W && ch < fused.c;   // whole warps stay alive for the __syncwarp below
+    const bool live = y_raw < H && x_raw < W && ch_raw < fused.c;   // whole warps stay alive for the __syncwarp below
     const int y = min(y_raw, H - 1), x = min(x_raw, W - 1);
-    const int ch_ld = live ? ch : 0;
-    (void)ch_ld;
     const int rem = y * W + x;
     const long long pix = (long long)b * HW + rem;
     // the flows of all frames at this pixel first: independent loads, shared by the 8 threads (channel groups) of the
@@ -371,7 +370,7 @@ softmax_wsum8_kernel(View feat, View logits, const float* __restrict__ offsets, 
     Vec8 r;
 #pragma unroll
     for (int k = 0; k < 8; ++k) r.v[k] = acc[k] / s[k];
-    st8<TO>(obase + pix * fused.c_pitch + ch, r);
+    if (live) st8<TO>(obase + pix * fused.c_pitch + ch, r);
   }
 }
 
