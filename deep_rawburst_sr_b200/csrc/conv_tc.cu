@@ -462,9 +462,11 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   return r;
 }
 
-// 32 (or 16) accumulator columns of this thread's pixel -> + bias -> activation -> bf16 -> own staging row
+// 32 (or 16) accumulator columns of this thread's pixel -> + bias -> activation -> bf16 -> own staging row.
+// The row's 16-byte slot c lives at physical slot (c ^ swz) (see lean_group); c0 = first slot of this chunk.
 template <int NC>
-__device__ __forceinline__ void lean_chunk(const uint32_t (&r)[32], uint32_t bias_s, bool has_bias, int act, uint32_t row_s) {
+__device__ __forceinline__ void lean_chunk(const uint32_t (&r)[32], uint32_t bias_s, bool has_bias, int act, uint32_t row_s,
+                                           uint32_t c0, uint32_t swz, bool has_res) {
   float v[NC];
 #pragma unroll
   for (int j = 0; j < NC; ++j) v[j] = __uint_as_float(r[j]);
@@ -473,6 +475,16 @@ __device__ __forceinline__ void lean_chunk(const uint32_t (&r)[32], uint32_t bia
     for (int j = 0; j < NC; j += 4) {
       const float4 b = lds128f(bias_s + j * 4);
       v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+    }
+  }
+  if (has_res) {   // residual of this pixel, prefetched into the same staging slots the result will overwrite
+#pragma unroll
+    for (int j = 0; j < NC; j += 8) {
+      const uint4 q = lds128(row_s + (((c0 + (uint32_t)(j >> 3)) ^ swz) << 4));
+      v[j] += __uint_as_float(q.x << 16); v[j + 1] += __uint_as_float(q.x & 0xFFFF0000u);
+      v[j + 2] += __uint_as_float(q.y << 16); v[j + 3] += __uint_as_float(q.y & 0xFFFF0000u);
+      v[j + 4] += __uint_as_float(q.z << 16); v[j + 5] += __uint_as_float(q.z & 0xFFFF0000u);
+      v[j + 6] += __uint_as_float(q.w << 16); v[j + 7] += __uint_as_float(q.w & 0xFFFF0000u);
     }
   }
   if (act == DBSR_ACT_RELU) {
@@ -484,18 +496,22 @@ __device__ __forceinline__ void lean_chunk(const uint32_t (&r)[32], uint32_t bia
   }
 #pragma unroll
   for (int j = 0; j < NC; j += 8)
-    sts128(row_s + j * 2, pack_bf16x2(v[j], v[j + 1]), pack_bf16x2(v[j + 2], v[j + 3]), pack_bf16x2(v[j + 4], v[j + 5]),
-           pack_bf16x2(v[j + 6], v[j + 7]));
+    sts128(row_s + (((c0 + (uint32_t)(j >> 3)) ^ swz) << 4), pack_bf16x2(v[j], v[j + 1]), pack_bf16x2(v[j + 2], v[j + 3]),
+           pack_bf16x2(v[j + 4], v[j + 5]), pack_bf16x2(v[j + 6], v[j + 7]));
 }
 
 // one channel group (GW = 64 / 32 / 16 channels) of this warp's 32 pixels (4 tile rows x 8)
 //   ywarp: element pointer of the warp's first pixel (tile row quarter*4, column 0) at the group's first channel
 //   rows_left / cols_in: in-image extent relative to that pixel; full: all 4 x 8 pixels are inside the image
+// Staging layout (per warp, dense rows of GW*2 bytes = LPP 16-byte slots): slot c of row r sits at physical slot
+// c ^ ((r * LPP / 8) % LPP).  Both access patterns are then bank-conflict free: the transposing writes (8 consecutive
+// rows, same c, per quarter-warp) and the coalescing reads (8 / LPP consecutive rows x LPP slots per quarter-warp) each
+// touch 8 distinct 16-byte bank groups.
 template <int GW>
 __device__ __forceinline__ void lean_group(uint32_t taddr, uint32_t bias_s, bool has_bias, int act, uint32_t stg_s, int lane,
                                            __nv_bfloat16* ywarp, long long y_row, long long y_col, bool full, int rows_left,
-                                           int cols_in) {
-  constexpr int LPP = GW / 8;        // lanes (16-byte chunks) per pixel
+                                           int cols_in, bool has_res) {
+  constexpr int LPP = GW / 8;        // lanes (16-byte slots) per pixel
   constexpr int PPI = 32 / LPP;      // pixels per warp instruction
   uint32_t r0[32], r1[32];
   if (GW >= 32) tmem_ld32_nowait(taddr, r0); else tmem_ld16_nowait(taddr, r0);
@@ -503,21 +519,43 @@ __device__ __forceinline__ void lean_group(uint32_t taddr, uint32_t bias_s, bool
   const int sub = lane / LPP, chunk = lane % LPP;
   const int r_lane = (PPI > 8) ? (sub >> 3) : 0, c_lane = sub & 7;
   __nv_bfloat16* yl = ywarp + r_lane * y_row + c_lane * y_col + chunk * 8;
-  const uint32_t rd_s = stg_s + (uint32_t)(sub * STG_ROW + chunk * 16);
-  const uint32_t row_s = stg_s + (uint32_t)(lane * STG_ROW);
+  const uint32_t row_s = stg_s + (uint32_t)(lane * GW * 2);
+  const uint32_t wswz = (uint32_t)((lane * LPP) >> 3) % LPP;
+  if (has_res) { cp_async_wait_all(); __syncwarp(); }     // the prefetched residual rows have landed
   tmem_wait_ld();
-  if (GW >= 32) lean_chunk<32>(r0, bias_s, has_bias, act, row_s); else lean_chunk<16>(r0, bias_s, has_bias, act, row_s);
-  if (GW == 64) lean_chunk<32>(r1, bias_s + 128u, has_bias, act, row_s + 64u);
+  if (GW >= 32) lean_chunk<32>(r0, bias_s, has_bias, act, row_s, 0u, wswz, has_res); else lean_chunk<16>(r0, bias_s, has_bias, act, row_s, 0u, wswz, has_res);
+  if (GW == 64) lean_chunk<32>(r1, bias_s + 128u, has_bias, act, row_s, 4u, wswz, has_res);
   __syncwarp();
 #pragma unroll
   for (int it = 0; it < LPP; ++it) {
     // staging row ml = it * PPI + sub  ->  tile row (ml >> 3), column (ml & 7)
     const int r_it = (it * PPI) >> 3, c_it = (it * PPI) & 7;
-    const uint4 q = lds128(rd_s + (uint32_t)(it * PPI * STG_ROW));
+    const uint32_t rswz = (uint32_t)(it * 4 + ((sub * LPP) >> 3)) % LPP;     // ((ml * LPP) / 8) % LPP
+    const uint4 q = lds128(stg_s + (uint32_t)((it * PPI + sub) * GW * 2) + (((uint32_t)chunk ^ rswz) << 4));
     if (full || (r_lane + r_it < rows_left && c_lane + c_it < cols_in))
       *reinterpret_cast<uint4*>(yl + r_it * y_row + c_it * y_col) = q;
   }
   __syncwarp();
+}
+
+// residual rows of this warp's 32 pixels (one channel group of GW channels) -> staging, asynchronously, in the layout
+// lean_group reads them from; issued before the wait for the accumulators so the latency hides behind the MMAs
+template <int GW>
+__device__ __forceinline__ void lean_prefetch_res(uint32_t stg_s, int lane, const __nv_bfloat16* rwarp, long long r_row,
+                                                  long long r_col, int rows_left, int cols_in, const void* safe) {
+  constexpr int LPP = GW / 8, PPI = 32 / LPP;
+  const int sub = lane / LPP, chunk = lane % LPP;
+  const int r_lane = (PPI > 8) ? (sub >> 3) : 0, c_lane = sub & 7;
+  const __nv_bfloat16* rl = rwarp + r_lane * r_row + c_lane * r_col + chunk * 8;
+#pragma unroll
+  for (int it = 0; it < LPP; ++it) {
+    const int r_it = (it * PPI) >> 3, c_it = (it * PPI) & 7;
+    const uint32_t rswz = (uint32_t)(it * 4 + ((sub * LPP) >> 3)) % LPP;
+    const bool ok = r_lane + r_it < rows_left && c_lane + c_it < cols_in;
+    const uint32_t dst = stg_s + (uint32_t)((it * PPI + sub) * GW * 2) + (((uint32_t)chunk ^ rswz) << 4);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(ok ? (const void*)(rl + r_it * r_row + c_it * r_col) : safe),
+                 "r"(ok ? 16u : 0u) : "memory");
+  }
 }
 
 template <int CK, bool RESIDENT>
@@ -738,7 +776,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
     const int ty = m >> 3, tx = m & 7;
     uint8_t* stg = smem_stg + (size_t)warp * STG_WARP_BYTES;
     int acc = 0; uint32_t acc_phase = 0;
-    if (p.bias_smem && p.vec_ok && p.y_dtype == DBSR_BF16 && p.res == nullptr) {
+    if (p.bias_smem && p.vec_ok && p.y_dtype == DBSR_BF16 && (p.res == nullptr || NT == 64 || NT == 32 || NT == 16)) {
       // ---------- lean coalesced path (every bf16 layer of the encoder / fusion / decoder trunks) ----------
       const uint32_t stg_s = smem_u32(stg);
       const uint32_t bias_s0 = smem_u32(bias_tab);
@@ -751,6 +789,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
       __nv_bfloat16* const ybase = reinterpret_cast<__nv_bfloat16*>(p.y) + p.y_coff + (long long)(quarter * 4) * y_row;
       const uint32_t tq = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(t * NT);
       const uint32_t acc_cols = (uint32_t)(p.mt * NT);
+      // epilogue-side residual (single channel group per warp, N tile <= 64): prefetched into the staging rows
+      const bool has_res = p.res != nullptr;
+      const long long r_row = (long long)p.yW * p.r_pitch, r_col = (long long)p.r_pitch;
+      const __nv_bfloat16* const rbase = reinterpret_cast<const __nv_bfloat16*>(p.res) + p.r_coff + (long long)(quarter * 4) * r_row;
+      const bool my_group = (p.mt == 2) || group == 0;      // NT <= 64 is one group: with mt == 1 warps 4..7 have no columns
       for (long long item = blockIdx.x; item < p.total_items; item += gridDim.x) {
         const ItemCoord c = decode_item(p, item);
         const int co0 = c.nt * NT;
@@ -768,6 +811,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
         const bool full = rows_left >= 4 && cols_in >= TILE_W;
         const uint32_t tbase = tq + (uint32_t)acc * acc_cols;
         const uint32_t bias_s = bias_s0 + (uint32_t)co0 * 4u;
+        if (has_res && my_group) {
+          const __nv_bfloat16* rwarp = rbase + ((long long)(c.img * p.yH + c.y0) * p.yW + tx0) * p.r_pitch + co0;
+          if (NT == 64) lean_prefetch_res<64>(stg_s, lane, rwarp, r_row, r_col, rows_left, cols_in, p.res);
+          else if (NT == 32) lean_prefetch_res<32>(stg_s, lane, rwarp, r_row, r_col, rows_left, cols_in, p.res);
+          else lean_prefetch_res<16>(stg_s, lane, rwarp, r_row, r_col, rows_left, cols_in, p.res);
+        }
         mbar_wait(&tfull_bar[acc], acc_phase, 400 + acc);
         tc_fence_after();
         int g0 = 0, gi = 0;
@@ -775,9 +824,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
           const int rem = NT - g0;
           const int gw = rem >= 64 ? 64 : (rem >= 32 ? 32 : 16);
           if (p.mt == 2 || (gi & 1) == group) {
-            if (gw == 64) lean_group<64>(tbase + (uint32_t)g0, bias_s + (uint32_t)g0 * 4u, has_bias, act, stg_s, lane, ywarp + g0, y_row, y_col, full, rows_left, cols_in);
-            else if (gw == 32) lean_group<32>(tbase + (uint32_t)g0, bias_s + (uint32_t)g0 * 4u, has_bias, act, stg_s, lane, ywarp + g0, y_row, y_col, full, rows_left, cols_in);
-            else lean_group<16>(tbase + (uint32_t)g0, bias_s + (uint32_t)g0 * 4u, has_bias, act, stg_s, lane, ywarp + g0, y_row, y_col, full, rows_left, cols_in);
+            if (gw == 64) lean_group<64>(tbase + (uint32_t)g0, bias_s + (uint32_t)g0 * 4u, has_bias, act, stg_s, lane, ywarp + g0, y_row, y_col, full, rows_left, cols_in, has_res);
+            else if (gw == 32) lean_group<32>(tbase + (uint32_t)g0, bias_s + (uint32_t)g0 * 4u, has_bias, act, stg_s, lane, ywarp + g0, y_row, y_col, full, rows_left, cols_in, has_res);
+            else lean_group<16>(tbase + (uint32_t)g0, bias_s + (uint32_t)g0 * 4u, has_bias, act, stg_s, lane, ywarp + g0, y_row, y_col, full, rows_left, cols_in, has_res);
           }
           g0 += gw; ++gi;
         }
@@ -1024,8 +1073,11 @@ static int tc_plan(const dbsr_conv_t* c, TcConfig* cfg, bool set_err) {
   // residual on the tensor core: extra K chunks with identity weights (bf16 residual, aligned, same channel chunking)
   cfg->res_chunks = 0;
   if (c->residual.data && !cfg->flat && c->residual.dtype == DBSR_BF16 && (c->residual.c_off % 8) == 0 &&
-      (c->residual.c_pitch % 8) == 0 && ((uintptr_t)c->residual.data % 16) == 0 && nt % ck == 0 && !getenv("DBSR_TC_NO_RESK"))
-    cfg->res_chunks = nt / ck;
+      (c->residual.c_pitch % 8) == 0 && ((uintptr_t)c->residual.data % 16) == 0 && nt % ck == 0 &&
+      !(vec && c->y.dtype == DBSR_BF16 && nt == 64 && cpad * 4 <= BIAS_TAB_BYTES))
+    cfg->res_chunks = nt / ck;       // N tile 64 takes the residual in the (prefetching) lean epilogue instead: there the extra
+                                     // K chunk costs a whole halo slot of the A ring; at N = 32 the epilogue is the bottleneck and at
+                                     // N = 128 the staging area holds half a pixel row, so both keep the tensor-core residual
   const int b_total = (cfg->nchunks * taps + cfg->res_chunks) * cfg->b_bytes;
   if (cpad == nt && cfg->a_slots * cfg->a_bytes + b_total <= budget && cfg->nchunks * taps + cfg->res_chunks <= 64) {
     cfg->b_resident = 1;
