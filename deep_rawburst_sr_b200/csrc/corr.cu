@@ -18,6 +18,43 @@ constexpr int HALO_H = CT_H + 8, HALO_W = CT_W + 8;
 constexpr int CORR_THREADS = 288;
 constexpr int CORR_SMEM = (HALO_H * HALO_W + CT_H * CT_W) * C_CH * (int)sizeof(float);
 
+struct Vec8c { float v[8]; };
+__device__ __forceinline__ Vec8c vec8_zero() {
+  Vec8c r;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) r.v[i] = 0.0f;
+  return r;
+}
+// 8 consecutive channels (16-byte aligned address); channels >= valid read as zero
+template <typename T> __device__ __forceinline__ Vec8c vec8_ld(const T* p, int valid);
+template <> __device__ __forceinline__ Vec8c vec8_ld<float>(const float* p, int valid) {
+  const float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+  Vec8c r;
+  r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w; r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w;
+  if (valid < 8) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) if (i >= valid) r.v[i] = 0.0f;
+  }
+  return r;
+}
+template <> __device__ __forceinline__ Vec8c vec8_ld<__nv_bfloat16>(const __nv_bfloat16* p, int valid) {
+  const uint4 q = __ldg(reinterpret_cast<const uint4*>(p));
+  Vec8c r;
+  r.v[0] = __uint_as_float(q.x << 16); r.v[1] = __uint_as_float(q.x & 0xFFFF0000u);
+  r.v[2] = __uint_as_float(q.y << 16); r.v[3] = __uint_as_float(q.y & 0xFFFF0000u);
+  r.v[4] = __uint_as_float(q.z << 16); r.v[5] = __uint_as_float(q.z & 0xFFFF0000u);
+  r.v[6] = __uint_as_float(q.w << 16); r.v[7] = __uint_as_float(q.w & 0xFFFF0000u);
+  if (valid < 8) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) if (i >= valid) r.v[i] = 0.0f;
+  }
+  return r;
+}
+__device__ __forceinline__ void vec8_sts(float* dst, const Vec8c& v) {
+  *reinterpret_cast<float4*>(dst) = make_float4(v.v[0], v.v[1], v.v[2], v.v[3]);
+  *reinterpret_cast<float4*>(dst + 4) = make_float4(v.v[4], v.v[5], v.v[6], v.v[7]);
+}
+
 struct CorrParams {
   View f1, f2, flow, out;
   float flow_scale;
@@ -25,6 +62,7 @@ struct CorrParams {
   int tiles_x;
 };
 
+template <bool VEC, typename T>
 __global__ void __launch_bounds__(CORR_THREADS) corr81_kernel(const CorrParams p) {
   extern __shared__ __align__(16) float smem[];
   float* f2_s = smem;                                // [HALO_H*HALO_W][32]
@@ -59,45 +97,91 @@ __global__ void __launch_bounds__(CORR_THREADS) corr81_kernel(const CorrParams p
   const bool active = row < th && strip * 4 < tw;      // this thread owns at least one real output pixel
 
   for (int c0 = 0; c0 < C; c0 += C_CH) {
-    // ---- stage f1 tile
-    for (int e = t; e < th * CT_W * C_CH; e += CORR_THREADS) {      // rows >= th are never read
-      const int ch = e & (C_CH - 1), pix = e >> 5;
-      const int y = ty0 + pix / CT_W, x = tx0 + pix % CT_W;
-      float v = 0.0f;
-      if (y < H && x < W && c0 + ch < C) v = view_ld(p.f1, base1 + (long long)y * W + x, c0 + ch);
-      f1_s[e] = v;
-    }
-    // ---- stage f2 halo tile (optionally backwarped)
-    for (int e = t; e < hh * HALO_W * C_CH; e += CORR_THREADS) {       // halo rows >= th + 8 are never read
-      const int ch = e & (C_CH - 1), pix = e >> 5;
-      const int hx = pix % HALO_W;
-      const int y = ty0 - 4 + pix / HALO_W, x = tx0 - 4 + hx;
-      if (hx >= ((hw + 3) & ~3) + 4) { f2_s[e] = 0.0f; continue; }         // columns past the strips that exist
-      float v = 0.0f;
-      if (y >= 0 && y < H && x >= 0 && x < W && c0 + ch < C) {
-        if (!warp2) {
-          v = view_ld(p.f2, base2 + (long long)y * W + x, c0 + ch);
-        } else {
-          const long long fp = basef + (long long)y * W + x;
-          const float u = (float)x + view_ld(p.flow, fp, 0) * sxw;
-          const float w = (float)y + view_ld(p.flow, fp, 1) * syh;
-          const float fu = floorf(u), fv = floorf(w);
-          const float ax = u - fu, ay = w - fv;
-          const int xa = (int)fu, ya = (int)fv;
-          float s = 0.0f, m = 0.0f;
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const int xx = xa + (k & 1), yy = ya + (k >> 1);
-            const float wt = ((k & 1) ? ax : 1.0f - ax) * ((k >> 1) ? ay : 1.0f - ay);
-            if (xx >= 0 && xx < W && yy >= 0 && yy < H) {
-              s = fmaf(view_ld(p.f2, base2 + (long long)yy * W + xx, c0 + ch), wt, s);
-              m += wt;
-            }
-          }
-          v = (m > 0.999f) ? s : 0.0f;  // pwcnet.py:34-38
-        }
+    if (VEC) {
+      // ---- vectorised staging: one task = one pixel x 8 channels (16 / 32 bytes of global memory per load)
+      const T* b1 = reinterpret_cast<const T*>(p.f1.data) + p.f1.c_off;
+      const T* b2 = reinterpret_cast<const T*>(p.f2.data) + p.f2.c_off;
+      for (int e = t; e < th * CT_W * (C_CH / 8); e += CORR_THREADS) {      // rows >= th are never read
+        const int g = e & 3, pix = e >> 2;
+        const int y = ty0 + pix / CT_W, x = tx0 + pix % CT_W;
+        const int ch = c0 + g * 8;
+        Vec8c v = vec8_zero();
+        if (x < W && ch < C) v = vec8_ld<T>(b1 + (base1 + (long long)y * W + x) * p.f1.c_pitch + ch, C - ch);
+        vec8_sts(&f1_s[pix * C_CH + g * 8], v);
       }
-      f2_s[e] = v;
+      for (int e = t; e < hh * HALO_W * (C_CH / 8); e += CORR_THREADS) {    // halo rows >= th + 8 are never read
+        const int g = e & 3, pix = e >> 2;
+        const int y = ty0 - 4 + pix / HALO_W, x = tx0 - 4 + pix % HALO_W;
+        const int ch = c0 + g * 8;
+        Vec8c v = vec8_zero();
+        if (y >= 0 && y < H && x >= 0 && x < W && ch < C) {
+          if (!warp2) {
+            v = vec8_ld<T>(b2 + (base2 + (long long)y * W + x) * p.f2.c_pitch + ch, C - ch);
+          } else {
+            const long long fp = basef + (long long)y * W + x;
+            const float u = (float)x + view_ld(p.flow, fp, 0) * sxw;
+            const float w = (float)y + view_ld(p.flow, fp, 1) * syh;
+            const float fu = floorf(u), fv = floorf(w);
+            const float ax = u - fu, ay = w - fv;
+            const int xa = (int)fu, ya = (int)fv;
+            float m = 0.0f;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const int xx = xa + (k & 1), yy = ya + (k >> 1);
+              const float wt = ((k & 1) ? ax : 1.0f - ax) * ((k >> 1) ? ay : 1.0f - ay);
+              if (xx >= 0 && xx < W && yy >= 0 && yy < H) {
+                const Vec8c a = vec8_ld<T>(b2 + (base2 + (long long)yy * W + xx) * p.f2.c_pitch + ch, C - ch);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) v.v[i] = fmaf(a.v[i], wt, v.v[i]);
+                m += wt;
+              }
+            }
+            if (!(m > 0.999f)) v = vec8_zero();  // pwcnet.py:34-38
+          }
+        }
+        vec8_sts(&f2_s[pix * C_CH + g * 8], v);
+      }
+    } else {
+    // ---- stage f1 tile
+      for (int e = t; e < th * CT_W * C_CH; e += CORR_THREADS) {      // rows >= th are never read
+        const int ch = e & (C_CH - 1), pix = e >> 5;
+        const int y = ty0 + pix / CT_W, x = tx0 + pix % CT_W;
+        float v = 0.0f;
+        if (y < H && x < W && c0 + ch < C) v = view_ld(p.f1, base1 + (long long)y * W + x, c0 + ch);
+        f1_s[e] = v;
+      }
+      // ---- stage f2 halo tile (optionally backwarped)
+      for (int e = t; e < hh * HALO_W * C_CH; e += CORR_THREADS) {       // halo rows >= th + 8 are never read
+        const int ch = e & (C_CH - 1), pix = e >> 5;
+        const int hx = pix % HALO_W;
+        const int y = ty0 - 4 + pix / HALO_W, x = tx0 - 4 + hx;
+        if (hx >= ((hw + 3) & ~3) + 4) { f2_s[e] = 0.0f; continue; }         // columns past the strips that exist
+        float v = 0.0f;
+        if (y >= 0 && y < H && x >= 0 && x < W && c0 + ch < C) {
+          if (!warp2) {
+            v = view_ld(p.f2, base2 + (long long)y * W + x, c0 + ch);
+          } else {
+            const long long fp = basef + (long long)y * W + x;
+            const float u = (float)x + view_ld(p.flow, fp, 0) * sxw;
+            const float w = (float)y + view_ld(p.flow, fp, 1) * syh;
+            const float fu = floorf(u), fv = floorf(w);
+            const float ax = u - fu, ay = w - fv;
+            const int xa = (int)fu, ya = (int)fv;
+            float s = 0.0f, m = 0.0f;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const int xx = xa + (k & 1), yy = ya + (k >> 1);
+              const float wt = ((k & 1) ? ax : 1.0f - ax) * ((k >> 1) ? ay : 1.0f - ay);
+              if (xx >= 0 && xx < W && yy >= 0 && yy < H) {
+                s = fmaf(view_ld(p.f2, base2 + (long long)yy * W + xx, c0 + ch), wt, s);
+                m += wt;
+              }
+            }
+            v = (m > 0.999f) ? s : 0.0f;  // pwcnet.py:34-38
+          }
+        }
+        f2_s[e] = v;
+      }
     }
     __syncthreads();
 
@@ -164,17 +248,25 @@ extern "C" int dbsr_corr81(const dbsr_nhwc_t* f1, const dbsr_nhwc_t* f2, const d
                  "corr81: pair->image mapping out of range");
   else
     DBSR_REQUIRE(f1->n >= pairs && f2->n >= pairs, "corr81: not enough images");
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(corr81_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CORR_SMEM);
-    DBSR_REQUIRE(e == cudaSuccess, "corr81: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
-    attr_set = true;
-  }
   CorrParams p;
   p.f1 = make_view(f1); p.f2 = make_view(f2); p.flow = make_view(has_flow ? flow : nullptr); p.out = make_view(out);
   p.flow_scale = flow_scale; p.group = group; p.act = act;
   p.tiles_x = ceil_div(f1->w, CT_W);
   dim3 grid(p.tiles_x * ceil_div(f1->h, CT_H), pairs);
-  corr81_kernel<<<grid, CORR_THREADS, CORR_SMEM, (cudaStream_t)stream>>>(p);
+  // vectorised staging needs 8-channel groups on 16-byte (bf16) / 32-byte (fp32) boundaries in both feature maps
+  auto vec_ok = [](const dbsr_nhwc_t* v) {
+    return v->c_off % 8 == 0 && v->c_pitch % 8 == 0 && ((uintptr_t)v->data % 32) == 0;
+  };
+  const bool vec = f1->dtype == f2->dtype && vec_ok(f1) && vec_ok(f2);
+  void (*kern)(const CorrParams) = !vec ? corr81_kernel<false, float>
+                                   : (f1->dtype == DBSR_BF16 ? corr81_kernel<true, __nv_bfloat16> : corr81_kernel<true, float>);
+  static bool attr_set[3] = {false, false, false};
+  const int ki = !vec ? 0 : (f1->dtype == DBSR_BF16 ? 1 : 2);
+  if (!attr_set[ki]) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, CORR_SMEM);
+    DBSR_REQUIRE(e == cudaSuccess, "corr81: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
+    attr_set[ki] = true;
+  }
+  kern<<<grid, CORR_THREADS, CORR_SMEM, (cudaStream_t)stream>>>(p);
   return check_launch("corr81");
 }

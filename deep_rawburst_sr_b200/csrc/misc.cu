@@ -184,6 +184,55 @@ __global__ void deconv4x4s2_kernel(View x, const float* __restrict__ w, const fl
 }
 
 // -------------------------------------------------------------------------------------------------------
+// Second half of ConvTranspose2d(k=4, s=2, p=1), Cout = 2 when the channel contraction ran as a 1x1 convolution:
+//   taps[n, iy, ix, (ky*4 + kx)*2 + oc] = sum_ic x[n, iy, ix, ic] * w[ic, oc, ky, kx]        (tensor cores / conv_direct)
+//   out[n, oy, ox, oc] = b[oc] + sum over the (up to) 2x2 (ky, kx) with iy = (oy + 1 - ky) / 2, ix = (ox + 1 - kx) / 2
+// The 2-channel flow deconvolution of the same level (netUpflow) is computed directly in the same pass.
+// One thread per output pixel.
+// -------------------------------------------------------------------------------------------------------
+__global__ void deconv_col2im_kernel(View taps, const float* __restrict__ bias_t, View y_t, View flow,
+                                     const float* __restrict__ wf, const float* __restrict__ bias_f, View y_f, View y_f2) {
+  const int h = taps.h, w = taps.w, Ho = 2 * h, Wo = 2 * w;
+  const long long total = (long long)taps.n * Ho * Wo;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int n = (int)(i / ((long long)Ho * Wo));
+    const int rem = (int)(i - (long long)n * Ho * Wo);
+    const int oy = rem / Wo, ox = rem - oy * Wo;
+    float t0 = bias_t[0], t1 = bias_t[1];
+    float f0 = 0.0f, f1 = 0.0f;
+    const bool has_flow = flow.data != nullptr;
+    if (has_flow) { f0 = bias_f[0]; f1 = bias_f[1]; }
+#pragma unroll
+    for (int a = 0; a < 2; ++a) {
+      const int ky = ((oy + 1) & 1) + 2 * a;
+      const int iy2 = oy + 1 - ky;
+      if (iy2 < 0 || (iy2 >> 1) >= h) continue;
+#pragma unroll
+      for (int b = 0; b < 2; ++b) {
+        const int kx = ((ox + 1) & 1) + 2 * b;
+        const int ix2 = ox + 1 - kx;
+        if (ix2 < 0 || (ix2 >> 1) >= w) continue;
+        const long long pix = ((long long)n * h + (iy2 >> 1)) * w + (ix2 >> 1);
+        const int tap = ky * 4 + kx;
+        t0 += view_ld(taps, pix, tap * 2 + 0);
+        t1 += view_ld(taps, pix, tap * 2 + 1);
+        if (has_flow) {
+          const float u = view_ld(flow, pix, 0), v = view_ld(flow, pix, 1);
+          const float* q = wf + tap * 4;      // [ky][kx][oc][ic]
+          f0 = fmaf(u, __ldg(q + 0), fmaf(v, __ldg(q + 1), f0));
+          f1 = fmaf(u, __ldg(q + 2), fmaf(v, __ldg(q + 3), f1));
+        }
+      }
+    }
+    view_st(y_t, i, 0, t0); view_st(y_t, i, 1, t1);
+    if (has_flow) {
+      view_st(y_f, i, 0, f0); view_st(y_f, i, 1, f1);
+      if (y_f2.data) { view_st(y_f2, i, 0, f0); view_st(y_f2, i, 1, f1); }
+    }
+  }
+}
+
+// -------------------------------------------------------------------------------------------------------
 // Flow head (pwcnet.py:274-279): bilinear resize of the quarter-resolution flow to (H, W) with
 // align_corners=False, x20, x(W/Wp, H/Hp).  Output NCHW fp32 (the public `offsets`).
 // -------------------------------------------------------------------------------------------------------
@@ -390,6 +439,26 @@ extern "C" int dbsr_deconv4x4s2(const dbsr_nhwc_t* x, const float* w, const floa
   deconv4x4s2_kernel<<<(unsigned)blocks, block, 0, (cudaStream_t)stream>>>(make_view(x), w, bias, make_view(y),
                                                                             make_view(has2 ? y2 : nullptr));
   return check_launch("deconv4x4s2");
+}
+
+extern "C" int dbsr_deconv_col2im(const dbsr_nhwc_t* taps, const float* bias_t, const dbsr_nhwc_t* y_t,
+                                  const dbsr_nhwc_t* flow, const float* wf, const float* bias_f, const dbsr_nhwc_t* y_f,
+                                  const dbsr_nhwc_t* y_f2, void* stream) {
+  DBSR_REQUIRE(view_ok(taps) && bias_t && view_ok(y_t) && taps->c == 32 && y_t->c == 2 && y_t->n == taps->n &&
+                   y_t->h == 2 * taps->h && y_t->w == 2 * taps->w, "deconv_col2im: bad tap / output geometry");
+  const bool has_flow = flow && flow->data;
+  if (has_flow)
+    DBSR_REQUIRE(view_ok(flow) && wf && bias_f && view_ok(y_f) && flow->c == 2 && flow->n == taps->n && flow->h == taps->h &&
+                     flow->w == taps->w && y_f->c == 2 && y_f->n == y_t->n && y_f->h == y_t->h && y_f->w == y_t->w,
+                 "deconv_col2im: bad flow geometry");
+  const bool has2 = has_flow && y_f2 && y_f2->data;
+  if (has2) DBSR_REQUIRE(view_ok(y_f2) && y_f2->c == 2 && y_f2->n == y_t->n && y_f2->h == y_t->h && y_f2->w == y_t->w,
+                         "deconv_col2im: second flow output geometry");
+  const long long total = (long long)y_t->n * y_t->h * y_t->w;
+  deconv_col2im_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
+      make_view(taps), bias_t, make_view(y_t), make_view(has_flow ? flow : nullptr), wf, bias_f,
+      make_view(has_flow ? y_f : nullptr), make_view(has2 ? y_f2 : nullptr));
+  return check_launch("deconv_col2im");
 }
 
 extern "C" int dbsr_flow_head(const dbsr_nhwc_t* flow4, float* offsets, int32_t H, int32_t W, int32_t Hp, int32_t Wp,

@@ -195,6 +195,9 @@ class DBSREngine:
                 cm, _s, length = prev.chmap_from('o5')
                 k = f'{pre}net{lname}.netUpfeat'
                 self.D[k] = (pack_deconv(sd[k + '.weight'], cm, length), sd[k + '.bias'].float().contiguous())
+                # the same transposed conv as a 1x1 conv Cin -> 32 planes (ky, kx, oc) + a scatter (ops.deconv_col2im)
+                w1 = sd[k + '.weight'].permute(2, 3, 1, 0).reshape(32, -1, 1, 1).contiguous()
+                self._add(k + '.taps', w1, None, tc=ptc, chmap=cm, cin_buf=length)
                 k = f'{pre}net{lname}.netUpflow'
                 self.D[k] = (pack_deconv(sd[k + '.weight']), sd[k + '.bias'].float().contiguous())
         cm, _s, length = self.pwc_layouts[2].chmap_from('o5')
@@ -382,9 +385,11 @@ class DBSREngine:
             else:
                 upflow = self._buf(ws, f'upflow{lvl}', pairs, h, w, 2, torch.float32)
                 wf, bf = self.D[f'{pre}net{lname}.netUpflow']
-                self._run('deconv', ops.deconv4x4s2, prev_flow, wf, bf, cat.slice(lay.off['upflow'], 2), upflow)
-                wt, bt = self.D[f'{pre}net{lname}.netUpfeat']
-                self._run('deconv', ops.deconv4x4s2, prev_cat, wt, bt, cat.slice(lay.off['upfeat'], 2))
+                _wt, bt = self.D[f'{pre}net{lname}.netUpfeat']
+                taps = self._buf(ws, f'taps{lvl}', pairs, prev_cat.h, prev_cat.w, 32, torch.float32)
+                self._conv(f'{pre}net{lname}.netUpfeat.taps', prev_cat, taps, ACT_NONE)
+                self._run('deconv', ops.deconv_col2im, taps, bt, cat.slice(lay.off['upfeat'], 2), prev_flow, wf, bf,
+                          cat.slice(lay.off['upflow'], 2), upflow)
                 self._run('copy', ops.copy_channels, f1, cat.slice(lay.off['f1'], lay.sizes['f1']), group, src_group, 0)
                 self._run('corr81', ops.corr81, f1, f2, vol, pairs, group, flow=upflow, flow_scale=PWC_BACKWARP[lvl],
                           act=ACT_LRELU)

@@ -119,6 +119,20 @@ def deconv4x4s2(x: Act, w: torch.Tensor, bias: torch.Tensor, y: Act, y2: Optiona
     return y
 
 
+def deconv_col2im(taps: Act, bias_t: torch.Tensor, y_t: Act, flow: Optional[Act] = None, wf: Optional[torch.Tensor] = None,
+                  bias_f: Optional[torch.Tensor] = None, y_f: Optional[Act] = None, y_f2: Optional[Act] = None) -> Act:
+    """scatter half of ConvTranspose2d(4, 2, 1) after a 1x1 conv produced the 32 (tap, oc) planes (+ the 2-channel
+    flow deconvolution of the same level when `flow` is given)"""
+    tv, yv = taps.view(), y_t.view()
+    fv = flow.view() if flow is not None else _NULL_VIEW
+    yfv = y_f.view() if y_f is not None else _NULL_VIEW
+    yf2v = y_f2.view() if y_f2 is not None else _NULL_VIEW
+    _lib.check(_lib.load_library().dbsr_deconv_col2im(ctypes.byref(tv), bias_t.data_ptr(), ctypes.byref(yv), ctypes.byref(fv),
+                                                      _ptr(wf), _ptr(bias_f), ctypes.byref(yfv), ctypes.byref(yf2v),
+                                                      _stream()), 'dbsr_deconv_col2im')
+    return y_t
+
+
 def corr81(f1: Act, f2: Act, out: Act, pairs: int, group: int = 0, flow: Optional[Act] = None, flow_scale: float = 0.0,
            act: int = ACT_NONE) -> Act:
     a, b, o = f1.view(), f2.view(), out.view()

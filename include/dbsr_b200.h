@@ -109,6 +109,15 @@ int dbsr_conv2d_tc_geometry(int32_t cin, int32_t cout, int32_t* ck, int32_t* kpa
  *   w: fp32 [4][4][2][Cin]; y, y2: [n, 2h, 2w, 2] views (y2 optional second destination, data NULL ok) */
 int dbsr_deconv4x4s2(const dbsr_nhwc_t* x, const float* w, const float* bias, const dbsr_nhwc_t* y,
                      const dbsr_nhwc_t* y2, void* stream);
+/* The same transposed convolution split for wide inputs (netUpfeat, Cin = 529 .. 565): the channel contraction runs
+ * as a 1x1 convolution Cin -> 32 (dbsr_conv2d_tc / dbsr_conv2d_direct, output channel (ky*4 + kx)*2 + oc) and this
+ * entry scatters the taps: y_t[n, oy, ox, oc] = bias_t[oc] + sum of the <= 4 taps that land on (oy, ox).
+ *   taps: [n, h, w, 32];  y_t: [n, 2h, 2w, 2].
+ *   flow != NULL (data != NULL): additionally netUpflow (pwcnet.py:119) of the 2-channel flow [n, h, w, 2] with
+ *   wf fp32 [4][4][2][2] ([ky][kx][oc][ic]) and bias_f, written to y_f and (optional) y_f2.                  */
+int dbsr_deconv_col2im(const dbsr_nhwc_t* taps, const float* bias_t, const dbsr_nhwc_t* y_t, const dbsr_nhwc_t* flow,
+                       const float* wf, const float* bias_f, const dbsr_nhwc_t* y_f, const dbsr_nhwc_t* y_f2,
+                       void* stream);
 
 /* -------------------------------------------------------------------------------------------------- */
 /* PWC-Net cost volume: replaces correlation.FunctionCorrelation (correlation.py:280-330, 3 launches +  */

@@ -119,6 +119,36 @@ def test_deconv4x4s2(dev, cin, h, w):
     assert (y2.to_nchw().cpu() - ref).abs().max() < 1e-4
 
 
+@pytest.mark.parametrize('cin,h,w', [(529, 1, 1), (661, 2, 3), (597, 8, 8), (565, 16, 16)])
+def test_deconv_as_conv1x1_plus_col2im(dev, cin, h, w):
+    """netUpfeat as a 1x1 conv to 32 (ky, kx, oc) planes + dbsr_deconv_col2im, with netUpflow fused into the scatter"""
+    from deep_rawburst_sr_b200 import ops
+    from deep_rawburst_sr_b200.engine import pack_deconv, pack_direct
+    g = _gen(cin + 7)
+    x = torch.randn(3, cin, h, w, generator=g)
+    wt = torch.randn(cin, 2, 4, 4, generator=g) / (cin * 4) ** 0.5
+    bt = torch.randn(2, generator=g)
+    fl = torch.randn(3, 2, h, w, generator=g) * 3
+    wf = torch.randn(2, 2, 4, 4, generator=g) / 3
+    bf = torch.randn(2, generator=g)
+    ref_t = O.deconv4x4s2(x, wt, bt)
+    ref_f = O.deconv4x4s2(fl, wf, bf)
+    w1 = wt.permute(2, 3, 1, 0).reshape(32, cin, 1, 1).contiguous()
+    taps = ops.Act.empty(3, h, w, 32, torch.float32, dev)
+    ops.conv2d(_act_from(x, dev), pack_direct(w1.to(dev)), None, taps, 1, 1, 1, ops.ACT_NONE)
+    y_t = ops.Act.empty(3, 2 * h, 2 * w, 16, torch.float32, dev, zero=True).slice(8, 2)
+    y_f = ops.Act.empty(3, 2 * h, 2 * w, 8, torch.float32, dev, zero=True).slice(2, 2)
+    y_f2 = ops.Act.empty(3, 2 * h, 2 * w, 2, torch.float32, dev)
+    ops.deconv_col2im(taps, bt.to(dev), y_t, _act_from(fl, dev), pack_deconv(wf.to(dev)), bf.to(dev), y_f, y_f2)
+    assert (y_t.to_nchw().cpu() - ref_t).abs().max() < 1e-4
+    assert (y_f.to_nchw().cpu() - ref_f).abs().max() < 1e-4
+    assert (y_f2.to_nchw().cpu() - ref_f).abs().max() < 1e-4
+    # without the flow half
+    y_t2 = ops.Act.empty(3, 2 * h, 2 * w, 2, torch.float32, dev)
+    ops.deconv_col2im(taps, bt.to(dev), y_t2)
+    assert (y_t2.to_nchw().cpu() - ref_t).abs().max() < 1e-4
+
+
 CORR_SHAPES = [(196, 1, 1), (128, 2, 2), (96, 4, 4), (64, 8, 8), (32, 16, 16), (32, 48, 48), (6, 5, 7), (64, 20, 33),
                (196, 3, 3), (128, 6, 6)]
 
@@ -137,6 +167,33 @@ def test_corr81_plain(dev, c, h, w):
     ref_l = O.lrelu(ref)
     ops.corr81(_act_from(f1, dev), _act_from(f2, dev), out, pairs=3, group=0, act=ops.ACT_LRELU)
     assert (out.to_nchw().cpu() - ref_l).abs().max() < 2e-5
+
+
+@pytest.mark.parametrize('c,h,w,mag', [(32, 16, 16, 3.0), (196, 1, 1, 0.0), (128, 2, 2, 1.0), (64, 8, 8, 2.0), (100, 5, 9, 2.0)])
+def test_corr81_bf16_vectorised_staging(dev, c, h, w, mag):
+    """bf16 feature maps in 8-channel-aligned buffers (the layout the engine uses): vectorised halo staging, channel
+    tails (C % 8 != 0) masked, with and without the fused backwarp"""
+    from deep_rawburst_sr_b200 import ops
+    g = _gen(c * 3 + h)
+    pitch = (c + 7) // 8 * 8
+    f1 = torch.randn(3, c, h, w, generator=g).bfloat16().float()
+    f2 = torch.randn(3, c, h, w, generator=g).bfloat16().float()
+
+    def act_bf16(t):
+        buf = torch.full((3, h, w, pitch), 7.0, dtype=torch.bfloat16, device=dev)     # poison in the pad channels
+        buf[..., :c] = t.permute(0, 2, 3, 1).to(dev).bfloat16()
+        return ops.Act(buf).slice(0, c)
+
+    out = ops.Act.empty(3, h, w, 88, torch.float32, dev, zero=True).slice(0, 81)
+    ops.corr81(act_bf16(f1), act_bf16(f2), out, pairs=3, group=0)
+    assert (out.to_nchw().cpu() - O.correlation81(f1, f2)).abs().max() < 2e-5
+    if mag > 0:
+        flow = (torch.rand(3, 2, h, w, generator=g) * 2 - 1) * mag
+        ref = O.lrelu(O.correlation81(f1, O.backwarp(f2, flow * 1.25)))
+        ops.corr81(act_bf16(f1), act_bf16(f2), out, pairs=3, group=0, flow=_act_from(flow, dev), flow_scale=1.25,
+                   act=ops.ACT_LRELU)
+        err = (out.to_nchw().cpu() - ref).abs()
+        assert (err > 5e-5).any(dim=1).float().mean() < 0.01, float(err.max())
 
 
 def test_corr81_golden_reference_vector(dev, golden_dir):
