@@ -50,6 +50,7 @@ PROTOTYPES = {
     'dbsr_conv2d_tc_supported': (_I, [_PC]),
     'dbsr_conv2d_tc_geometry': (_I, [_I, _I, ctypes.POINTER(_I), ctypes.POINTER(_I), ctypes.POINTER(_I),
                                      ctypes.POINTER(_I)]),
+    'dbsr_space_to_depth2': (_I, [_PV, _PV, _VP]),
     'dbsr_deconv4x4s2': (_I, [_PV, _VP, _VP, _PV, _PV, _VP]),
     'dbsr_deconv_col2im': (_I, [_PV, _VP, _PV, _PV, _VP, _VP, _PV, _PV, _VP]),
     'dbsr_corr81': (_I, [_PV, _PV, _PV, _F, _PV, _I, _I, _I, _VP]),

@@ -74,6 +74,29 @@ __global__ void copy_channels_kernel(View src, View dst, int group, int src_grou
 }
 
 // -------------------------------------------------------------------------------------------------------
+// Space to depth (2x2): y[n, Y, X, (p*2 + q)*C + c] = x[n, 2Y + p, 2X + q, c]  (zero beyond the image: odd sizes).
+// A 3x3 / stride-2 / pad-1 convolution of x is then a 3x3 / stride-1 / pad-1 convolution of y whose taps
+// (ky', kx') in {0, 1}^2 carry the weights (engine.pack_s2d_weight) -- which is how the PWC-Net extractor's
+// stride-2 layers (pwcnet.py:49-97) reach the tensor-core kernel.  Converts dtype on the way.
+// -------------------------------------------------------------------------------------------------------
+__global__ void space_to_depth2_kernel(View x, View y) {
+  const int C = x.c, C4 = 4 * C;
+  const long long total = (long long)y.n * y.h * y.w * C4;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int k = (int)(i % C4);
+    const long long pix = i / C4;
+    const int X = (int)(pix % y.w);
+    const long long t = pix / y.w;
+    const int Y = (int)(t % y.h), n = (int)(t / y.h);
+    const int pq = k / C, c = k - pq * C;
+    const int sy = 2 * Y + (pq >> 1), sx = 2 * X + (pq & 1);
+    float v = 0.0f;
+    if (sy < x.h && sx < x.w) v = view_ld(x, ((long long)n * x.h + sy) * x.w + sx, c);
+    view_st(y, pix, k, v);
+  }
+}
+
+// -------------------------------------------------------------------------------------------------------
 // Burst preparation.  One thread per output pixel of either destination.
 //   enc_in: channels-last copy of the packed RAW frame (zero-padded channels)
 //   pwc_in: RGGB->RGB (encoders.py:52) then bilinear resize to (Hp, Wp), align_corners=False
@@ -413,6 +436,14 @@ extern "C" int dbsr_copy_channels(const dbsr_nhwc_t* src, const dbsr_nhwc_t* dst
   copy_channels_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(make_view(src), make_view(dst), group,
                                                                                 src_group, src_first);
   return check_launch("copy_channels");
+}
+
+extern "C" int dbsr_space_to_depth2(const dbsr_nhwc_t* x, const dbsr_nhwc_t* y, void* stream) {
+  DBSR_REQUIRE(view_ok(x) && view_ok(y) && y->n == x->n && y->h == (x->h + 1) / 2 && y->w == (x->w + 1) / 2 &&
+                   y->c == 4 * x->c, "space_to_depth2: output must be [n, ceil(h/2), ceil(w/2), 4c]");
+  const long long total = (long long)y->n * y->h * y->w * y->c;
+  space_to_depth2_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(make_view(x), make_view(y));
+  return check_launch("space_to_depth2");
 }
 
 extern "C" int dbsr_prep_burst(const float* burst, int32_t frames, int32_t H, int32_t W, const dbsr_nhwc_t* enc_in,

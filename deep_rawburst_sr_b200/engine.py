@@ -102,6 +102,21 @@ def permute_shuffle_rows(t: torch.Tensor, r: int) -> torch.Tensor:
     return t.reshape(c, r, r, *t.shape[1:]).permute(1, 2, 0, *range(3, t.dim() + 2)).reshape(t.shape).contiguous()
 
 
+def pack_s2d_weight(w: torch.Tensor) -> torch.Tensor:
+    """3x3 / stride-2 / pad-1 conv weight [Cout, C, 3, 3] -> the equivalent 3x3 / stride-1 / pad-1 weight
+    [Cout, 4C, 3, 3] over the space-to-depth input (channel (p*2 + q)*C + c = x[2Y + p, 2X + q, c]):
+    input row 2Y + dy is s2d row Y - 1, parity 1 for dy = -1; row Y, parity dy for dy = 0, 1 (same along x)."""
+    cout, c = w.shape[0], w.shape[1]
+    out = torch.zeros((cout, 4 * c, 3, 3), dtype=w.dtype, device=w.device)
+    pos = {-1: (0, 1), 0: (1, 0), 1: (1, 1)}      # d -> (tap index in the s2d kernel, parity)
+    for dy in (-1, 0, 1):
+        ky, p = pos[dy]
+        for dx in (-1, 0, 1):
+            kx, q = pos[dx]
+            out[:, (p * 2 + q) * c:(p * 2 + q + 1) * c, ky, kx] = w[:, :, dy + 1, dx + 1]
+    return out
+
+
 def pack_deconv(w: torch.Tensor, chmap=None, cin_buf: Optional[int] = None) -> torch.Tensor:
     """ConvTranspose2d weight [Cin, 2, 4, 4] -> fp32 [4, 4, 2, Cin_buf]."""
     cin = w.shape[0]
@@ -181,6 +196,8 @@ class DBSREngine:
             for idx in (0, 2, 4):
                 k = f'{pre}netExtractor.net{name}.{idx}'
                 self._add(k, sd[k + '.weight'], sd[k + '.bias'], tc=ptc and idx != 0)   # idx 0 is the stride-2 conv
+                if idx == 0 and ptc:     # tensor-core form of the stride-2 conv: stride 1 over the space-to-depth input
+                    self._add(k + '.s2d', pack_s2d_weight(sd[k + '.weight']), sd[k + '.bias'], tc=True)
         self.pwc_layouts = {l: PwcLayout(l) for l in (2, 3, 4, 5, 6)}
         segs = ['V', 'o1', 'o2', 'o3', 'o4', 'o5']   # input of netOne..netSix starts at this segment
         for lvl in (6, 5, 4, 3, 2):
@@ -262,8 +279,10 @@ class DBSREngine:
     # helpers
     # ------------------------------------------------------------------------------------------------
     def _conv(self, key: str, x: Act, y: Act, act: int, stride: int = 1, dilation: int = 1,
-              residual: Optional[Act] = None, force_direct: bool = False, no_bias: bool = False) -> Act:
+              residual: Optional[Act] = None, force_direct: bool = False, no_bias: bool = False,
+              real_cin: Optional[int] = None) -> Act:
         cw = self.W[key]
+        cin_alg = cw.cin if real_cin is None else real_cin       # algorithmic input channels for the FLOP count
         bias, bias_tc = (None, None) if no_bias else (cw.bias, cw.bias_tc)
         use_tc = (cw.tc is not None and not force_direct and x.dtype == torch.bfloat16 and stride == 1)
         if use_tc:
@@ -271,10 +290,10 @@ class DBSREngine:
         self.launches += 1
         fam = 'conv_tc' if use_tc else 'conv_direct'
         ho, wo = (y.h, y.w) if cw.shuffle_r <= 1 else (y.h // cw.shuffle_r, y.w // cw.shuffle_r)
-        self.flops[fam] = self.flops.get(fam, 0) + 2 * x.n * ho * wo * cw.cout * cw.cin * cw.ksize * cw.ksize
+        self.flops[fam] = self.flops.get(fam, 0) + 2 * x.n * ho * wo * cw.cout * cin_alg * cw.ksize * cw.ksize
         ev = self._tic(fam)
         if ev is not None and self.layer_events is not None:
-            fl = 2 * x.n * ho * wo * cw.cout * cw.cin * cw.ksize * cw.ksize
+            fl = 2 * x.n * ho * wo * cw.cout * cin_alg * cw.ksize * cw.ksize
             self.layer_events.setdefault(key, []).append((self.timers[fam][-1], fl, fam, (x.n, x.h, x.w, cw.cin, cw.cout)))
         if use_tc:
             ops.conv2d(x, cw.tc, bias_tc, y, cw.ksize, stride, dilation, act, residual, cw.shuffle_r, tensor_core=True)
@@ -358,7 +377,13 @@ class DBSREngine:
             t1 = self._buf(ws, f'ext{l}_a', n, h, w, c, self.pwc_dtype)
             t2 = self._buf(ws, f'ext{l}_b', n, h, w, c, self.pwc_dtype)
             f = self._buf(ws, f'ext{l}_f', n, h, w, c, self.pwc_dtype)
-            self._conv(f'{pre}netExtractor.net{name}.0', x, t1, ACT_LRELU, stride=2)
+            k0 = f'{pre}netExtractor.net{name}.0'
+            if (k0 + '.s2d') in self.W:
+                xs = self._buf(ws, f'ext{l}_s2d', n, h, w, 4 * x.c, torch.bfloat16)
+                self._run('copy', ops.space_to_depth2, x, xs)
+                self._conv(k0 + '.s2d', xs, t1, ACT_LRELU, real_cin=x.c)
+            else:
+                self._conv(k0, x, t1, ACT_LRELU, stride=2)
             self._conv(f'{pre}netExtractor.net{name}.2', t1, t2, ACT_LRELU)
             self._conv(f'{pre}netExtractor.net{name}.4', t2, f, ACT_LRELU)
             feats.append(f)

@@ -111,6 +111,12 @@ def conv2d_tc_geometry(cin: int, cout: int):
     return a.value, b.value, c.value, d.value
 
 
+def space_to_depth2(x: Act, y: Act) -> Act:
+    xv, yv = x.view(), y.view()
+    _lib.check(_lib.load_library().dbsr_space_to_depth2(ctypes.byref(xv), ctypes.byref(yv), _stream()), 'dbsr_space_to_depth2')
+    return y
+
+
 def deconv4x4s2(x: Act, w: torch.Tensor, bias: torch.Tensor, y: Act, y2: Optional[Act] = None) -> Act:
     xv, yv = x.view(), y.view()
     y2v = y2.view() if y2 is not None else _NULL_VIEW

@@ -105,6 +105,11 @@ int dbsr_conv2d_tc_supported(const dbsr_conv_t* p);
 int dbsr_conv2d_tc_geometry(int32_t cin, int32_t cout, int32_t* ck, int32_t* kpad, int32_t* n_tile,
                             int32_t* cout_pad);
 
+/* y[n, Y, X, (p*2 + q)*C + c] = x[n, 2Y + p, 2X + q, c], zero beyond the image; dtype converted to y's.
+ *   Turns the stride-2 3x3 convs of the PWC-Net extractor (pwcnet.py:49-97) into stride-1 3x3 convs over 4C channels
+ *   that dbsr_conv2d_tc covers (weights repacked on the host: taps (ky', kx') in {0,1}^2, the other five are zero). */
+int dbsr_space_to_depth2(const dbsr_nhwc_t* x, const dbsr_nhwc_t* y, void* stream);
+
 /* ConvTranspose2d(k=4, s=2, p=1), Cout = 2 (pwcnet.py:119-120 netUpflow / netUpfeat).
  *   w: fp32 [4][4][2][Cin]; y, y2: [n, 2h, 2w, 2] views (y2 optional second destination, data NULL ok) */
 int dbsr_deconv4x4s2(const dbsr_nhwc_t* x, const float* w, const float* bias, const dbsr_nhwc_t* y,

@@ -149,6 +149,27 @@ def test_deconv_as_conv1x1_plus_col2im(dev, cin, h, w):
     assert (y_t2.to_nchw().cpu() - ref_t).abs().max() < 1e-4
 
 
+@pytest.mark.parametrize('c,co,h,w', [(3, 16, 64, 64), (16, 32, 32, 32), (64, 96, 8, 8), (128, 196, 2, 2), (8, 16, 7, 9)])
+def test_stride2_conv_as_space_to_depth_plus_tc(dev, c, co, h, w):
+    """PWC extractor stride-2 layers: dbsr_space_to_depth2 (fp32 -> bf16) + the tcgen05 conv with the repacked weight"""
+    from deep_rawburst_sr_b200 import ops
+    from deep_rawburst_sr_b200.engine import pack_s2d_weight, pack_tc
+    g = _gen(c + co)
+    x = torch.randn(3, c, h, w, generator=g).bfloat16().float()
+    wt = (torch.randn(co, c, 3, 3, generator=g) / (9 * c) ** 0.5).bfloat16().float()
+    b = torch.randn(co, generator=g)
+    ref = O.lrelu(F.conv2d(x, wt, b, stride=2, padding=1))
+    ho, wo = (h + 1) // 2, (w + 1) // 2
+    xs = ops.Act.empty(3, ho, wo, (4 * c + 7) // 8 * 8, torch.bfloat16, dev, zero=True).slice(0, 4 * c)
+    ops.space_to_depth2(_act_from(x, dev), xs)
+    ref_s = F.pad(x, (0, wo * 2 - w, 0, ho * 2 - h)).view(3, c, ho, 2, wo, 2).permute(0, 3, 5, 1, 2, 4).reshape(3, 4 * c, ho, wo)
+    assert (xs.to_nchw().cpu() - ref_s).abs().max() == 0
+    y = ops.Act.empty(3, ho, wo, (co + 7) // 8 * 8, torch.bfloat16, dev, zero=True).slice(0, co)
+    ops.conv2d(xs, pack_tc(pack_s2d_weight(wt).to(dev)), b.to(dev), y, 3, 1, 1, ops.ACT_LRELU, tensor_core=True)
+    got = y.to_nchw().cpu()
+    assert (got - ref).abs().max() < 2e-2 * max(1.0, float(ref.abs().max()))
+
+
 CORR_SHAPES = [(196, 1, 1), (128, 2, 2), (96, 4, 4), (64, 8, 8), (32, 16, 16), (32, 48, 48), (6, 5, 7), (64, 20, 33),
                (196, 3, 3), (128, 6, 6)]
 

@@ -91,3 +91,21 @@ def test_icnr_matches_reference_structure():
     k = ICNR(torch.zeros(2048, 64, 1, 1), 8)
     assert tuple(k.shape) == (2048, 64, 1, 1)
     assert torch.equal(k[0], k[63]) and torch.equal(k[64], k[127]) and not torch.equal(k[0], k[64])
+
+
+def test_pack_s2d_weight_is_the_stride2_conv():
+    """3x3 / stride 2 / pad 1 == 3x3 / stride 1 / pad 1 over the space-to-depth input with the repacked weight
+    (how the PWC extractor's stride-2 layers, pwcnet.py:49-97, reach the tensor-core kernel); odd sizes included"""
+    import torch
+    import torch.nn.functional as F
+    from deep_rawburst_sr_b200.engine import pack_s2d_weight
+    g = torch.Generator().manual_seed(5)
+    for (c, co, h, w) in [(3, 16, 8, 8), (16, 32, 6, 10), (5, 7, 7, 9), (8, 4, 2, 2), (4, 4, 1, 3)]:
+        x = torch.randn(2, c, h, w, generator=g)
+        wt = torch.randn(co, c, 3, 3, generator=g)
+        ref = F.conv2d(x, wt, stride=2, padding=1)
+        hp, wp = (h + 1) // 2 * 2, (w + 1) // 2 * 2
+        xp = F.pad(x, (0, wp - w, 0, hp - h))
+        xs = xp.view(2, c, hp // 2, 2, wp // 2, 2).permute(0, 3, 5, 1, 2, 4).reshape(2, 4 * c, hp // 2, wp // 2)
+        got = F.conv2d(xs, pack_s2d_weight(wt), stride=1, padding=1)
+        assert got.shape == ref.shape and (got - ref).abs().max() < 1e-4
