@@ -167,6 +167,8 @@ def main():
     # ---- device-resident throughput ("value"): K forwards, inputs already in HBM
     for _ in range(args.warmup):
         net(dev_in)
+    for _ in range(2):      # untimed: the CUDA graph of this shape is captured on the 2nd call; make sure replays have run
+        net(dev_in)
     barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:

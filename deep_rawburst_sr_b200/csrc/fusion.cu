@@ -375,38 +375,181 @@ softmax_wsum8_kernel(View feat, View logits, const float* __restrict__ offsets, 
 }
 
 
-// upsampling.py:59-65: per-channel 3x3 blur with zero padding, 8 channels per thread
+// ---------------------------------------------------------------------------------------------------------
+// Asynchronously prefetched variant (bf16 embeddings and logits, warp on the fly): the kernel above is bound by memory
+// latency -- 6 warps per scheduler each waiting for 5 dependent-free 16-byte loads per frame -- so here every thread
+// keeps WS_STAGES frames of its five loads (logits + 4 bilinear taps) in flight as cp.async copies into its own slots
+// of a shared-memory ring.  A thread only ever reads the slots it filled itself: no block-level barrier in the loop,
+// only cp.async.wait_group.  Out-of-image taps are zero-filled by the copy (src-size 0), which is grid_sample's
+// zero padding, so the weights need no mask.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int WS_STAGES = 3;
+constexpr int WS_ASYNC_SMEM = WS_STAGES * 5 * 256 * 16;
+__device__ __forceinline__ void cp_async_16(uint32_t dst, const void* src, uint32_t bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ Vec8 unpack_bf16x8(const uint4& q) {
+  Vec8 r;
+  r.v[0] = __uint_as_float(q.x << 16); r.v[1] = __uint_as_float(q.x & 0xFFFF0000u);
+  r.v[2] = __uint_as_float(q.y << 16); r.v[3] = __uint_as_float(q.y & 0xFFFF0000u);
+  r.v[4] = __uint_as_float(q.z << 16); r.v[5] = __uint_as_float(q.z & 0xFFFF0000u);
+  r.v[6] = __uint_as_float(q.w << 16); r.v[7] = __uint_as_float(q.w & 0xFFFF0000u);
+  return r;
+}
+template <typename TO>
+__global__ void __launch_bounds__(256, 3)
+softmax_wsum8_async_kernel(View feat, View logits, const float* __restrict__ offsets, View fused, int frames) {
+  extern __shared__ __align__(16) uint4 ring[];        // [WS_STAGES][5][256]
+  __shared__ float2 offs_s[32][16];
+  const int H = fused.h, W = fused.w;
+  const int HW = H * W;
+  const __nv_bfloat16* fbase = reinterpret_cast<const __nv_bfloat16*>(feat.data) + feat.c_off;
+  const __nv_bfloat16* lbase = reinterpret_cast<const __nv_bfloat16*>(logits.data) + logits.c_off;
+  TO* obase = reinterpret_cast<TO*>(fused.data) + fused.c_off;
+  const int tiles_x = (W + WS_TW - 1) / WS_TW;
+  const int tid = threadIdx.x;
+  const int g = tid & 7, px = (tid >> 3) & 7, py = tid >> 6;
+  const int b = blockIdx.z;
+  const int ch_raw = blockIdx.y * 64 + g * 8;
+  const int ch = min(ch_raw, fused.c - 8);   // clamped for the loads; the store is predicated on `live`
+  const int y_raw = (blockIdx.x / tiles_x) * WS_TH + py, x_raw = (blockIdx.x % tiles_x) * WS_TW + px;
+  const bool live = y_raw < H && x_raw < W && ch_raw < fused.c;
+  const int y = min(y_raw, H - 1), x = min(x_raw, W - 1);
+  const int rem = y * W + x;
+  // flows of all frames at this pixel, shared by the 8 channel-group threads of the pixel (all in one warp)
+#pragma unroll
+  for (int q = 0; q < 2; ++q) {
+    const int n = g + 8 * q;
+    if (n + 1 < frames) {
+      const long long pr = (long long)b * (frames - 1) + n;
+      offs_s[tid >> 3][n] = make_float2(__ldg(offsets + (pr * 2 + 0) * HW + rem), __ldg(offsets + (pr * 2 + 1) * HW + rem));
+    }
+  }
+  __syncwarp();
+  const uint32_t ring_s = (uint32_t)__cvta_generic_to_shared(ring) + (uint32_t)tid * 16u;
+  const float fxp = (float)x, fyp = (float)y;
+  auto issue = [&](int n) {       // frame n (1 .. frames-1) -> stage (n-1) % WS_STAGES
+    const uint32_t dst = ring_s + (uint32_t)(((n - 1) % WS_STAGES) * 5 * 256 * 16);
+    const long long img = (long long)b * frames + n;
+    cp_async_16(dst, lbase + (img * HW + rem) * logits.c_pitch + ch, 16u);
+    const float2 o2 = offs_s[tid >> 3][n - 1];
+    const float fu = floorf(fxp + o2.x), fv = floorf(fyp + o2.y);
+    const int x0 = (int)fu, y0 = (int)fv;
+    const __nv_bfloat16* ib = fbase + img * HW * feat.c_pitch + ch;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int xx = x0 + (k & 1), yy = y0 + (k >> 1);
+      const bool ok = xx >= 0 && xx < W && yy >= 0 && yy < H;
+      cp_async_16(dst + (uint32_t)((1 + k) * 256 * 16), ok ? (const void*)(ib + (long long)(yy * W + xx) * feat.c_pitch) : (const void*)fbase,
+                  ok ? 16u : 0u);
+    }
+  };
+#pragma unroll
+  for (int n = 1; n <= WS_STAGES; ++n) {
+    if (n < frames) issue(n);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  }
+  // reference frame (never warped): plain loads while the ring fills
+  float m[8], s[8], acc[8];
+  {
+    const long long img = (long long)b * frames;
+    const Vec8 l = ld8<__nv_bfloat16>(lbase + (img * HW + rem) * logits.c_pitch + ch);
+    const Vec8 a = ld8<__nv_bfloat16>(fbase + (img * HW + rem) * feat.c_pitch + ch);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { m[k] = l.v[k]; s[k] = 1.0f; acc[k] = a.v[k]; }
+  }
+  for (int n = 1; n < frames; ++n) {
+    asm volatile("cp.async.wait_group %0;" ::"n"(WS_STAGES - 1) : "memory");
+    const uint4* st = ring + ((n - 1) % WS_STAGES) * 5 * 256 + tid;
+    const Vec8 l = unpack_bf16x8(st[0]);
+    const float2 o2 = offs_s[tid >> 3][n - 1];
+    const float u = fxp + o2.x, v = fyp + o2.y;
+    const float ax = u - floorf(u), ay = v - floorf(v);
+    Vec8 a;
+    {
+      const Vec8 t0 = unpack_bf16x8(st[256]), t1 = unpack_bf16x8(st[512]);
+      const float w0 = (1.0f - ax) * (1.0f - ay), w1 = ax * (1.0f - ay);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) a.v[k] = fmaf(t1.v[k], w1, t0.v[k] * w0);
+      const Vec8 t2 = unpack_bf16x8(st[768]), t3 = unpack_bf16x8(st[1024]);
+      const float w2 = (1.0f - ax) * ay, w3 = ax * ay;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) a.v[k] = fmaf(t3.v[k], w3, fmaf(t2.v[k], w2, a.v[k]));
+    }
+    // the slots of this stage are consumed (values are in registers): refill it with frame n + WS_STAGES
+    if (n + WS_STAGES < frames) issue(n + WS_STAGES);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    // online softmax with ONE exponential per element (see softmax_wsum8_kernel)
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const float d = l.v[k] - m[k];
+      const float ex = __expf(-fabsf(d));
+      const bool up = d > 0.0f;
+      const float sc = up ? ex : 1.0f;
+      const float e = up ? 1.0f : ex;
+      s[k] = fmaf(s[k], sc, e);
+      acc[k] = fmaf(acc[k], sc, a.v[k] * e);
+      m[k] = up ? l.v[k] : m[k];
+    }
+  }
+  Vec8 r;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) r.v[k] = acc[k] / s[k];
+  if (live) st8<TO>(obase + ((long long)b * HW + rem) * fused.c_pitch + ch, r);
+}
+
+
+// upsampling.py:59-65: per-channel 3x3 blur with zero padding, 8 channels per thread.
+// Row-sliding variant: a thread owns (x, 8 channels) and walks BLUR_ROWS output rows; every input row is loaded once
+// per thread (3 x-taps, the neighbours are the adjacent threads' lines -> L1) and feeds the three output rows it
+// touches through rolling partial sums, instead of 9 loads per output (whose vertical neighbours miss L1 and made the
+// kernel L2-bound).   out[y] = h0[y-1] + h1[y] + h2[y+1],  hk[r] = sum_dx K[k][dx] * in[r][x+dx-1]
+constexpr int BLUR_ROWS = 16;
 template <typename T>
-__global__ void __launch_bounds__(256) blur3x3_v8_kernel(View x, View y, float k0, float k1, float k2, float k3, float k4,
-                                                         float k5, float k6, float k7, float k8) {
+__global__ void __launch_bounds__(256) blur3x3_rows_kernel(View x, View y, float k0, float k1, float k2, float k3, float k4,
+                                                           float k5, float k6, float k7, float k8) {
   const float kk[9] = {k0, k1, k2, k3, k4, k5, k6, k7, k8};
   const int H = x.h, W = x.w, C8 = x.c >> 3;
-  const long long total = (long long)x.n * H * W * C8;
-  const T* xb = reinterpret_cast<const T*>(x.data) + x.c_off;
-  T* yb = reinterpret_cast<T*>(y.data) + y.c_off;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    const int c8 = (int)(i % C8);
-    const long long pix = i / C8;
-    const int n = (int)(pix / ((long long)H * W));
-    const int rem = (int)(pix - (long long)n * H * W);
-    const int py = rem / W, px = rem - py * W;
-    Vec8 acc;
+  const int col = blockIdx.x * blockDim.x + threadIdx.x;       // (pixel column, channel group)
+  if (col >= W * C8) return;
+  const int px = col / C8, c8 = col - px * C8;
+  const int y0 = blockIdx.y * BLUR_ROWS, n = blockIdx.z;
+  const T* xb = reinterpret_cast<const T*>(x.data) + x.c_off + c8 * 8;
+  T* yb = reinterpret_cast<T*>(y.data) + y.c_off + c8 * 8;
+  Vec8 a0, a1;          // a0: output row r-1 so far (h0[r-2] + h1[r-1]); a1: output row r so far (h0[r-1])
 #pragma unroll
-    for (int k = 0; k < 8; ++k) acc.v[k] = 0.0f;
+  for (int k = 0; k < 8; ++k) { a0.v[k] = 0.0f; a1.v[k] = 0.0f; }
+  const int r_end = min(y0 + BLUR_ROWS, H);
+#pragma unroll 3
+  for (int r = y0 - 1; r <= r_end; ++r) {
+    Vec8 h0, h1, h2;
 #pragma unroll
-    for (int dy = -1; dy <= 1; ++dy)
+    for (int k = 0; k < 8; ++k) { h0.v[k] = 0.0f; h1.v[k] = 0.0f; h2.v[k] = 0.0f; }
+    if (r >= 0 && r < H) {
+      const T* row = xb + ((long long)n * H + r) * W * x.c_pitch;
 #pragma unroll
-      for (int dx = -1; dx <= 1; ++dx) {
-        const int yy = py + dy, xx = px + dx;
-        if (yy >= 0 && yy < H && xx >= 0 && xx < W) {
-          const Vec8 a = ld8<T>(xb + (((long long)n * H + yy) * W + xx) * x.c_pitch + c8 * 8);
-          const float w = kk[(dy + 1) * 3 + (dx + 1)];
+      for (int dx = 0; dx < 3; ++dx) {
+        const int xx = px + dx - 1;
+        if (xx >= 0 && xx < W) {
+          const Vec8 a = ld8<T>(row + (long long)xx * x.c_pitch);
 #pragma unroll
-          for (int k = 0; k < 8; ++k) acc.v[k] = fmaf(a.v[k], w, acc.v[k]);
+          for (int k = 0; k < 8; ++k) {
+            h0.v[k] = fmaf(a.v[k], kk[dx], h0.v[k]);          // row r is the row ABOVE output r+1: kernel row 0
+            h1.v[k] = fmaf(a.v[k], kk[3 + dx], h1.v[k]);      // ... the centre row of output r
+            h2.v[k] = fmaf(a.v[k], kk[6 + dx], h2.v[k]);      // ... the row BELOW output r-1: kernel row 2
+          }
         }
       }
-    st8<T>(yb + pix * y.c_pitch + c8 * 8, acc);
+    }
+    // output row r-1 is complete once row r has contributed
+    if (r - 1 >= y0 && r - 1 < r_end) {
+      Vec8 o;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) o.v[k] = a0.v[k] + h2.v[k];
+      st8<T>(yb + (((long long)n * H + (r - 1)) * W + px) * y.c_pitch, o);
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { a0.v[k] = a1.v[k] + h1.v[k]; a1.v[k] = h0.v[k]; }
   }
 }
 
@@ -466,7 +609,16 @@ extern "C" int dbsr_softmax_wsum(const dbsr_nhwc_t* feat, const dbsr_nhwc_t* log
   const int g = grid_cap(total, 256);
   if (v8) {
     dim3 grid8(((fused->w + WS_TW - 1) / WS_TW) * ((fused->h + WS_TH - 1) / WS_TH), (fused->c + 63) / 64, fused->n);
-    if (key == 0) softmax_wsum8_kernel<float, float, float><<<grid8, 256, 0, st>>>(f, l, offsets, o, frames);
+    if (key == 7 && offsets != nullptr && frames >= 2 && frames <= 17) {
+      static bool attr_set = false;
+      if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(softmax_wsum8_async_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, WS_ASYNC_SMEM);
+        DBSR_REQUIRE(e == cudaSuccess, "softmax_wsum: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
+        attr_set = true;
+      }
+      softmax_wsum8_async_kernel<__nv_bfloat16><<<grid8, 256, WS_ASYNC_SMEM, st>>>(f, l, offsets, o, frames);
+    }
+    else if (key == 0) softmax_wsum8_kernel<float, float, float><<<grid8, 256, 0, st>>>(f, l, offsets, o, frames);
     else if (key == 7) softmax_wsum8_kernel<__nv_bfloat16, __nv_bfloat16, __nv_bfloat16><<<grid8, 256, 0, st>>>(f, l, offsets, o, frames);
     else softmax_wsum8_kernel<__nv_bfloat16, float, __nv_bfloat16><<<grid8, 256, 0, st>>>(f, l, offsets, o, frames);
   } else
@@ -509,12 +661,12 @@ extern "C" int dbsr_blur3x3(const dbsr_nhwc_t* x, const dbsr_nhwc_t* y, const fl
   DBSR_REQUIRE(view_ok(x) && view_ok(y) && k9 && x->n == y->n && x->h == y->h && x->w == y->w && x->c == y->c &&
                    x->dtype == y->dtype, "blur3x3: bad arguments");
   DBSR_REQUIRE(vec8_ok(x) && vec8_ok(y), "blur3x3: channels must be multiples of 8 and 16-byte aligned");
-  const long long total = (long long)x->n * x->h * x->w * (x->c / 8);
-  const int g = grid_cap(total, 256);
   cudaStream_t st = (cudaStream_t)stream;
+  DBSR_REQUIRE(x->n <= 65535, "blur3x3: more than 65535 images");
+  dim3 grid((unsigned)ceil_div((long long)x->w * (x->c / 8), 256), (unsigned)ceil_div(x->h, BLUR_ROWS), (unsigned)x->n);
   if (x->dtype == DBSR_F32)
-    blur3x3_v8_kernel<float><<<g, 256, 0, st>>>(make_view(x), make_view(y), k9[0], k9[1], k9[2], k9[3], k9[4], k9[5], k9[6], k9[7], k9[8]);
+    blur3x3_rows_kernel<float><<<grid, 256, 0, st>>>(make_view(x), make_view(y), k9[0], k9[1], k9[2], k9[3], k9[4], k9[5], k9[6], k9[7], k9[8]);
   else
-    blur3x3_v8_kernel<__nv_bfloat16><<<g, 256, 0, st>>>(make_view(x), make_view(y), k9[0], k9[1], k9[2], k9[3], k9[4], k9[5], k9[6], k9[7], k9[8]);
+    blur3x3_rows_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(make_view(x), make_view(y), k9[0], k9[1], k9[2], k9[3], k9[4], k9[5], k9[6], k9[7], k9[8]);
   return check_launch("blur3x3");
 }
