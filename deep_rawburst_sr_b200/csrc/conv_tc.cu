@@ -104,6 +104,10 @@ __device__ __forceinline__ void cp_async16(void* dst_smem, const void* src, uint
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
+// programmatic dependent launch: the kernel may start while its predecessor in the stream is still draining; everything
+// before this call must only touch on-chip state
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
@@ -597,6 +601,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
     if (p.res_chunks) { tma_prefetch_desc(&tmap_r); tma_prefetch_desc(&tmap_i); }
   }
   if (warp == WARP_MMA) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+  // Programmatic dependent launch: everything above touches only on-chip state and the kernel parameters, so it may run
+  // while the preceding kernel of the stream is still draining; all global-memory traffic (activations, residual, y,
+  // and -- because a caller may have produced them just before -- weights and bias) comes after this wait.
+  griddep_wait();
   if (p.bias_smem && warp < 8)
     for (int i = threadIdx.x; i < p.cout_pad; i += 256) bias_tab[i] = p.bias ? __ldg(p.bias + i) : 0.0f;
   tc_fence_before();
@@ -1117,7 +1125,17 @@ static int launch_tc(const CUtensorMap& mx, const CUtensorMap& mw, const CUtenso
   }
   int grid = (int)(p.total_items < num_sms ? p.total_items : num_sms);
   if (const char* e = getenv("DBSR_TC_GRID")) { const int g = atoi(e); if (g > 0 && g < grid) grid = g; }   // debug knob
-  conv_tc_kernel<CK, RESIDENT><<<grid, TC_THREADS, smem, st>>>(mx, mw, mr, mi, p);
+  // programmatic dependent launch: CTAs may be scheduled (barrier init, tensor-map prefetch, TMEM allocation) as soon as
+  // the SMs of the preceding kernel drain; the kernel calls griddepcontrol.wait before its first global access
+  static const bool pdl = getenv("DBSR_TC_NO_PDL") == nullptr;
+  cudaLaunchConfig_t lc = {};
+  lc.gridDim = dim3((unsigned)grid); lc.blockDim = dim3(TC_THREADS); lc.dynamicSmemBytes = (size_t)smem; lc.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  lc.attrs = attr; lc.numAttrs = pdl ? 1 : 0;
+  cudaError_t le = cudaLaunchKernelEx(&lc, conv_tc_kernel<CK, RESIDENT>, mx, mw, mr, mi, p);
+  if (le != cudaSuccess) { set_error("conv2d_tc: launch failed: %s", cudaGetErrorString(le)); return 2; }
   return check_launch("conv2d_tc");
 }
 
