@@ -76,6 +76,24 @@ __device__ __forceinline__ void view_st(const View& v, long long pix, int ch, fl
   else reinterpret_cast<__nv_bfloat16*>(v.data)[off] = __float2bfloat16_rn(val);
 }
 
+// ---- programmatic dependent launch ---------------------------------------------------------------------
+// Kernels launched through launch_pdl may be scheduled while the preceding kernel of the stream is still draining
+// (hides launch latency between the ~140 dependent launches of one forward); they call griddep_wait() before their
+// first global-memory access.  griddep_wait() is a no-op for a normally launched kernel.
+#ifdef __CUDACC__
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+template <typename... KArgs, typename... Args>
+inline void launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t lc = {};
+  lc.gridDim = grid; lc.blockDim = block; lc.dynamicSmemBytes = smem; lc.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  lc.attrs = attr; lc.numAttrs = 1;
+  cudaLaunchKernelEx(&lc, kern, static_cast<KArgs>(args)...);     // errors surface through check_launch()
+}
+#endif
+
 inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
 
 }  // namespace dbsr

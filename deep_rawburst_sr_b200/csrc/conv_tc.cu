@@ -104,10 +104,6 @@ __device__ __forceinline__ void cp_async16(void* dst_smem, const void* src, uint
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
-// programmatic dependent launch: the kernel may start while its predecessor in the stream is still draining; everything
-// before this call must only touch on-chip state
-__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
-
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 

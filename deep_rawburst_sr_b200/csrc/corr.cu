@@ -64,6 +64,7 @@ struct CorrParams {
 
 template <bool VEC, typename T>
 __global__ void __launch_bounds__(CORR_THREADS) corr81_kernel(const CorrParams p) {
+  griddep_wait();
   extern __shared__ __align__(16) float smem[];
   float* f2_s = smem;                                // [HALO_H*HALO_W][32]
   float* f1_s = smem + HALO_H * HALO_W * C_CH;       // [CT_H*CT_W][32]
@@ -267,6 +268,6 @@ extern "C" int dbsr_corr81(const dbsr_nhwc_t* f1, const dbsr_nhwc_t* f2, const d
     DBSR_REQUIRE(e == cudaSuccess, "corr81: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
     attr_set[ki] = true;
   }
-  kern<<<grid, CORR_THREADS, CORR_SMEM, (cudaStream_t)stream>>>(p);
+  launch_pdl(kern, grid, dim3(CORR_THREADS), (size_t)CORR_SMEM, (cudaStream_t)stream, p);
   return check_launch("corr81");
 }

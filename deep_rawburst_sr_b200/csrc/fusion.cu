@@ -243,6 +243,7 @@ __device__ __forceinline__ Vec8 gather8(const T* img_base, int c_pitch, const Ta
 template <typename TQ, typename TO>
 __global__ void __launch_bounds__(256)
 warp_proj_kernel(View q, const float* __restrict__ bias, const float* __restrict__ offsets, View wp_in, int frames) {
+  griddep_wait();
   const int H = q.h, W = q.w, C = q.c, C8 = C >> 3;
   const int HW = H * W;
   const long long total = (long long)q.n * HW * C8;
@@ -399,6 +400,7 @@ __device__ __forceinline__ Vec8 unpack_bf16x8(const uint4& q) {
 template <typename TO>
 __global__ void __launch_bounds__(256, 3)
 softmax_wsum8_async_kernel(View feat, View logits, const float* __restrict__ offsets, View fused, int frames) {
+  griddep_wait();
   extern __shared__ __align__(16) uint4 ring[];        // [WS_STAGES][5][256]
   __shared__ float2 offs_s[32][16];
   const int H = fused.h, W = fused.w;
@@ -508,6 +510,7 @@ constexpr int BLUR_ROWS = 16;
 template <typename T>
 __global__ void __launch_bounds__(256) blur3x3_rows_kernel(View x, View y, float k0, float k1, float k2, float k3, float k4,
                                                            float k5, float k6, float k7, float k8) {
+  griddep_wait();
   const float kk[9] = {k0, k1, k2, k3, k4, k5, k6, k7, k8};
   const int H = x.h, W = x.w, C8 = x.c >> 3;
   const int col = blockIdx.x * blockDim.x + threadIdx.x;       // (pixel column, channel group)
@@ -616,7 +619,7 @@ extern "C" int dbsr_softmax_wsum(const dbsr_nhwc_t* feat, const dbsr_nhwc_t* log
         DBSR_REQUIRE(e == cudaSuccess, "softmax_wsum: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
         attr_set = true;
       }
-      softmax_wsum8_async_kernel<__nv_bfloat16><<<grid8, 256, WS_ASYNC_SMEM, st>>>(f, l, offsets, o, frames);
+      launch_pdl(softmax_wsum8_async_kernel<__nv_bfloat16>, dim3(grid8), dim3(256), WS_ASYNC_SMEM, st, f, l, offsets, o, frames);
     }
     else if (key == 0) softmax_wsum8_kernel<float, float, float><<<grid8, 256, 0, st>>>(f, l, offsets, o, frames);
     else if (key == 7) softmax_wsum8_kernel<__nv_bfloat16, __nv_bfloat16, __nv_bfloat16><<<grid8, 256, 0, st>>>(f, l, offsets, o, frames);
@@ -652,8 +655,8 @@ extern "C" int dbsr_warp_proj(const dbsr_nhwc_t* q, const float* bias, const flo
   const long long total = (long long)q->n * q->h * q->w * (q->c / 8);
   const int g = grid_cap(total, 256);
   cudaStream_t st = (cudaStream_t)stream;
-  if (q->dtype == DBSR_F32) warp_proj_kernel<float, float><<<g, 256, 0, st>>>(make_view(q), bias, offsets, make_view(wp_in), frames);
-  else warp_proj_kernel<__nv_bfloat16, __nv_bfloat16><<<g, 256, 0, st>>>(make_view(q), bias, offsets, make_view(wp_in), frames);
+  if (q->dtype == DBSR_F32) launch_pdl(warp_proj_kernel<float, float>, dim3(g), dim3(256), 0, st, make_view(q), bias, offsets, make_view(wp_in), frames);
+  else launch_pdl(warp_proj_kernel<__nv_bfloat16, __nv_bfloat16>, dim3(g), dim3(256), 0, st, make_view(q), bias, offsets, make_view(wp_in), frames);
   return check_launch("warp_proj");
 }
 
@@ -665,8 +668,8 @@ extern "C" int dbsr_blur3x3(const dbsr_nhwc_t* x, const dbsr_nhwc_t* y, const fl
   DBSR_REQUIRE(x->n <= 65535, "blur3x3: more than 65535 images");
   dim3 grid((unsigned)ceil_div((long long)x->w * (x->c / 8), 256), (unsigned)ceil_div(x->h, BLUR_ROWS), (unsigned)x->n);
   if (x->dtype == DBSR_F32)
-    blur3x3_rows_kernel<float><<<grid, 256, 0, st>>>(make_view(x), make_view(y), k9[0], k9[1], k9[2], k9[3], k9[4], k9[5], k9[6], k9[7], k9[8]);
+    launch_pdl(blur3x3_rows_kernel<float>, dim3(grid), dim3(256), 0, st, make_view(x), make_view(y), k9[0], k9[1], k9[2], k9[3], k9[4], k9[5], k9[6], k9[7], k9[8]);
   else
-    blur3x3_rows_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(make_view(x), make_view(y), k9[0], k9[1], k9[2], k9[3], k9[4], k9[5], k9[6], k9[7], k9[8]);
+    launch_pdl(blur3x3_rows_kernel<__nv_bfloat16>, dim3(grid), dim3(256), 0, st, make_view(x), make_view(y), k9[0], k9[1], k9[2], k9[3], k9[4], k9[5], k9[6], k9[7], k9[8]);
   return check_launch("blur3x3");
 }

@@ -60,6 +60,7 @@ __global__ void nhwc_to_nchw_kernel(View src, float* __restrict__ dst) {
 }
 
 __global__ void copy_channels_kernel(View src, View dst, int group, int src_group, int src_first) {
+  griddep_wait();
   const long long total = (long long)dst.n * dst.h * dst.w * dst.c;
   const int HW = dst.h * dst.w;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
@@ -80,6 +81,7 @@ __global__ void copy_channels_kernel(View src, View dst, int group, int src_grou
 // stride-2 layers (pwcnet.py:49-97) reach the tensor-core kernel.  Converts dtype on the way.
 // -------------------------------------------------------------------------------------------------------
 __global__ void space_to_depth2_kernel(View x, View y) {
+  griddep_wait();
   const int C = x.c, C4 = 4 * C;
   const long long total = (long long)y.n * y.h * y.w * C4;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -95,6 +97,26 @@ __global__ void space_to_depth2_kernel(View x, View y) {
     view_st(y, pix, k, v);
   }
 }
+// bf16 -> bf16 with C % 8 == 0 and 16-byte aligned views: one thread moves 8 channels (16 bytes)
+__global__ void space_to_depth2_v8_kernel(View x, View y) {
+  griddep_wait();
+  const int C8 = x.c >> 3, G = 4 * C8;
+  const long long total = (long long)y.n * y.h * y.w * G;
+  const __nv_bfloat16* xb = reinterpret_cast<const __nv_bfloat16*>(x.data) + x.c_off;
+  __nv_bfloat16* yb = reinterpret_cast<__nv_bfloat16*>(y.data) + y.c_off;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int k = (int)(i % G);
+    const long long pix = i / G;
+    const int X = (int)(pix % y.w);
+    const long long t = pix / y.w;
+    const int Y = (int)(t % y.h), n = (int)(t / y.h);
+    const int pq = k / C8, c8 = k - pq * C8;
+    const int sy = 2 * Y + (pq >> 1), sx = 2 * X + (pq & 1);
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (sy < x.h && sx < x.w) v = __ldg(reinterpret_cast<const uint4*>(xb + (((long long)n * x.h + sy) * x.w + sx) * x.c_pitch + c8 * 8));
+    *reinterpret_cast<uint4*>(yb + pix * y.c_pitch + pq * x.c + c8 * 8) = v;
+  }
+}
 
 // -------------------------------------------------------------------------------------------------------
 // Burst preparation.  One thread per output pixel of either destination.
@@ -103,6 +125,7 @@ __global__ void space_to_depth2_kernel(View x, View y) {
 //           (pwcnet.py:266-271): src = (dst + 0.5) * in/out - 0.5, clamped at 0, neighbour clamped.
 // -------------------------------------------------------------------------------------------------------
 __global__ void prep_burst_kernel(const float* __restrict__ burst, int H, int W, View enc_in, View pwc_in) {
+  griddep_wait();
   const int HW = H * W;
   const long long n_enc = (long long)enc_in.n * HW;
   const long long n_pwc = (long long)pwc_in.n * pwc_in.h * pwc_in.w;
@@ -215,6 +238,7 @@ __global__ void deconv4x4s2_kernel(View x, const float* __restrict__ w, const fl
 // -------------------------------------------------------------------------------------------------------
 __global__ void deconv_col2im_kernel(View taps, const float* __restrict__ bias_t, View y_t, View flow,
                                      const float* __restrict__ wf, const float* __restrict__ bias_f, View y_f, View y_f2) {
+  griddep_wait();
   const int h = taps.h, w = taps.w, Ho = 2 * h, Wo = 2 * w;
   const long long total = (long long)taps.n * Ho * Wo;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -260,6 +284,7 @@ __global__ void deconv_col2im_kernel(View taps, const float* __restrict__ bias_t
 // align_corners=False, x20, x(W/Wp, H/Hp).  Output NCHW fp32 (the public `offsets`).
 // -------------------------------------------------------------------------------------------------------
 __global__ void flow_head_kernel(View f4, float* __restrict__ offsets, int H, int W, float mulx, float muly) {
+  griddep_wait();
   const long long total = (long long)f4.n * H * W;
   const int h4 = f4.h, w4 = f4.w;
   const float sy = (float)h4 / (float)H, sx = (float)w4 / (float)W;
@@ -288,6 +313,7 @@ __global__ void flow_head_kernel(View f4, float* __restrict__ offsets, int H, in
 
 // merging.py:91-105: zeros for the reference frame, floor-mod for the others
 __global__ void offsets_mod_kernel(const float* __restrict__ offsets, View out, int frames, float modulo) {
+  griddep_wait();
   const int HW = out.h * out.w;
   const long long total = (long long)out.n * HW;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
@@ -337,6 +363,7 @@ __global__ void build_wp_input_kernel(View proj, View wp_in, int frames) {
 template <typename T, bool VEC>
 __global__ void __launch_bounds__(256) predictor_kernel(View x, const float* __restrict__ w, const float* __restrict__ bias,
                                                         int cout, float* __restrict__ pred) {
+  griddep_wait();
   extern __shared__ float ws[];  // [cout][C] + [cout]
   const int C = x.c;
   for (int i = threadIdx.x; i < cout * C; i += blockDim.x) ws[i] = w[i];
@@ -433,7 +460,7 @@ extern "C" int dbsr_copy_channels(const dbsr_nhwc_t* src, const dbsr_nhwc_t* dst
   else
     DBSR_REQUIRE(src->n == dst->n, "copy_channels: image count mismatch");
   const long long total = (long long)dst->n * dst->h * dst->w * dst->c;
-  copy_channels_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(make_view(src), make_view(dst), group,
+  launch_pdl(copy_channels_kernel, dim3(grid_for(total, 256)), dim3(256), 0, (cudaStream_t)stream, make_view(src), make_view(dst), group,
                                                                                 src_group, src_first);
   return check_launch("copy_channels");
 }
@@ -442,7 +469,10 @@ extern "C" int dbsr_space_to_depth2(const dbsr_nhwc_t* x, const dbsr_nhwc_t* y, 
   DBSR_REQUIRE(view_ok(x) && view_ok(y) && y->n == x->n && y->h == (x->h + 1) / 2 && y->w == (x->w + 1) / 2 &&
                    y->c == 4 * x->c, "space_to_depth2: output must be [n, ceil(h/2), ceil(w/2), 4c]");
   const long long total = (long long)y->n * y->h * y->w * y->c;
-  space_to_depth2_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(make_view(x), make_view(y));
+  const bool v8 = x->dtype == DBSR_BF16 && y->dtype == DBSR_BF16 && x->c % 8 == 0 && x->c_off % 8 == 0 && x->c_pitch % 8 == 0 &&
+                  y->c_off % 8 == 0 && y->c_pitch % 8 == 0 && ((uintptr_t)x->data % 16) == 0 && ((uintptr_t)y->data % 16) == 0;
+  if (v8) launch_pdl(space_to_depth2_v8_kernel, dim3(grid_for(total / 8, 256)), dim3(256), 0, (cudaStream_t)stream, make_view(x), make_view(y));
+  else launch_pdl(space_to_depth2_kernel, dim3(grid_for(total, 256)), dim3(256), 0, (cudaStream_t)stream, make_view(x), make_view(y));
   return check_launch("space_to_depth2");
 }
 
@@ -452,7 +482,7 @@ extern "C" int dbsr_prep_burst(const float* burst, int32_t frames, int32_t H, in
   DBSR_REQUIRE(enc_in->n == frames && pwc_in->n == frames && enc_in->h == H && enc_in->w == W && enc_in->c >= 4 &&
                    pwc_in->c >= 3, "prep_burst: geometry mismatch");
   const long long total = (long long)frames * H * W + (long long)frames * pwc_in->h * pwc_in->w;
-  prep_burst_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(burst, H, W, make_view(enc_in),
+  launch_pdl(prep_burst_kernel, dim3(grid_for(total, 256)), dim3(256), 0, (cudaStream_t)stream, burst, H, W, make_view(enc_in),
                                                                              make_view(pwc_in));
   return check_launch("prep_burst");
 }
@@ -486,7 +516,7 @@ extern "C" int dbsr_deconv_col2im(const dbsr_nhwc_t* taps, const float* bias_t, 
   if (has2) DBSR_REQUIRE(view_ok(y_f2) && y_f2->c == 2 && y_f2->n == y_t->n && y_f2->h == y_t->h && y_f2->w == y_t->w,
                          "deconv_col2im: second flow output geometry");
   const long long total = (long long)y_t->n * y_t->h * y_t->w;
-  deconv_col2im_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
+  launch_pdl(deconv_col2im_kernel, dim3(grid_for(total, 256)), dim3(256), 0, (cudaStream_t)stream, 
       make_view(taps), bias_t, make_view(y_t), make_view(has_flow ? flow : nullptr), wf, bias_f,
       make_view(has_flow ? y_f : nullptr), make_view(has2 ? y_f2 : nullptr));
   return check_launch("deconv_col2im");
@@ -496,7 +526,7 @@ extern "C" int dbsr_flow_head(const dbsr_nhwc_t* flow4, float* offsets, int32_t 
                               void* stream) {
   DBSR_REQUIRE(view_ok(flow4) && offsets && flow4->c == 2, "flow_head: bad arguments");
   const long long total = (long long)flow4->n * H * W;
-  flow_head_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(make_view(flow4), offsets, H, W,
+  launch_pdl(flow_head_kernel, dim3(grid_for(total, 256)), dim3(256), 0, (cudaStream_t)stream, make_view(flow4), offsets, H, W,
                                                                             (float)W / (float)Wp, (float)H / (float)Hp);
   return check_launch("flow_head");
 }
@@ -506,7 +536,7 @@ extern "C" int dbsr_offsets_mod(const float* offsets, const dbsr_nhwc_t* out, in
   DBSR_REQUIRE(offsets && view_ok(out) && out->n == bursts * frames && out->c >= 2 && frames >= 2,
                "offsets_mod: bad arguments");
   const long long total = (long long)out->n * out->h * out->w;
-  offsets_mod_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(offsets, make_view(out), frames, modulo);
+  launch_pdl(offsets_mod_kernel, dim3(grid_for(total, 256)), dim3(256), 0, (cudaStream_t)stream, offsets, make_view(out), frames, modulo);
   return check_launch("offsets_mod");
 }
 
@@ -530,11 +560,11 @@ extern "C" int dbsr_predictor(const dbsr_nhwc_t* x, const float* w, const float*
   const int g = grid_for(total, 256) * 4;   // grid_for caps at 16 blocks/SM worth; one thread per pixel here
   cudaStream_t st = (cudaStream_t)stream;
   if (x->dtype == DBSR_BF16) {
-    if (vec) predictor_kernel<__nv_bfloat16, true><<<g, 256, smem, st>>>(make_view(x), w, bias, cout, pred);
-    else predictor_kernel<__nv_bfloat16, false><<<g, 256, smem, st>>>(make_view(x), w, bias, cout, pred);
+    if (vec) launch_pdl(predictor_kernel<__nv_bfloat16, true>, dim3(g), dim3(256), smem, st, make_view(x), w, bias, cout, pred);
+    else launch_pdl(predictor_kernel<__nv_bfloat16, false>, dim3(g), dim3(256), smem, st, make_view(x), w, bias, cout, pred);
   } else {
-    if (vec) predictor_kernel<float, true><<<g, 256, smem, st>>>(make_view(x), w, bias, cout, pred);
-    else predictor_kernel<float, false><<<g, 256, smem, st>>>(make_view(x), w, bias, cout, pred);
+    if (vec) launch_pdl(predictor_kernel<float, true>, dim3(g), dim3(256), smem, st, make_view(x), w, bias, cout, pred);
+    else launch_pdl(predictor_kernel<float, false>, dim3(g), dim3(256), smem, st, make_view(x), w, bias, cout, pred);
   }
   return check_launch("predictor");
 }

@@ -164,6 +164,11 @@ def test_stride2_conv_as_space_to_depth_plus_tc(dev, c, co, h, w):
     ops.space_to_depth2(_act_from(x, dev), xs)
     ref_s = F.pad(x, (0, wo * 2 - w, 0, ho * 2 - h)).view(3, c, ho, 2, wo, 2).permute(0, 3, 5, 1, 2, 4).reshape(3, 4 * c, ho, wo)
     assert (xs.to_nchw().cpu() - ref_s).abs().max() == 0
+    if c % 8 == 0:      # bf16 -> bf16, 16-byte vector path
+        xb = ops.Act(x.permute(0, 2, 3, 1).contiguous().to(dev).bfloat16())
+        xs2 = ops.Act.empty(3, ho, wo, 4 * c + 8, torch.bfloat16, dev, zero=True).slice(8, 4 * c)
+        ops.space_to_depth2(xb, xs2)
+        assert (xs2.to_nchw().cpu() - ref_s).abs().max() == 0
     y = ops.Act.empty(3, ho, wo, (co + 7) // 8 * 8, torch.bfloat16, dev, zero=True).slice(0, co)
     ops.conv2d(xs, pack_tc(pack_s2d_weight(wt).to(dev)), b.to(dev), y, 3, 1, 1, ops.ACT_LRELU, tensor_core=True)
     got = y.to_nchw().cpu()
