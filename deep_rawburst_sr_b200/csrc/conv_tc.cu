@@ -1101,6 +1101,19 @@ static int tc_plan(const dbsr_conv_t* c, TcConfig* cfg, bool set_err) {
 #undef TC_REQ
 }
 
+// A 3x3 "same" convolution of a 1x1 map only ever sees its centre tap (the other eight read zero padding): run it as
+// the 1x1 convolution with that tap's weight tile (PWC-Net level 6 at 48^2 / 64^2 inputs: 9 launches per forward).
+static dbsr_conv_t centre_tap_form(const dbsr_conv_t* c) {
+  dbsr_conv_t cc = *c;
+  if (c->ksize == 3 && c->x.h == 1 && c->x.w == 1 && c->w && c->shuffle_r <= 1 && c->x.c > 0 && c->y.c > 0) {
+    int ck, kpad, nt, cpad;
+    tc_geometry(c->x.c, c->y.c, &ck, &kpad, &nt, &cpad);
+    cc.ksize = 1; cc.dilation = 1;
+    cc.w = reinterpret_cast<const __nv_bfloat16*>(c->w) + (size_t)4 * cpad * kpad;      // packed [tap][cout_pad][kpad]
+  }
+  return cc;
+}
+
 template <int CK, bool RESIDENT>
 static int launch_tc(const CUtensorMap& mx, const CUtensorMap& mw, const CUtensorMap& mr, const CUtensorMap& mi,
                      const ConvTcParams& p, int smem, cudaStream_t st) {
@@ -1150,11 +1163,16 @@ extern "C" int dbsr_conv2d_tc_geometry(int32_t cin, int32_t cout, int32_t* ck, i
 
 extern "C" int dbsr_conv2d_tc_supported(const dbsr_conv_t* c) {
   TcConfig cfg;
-  return tc_plan(c, &cfg, false) == 0 ? 1 : 0;
+  if (!c) return 0;
+  const dbsr_conv_t cc = centre_tap_form(c);
+  return tc_plan(&cc, &cfg, false) == 0 ? 1 : 0;
 }
 
-extern "C" int dbsr_conv2d_tc(const dbsr_conv_t* c, void* stream) {
+extern "C" int dbsr_conv2d_tc(const dbsr_conv_t* c_in, void* stream) {
   TcConfig cfg;
+  DBSR_REQUIRE(c_in != nullptr, "conv2d_tc: null descriptor");
+  const dbsr_conv_t cc = centre_tap_form(c_in);
+  const dbsr_conv_t* c = &cc;
   if (tc_plan(c, &cfg, true)) return 1;
   EncodeTiledFn encode = get_encode();
   DBSR_REQUIRE(encode != nullptr, "conv2d_tc: cuTensorMapEncodeTiled entry point not available");

@@ -229,6 +229,88 @@ __global__ void __launch_bounds__(CORR_THREADS) corr81_kernel(const CorrParams p
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Small maps (H*W <= 64: pyramid levels 6..3 of the 48^2 .. 128^2 configs).  The tiled kernel above gives a 1x1 .. 8x8 map
+// one 8x16 tile of which a handful of threads own real pixels (9 threads for a 1x1 map: a serial latency chain).  Here
+// one CTA holds both whole maps of a pair in shared memory as [pixel][C] fp32 (the second one backwarped while it is
+// staged) and spreads the H*W*81 outputs over the threads: thread -> (pixel p, displacement d), dot product over C.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int CORR_SMALL_THREADS = 256;
+template <typename T>
+__global__ void __launch_bounds__(CORR_SMALL_THREADS) corr81_small_kernel(const CorrParams p) {
+  griddep_wait();
+  extern __shared__ __align__(16) float smem[];
+  const int H = p.f1.h, W = p.f1.w, C = p.f1.c, HW = H * W;
+  const int Cp = ((C + 7) & ~7) + 4;                 // row pitch in floats: 16-byte aligned, rows 4 banks apart
+  float* f1_s = smem;
+  float* f2_s = smem + HW * Cp;
+  const int t = threadIdx.x, pair = blockIdx.x;
+  int i1 = pair, i2 = pair;
+  if (p.group > 0) {
+    const int b = pair / p.group;
+    i1 = b * (p.group + 1);
+    i2 = i1 + 1 + (pair - b * p.group);
+  }
+  const long long base1 = (long long)i1 * HW, base2 = (long long)i2 * HW, basef = (long long)pair * HW;
+  const bool warp2 = p.flow.data != nullptr;
+  const float sxw = warp2 ? p.flow_scale * (float)W / (float)(W - 1) : 0.0f;
+  const float syh = warp2 ? p.flow_scale * (float)H / (float)(H - 1) : 0.0f;
+  const T* b1 = reinterpret_cast<const T*>(p.f1.data) + p.f1.c_off;
+  const T* b2 = reinterpret_cast<const T*>(p.f2.data) + p.f2.c_off;
+  const int G = (C + 7) >> 3;
+  for (int e = t; e < HW * G; e += CORR_SMALL_THREADS) {
+    const int g = e % G, pix = e / G;
+    const int ch = g * 8;
+    vec8_sts(&f1_s[pix * Cp + ch], vec8_ld<T>(b1 + (base1 + pix) * p.f1.c_pitch + ch, C - ch));
+    Vec8c v = vec8_zero();
+    if (!warp2) {
+      v = vec8_ld<T>(b2 + (base2 + pix) * p.f2.c_pitch + ch, C - ch);
+    } else {
+      const int y = pix / W, x = pix - y * W;
+      const float u = (float)x + view_ld(p.flow, basef + pix, 0) * sxw;
+      const float w = (float)y + view_ld(p.flow, basef + pix, 1) * syh;
+      const float fu = floorf(u), fv = floorf(w);
+      const float ax = u - fu, ay = w - fv;
+      const int xa = (int)fu, ya = (int)fv;
+      float m = 0.0f;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int xx = xa + (k & 1), yy = ya + (k >> 1);
+        const float wt = ((k & 1) ? ax : 1.0f - ax) * ((k >> 1) ? ay : 1.0f - ay);
+        if (xx >= 0 && xx < W && yy >= 0 && yy < H) {
+          const Vec8c a = vec8_ld<T>(b2 + (base2 + (long long)yy * W + xx) * p.f2.c_pitch + ch, C - ch);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) v.v[i] = fmaf(a.v[i], wt, v.v[i]);
+          m += wt;
+        }
+      }
+      if (!(m > 0.999f)) v = vec8_zero();  // pwcnet.py:34-38
+    }
+    vec8_sts(&f2_s[pix * Cp + ch], v);
+  }
+  __syncthreads();
+  const int C8 = G * 8;
+  const float invC = 1.0f / (float)C;
+  (void)invC;
+  for (int e = t; e < HW * 81; e += CORR_SMALL_THREADS) {
+    const int pix = e / 81, d = e - pix * 81;
+    const int y = pix / W, x = pix - y * W;
+    const int yy = y + d / 9 - 4, xx = x + d % 9 - 4;
+    float acc = 0.0f;
+    if (yy >= 0 && yy < H && xx >= 0 && xx < W) {
+      const float4* a = reinterpret_cast<const float4*>(&f1_s[pix * Cp]);
+      const float4* b = reinterpret_cast<const float4*>(&f2_s[(yy * W + xx) * Cp]);
+      float s0 = 0.0f, s1 = 0.0f, s2 = 0.0f, s3 = 0.0f;
+      for (int c4 = 0; c4 < C8 / 4; ++c4) {
+        const float4 u = a[c4], v = b[c4];
+        s0 = fmaf(u.x, v.x, s0); s1 = fmaf(u.y, v.y, s1); s2 = fmaf(u.z, v.z, s2); s3 = fmaf(u.w, v.w, s3);
+      }
+      acc = (s0 + s1) + (s2 + s3);
+    }
+    view_st(p.out, basef + pix, d, apply_act(acc / (float)C, p.act));
+  }
+}
+
 }  // namespace dbsr
 
 using namespace dbsr;
@@ -259,6 +341,21 @@ extern "C" int dbsr_corr81(const dbsr_nhwc_t* f1, const dbsr_nhwc_t* f2, const d
     return v->c_off % 8 == 0 && v->c_pitch % 8 == 0 && ((uintptr_t)v->data % 32) == 0;
   };
   const bool vec = f1->dtype == f2->dtype && vec_ok(f1) && vec_ok(f2);
+  // small maps: both maps of a pair in shared memory, outputs spread over the threads
+  const int cp_small = ((f1->c + 7) & ~7) + 4;
+  const size_t small_smem = (size_t)2 * f1->h * f1->w * cp_small * sizeof(float);
+  if (vec && f1->h * f1->w <= 64 && small_smem <= 160 * 1024) {
+    void (*ks)(const CorrParams) = f1->dtype == DBSR_BF16 ? corr81_small_kernel<__nv_bfloat16> : corr81_small_kernel<float>;
+    static size_t configured[2] = {0, 0};
+    const int si = f1->dtype == DBSR_BF16 ? 0 : 1;
+    if (small_smem > 48 * 1024 && small_smem > configured[si]) {
+      cudaError_t e = cudaFuncSetAttribute(ks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)small_smem);
+      DBSR_REQUIRE(e == cudaSuccess, "corr81: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
+      configured[si] = small_smem;
+    }
+    launch_pdl(ks, dim3((unsigned)pairs), dim3(CORR_SMALL_THREADS), small_smem, (cudaStream_t)stream, p);
+    return check_launch("corr81");
+  }
   void (*kern)(const CorrParams) = !vec ? corr81_kernel<false, float>
                                    : (f1->dtype == DBSR_BF16 ? corr81_kernel<true, __nv_bfloat16> : corr81_kernel<true, float>);
   static bool attr_set[3] = {false, false, false};
