@@ -185,7 +185,24 @@ def main():
     launches = eng.launches
     value = world * B * args.steps / (ms_total / 1e3)
 
-    # ---- end to end through the public module with HOST buffers (H2D of the burst + D2H of pred inside the region)
+    # ---- end to end with HOST buffers, every step: H2D of the burst from pinned memory + forward + D2H of pred.
+    #      (a) the public host-buffer front end (HostPipeline: the copies of neighbouring steps overlap the compute on
+    #          separate streams; all K copies in and K copies out are inside the timed region, drain included)
+    from deep_rawburst_sr_b200.pipeline import HostPipeline
+    pipe = HostPipeline(net, depth=2)
+    for _ in range(2):
+        pipe.submit(host_in, host_out)
+    pipe.drain()
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        pipe.submit(host_in, host_out)
+    e1.record(pipe.s_out)
+    pipe.drain()
+    barrier()
+    ms_e2e = max_over_ranks(e0.elapsed_time(e1))
+    e2e = world * B * args.steps / (ms_e2e / 1e3)
+    #      (b) the reference's calling pattern, copies serialised with the forward on one stream: net(x.cuda()) ; pred.cpu()
     for _ in range(2):
         p, _ = net(host_in.to(dev, non_blocking=True))
         host_out.copy_(p, non_blocking=True)
@@ -196,8 +213,8 @@ def main():
         host_out.copy_(p, non_blocking=True)
     e1.record()
     barrier()
-    ms_e2e = max_over_ranks(e0.elapsed_time(e1))
-    e2e = world * B * args.steps / (ms_e2e / 1e3)
+    ms_e2e_sync = max_over_ranks(e0.elapsed_time(e1))
+    e2e_sync = world * B * args.steps / (ms_e2e_sync / 1e3)
     if rank == 0:
         sampler.stop_flag = True
         sampler.join(timeout=3)
@@ -207,6 +224,7 @@ def main():
     #      per step makes the step CPU-bound
     net.use_cuda_graph = False
     eng.flops = {}
+    eng.hbm_bytes = {}
     eng.timers = {}
     eng.layer_events = {}
     for _ in range(args.steps):
@@ -220,6 +238,7 @@ def main():
                 f.write(f'{ms / args.steps:9.4f} ms/step {tf:8.1f} TFLOP/s {family:12s} n,h,w,cin,cout={shape} x{n // args.steps} {key}\n')
     eng.layer_events = None
     flops = dict(eng.flops)
+    alg_bytes = dict(eng.hbm_bytes)
     eng.timers = None
 
     if rank != 0:
@@ -234,9 +253,21 @@ def main():
     if dom in ('conv_tc', 'conv_direct'):
         ms, n = fam[dom]
         ach = flops.get(dom, 0) / (ms / 1e3) / 1e12
+        # measured DRAM traffic of the same launches (ncu dram__bytes_read/write.sum of one forward at this config,
+        # committed under profiles/ by tools/gpu_ncu_traffic.sh + tools/traffic_table.py), per launch like `achieved`
+        traffic = None
+        tpath = os.path.join(ROOT, 'profiles', f'r01_traffic_b{B}.json')
+        if S == 48 and args.precision == 'bf16' and os.path.exists(tpath):
+            tf = json.load(open(tpath))['families'].get(dom)
+            if tf:
+                traffic = (tf['dram_read_bytes'] + tf['dram_write_bytes']) / tf['launches']
         roofline = {'kernel': dom, 'bound': 'tensor', 'achieved': ach, 'peak': pk['tflops'], 'unit': 'TFLOP/s',
-                    'frac': ach / pk['tflops'], 'traffic': None, 'peak_source': pk['src'],
-                    'launches': n, 'kernel_ms_per_step': ms / args.steps}
+                    'frac': ach / pk['tflops'], 'traffic': traffic, 'peak_source': pk['src'],
+                    'launches': n, 'kernel_ms_per_step': ms / args.steps,
+                    'flops_per_launch': flops.get(dom, 0) / max(n, 1), 'us_per_launch': ms * 1e3 / max(n, 1),
+                    'algorithmic_bytes_per_launch': alg_bytes.get(dom, 0) / max(n, 1),
+                    'note': 'family of ~111 implicit-GEMM conv launches per step (Cout 2..512); SS-mode tcgen05 operand '
+                            'fetch (128 B/clk/SM shared memory) bounds N<128 layers below the tensor peak, see DESIGN.md 4.1'}
     elif dom is not None:
         ms, n = fam[dom]
         roofline = {'kernel': dom, 'bound': 'hbm', 'achieved': None, 'peak': pk['hbm_gbs'], 'unit': 'GB/s', 'frac': None,
@@ -286,7 +317,10 @@ def main():
                    'global_batch': B * world, 'parallelism': f'burst-sharded x{world}, no data-path collective',
                    'l2': 'per-step activation working set (~GBs) >> 126 MB L2; no explicit flush'},
         'e2e': {'value': e2e, 'unit': 'bursts/s', 'ms_per_step': ms_e2e / args.steps,
-                'h2d_bytes_per_step': host_in.numel() * 4, 'd2h_bytes_per_step': host_out.numel() * 4},
+                'h2d_bytes_per_step': host_in.numel() * 4, 'd2h_bytes_per_step': host_out.numel() * 4,
+                'api': 'deep_rawburst_sr_b200.pipeline.HostPipeline.submit(host_in, host_out)',
+                'serialised_copies': {'value': e2e_sync, 'ms_per_step': ms_e2e_sync / args.steps,
+                                      'api': 'net(host_in.to(device)) ; host_out.copy_(pred)'}},
         'gpu_launches': launches, 'cuda_graph': not args.no_graph,
         'roofline': roofline,
         'kernel_families': families,

@@ -166,6 +166,7 @@ class DBSREngine:
         self.layer_events = None   # when a dict (and timers is on): conv layer key -> [(events, flops, family, shape)]
         self.timers = None   # when a dict: family -> list of (start, end) CUDA events on the launching stream
         self.flops = {}      # family -> algorithmic FLOPs (2*MAC, real channel counts) launched since reset
+        self.hbm_bytes = {}  # family -> algorithmic HBM bytes (input + output + residual maps, once each) since reset
         sd = {k: v.detach().to(self.device) for k, v in state_dict.items()}
         if 'pwc' in parts:
             self._pack_pwc(sd)
@@ -291,6 +292,11 @@ class DBSREngine:
         fam = 'conv_tc' if use_tc else 'conv_direct'
         ho, wo = (y.h, y.w) if cw.shuffle_r <= 1 else (y.h // cw.shuffle_r, y.w // cw.shuffle_r)
         self.flops[fam] = self.flops.get(fam, 0) + 2 * x.n * ho * wo * cw.cout * cin_alg * cw.ksize * cw.ksize
+        es_in, es_out = x.buf.element_size(), y.buf.element_size()
+        nbytes = x.n * x.h * x.w * cin_alg * es_in + y.n * y.h * y.w * y.c * es_out
+        if residual is not None:
+            nbytes += residual.n * residual.h * residual.w * residual.c * residual.buf.element_size()
+        self.hbm_bytes[fam] = self.hbm_bytes.get(fam, 0) + nbytes
         ev = self._tic(fam)
         if ev is not None and self.layer_events is not None:
             fl = 2 * x.n * ho * wo * cw.cout * cin_alg * cw.ksize * cw.ksize
