@@ -29,7 +29,7 @@ CONV_GFLOP_PER_BURST = {48: 223.28, 80: 644.10}   # SURVEY.md App. B (2*MAC, all
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--steps', type=int, default=20)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--batch', type=int, default=32, help='bursts per GPU per step')
@@ -63,6 +63,26 @@ class ClockSampler(threading.Thread):
         self.max_mhz = None
 
     def run(self):
+        # NVML in-process (a few microseconds per query); spawning nvidia-smi inside a ~100 ms timed region perturbs it
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            bits = {'hw_slowdown': pynvml.nvmlClocksEventReasonHwSlowdown,
+                    'hw_thermal_slowdown': pynvml.nvmlClocksEventReasonHwThermalSlowdown,
+                    'sw_thermal_slowdown': pynvml.nvmlClocksEventReasonSwThermalSlowdown,
+                    'sw_power_cap': pynvml.nvmlClocksEventReasonSwPowerCap}
+            while not self.stop_flag:
+                self.samples.append(float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)))
+                r = pynvml.nvmlDeviceGetCurrentClocksEventReasons(h)
+                for n, bit in bits.items():
+                    if r & bit:
+                        self.reasons.add(n)
+                time.sleep(0.01)
+            return
+        except Exception:
+            pass
         q = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
              'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
         names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
@@ -167,8 +187,15 @@ def main():
     # ---- device-resident throughput ("value"): K forwards, inputs already in HBM
     for _ in range(args.warmup):
         net(dev_in)
-    for _ in range(2):      # untimed: the CUDA graph of this shape is captured on the 2nd call; make sure replays have run
+    # untimed settle phase on top of the W warm-up steps: the CUDA graph of this shape is captured on the 2nd call, and a
+    # GPU coming out of idle needs a few hundred ms of load before clocks / power state are steady (a 5-step timed region
+    # right after process start measured 1.2-2.4x slow on this pool)
+    t_settle = time.perf_counter()
+    while True:
         net(dev_in)
+        torch.cuda.synchronize()
+        if time.perf_counter() - t_settle > 1.0:
+            break
     barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:

@@ -217,7 +217,12 @@ struct ConvTcParams {
   int res_chunks;       // > 0: the residual is accumulated on the tensor core as res_chunks extra K chunks (identity weights)
   int r_tx_bytes;       // bytes of one residual box {CK, 8*mt px, 16 rows}
   int flat;             // small-map mode: the A box holds flat_ni whole zero-bordered images, M rows = flat slots
-  int flat_s, flat_ni;  // slots per image (H+2)*(W+2); images per item
+  int flat_s, flat_ni;  // slots per image (H+2)*(W+2); images per M tile
+  // second M tile of an item (mt == 2): offset of its A rows inside the box (16-byte units), image and column offset.
+  //   wide maps : side by side in x        -> t1_step16 = 8 pixel rows, t1_dimg = 0,       t1_dx = 8
+  //   narrow / flat maps: the NEXT image(s) -> t1_step16 = one image box,  t1_dimg = 1 / ni, t1_dx = 0
+  int t1_step16, t1_dimg, t1_dx;
+  int imgs_per_item;    // images one item (= one A box) covers: 1, 2 (narrow pair), flat_ni * mt
   // output
   void* y; int y_dtype; int y_pitch; int y_coff; int yH, yW;
   const void* res; int r_dtype; int r_pitch; int r_coff;   // residual with the geometry of y
@@ -423,15 +428,15 @@ __device__ __forceinline__ ItemCoord decode_item(const ConvTcParams& p, long lon
   const unsigned item = (unsigned)item64;            // item counts fit 32 bits (64-bit div/mod costs ~100 instr each)
   const unsigned tm = fast_div(item, (unsigned)p.ntiles_n, p.md_nt, p.one_nt, p.fastdiv);
   c.nt = (int)(item - tm * (unsigned)p.ntiles_n);
-  if (p.flat) {   // item = flat_ni consecutive images
-    c.img = (int)tm * p.flat_ni; c.y0 = 0; c.x0 = 0;
+  if (p.flat) {   // item = imgs_per_item consecutive images
+    c.img = (int)tm * p.imgs_per_item; c.y0 = 0; c.x0 = 0;
     return c;
   }
   const unsigned per_img = (unsigned)(p.items_x * p.tiles_y);
   const unsigned img = fast_div(tm, per_img, p.md_img, p.one_img, p.fastdiv);
   const unsigned rem = tm - img * per_img;
   const unsigned ry = fast_div(rem, (unsigned)p.items_x, p.md_x, p.one_x, p.fastdiv);
-  c.img = (int)img;
+  c.img = (int)img * p.imgs_per_item;
   c.y0 = (int)ry * TILE_H;
   c.x0 = (int)(rem - ry * (unsigned)p.items_x) * (TILE_W * p.mt);
   return c;
@@ -684,7 +689,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
         const int ky = tap / 3, kx = tap - 3 * (tap / 3);
         tap_off[tap] = (p.ksize == 3) ? (uint32_t)((ky * p.dil) * p.halo_w + kx * p.dil) * (ROW_BYTES >> 4) : 0u;
       }
-      const uint32_t tile_step = (uint32_t)TILE_W * (ROW_BYTES >> 4);   // second 16x8 tile of the item
+      const uint32_t tile_step = (uint32_t)p.t1_step16;                  // second M tile of the item
       const bool two_tiles = p.mt == 2;
       const uint32_t b_step = (uint32_t)p.b_bytes >> 4;
       const uint32_t a_step = (uint32_t)p.a_bytes >> 4;
@@ -780,7 +785,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
     const int ty = m >> 3, tx = m & 7;
     uint8_t* stg = smem_stg + (size_t)warp * STG_WARP_BYTES;
     int acc = 0; uint32_t acc_phase = 0;
-    if (p.bias_smem && p.vec_ok && p.y_dtype == DBSR_BF16 && (p.res == nullptr || NT == 64 || NT == 32 || NT == 16)) {
+    if (!p.flat && p.bias_smem && p.vec_ok && p.y_dtype == DBSR_BF16 && (p.res == nullptr || NT == 64 || NT == 32 || NT == 16)) {
       // ---------- lean coalesced path (every bf16 layer of the encoder / fusion / decoder trunks) ----------
       const uint32_t stg_s = smem_u32(stg);
       const uint32_t bias_s0 = smem_u32(bias_tab);
@@ -801,22 +806,23 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
       for (long long item = blockIdx.x; item < p.total_items; item += gridDim.x) {
         const ItemCoord c = decode_item(p, item);
         const int co0 = c.nt * NT;
-        const int tx0 = c.x0 + t * TILE_W;
+        const int tx0 = c.x0 + t * p.t1_dx;
+        const int img_t = c.img + t * p.t1_dimg;             // narrow maps: the second tile is the next image
         __nv_bfloat16* ywarp;
         if (shuffle) {
           // packed channel co' = i*256 + j*32 + c ; N tile = 128 -> HR row phase i = nt / 2, first HR column j0 = (nt & 1) * 4
           const int per_i = p.shuffle_r * 32;
           const int si = co0 / per_i, j0 = (co0 - si * per_i) >> 5;
-          ywarp = ybase + ((long long)(c.img * p.yH + c.y0 * p.shuffle_r + si) * p.yW + (tx0 * p.shuffle_r + j0)) * p.y_pitch;
+          ywarp = ybase + ((long long)(img_t * p.yH + c.y0 * p.shuffle_r + si) * p.yW + (tx0 * p.shuffle_r + j0)) * p.y_pitch;
         } else {
-          ywarp = ybase + ((long long)(c.img * p.yH + c.y0) * p.yW + tx0) * p.y_pitch + co0;
+          ywarp = ybase + ((long long)(img_t * p.yH + c.y0) * p.yW + tx0) * p.y_pitch + co0;
         }
-        const int rows_left = p.H - c.y0 - quarter * 4, cols_in = p.W - tx0;
+        const int rows_left = (img_t < p.n) ? p.H - c.y0 - quarter * 4 : 0, cols_in = p.W - tx0;   // image past the batch: nothing
         const bool full = rows_left >= 4 && cols_in >= TILE_W;
         const uint32_t tbase = tq + (uint32_t)acc * acc_cols;
         const uint32_t bias_s = bias_s0 + (uint32_t)co0 * 4u;
         if (has_res && my_group) {
-          const __nv_bfloat16* rwarp = rbase + ((long long)(c.img * p.yH + c.y0) * p.yW + tx0) * p.r_pitch + co0;
+          const __nv_bfloat16* rwarp = rbase + ((long long)(img_t * p.yH + c.y0) * p.yW + tx0) * p.r_pitch + co0;
           if (NT == 64) lean_prefetch_res<64>(stg_s, lane, rwarp, r_row, r_col, rows_left, cols_in, p.res);
           else if (NT == 32) lean_prefetch_res<32>(stg_s, lane, rwarp, r_row, r_col, rows_left, cols_in, p.res);
           else lean_prefetch_res<16>(stg_s, lane, rwarp, r_row, r_col, rows_left, cols_in, p.res);
@@ -845,24 +851,25 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
       const int co0 = c.nt * NT;
       const int t = (p.mt == 2) ? group : 0;
       const uint32_t tbase = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)((acc * p.mt + t) * NT);
-      if (p.vec_ok && p.y_dtype == DBSR_BF16) {
+      if (!p.flat && p.vec_ok && p.y_dtype == DBSR_BF16) {
         // ---------- coalesced path: 64/32/16-channel groups through the per-warp staging rows ----------
-        const int tx0 = c.x0 + t * TILE_W;
+        const int tx0 = c.x0 + t * p.t1_dx;
+        const long long img_t = c.img + t * p.t1_dimg;
         TileGeo tg;
         if (p.shuffle_r > 1) {
           // packed channel co' = i*256 + j*32 + c ; N tile = 128 -> HR row phase i = nt / 2, first HR column j0 = (nt & 1) * 4
           const int per_i = p.shuffle_r * 32;
           const int si = co0 / per_i, j0 = (co0 - si * per_i) / 32;
           tg.y = reinterpret_cast<__nv_bfloat16*>(p.y) +
-                 (((long long)c.img * p.yH + (c.y0 * p.shuffle_r + si)) * p.yW + (tx0 * p.shuffle_r + j0)) * p.y_pitch + p.y_coff;
+                 ((img_t * p.yH + (c.y0 * p.shuffle_r + si)) * p.yW + (tx0 * p.shuffle_r + j0)) * p.y_pitch + p.y_coff;
           tg.y_row = p.shuffle_r * p.yW * p.y_pitch; tg.y_col = p.shuffle_r * p.y_pitch;
         } else {
-          tg.y = reinterpret_cast<__nv_bfloat16*>(p.y) + (((long long)c.img * p.yH + c.y0) * p.yW + tx0) * p.y_pitch + p.y_coff + co0;
+          tg.y = reinterpret_cast<__nv_bfloat16*>(p.y) + ((img_t * p.yH + c.y0) * p.yW + tx0) * p.y_pitch + p.y_coff + co0;
           tg.y_row = p.yW * p.y_pitch; tg.y_col = p.y_pitch;
         }
-        tg.r = reinterpret_cast<const __nv_bfloat16*>(p.res) + (((long long)c.img * p.yH + c.y0) * p.yW + tx0) * p.r_pitch + p.r_coff + co0;
+        tg.r = reinterpret_cast<const __nv_bfloat16*>(p.res) + ((img_t * p.yH + c.y0) * p.yW + tx0) * p.r_pitch + p.r_coff + co0;
         tg.r_row = p.yW * p.r_pitch; tg.r_col = p.r_pitch;
-        tg.rows_in = min(TILE_H, p.H - c.y0); tg.cols_in = min(TILE_W, p.W - tx0);
+        tg.rows_in = (img_t < p.n) ? min(TILE_H, p.H - c.y0) : 0; tg.cols_in = min(TILE_W, p.W - tx0);
         mbar_wait(&tfull_bar[acc], acc_phase, 400 + acc);
         tc_fence_after();
         int g0 = 0, gi = 0;
@@ -878,13 +885,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
         }
       } else {
         // ---------- generic path (fp32 outputs, odd channel counts, flat mode): one thread stores its own pixel ----------
-        int y = c.y0 + ty, x = c.x0 + t * TILE_W + tx;
-        long long img = c.img;
-        bool valid = (y < p.H) && (x < p.W);
+        int y = c.y0 + ty, x = c.x0 + t * p.t1_dx + tx;
+        long long img = c.img + t * p.t1_dimg;
+        bool valid = (y < p.H) && (x < p.W) && (img < p.n);
         if (p.flat) {   // M row m = flat slot: image j = m / S, padded row / column inside it
           const int j = m / p.flat_s, rem = m - j * p.flat_s;
           y = rem / p.halo_w; x = rem - y * p.halo_w;
-          img = c.img + j;
+          img += j;
           valid = (j < p.flat_ni) && (y < p.H) && (x < p.W) && (img < p.n);   // rows past the box belong to nobody
         }
         const long long off = ((img * p.yH + y) * p.yW + x) * p.y_pitch + p.y_coff + co0;
@@ -985,6 +992,7 @@ static const void* identity_weights(int n, cudaStream_t st) {
 
 struct TcConfig {
   int flat, flat_s, flat_ni, res_chunks;
+  int pair_img;    // narrow maps (one tile column): the two M tiles of an item are two consecutive images
   int n_tile, ck, nchunks, cout, cout_pad, mt, halo_w, rows, a_slots, b_stages, b_resident, a_bytes, a_tx_bytes, b_bytes,
       smem_bytes, tmem_cols, vec_ok;
 };
@@ -1042,30 +1050,36 @@ static int tc_plan(const dbsr_conv_t* c, TcConfig* cfg, bool set_err) {
     if (ni >= 2) { cfg->flat = 1; cfg->flat_s = S; cfg->flat_ni = ni_use; }
   }
   bool found = false;
+  cfg->pair_img = 0;
   if (cfg->flat) {
-    cfg->mt = 1; cfg->halo_w = c->x.w + 2; cfg->rows = c->x.h + 2;
-    cfg->a_tx_bytes = cfg->flat_ni * cfg->flat_s * ck * 2;
-    // the MMA reads up to slot 127 + 2*halo_w + 2 (garbage rows beyond the box only feed masked outputs)
-    cfg->a_bytes = round_up((128 + 2 * cfg->halo_w + 2) * ck * 2 > cfg->a_tx_bytes ? (128 + 2 * cfg->halo_w + 2) * ck * 2
-                                                                                   : cfg->a_tx_bytes, 1024);
+    // two M tiles (2 * ni images) per item share every weight tile when that still leaves work for half the SMs: the
+    // CTAs of these tiny-M layers are bound by streaming the whole weight set from L2 once per item
+    cfg->mt = (ceil_div(c->x.n, cfg->flat_ni) >= 100 && 2 * 2 * nt <= 512) ? 2 : 1;
+    cfg->halo_w = c->x.w + 2; cfg->rows = c->x.h + 2;
+    cfg->a_tx_bytes = cfg->mt * cfg->flat_ni * cfg->flat_s * ck * 2;
+    // the MMA reads up to slot 127 + 2*halo_w + 2 of its tile (garbage rows beyond the box only feed masked outputs)
+    const int a_read = ((cfg->mt - 1) * cfg->flat_ni * cfg->flat_s + 128 + 2 * cfg->halo_w + 2) * ck * 2;
+    cfg->a_bytes = round_up(a_read > cfg->a_tx_bytes ? a_read : cfg->a_tx_bytes, 1024);
     cfg->a_slots = 4;
     while (cfg->a_slots > 1 && cfg->a_slots * cfg->a_bytes + 4 * cfg->b_bytes > budget) cfg->a_slots--;
-    found = true;
-    vec = false;   // flat slots are not contiguous pixels: per-thread masked epilogue
-    cfg->vec_ok = 0;
+    found = true;   // flat slots are not tile pixels: per-thread epilogue (16-byte accesses when vec_ok, else masked scalars)
   }
   // item width (mt tiles) and depth of the activation ring: prefer 2 tiles x 4 slots, shrink until the halo boxes
   // leave room for the weight stages (large dilations have large halos)
-  for (int mt = (tiles_x >= 2 ? 2 : 1); mt >= 1 && !found; --mt) {
+  // narrow maps (W <= 8, one tile column): pair two consecutive IMAGES in one item instead of two tile columns
+  const bool can_pair = tiles_x == 1 && !cfg->flat && c->x.n >= 2 * 148 && !c->residual.data && r == 1 && 2 * 2 * nt <= 512;
+  for (int mt = ((tiles_x >= 2 || can_pair) ? 2 : 1); mt >= 1 && !found; --mt) {
     for (int slots = 4; slots >= 1 && !found; --slots) {
-      const int hw = TILE_W * mt + 2 * pad;
-      const int ab = round_up(cfg->rows * hw * ck * 2, 1024);
+      const bool pair = can_pair && mt == 2;
+      const int hw = TILE_W * (pair ? 1 : mt) + 2 * pad;
+      const int ab = round_up(cfg->rows * hw * ck * 2 * (pair ? 2 : 1), 1024);
       const int b_all = ((kpad / ck) * taps + (c->residual.data ? (nt + ck - 1) / ck : 0)) * cfg->b_bytes;
       const bool want_resident = cpad == nt && (kpad / ck) * taps <= 64 && b_all <= budget / 2;
       const int b_need = want_resident ? b_all : 4 * cfg->b_bytes;
       if (slots * ab + b_need <= budget || (slots == 1 && ab + 2 * cfg->b_bytes <= budget)) {
         cfg->mt = mt; cfg->a_slots = slots; cfg->halo_w = hw; cfg->a_bytes = ab;
-        cfg->a_tx_bytes = cfg->rows * hw * ck * 2;
+        cfg->a_tx_bytes = cfg->rows * hw * ck * 2 * (pair ? 2 : 1);
+        cfg->pair_img = pair ? 1 : 0;
         found = true;
       }
     }
@@ -1186,7 +1200,7 @@ extern "C" int dbsr_conv2d_tc(const dbsr_conv_t* c_in, void* stream) {
     cuuint64_t strides[3] = {(cuuint64_t)c->x.c_pitch * 2, (cuuint64_t)c->x.w * c->x.c_pitch * 2,
                              (cuuint64_t)c->x.h * c->x.w * c->x.c_pitch * 2};
     cuuint32_t box[4] = {(cuuint32_t)cfg.ck, (cuuint32_t)cfg.halo_w, (cuuint32_t)cfg.rows,
-                         (cuuint32_t)(cfg.flat ? cfg.flat_ni : 1)};
+                         (cuuint32_t)(cfg.flat ? cfg.flat_ni * cfg.mt : (cfg.pair_img ? 2 : 1))};
     cuuint32_t es[4] = {1, 1, 1, 1};
     void* base = reinterpret_cast<__nv_bfloat16*>(c->x.data) + c->x.c_off;
     CUresult rc = encode(&mx, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, base, dims, strides, box, es,
@@ -1242,10 +1256,14 @@ extern "C" int dbsr_conv2d_tc(const dbsr_conv_t* c_in, void* stream) {
   p.nchunks = cfg.nchunks; p.cout_pad = cfg.cout_pad; p.cout = cfg.cout; p.n_tile = cfg.n_tile; p.mt = cfg.mt;
   p.tmem_cols = cfg.tmem_cols; p.vec_ok = cfg.vec_ok;
   p.ntiles_n = cfg.cout_pad / cfg.n_tile;
-  p.items_x = ceil_div(p.W, TILE_W * cfg.mt); p.tiles_y = ceil_div(p.H, TILE_H);
-  p.total_items = (long long)p.n * p.items_x * p.tiles_y * p.ntiles_n;
+  p.items_x = cfg.pair_img ? 1 : ceil_div(p.W, TILE_W * cfg.mt); p.tiles_y = ceil_div(p.H, TILE_H);
   p.flat = cfg.flat; p.flat_s = cfg.flat_s; p.flat_ni = cfg.flat_ni;
-  if (cfg.flat) p.total_items = (long long)ceil_div(p.n, cfg.flat_ni) * p.ntiles_n;
+  p.imgs_per_item = cfg.flat ? cfg.flat_ni * cfg.mt : (cfg.pair_img ? 2 : 1);
+  const int row16 = cfg.ck * 2 / 16;                                   // 16-byte units per pixel row of the A box
+  if (cfg.flat) { p.t1_step16 = cfg.flat_ni * cfg.flat_s * row16; p.t1_dimg = cfg.flat_ni; p.t1_dx = 0; }
+  else if (cfg.pair_img) { p.t1_step16 = cfg.rows * cfg.halo_w * row16; p.t1_dimg = 1; p.t1_dx = 0; }
+  else { p.t1_step16 = TILE_W * row16; p.t1_dimg = 0; p.t1_dx = TILE_W; }
+  p.total_items = (long long)ceil_div(p.n, p.imgs_per_item) * (cfg.flat ? 1 : p.items_x * p.tiles_y) * p.ntiles_n;
   DBSR_REQUIRE(p.total_items < (1LL << 31) && (long long)c->y.n * c->y.h * c->y.w < (1LL << 31),
                "conv2d_tc: more than 2^31 work items / output pixels");
   {

@@ -43,6 +43,13 @@ TC_CASES = {
     'flat_4x4_437x96_n11': (437, 96, 3, 1, 11, 4, 4, 2, False, False, 0),
     'flat_4x4_629x2_f32': (629, 2, 3, 1, 7, 4, 4, 0, True, True, 0),
     'flat_2x3_128x128': (128, 128, 3, 1, 9, 2, 3, 1, True, False, 0),
+    # many small images: an item holds TWO M tiles that share every weight tile -- flat mode (2 x ni images, odd image count
+    # so the last item is half empty) and narrow regular maps (two consecutive 8x8 / 8x5 images per item)
+    'flat_4x4_pair_209x128_n331': (209, 128, 3, 1, 331, 4, 4, 2, False, False, 0),
+    'flat_2x2_pair_96x48_n1001_f32': (96, 48, 3, 1, 1001, 2, 2, 0, False, True, 0),
+    'narrow_8x8_pair_136x128_n301': (136, 128, 3, 1, 301, 8, 8, 2, False, False, 0),
+    'narrow_8x5_pair_64x64_n297_k1': (64, 64, 1, 1, 297, 8, 5, 1, False, False, 0),
+    'narrow_20x8_pair_32x32_n300': (32, 32, 3, 1, 300, 20, 8, 1, False, False, 0),
 }
 
 
