@@ -52,58 +52,73 @@ def peaks():
 
 
 class ClockSampler(threading.Thread):
-    """samples nvidia-smi SM clocks / throttle reasons during the timed region"""
+    """samples SM clocks / clock-event reasons during the timed regions.  NVML is initialised in the constructor (on the
+    main thread, BEFORE any timed region: nvmlInit / an nvidia-smi spawn take the driver lock for tens of ms and stall
+    kernel submission -- inside a 50-200 ms region that reads as a 1.2-2.4x slowdown); the thread then only issues
+    in-process queries (microseconds).  Only samples taken while `active` is set are kept."""
 
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index = index
         self.stop_flag = False
+        self.active = False
         self.samples = []
         self.reasons = set()
         self.max_mhz = None
-
-    def run(self):
-        # NVML in-process (a few microseconds per query); spawning nvidia-smi inside a ~100 ms timed region perturbs it
+        self.nvml = None
         try:
             import pynvml
             pynvml.nvmlInit()
-            h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
-            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
-            bits = {'hw_slowdown': pynvml.nvmlClocksEventReasonHwSlowdown,
-                    'hw_thermal_slowdown': pynvml.nvmlClocksEventReasonHwThermalSlowdown,
-                    'sw_thermal_slowdown': pynvml.nvmlClocksEventReasonSwThermalSlowdown,
-                    'sw_power_cap': pynvml.nvmlClocksEventReasonSwPowerCap}
-            while not self.stop_flag:
-                self.samples.append(float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)))
-                r = pynvml.nvmlDeviceGetCurrentClocksEventReasons(h)
-                for n, bit in bits.items():
-                    if r & bit:
-                        self.reasons.add(n)
-                time.sleep(0.01)
-            return
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            pynvml.nvmlDeviceGetClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.bits = {'hw_slowdown': pynvml.nvmlClocksEventReasonHwSlowdown,
+                         'hw_thermal_slowdown': pynvml.nvmlClocksEventReasonHwThermalSlowdown,
+                         'sw_thermal_slowdown': pynvml.nvmlClocksEventReasonSwThermalSlowdown,
+                         'sw_power_cap': pynvml.nvmlClocksEventReasonSwPowerCap}
+            self.nvml = pynvml
         except Exception:
-            pass
+            self.nvml = None
+
+    def run(self):
+        if self.nvml is not None:
+            nv = self.nvml
+            while not self.stop_flag:
+                if self.active:
+                    try:
+                        self.samples.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                        r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                        for n, bit in self.bits.items():
+                            if r & bit:
+                                self.reasons.add(n)
+                    except Exception:
+                        pass
+                time.sleep(0.005)
+            return
+        # fallback without NVML bindings: nvidia-smi (coarse; perturbs short regions)
         q = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
              'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
         names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
         while not self.stop_flag:
-            try:
-                out = subprocess.run(['nvidia-smi', f'--query-gpu={q}', '--format=csv,noheader,nounits', '-i', str(self.index)],
-                                     capture_output=True, text=True, timeout=5).stdout.strip().split('\n')[0]
-                f = [v.strip() for v in out.split(',')]
-                self.samples.append(float(f[0]))
-                self.max_mhz = float(f[1])
-                for n, v in zip(names, f[2:]):
-                    if v.lower().startswith('active'):
-                        self.reasons.add(n)
-            except Exception:
-                pass
+            if self.active:
+                try:
+                    out = subprocess.run(['nvidia-smi', f'--query-gpu={q}', '--format=csv,noheader,nounits', '-i', str(self.index)],
+                                         capture_output=True, text=True, timeout=5).stdout.strip().split('\n')[0]
+                    f = [v.strip() for v in out.split(',')]
+                    self.samples.append(float(f[0]))
+                    self.max_mhz = float(f[1])
+                    for n, v in zip(names, f[2:]):
+                        if v.lower().startswith('active'):
+                            self.reasons.add(n)
+                except Exception:
+                    pass
             time.sleep(0.2)
 
     def summary(self):
         s = sorted(self.samples)
         med = s[len(s) // 2] if s else None
-        return {'sm_mhz': med, 'sm_max_mhz': self.max_mhz, 'reasons': sorted(self.reasons), 'samples': len(s)}
+        return {'sm_mhz': med, 'sm_min_mhz': s[0] if s else None, 'sm_max_mhz': self.max_mhz, 'reasons': sorted(self.reasons),
+                'samples': len(s), 'source': 'nvml' if self.nvml is not None else 'nvidia-smi'}
 
 
 def cpu_reference_arm(args, rank):
@@ -184,22 +199,16 @@ def main():
         print(json.dumps({'one_forward': True, 'launches_per_forward': eng.launches // (max(1, args.warmup) + 1)}))
         return
 
-    # ---- device-resident throughput ("value"): K forwards, inputs already in HBM
-    for _ in range(args.warmup):
-        net(dev_in)
-    # untimed settle phase on top of the W warm-up steps: the CUDA graph of this shape is captured on the 2nd call, and a
-    # GPU coming out of idle needs a few hundred ms of load before clocks / power state are steady (a 5-step timed region
-    # right after process start measured 1.2-2.4x slow on this pool)
-    t_settle = time.perf_counter()
-    while True:
-        net(dev_in)
-        torch.cuda.synchronize()
-        if time.perf_counter() - t_settle > 1.0:
-            break
-    barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+    # ---- device-resident throughput ("value"): K forwards, inputs already in HBM
+    for _ in range(args.warmup):
+        net(dev_in)
+    for _ in range(2):      # untimed: the CUDA graph of this shape is captured on the 2nd call; make sure replays have run
+        net(dev_in)
+    barrier()
+    sampler.active = True
     eng.launches = 0
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
@@ -242,6 +251,7 @@ def main():
     barrier()
     ms_e2e_sync = max_over_ranks(e0.elapsed_time(e1))
     e2e_sync = world * B * args.steps / (ms_e2e_sync / 1e3)
+    sampler.active = False
     if rank == 0:
         sampler.stop_flag = True
         sampler.join(timeout=3)
