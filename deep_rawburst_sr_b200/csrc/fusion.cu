@@ -384,7 +384,10 @@ softmax_wsum8_kernel(View feat, View logits, const float* __restrict__ offsets, 
 // only cp.async.wait_group.  Out-of-image taps are zero-filled by the copy (src-size 0), which is grid_sample's
 // zero padding, so the weights need no mask.
 // ---------------------------------------------------------------------------------------------------------
-constexpr int WS_STAGES = 3;
+#ifndef WS_STAGES_N
+#define WS_STAGES_N 3
+#endif
+constexpr int WS_STAGES = WS_STAGES_N;
 constexpr int WS_ASYNC_SMEM = WS_STAGES * 5 * 256 * 16;
 __device__ __forceinline__ void cp_async_16(uint32_t dst, const void* src, uint32_t bytes) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(bytes) : "memory");
@@ -398,7 +401,7 @@ __device__ __forceinline__ Vec8 unpack_bf16x8(const uint4& q) {
   return r;
 }
 template <typename TO>
-__global__ void __launch_bounds__(256, 3)
+__global__ void __launch_bounds__(256, (WS_STAGES_N >= 4) ? 2 : 3)
 softmax_wsum8_async_kernel(View feat, View logits, const float* __restrict__ offsets, View fused, int frames) {
   griddep_wait();
   extern __shared__ __align__(16) uint4 ring[];        // [WS_STAGES][5][256]
