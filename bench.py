@@ -316,6 +316,10 @@ def main():
         'warp': B * ((FRAMES * C * es) * 2 + (FRAMES - 1) * 2 * 4) * HW,                 # read 14 maps, write 14 maps, flow
         'softmax_wsum': B * (2 * FRAMES * C * es + C * es) * HW,                          # 14 feat + 14 logit maps, fused out
     }
+    # cost volume: per pair and pyramid level both feature maps in, 81 channels out
+    from deep_rawburst_sr_b200.engine import PWC_EXT_CH
+    hp = (S + 63) // 64 * 64
+    hbm_bytes['corr81'] = sum(B * (FRAMES - 1) * (2 * PWC_EXT_CH[l] + 81) * (hp >> l) * (hp >> l) * es for l in (2, 3, 4, 5, 6))
     families = {k: {'ms_per_step': v[0] / args.steps, 'launches_per_step': v[1] / args.steps,
                     'tflops': (flops.get(k, 0) / (v[0] / 1e3) / 1e12) if k in flops and v[0] > 0 else None,
                     'hbm_gbs': (hbm_bytes[k] * args.steps / (v[0] / 1e3) / 1e9) if k in hbm_bytes and v[0] > 0 else None}

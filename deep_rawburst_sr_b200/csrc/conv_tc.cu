@@ -204,6 +204,7 @@ struct ConvTcParams {
   int mt;               // 16x8 tiles per item (1 or 2, side by side along x)
   int tmem_cols;        // power of two >= max(32, 2 * mt * n_tile)
   int vec_ok;           // 1: aligned fast path (16-byte accesses, every 32-column chunk fully inside cout)
+  int align_ok;         // 1: y / residual / bias allow 16-byte accesses (chunks that end inside cout use them per thread)
   int ntiles_n;         // cout_pad / n_tile
   int items_x, tiles_y;
   long long total_items;
@@ -240,7 +241,7 @@ __device__ __forceinline__ void epilogue_chunk(const ConvTcParams& p, const uint
   float v[NC];
 #pragma unroll
   for (int j = 0; j < NC; ++j) v[j] = __uint_as_float(r[j]);
-  if (p.vec_ok) {
+  if (p.align_ok && co + NC <= p.cout) {
     uint4 rq[NC / 8];
     if (p.res) {   // bf16 on the fast path
       if (rq_pref) {
@@ -994,7 +995,7 @@ struct TcConfig {
   int flat, flat_s, flat_ni, res_chunks;
   int pair_img;    // narrow maps (one tile column): the two M tiles of an item are two consecutive images
   int n_tile, ck, nchunks, cout, cout_pad, mt, halo_w, rows, a_slots, b_stages, b_resident, a_bytes, a_tx_bytes, b_bytes,
-      smem_bytes, tmem_cols, vec_ok;
+      smem_bytes, tmem_cols, vec_ok, align_ok;
 };
 
 static int tc_plan(const dbsr_conv_t* c, TcConfig* cfg, bool set_err) {
@@ -1016,8 +1017,7 @@ static int tc_plan(const dbsr_conv_t* c, TcConfig* cfg, bool set_err) {
            "conv2d_tc: pixel-shuffle mode needs r=8 and a dense 32-channel output map");
   const size_t yes = elem_size(c->y.dtype);
   // fast path: no channel padding (every accumulator chunk lies inside cout) and 16-byte aligned rows
-  bool vec = cout == cpad && ((c->y.c_off * yes) % 16) == 0 && ((c->y.c_pitch * yes) % 16) == 0 &&
-             ((uintptr_t)c->y.data % 16) == 0;
+  bool vec = ((c->y.c_off * yes) % 16) == 0 && ((c->y.c_pitch * yes) % 16) == 0 && ((uintptr_t)c->y.data % 16) == 0;
   if (c->residual.data) {
     TC_REQ(r == 1 && view_ok(&c->residual) && c->residual.n == c->y.n && c->residual.h == c->y.h &&
                c->residual.w == c->y.w && c->residual.c == c->y.c,
@@ -1026,6 +1026,8 @@ static int tc_plan(const dbsr_conv_t* c, TcConfig* cfg, bool set_err) {
           ((uintptr_t)c->residual.data % 16) == 0;
   }
   if (c->bias) vec = vec && ((uintptr_t)c->bias % 16) == 0;
+  cfg->align_ok = vec ? 1 : 0;
+  vec = vec && cout == cpad;
   cfg->vec_ok = vec ? 1 : 0;
   cfg->n_tile = nt;
   cfg->ck = ck;
@@ -1117,6 +1119,8 @@ static int tc_plan(const dbsr_conv_t* c, TcConfig* cfg, bool set_err) {
 
 // A 3x3 "same" convolution of a 1x1 map only ever sees its centre tap (the other eight read zero padding): run it as
 // the 1x1 convolution with that tap's weight tile (PWC-Net level 6 at 48^2 / 64^2 inputs: 9 launches per forward).
+// A 1x1 convolution does not care which pixels are neighbours, so n maps of 1x1 are then viewed as ONE image of
+// (n / 8) x 8 pixels (they are contiguous in memory): full 16x8 M tiles instead of one pixel per 128-row tile.
 static dbsr_conv_t centre_tap_form(const dbsr_conv_t* c) {
   dbsr_conv_t cc = *c;
   if (c->ksize == 3 && c->x.h == 1 && c->x.w == 1 && c->w && c->shuffle_r <= 1 && c->x.c > 0 && c->y.c > 0) {
@@ -1124,6 +1128,13 @@ static dbsr_conv_t centre_tap_form(const dbsr_conv_t* c) {
     tc_geometry(c->x.c, c->y.c, &ck, &kpad, &nt, &cpad);
     cc.ksize = 1; cc.dilation = 1;
     cc.w = reinterpret_cast<const __nv_bfloat16*>(c->w) + (size_t)4 * cpad * kpad;      // packed [tap][cout_pad][kpad]
+  }
+  if (cc.ksize == 1 && cc.x.h == 1 && cc.x.w == 1 && cc.x.n % 8 == 0 && cc.x.n >= 16 && cc.shuffle_r <= 1 &&
+      cc.y.h == 1 && cc.y.w == 1 && cc.y.n == cc.x.n) {
+    const int rows = cc.x.n / 8;
+    cc.x.n = 1; cc.x.h = rows; cc.x.w = 8;
+    cc.y.n = 1; cc.y.h = rows; cc.y.w = 8;
+    if (cc.residual.data && cc.residual.h == 1 && cc.residual.w == 1) { cc.residual.n = 1; cc.residual.h = rows; cc.residual.w = 8; }
   }
   return cc;
 }
@@ -1254,7 +1265,7 @@ extern "C" int dbsr_conv2d_tc(const dbsr_conv_t* c_in, void* stream) {
   p.n = c->x.n; p.H = c->x.h; p.W = c->x.w;
   p.ksize = c->ksize; p.dil = c->dilation;
   p.nchunks = cfg.nchunks; p.cout_pad = cfg.cout_pad; p.cout = cfg.cout; p.n_tile = cfg.n_tile; p.mt = cfg.mt;
-  p.tmem_cols = cfg.tmem_cols; p.vec_ok = cfg.vec_ok;
+  p.tmem_cols = cfg.tmem_cols; p.vec_ok = cfg.vec_ok; p.align_ok = cfg.align_ok;
   p.ntiles_n = cfg.cout_pad / cfg.n_tile;
   p.items_x = cfg.pair_img ? 1 : ceil_div(p.W, TILE_W * cfg.mt); p.tiles_y = ceil_div(p.H, TILE_H);
   p.flat = cfg.flat; p.flat_s = cfg.flat_s; p.flat_ni = cfg.flat_ni;

@@ -50,6 +50,11 @@ TC_CASES = {
     'narrow_8x8_pair_136x128_n301': (136, 128, 3, 1, 301, 8, 8, 2, False, False, 0),
     'narrow_8x5_pair_64x64_n297_k1': (64, 64, 1, 1, 297, 8, 5, 1, False, False, 0),
     'narrow_20x8_pair_32x32_n300': (32, 32, 3, 1, 300, 20, 8, 1, False, False, 0),
+    # 1x1 maps, image count a multiple of 8: centre tap only, the n maps viewed as one (n/8) x 8 image
+    'centre_1x1_196x196_n448': (196, 196, 3, 1, 448, 1, 1, 2, False, False, 0),
+    'centre_1x1_512x196_n448_res': (512, 192, 3, 1, 448, 1, 1, 1, True, False, 0),
+    'centre_1x1_529x2_f32_n416': (529, 2, 3, 1, 416, 1, 1, 0, False, True, 0),
+    'k1_1x1_529x32_f32_n416': (529, 32, 1, 1, 416, 1, 1, 0, False, True, 0),
 }
 
 
