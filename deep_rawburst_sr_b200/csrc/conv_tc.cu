@@ -1047,9 +1047,7 @@ static int tc_plan(const dbsr_conv_t* c, TcConfig* cfg, bool set_err) {
     const int S = (c->x.h + 2) * (c->x.w + 2);
     const int last = (c->x.h - 1) * (c->x.w + 2) + (c->x.w - 1);
     const int ni = (127 - last) / S + 1;
-    int ni_use = ni;
-    if (const char* e = getenv("DBSR_TC_FLAT_NI")) { const int v = atoi(e); if (v >= 1 && v < ni) ni_use = v; }   // debug knob
-    if (ni >= 2) { cfg->flat = 1; cfg->flat_s = S; cfg->flat_ni = ni_use; }
+    if (ni >= 2) { cfg->flat = 1; cfg->flat_s = S; cfg->flat_ni = ni; }
   }
   bool found = false;
   cfg->pair_img = 0;
@@ -1158,10 +1156,9 @@ static int launch_tc(const CUtensorMap& mx, const CUtensorMap& mw, const CUtenso
     cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
   }
   int grid = (int)(p.total_items < num_sms ? p.total_items : num_sms);
-  if (const char* e = getenv("DBSR_TC_GRID")) { const int g = atoi(e); if (g > 0 && g < grid) grid = g; }   // debug knob
   // programmatic dependent launch: CTAs may be scheduled (barrier init, tensor-map prefetch, TMEM allocation) as soon as
   // the SMs of the preceding kernel drain; the kernel calls griddepcontrol.wait before its first global access
-  static const bool pdl = getenv("DBSR_TC_NO_PDL") == nullptr;
+  static const bool pdl = getenv("DBSR_TC_NO_PDL") == nullptr;     // A/B switch: DBSR_TC_NO_PDL=1 launches normally
   cudaLaunchConfig_t lc = {};
   lc.gridDim = dim3((unsigned)grid); lc.blockDim = dim3(TC_THREADS); lc.dynamicSmemBytes = (size_t)smem; lc.stream = st;
   cudaLaunchAttribute attr[1];
