@@ -109,6 +109,35 @@ def test_batch_invariance_and_reuse(dev):
         assert torch.equal(p_i[0], p_all[i])
 
 
+@pytest.mark.parametrize('B,N,S', [(32, 14, 48), (16, 14, 80)])
+def test_full_size_configs_burst_independence(dev, B, N, S):
+    """BASELINE.json configs[1] / configs[2] at full size (where the oracle takes minutes): size-independent properties.
+    Bursts are independent on this path, so (a) every burst of the full batch is bit-identical to the same burst run in a
+    batch of 2 (different tile packing, pair / flat grouping and item counts in every kernel), (b) CUDA-graph replay equals
+    eager, (c) one burst of the batch agrees with the CPU oracle's fp32 forward within the bf16 tolerance, (d) the
+    offsets of the reference frame pairs are finite and the output is finite everywhere."""
+    sd = O.make_state_dict(0)
+    net = _net(sd, dev, 'bf16')
+    net.return_fusion_weights = False
+    burst = O.make_burst(77, B, N, S, S)
+    p_all, aux = net(burst.to(dev))
+    p_all = p_all.clone()
+    assert torch.isfinite(p_all).all() and torch.isfinite(aux['offsets']).all()
+    assert p_all.shape == (B, 3, 8 * S, 8 * S) and aux['offsets'].shape == (B, N - 1, 2, S, S)
+    for i in (0, B // 2 - 1, B - 2):
+        p_2, _ = net(burst[i:i + 2].to(dev))
+        assert torch.equal(p_2, p_all[i:i + 2]), f'burst {i} differs between batch {B} and batch 2'
+    net.use_cuda_graph = True
+    for _ in range(2):
+        p_g, _ = net(burst.to(dev))
+    assert torch.equal(p_g, p_all)
+    if S == 48:      # one burst against the oracle's library-op forward (a second of CPU)
+        ref = O.dbsr_forward_fast(burst[B - 1:B], sd)
+        ref = ref[0] if isinstance(ref, (tuple, list)) else ref
+        err = (p_all[B - 1:B].cpu() - ref).abs().max().item()
+        assert err <= 1e-2, err
+
+
 def test_module_seams_match_fused_path(dev):
     """encoder -> merging -> decoder called one by one (NCHW dict seams of the reference) == fused engine path"""
     sd = O.make_state_dict(1)
