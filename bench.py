@@ -164,11 +164,13 @@ def main():
     if world > 1:
         dist.init_process_group('nccl', device_id=dev)
 
-    from oracle import dbsr_oracle as O   # weight recipe only (random-init weights of the reference architecture)
+    # random-init weights of the reference architecture: the modules' own default initialisation (+ ICNR), as the
+    # reference's factory would produce without a checkpoint.  The product arm never touches oracle/.
     from deep_rawburst_sr_b200.models.dbsr.dbsrnet import dbsrnet_default_synthetic
+    torch.manual_seed(0)
     net = dbsrnet_default_synthetic()
-    net.load_state_dict(O.make_state_dict(0), strict=True)
     net = net.to(dev).eval().set_precision(args.precision)
+    net.use_cuda_graph = not args.no_graph     # the ~137 launches of one forward are captured once per shape and replayed
     eng = net.engine(dev)
 
     B, S = args.batch, args.size
@@ -220,6 +222,33 @@ def main():
     ms_total = max_over_ranks(e0.elapsed_time(e1))
     launches = eng.launches
     value = world * B * args.steps / (ms_total / 1e3)
+
+    # ---- N > 1: the same K forwards, each followed by the NCCL all-gather of `pred` over NVLink on a side stream
+    #      (SURVEY.md 8e output gather; OutputGatherer double-buffers so the gather of step i overlaps forward i+1)
+    gather = None
+    if world > 1:
+        try:
+            from deep_rawburst_sr_b200.sharding import OutputGatherer
+            gat = OutputGatherer(B * world, depth=2)
+            for _ in range(2):
+                pred, _aux = net(dev_in)
+                _full, gev = gat.submit(pred)
+            barrier()
+            e0.record()
+            for _ in range(args.steps):
+                pred, _aux = net(dev_in)
+                _full, gev = gat.submit(pred)
+            torch.cuda.current_stream().wait_event(gev)
+            e1.record()
+            barrier()
+            ms_g = max_over_ranks(e0.elapsed_time(e1))
+            gather = {'value': world * B * args.steps / (ms_g / 1e3), 'unit': 'bursts/s', 'ms_per_step': ms_g / args.steps,
+                      'collective': 'nccl all_gather_into_tensor of pred on a side stream, overlapped with the next forward',
+                      'bytes_gathered_per_rank_per_step': int(_full.numel() * 4),
+                      'gathered_shape': list(_full.shape)}
+        except Exception as ex:      # the gather is the caller's choice, not part of `value`: report, do not fail the bench
+            gather = {'error': repr(ex)[:200]}
+        barrier()
 
     # ---- end to end with HOST buffers, every step: H2D of the burst from pinned memory + forward + D2H of pred.
     #      (a) the public host-buffer front end (HostPipeline: the copies of neighbouring steps overlap the compute on
@@ -332,6 +361,7 @@ def main():
 
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
+        from oracle import dbsr_oracle as O   # cpu_baseline leg only: the reference algorithm on the host cores
         cores = os.cpu_count() or 1
         torch.set_num_threads(cores)
         sd = O.make_state_dict(0)
@@ -362,7 +392,7 @@ def main():
                 'api': 'deep_rawburst_sr_b200.pipeline.HostPipeline.submit(host_in, host_out)',
                 'serialised_copies': {'value': e2e_sync, 'ms_per_step': ms_e2e_sync / args.steps,
                                       'api': 'net(host_in.to(device)) ; host_out.copy_(pred)'}},
-        'gpu_launches': launches, 'cuda_graph': not args.no_graph,
+        'gpu_launches': launches, 'cuda_graph': not args.no_graph, 'output_gather': gather,
         'roofline': roofline,
         'kernel_families': families,
         'cpu_baseline': cpu,

@@ -1,0 +1,169 @@
+#!/usr/bin/env python
+"""Microbenchmark of the HBM-bound kernels of the DBSR path (BASELINE.json configs[3]: "PWCNet alignment + warp-fuse
+microbench only: 14-frame 64-channel embeddings at 96x96 and 160x160 flow resolution"; shapes from SURVEY.md 8(d)).
+
+    python bench_micro.py [--iters K] [--warmup W] [--bursts B] [--out file.json]
+
+Three legs, every one through the C ABI (`ops.*` -> libdbsr_b200.so), one JSON line each (rank 0 / one GPU):
+
+* `corr81`      cost volume (correlation.py:280-330 + the fused backwarp / LeakyReLU of pwcnet.py:161,169) at the five
+                pyramid level shapes of a 96^2 and a 160^2 frame, 13*B pairs: achieved HBM GB/s = algorithmic bytes
+                (f1 + f2 read once, 81-channel volume written once) / device time, against the measured HBM peak.
+* `warp_fuse`   fused bilinear warp + softmax over the burst + weighted sum (warp.py:19-46, merging.py:117-124):
+                C=64 at S=96,160 (the cfg-4 stress shape) and the network's real shape C=512 at S=48,80; flows
+                U(-4,4) px so that out-of-image taps occur.  Bytes: (28*C*s + 13*2*4)*S^2 + C*s*S^2 per burst.
+* `pwc_align`   the whole PWC-Net alignment of a burst batch (pwcnet.py:248-281) at 96^2 / 160^2: pairs/s.
+
+Timing: CUDA events on the launching stream around EVERY launch, W warm-up launches, and the L2 is flushed between
+timed launches (a 512 MB buffer is overwritten), so small level shapes cannot be served from the 126 MB L2.
+The median launch time is reported (min next to it).
+"""
+import argparse
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+FRAMES = 14
+EXT_CH = {2: 32, 3: 64, 4: 96, 5: 128, 6: 196}
+
+
+def peak_hbm():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        return json.load(open(p))['hbm_gbs'], 'measured'
+    return 6650.0, 'fallback'
+
+
+class Timer:
+    def __init__(self, dev, iters, warmup):
+        self.iters, self.warmup = iters, warmup
+        self.flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
+
+    def __call__(self, fn):
+        for _ in range(self.warmup):
+            fn()
+        evs = []
+        for _ in range(self.iters):
+            self.flush.zero_()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            fn()
+            b.record()
+            evs.append((a, b))
+        torch.cuda.synchronize()
+        t = sorted(a.elapsed_time(b) for a, b in evs)
+        return t[len(t) // 2], t[0]
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--iters', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--bursts', type=int, default=8, help='bursts per launch (13 pairs each)')
+    ap.add_argument('--legs', default='corr81,warp_fuse,pwc_align')
+    ap.add_argument('--out', default='')
+    args = ap.parse_args()
+    from deep_rawburst_sr_b200 import ops
+    from deep_rawburst_sr_b200.ops import ACT_LRELU, Act
+    dev = torch.device('cuda', int(os.environ.get('LOCAL_RANK', '0')))
+    torch.cuda.set_device(dev)
+    ops.require_device(torch.empty(1, device=dev))
+    timer = Timer(dev, args.iters, args.warmup)
+    peak, peak_src = peak_hbm()
+    B = args.bursts
+    P = B * (FRAMES - 1)
+    lines = []
+
+    def emit(d):
+        d.update({'peak_gbs': peak, 'peak_source': peak_src, 'l2': 'flushed between launches (512 MB overwrite)'})
+        lines.append(d)
+        print(json.dumps(d), flush=True)
+
+    legs = args.legs.split(',')
+    g = torch.Generator().manual_seed(4)
+
+    def padded(t, dt):
+        """[n, h, w, c] host tensor -> device Act whose pixel pitch is rounded up to 8 channels (the engine's layout)"""
+        n, h, w, c = t.shape
+        a = Act.empty(n, h, w, (c + 7) // 8 * 8, dt, dev, zero=True)
+        a.buf[..., :c] = t.to(dev).to(dt)
+        return a.slice(0, c)
+    if 'corr81' in legs:
+        for S in (96, 160):
+            hp = (S + 63) // 64 * 64
+            for dt in (torch.bfloat16, torch.float32):
+                es = 2 if dt == torch.bfloat16 else 4
+                tot_b, tot_ms = 0, 0.0
+                per_level = []
+                for lvl in (2, 3, 4, 5, 6):
+                    C, h = EXT_CH[lvl], hp >> lvl
+                    f1 = padded(torch.randn(P, h, h, C, generator=g), dt)
+                    f2 = padded(torch.randn(P, h, h, C, generator=g), dt)
+                    vol = Act.empty(P, h, h, 88, dt, dev, zero=True).slice(0, 81)
+                    flow = padded((torch.rand(P, h, h, 2, generator=g) * 2 - 1) * 0.5, torch.float32) if lvl < 6 else None
+                    med, mn = timer(lambda: ops.corr81(f1, f2, vol, P, 0, flow=flow, flow_scale=1.0 if flow is not None else 0.0,
+                                                       act=ACT_LRELU))
+                    nbytes = P * (2 * C + 81) * h * h * es
+                    per_level.append({'level': lvl, 'C': C, 'h': h, 'us': med * 1e3, 'us_min': mn * 1e3,
+                                      'gbs': nbytes / med / 1e6, 'bytes': nbytes})
+                    tot_b += nbytes
+                    tot_ms += med
+                big = per_level[0]
+                emit({'leg': 'corr81', 'frame': S, 'pairs': P, 'dtype': 'bf16' if es == 2 else 'f32',
+                      'algorithmic_bytes': tot_b, 'us_all_levels': tot_ms * 1e3, 'hbm_gbs_all_levels': tot_b / tot_ms / 1e6,
+                      'hbm_gbs_level2': big['gbs'], 'hbm_frac_level2': big['gbs'] / peak, 'levels': per_level})
+    if 'warp_fuse' in legs:
+        for C, S, nb in ((64, 96, B), (64, 160, B), (512, 48, 4 * B), (512, 80, 2 * B)):
+            for dt in (torch.bfloat16, torch.float32):
+                es = 2 if dt == torch.bfloat16 else 4
+                feat = Act(torch.rand(nb * FRAMES, S, S, C, generator=g).to(dev).to(dt))
+                logits = Act(torch.randn(nb * FRAMES, S, S, C, generator=g).to(dev).to(dt))
+                fused = Act.empty(nb, S, S, C, dt, dev)
+                for amp in (4.0, 0.8):
+                    offs = ((torch.rand(nb * (FRAMES - 1), 2, S, S, generator=g) * 2 - 1) * amp).to(dev)
+                    med, mn = timer(lambda: ops.softmax_wsum(feat, logits, fused, FRAMES, offsets=offs))
+                    nbytes = nb * ((2 * FRAMES * C * es + (FRAMES - 1) * 2 * 4) * S * S + C * es * S * S)
+                    emit({'leg': 'warp_fuse', 'C': C, 'S': S, 'bursts': nb, 'dtype': 'bf16' if es == 2 else 'f32',
+                          'flow_px': amp, 'algorithmic_bytes': nbytes, 'us': med * 1e3, 'us_min': mn * 1e3,
+                          'hbm_gbs': nbytes / med / 1e6, 'hbm_frac': nbytes / med / 1e6 / peak})
+                del feat, logits, fused
+    if 'pwc_align' in legs:
+        from deep_rawburst_sr_b200.engine import DBSREngine
+        from deep_rawburst_sr_b200.models.alignment.pwcnet import PWCNet
+        torch.manual_seed(0)
+        sd = {'encoder.alignment_net.' + k: v for k, v in PWCNet(load_pretrained=False).state_dict().items()}
+        for prec in ('bf16', 'fp32'):
+            eng = DBSREngine(sd, dev, precision=prec, parts=('pwc',))
+            for S in (96, 160):
+                nb = B if prec == 'bf16' else max(1, B // 4)
+                hp = (S + 63) // 64 * 64
+                burst = torch.rand(nb, FRAMES, 4, S, S, generator=g).to(dev)
+                ws = eng.workspace(('micro', nb, S))
+                enc_in = eng._buf(ws, 'enc_in', nb * FRAMES, S, S, 8, eng.act_dtype)
+                pwc_in = eng._buf(ws, 'pwc_in', nb * FRAMES, hp, hp, 4, torch.float32)
+                offsets = torch.empty((nb * (FRAMES - 1), 2, S, S), dtype=torch.float32, device=dev)
+
+                def run():
+                    ops.prep_burst(burst, enc_in, pwc_in)
+                    eng.pwc_burst(ws, pwc_in, nb, FRAMES, S, S, offsets)
+                n0 = eng.launches
+                med, mn = timer(run)
+                emit({'leg': 'pwc_align', 'frame': S, 'bursts': nb, 'pairs': nb * (FRAMES - 1), 'precision': prec,
+                      'ms': med, 'ms_min': mn, 'pairs_per_s': nb * (FRAMES - 1) / med * 1e3,
+                      'launches': (eng.launches - n0) // (args.iters + args.warmup) + 1,
+                      'finite': bool(torch.isfinite(offsets).all().item())})
+                del burst
+                eng._ws.clear()
+    if args.out:
+        with open(args.out, 'w') as f:
+            for d in lines:
+                f.write(json.dumps(d) + '\n')
+
+
+if __name__ == '__main__':
+    main()

@@ -60,10 +60,15 @@ struct CorrParams {
   float flow_scale;
   int group, act;
   int tiles_x;
+  int vec_out;      // 1: the 81-channel volume is stored as 11 groups of 8 channels (the 7 pad channels are zeroed)
 };
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  const __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
 
 template <bool VEC, typename T>
-__global__ void __launch_bounds__(CORR_THREADS) corr81_kernel(const CorrParams p) {
+__global__ void __launch_bounds__(CORR_THREADS, 2) corr81_kernel(const CorrParams p) {
   griddep_wait();
   extern __shared__ __align__(16) float smem[];
   float* f2_s = smem;                                // [HALO_H*HALO_W][32]
@@ -212,20 +217,47 @@ __global__ void __launch_bounds__(CORR_THREADS) corr81_kernel(const CorrParams p
     __syncthreads();
   }
 
-  // ---- epilogue: scale, activation, transpose through smem for coalesced 81-channel rows
-  float* out_s = smem;  // [128][81]
+  // ---- epilogue: scale, activation, transpose through smem.  out_s is displacement-major [81][OUT_P]: a thread's four
+  // pixels of one displacement are one conflict-free STS.128 (a warp covers the 128 consecutive pixels of the tile).
+  float* out_s = smem;
+  constexpr int OUT_P = CT_H * CT_W + 4;
   const float invC = 1.0f / (float)C;
-  (void)invC;
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
-#pragma unroll
-    for (int d = 0; d < 9; ++d)
-      out_s[(row * CT_W + strip * 4 + i) * 81 + dy * 9 + d] = apply_act(acc[i][d] / (float)C, p.act);
+  for (int d = 0; d < 9; ++d) {
+    float4 v;
+    v.x = apply_act(acc[0][d] * invC, p.act); v.y = apply_act(acc[1][d] * invC, p.act);
+    v.z = apply_act(acc[2][d] * invC, p.act); v.w = apply_act(acc[3][d] * invC, p.act);
+    *reinterpret_cast<float4*>(&out_s[(dy * 9 + d) * OUT_P + row * CT_W + strip * 4]) = v;
+  }
   __syncthreads();
-  for (int e = t; e < th * CT_W * 81; e += CORR_THREADS) {
-    const int pix = e / 81, ch = e - pix * 81;
-    const int y = ty0 + pix / CT_W, x = tx0 + pix % CT_W;
-    if (y < H && x < W) view_st(p.out, (long long)pair * H * W + (long long)y * W + x, ch, out_s[e]);
+  if (p.vec_out) {
+    // 16-byte (bf16) / 2 x 16-byte (fp32) stores of 8 displacements; the 7 channels after the 81st are the pad of the
+    // volume's 8-aligned concat segment (host-checked: c_off + 88 <= c_pitch) and are written as zeros
+    for (int e = t; e < 11 * CT_H * CT_W; e += CORR_THREADS) {
+      const int pix = e & (CT_H * CT_W - 1), g = e >> 7;
+      const int y = ty0 + pix / CT_W, x = tx0 + pix % CT_W;
+      if (y < H && x < W) {
+        float v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = (g * 8 + j < 81) ? out_s[(g * 8 + j) * OUT_P + pix] : 0.0f;
+        const long long o = ((long long)pair * H * W + (long long)y * W + x) * p.out.c_pitch + p.out.c_off + g * 8;
+        if (p.out.dtype == DBSR_BF16) {
+          uint4 q;
+          q.x = pack_bf16x2(v[0], v[1]); q.y = pack_bf16x2(v[2], v[3]); q.z = pack_bf16x2(v[4], v[5]); q.w = pack_bf16x2(v[6], v[7]);
+          *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out.data) + o) = q;
+        } else {
+          float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out.data) + o);
+          dst[0] = make_float4(v[0], v[1], v[2], v[3]);
+          dst[1] = make_float4(v[4], v[5], v[6], v[7]);
+        }
+      }
+    }
+  } else {
+    for (int e = t; e < 81 * CT_H * CT_W; e += CORR_THREADS) {
+      const int pix = e & (CT_H * CT_W - 1), ch = e >> 7;
+      const int y = ty0 + pix / CT_W, x = tx0 + pix % CT_W;
+      if (y < H && x < W) view_st(p.out, (long long)pair * H * W + (long long)y * W + x, ch, out_s[ch * OUT_P + pix]);
+    }
   }
 }
 
@@ -335,6 +367,9 @@ extern "C" int dbsr_corr81(const dbsr_nhwc_t* f1, const dbsr_nhwc_t* f2, const d
   p.f1 = make_view(f1); p.f2 = make_view(f2); p.flow = make_view(has_flow ? flow : nullptr); p.out = make_view(out);
   p.flow_scale = flow_scale; p.group = group; p.act = act;
   p.tiles_x = ceil_div(f1->w, CT_W);
+  const int out_es = out->dtype == DBSR_BF16 ? 2 : 4;
+  p.vec_out = out->c_off % 8 == 0 && out->c_pitch % 8 == 0 && out->c_off + 88 <= out->c_pitch &&
+              ((uintptr_t)out->data + (size_t)out->c_off * out_es) % 16 == 0;
   dim3 grid(p.tiles_x * ceil_div(f1->h, CT_H), pairs);
   // vectorised staging needs 8-channel groups on 16-byte (bf16) / 32-byte (fp32) boundaries in both feature maps
   auto vec_ok = [](const dbsr_nhwc_t* v) {
@@ -363,6 +398,10 @@ extern "C" int dbsr_corr81(const dbsr_nhwc_t* f1, const dbsr_nhwc_t* f2, const d
   if (!attr_set[ki]) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, CORR_SMEM);
     DBSR_REQUIRE(e == cudaSuccess, "corr81: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
+    // ncu: with the default carve-out the driver sized shared memory for ONE 64 KB CTA per SM (9 warps, 69 % of the
+    // cycles without an eligible warp); ask for the maximum so that two CTAs overlap staging and accumulation
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    DBSR_REQUIRE(e == cudaSuccess, "corr81: carve-out attribute failed: %s", cudaGetErrorString(e));
     attr_set[ki] = true;
   }
   launch_pdl(kern, grid, dim3(CORR_THREADS), (size_t)CORR_SMEM, (cudaStream_t)stream, p);

@@ -384,13 +384,14 @@ softmax_wsum8_kernel(View feat, View logits, const float* __restrict__ offsets, 
 // only cp.async.wait_group.  Out-of-image taps are zero-filled by the copy (src-size 0), which is grid_sample's
 // zero padding, so the weights need no mask.
 // ---------------------------------------------------------------------------------------------------------
-#ifndef WS_STAGES_N
-#define WS_STAGES_N 3
-#endif
-constexpr int WS_STAGES = WS_STAGES_N;
-constexpr int WS_ASYNC_SMEM = WS_STAGES * 5 * 256 * 16;
+constexpr int ws_async_smem(int stages) { return stages * 5 * 256 * 16; }
 __device__ __forceinline__ void cp_async_16(uint32_t dst, const void* src, uint32_t bytes) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(bytes) : "memory");
+}
+// L1-allocating form for the bilinear taps: the four taps of neighbouring pixels overlap (a tile of 8x4 pixels touches
+// ~9x5 distinct 128-byte lines with 128 requests), so letting L1 merge them cuts the L2 -> SM traffic of the gather
+__device__ __forceinline__ void cp_async_16_ca(uint32_t dst, const void* src, uint32_t bytes) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ Vec8 unpack_bf16x8(const uint4& q) {
   Vec8 r;
@@ -400,8 +401,8 @@ __device__ __forceinline__ Vec8 unpack_bf16x8(const uint4& q) {
   r.v[6] = __uint_as_float(q.w << 16); r.v[7] = __uint_as_float(q.w & 0xFFFF0000u);
   return r;
 }
-template <typename TO>
-__global__ void __launch_bounds__(256, (WS_STAGES_N >= 4) ? 2 : 3)
+template <typename TO, int WS_STAGES, bool TAPS_L1>
+__global__ void __launch_bounds__(256, (WS_STAGES >= 4) ? 2 : 3)
 softmax_wsum8_async_kernel(View feat, View logits, const float* __restrict__ offsets, View fused, int frames) {
   griddep_wait();
   extern __shared__ __align__(16) uint4 ring[];        // [WS_STAGES][5][256]
@@ -445,8 +446,9 @@ softmax_wsum8_async_kernel(View feat, View logits, const float* __restrict__ off
     for (int k = 0; k < 4; ++k) {
       const int xx = x0 + (k & 1), yy = y0 + (k >> 1);
       const bool ok = xx >= 0 && xx < W && yy >= 0 && yy < H;
-      cp_async_16(dst + (uint32_t)((1 + k) * 256 * 16), ok ? (const void*)(ib + (long long)(yy * W + xx) * feat.c_pitch) : (const void*)fbase,
-                  ok ? 16u : 0u);
+      const void* src = ok ? (const void*)(ib + (long long)(yy * W + xx) * feat.c_pitch) : (const void*)fbase;
+      if (TAPS_L1) cp_async_16_ca(dst + (uint32_t)((1 + k) * 256 * 16), src, ok ? 16u : 0u);
+      else cp_async_16(dst + (uint32_t)((1 + k) * 256 * 16), src, ok ? 16u : 0u);
     }
   };
 #pragma unroll
@@ -500,6 +502,168 @@ softmax_wsum8_async_kernel(View feat, View logits, const float* __restrict__ off
   Vec8 r;
 #pragma unroll
   for (int k = 0; k < 8; ++k) r.v[k] = acc[k] / s[k];
+  if (live) st8<TO>(obase + ((long long)b * HW + rem) * fused.c_pitch + ch, r);
+}
+
+
+// ---------------------------------------------------------------------------------------------------------
+// Lean pair-pipelined variant.  ncu on the kernel above (B=32, 48^2): Issue Slots Busy 88 %, IPC 3.5, DRAM 35 % -- it
+// is INSTRUCTION bound, ~370 warp instructions per thread-frame, of which ~150 are address arithmetic (64-bit image
+// offsets, four tap offsets, bounds tests, ring slot modulo) repeated by each of the 8 channel-group threads of a pixel
+// for every frame.  Here that work is done ONCE per (pixel, frame) before the loop: a 32-byte record
+// {4 byte offsets of the clamped taps, 4 bilinear weights with out-of-image taps zeroed} in shared memory, so that the
+// per-frame issue path is 1 LDS.128 + pointer bumps + 5 cp.async, and the consume path needs no masks.  Frames are
+// processed in PAIRS (ring = 2 stages x 2 frames): the online softmax rescales the running sum once per pair
+// (3 exponentials per 2 frames, no selects).  BF2 = true additionally does the bilinear interpolation in packed
+// bf16x2 arithmetic (HFMA2.BF16: 16 instead of 64 unpack + FMA instructions per frame).
+// ---------------------------------------------------------------------------------------------------------
+struct __align__(16) WsRec { uint32_t o[4]; float w[4]; };
+constexpr int WSP_MAX_OTHERS = 16;
+constexpr int WSP_SMEM = 2 * 2 * 5 * 256 * 16;           // ring: [2 stages][2 frames][5 loads][256 threads] x 16 bytes
+__device__ __forceinline__ float ex2f(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+template <typename TO, bool BF2>
+__global__ void __launch_bounds__(256, 2)
+softmax_wsum8_pair_kernel(View feat, View logits, const float* __restrict__ offsets, View fused, int frames) {
+  griddep_wait();
+  extern __shared__ __align__(16) uint4 ring[];
+  __shared__ WsRec rec_s[32][WSP_MAX_OTHERS];
+  const int H = fused.h, W = fused.w;
+  const int HW = H * W;
+  const __nv_bfloat16* fbase = reinterpret_cast<const __nv_bfloat16*>(feat.data) + feat.c_off;
+  const __nv_bfloat16* lbase = reinterpret_cast<const __nv_bfloat16*>(logits.data) + logits.c_off;
+  TO* obase = reinterpret_cast<TO*>(fused.data) + fused.c_off;
+  const int tiles_x = (W + WS_TW - 1) / WS_TW;
+  const int tid = threadIdx.x;
+  const int g = tid & 7, pix = tid >> 3, px = pix & 7, py = pix >> 3;
+  const int b = blockIdx.z;
+  const int ch_raw = blockIdx.y * 64 + g * 8;
+  const int ch = min(ch_raw, fused.c - 8);   // clamped for the loads; the store is predicated on `live`
+  const int y_raw = (blockIdx.x / tiles_x) * WS_TH + py, x_raw = (blockIdx.x % tiles_x) * WS_TW + px;
+  const bool live = y_raw < H && x_raw < W && ch_raw < fused.c;
+  const int y = min(y_raw, H - 1), x = min(x_raw, W - 1);
+  const int rem = y * W + x;
+  const int others = frames - 1;
+  // ---- per (pixel, frame) gather records, computed by the 8 channel-group threads of the pixel (2 frames each)
+#pragma unroll
+  for (int q = 0; q < 2; ++q) {
+    const int k = g + 8 * q;
+    if (k < others) {
+      const long long pr = (long long)b * others + k;
+      const float u = (float)x + __ldg(offsets + (pr * 2 + 0) * HW + rem);
+      const float v = (float)y + __ldg(offsets + (pr * 2 + 1) * HW + rem);
+      const float fu = floorf(u), fv = floorf(v);
+      const float ax = u - fu, ay = v - fv;
+      const int x0 = (int)fminf(fmaxf(fu, -2.0f), (float)W), y0 = (int)fminf(fmaxf(fv, -2.0f), (float)H);
+      const bool okx0 = x0 >= 0 && x0 < W, okx1 = x0 + 1 >= 0 && x0 + 1 < W;
+      const bool oky0 = y0 >= 0 && y0 < H, oky1 = y0 + 1 >= 0 && y0 + 1 < H;
+      const int x0c = min(max(x0, 0), W - 1), x1c = min(max(x0 + 1, 0), W - 1);
+      const int y0c = min(max(y0, 0), H - 1), y1c = min(max(y0 + 1, 0), H - 1);
+      const uint32_t pb = (uint32_t)feat.c_pitch * 2u;
+      WsRec r;
+      r.o[0] = (uint32_t)(y0c * W + x0c) * pb; r.o[1] = (uint32_t)(y0c * W + x1c) * pb;
+      r.o[2] = (uint32_t)(y1c * W + x0c) * pb; r.o[3] = (uint32_t)(y1c * W + x1c) * pb;
+      r.w[0] = (okx0 && oky0) ? (1.0f - ax) * (1.0f - ay) : 0.0f; r.w[1] = (okx1 && oky0) ? ax * (1.0f - ay) : 0.0f;
+      r.w[2] = (okx0 && oky1) ? (1.0f - ax) * ay : 0.0f;          r.w[3] = (okx1 && oky1) ? ax * ay : 0.0f;
+      rec_s[pix][k] = r;
+    }
+  }
+  __syncwarp();     // a pixel's 8 threads are in one warp
+  const uint32_t ring_s = (uint32_t)__cvta_generic_to_shared(ring) + (uint32_t)tid * 16u;
+  const size_t lstride = (size_t)HW * logits.c_pitch * 2, fstride = (size_t)HW * feat.c_pitch * 2;
+  const char* l0 = reinterpret_cast<const char*>(lbase + ((long long)b * frames * HW + rem) * logits.c_pitch + ch);
+  const char* f0 = reinterpret_cast<const char*>(fbase + (long long)b * frames * HW * feat.c_pitch + ch);
+  const char* lq = l0 + lstride;        // next frame to issue (frame 1)
+  const char* fq = f0 + fstride;
+  int nq = 1;
+  auto issue_pair = [&](uint32_t dst) {   // the next two frames -> ring stage at dst (skips frames past the burst)
+#pragma unroll
+    for (int f = 0; f < 2; ++f) {
+      if (nq < frames) {
+        const uint32_t d = dst + (uint32_t)(f * 5 * 4096);
+        cp_async_16(d, lq, 16u);
+        const uint4 o = *reinterpret_cast<const uint4*>(rec_s[pix][nq - 1].o);
+        cp_async_16(d + 4096u, fq + o.x, 16u);
+        cp_async_16(d + 8192u, fq + o.y, 16u);
+        cp_async_16(d + 12288u, fq + o.z, 16u);
+        cp_async_16(d + 16384u, fq + o.w, 16u);
+        lq += lstride; fq += fstride; ++nq;
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  issue_pair(ring_s);
+  issue_pair(ring_s + 2u * 5u * 4096u);
+  // reference frame (never warped): plain loads while the ring fills.  The running maximum m is kept in log2 units.
+  constexpr float LOG2E = 1.4426950408889634f;
+  float m[8], s[8], acc[8];
+  {
+    const Vec8 l = ld8<__nv_bfloat16>(reinterpret_cast<const __nv_bfloat16*>(l0));
+    const Vec8 a = ld8<__nv_bfloat16>(reinterpret_cast<const __nv_bfloat16*>(f0 + (size_t)rem * feat.c_pitch * 2));
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { m[k] = l.v[k] * LOG2E; s[k] = 1.0f; acc[k] = a.v[k]; }
+  }
+  const int npairs = (others + 1) >> 1;
+  for (int pp = 0; pp < npairs; ++pp) {
+    asm volatile("cp.async.wait_group 1;" ::: "memory");
+    const int stg = pp & 1;
+    const uint4* st = ring + stg * (2 * 5 * 256) + tid;
+    const int n0 = 2 * pp;                     // index of the pair's first frame among the others
+    const bool has2 = n0 + 1 < others;
+    Vec8 lA, lB, aA, aB;
+    auto interp = [&](const uint4* sf, const WsRec& rc, Vec8& a) {
+      const float4 w = *reinterpret_cast<const float4*>(rc.w);
+      if (BF2) {
+        const __nv_bfloat162 w0 = __float2bfloat162_rn(w.x), w1 = __float2bfloat162_rn(w.y),
+                             w2 = __float2bfloat162_rn(w.z), w3 = __float2bfloat162_rn(w.w);
+        const uint4 t0 = sf[256], t1 = sf[512], t2 = sf[768], t3 = sf[1024];
+        const uint32_t* q0 = &t0.x; const uint32_t* q1 = &t1.x; const uint32_t* q2 = &t2.x; const uint32_t* q3 = &t3.x;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          __nv_bfloat162 r = __hmul2(*reinterpret_cast<const __nv_bfloat162*>(q0 + j), w0);
+          r = __hfma2(*reinterpret_cast<const __nv_bfloat162*>(q1 + j), w1, r);
+          r = __hfma2(*reinterpret_cast<const __nv_bfloat162*>(q2 + j), w2, r);
+          r = __hfma2(*reinterpret_cast<const __nv_bfloat162*>(q3 + j), w3, r);
+          const uint32_t rb = *reinterpret_cast<const uint32_t*>(&r);
+          a.v[2 * j] = __uint_as_float(rb << 16); a.v[2 * j + 1] = __uint_as_float(rb & 0xFFFF0000u);
+        }
+      } else {
+        const Vec8 t0 = unpack_bf16x8(sf[256]), t1 = unpack_bf16x8(sf[512]);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) a.v[k] = fmaf(t1.v[k], w.y, t0.v[k] * w.x);
+        const Vec8 t2 = unpack_bf16x8(sf[768]), t3 = unpack_bf16x8(sf[1024]);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) a.v[k] = fmaf(t3.v[k], w.w, fmaf(t2.v[k], w.z, a.v[k]));
+      }
+    };
+    lA = unpack_bf16x8(st[0]);
+    interp(st, rec_s[pix][n0], aA);
+    if (has2) {
+      lB = unpack_bf16x8(st[5 * 256]);
+      interp(st + 5 * 256, rec_s[pix][n0 + 1], aB);
+    } else {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) { lB.v[k] = -INFINITY; aB.v[k] = 0.0f; }
+    }
+    // this stage's slots are consumed (values are in registers): refill it with the pair after next
+    issue_pair(ring_s + (uint32_t)(stg * 2 * 5 * 4096));
+    // online softmax, one rescale per pair: 3 exponentials per 2 frames and element
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const float la = lA.v[k] * LOG2E, lb = lB.v[k] * LOG2E;
+      const float mn = fmaxf(m[k], fmaxf(la, lb));
+      const float sc = ex2f(m[k] - mn), ea = ex2f(la - mn), eb = ex2f(lb - mn);
+      s[k] = fmaf(s[k], sc, ea + eb);
+      acc[k] = fmaf(acc[k], sc, fmaf(aA.v[k], ea, aB.v[k] * eb));
+      m[k] = mn;
+    }
+  }
+  Vec8 r;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) r.v[k] = __fdividef(acc[k], s[k]);
   if (live) st8<TO>(obase + ((long long)b * HW + rem) * fused.c_pitch + ch, r);
 }
 
@@ -616,13 +780,42 @@ extern "C" int dbsr_softmax_wsum(const dbsr_nhwc_t* feat, const dbsr_nhwc_t* log
   if (v8) {
     dim3 grid8(((fused->w + WS_TW - 1) / WS_TW) * ((fused->h + WS_TH - 1) / WS_TH), (fused->c + 63) / 64, fused->n);
     if (key == 7 && offsets != nullptr && frames >= 2 && frames <= 17) {
-      static bool attr_set = false;
-      if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(softmax_wsum8_async_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, WS_ASYNC_SMEM);
-        DBSR_REQUIRE(e == cudaSuccess, "softmax_wsum: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
-        attr_set = true;
+      // TEMPORARY tuning knob (removed once the variant is chosen): DBSR_WS_VARIANT = 0..4
+      typedef void (*ws_fn)(View, View, const float*, View, int);
+      static const ws_fn fns[5] = {softmax_wsum8_async_kernel<__nv_bfloat16, 3, false>, softmax_wsum8_async_kernel<__nv_bfloat16, 3, true>,
+                                   softmax_wsum8_async_kernel<__nv_bfloat16, 2, true>, softmax_wsum8_async_kernel<__nv_bfloat16, 4, true>,
+                                   softmax_wsum8_async_kernel<__nv_bfloat16, 2, false>};
+      static const int stages[5] = {3, 3, 2, 4, 2};
+      static bool attr_set[5] = {false, false, false, false, false};
+      const char* ev = getenv("DBSR_WS_VARIANT");
+      int var = ev ? atoi(ev) : 0;
+      if ((var == 5 || var == 6) && frames - 1 <= WSP_MAX_OTHERS && (long long)fused->h * fused->w * feat->c_pitch * 2 < (1ll << 32)) {
+        typedef void (*wsp_fn)(View, View, const float*, View, int);
+        const wsp_fn kp = var == 5 ? (wsp_fn)softmax_wsum8_pair_kernel<__nv_bfloat16, false> : (wsp_fn)softmax_wsum8_pair_kernel<__nv_bfloat16, true>;
+        static bool pset[2] = {false, false};
+        if (!pset[var - 5]) {
+          cudaError_t e = cudaFuncSetAttribute(kp, cudaFuncAttributeMaxDynamicSharedMemorySize, WSP_SMEM);
+          DBSR_REQUIRE(e == cudaSuccess, "softmax_wsum: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
+          pset[var - 5] = true;
+        }
+        launch_pdl(kp, dim3(grid8), dim3(256), (size_t)WSP_SMEM, st, f, l, offsets, o, frames);
+        int rc2 = check_launch("softmax_wsum");
+        if (rc2) return rc2;
+        if (weights_out) {
+          const long long tw = (long long)fused->n * fused->c * fused->h * fused->w;
+          fusion_weights_kernel<<<grid_cap(tw, 256), 256, 0, st>>>(l, weights_out, frames);
+          rc2 = check_launch("fusion_weights");
+        }
+        return rc2;
       }
-      launch_pdl(softmax_wsum8_async_kernel<__nv_bfloat16>, dim3(grid8), dim3(256), WS_ASYNC_SMEM, st, f, l, offsets, o, frames);
+      if (var < 0 || var > 4) var = 0;
+      const int smem = ws_async_smem(stages[var]);
+      if (!attr_set[var]) {
+        cudaError_t e = cudaFuncSetAttribute(fns[var], cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        DBSR_REQUIRE(e == cudaSuccess, "softmax_wsum: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
+        attr_set[var] = true;
+      }
+      launch_pdl(fns[var], dim3(grid8), dim3(256), (size_t)smem, st, f, l, offsets, o, frames);
     }
     else if (key == 0) softmax_wsum8_kernel<float, float, float><<<grid8, 256, 0, st>>>(f, l, offsets, o, frames);
     else if (key == 7) softmax_wsum8_kernel<__nv_bfloat16, __nv_bfloat16, __nv_bfloat16><<<grid8, 256, 0, st>>>(f, l, offsets, o, frames);

@@ -51,3 +51,65 @@ def max_over_ranks(value: float, device) -> float:
     t = torch.tensor([value], dtype=torch.float64, device=device)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     return float(t.item())
+
+
+class OutputGatherer:
+    """Overlapped gather of per-rank predictions ("run it on a side stream overlapped with the next batch").
+
+    `submit(local)` copies this rank's `pred` shard (possibly a static CUDA-graph output that the next forward overwrites)
+    into one of `depth` staging slots on the CURRENT stream, then all-gathers the slot into `[total, ...]` on a side
+    stream over NCCL / NVLink while the caller launches the next forward.  It returns `(gathered, event)`; `gathered` is
+    valid once `event` has completed and is reused `depth` submissions later.  Ragged shards are padded to the largest
+    shard (the first `total % world` ranks own one burst more, `shard_range`).  On CPU tensors (gloo, tests) the same
+    logic runs synchronously without streams."""
+
+    def __init__(self, total: int, depth: int = 2):
+        assert depth >= 1
+        self.total, self.depth = total, depth
+        self.world = dist.get_world_size() if (dist.is_available() and dist.is_initialized()) else 1
+        self.sizes = shard_sizes(total, self.world)
+        self.pad = max(self.sizes)
+        self._stage = [None] * depth
+        self._out = [None] * depth
+        self._done = [None] * depth
+        self._side = None
+        self._i = 0
+
+    def submit(self, local: torch.Tensor):
+        k = self._i % self.depth
+        self._i += 1
+        cuda = local.is_cuda
+        tail = tuple(local.shape[1:])
+        if self._stage[k] is None or tuple(self._stage[k].shape[1:]) != tail or self._stage[k].dtype != local.dtype:
+            self._stage[k] = local.new_zeros((self.pad,) + tail)
+            self._out[k] = local.new_empty((self.world * self.pad,) + tail)
+            self._done[k] = None
+        cur = torch.cuda.current_stream(local.device) if cuda else None
+        if cuda and self._done[k] is not None:
+            cur.wait_event(self._done[k])            # the gather that last read this slot has finished
+        self._stage[k][:local.shape[0]].copy_(local, non_blocking=True)
+        if self.world == 1:
+            ev = None
+            if cuda:
+                ev = torch.cuda.Event()
+                ev.record(cur)
+            return self._stage[k][:self.total], ev
+        if not cuda:
+            dist.all_gather_into_tensor(self._out[k], self._stage[k])
+            return self._compact(self._out[k]), None
+        if self._side is None:
+            self._side = torch.cuda.Stream(device=local.device)
+        staged = torch.cuda.Event()
+        staged.record(cur)
+        self._side.wait_event(staged)
+        with torch.cuda.stream(self._side):
+            dist.all_gather_into_tensor(self._out[k], self._stage[k])
+            ev = torch.cuda.Event()
+            ev.record(self._side)
+        self._done[k] = ev
+        return self._compact(self._out[k]), ev
+
+    def _compact(self, out: torch.Tensor) -> torch.Tensor:
+        if all(s == self.pad for s in self.sizes):
+            return out                                # even shards: the gathered buffer is already [total, ...]
+        return torch.cat([out[r * self.pad:r * self.pad + s] for r, s in enumerate(self.sizes)], dim=0)

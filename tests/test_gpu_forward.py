@@ -138,6 +138,28 @@ def test_full_size_configs_burst_independence(dev, B, N, S):
         assert err <= 1e-2, err
 
 
+def test_large_crop_256(dev):
+    """BASELINE.json configs[4]: one 14x4x256x256 burst -> 3x2048x2048 (what each rank of the 8-GPU large-crop run
+    computes).  H is a multiple of 64, so the PWC resize is the identity and the level-2 cost volume is 64x64.  The full
+    14-frame burst must be finite and replay-stable; a 3-frame sub-burst of the same crop (seconds on the CPU) is checked
+    against the oracle within the bf16 tolerance."""
+    sd = O.make_state_dict(0)
+    net = _net(sd, dev, 'bf16')
+    net.return_fusion_weights = False
+    burst = O.make_burst(5, 1, 14, 256, 256)
+    pred, aux = net(burst.to(dev))
+    assert pred.shape == (1, 3, 2048, 2048) and aux['offsets'].shape == (1, 13, 2, 256, 256)
+    assert torch.isfinite(pred).all() and torch.isfinite(aux['offsets']).all()
+    again, _ = net(burst.to(dev))
+    assert torch.equal(pred, again)
+    sub = burst[:, :3].contiguous()
+    ref = O.dbsr_forward_fast(sub, sd)
+    ref = ref[0] if isinstance(ref, (tuple, list)) else ref
+    p3, _ = net(sub.to(dev))
+    err = (p3.cpu() - ref).abs().max().item()
+    assert err <= 1e-2, err
+
+
 def test_module_seams_match_fused_path(dev):
     """encoder -> merging -> decoder called one by one (NCHW dict seams of the reference) == fused engine path"""
     sd = O.make_state_dict(1)

@@ -213,6 +213,14 @@ def test_corr81_bf16_vectorised_staging(dev, c, h, w, mag):
     out = ops.Act.empty(3, h, w, 88, torch.float32, dev, zero=True).slice(0, 81)
     ops.corr81(act_bf16(f1), act_bf16(f2), out, pairs=3, group=0)
     assert (out.to_nchw().cpu() - O.correlation81(f1, f2)).abs().max() < 2e-5
+    # bf16 volume written into its 8-aligned concat segment (16-byte stores of 8 displacements; the 7 pad channels after
+    # the 81st are zeroed, the neighbouring segments must stay untouched)
+    cat = torch.full((3, h, w, 104), 3.0, dtype=torch.bfloat16, device=dev)
+    ops.corr81(act_bf16(f1), act_bf16(f2), ops.Act(cat).slice(8, 81), pairs=3, group=0)
+    ref81 = O.correlation81(f1, f2)
+    got81 = cat[..., 8:89].float().permute(0, 3, 1, 2).cpu()
+    assert (got81 - ref81).abs().max() <= 2e-5 + ref81.abs().max() * 2.0 ** -8
+    assert (cat[..., :8] == 3.0).all() and (cat[..., 96:] == 3.0).all() and (cat[..., 89:96] == 0).all()
     if mag > 0:
         flow = (torch.rand(3, 2, h, w, generator=g) * 2 - 1) * mag
         ref = O.lrelu(O.correlation81(f1, O.backwarp(f2, flow * 1.25)))
@@ -348,6 +356,35 @@ def test_softmax_wsum(dev, with_offsets, dtype):
                      offsets=offs.to(dev) if with_offsets else None, weights_out=wout)
     assert (fused.to_nchw().cpu() - ref).abs().max() < (1e-5 if dtype == torch.float32 else 6e-3)   # bf16 output rounding
     assert (wout.cpu() - w).abs().max() < 1e-6
+
+
+@pytest.mark.parametrize('N', [2, 3, 4, 14, 17])
+@pytest.mark.parametrize('C,H,W', [(64, 6, 9), (512, 9, 8), (72, 5, 5)])
+def test_softmax_wsum_bf16_gather_frame_counts(dev, N, C, H, W):
+    """the bf16 warp-on-the-fly kernel pipelines the burst in PAIRS of frames: odd / even numbers of other frames, a
+    single other frame, the maximum burst length, channel counts with a partial 64-channel slice, flows that leave the
+    image (zero padding) and logits far apart (overflow guard)"""
+    from deep_rawburst_sr_b200 import ops
+    g = _gen(N * 7 + C)
+    B = 2
+    feat = torch.rand(B * N, C, H, W, generator=g).bfloat16().float()
+    logits = (torch.randn(B * N, C, H, W, generator=g) * 3).bfloat16().float()
+    logits[0, :, 0, 0] = 40.0
+    logits[N - 1, :, 1, 1] = -40.0
+    logits[N - 1, :, 2, 2] = 60.0
+    offs = (torch.rand(B * (N - 1), 2, H, W, generator=g) * 2 - 1) * 5
+    offs[0, :, 0, 0] = torch.tensor([-100.0, 3.0])       # far outside
+    offs[0, :, 0, 1] = torch.tensor([0.0, 0.0])          # exactly on the grid
+    offs[0, :, H - 1, W - 1] = torch.tensor([0.5, 0.5])  # half of the taps outside
+    f5 = feat.view(B, N, C, H, W)
+    a5 = torch.cat([f5[:, :1], O.warp(f5[:, 1:].reshape(-1, C, H, W), offs).view(B, N - 1, C, H, W)], 1)
+    w = torch.softmax(logits.view(B, N, C, H, W), dim=1)
+    ref = (a5 * w).sum(1)
+    fused = ops.Act.empty(B, H, W, C, torch.bfloat16, dev)
+    ops.softmax_wsum(_act_from(feat, dev, dtype=torch.bfloat16), _act_from(logits, dev, dtype=torch.bfloat16), fused, N,
+                     offsets=offs.to(dev))
+    err = (fused.to_nchw().cpu() - ref).abs().max().item()
+    assert err < 6e-3, err          # bf16 output rounding (values in [0, 1))
 
 
 def test_blur_and_predictor(dev):

@@ -32,6 +32,12 @@ def _worker(rank, world, port, total, out_dir):
     bursts = torch.rand(total, 4, 4, 6, 6, generator=g)
     full = sharding.sharded_forward(_standin_forward, bursts, gather=True)
     mx = sharding.max_over_ranks(float(rank + 1), torch.device('cpu'))
+    # the overlapped gatherer (side-stream NCCL on the GPU box) runs the same slot / padding logic synchronously on CPU
+    gat = sharding.OutputGatherer(total, depth=2)
+    lo, hi = sharding.shard_range(total, rank, world)
+    for rep in range(3):     # slots are recycled
+        got, ev = gat.submit(_standin_forward(bursts[lo:hi]) + rep)
+        assert ev is None and torch.equal(got, _standin_forward(bursts) + rep)
     torch.save({'full': full, 'mx': mx, 'range': sharding.shard_range(total, rank, world)}, os.path.join(out_dir, f'r{rank}.pt'))
     dist.destroy_process_group()
 
