@@ -377,21 +377,10 @@ softmax_wsum8_kernel(View feat, View logits, const float* __restrict__ offsets, 
 
 
 // ---------------------------------------------------------------------------------------------------------
-// Asynchronously prefetched variant (bf16 embeddings and logits, warp on the fly): the kernel above is bound by memory
-// latency -- 6 warps per scheduler each waiting for 5 dependent-free 16-byte loads per frame -- so here every thread
-// keeps WS_STAGES frames of its five loads (logits + 4 bilinear taps) in flight as cp.async copies into its own slots
-// of a shared-memory ring.  A thread only ever reads the slots it filled itself: no block-level barrier in the loop,
-// only cp.async.wait_group.  Out-of-image taps are zero-filled by the copy (src-size 0), which is grid_sample's
-// zero padding, so the weights need no mask.
+// helpers of the asynchronously prefetched bf16 kernel below
 // ---------------------------------------------------------------------------------------------------------
-constexpr int ws_async_smem(int stages) { return stages * 5 * 256 * 16; }
 __device__ __forceinline__ void cp_async_16(uint32_t dst, const void* src, uint32_t bytes) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(bytes) : "memory");
-}
-// L1-allocating form for the bilinear taps: the four taps of neighbouring pixels overlap (a tile of 8x4 pixels touches
-// ~9x5 distinct 128-byte lines with 128 requests), so letting L1 merge them cuts the L2 -> SM traffic of the gather
-__device__ __forceinline__ void cp_async_16_ca(uint32_t dst, const void* src, uint32_t bytes) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ Vec8 unpack_bf16x8(const uint4& q) {
   Vec8 r;
@@ -401,121 +390,21 @@ __device__ __forceinline__ Vec8 unpack_bf16x8(const uint4& q) {
   r.v[6] = __uint_as_float(q.w << 16); r.v[7] = __uint_as_float(q.w & 0xFFFF0000u);
   return r;
 }
-template <typename TO, int WS_STAGES, bool TAPS_L1>
-__global__ void __launch_bounds__(256, (WS_STAGES >= 4) ? 2 : 3)
-softmax_wsum8_async_kernel(View feat, View logits, const float* __restrict__ offsets, View fused, int frames) {
-  griddep_wait();
-  extern __shared__ __align__(16) uint4 ring[];        // [WS_STAGES][5][256]
-  __shared__ float2 offs_s[32][16];
-  const int H = fused.h, W = fused.w;
-  const int HW = H * W;
-  const __nv_bfloat16* fbase = reinterpret_cast<const __nv_bfloat16*>(feat.data) + feat.c_off;
-  const __nv_bfloat16* lbase = reinterpret_cast<const __nv_bfloat16*>(logits.data) + logits.c_off;
-  TO* obase = reinterpret_cast<TO*>(fused.data) + fused.c_off;
-  const int tiles_x = (W + WS_TW - 1) / WS_TW;
-  const int tid = threadIdx.x;
-  const int g = tid & 7, px = (tid >> 3) & 7, py = tid >> 6;
-  const int b = blockIdx.z;
-  const int ch_raw = blockIdx.y * 64 + g * 8;
-  const int ch = min(ch_raw, fused.c - 8);   // clamped for the loads; the store is predicated on `live`
-  const int y_raw = (blockIdx.x / tiles_x) * WS_TH + py, x_raw = (blockIdx.x % tiles_x) * WS_TW + px;
-  const bool live = y_raw < H && x_raw < W && ch_raw < fused.c;
-  const int y = min(y_raw, H - 1), x = min(x_raw, W - 1);
-  const int rem = y * W + x;
-  // flows of all frames at this pixel, shared by the 8 channel-group threads of the pixel (all in one warp)
-#pragma unroll
-  for (int q = 0; q < 2; ++q) {
-    const int n = g + 8 * q;
-    if (n + 1 < frames) {
-      const long long pr = (long long)b * (frames - 1) + n;
-      offs_s[tid >> 3][n] = make_float2(__ldg(offsets + (pr * 2 + 0) * HW + rem), __ldg(offsets + (pr * 2 + 1) * HW + rem));
-    }
-  }
-  __syncwarp();
-  const uint32_t ring_s = (uint32_t)__cvta_generic_to_shared(ring) + (uint32_t)tid * 16u;
-  const float fxp = (float)x, fyp = (float)y;
-  auto issue = [&](int n) {       // frame n (1 .. frames-1) -> stage (n-1) % WS_STAGES
-    const uint32_t dst = ring_s + (uint32_t)(((n - 1) % WS_STAGES) * 5 * 256 * 16);
-    const long long img = (long long)b * frames + n;
-    cp_async_16(dst, lbase + (img * HW + rem) * logits.c_pitch + ch, 16u);
-    const float2 o2 = offs_s[tid >> 3][n - 1];
-    const float fu = floorf(fxp + o2.x), fv = floorf(fyp + o2.y);
-    const int x0 = (int)fu, y0 = (int)fv;
-    const __nv_bfloat16* ib = fbase + img * HW * feat.c_pitch + ch;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const int xx = x0 + (k & 1), yy = y0 + (k >> 1);
-      const bool ok = xx >= 0 && xx < W && yy >= 0 && yy < H;
-      const void* src = ok ? (const void*)(ib + (long long)(yy * W + xx) * feat.c_pitch) : (const void*)fbase;
-      if (TAPS_L1) cp_async_16_ca(dst + (uint32_t)((1 + k) * 256 * 16), src, ok ? 16u : 0u);
-      else cp_async_16(dst + (uint32_t)((1 + k) * 256 * 16), src, ok ? 16u : 0u);
-    }
-  };
-#pragma unroll
-  for (int n = 1; n <= WS_STAGES; ++n) {
-    if (n < frames) issue(n);
-    asm volatile("cp.async.commit_group;" ::: "memory");
-  }
-  // reference frame (never warped): plain loads while the ring fills
-  float m[8], s[8], acc[8];
-  {
-    const long long img = (long long)b * frames;
-    const Vec8 l = ld8<__nv_bfloat16>(lbase + (img * HW + rem) * logits.c_pitch + ch);
-    const Vec8 a = ld8<__nv_bfloat16>(fbase + (img * HW + rem) * feat.c_pitch + ch);
-#pragma unroll
-    for (int k = 0; k < 8; ++k) { m[k] = l.v[k]; s[k] = 1.0f; acc[k] = a.v[k]; }
-  }
-  for (int n = 1; n < frames; ++n) {
-    asm volatile("cp.async.wait_group %0;" ::"n"(WS_STAGES - 1) : "memory");
-    const uint4* st = ring + ((n - 1) % WS_STAGES) * 5 * 256 + tid;
-    const Vec8 l = unpack_bf16x8(st[0]);
-    const float2 o2 = offs_s[tid >> 3][n - 1];
-    const float u = fxp + o2.x, v = fyp + o2.y;
-    const float ax = u - floorf(u), ay = v - floorf(v);
-    Vec8 a;
-    {
-      const Vec8 t0 = unpack_bf16x8(st[256]), t1 = unpack_bf16x8(st[512]);
-      const float w0 = (1.0f - ax) * (1.0f - ay), w1 = ax * (1.0f - ay);
-#pragma unroll
-      for (int k = 0; k < 8; ++k) a.v[k] = fmaf(t1.v[k], w1, t0.v[k] * w0);
-      const Vec8 t2 = unpack_bf16x8(st[768]), t3 = unpack_bf16x8(st[1024]);
-      const float w2 = (1.0f - ax) * ay, w3 = ax * ay;
-#pragma unroll
-      for (int k = 0; k < 8; ++k) a.v[k] = fmaf(t3.v[k], w3, fmaf(t2.v[k], w2, a.v[k]));
-    }
-    // the slots of this stage are consumed (values are in registers): refill it with frame n + WS_STAGES
-    if (n + WS_STAGES < frames) issue(n + WS_STAGES);
-    asm volatile("cp.async.commit_group;" ::: "memory");
-    // online softmax with ONE exponential per element (see softmax_wsum8_kernel)
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      const float d = l.v[k] - m[k];
-      const float ex = __expf(-fabsf(d));
-      const bool up = d > 0.0f;
-      const float sc = up ? ex : 1.0f;
-      const float e = up ? 1.0f : ex;
-      s[k] = fmaf(s[k], sc, e);
-      acc[k] = fmaf(acc[k], sc, a.v[k] * e);
-      m[k] = up ? l.v[k] : m[k];
-    }
-  }
-  Vec8 r;
-#pragma unroll
-  for (int k = 0; k < 8; ++k) r.v[k] = acc[k] / s[k];
-  if (live) st8<TO>(obase + ((long long)b * HW + rem) * fused.c_pitch + ch, r);
-}
-
 
 // ---------------------------------------------------------------------------------------------------------
-// Lean pair-pipelined variant.  ncu on the kernel above (B=32, 48^2): Issue Slots Busy 88 %, IPC 3.5, DRAM 35 % -- it
-// is INSTRUCTION bound, ~370 warp instructions per thread-frame, of which ~150 are address arithmetic (64-bit image
-// offsets, four tap offsets, bounds tests, ring slot modulo) repeated by each of the 8 channel-group threads of a pixel
-// for every frame.  Here that work is done ONCE per (pixel, frame) before the loop: a 32-byte record
-// {4 byte offsets of the clamped taps, 4 bilinear weights with out-of-image taps zeroed} in shared memory, so that the
-// per-frame issue path is 1 LDS.128 + pointer bumps + 5 cp.async, and the consume path needs no masks.  Frames are
-// processed in PAIRS (ring = 2 stages x 2 frames): the online softmax rescales the running sum once per pair
-// (3 exponentials per 2 frames, no selects).  BF2 = true additionally does the bilinear interpolation in packed
-// bf16x2 arithmetic (HFMA2.BF16: 16 instead of 64 unpack + FMA instructions per frame).
+// Asynchronously prefetched, pair-pipelined kernel (bf16 embeddings and logits, warp on the fly).
+// History (profiles/): the register-resident kernel above is latency bound (6 warps per scheduler, each waiting on 5
+// loads per frame); a first cp.async version (every thread keeps 3 frames x 5 copies in flight in its own slots of a
+// shared-memory ring, no block barrier in the loop) reached 3.0 TB/s and then turned out INSTRUCTION bound (ncu, B=32,
+// 48^2: issue slots 88 % busy, IPC 3.5, DRAM 35 %): ~370 warp instructions per thread-frame, ~150 of them address
+// arithmetic (64-bit image offsets, four tap offsets, bounds tests, ring-slot modulo) repeated by each of the 8
+// channel-group threads of a pixel for every frame.  Here that work is done ONCE per (pixel, frame) before the loop:
+// a 32-byte record {4 byte offsets of the clamped taps, 4 bilinear weights with out-of-image taps zeroed (= the zero
+// padding of grid_sample)} in shared memory, so the per-frame issue path is 1 LDS.128 + pointer bumps + 5 cp.async
+// and the consume path needs no masks.  Frames are processed in PAIRS (ring = 2 stages x 2 frames, a thread only
+// reads slots it filled itself: cp.async.wait_group is the only synchronisation): the online softmax rescales the
+// running sums once per pair (3 exponentials per 2 frames, no selects).  181 instructions per thread-frame,
+// 4.1-4.2 TB/s (63 % of the measured HBM peak).
 // ---------------------------------------------------------------------------------------------------------
 struct __align__(16) WsRec { uint32_t o[4]; float w[4]; };
 constexpr int WSP_MAX_OTHERS = 16;
@@ -525,7 +414,7 @@ __device__ __forceinline__ float ex2f(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
-template <typename TO, bool BF2>
+template <typename TO>
 __global__ void __launch_bounds__(256, 2)
 softmax_wsum8_pair_kernel(View feat, View logits, const float* __restrict__ offsets, View fused, int frames) {
   griddep_wait();
@@ -616,28 +505,12 @@ softmax_wsum8_pair_kernel(View feat, View logits, const float* __restrict__ offs
     Vec8 lA, lB, aA, aB;
     auto interp = [&](const uint4* sf, const WsRec& rc, Vec8& a) {
       const float4 w = *reinterpret_cast<const float4*>(rc.w);
-      if (BF2) {
-        const __nv_bfloat162 w0 = __float2bfloat162_rn(w.x), w1 = __float2bfloat162_rn(w.y),
-                             w2 = __float2bfloat162_rn(w.z), w3 = __float2bfloat162_rn(w.w);
-        const uint4 t0 = sf[256], t1 = sf[512], t2 = sf[768], t3 = sf[1024];
-        const uint32_t* q0 = &t0.x; const uint32_t* q1 = &t1.x; const uint32_t* q2 = &t2.x; const uint32_t* q3 = &t3.x;
+      const Vec8 t0 = unpack_bf16x8(sf[256]), t1 = unpack_bf16x8(sf[512]);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          __nv_bfloat162 r = __hmul2(*reinterpret_cast<const __nv_bfloat162*>(q0 + j), w0);
-          r = __hfma2(*reinterpret_cast<const __nv_bfloat162*>(q1 + j), w1, r);
-          r = __hfma2(*reinterpret_cast<const __nv_bfloat162*>(q2 + j), w2, r);
-          r = __hfma2(*reinterpret_cast<const __nv_bfloat162*>(q3 + j), w3, r);
-          const uint32_t rb = *reinterpret_cast<const uint32_t*>(&r);
-          a.v[2 * j] = __uint_as_float(rb << 16); a.v[2 * j + 1] = __uint_as_float(rb & 0xFFFF0000u);
-        }
-      } else {
-        const Vec8 t0 = unpack_bf16x8(sf[256]), t1 = unpack_bf16x8(sf[512]);
+      for (int k = 0; k < 8; ++k) a.v[k] = fmaf(t1.v[k], w.y, t0.v[k] * w.x);
+      const Vec8 t2 = unpack_bf16x8(sf[768]), t3 = unpack_bf16x8(sf[1024]);
 #pragma unroll
-        for (int k = 0; k < 8; ++k) a.v[k] = fmaf(t1.v[k], w.y, t0.v[k] * w.x);
-        const Vec8 t2 = unpack_bf16x8(sf[768]), t3 = unpack_bf16x8(sf[1024]);
-#pragma unroll
-        for (int k = 0; k < 8; ++k) a.v[k] = fmaf(t3.v[k], w.w, fmaf(t2.v[k], w.z, a.v[k]));
-      }
+      for (int k = 0; k < 8; ++k) a.v[k] = fmaf(t3.v[k], w.w, fmaf(t2.v[k], w.z, a.v[k]));
     };
     lA = unpack_bf16x8(st[0]);
     interp(st, rec_s[pix][n0], aA);
@@ -779,43 +652,17 @@ extern "C" int dbsr_softmax_wsum(const dbsr_nhwc_t* feat, const dbsr_nhwc_t* log
   const int g = grid_cap(total, 256);
   if (v8) {
     dim3 grid8(((fused->w + WS_TW - 1) / WS_TW) * ((fused->h + WS_TH - 1) / WS_TH), (fused->c + 63) / 64, fused->n);
-    if (key == 7 && offsets != nullptr && frames >= 2 && frames <= 17) {
-      // TEMPORARY tuning knob (removed once the variant is chosen): DBSR_WS_VARIANT = 0..4
-      typedef void (*ws_fn)(View, View, const float*, View, int);
-      static const ws_fn fns[5] = {softmax_wsum8_async_kernel<__nv_bfloat16, 3, false>, softmax_wsum8_async_kernel<__nv_bfloat16, 3, true>,
-                                   softmax_wsum8_async_kernel<__nv_bfloat16, 2, true>, softmax_wsum8_async_kernel<__nv_bfloat16, 4, true>,
-                                   softmax_wsum8_async_kernel<__nv_bfloat16, 2, false>};
-      static const int stages[5] = {3, 3, 2, 4, 2};
-      static bool attr_set[5] = {false, false, false, false, false};
-      const char* ev = getenv("DBSR_WS_VARIANT");
-      int var = ev ? atoi(ev) : 0;
-      if ((var == 5 || var == 6) && frames - 1 <= WSP_MAX_OTHERS && (long long)fused->h * fused->w * feat->c_pitch * 2 < (1ll << 32)) {
-        typedef void (*wsp_fn)(View, View, const float*, View, int);
-        const wsp_fn kp = var == 5 ? (wsp_fn)softmax_wsum8_pair_kernel<__nv_bfloat16, false> : (wsp_fn)softmax_wsum8_pair_kernel<__nv_bfloat16, true>;
-        static bool pset[2] = {false, false};
-        if (!pset[var - 5]) {
-          cudaError_t e = cudaFuncSetAttribute(kp, cudaFuncAttributeMaxDynamicSharedMemorySize, WSP_SMEM);
-          DBSR_REQUIRE(e == cudaSuccess, "softmax_wsum: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
-          pset[var - 5] = true;
-        }
-        launch_pdl(kp, dim3(grid8), dim3(256), (size_t)WSP_SMEM, st, f, l, offsets, o, frames);
-        int rc2 = check_launch("softmax_wsum");
-        if (rc2) return rc2;
-        if (weights_out) {
-          const long long tw = (long long)fused->n * fused->c * fused->h * fused->w;
-          fusion_weights_kernel<<<grid_cap(tw, 256), 256, 0, st>>>(l, weights_out, frames);
-          rc2 = check_launch("fusion_weights");
-        }
-        return rc2;
-      }
-      if (var < 0 || var > 4) var = 0;
-      const int smem = ws_async_smem(stages[var]);
-      if (!attr_set[var]) {
-        cudaError_t e = cudaFuncSetAttribute(fns[var], cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    // bf16 in / bf16 out with the warp folded in (the engine's path): the pair-pipelined cp.async kernel.  Its gather
+    // records hold 32-bit byte offsets inside one image and at most WSP_MAX_OTHERS non-reference frames
+    if (key == 7 && offsets != nullptr && frames >= 2 && frames - 1 <= WSP_MAX_OTHERS &&
+        (long long)fused->h * fused->w * feat->c_pitch * 2 < (1ll << 32)) {
+      static bool attr_set = false;
+      if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(softmax_wsum8_pair_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, WSP_SMEM);
         DBSR_REQUIRE(e == cudaSuccess, "softmax_wsum: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
-        attr_set[var] = true;
+        attr_set = true;
       }
-      launch_pdl(fns[var], dim3(grid8), dim3(256), (size_t)smem, st, f, l, offsets, o, frames);
+      launch_pdl(softmax_wsum8_pair_kernel<__nv_bfloat16>, dim3(grid8), dim3(256), (size_t)WSP_SMEM, st, f, l, offsets, o, frames);
     }
     else if (key == 0) softmax_wsum8_kernel<float, float, float><<<grid8, 256, 0, st>>>(f, l, offsets, o, frames);
     else if (key == 7) softmax_wsum8_kernel<__nv_bfloat16, __nv_bfloat16, __nv_bfloat16><<<grid8, 256, 0, st>>>(f, l, offsets, o, frames);
