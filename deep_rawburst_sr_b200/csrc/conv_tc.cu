@@ -230,7 +230,11 @@ struct ConvTcParams {
   const float* bias;
   int act;
   int shuffle_r;        // 8: pixel shuffle addressing (y is the (8H, 8W, 32) map)
+  // fused 1x1 predictor (dbsr_conv2d_tc_predictor): y is NOT written; every epilogue thread owns all n_tile = cout_pad
+  // channels of its pixel and stores pred[n, k, y, x] = relu(pred_b[k] + sum_c pred_w[k][c] * act(conv)[c]), fp32 NCHW
+  float* pred; const float* pred_w; const float* pred_b; int pred_c;
 };
+constexpr int PRED_TAB_OFF = 64;   // floats: predictor weights [pred_c][cout_pad] + bias [pred_c] follow the bias table
 
 // epilogue of NC (32 or 16) accumulator columns held by one thread (= one output pixel).
 // rq: residual values of this chunk prefetched by the caller (fast path only, nullptr = load here)
@@ -609,6 +613,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
   griddep_wait();
   if (p.bias_smem && warp < 8)
     for (int i = threadIdx.x; i < p.cout_pad; i += 256) bias_tab[i] = p.bias ? __ldg(p.bias + i) : 0.0f;
+  if (p.pred != nullptr && warp < 8)
+    for (int i = threadIdx.x; i < p.pred_c * (p.cout_pad + 1); i += 256)
+      bias_tab[PRED_TAB_OFF + i] = i >= p.pred_c * p.cout_pad ? __ldg(p.pred_b + (i - p.pred_c * p.cout_pad))
+                                   : ((i % p.cout_pad) < p.cout ? __ldg(p.pred_w + (i / p.cout_pad) * p.cout + (i % p.cout_pad)) : 0.0f);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -786,7 +794,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
     const int ty = m >> 3, tx = m & 7;
     uint8_t* stg = smem_stg + (size_t)warp * STG_WARP_BYTES;
     int acc = 0; uint32_t acc_phase = 0;
-    if (!p.flat && p.bias_smem && p.vec_ok && p.y_dtype == DBSR_BF16 && (p.res == nullptr || NT == 64 || NT == 32 || NT == 16)) {
+    if (p.pred == nullptr && !p.flat && p.bias_smem && p.vec_ok && p.y_dtype == DBSR_BF16 &&
+        (p.res == nullptr || NT == 64 || NT == 32 || NT == 16)) {
       // ---------- lean coalesced path (every bf16 layer of the encoder / fusion / decoder trunks) ----------
       const uint32_t stg_s = smem_u32(stg);
       const uint32_t bias_s0 = smem_u32(bias_tab);
@@ -852,7 +861,32 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
       const int co0 = c.nt * NT;
       const int t = (p.mt == 2) ? group : 0;
       const uint32_t tbase = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)((acc * p.mt + t) * NT);
-      if (!p.flat && p.vec_ok && p.y_dtype == DBSR_BF16) {
+      if (p.pred != nullptr) {
+        // ---------- fused 1x1 predictor (NT == cout_pad == 32): the thread holds all channels of its pixel ----------
+        const int y = c.y0 + ty, x = c.x0 + t * p.t1_dx + tx;
+        const long long img = c.img + t * p.t1_dimg;
+        const bool valid = (y < p.H) && (x < p.W) && (img < p.n) && (p.mt == 2 || group == 0);
+        mbar_wait(&tfull_bar[acc], acc_phase, 400 + acc);
+        tc_fence_after();
+        if (p.mt == 2 || group == 0) {
+          uint32_t r[32];
+          tmem_ld32(tbase, r);
+          if (valid) {
+            float v[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = apply_act(__uint_as_float(r[j]) + bias_tab[j], p.act);
+            const float* pt = bias_tab + PRED_TAB_OFF;
+            const long long plane = (long long)p.H * p.W;
+            float* dst = p.pred + img * p.pred_c * plane + (long long)y * p.W + x;
+            for (int k = 0; k < p.pred_c; ++k) {
+              float s0 = pt[p.pred_c * 32 + k], s1 = 0.0f;
+#pragma unroll
+              for (int j = 0; j < 32; j += 2) { s0 = fmaf(v[j], pt[k * 32 + j], s0); s1 = fmaf(v[j + 1], pt[k * 32 + j + 1], s1); }
+              dst[k * plane] = fmaxf(s0 + s1, 0.0f);
+            }
+          }
+        }
+      } else if (!p.flat && p.vec_ok && p.y_dtype == DBSR_BF16) {
         // ---------- coalesced path: 64/32/16-channel groups through the per-warp staging rows ----------
         const int tx0 = c.x0 + t * p.t1_dx;
         const long long img_t = c.img + t * p.t1_dimg;
@@ -1190,7 +1224,8 @@ extern "C" int dbsr_conv2d_tc_supported(const dbsr_conv_t* c) {
   return tc_plan(&cc, &cfg, false) == 0 ? 1 : 0;
 }
 
-extern "C" int dbsr_conv2d_tc(const dbsr_conv_t* c_in, void* stream) {
+static int conv2d_tc_impl(const dbsr_conv_t* c_in, void* stream, const float* pred_w, const float* pred_b, int pred_c,
+                          float* pred) {
   TcConfig cfg;
   DBSR_REQUIRE(c_in != nullptr, "conv2d_tc: null descriptor");
   const dbsr_conv_t cc = centre_tap_form(c_in);
@@ -1298,9 +1333,25 @@ extern "C" int dbsr_conv2d_tc(const dbsr_conv_t* c_in, void* stream) {
   p.r_tx_bytes = TILE_H * TILE_W * cfg.mt * cfg.ck * 2;
   if (cfg.res_chunks > 0) p.res = nullptr;   // accumulated by the MMAs, nothing left for the epilogue
   p.bias = c->bias; p.act = c->act; p.shuffle_r = r;
+  p.pred = pred; p.pred_w = pred_w; p.pred_b = pred_b; p.pred_c = pred_c;
+  if (pred != nullptr)
+    DBSR_REQUIRE(pred_w && pred_b && pred_c >= 1 && pred_c <= 4 && cfg.n_tile == 32 && cfg.cout_pad == 32 && !cfg.flat &&
+                     r == 1 && p.bias_smem && (cfg.res_chunks > 0 || c->residual.data == nullptr),
+                 "conv2d_tc_predictor: needs a 3x3 / 1x1 conv with <= 32 output channels on maps wider than 8 pixels, "
+                 "residual (if any) accumulated on the tensor core, and 1..4 predictor channels");
   cudaStream_t st = (cudaStream_t)stream;
   if (cfg.ck == 64) return cfg.b_resident ? launch_tc<64, true>(mx, mw, mr, mi, p, cfg.smem_bytes, st)
                                           : launch_tc<64, false>(mx, mw, mr, mi, p, cfg.smem_bytes, st);
   return cfg.b_resident ? launch_tc<32, true>(mx, mw, mr, mi, p, cfg.smem_bytes, st)
                         : launch_tc<32, false>(mx, mw, mr, mi, p, cfg.smem_bytes, st);
+}
+
+extern "C" int dbsr_conv2d_tc(const dbsr_conv_t* c, void* stream) {
+  return conv2d_tc_impl(c, stream, nullptr, nullptr, 0, nullptr);
+}
+
+extern "C" int dbsr_conv2d_tc_predictor(const dbsr_conv_t* c, const float* pred_w, const float* pred_b, int32_t pred_c,
+                                        float* pred, void* stream) {
+  DBSR_REQUIRE(pred != nullptr, "conv2d_tc_predictor: null output");
+  return conv2d_tc_impl(c, stream, pred_w, pred_b, pred_c, pred);
 }

@@ -16,7 +16,9 @@ namespace dbsr {
 constexpr int CT_H = 8, CT_W = 16, C_CH = 32;
 constexpr int HALO_H = CT_H + 8, HALO_W = CT_W + 8;
 constexpr int CORR_THREADS = 288;
-constexpr int CORR_SMEM = (HALO_H * HALO_W + CT_H * CT_W) * C_CH * (int)sizeof(float);
+// f2 halo tile + f1 tile (fp32, one 32-channel chunk) + one 32-byte gather record per halo pixel (fused backwarp)
+struct __align__(16) CorrRec { uint32_t o[4]; float w[4]; };
+constexpr int CORR_SMEM = (HALO_H * HALO_W + CT_H * CT_W) * C_CH * (int)sizeof(float) + HALO_H * HALO_W * (int)sizeof(CorrRec);
 
 struct Vec8c { float v[8]; };
 __device__ __forceinline__ Vec8c vec8_zero() {
@@ -73,6 +75,7 @@ __global__ void __launch_bounds__(CORR_THREADS, 2) corr81_kernel(const CorrParam
   extern __shared__ __align__(16) float smem[];
   float* f2_s = smem;                                // [HALO_H*HALO_W][32]
   float* f1_s = smem + HALO_H * HALO_W * C_CH;       // [CT_H*CT_W][32]
+  CorrRec* rec_s = reinterpret_cast<CorrRec*>(f1_s + CT_H * CT_W * C_CH);   // [HALO_H*HALO_W]
 
   const int t = threadIdx.x;
   const int lane = t & 31;
@@ -102,6 +105,40 @@ __global__ void __launch_bounds__(CORR_THREADS, 2) corr81_kernel(const CorrParam
   const int hh = th + 8, hw = tw + 8;                  // halo extent actually needed
   const bool active = row < th && strip * 4 < tw;      // this thread owns at least one real output pixel
 
+  if (VEC && warp2) {
+    // ---- backwarp records, once per CTA (they do not depend on the channel chunk): per halo pixel the pixel offsets
+    // of the 4 bilinear taps (clamped into the image) and their weights with out-of-image taps zeroed; pwcnet.py:34-38
+    // zeroes the whole pixel unless the sampled ones-channel (= the sum of the in-image weights) exceeds 0.999.
+    for (int pix = t; pix < hh * HALO_W; pix += CORR_THREADS) {
+      const int y = ty0 - 4 + pix / HALO_W, x = tx0 - 4 + pix % HALO_W;
+      CorrRec r;
+      r.o[0] = r.o[1] = r.o[2] = r.o[3] = 0u;
+      r.w[0] = r.w[1] = r.w[2] = r.w[3] = 0.0f;
+      if (y >= 0 && y < H && x >= 0 && x < W) {
+        const long long fp = basef + (long long)y * W + x;
+        const float u = (float)x + view_ld(p.flow, fp, 0) * sxw;
+        const float w = (float)y + view_ld(p.flow, fp, 1) * syh;
+        const float fu = floorf(u), fv = floorf(w);
+        const float ax = u - fu, ay = w - fv;
+        const int xa = (int)fminf(fmaxf(fu, -2.0f), (float)W), ya = (int)fminf(fmaxf(fv, -2.0f), (float)H);
+        float m = 0.0f;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int xx = xa + (k & 1), yy = ya + (k >> 1);
+          const float wt = ((k & 1) ? ax : 1.0f - ax) * ((k >> 1) ? ay : 1.0f - ay);
+          if (xx >= 0 && xx < W && yy >= 0 && yy < H) {
+            r.o[k] = (uint32_t)(yy * W + xx);
+            r.w[k] = wt;
+            m += wt;
+          }
+        }
+        if (!(m > 0.999f)) r.w[0] = r.w[1] = r.w[2] = r.w[3] = 0.0f;
+      }
+      rec_s[pix] = r;
+    }
+    __syncthreads();
+  }
+
   for (int c0 = 0; c0 < C; c0 += C_CH) {
     if (VEC) {
       // ---- vectorised staging: one task = one pixel x 8 channels (16 / 32 bytes of global memory per load)
@@ -124,25 +161,18 @@ __global__ void __launch_bounds__(CORR_THREADS, 2) corr81_kernel(const CorrParam
           if (!warp2) {
             v = vec8_ld<T>(b2 + (base2 + (long long)y * W + x) * p.f2.c_pitch + ch, C - ch);
           } else {
-            const long long fp = basef + (long long)y * W + x;
-            const float u = (float)x + view_ld(p.flow, fp, 0) * sxw;
-            const float w = (float)y + view_ld(p.flow, fp, 1) * syh;
-            const float fu = floorf(u), fv = floorf(w);
-            const float ax = u - fu, ay = w - fv;
-            const int xa = (int)fu, ya = (int)fv;
-            float m = 0.0f;
+            const uint4 ro = *reinterpret_cast<const uint4*>(rec_s[pix].o);
+            const float4 rw = *reinterpret_cast<const float4*>(rec_s[pix].w);
+            const uint32_t ok[4] = {ro.x, ro.y, ro.z, ro.w};
+            const float wk[4] = {rw.x, rw.y, rw.z, rw.w};
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-              const int xx = xa + (k & 1), yy = ya + (k >> 1);
-              const float wt = ((k & 1) ? ax : 1.0f - ax) * ((k >> 1) ? ay : 1.0f - ay);
-              if (xx >= 0 && xx < W && yy >= 0 && yy < H) {
-                const Vec8c a = vec8_ld<T>(b2 + (base2 + (long long)yy * W + xx) * p.f2.c_pitch + ch, C - ch);
+              if (wk[k] != 0.0f) {
+                const Vec8c a = vec8_ld<T>(b2 + (base2 + (long long)ok[k]) * p.f2.c_pitch + ch, C - ch);
 #pragma unroll
-                for (int i = 0; i < 8; ++i) v.v[i] = fmaf(a.v[i], wt, v.v[i]);
-                m += wt;
+                for (int i = 0; i < 8; ++i) v.v[i] = fmaf(a.v[i], wk[k], v.v[i]);
               }
             }
-            if (!(m > 0.999f)) v = vec8_zero();  // pwcnet.py:34-38
           }
         }
         vec8_sts(&f2_s[pix * C_CH + g * 8], v);

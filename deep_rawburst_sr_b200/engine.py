@@ -281,7 +281,7 @@ class DBSREngine:
     # ------------------------------------------------------------------------------------------------
     def _conv(self, key: str, x: Act, y: Act, act: int, stride: int = 1, dilation: int = 1,
               residual: Optional[Act] = None, force_direct: bool = False, no_bias: bool = False,
-              real_cin: Optional[int] = None) -> Act:
+              real_cin: Optional[int] = None, pred: Optional[torch.Tensor] = None) -> Act:
         cw = self.W[key]
         cin_alg = cw.cin if real_cin is None else real_cin       # algorithmic input channels for the FLOP count
         bias, bias_tc = (None, None) if no_bias else (cw.bias, cw.bias_tc)
@@ -296,12 +296,18 @@ class DBSREngine:
         nbytes = x.n * x.h * x.w * cin_alg * es_in + y.n * y.h * y.w * y.c * es_out
         if residual is not None:
             nbytes += residual.n * residual.h * residual.w * residual.c * residual.buf.element_size()
+        if pred is not None:     # the output map is replaced by the fp32 prediction
+            nbytes += pred.numel() * 4 - y.n * y.h * y.w * y.c * es_out
         self.hbm_bytes[fam] = self.hbm_bytes.get(fam, 0) + nbytes
         ev = self._tic(fam)
         if ev is not None and self.layer_events is not None:
             fl = 2 * x.n * ho * wo * cw.cout * cin_alg * cw.ksize * cw.ksize
             self.layer_events.setdefault(key, []).append((self.timers[fam][-1], fl, fam, (x.n, x.h, x.w, cw.cin, cw.cout)))
-        if use_tc:
+        if pred is not None:
+            assert use_tc, 'the fused predictor epilogue exists on the tensor-core path only'
+            self.flops[fam] += 2 * x.n * ho * wo * self.pred_w.shape[0] * cw.cout
+            ops.conv2d_tc_predictor(x, cw.tc, bias_tc, y, cw.ksize, act, residual, self.pred_w, self.pred_b, pred)
+        elif use_tc:
             ops.conv2d(x, cw.tc, bias_tc, y, cw.ksize, stride, dilation, act, residual, cw.shuffle_r, tensor_core=True)
         else:
             ops.conv2d(x, cw.direct, bias, y, cw.ksize, stride, dilation, act, residual, cw.shuffle_r)
@@ -537,10 +543,22 @@ class DBSREngine:
         else:
             cur, nxt = ha, hb
         for i in range(self.dec_post):
-            self._resblock(f'decoder.post_res_layers.{i}', cur, ht, nxt)
+            key = f'decoder.post_res_layers.{i}'
+            if i == self.dec_post - 1 and self._fuse_predictor(key + '.conv2.0', ht, nxt, cur):
+                # last block: relu(x + conv2(relu(conv1(x)))) never goes to HBM -- the tcgen05 epilogue applies the 1x1
+                # predictor + ReLU (decoders.py:52,61) to the 32 channels each thread holds and writes `pred` directly
+                self._conv(key + '.conv1.0', cur, ht, ACT_RELU)
+                self._conv(key + '.conv2.0', ht, nxt, ACT_RELU, residual=cur, pred=pred)
+                return pred
+            self._resblock(key, cur, ht, nxt)
             cur, nxt = nxt, cur
         self._run('predictor', ops.predictor, cur, self.pred_w, self.pred_b, pred)
         return pred
+
+    def _fuse_predictor(self, key: str, x: Act, y: Act, residual: Act) -> bool:
+        cw = self.W[key]
+        return (cw.tc is not None and x.dtype == torch.bfloat16 and cw.cout == 32 and self.pred_w.shape[0] <= 4 and
+                x.w > 8 and ops.conv2d_tc_supported(x, cw.tc, cw.bias_tc, y, cw.ksize, 1, 1, residual, 0))
 
     # ------------------------------------------------------------------------------------------------
     # whole forward

@@ -95,6 +95,21 @@ def conv2d(x: Act, w: torch.Tensor, bias: Optional[torch.Tensor], y: Act, ksize:
     return y
 
 
+def conv2d_tc_predictor(x: Act, w: torch.Tensor, bias: Optional[torch.Tensor], y: Act, ksize: int, act: int,
+                        residual: Optional[Act], pred_w: torch.Tensor, pred_b: torch.Tensor, pred: torch.Tensor) -> torch.Tensor:
+    """tcgen05 conv whose epilogue applies the 1x1 predictor + ReLU and writes `pred` [n, k, h, w] fp32 directly (the conv
+    output map `y` is not written; it only describes the geometry)."""
+    k = pred_w.shape[0]
+    assert pred_w.dtype == torch.float32 and pred_w.is_contiguous() and pred_w.shape[1] == y.c
+    assert pred_b.dtype == torch.float32 and pred_b.numel() == k
+    assert pred.dtype == torch.float32 and pred.is_contiguous() and tuple(pred.shape) == (x.n, k, x.h, x.w)
+    d = ConvDesc(x.view(), y.view(), residual.view() if residual is not None else _NULL_VIEW, w.data_ptr(),
+                 _ptr(bias), ksize, 1, 1, act, 0)
+    _lib.check(_lib.load_library().dbsr_conv2d_tc_predictor(ctypes.byref(d), pred_w.data_ptr(), pred_b.data_ptr(), k,
+                                                            pred.data_ptr(), _stream()), 'dbsr_conv2d_tc_predictor')
+    return pred
+
+
 def conv2d_tc_supported(x: Act, w: torch.Tensor, bias, y: Act, ksize: int, stride: int = 1, dilation: int = 1,
                         residual: Optional[Act] = None, shuffle_r: int = 0) -> bool:
     d = ConvDesc(x.view(), y.view(), residual.view() if residual is not None else _NULL_VIEW, w.data_ptr(),

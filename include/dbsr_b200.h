@@ -101,6 +101,14 @@ int dbsr_conv2d_direct(const dbsr_conv_t* p, void* stream);
  *   (dbsr_conv2d_tc_supported) and never falls back silently inside a call.                              */
 int dbsr_conv2d_tc(const dbsr_conv_t* p, void* stream);
 int dbsr_conv2d_tc_supported(const dbsr_conv_t* p);
+/* The same convolution with the decoder's 1x1 predictor + ReLU (models/dbsr/decoders.py:52,61: conv_block(post_conv_dim, 3,
+ * 1, activation) after the last post-res block) folded into the epilogue: every epilogue thread owns all (<= 32) output
+ * channels of its pixel, so  pred[n, k, y, x] = relu(pred_b[k] + sum_c pred_w[k][c] * act(conv(x) + bias (+ residual))[c])
+ * is computed in fp32 registers and stored as fp32 NCHW; the map y itself is NOT written (p->y only gives the geometry).
+ *   Needs Cout <= 32 on a map wider than 8 pixels, a residual (if any) that the kernel accumulates on the tensor core
+ *   (bf16, Cout == 32), 1 <= pred_c <= 4.  pred_w: fp32 [pred_c][Cout], pred_b: fp32 [pred_c].                       */
+int dbsr_conv2d_tc_predictor(const dbsr_conv_t* p, const float* pred_w, const float* pred_b, int32_t pred_c, float* pred,
+                             void* stream);
 /* tiling chosen for (Cin, Cout): K chunk (64 -> SWIZZLE_128B, 32 -> SWIZZLE_64B), padded K, UMMA N, padded Cout */
 int dbsr_conv2d_tc_geometry(int32_t cin, int32_t cout, int32_t* ck, int32_t* kpad, int32_t* n_tile,
                             int32_t* cout_pad);

@@ -108,6 +108,41 @@ def test_conv2d_tc(name):
     assert err <= tol, f'{name}: max abs err {err} > {tol}'
 
 
+@pytest.mark.parametrize('n,h,w,use_res,k', [(2, 48, 40, True, 3), (1, 21, 19, True, 3), (3, 16, 16, False, 3), (301, 20, 8, True, 3),
+                                             (2, 32, 32, False, 1)])
+def test_conv2d_tc_fused_predictor(n, h, w, use_res, k):
+    """dbsr_conv2d_tc_predictor: 32 -> 32 conv (+ tensor-core residual) + ReLU with the 1x1 predictor 32 -> 3 + ReLU folded
+    into the epilogue (decoders.py:52,61), fp32 NCHW output, the conv's own output map untouched.  Reference: fp32 conv of
+    the same bf16-rounded operands, predictor on the UNROUNDED activations (what the fused kernel computes).  Covers ragged
+    tiles (21x19), the narrow-map image-pair item layout (20x8) and the 1x1 form."""
+    if not torch.cuda.is_available():
+        pytest.skip('needs a CUDA device')
+    from deep_rawburst_sr_b200 import ops
+    from deep_rawburst_sr_b200.engine import pack_tc
+    dev = torch.device('cuda:0')
+    g = torch.Generator().manual_seed(n * 1000 + h)
+    x = torch.randn(n, 32, h, w, generator=g).bfloat16().float()
+    wt = (torch.randn(32, 32, k, k, generator=g) / (32 * k * k) ** 0.5).bfloat16().float()
+    b = torch.randn(32, generator=g)
+    pw = torch.randn(3, 32, generator=g) / 32 ** 0.5
+    pb = torch.randn(3, generator=g) * 0.1
+    mid = F.conv2d(x, wt, b, padding=(k - 1) // 2)
+    res = None
+    if use_res:
+        res = torch.randn(mid.shape, generator=g).bfloat16().float()
+        mid = mid + res
+    ref = torch.relu(F.conv2d(torch.relu(mid), pw.view(3, 32, 1, 1), pb))
+    xa = ops.Act.empty(n, h, w, 32, torch.bfloat16, dev).from_nchw(x.to(dev))
+    ya = ops.Act(torch.full((n, h, w, 32), 5.0, dtype=torch.bfloat16, device=dev))
+    ra = ops.Act.empty(n, h, w, 32, torch.bfloat16, dev).from_nchw(res.to(dev)) if use_res else None
+    pred = torch.full((n, 3, h, w), -1.0, device=dev)
+    ops.conv2d_tc_predictor(xa, pack_tc(wt.to(dev)), b.to(dev), ya, k, ops.ACT_RELU, ra, pw.to(dev).contiguous(), pb.to(dev), pred)
+    torch.cuda.synchronize()
+    err = (pred.cpu() - ref).abs().max().item()
+    assert err <= 1e-4 * max(1.0, ref.abs().max().item()), err
+    assert (ya.buf == 5.0).all()        # the conv's output map is not written in this mode
+
+
 if __name__ == '__main__':
     # probe mode: `python tests/test_gpu_tc.py <case>` prints the error of one case (one process per case so a
     # device fault in one variant does not hide the others)
