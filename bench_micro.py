@@ -4,7 +4,7 @@ microbench only: 14-frame 64-channel embeddings at 96x96 and 160x160 flow resolu
 
     python bench_micro.py [--iters K] [--warmup W] [--bursts B] [--out file.json]
 
-Three legs, every one through the C ABI (`ops.*` -> libdbsr_b200.so), one JSON line each (rank 0 / one GPU):
+Four legs, every one through the C ABI (`ops.*` -> libdbsr_b200.so), one JSON line each (rank 0 / one GPU):
 
 * `corr81`      cost volume (correlation.py:280-330 + the fused backwarp / LeakyReLU of pwcnet.py:161,169) at the five
                 pyramid level shapes of a 96^2 and a 160^2 frame, 13*B pairs: achieved HBM GB/s = algorithmic bytes
@@ -13,6 +13,8 @@ Three legs, every one through the C ABI (`ops.*` -> libdbsr_b200.so), one JSON l
                 C=64 at S=96,160 (the cfg-4 stress shape) and the network's real shape C=512 at S=48,80; flows
                 U(-4,4) px so that out-of-image taps occur.  Bytes: (28*C*s + 13*2*4)*S^2 + C*s*S^2 per burst.
 * `pwc_align`   the whole PWC-Net alignment of a burst batch (pwcnet.py:248-281) at 96^2 / 160^2: pairs/s.
+* `sca`         SpatialColorAlignment.forward (models/loss/spatial_color_alignment.py:85-108) at the BurstSR evaluation
+                shape (640^2 prediction / ground truth, 80^2 RAW burst): images/s.
 
 Timing: CUDA events on the launching stream around EVERY launch, W warm-up launches, and the L2 is flushed between
 timed launches (a 512 MB buffer is overwritten), so small level shapes cannot be served from the 126 MB L2.
@@ -65,7 +67,7 @@ def main():
     ap.add_argument('--iters', type=int, default=20)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--bursts', type=int, default=8, help='bursts per launch (13 pairs each)')
-    ap.add_argument('--legs', default='corr81,warp_fuse,pwc_align')
+    ap.add_argument('--legs', default='corr81,warp_fuse,pwc_align,sca')
     ap.add_argument('--out', default='')
     args = ap.parse_args()
     from deep_rawburst_sr_b200 import ops
@@ -159,6 +161,22 @@ def main():
                       'finite': bool(torch.isfinite(offsets).all().item())})
                 del burst
                 eng._ws.clear()
+    if 'sca' in legs:
+        # the BurstSR metric path (PWC-Net at the 640^2 output resolution + two warps + colour matching)
+        from deep_rawburst_sr_b200.models.alignment.pwcnet import PWCNet
+        from deep_rawburst_sr_b200.models.loss.spatial_color_alignment import SpatialColorAlignment
+        torch.manual_seed(0)
+        for prec in ('bf16', 'fp32'):
+            nb = 4 if prec == 'bf16' else 1
+            pwc = PWCNet(load_pretrained=False).to(dev).eval().set_precision(prec)
+            sca = SpatialColorAlignment(pwc, sr_factor=4)
+            sca.to(dev)
+            gt = torch.rand(nb, 3, 640, 640, generator=g).to(dev)
+            pred = (gt + 0.02 * torch.randn(nb, 3, 640, 640, generator=g).to(dev)).clamp(0, 1)
+            burst = torch.rand(nb, 14, 4, 80, 80, generator=g).to(dev)
+            med, mn = timer(lambda: sca(pred, gt, burst))
+            emit({'leg': 'sca', 'images': nb, 'size': 640, 'alignment_net_precision': prec, 'ms': med, 'ms_min': mn,
+                  'images_per_s': nb / med * 1e3})
     if args.out:
         with open(args.out, 'w') as f:
             for d in lines:

@@ -99,6 +99,9 @@ class PWCNet(torch.nn.Module):
         super(PWCNet, self).__init__()
         self.net = Network()
         self.rgb2bgr = rgb2bgr
+        # 'fp32': exact CUDA-core path (flows within 1e-4 px of the reference); 'bf16': tcgen05 tensor cores (the precision
+        # the burst forward uses for PWC-Net, ~1e-2 px) -- e.g. for the output-resolution alignment of the BurstSR metric
+        self.precision = 'fp32'
         self._engine = None
         if load_pretrained:
             if weights_path is None:
@@ -115,9 +118,15 @@ class PWCNet(torch.nn.Module):
         self._engine = None
         return super().load_state_dict(*a, **k)
 
+    def set_precision(self, precision: str):
+        assert precision in ('fp32', 'bf16')
+        self.precision = precision
+        self._engine = None
+        return self
+
     def engine(self, device):
-        if self._engine is None or self._engine.device != torch.device(device):
-            self._engine = DBSREngine(self.state_dict(), device, precision='fp32', pwc_prefix='net.', parts=('pwc',))
+        if self._engine is None or self._engine.device != torch.device(device) or self._engine.precision != self.precision:
+            self._engine = DBSREngine(self.state_dict(), device, precision=self.precision, pwc_prefix='net.', parts=('pwc',))
         return self._engine
 
     @torch.no_grad()

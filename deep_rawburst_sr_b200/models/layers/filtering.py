@@ -1,4 +1,4 @@
-"""gauss_1d / gauss_2d as in the reference (models/layers/filtering.py:20-40); host-side, builds the 3x3 blur taps."""
+"""gauss_1d / gauss_2d / get_gaussian_kernel / apply_kernel as in the reference (models/layers/filtering.py:20-62)."""
 import math
 
 import torch
@@ -21,3 +21,31 @@ def gauss_2d(sz, sigma, center, end_pad=(0, 0), density=False):
         center = torch.tensor(center).view(1, 2)
     return gauss_1d(sz[0], sigma[0], center[:, 0], end_pad[0], density).reshape(center.shape[0], 1, -1) * \
         gauss_1d(sz[1], sigma[1], center[:, 1], end_pad[1], density).reshape(center.shape[0], -1, 1)
+
+
+def get_gaussian_kernel(sd, ksz=None):
+    """ Returns a 2D Gaussian kernel with standard deviation sd (filtering.py:43-52) """
+    if ksz is None:
+        ksz = int(4 * sd + 1)
+    assert ksz % 2 == 1
+    K = gauss_2d(ksz, sd, (0.0, 0.0), density=True)
+    K = K / K.sum()
+    return K.unsqueeze(0), ksz
+
+
+def apply_kernel(im, ksz, kernel):
+    """ apply the provided kernel on input image (filtering.py:55-62): reflect padding + per-channel correlation.
+    Written as an explicit sum over the ksz^2 taps so that the result is exact fp32 on the device (a cudnn convolution
+    would run in TF32 by default); the images on this path are the 80x80 low-resolution frames. """
+    import torch.nn.functional as F
+    shape = im.shape
+    im = im.reshape(-1, 1, *im.shape[-2:])
+    r = ksz // 2
+    imp = F.pad(im, [r, r, r, r], mode='reflect')
+    H, W = shape[-2:]
+    k = kernel.reshape(ksz, ksz).to(im.device, im.dtype)
+    out = torch.zeros_like(im)
+    for dy in range(ksz):
+        for dx in range(ksz):
+            out = out + k[dy, dx] * imp[..., dy:dy + H, dx:dx + W]
+    return out.view(shape)

@@ -1,0 +1,89 @@
+"""Image-quality metrics of the DBSR path with the reference's interface (models/loss/image_quality_v2.py):
+`PixelWiseError` (:24-66), `PSNR` (:69-101) and `AlignedL2` (:166-191, the BurstSR loss / metric built on
+`SpatialColorAlignment`).  SSIM / LPIPS depend on packages outside this path and are not provided."""
+import math
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import spatial_color_alignment as sca_utils
+
+
+class PixelWiseError(nn.Module):
+    """ Computes pixel-wise error using the specified metric. Optionally boundary pixels are ignored during error
+        calculation """
+    def __init__(self, metric='l1', boundary_ignore=None):
+        super().__init__()
+        self.boundary_ignore = boundary_ignore
+        if metric == 'l1':
+            self.loss_fn = F.l1_loss
+        elif metric == 'l2':
+            self.loss_fn = F.mse_loss
+        elif metric == 'l2_sqrt':
+            self.loss_fn = lambda pred, gt: (((pred - gt) ** 2).sum(dim=-3)).sqrt().mean()
+        elif metric == 'charbonnier':
+            self.loss_fn = lambda pred, gt: ((pred - gt) ** 2 + 1e-3 ** 2).sqrt().mean()
+        else:
+            raise Exception
+
+    def forward(self, pred, gt, valid=None):
+        if self.boundary_ignore is not None:
+            b = self.boundary_ignore
+            pred = pred[..., b:-b, b:-b]
+            gt = gt[..., b:-b, b:-b]
+            if valid is not None:
+                valid = valid[..., b:-b, b:-b]
+        if valid is None:
+            return self.loss_fn(pred, gt)
+        err = self.loss_fn(pred, gt, reduction='none')
+        eps = 1e-12
+        elem_ratio = err.numel() / valid.numel()
+        return (err * valid.float()).sum() / (valid.float().sum() * elem_ratio + eps)
+
+
+class PSNR(nn.Module):
+    def __init__(self, boundary_ignore=None, max_value=1.0):
+        super().__init__()
+        self.l2 = PixelWiseError(metric='l2', boundary_ignore=boundary_ignore)
+        self.max_value = max_value
+
+    def psnr(self, pred, gt, valid=None):
+        mse = self.l2(pred, gt, valid=valid)
+        if getattr(self, 'max_value', 1.0) is not None:
+            psnr = 20 * math.log10(getattr(self, 'max_value', 1.0)) - 10.0 * mse.log10()
+        else:
+            psnr = 20 * gt.max().log10() - 10.0 * mse.log10()
+        if torch.isinf(psnr) or torch.isnan(psnr):
+            print('invalid psnr')
+        return psnr
+
+    def forward(self, pred, gt, valid=None):
+        if valid is None:
+            psnr_all = [self.psnr(p.unsqueeze(0), g.unsqueeze(0)) for p, g in zip(pred, gt)]
+        else:
+            psnr_all = [self.psnr(p.unsqueeze(0), g.unsqueeze(0), v.unsqueeze(0)) for p, g, v in zip(pred, gt, valid)]
+        psnr_all = [p for p in psnr_all if not (torch.isinf(p) or torch.isnan(p))]
+        if len(psnr_all) == 0:
+            return 0
+        return sum(psnr_all) / len(psnr_all)
+
+
+class AlignedL2(nn.Module):
+    """ Computes L2 error after performing spatial and color alignment of the input image to GT"""
+    def __init__(self, alignment_net, sr_factor=4, boundary_ignore=None):
+        super().__init__()
+        self.sca = sca_utils.SpatialColorAlignment(alignment_net, sr_factor)
+        self.boundary_ignore = boundary_ignore
+
+    def forward(self, pred, gt, burst_input):
+        pred_warped_m, valid = self.sca(pred, gt, burst_input)
+        if self.boundary_ignore is not None:
+            b = self.boundary_ignore
+            pred_warped_m = pred_warped_m[..., b:-b, b:-b]
+            gt = gt[..., b:-b, b:-b]
+            valid = valid[..., b:-b, b:-b]
+        mse = F.mse_loss(pred_warped_m, gt, reduction='none')
+        eps = 1e-12
+        elem_ratio = mse.numel() / valid.numel()
+        return (mse * valid.float()).sum() / (valid.float().sum() * elem_ratio + eps)

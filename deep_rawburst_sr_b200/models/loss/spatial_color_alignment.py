@@ -1,0 +1,80 @@
+"""Spatial + colour alignment of a prediction to the ground truth (BurstSR metrics), with the reference's interface
+(models/loss/spatial_color_alignment.py:23-108): `match_colors(im_ref, im_q, im_test, ksz, gauss_kernel)` and
+`SpatialColorAlignment(alignment_net, sr_factor=4).forward(pred, gt, burst_input) -> (pred_warped_m, valid)`.
+
+SURVEY.md 8(f) rank 1: the metric runs PWC-Net AGAIN at the output resolution (640^2 -> level-2 maps 160^2) plus two
+warps -- those are the sm_100a kernels of the hot path (`PWCNet` -> DBSREngine's extractor / cost volume / decoder /
+refiner kernels, `warp` -> dbsr_warp).  The rest is a few hundred kB of per-image glue (7x7 Gaussian on the 80x80 LR
+frames, a 3x3 least-squares colour matrix, thresholds, x8 resizes of a mask) and stays in torch ops ON THE DEVICE,
+written so that no TF32 path is involved (explicit tap sums and broadcasts instead of cudnn conv / matmul).  CPU tensors
+are refused like everywhere else in this package.
+"""
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from ... import ops
+from ..layers import warp as lispr_warp
+from ..layers.filtering import apply_kernel, get_gaussian_kernel
+
+
+def _color_apply(im, c_mat):
+    """im [B, 3, H, W], c_mat [B, 3, 3]: out[b, j] = sum_i im[b, i] * c_mat[b, i, j]  (the reference's
+    matmul(im_re.permute(0, 2, 1), c_mat), spatial_color_alignment.py:45,66) as an exact-fp32 broadcast."""
+    return (im.unsqueeze(2) * c_mat.unsqueeze(-1).unsqueeze(-1)).sum(dim=1)
+
+
+def match_colors(im_ref, im_q, im_test, ksz, gauss_kernel):
+    """Estimates a colour transformation matrix between im_ref and im_q and applies it to im_test
+    (spatial_color_alignment.py:23-69)."""
+    ops.require_device(im_ref)
+    gauss_kernel = gauss_kernel.to(im_ref.device)
+    bi = 5
+    im_ref_mean = apply_kernel(im_ref, ksz, gauss_kernel)[:, :, bi:-bi, bi:-bi].contiguous()
+    im_q_mean = apply_kernel(im_q, ksz, gauss_kernel)[:, :, bi:-bi, bi:-bi].contiguous()
+    im_ref_mean_re = im_ref_mean.view(*im_ref_mean.shape[:2], -1)
+    im_q_mean_re = im_q_mean.view(*im_q_mean.shape[:2], -1)
+    # least squares per image: argmin_X || iq^T X - ir^T ||  (the reference's removed torch.lstsq(ir.t(), iq.t()), :40-42),
+    # batched over the images; fp64 normal equations of a [P, 3] system are exact enough and need no host round trip
+    A = im_q_mean_re.permute(0, 2, 1).double()
+    Bm = im_ref_mean_re.permute(0, 2, 1).double()
+    c_mat = torch.linalg.solve(A.transpose(1, 2) @ A, A.transpose(1, 2) @ Bm).float()
+    im_q_mean_conv = _color_apply(im_q_mean, c_mat)
+    err = ((im_q_mean_conv - im_ref_mean) * 255.0).norm(dim=1)
+    thresh = 20
+    valid = err < thresh
+    pad = (im_q.shape[-1] - valid.shape[-1]) // 2
+    valid = F.pad(valid, [pad, pad, pad, pad])
+    upsample_factor = im_test.shape[-1] / valid.shape[-1]
+    valid = F.interpolate(valid.unsqueeze(1).float(), scale_factor=upsample_factor, mode='bilinear')
+    valid = valid > 0.9
+    im_t_conv = _color_apply(im_test, c_mat)
+    return im_t_conv, valid
+
+
+class SpatialColorAlignment(nn.Module):
+    def __init__(self, alignment_net, sr_factor=4):
+        super().__init__()
+        self.sr_factor = sr_factor
+        self.alignment_net = alignment_net
+        self.gauss_kernel, self.ksz = get_gaussian_kernel(sd=1.5)
+
+    def to(self, device):
+        """ Move the network to device (reference signature: returns None, spatial_color_alignment.py:80-87) """
+        self.alignment_net.to(device)
+        self.gauss_kernel = self.gauss_kernel.to(device)
+
+    @torch.no_grad()
+    def forward(self, pred, gt, burst_input):
+        ops.require_device(pred)
+        # flow between the prediction and the ground truth: PWC-Net at the output resolution on the sm_100a kernels
+        flow = self.alignment_net(pred / (pred.max() + 1e-6), gt / (gt.max() + 1e-6))
+        pred_warped = lispr_warp.warp(pred, flow)
+        sr_factor = self.sr_factor
+        ds_factor = 1.0 / float(2.0 * sr_factor)
+        flow_ds = F.interpolate(flow, scale_factor=ds_factor, mode='bilinear') * ds_factor
+        burst_0 = burst_input[:, 0, [0, 1, 3]].contiguous()
+        burst_0_warped = lispr_warp.warp(burst_0, flow_ds)
+        frame_gt_ds = F.interpolate(gt, scale_factor=ds_factor, mode='bilinear')
+        pred_warped_m, valid = match_colors(frame_gt_ds, burst_0_warped, pred_warped, self.ksz, self.gauss_kernel)
+        return pred_warped_m, valid

@@ -109,3 +109,17 @@ def test_pack_s2d_weight_is_the_stride2_conv():
         xs = xp.view(2, c, hp // 2, 2, wp // 2, 2).permute(0, 3, 5, 1, 2, 4).reshape(2, 4 * c, hp // 2, wp // 2)
         got = F.conv2d(xs, pack_s2d_weight(wt), stride=1, padding=1)
         assert got.shape == ref.shape and (got - ref).abs().max() < 1e-4
+
+
+def test_gaussian_filter_glue_matches_oracle():
+    """get_gaussian_kernel / apply_kernel (reference models/layers/filtering.py:43-62) are device-agnostic torch glue:
+    on CPU they must equal the oracle's explicit-index restatement (reflect padding included)"""
+    import torch
+    from deep_rawburst_sr_b200.models.layers.filtering import apply_kernel, get_gaussian_kernel
+    from oracle import sca_oracle as S
+    K, ksz = get_gaussian_kernel(sd=1.5)
+    Ko, ksz_o = S.gaussian_kernel(1.5)
+    assert ksz == ksz_o == 7 and tuple(K.shape) == (1, 1, 7, 7)      # conv2d weight shape, as the reference
+    assert (K[0, 0] - Ko).abs().max() < 1e-7 and abs(float(K.sum()) - 1.0) < 1e-6
+    x = torch.rand(2, 3, 11, 9, generator=torch.Generator().manual_seed(3))
+    assert (apply_kernel(x, ksz, K) - S.apply_kernel(x, ksz, Ko)).abs().max() < 1e-6

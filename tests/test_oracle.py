@@ -98,3 +98,21 @@ def test_library_op_restatement_matches_explicit_oracle():
     p1, a1 = O.dbsr_forward_fast(burst, sd)
     assert (p0 - p1).abs().max().item() < 2e-5
     assert (a0['offsets'] - a1['offsets']).abs().max().item() < 1e-4
+
+
+@pytest.mark.parametrize('name', ['sca_b2_192', 'sca_b1_128_gain2'])
+def test_sca_oracle_matches_reference_golden(golden_dir, name):
+    """spatial + colour alignment: oracle/sca_oracle.py against vectors produced by the reference's
+    SpatialColorAlignment / AlignedL2 themselves (oracle/make_golden_sca.py)"""
+    from oracle import sca_oracle as S
+    g = np.load(os.path.join(golden_dir, name + '.npz'))
+    wseed, iseed, B, size = [int(v) for v in g['meta']]
+    sd = S.pwc_state_dict(wseed, float(g['gain'][0]))
+    pred, gt, burst = S.make_sca_inputs(iseed, B, size)
+    pm, valid, aux = S.spatial_color_alignment(pred, gt, burst, sd)
+    assert np.abs(aux['flow'].numpy() - g['flow']).max() < 1e-4
+    assert np.abs(pm.numpy() - g['pred_m']).max() < 1e-4
+    assert (valid.numpy() != g['valid']).mean() < 1e-3
+    assert 0.02 < valid.float().mean() < 0.9          # the mask is neither empty nor full
+    l2 = float(S.aligned_l2(pred, gt, burst, sd, boundary_ignore=16))
+    assert abs(l2 - float(g['aligned_l2'][0])) <= 1e-4 * float(g['aligned_l2'][0])
