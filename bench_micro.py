@@ -143,16 +143,13 @@ def main():
             eng = DBSREngine(sd, dev, precision=prec, parts=('pwc',))
             for S in (96, 160):
                 nb = B if prec == 'bf16' else max(1, B // 4)
-                hp = (S + 63) // 64 * 64
                 burst = torch.rand(nb, FRAMES, 4, S, S, generator=g).to(dev)
                 ws = eng.workspace(('micro', nb, S))
                 enc_in = eng._buf(ws, 'enc_in', nb * FRAMES, S, S, 8, eng.act_dtype)
-                pwc_in = eng._buf(ws, 'pwc_in', nb * FRAMES, hp, hp, 4, torch.float32)
                 offsets = torch.empty((nb * (FRAMES - 1), 2, S, S), dtype=torch.float32, device=dev)
 
                 def run():
-                    ops.prep_burst(burst, enc_in, pwc_in)
-                    eng.pwc_burst(ws, pwc_in, nb, FRAMES, S, S, offsets)
+                    eng.prep_and_align(ws, burst, enc_in, offsets)
                 n0 = eng.launches
                 med, mn = timer(run)
                 emit({'leg': 'pwc_align', 'frame': S, 'bursts': nb, 'pairs': nb * (FRAMES - 1), 'precision': prec,

@@ -45,6 +45,7 @@ PROTOTYPES = {
     'dbsr_nhwc_to_nchw': (_I, [_PV, _VP, _VP]),
     'dbsr_copy_channels': (_I, [_PV, _PV, _I, _I, _I, _VP]),
     'dbsr_prep_burst': (_I, [_VP, _I, _I, _I, _PV, _PV, _VP]),
+    'dbsr_prep_burst_s2d': (_I, [_VP, _I, _I, _I, _I, _I, _PV, _PV, _VP]),
     'dbsr_conv2d_direct': (_I, [_PC, _VP]),
     'dbsr_conv2d_tc': (_I, [_PC, _VP]),
     'dbsr_conv2d_tc_supported': (_I, [_PC]),

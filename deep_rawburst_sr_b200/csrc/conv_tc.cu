@@ -232,9 +232,12 @@ struct ConvTcParams {
   int shuffle_r;        // 8: pixel shuffle addressing (y is the (8H, 8W, 32) map)
   // fused 1x1 predictor (dbsr_conv2d_tc_predictor): y is NOT written; every epilogue thread owns all n_tile = cout_pad
   // channels of its pixel and stores pred[n, k, y, x] = relu(pred_b[k] + sum_c pred_w[k][c] * act(conv)[c]), fp32 NCHW
-  float* pred; const float* pred_w; const float* pred_b; int pred_c;
+  // The predictor weights travel IN the kernel parameters (constant bank): the 96 FMAs per pixel then take their weight
+  // operand from the constant cache -- a first version that read them from shared memory added 1024 LDS wavefronts per
+  // item to a kernel whose bottleneck is the shared-memory data pipe and was 100 us slower per launch.
+  float* pred; int pred_c;
+  float pred_wb[4 * 32 + 4];   // [k][32] weights (zero beyond cout), then [k] biases
 };
-constexpr int PRED_TAB_OFF = 64;   // floats: predictor weights [pred_c][cout_pad] + bias [pred_c] follow the bias table
 
 // epilogue of NC (32 or 16) accumulator columns held by one thread (= one output pixel).
 // rq: residual values of this chunk prefetched by the caller (fast path only, nullptr = load here)
@@ -613,10 +616,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
   griddep_wait();
   if (p.bias_smem && warp < 8)
     for (int i = threadIdx.x; i < p.cout_pad; i += 256) bias_tab[i] = p.bias ? __ldg(p.bias + i) : 0.0f;
-  if (p.pred != nullptr && warp < 8)
-    for (int i = threadIdx.x; i < p.pred_c * (p.cout_pad + 1); i += 256)
-      bias_tab[PRED_TAB_OFF + i] = i >= p.pred_c * p.cout_pad ? __ldg(p.pred_b + (i - p.pred_c * p.cout_pad))
-                                   : ((i % p.cout_pad) < p.cout ? __ldg(p.pred_w + (i / p.cout_pad) * p.cout + (i % p.cout_pad)) : 0.0f);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -873,16 +872,26 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
           tmem_ld32(tbase, r);
           if (valid) {
             float v[32];
+            const uint32_t bias_s = smem_u32(bias_tab);
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = apply_act(__uint_as_float(r[j]) + bias_tab[j], p.act);
-            const float* pt = bias_tab + PRED_TAB_OFF;
+            for (int j = 0; j < 32; j += 4) {
+              const float4 b4 = lds128f(bias_s + (uint32_t)j * 4u);
+              v[j] = apply_act(__uint_as_float(r[j]) + b4.x, p.act); v[j + 1] = apply_act(__uint_as_float(r[j + 1]) + b4.y, p.act);
+              v[j + 2] = apply_act(__uint_as_float(r[j + 2]) + b4.z, p.act); v[j + 3] = apply_act(__uint_as_float(r[j + 3]) + b4.w, p.act);
+            }
             const long long plane = (long long)p.H * p.W;
             float* dst = p.pred + img * p.pred_c * plane + (long long)y * p.W + x;
-            for (int k = 0; k < p.pred_c; ++k) {
-              float s0 = pt[p.pred_c * 32 + k], s1 = 0.0f;
 #pragma unroll
-              for (int j = 0; j < 32; j += 2) { s0 = fmaf(v[j], pt[k * 32 + j], s0); s1 = fmaf(v[j + 1], pt[k * 32 + j + 1], s1); }
-              dst[k * plane] = fmaxf(s0 + s1, 0.0f);
+            for (int k = 0; k < 4; ++k) {
+              if (k < p.pred_c) {
+                float s0 = p.pred_wb[128 + k], s1 = 0.0f;
+#pragma unroll
+                for (int j = 0; j < 32; j += 2) {
+                  s0 = fmaf(v[j], p.pred_wb[k * 32 + j], s0);
+                  s1 = fmaf(v[j + 1], p.pred_wb[k * 32 + j + 1], s1);
+                }
+                dst[k * plane] = fmaxf(s0 + s1, 0.0f);
+              }
             }
           }
         }
@@ -1333,12 +1342,18 @@ static int conv2d_tc_impl(const dbsr_conv_t* c_in, void* stream, const float* pr
   p.r_tx_bytes = TILE_H * TILE_W * cfg.mt * cfg.ck * 2;
   if (cfg.res_chunks > 0) p.res = nullptr;   // accumulated by the MMAs, nothing left for the epilogue
   p.bias = c->bias; p.act = c->act; p.shuffle_r = r;
-  p.pred = pred; p.pred_w = pred_w; p.pred_b = pred_b; p.pred_c = pred_c;
-  if (pred != nullptr)
+  p.pred = pred; p.pred_c = pred_c;
+  memset(p.pred_wb, 0, sizeof(p.pred_wb));
+  if (pred != nullptr) {
     DBSR_REQUIRE(pred_w && pred_b && pred_c >= 1 && pred_c <= 4 && cfg.n_tile == 32 && cfg.cout_pad == 32 && !cfg.flat &&
                      r == 1 && p.bias_smem && (cfg.res_chunks > 0 || c->residual.data == nullptr),
-                 "conv2d_tc_predictor: needs a 3x3 / 1x1 conv with <= 32 output channels on maps wider than 8 pixels, "
+                 "conv2d_tc_predictor: needs a 3x3 / 1x1 conv with <= 32 output channels on maps larger than 8x8, "
                  "residual (if any) accumulated on the tensor core, and 1..4 predictor channels");
+    for (int k = 0; k < pred_c; ++k) {
+      for (int j = 0; j < cfg.cout; ++j) p.pred_wb[k * 32 + j] = pred_w[k * cfg.cout + j];     // HOST arrays
+      p.pred_wb[128 + k] = pred_b[k];
+    }
+  }
   cudaStream_t st = (cudaStream_t)stream;
   if (cfg.ck == 64) return cfg.b_resident ? launch_tc<64, true>(mx, mw, mr, mi, p, cfg.smem_bytes, st)
                                           : launch_tc<64, false>(mx, mw, mr, mi, p, cfg.smem_bytes, st);

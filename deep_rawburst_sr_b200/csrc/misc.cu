@@ -74,6 +74,24 @@ __global__ void copy_channels_kernel(View src, View dst, int group, int src_grou
   }
 }
 
+// same dtype, channel counts / offsets / pitches multiples of 8 (bf16) and 16-byte aligned views: one thread moves 16
+// bytes; grid.y walks the images so that the per-thread decode is 32-bit (the generic kernel above spends its time in
+// 64-bit divisions and per-element dtype dispatch)
+__global__ void copy_channels_v8_kernel(View src, View dst, int group, int src_group, int src_first) {
+  griddep_wait();
+  const int HW = dst.h * dst.w, C8 = dst.c >> 3;
+  const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (unsigned)(HW * C8)) return;
+  const int rem = (int)(idx / (unsigned)C8), c8 = (int)(idx - (unsigned)rem * (unsigned)C8);
+  const __nv_bfloat16* sb = reinterpret_cast<const __nv_bfloat16*>(src.data) + src.c_off + c8 * 8;
+  __nv_bfloat16* db = reinterpret_cast<__nv_bfloat16*>(dst.data) + dst.c_off + c8 * 8;
+  for (int n = blockIdx.y; n < dst.n; n += gridDim.y) {
+    const int sn = group > 0 ? (n / group) * src_group + src_first : n;
+    const uint4 v = __ldg(reinterpret_cast<const uint4*>(sb + ((long long)sn * HW + rem) * src.c_pitch));
+    *reinterpret_cast<uint4*>(db + ((long long)n * HW + rem) * dst.c_pitch) = v;
+  }
+}
+
 // -------------------------------------------------------------------------------------------------------
 // Space to depth (2x2): y[n, Y, X, (p*2 + q)*C + c] = x[n, 2Y + p, 2X + q, c]  (zero beyond the image: odd sizes).
 // A 3x3 / stride-2 / pad-1 convolution of x is then a 3x3 / stride-1 / pad-1 convolution of y whose taps
@@ -167,6 +185,71 @@ __global__ void prep_burst_kernel(const float* __restrict__ burst, int H, int W,
         rgb[c] = top * (1.0f - wy) + bot * wy;
       }
       for (int c = 0; c < pwc_in.c; ++c) view_st(pwc_in, j, c, c < 3 ? rgb[c] : 0.0f);
+    }
+  }
+}
+
+// The same preparation for the bf16 tensor-core PWC-Net path, with the space-to-depth of the extractor's first stride-2
+// conv folded in: instead of the fp32 [Hp, Wp, 4] image (29 MB at B=32) and a second kernel that re-reads it, the
+// resized RGB image is written directly as pwc_s2d[n, Y, X, (2p + q) * 3 + c] = rgb[n, 2Y + p, 2X + q, c] in bf16
+// (12 channels + 4 zero pad = two 16-byte stores per thread).  grid.y walks the frames (32-bit decode per thread).
+__device__ __forceinline__ void resized_rgb(const float* __restrict__ b, int H, int W, int HW, float sy, float sx, int oy, int ox,
+                                            float (&rgb)[3]) {
+  const float fy = fmaxf((oy + 0.5f) * sy - 0.5f, 0.0f);
+  const float fx = fmaxf((ox + 0.5f) * sx - 0.5f, 0.0f);
+  const int y0 = min((int)fy, H - 1), x0 = min((int)fx, W - 1);
+  const int y1 = min(y0 + 1, H - 1), x1 = min(x0 + 1, W - 1);
+  const float wy = fy - (float)y0, wx = fx - (float)x0;
+  const int p00 = y0 * W + x0, p01 = y0 * W + x1, p10 = y1 * W + x0, p11 = y1 * W + x1;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    float v[4];
+    const int pix[4] = {p00, p01, p10, p11};
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      if (c == 0) v[t] = __ldg(b + pix[t]);
+      else if (c == 1) v[t] = (__ldg(b + HW + pix[t]) + __ldg(b + 2 * HW + pix[t])) / 2.0f;
+      else v[t] = __ldg(b + 3 * HW + pix[t]);
+    }
+    const float top = v[0] * (1.0f - wx) + v[1] * wx;       // same association as prep_burst_kernel / ATen
+    const float bot = v[2] * (1.0f - wx) + v[3] * wx;
+    rgb[c] = top * (1.0f - wy) + bot * wy;
+  }
+}
+__device__ __forceinline__ uint32_t bf16x2_bits(float lo, float hi) {
+  const __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
+__global__ void __launch_bounds__(256) prep_burst_s2d_kernel(const float* __restrict__ burst, int H, int W, int Hp, int Wp,
+                                                             View enc_in, View pwc_s2d) {
+  griddep_wait();
+  const int HW = H * W, H2 = Hp >> 1, W2 = Wp >> 1;
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= HW + H2 * W2) return;
+  const bool enc_vec = enc_in.dtype == DBSR_BF16 && enc_in.c_off == 0 && enc_in.c_pitch == 8 && ((uintptr_t)enc_in.data % 16) == 0;
+  const float sy = (float)H / (float)Hp, sx = (float)W / (float)Wp;
+  for (int f = blockIdx.y; f < enc_in.n; f += gridDim.y) {
+    const float* b = burst + (long long)f * 4 * HW;
+    if (idx < HW) {
+      const float v0 = __ldg(b + idx), v1 = __ldg(b + HW + idx), v2 = __ldg(b + 2 * HW + idx), v3 = __ldg(b + 3 * HW + idx);
+      const long long i = (long long)f * HW + idx;
+      if (enc_vec) {
+        *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(enc_in.data) + i * 8) =
+            make_uint4(bf16x2_bits(v0, v1), bf16x2_bits(v2, v3), 0u, 0u);
+      } else {
+        const float v[4] = {v0, v1, v2, v3};
+        for (int c = 0; c < enc_in.c; ++c) view_st(enc_in, i, c, c < 4 ? v[c] : 0.0f);
+      }
+    } else {
+      const int j = idx - HW;
+      const int Y = j / W2, X = j - Y * W2;
+      float r[4][3];
+#pragma unroll
+      for (int pq = 0; pq < 4; ++pq) resized_rgb(b, H, W, HW, sy, sx, 2 * Y + (pq >> 1), 2 * X + (pq & 1), r[pq]);
+      uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(pwc_s2d.data) + ((long long)f * H2 * W2 + j) * 16);
+      dst[0] = make_uint4(bf16x2_bits(r[0][0], r[0][1]), bf16x2_bits(r[0][2], r[1][0]), bf16x2_bits(r[1][1], r[1][2]),
+                          bf16x2_bits(r[2][0], r[2][1]));
+      dst[1] = make_uint4(bf16x2_bits(r[2][2], r[3][0]), bf16x2_bits(r[3][1], r[3][2]), 0u, 0u);
     }
   }
 }
@@ -315,11 +398,11 @@ __global__ void flow_head_kernel(View f4, float* __restrict__ offsets, int H, in
 __global__ void offsets_mod_kernel(const float* __restrict__ offsets, View out, int frames, float modulo) {
   griddep_wait();
   const int HW = out.h * out.w;
-  const long long total = (long long)out.n * HW;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    const int img = (int)(i / HW);
-    const int rem = (int)(i - (long long)img * HW);
+  const int rem = blockIdx.x * blockDim.x + threadIdx.x;
+  if (rem >= HW) return;
+  // 8-channel bf16 rows (the engine's layout): the two offsets and six zero channels are one 16-byte store
+  const bool vec = out.dtype == DBSR_BF16 && out.c == 8 && out.c_off == 0 && out.c_pitch == 8 && ((uintptr_t)out.data % 16) == 0;
+  for (int img = blockIdx.y; img < out.n; img += gridDim.y) {
     const int b = img / frames, f = img - b * frames;
     float v[2] = {0.0f, 0.0f};
     if (f > 0) {
@@ -335,7 +418,14 @@ __global__ void offsets_mod_kernel(const float* __restrict__ offsets, View out, 
         v[c] = r;
       }
     }
-    for (int c = 0; c < out.c; ++c) view_st(out, i, c, c < 2 ? v[c] : 0.0f);
+    const long long i = (long long)img * HW + rem;
+    if (vec) {
+      const __nv_bfloat162 h = __floats2bfloat162_rn(v[0], v[1]);
+      *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(out.data) + i * 8) =
+          make_uint4(*reinterpret_cast<const uint32_t*>(&h), 0u, 0u, 0u);
+    } else {
+      for (int c = 0; c < out.c; ++c) view_st(out, i, c, c < 2 ? v[c] : 0.0f);
+    }
   }
 }
 
@@ -460,6 +550,15 @@ extern "C" int dbsr_copy_channels(const dbsr_nhwc_t* src, const dbsr_nhwc_t* dst
   else
     DBSR_REQUIRE(src->n == dst->n, "copy_channels: image count mismatch");
   const long long total = (long long)dst->n * dst->h * dst->w * dst->c;
+  auto al = [](const dbsr_nhwc_t* v) {
+    return v->dtype == DBSR_BF16 && v->c_off % 8 == 0 && v->c_pitch % 8 == 0 && ((uintptr_t)v->data % 16) == 0;
+  };
+  if (al(src) && al(dst) && dst->c % 8 == 0 && (long long)dst->h * dst->w * (dst->c / 8) < (1ll << 31)) {
+    const dim3 g((unsigned)ceil_div((long long)dst->h * dst->w * (dst->c / 8), 256), (unsigned)(dst->n < 65535 ? dst->n : 65535));
+    launch_pdl(copy_channels_v8_kernel, dim3(g), dim3(256), 0, (cudaStream_t)stream, make_view(src), make_view(dst), group, src_group,
+               src_first);
+    return check_launch("copy_channels");
+  }
   launch_pdl(copy_channels_kernel, dim3(grid_for(total, 256)), dim3(256), 0, (cudaStream_t)stream, make_view(src), make_view(dst), group,
                                                                                 src_group, src_first);
   return check_launch("copy_channels");
@@ -485,6 +584,22 @@ extern "C" int dbsr_prep_burst(const float* burst, int32_t frames, int32_t H, in
   launch_pdl(prep_burst_kernel, dim3(grid_for(total, 256)), dim3(256), 0, (cudaStream_t)stream, burst, H, W, make_view(enc_in),
                                                                              make_view(pwc_in));
   return check_launch("prep_burst");
+}
+
+extern "C" int dbsr_prep_burst_s2d(const float* burst, int32_t frames, int32_t H, int32_t W, int32_t Hp, int32_t Wp,
+                                   const dbsr_nhwc_t* enc_in, const dbsr_nhwc_t* pwc_s2d, void* stream) {
+  DBSR_REQUIRE(burst && view_ok(enc_in) && view_ok(pwc_s2d), "prep_burst_s2d: bad arguments");
+  DBSR_REQUIRE(enc_in->n == frames && enc_in->h == H && enc_in->w == W && enc_in->c >= 4, "prep_burst_s2d: enc_in geometry mismatch");
+  DBSR_REQUIRE(Hp >= H && Wp >= W && Hp % 2 == 0 && Wp % 2 == 0 && pwc_s2d->n == frames && pwc_s2d->h == Hp / 2 &&
+                   pwc_s2d->w == Wp / 2 && pwc_s2d->c == 12 && pwc_s2d->c_off == 0 && pwc_s2d->c_pitch == 16 &&
+                   pwc_s2d->dtype == DBSR_BF16 && ((uintptr_t)pwc_s2d->data % 16) == 0,
+               "prep_burst_s2d: pwc_s2d must be a dense bf16 [frames, Hp/2, Wp/2, 12 (+4 pad)] buffer");
+  const long long per_frame = (long long)H * W + (long long)(Hp / 2) * (Wp / 2);
+  DBSR_REQUIRE(per_frame < (1ll << 31), "prep_burst_s2d: frame too large");
+  const dim3 g((unsigned)ceil_div(per_frame, 256), (unsigned)(frames < 65535 ? frames : 65535));
+  launch_pdl(prep_burst_s2d_kernel, dim3(g), dim3(256), 0, (cudaStream_t)stream, burst, H, W, Hp, Wp, make_view(enc_in),
+             make_view(pwc_s2d));
+  return check_launch("prep_burst_s2d");
 }
 
 extern "C" int dbsr_deconv4x4s2(const dbsr_nhwc_t* x, const float* w, const float* bias, const dbsr_nhwc_t* y,
@@ -535,8 +650,8 @@ extern "C" int dbsr_offsets_mod(const float* offsets, const dbsr_nhwc_t* out, in
                                 float modulo, void* stream) {
   DBSR_REQUIRE(offsets && view_ok(out) && out->n == bursts * frames && out->c >= 2 && frames >= 2,
                "offsets_mod: bad arguments");
-  const long long total = (long long)out->n * out->h * out->w;
-  launch_pdl(offsets_mod_kernel, dim3(grid_for(total, 256)), dim3(256), 0, (cudaStream_t)stream, offsets, make_view(out), frames, modulo);
+  const dim3 g((unsigned)ceil_div((long long)out->h * out->w, 256), (unsigned)(out->n < 65535 ? out->n : 65535));
+  launch_pdl(offsets_mod_kernel, dim3(g), dim3(256), 0, (cudaStream_t)stream, offsets, make_view(out), frames, modulo);
   return check_launch("offsets_mod");
 }
 

@@ -274,6 +274,10 @@ class DBSREngine:
                 add(f'decoder.post_res_layers.{i}.conv2.0')
             self.pred_w = sd['decoder.predictor.0.weight'].float().reshape(sd['decoder.predictor.0.weight'].shape[0], -1).contiguous()
             self.pred_b = sd['decoder.predictor.0.bias'].float().contiguous()
+            # host copies for the fused predictor epilogue (its weights travel in the kernel parameters)
+            import ctypes
+            self.pred_w_host = (ctypes.c_float * self.pred_w.numel())(*self.pred_w.reshape(-1).cpu().tolist())
+            self.pred_b_host = (ctypes.c_float * self.pred_b.numel())(*self.pred_b.cpu().tolist())
             self.feat_dim = sd['decoder.init_layer.0.weight'].shape[1]
 
     # ------------------------------------------------------------------------------------------------
@@ -306,7 +310,7 @@ class DBSREngine:
         if pred is not None:
             assert use_tc, 'the fused predictor epilogue exists on the tensor-core path only'
             self.flops[fam] += 2 * x.n * ho * wo * self.pred_w.shape[0] * cw.cout
-            ops.conv2d_tc_predictor(x, cw.tc, bias_tc, y, cw.ksize, act, residual, self.pred_w, self.pred_b, pred)
+            ops.conv2d_tc_predictor(x, cw.tc, bias_tc, y, cw.ksize, act, residual, self.pred_w_host, self.pred_b_host, pred)
         elif use_tc:
             ops.conv2d(x, cw.tc, bias_tc, y, cw.ksize, stride, dilation, act, residual, cw.shuffle_r, tensor_core=True)
         else:
@@ -376,12 +380,18 @@ class DBSREngine:
     # ------------------------------------------------------------------------------------------------
     # PWC-Net  (reference models/alignment/pwcnet.py)
     # ------------------------------------------------------------------------------------------------
-    def pwc_extract(self, ws: dict, pwc_in: Act) -> list:
-        """Extractor pyramid (pwcnet.py:45-111) on every image of `pwc_in` [n, Hp, Wp, >=3]."""
+    def pwc_extract(self, ws: dict, pwc_in: Optional[Act], s2d0: Optional[Act] = None) -> list:
+        """Extractor pyramid (pwcnet.py:45-111) on every image of `pwc_in` [n, Hp, Wp, >=3] -- or, on the bf16 path, of
+        `s2d0` [n, Hp/2, Wp/2, 12]: the same images already in the space-to-depth layout of the first stride-2 conv
+        (written by ops.prep_burst_s2d)."""
         pre = self.pwc_prefix
-        n = pwc_in.n
-        x = pwc_in.slice(0, 3)
-        h, w = pwc_in.h, pwc_in.w
+        if s2d0 is not None:
+            n, h, w = s2d0.n, 2 * s2d0.h, 2 * s2d0.w
+            x = None
+        else:
+            n = pwc_in.n
+            x = pwc_in.slice(0, 3)
+            h, w = pwc_in.h, pwc_in.w
         feats = []
         for l, name in enumerate(PWC_NAMES):
             c = PWC_EXT_CH[l + 1]
@@ -390,7 +400,9 @@ class DBSREngine:
             t2 = self._buf(ws, f'ext{l}_b', n, h, w, c, self.pwc_dtype)
             f = self._buf(ws, f'ext{l}_f', n, h, w, c, self.pwc_dtype)
             k0 = f'{pre}netExtractor.net{name}.0'
-            if (k0 + '.s2d') in self.W:
+            if l == 0 and s2d0 is not None:
+                self._conv(k0 + '.s2d', s2d0, t1, ACT_LRELU, real_cin=3)
+            elif (k0 + '.s2d') in self.W:
                 xs = self._buf(ws, f'ext{l}_s2d', n, h, w, 4 * x.c, torch.bfloat16)
                 self._run('copy', ops.space_to_depth2, x, xs)
                 self._conv(k0 + '.s2d', xs, t1, ACT_LRELU, real_cin=x.c)
@@ -449,13 +461,31 @@ class DBSREngine:
         self._conv(f'{pre}netRefiner.netMain.12', x, flow4, ACT_NONE, dilation=1, residual=prev_flow)
         return flow4
 
-    def pwc_burst(self, ws: dict, pwc_in: Act, B: int, N: int, H: int, W: int, offsets: torch.Tensor) -> torch.Tensor:
+    def pwc_burst(self, ws: dict, pwc_in: Optional[Act], B: int, N: int, H: int, W: int, offsets: torch.Tensor,
+                  s2d0: Optional[Act] = None) -> torch.Tensor:
         """PWCNet.forward (pwcnet.py:248-281) for a burst batch: frame 0 of every burst is the target; the pyramid of
         each frame is computed once (the reference recomputes the reference frame's pyramid N-1 times)."""
-        feats = self.pwc_extract(ws, pwc_in)
+        feats = self.pwc_extract(ws, pwc_in, s2d0)
         flow4 = self.pwc_decode(ws, feats, feats, B * (N - 1), N - 1, N)
-        self._run('flow_head', ops.flow_head, flow4, offsets, H, W, pwc_in.h, pwc_in.w)
+        Hp, Wp = (2 * s2d0.h, 2 * s2d0.w) if s2d0 is not None else (pwc_in.h, pwc_in.w)
+        self._run('flow_head', ops.flow_head, flow4, offsets, H, W, Hp, Wp)
         return offsets
+
+    def prep_and_align(self, ws: dict, burst: torch.Tensor, enc_in: Act, offsets: torch.Tensor) -> torch.Tensor:
+        """burst [B, N, 4, H, W] fp32 -> `enc_in` (channels-last packed RAW for the encoder) and the flows `offsets`
+        [B*(N-1), 2, H, W] of every frame towards frame 0 (encoders.py:52-61 + PWCNet.forward)."""
+        B, N, _, H, W = burst.shape
+        Hp, Wp = int(math.ceil(H / 64.0) * 64), int(math.ceil(W / 64.0) * 64)
+        F_ = B * N
+        s2d0 = pwc_in = None
+        if (self.pwc_prefix + 'netExtractor.netOne.0.s2d') in self.W:
+            # bf16 PWC-Net: RGGB->RGB + resize written straight into the space-to-depth layout of the first stride-2 conv
+            s2d0 = self._buf(ws, 'ext0_s2d', F_, Hp // 2, Wp // 2, 12, torch.bfloat16)
+            self._run('prep_burst', ops.prep_burst_s2d, burst, enc_in, s2d0, Hp, Wp)
+        else:
+            pwc_in = self._buf(ws, 'pwc_in', F_, Hp, Wp, 4, torch.float32)
+            self._run('prep_burst', ops.prep_burst, burst, enc_in, pwc_in)
+        return self.pwc_burst(ws, pwc_in, B, N, H, W, offsets, s2d0)
 
     # ------------------------------------------------------------------------------------------------
     # DBSR stages
@@ -576,14 +606,12 @@ class DBSREngine:
         ws = self.workspace((B, N, H, W))
         F_ = B * N
         enc_in = self._buf(ws, 'enc_in', F_, H, W, 8, self.act_dtype)
-        pwc_in = self._buf(ws, 'pwc_in', F_, Hp, Wp, 4, torch.float32)
-        self._run('prep_burst', ops.prep_burst, burst, enc_in, pwc_in)
         if out is None:
             out = {}
         offsets = out.get('offsets')
         if offsets is None:
             offsets = torch.empty((B * (N - 1), 2, H, W), dtype=torch.float32, device=self.device)
-        self.pwc_burst(ws, pwc_in, B, N, H, W, offsets)
+        self.prep_and_align(ws, burst, enc_in, offsets)
         feat = self.encode(ws, enc_in)
         weights = None
         if return_weights:

@@ -96,17 +96,24 @@ def conv2d(x: Act, w: torch.Tensor, bias: Optional[torch.Tensor], y: Act, ksize:
 
 
 def conv2d_tc_predictor(x: Act, w: torch.Tensor, bias: Optional[torch.Tensor], y: Act, ksize: int, act: int,
-                        residual: Optional[Act], pred_w: torch.Tensor, pred_b: torch.Tensor, pred: torch.Tensor) -> torch.Tensor:
+                        residual: Optional[Act], pred_w, pred_b, pred: torch.Tensor) -> torch.Tensor:
     """tcgen05 conv whose epilogue applies the 1x1 predictor + ReLU and writes `pred` [n, k, h, w] fp32 directly (the conv
-    output map `y` is not written; it only describes the geometry)."""
-    k = pred_w.shape[0]
-    assert pred_w.dtype == torch.float32 and pred_w.is_contiguous() and pred_w.shape[1] == y.c
-    assert pred_b.dtype == torch.float32 and pred_b.numel() == k
+    output map `y` is not written; it only describes the geometry).  pred_w [k][Cout] / pred_b [k]: HOST values (CPU
+    tensors, lists or ctypes float arrays) -- they are copied into the kernel parameters."""
+    if not isinstance(pred_w, ctypes.Array):
+        pw = torch.as_tensor(pred_w, dtype=torch.float32).cpu().reshape(-1, y.c)
+        pred_w = (ctypes.c_float * pw.numel())(*pw.reshape(-1).tolist())
+    if not isinstance(pred_b, ctypes.Array):
+        pb = torch.as_tensor(pred_b, dtype=torch.float32).cpu().reshape(-1)
+        pred_b = (ctypes.c_float * pb.numel())(*pb.tolist())
+    k = len(pred_b)
+    assert len(pred_w) == k * y.c
     assert pred.dtype == torch.float32 and pred.is_contiguous() and tuple(pred.shape) == (x.n, k, x.h, x.w)
     d = ConvDesc(x.view(), y.view(), residual.view() if residual is not None else _NULL_VIEW, w.data_ptr(),
                  _ptr(bias), ksize, 1, 1, act, 0)
-    _lib.check(_lib.load_library().dbsr_conv2d_tc_predictor(ctypes.byref(d), pred_w.data_ptr(), pred_b.data_ptr(), k,
-                                                            pred.data_ptr(), _stream()), 'dbsr_conv2d_tc_predictor')
+    _lib.check(_lib.load_library().dbsr_conv2d_tc_predictor(ctypes.byref(d), ctypes.cast(pred_w, ctypes.c_void_p),
+                                                            ctypes.cast(pred_b, ctypes.c_void_p), k, pred.data_ptr(),
+                                                            _stream()), 'dbsr_conv2d_tc_predictor')
     return pred
 
 
@@ -176,6 +183,16 @@ def prep_burst(burst: torch.Tensor, enc_in: Act, pwc_in: Act) -> None:
     e, p = enc_in.view(), pwc_in.view()
     _lib.check(_lib.load_library().dbsr_prep_burst(burst.data_ptr(), frames, burst.shape[3], burst.shape[4],
                                                    ctypes.byref(e), ctypes.byref(p), _stream()), 'dbsr_prep_burst')
+
+
+def prep_burst_s2d(burst: torch.Tensor, enc_in: Act, pwc_s2d: Act, Hp: int, Wp: int) -> None:
+    """prep_burst for the bf16 PWC-Net path: the resized RGB image is written directly in the space-to-depth layout the
+    extractor's first (stride-2) convolution consumes, bf16 [frames, Hp/2, Wp/2, 12 (+4 pad)]"""
+    assert burst.dtype == torch.float32 and burst.is_contiguous() and burst.dim() == 5 and burst.shape[2] == 4
+    frames = burst.shape[0] * burst.shape[1]
+    e, p = enc_in.view(), pwc_s2d.view()
+    _lib.check(_lib.load_library().dbsr_prep_burst_s2d(burst.data_ptr(), frames, burst.shape[3], burst.shape[4], Hp, Wp,
+                                                       ctypes.byref(e), ctypes.byref(p), _stream()), 'dbsr_prep_burst_s2d')
 
 
 def flow_head(flow4: Act, offsets: torch.Tensor, H: int, W: int, Hp: int, Wp: int) -> torch.Tensor:

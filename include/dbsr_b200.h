@@ -69,6 +69,12 @@ int dbsr_copy_channels(const dbsr_nhwc_t* src, const dbsr_nhwc_t* dst, int32_t g
 /* -------------------------------------------------------------------------------------------------- */
 int dbsr_prep_burst(const float* burst, int32_t frames, int32_t H, int32_t W, const dbsr_nhwc_t* enc_in,
                     const dbsr_nhwc_t* pwc_in, void* stream);
+/* The same for the bf16 tensor-core PWC-Net path with the space-to-depth of the extractor's first stride-2 convolution
+ * (dbsr_space_to_depth2 above) folded in: the resized RGB image is written directly as
+ *   pwc_s2d[n, Y, X, (2p + q) * 3 + c] = rgb[n, 2Y + p, 2X + q, c]   bf16, dense [frames, Hp/2, Wp/2, 12 (+4 zero pad)]
+ * so the fp32 [Hp, Wp] image never exists in HBM.  Hp, Wp: the multiples of 64 of pwcnet.py:263-264.                 */
+int dbsr_prep_burst_s2d(const float* burst, int32_t frames, int32_t H, int32_t W, int32_t Hp, int32_t Wp,
+                        const dbsr_nhwc_t* enc_in, const dbsr_nhwc_t* pwc_s2d, void* stream);
 
 /* -------------------------------------------------------------------------------------------------- */
 /* convolution, CUDA-core path (exact fp32 accumulate; any Cin/Cout/stride/dilation)                   */
@@ -106,7 +112,8 @@ int dbsr_conv2d_tc_supported(const dbsr_conv_t* p);
  * channels of its pixel, so  pred[n, k, y, x] = relu(pred_b[k] + sum_c pred_w[k][c] * act(conv(x) + bias (+ residual))[c])
  * is computed in fp32 registers and stored as fp32 NCHW; the map y itself is NOT written (p->y only gives the geometry).
  *   Needs Cout <= 32 on a map wider than 8 pixels, a residual (if any) that the kernel accumulates on the tensor core
- *   (bf16, Cout == 32), 1 <= pred_c <= 4.  pred_w: fp32 [pred_c][Cout], pred_b: fp32 [pred_c].                       */
+ *   (bf16, Cout == 32), 1 <= pred_c <= 4.  pred_w: fp32 [pred_c][Cout], pred_b: fp32 [pred_c] -- HOST arrays: the <= 132
+ *   values are copied into the kernel parameters (constant bank), the only non-device pointers of this ABI.            */
 int dbsr_conv2d_tc_predictor(const dbsr_conv_t* p, const float* pred_w, const float* pred_b, int32_t pred_c, float* pred,
                              void* stream);
 /* tiling chosen for (Cin, Cout): K chunk (64 -> SWIZZLE_128B, 32 -> SWIZZLE_64B), padded K, UMMA N, padded Cout */

@@ -33,6 +33,20 @@ def _act_from(x_nchw, dev, dtype=torch.float32, pitch=None, c_off=0):
     return v
 
 
+def test_copy_channels_vector_and_generic(dev):
+    """copy of a feature map into a channel slice of a wider buffer with the burst pair->image mapping (reference frame of
+    burst b replicated to its N-1 pairs): 16-byte vector path (bf16, 8-aligned) and the generic scalar path"""
+    from deep_rawburst_sr_b200 import ops
+    B, N, C, H, W = 3, 4, 32, 6, 5
+    src = torch.randn(B * N, C, H, W, generator=_gen(21)).bfloat16().float()
+    want = src.view(B, N, C, H, W)[:, :1].expand(-1, N - 1, -1, -1, -1).reshape(-1, C, H, W)
+    for c_off, c in ((16, C), (13, C - 3)):          # aligned -> vector kernel; odd offset / count -> generic kernel
+        dst = ops.Act(torch.full((B * (N - 1), H, W, 64), 2.0, dtype=torch.bfloat16, device=dev))
+        ops.copy_channels(_act_from(src[:, :c].contiguous(), dev, dtype=torch.bfloat16, pitch=40), dst.slice(c_off, c), N - 1, N, 0)
+        assert torch.equal(dst.slice(c_off, c).to_nchw().cpu(), want[:, :c])
+        assert (dst.buf[..., :c_off] == 2.0).all() and (dst.buf[..., c_off + c:] == 2.0).all()
+
+
 def test_layout_roundtrip(dev):
     x = torch.randn(3, 37, 9, 11, generator=_gen(0))
     for dtype, tol in ((torch.float32, 0.0), (torch.bfloat16, 2e-2)):
@@ -287,6 +301,26 @@ def test_prep_burst_and_flow_head(dev):
     assert (offsets.cpu() - ref).abs().max() < 2e-6 * max(1.0, float(ref.abs().max()))   # fp32 round-off, |flow| ~ 20
 
 
+@pytest.mark.parametrize('H,W', [(24, 40), (48, 48), (80, 80), (64, 128)])
+def test_prep_burst_s2d_equals_prep_plus_space_to_depth(dev, H, W):
+    """the fused preparation of the bf16 PWC-Net path (RGGB->RGB + resize + space-to-depth + bf16) is bit-identical to
+    prep_burst followed by space_to_depth2, and its encoder input equals the packed RAW frame (bf16-rounded)"""
+    from deep_rawburst_sr_b200 import ops
+    burst = torch.rand(2, 3, 4, H, W, generator=_gen(H + W)).to(dev)
+    Hp, Wp = (H + 63) // 64 * 64, (W + 63) // 64 * 64
+    enc_a = ops.Act.empty(6, H, W, 8, torch.bfloat16, dev)
+    pwc_in = ops.Act.empty(6, Hp, Wp, 4, torch.float32, dev)
+    ops.prep_burst(burst, enc_a, pwc_in)
+    ref = ops.Act.empty(6, Hp // 2, Wp // 2, 16, torch.bfloat16, dev, zero=True).slice(0, 12)
+    ops.space_to_depth2(pwc_in.slice(0, 3), ref)
+    enc_b = ops.Act(torch.full((6, H, W, 8), 9.0, dtype=torch.bfloat16, device=dev))
+    got = ops.Act(torch.full((6, Hp // 2, Wp // 2, 16), 9.0, dtype=torch.bfloat16, device=dev)).slice(0, 12)
+    ops.prep_burst_s2d(burst, enc_b, got, Hp, Wp)
+    assert torch.equal(got.buf, ref.buf)          # pad channels included (zero)
+    assert torch.equal(enc_b.buf, enc_a.buf)
+    assert torch.equal(enc_b.buf[..., :4].float(), burst.view(6, 4, H, W).permute(0, 2, 3, 1).bfloat16().float())
+
+
 @pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
 def test_warp(dev, dtype, golden_dir):
     import os
@@ -324,6 +358,11 @@ def test_offsets_mod_and_wp_input(dev):
     got = out.slice(0, 2).to_nchw().cpu()
     assert torch.equal(got, ref), (got - ref).abs().max()
     assert float(out.buf[..., 2:].abs().max()) == 0
+    # the engine's layout: dense 8-channel bf16 rows (one 16-byte store per pixel)
+    out16 = ops.Act(torch.full((B * N, H, W, 8), 5.0, dtype=torch.bfloat16, device=dev))
+    ops.offsets_mod(offs.to(dev), out16, B, N, 1.0)
+    assert torch.equal(out16.slice(0, 2).to_nchw().cpu(), ref.bfloat16().float())
+    assert float(out16.buf[..., 2:].float().abs().max()) == 0
     proj = torch.randn(B * N, 16, H, W, generator=g)
     wp = ops.Act.empty(B * N, H, W, 48, torch.float32, dev, zero=True)
     ops.build_wp_input(_act_from(proj, dev), wp, N)
@@ -396,8 +435,16 @@ def test_blur_and_predictor(dev):
     K = O.gauss_kernel3()
     ref = F.conv2d(x.view(-1, 1, 16, 24), K.view(1, 1, 3, 3), padding=1).view(2, 32, 16, 24)
     y = ops.Act.empty(2, 16, 24, 32, torch.float32, dev)
-    ops.blur3x3(_act_from(x, dev), y, K.reshape(-1).tolist())
+    ops.blur3x3(_act_from(x, dev), y, K.reshape(-1).tolist())          # Gaussian = rank 1: separable kernel
     assert (y.to_nchw().cpu() - ref).abs().max() < 1e-6
+    # a kernel that is NOT separable takes the 9-tap path; tall maps cross the 32-row blocks of the separable one
+    K9 = torch.rand(3, 3, generator=g)
+    for kk in (K9, torch.outer(torch.tensor([0.2, 0.5, 0.3]), torch.tensor([0.1, 0.7, 0.2]))):
+        xt = torch.rand(1, 8, 70, 9, generator=g)
+        reft = F.conv2d(xt.view(-1, 1, 70, 9), kk.view(1, 1, 3, 3), padding=1).view(1, 8, 70, 9)
+        yt = ops.Act.empty(1, 70, 9, 8, torch.float32, dev)
+        ops.blur3x3(_act_from(xt, dev), yt, kk.reshape(-1).tolist())
+        assert (yt.to_nchw().cpu() - reft).abs().max() < 1e-6
     wt = torch.randn(3, 32, generator=g)
     b = torch.randn(3, generator=g)
     pred = torch.empty(2, 3, 16, 24, device=dev)

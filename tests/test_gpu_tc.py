@@ -136,7 +136,7 @@ def test_conv2d_tc_fused_predictor(n, h, w, use_res, k):
     ya = ops.Act(torch.full((n, h, w, 32), 5.0, dtype=torch.bfloat16, device=dev))
     ra = ops.Act.empty(n, h, w, 32, torch.bfloat16, dev).from_nchw(res.to(dev)) if use_res else None
     pred = torch.full((n, 3, h, w), -1.0, device=dev)
-    ops.conv2d_tc_predictor(xa, pack_tc(wt.to(dev)), b.to(dev), ya, k, ops.ACT_RELU, ra, pw.to(dev).contiguous(), pb.to(dev), pred)
+    ops.conv2d_tc_predictor(xa, pack_tc(wt.to(dev)), b.to(dev), ya, k, ops.ACT_RELU, ra, pw, pb, pred)
     torch.cuda.synchronize()
     err = (pred.cpu() - ref).abs().max().item()
     assert err <= 1e-4 * max(1.0, ref.abs().max().item()), err

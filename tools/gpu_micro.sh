@@ -16,8 +16,10 @@ for l in open('gpurun_out/micro.json'):
     elif d['leg'] == 'corr81':
         print('corr81', d['frame'], d['dtype'], 'all %.1f us %.0f GB/s' % (d['us_all_levels'], d['hbm_gbs_all_levels']),
               ' '.join('L%d:%.1fus' % (x['level'], x['us']) for x in d['levels']))
-    else:
+    elif d['leg'] == 'pwc_align':
         print('pwc_align', d['frame'], d['precision'], '%.2f ms %.0f pairs/s' % (d['ms'], d['pairs_per_s']))
+    elif d['leg'] == 'sca':
+        print('sca', d['size'], d['alignment_net_precision'], '%.2f ms %.0f images/s' % (d['ms'], d['images_per_s']))
 PY
 if [ "${RUN_NCU:-1}" = "1" ]; then
   echo "== ncu"
