@@ -40,6 +40,7 @@ def parse():
     ap.add_argument('--layers-out', default='', help='write the per-conv-layer time table of the instrumented pass here')
     ap.add_argument('--one-forward', action='store_true', help='profiling aid: warm up, run ONE eager forward, exit')
     ap.add_argument('--no-graph', action='store_true', help='launch eagerly instead of replaying a CUDA graph')
+    ap.add_argument('--no-overlap', action='store_true', help='run PWC-Net and the encoder on ONE stream (default: two, fork / join)')
     return ap.parse_args()
 
 
@@ -172,6 +173,7 @@ def main():
     net = net.to(dev).eval().set_precision(args.precision)
     net.use_cuda_graph = not args.no_graph     # the ~137 launches of one forward are captured once per shape and replayed
     eng = net.engine(dev)
+    eng.overlap_alignment = not args.no_overlap
 
     B, S = args.batch, args.size
     gen = torch.Generator().manual_seed(1000 + rank)
@@ -392,7 +394,7 @@ def main():
                 'api': 'deep_rawburst_sr_b200.pipeline.HostPipeline.submit(host_in, host_out)',
                 'serialised_copies': {'value': e2e_sync, 'ms_per_step': ms_e2e_sync / args.steps,
                                       'api': 'net(host_in.to(device)) ; host_out.copy_(pred)'}},
-        'gpu_launches': launches, 'cuda_graph': not args.no_graph, 'output_gather': gather,
+        'gpu_launches': launches, 'cuda_graph': not args.no_graph, 'alignment_encoder_overlap': not args.no_overlap, 'output_gather': gather,
         'roofline': roofline,
         'kernel_families': families,
         'cpu_baseline': cpu,

@@ -162,6 +162,8 @@ class DBSREngine:
         self.D: Dict[str, tuple] = {}
         self._ws: Dict[tuple, dict] = {}
         self._graphs: Dict[tuple, tuple] = {}
+        self._side = None                 # second stream of the alignment / encoder overlap
+        self.overlap_alignment = True
         self.launches = 0
         self.layer_events = None   # when a dict (and timers is on): conv layer key -> [(events, flops, family, shape)]
         self.timers = None   # when a dict: family -> list of (start, end) CUDA events on the launching stream
@@ -475,17 +477,22 @@ class DBSREngine:
         """burst [B, N, 4, H, W] fp32 -> `enc_in` (channels-last packed RAW for the encoder) and the flows `offsets`
         [B*(N-1), 2, H, W] of every frame towards frame 0 (encoders.py:52-61 + PWCNet.forward)."""
         B, N, _, H, W = burst.shape
+        s2d0, pwc_in = self.prep(ws, burst, enc_in)
+        return self.pwc_burst(ws, pwc_in, B, N, H, W, offsets, s2d0)
+
+    def prep(self, ws: dict, burst: torch.Tensor, enc_in: Act):
+        """burst -> `enc_in` + the PWC-Net input: (s2d0, None) on the bf16 path (RGGB->RGB + resize written straight into
+        the space-to-depth layout of the extractor's first stride-2 conv), (None, pwc_in) on the fp32 path."""
+        B, N, _, H, W = burst.shape
         Hp, Wp = int(math.ceil(H / 64.0) * 64), int(math.ceil(W / 64.0) * 64)
         F_ = B * N
-        s2d0 = pwc_in = None
         if (self.pwc_prefix + 'netExtractor.netOne.0.s2d') in self.W:
-            # bf16 PWC-Net: RGGB->RGB + resize written straight into the space-to-depth layout of the first stride-2 conv
             s2d0 = self._buf(ws, 'ext0_s2d', F_, Hp // 2, Wp // 2, 12, torch.bfloat16)
             self._run('prep_burst', ops.prep_burst_s2d, burst, enc_in, s2d0, Hp, Wp)
-        else:
-            pwc_in = self._buf(ws, 'pwc_in', F_, Hp, Wp, 4, torch.float32)
-            self._run('prep_burst', ops.prep_burst, burst, enc_in, pwc_in)
-        return self.pwc_burst(ws, pwc_in, B, N, H, W, offsets, s2d0)
+            return s2d0, None
+        pwc_in = self._buf(ws, 'pwc_in', F_, Hp, Wp, 4, torch.float32)
+        self._run('prep_burst', ops.prep_burst, burst, enc_in, pwc_in)
+        return None, pwc_in
 
     # ------------------------------------------------------------------------------------------------
     # DBSR stages
@@ -611,8 +618,22 @@ class DBSREngine:
         offsets = out.get('offsets')
         if offsets is None:
             offsets = torch.empty((B * (N - 1), 2, H, W), dtype=torch.float32, device=self.device)
-        self.prep_and_align(ws, burst, enc_in, offsets)
-        feat = self.encode(ws, enc_in)
+        if self.overlap_alignment and self.timers is None:
+            # PWC-Net (many short launches, most of them on 50-75 of the 148 SMs) and the encoder conv stack (persistent
+            # full-grid launches) are independent until the fusion: run them on two streams so that encoder CTAs fill
+            # the SMs the small alignment kernels leave idle.  Inside a CUDA-graph capture this becomes a fork / join.
+            s2d0, pwc_in = self.prep(ws, burst, enc_in)
+            cur = torch.cuda.current_stream(self.device)
+            if self._side is None:
+                self._side = torch.cuda.Stream(device=self.device)
+            self._side.wait_stream(cur)
+            with torch.cuda.stream(self._side):
+                self.pwc_burst(ws, pwc_in, B, N, H, W, offsets, s2d0)
+            feat = self.encode(ws, enc_in)
+            cur.wait_stream(self._side)
+        else:
+            self.prep_and_align(ws, burst, enc_in, offsets)
+            feat = self.encode(ws, enc_in)
         weights = None
         if return_weights:
             weights = torch.empty((B, N, self.feat_dim, H, W), dtype=torch.float32, device=self.device)

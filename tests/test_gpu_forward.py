@@ -160,6 +160,25 @@ def test_large_crop_256(dev):
     assert err <= 1e-2, err
 
 
+def test_alignment_encoder_overlap_is_bit_identical(dev):
+    """PWC-Net and the encoder run on two streams (fork after the burst preparation, join before the fusion): the result
+    must equal the single-stream order bit for bit, eagerly and under CUDA-graph replay, call after call"""
+    sd = O.make_state_dict(0)
+    net = _net(sd, dev, 'bf16')
+    net.return_fusion_weights = False
+    bursts = [O.make_burst(40 + i, 3, 6, 24, 32).to(dev) for i in range(3)]
+    eng = net.engine(dev)
+    eng.overlap_alignment = False
+    want = [(net(b)[0].clone(), net(b)[1]['offsets'].clone()) for b in bursts]
+    eng.overlap_alignment = True
+    for graph in (False, True):
+        net.use_cuda_graph = graph
+        for rep in range(2):
+            for b, (p_ref, o_ref) in zip(bursts, want):
+                p, aux = net(b)
+                assert torch.equal(p, p_ref) and torch.equal(aux['offsets'], o_ref)
+
+
 def test_module_seams_match_fused_path(dev):
     """encoder -> merging -> decoder called one by one (NCHW dict seams of the reference) == fused engine path"""
     sd = O.make_state_dict(1)
