@@ -167,6 +167,45 @@ def make_burst(seed: int, B: int, N: int, H: int, W: int):
 
 # ----------------------------------------------------------------------------------------------------
 # Elementary ops restated by hand
+def make_realistic_burst(seed: int, B: int, N: int, H: int, W: int, max_shift: float = 24.0, max_rot_deg: float = 1.0):
+    """Data-free restatement of the reference's synthetic burst generator (SURVEY.md 8(d) "realistic" inputs):
+    a low-pass random RGB scene of (8H+48) x (8W+48) pixels; per frame a random translation of up to +-max_shift HR pixels and
+    rotation of up to +-max_rot_deg (train_settings/dbsr/default_synthetic.py:37-41; frame 0 is the untransformed base
+    frame, data/synthetic_burst_generation.py:150-160) resampled bilinearly; centre crop 8H x 8W; x4 box downsample to the
+    2H x 2W RGB image; RGGB mosaic (data/camera_pipeline.py:139-150); shot / read noise with the levels of
+    random_noise_levels / add_noise (camera_pipeline.py:165-182: log-uniform shot in [1e-4, 1.2e-2],
+    log read = 2.18 log shot + 1.2 + N(0, 0.26)); clamp to [0, 1]; 14-bit quantisation.  Returns [B, N, 4, H, W]."""
+    g = torch.Generator().manual_seed(77000 + seed)
+    hr_h, hr_w = 8 * H + 48, 8 * W + 48
+    coarse = torch.rand(B, 3, hr_h // 16 + 2, hr_w // 16 + 2, generator=g)
+    scene = F.interpolate(coarse, size=(hr_h, hr_w), mode='bicubic', align_corners=False).clamp(0.0, 1.0)
+    ys, xs = torch.meshgrid(torch.arange(hr_h, dtype=torch.float32), torch.arange(hr_w, dtype=torch.float32), indexing='ij')
+    cy, cx = (hr_h - 1) / 2.0, (hr_w - 1) / 2.0
+    frames = []
+    for n in range(N):
+        if n == 0:
+            t = torch.zeros(B, 2)
+            th = torch.zeros(B)
+        else:
+            t = (torch.rand(B, 2, generator=g) * 2 - 1) * max_shift
+            th = (torch.rand(B, generator=g) * 2 - 1) * math.radians(max_rot_deg)
+        c, s_ = torch.cos(th).view(B, 1, 1), torch.sin(th).view(B, 1, 1)
+        u = c * (xs - cx) - s_ * (ys - cy) + cx + t[:, 0].view(B, 1, 1)
+        v = s_ * (xs - cx) + c * (ys - cy) + cy + t[:, 1].view(B, 1, 1)
+        moved = bilinear_sample_zeros(scene, u, v)
+        crop = moved[:, :, 24:24 + 8 * H, 24:24 + 8 * W]
+        rgb = F.avg_pool2d(crop, 4)                                    # [B, 3, 2H, 2W]
+        raw = torch.stack([rgb[:, 0, 0::2, 0::2], rgb[:, 1, 0::2, 1::2], rgb[:, 1, 1::2, 0::2], rgb[:, 2, 1::2, 1::2]], 1)
+        frames.append(raw)
+    burst = torch.stack(frames, 1)                                     # [B, N, 4, H, W]
+    log_shot = torch.rand(B, generator=g) * (math.log(1.2e-2) - math.log(1e-4)) + math.log(1e-4)
+    log_read = 2.18 * log_shot + 1.2 + 0.26 * torch.randn(B, generator=g)
+    shot, read = torch.exp(log_shot).view(B, 1, 1, 1, 1), torch.exp(log_read).view(B, 1, 1, 1, 1)
+    burst = burst + torch.randn(burst.shape, generator=g) * torch.sqrt(burst * shot + read)
+    burst = burst.clamp(0.0, 1.0)
+    return (torch.round(burst * 2 ** 14) / 2 ** 14).contiguous()
+
+
 # ----------------------------------------------------------------------------------------------------
 def lrelu(x):
     return torch.where(x > 0, x, 0.1 * x)
