@@ -69,7 +69,7 @@ def test_fp32_path_stress_flows_against_oracle(dev):
 
 
 @pytest.mark.parametrize('pwc_precision', [None, 'fp32'])
-@pytest.mark.parametrize('shape', [(1, 14, 48, 48), (2, 5, 16, 24), (1, 2, 24, 24)])
+@pytest.mark.parametrize('shape', [(1, 14, 48, 48), (2, 5, 16, 24), (1, 2, 24, 24), (1, 3, 30, 46), (1, 18, 16, 16)])
 def test_bf16_path_tolerance(dev, shape, pwc_precision):
     B, N, H, W = shape
     sd = O.make_state_dict(0)
