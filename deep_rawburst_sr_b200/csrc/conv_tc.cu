@@ -94,6 +94,15 @@ __device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* ba
       ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
 }
+// shared -> global tensor store of one box (bulk async-group completion); coordinates are clipped by the tensor map
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, uint32_t src_smem, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(map)), "r"(src_smem), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
 }
@@ -235,6 +244,7 @@ struct ConvTcParams {
   // The predictor weights travel IN the kernel parameters (constant bank): the 96 FMAs per pixel then take their weight
   // operand from the constant cache -- a first version that read them from shared memory added 1024 LDS wavefronts per
   // item to a kernel whose bottleneck is the shared-memory data pipe and was 100 us slower per launch.
+  int tma_store;        // lean epilogue: the staged 32-pixel x GW-channel block of a warp leaves as ONE TMA tensor store
   float* pred; int pred_c;
   float pred_wb[4 * 32 + 4];   // [k][32] weights (zero beyond cout), then [k] biases
 };
@@ -523,7 +533,8 @@ __device__ __forceinline__ void lean_chunk(const uint32_t (&r)[32], uint32_t bia
 template <int GW>
 __device__ __forceinline__ void lean_group(uint32_t taddr, uint32_t bias_s, bool has_bias, int act, uint32_t stg_s, int lane,
                                            __nv_bfloat16* ywarp, long long y_row, long long y_col, bool full, int rows_left,
-                                           int cols_in, bool has_res) {
+                                           int cols_in, bool has_res, const CUtensorMap* tmap_y = nullptr, int sc = 0, int sx = 0,
+                                           int sy = 0, int sn = 0) {
   constexpr int LPP = GW / 8;        // lanes (16-byte slots) per pixel
   constexpr int PPI = 32 / LPP;      // pixels per warp instruction
   uint32_t r0[32], r1[32];
@@ -533,17 +544,32 @@ __device__ __forceinline__ void lean_group(uint32_t taddr, uint32_t bias_s, bool
   const int r_lane = (PPI > 8) ? (sub >> 3) : 0, c_lane = sub & 7;
   __nv_bfloat16* yl = ywarp + r_lane * y_row + c_lane * y_col + chunk * 8;
   const uint32_t row_s = stg_s + (uint32_t)(lane * GW * 2);
-  const uint32_t wswz = (uint32_t)((lane * LPP) >> 3) % LPP;
+  // swizzle = 128-byte line index of the row (ABSOLUTE shared address, as the TMA swizzle modes define it) mod LPP
+  const uint32_t base_sw = stg_s >> 7;
+  const uint32_t wswz = (base_sw + (uint32_t)((lane * LPP) >> 3)) % LPP;
   if (has_res) { cp_async_wait_all(); __syncwarp(); }     // the prefetched residual rows have landed
   tmem_wait_ld();
+  if (tmap_y != nullptr) {       // the previous TMA store of this warp has finished READING the staging rows
+    if (lane == 0) tma_store_wait_read();
+    __syncwarp();
+  }
   if (GW >= 32) lean_chunk<32>(r0, bias_s, has_bias, act, row_s, 0u, wswz, has_res); else lean_chunk<16>(r0, bias_s, has_bias, act, row_s, 0u, wswz, has_res);
   if (GW == 64) lean_chunk<32>(r1, bias_s + 128u, has_bias, act, row_s, 4u, wswz, has_res);
+  if (tmap_y != nullptr) {
+    // The staging rows are exactly the box {GW channels, 8 pixels, 4 rows} in the SWIZZLE_(2*GW)B layout: one elected lane
+    // hands them to the TMA engine, which clips at the image border; the warp does not read them back (ncu / A-B
+    // experiments: the LDS + STG read-back was 22 % of the 32 -> 32 layers and 24 % of the 4 -> 64 layer).
+    fence_async_smem();
+    __syncwarp();
+    if (lane == 0 && rows_left > 0) tma_store_4d(tmap_y, stg_s, sc, sx, sy, sn);
+    return;
+  }
   __syncwarp();
 #pragma unroll
   for (int it = 0; it < LPP; ++it) {
     // staging row ml = it * PPI + sub  ->  tile row (ml >> 3), column (ml & 7)
     const int r_it = (it * PPI) >> 3, c_it = (it * PPI) & 7;
-    const uint32_t rswz = (uint32_t)(it * 4 + ((sub * LPP) >> 3)) % LPP;     // ((ml * LPP) / 8) % LPP
+    const uint32_t rswz = (base_sw + (uint32_t)(it * 4 + ((sub * LPP) >> 3))) % LPP;     // (line index of row ml) % LPP
     const uint4 q = lds128(stg_s + (uint32_t)((it * PPI + sub) * GW * 2) + (((uint32_t)chunk ^ rswz) << 4));
     if (full || (r_lane + r_it < rows_left && c_lane + c_it < cols_in))
       *reinterpret_cast<uint4*>(yl + r_it * y_row + c_it * y_col) = q;
@@ -563,7 +589,7 @@ __device__ __forceinline__ void lean_prefetch_res(uint32_t stg_s, int lane, cons
 #pragma unroll
   for (int it = 0; it < LPP; ++it) {
     const int r_it = (it * PPI) >> 3, c_it = (it * PPI) & 7;
-    const uint32_t rswz = (uint32_t)(it * 4 + ((sub * LPP) >> 3)) % LPP;
+    const uint32_t rswz = ((stg_s >> 7) + (uint32_t)(it * 4 + ((sub * LPP) >> 3))) % LPP;
     const bool ok = r_lane + r_it < rows_left && c_lane + c_it < cols_in;
     const uint32_t dst = stg_s + (uint32_t)((it * PPI + sub) * GW * 2) + (((uint32_t)chunk ^ rswz) << 4);
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(ok ? (const void*)(rl + r_it * r_row + c_it * r_col) : safe),
@@ -574,7 +600,8 @@ __device__ __forceinline__ void lean_prefetch_res(uint32_t stg_s, int lane, cons
 template <int CK, bool RESIDENT>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
-               const __grid_constant__ CUtensorMap tmap_r, const __grid_constant__ CUtensorMap tmap_i, const ConvTcParams p) {
+               const __grid_constant__ CUtensorMap tmap_r, const __grid_constant__ CUtensorMap tmap_i,
+               const __grid_constant__ CUtensorMap tmap_y, const ConvTcParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* smem_a = smem;                                         // [a_slots][a_bytes]
@@ -608,6 +635,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
     tma_prefetch_desc(&tmap_x);
     tma_prefetch_desc(&tmap_w);
     if (p.res_chunks) { tma_prefetch_desc(&tmap_r); tma_prefetch_desc(&tmap_i); }
+    if (p.tma_store) tma_prefetch_desc(&tmap_y);
   }
   if (warp == WARP_MMA) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
   // Programmatic dependent launch: everything above touches only on-chip state and the kernel parameters, so it may run
@@ -843,9 +871,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
           const int rem = NT - g0;
           const int gw = rem >= 64 ? 64 : (rem >= 32 ? 32 : 16);
           if (p.mt == 2 || (gi & 1) == group) {
-            if (gw == 64) lean_group<64>(tbase + (uint32_t)g0, bias_s + (uint32_t)g0 * 4u, has_bias, act, stg_s, lane, ywarp + g0, y_row, y_col, full, rows_left, cols_in, has_res);
-            else if (gw == 32) lean_group<32>(tbase + (uint32_t)g0, bias_s + (uint32_t)g0 * 4u, has_bias, act, stg_s, lane, ywarp + g0, y_row, y_col, full, rows_left, cols_in, has_res);
-            else lean_group<16>(tbase + (uint32_t)g0, bias_s + (uint32_t)g0 * 4u, has_bias, act, stg_s, lane, ywarp + g0, y_row, y_col, full, rows_left, cols_in, has_res);
+            const CUtensorMap* ty_map = p.tma_store ? &tmap_y : nullptr;
+            const int sy = c.y0 + quarter * 4;
+            if (gw == 64) lean_group<64>(tbase + (uint32_t)g0, bias_s + (uint32_t)g0 * 4u, has_bias, act, stg_s, lane, ywarp + g0, y_row, y_col, full, rows_left, cols_in, has_res, ty_map, co0 + g0, tx0, sy, img_t);
+            else if (gw == 32) lean_group<32>(tbase + (uint32_t)g0, bias_s + (uint32_t)g0 * 4u, has_bias, act, stg_s, lane, ywarp + g0, y_row, y_col, full, rows_left, cols_in, has_res, ty_map, co0 + g0, tx0, sy, img_t);
+            else lean_group<16>(tbase + (uint32_t)g0, bias_s + (uint32_t)g0 * 4u, has_bias, act, stg_s, lane, ywarp + g0, y_row, y_col, full, rows_left, cols_in, has_res, ty_map, co0 + g0, tx0, sy, img_t);
           }
           g0 += gw; ++gi;
         }
@@ -965,6 +995,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
     }
   }
 
+  if (p.tma_store && warp < 8 && lane == 0) tma_store_wait_all();     // this warp's tensor stores have been written
   tc_fence_before();
   __syncthreads();
   if (warp == WARP_MMA) {
@@ -1182,7 +1213,7 @@ static dbsr_conv_t centre_tap_form(const dbsr_conv_t* c) {
 
 template <int CK, bool RESIDENT>
 static int launch_tc(const CUtensorMap& mx, const CUtensorMap& mw, const CUtensorMap& mr, const CUtensorMap& mi,
-                     const ConvTcParams& p, int smem, cudaStream_t st) {
+                     const CUtensorMap& my, const ConvTcParams& p, int smem, cudaStream_t st) {
   static int configured_smem = 0;
   if (smem > configured_smem) {
     cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<CK, RESIDENT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
@@ -1208,7 +1239,7 @@ static int launch_tc(const CUtensorMap& mx, const CUtensorMap& mw, const CUtenso
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   lc.attrs = attr; lc.numAttrs = pdl ? 1 : 0;
-  cudaError_t le = cudaLaunchKernelEx(&lc, conv_tc_kernel<CK, RESIDENT>, mx, mw, mr, mi, p);
+  cudaError_t le = cudaLaunchKernelEx(&lc, conv_tc_kernel<CK, RESIDENT>, mx, mw, mr, mi, my, p);
   if (le != cudaSuccess) { set_error("conv2d_tc: launch failed: %s", cudaGetErrorString(le)); return 2; }
   return check_launch("conv2d_tc");
 }
@@ -1354,11 +1385,35 @@ static int conv2d_tc_impl(const dbsr_conv_t* c_in, void* stream, const float* pr
       p.pred_wb[128 + k] = pred_b[k];
     }
   }
+  // TMA tensor store of the lean epilogue: bf16 lean path without epilogue-side residual / pixel shuffle, one box shape
+  // per launch (every channel group of the N tile has the same width), staging rows on 128-byte lines
+  alignas(64) CUtensorMap my;
+  memset(&my, 0, sizeof(my));
+  p.tma_store = 0;
+  {
+    const int gw = (cfg.n_tile % 64 == 0) ? 64 : (cfg.n_tile == 32 ? 32 : (cfg.n_tile == 16 ? 16 : 0));
+    const size_t stg_off = (size_t)cfg.a_slots * cfg.a_bytes + (size_t)cfg.b_stages * cfg.b_bytes;
+    static const bool enabled = getenv("DBSR_TC_NO_TMA_STORE") == nullptr;
+    if (enabled && gw && pred == nullptr && !cfg.flat && p.bias_smem && cfg.vec_ok && c->y.dtype == DBSR_BF16 && p.res == nullptr &&
+        r == 1 && stg_off % 128 == 0) {
+      cuuint64_t dims[4] = {(cuuint64_t)c->y.c, (cuuint64_t)c->y.w, (cuuint64_t)c->y.h, (cuuint64_t)c->y.n};
+      cuuint64_t strides[3] = {(cuuint64_t)c->y.c_pitch * 2, (cuuint64_t)c->y.w * c->y.c_pitch * 2,
+                               (cuuint64_t)c->y.h * c->y.w * c->y.c_pitch * 2};
+      cuuint32_t box[4] = {(cuuint32_t)gw, (cuuint32_t)TILE_W, 4u, 1u};
+      cuuint32_t es[4] = {1, 1, 1, 1};
+      const CUtensorMapSwizzle sw = gw == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (gw == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+      void* base = reinterpret_cast<__nv_bfloat16*>(c->y.data) + c->y.c_off;
+      CUresult rc = encode(&my, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, base, dims, strides, box, es,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      DBSR_REQUIRE(rc == CUDA_SUCCESS, "conv2d_tc: cuTensorMapEncodeTiled(y) failed with %d", (int)rc);
+      p.tma_store = 1;
+    }
+  }
   cudaStream_t st = (cudaStream_t)stream;
-  if (cfg.ck == 64) return cfg.b_resident ? launch_tc<64, true>(mx, mw, mr, mi, p, cfg.smem_bytes, st)
-                                          : launch_tc<64, false>(mx, mw, mr, mi, p, cfg.smem_bytes, st);
-  return cfg.b_resident ? launch_tc<32, true>(mx, mw, mr, mi, p, cfg.smem_bytes, st)
-                        : launch_tc<32, false>(mx, mw, mr, mi, p, cfg.smem_bytes, st);
+  if (cfg.ck == 64) return cfg.b_resident ? launch_tc<64, true>(mx, mw, mr, mi, my, p, cfg.smem_bytes, st)
+                                          : launch_tc<64, false>(mx, mw, mr, mi, my, p, cfg.smem_bytes, st);
+  return cfg.b_resident ? launch_tc<32, true>(mx, mw, mr, mi, my, p, cfg.smem_bytes, st)
+                        : launch_tc<32, false>(mx, mw, mr, mi, my, p, cfg.smem_bytes, st);
 }
 
 extern "C" int dbsr_conv2d_tc(const dbsr_conv_t* c, void* stream) {
