@@ -100,6 +100,11 @@ __device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, uint32_t sr
                ::"l"(reinterpret_cast<uint64_t>(map)), "r"(src_smem), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
   asm volatile("cp.async.bulk.commit_group;" ::: "memory");
 }
+__device__ __forceinline__ void tma_store_5d(const CUtensorMap* map, uint32_t src_smem, int c0, int c1, int c2, int c3, int c4) {
+  asm volatile("cp.async.bulk.tensor.5d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(map)), "r"(src_smem), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4) : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
 __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -534,7 +539,7 @@ template <int GW>
 __device__ __forceinline__ void lean_group(uint32_t taddr, uint32_t bias_s, bool has_bias, int act, uint32_t stg_s, int lane,
                                            __nv_bfloat16* ywarp, long long y_row, long long y_col, bool full, int rows_left,
                                            int cols_in, bool has_res, const CUtensorMap* tmap_y = nullptr, int sc = 0, int sx = 0,
-                                           int sy = 0, int sn = 0) {
+                                           int sy = 0, int sn = 0, int si = -1) {
   constexpr int LPP = GW / 8;        // lanes (16-byte slots) per pixel
   constexpr int PPI = 32 / LPP;      // pixels per warp instruction
   uint32_t r0[32], r1[32];
@@ -561,7 +566,10 @@ __device__ __forceinline__ void lean_group(uint32_t taddr, uint32_t bias_s, bool
     // experiments: the LDS + STG read-back was 22 % of the 32 -> 32 layers and 24 % of the 4 -> 64 layer).
     fence_async_smem();
     __syncwarp();
-    if (lane == 0 && rows_left > 0) tma_store_4d(tmap_y, stg_s, sc, sx, sy, sn);
+    if (lane == 0 && rows_left > 0) {
+      if (si < 0) tma_store_4d(tmap_y, stg_s, sc, sx, sy, sn);
+      else tma_store_5d(tmap_y, stg_s, sc, sx, si, sy, sn);       // pixel shuffle: {(j, c), x, i, y, n}
+    }
     return;
   }
   __syncwarp();
@@ -873,9 +881,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
           if (p.mt == 2 || (gi & 1) == group) {
             const CUtensorMap* ty_map = p.tma_store ? &tmap_y : nullptr;
             const int sy = c.y0 + quarter * 4;
-            if (gw == 64) lean_group<64>(tbase + (uint32_t)g0, bias_s + (uint32_t)g0 * 4u, has_bias, act, stg_s, lane, ywarp + g0, y_row, y_col, full, rows_left, cols_in, has_res, ty_map, co0 + g0, tx0, sy, img_t);
-            else if (gw == 32) lean_group<32>(tbase + (uint32_t)g0, bias_s + (uint32_t)g0 * 4u, has_bias, act, stg_s, lane, ywarp + g0, y_row, y_col, full, rows_left, cols_in, has_res, ty_map, co0 + g0, tx0, sy, img_t);
-            else lean_group<16>(tbase + (uint32_t)g0, bias_s + (uint32_t)g0 * 4u, has_bias, act, stg_s, lane, ywarp + g0, y_row, y_col, full, rows_left, cols_in, has_res, ty_map, co0 + g0, tx0, sy, img_t);
+            // pixel shuffle: packed channel co' = i*256 + j*32 + c -> store coordinates ((j, c) = co' % 256, i = co' / 256)
+            const int sc = shuffle ? (co0 + g0) % (p.shuffle_r * 32) : co0 + g0;
+            const int si = shuffle ? (co0 + g0) / (p.shuffle_r * 32) : -1;
+            if (gw == 64) lean_group<64>(tbase + (uint32_t)g0, bias_s + (uint32_t)g0 * 4u, has_bias, act, stg_s, lane, ywarp + g0, y_row, y_col, full, rows_left, cols_in, has_res, ty_map, sc, tx0, sy, img_t, si);
+            else if (gw == 32) lean_group<32>(tbase + (uint32_t)g0, bias_s + (uint32_t)g0 * 4u, has_bias, act, stg_s, lane, ywarp + g0, y_row, y_col, full, rows_left, cols_in, has_res, ty_map, sc, tx0, sy, img_t, si);
+            else lean_group<16>(tbase + (uint32_t)g0, bias_s + (uint32_t)g0 * 4u, has_bias, act, stg_s, lane, ywarp + g0, y_row, y_col, full, rows_left, cols_in, has_res, ty_map, sc, tx0, sy, img_t, si);
           }
           g0 += gw; ++gi;
         }
@@ -1394,18 +1405,31 @@ static int conv2d_tc_impl(const dbsr_conv_t* c_in, void* stream, const float* pr
     const int gw = (cfg.n_tile % 64 == 0) ? 64 : (cfg.n_tile == 32 ? 32 : (cfg.n_tile == 16 ? 16 : 0));
     const size_t stg_off = (size_t)cfg.a_slots * cfg.a_bytes + (size_t)cfg.b_stages * cfg.b_bytes;
     static const bool enabled = getenv("DBSR_TC_NO_TMA_STORE") == nullptr;
-    if (enabled && gw && pred == nullptr && !cfg.flat && p.bias_smem && cfg.vec_ok && c->y.dtype == DBSR_BF16 && p.res == nullptr &&
-        r == 1 && stg_off % 128 == 0) {
+    const bool ok = enabled && gw && pred == nullptr && !cfg.flat && p.bias_smem && cfg.vec_ok && c->y.dtype == DBSR_BF16 &&
+                    p.res == nullptr && stg_off % 128 == 0;
+    const CUtensorMapSwizzle sw = gw == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (gw == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+    void* base = reinterpret_cast<__nv_bfloat16*>(c->y.data) + c->y.c_off;
+    if (ok && r == 1) {
       cuuint64_t dims[4] = {(cuuint64_t)c->y.c, (cuuint64_t)c->y.w, (cuuint64_t)c->y.h, (cuuint64_t)c->y.n};
       cuuint64_t strides[3] = {(cuuint64_t)c->y.c_pitch * 2, (cuuint64_t)c->y.w * c->y.c_pitch * 2,
                                (cuuint64_t)c->y.h * c->y.w * c->y.c_pitch * 2};
       cuuint32_t box[4] = {(cuuint32_t)gw, (cuuint32_t)TILE_W, 4u, 1u};
       cuuint32_t es[4] = {1, 1, 1, 1};
-      const CUtensorMapSwizzle sw = gw == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (gw == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
-      void* base = reinterpret_cast<__nv_bfloat16*>(c->y.data) + c->y.c_off;
       CUresult rc = encode(&my, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, base, dims, strides, box, es,
                            CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
       DBSR_REQUIRE(rc == CUDA_SUCCESS, "conv2d_tc: cuTensorMapEncodeTiled(y) failed with %d", (int)rc);
+      p.tma_store = 1;
+    } else if (ok && r == 8 && gw == 64) {
+      // pixel shuffle: y is the dense [n, 8H, 8W, 32] map; element (n, 8y + i, 8x + j, c) is addressed as the 5-D tensor
+      // {(j, c): 256, x: W, i: 8, y: H, n}; a warp's 32 LR pixels x 64 packed channels are the box {64, 8, 1, 4, 1}
+      const cuuint64_t W = (cuuint64_t)c->x.w, H = (cuuint64_t)c->x.h;
+      cuuint64_t dims[5] = {256, W, 8, H, (cuuint64_t)c->y.n};
+      cuuint64_t strides[4] = {512, 8 * W * 64, 8 * 8 * W * 64, 8 * H * 8 * W * 64};
+      cuuint32_t box[5] = {64u, (cuuint32_t)TILE_W, 1u, 4u, 1u};
+      cuuint32_t es[5] = {1, 1, 1, 1, 1};
+      CUresult rc = encode(&my, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, base, dims, strides, box, es,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      DBSR_REQUIRE(rc == CUDA_SUCCESS, "conv2d_tc: cuTensorMapEncodeTiled(y, pixel shuffle) failed with %d", (int)rc);
       p.tma_store = 1;
     }
   }
