@@ -867,6 +867,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
         const uint32_t tbase = tq + (uint32_t)acc * acc_cols;
         const uint32_t bias_s = bias_s0 + (uint32_t)co0 * 4u;
         if (has_res && my_group) {
+          if (p.tma_store) {      // the previous item's tensor store has finished reading the rows the prefetch overwrites
+            if (lane == 0) tma_store_wait_read();
+            __syncwarp();
+          }
           const __nv_bfloat16* rwarp = rbase + ((long long)(img_t * p.yH + c.y0) * p.yW + tx0) * p.r_pitch + co0;
           if (NT == 64) lean_prefetch_res<64>(stg_s, lane, rwarp, r_row, r_col, rows_left, cols_in, p.res);
           else if (NT == 32) lean_prefetch_res<32>(stg_s, lane, rwarp, r_row, r_col, rows_left, cols_in, p.res);
@@ -1405,8 +1409,9 @@ static int conv2d_tc_impl(const dbsr_conv_t* c_in, void* stream, const float* pr
     const int gw = (cfg.n_tile % 64 == 0) ? 64 : (cfg.n_tile == 32 ? 32 : (cfg.n_tile == 16 ? 16 : 0));
     const size_t stg_off = (size_t)cfg.a_slots * cfg.a_bytes + (size_t)cfg.b_stages * cfg.b_bytes;
     static const bool enabled = getenv("DBSR_TC_NO_TMA_STORE") == nullptr;
+    // (an epilogue-side residual -- N tile 64 -- is prefetched into the same staging rows and is compatible)
     const bool ok = enabled && gw && pred == nullptr && !cfg.flat && p.bias_smem && cfg.vec_ok && c->y.dtype == DBSR_BF16 &&
-                    p.res == nullptr && stg_off % 128 == 0;
+                    (p.res == nullptr || cfg.n_tile == 64 || cfg.n_tile == 32 || cfg.n_tile == 16) && stg_off % 128 == 0;
     const CUtensorMapSwizzle sw = gw == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (gw == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
     void* base = reinterpret_cast<__nv_bfloat16*>(c->y.data) + c->y.c_off;
     if (ok && r == 1) {
