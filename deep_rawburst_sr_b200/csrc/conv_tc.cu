@@ -1226,6 +1226,7 @@ static dbsr_conv_t centre_tap_form(const dbsr_conv_t* c) {
   return cc;
 }
 
+static int g_grid_limit = 0;     // dbsr_conv2d_tc_set_grid_limit: CTAs per launch (0 = one per SM)
 template <int CK, bool RESIDENT>
 static int launch_tc(const CUtensorMap& mx, const CUtensorMap& mw, const CUtensorMap& mr, const CUtensorMap& mi,
                      const CUtensorMap& my, const ConvTcParams& p, int smem, cudaStream_t st) {
@@ -1245,6 +1246,7 @@ static int launch_tc(const CUtensorMap& mx, const CUtensorMap& mw, const CUtenso
     cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
   }
   int grid = (int)(p.total_items < num_sms ? p.total_items : num_sms);
+  if (g_grid_limit > 0 && grid > g_grid_limit) grid = g_grid_limit;
   // programmatic dependent launch: CTAs may be scheduled (barrier init, tensor-map prefetch, TMEM allocation) as soon as
   // the SMs of the preceding kernel drain; the kernel calls griddepcontrol.wait before its first global access
   static const bool pdl = getenv("DBSR_TC_NO_PDL") == nullptr;     // A/B switch: DBSR_TC_NO_PDL=1 launches normally
@@ -1453,4 +1455,9 @@ extern "C" int dbsr_conv2d_tc_predictor(const dbsr_conv_t* c, const float* pred_
                                         float* pred, void* stream) {
   DBSR_REQUIRE(pred != nullptr, "conv2d_tc_predictor: null output");
   return conv2d_tc_impl(c, stream, pred_w, pred_b, pred_c, pred);
+}
+
+extern "C" int dbsr_conv2d_tc_set_grid_limit(int32_t ctas) {
+  g_grid_limit = ctas > 0 ? ctas : 0;
+  return 0;
 }

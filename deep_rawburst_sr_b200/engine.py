@@ -164,6 +164,10 @@ class DBSREngine:
         self._graphs: Dict[tuple, tuple] = {}
         self._side = None                 # second stream of the alignment / encoder overlap
         self.overlap_alignment = True
+        # persistent-grid size of the encoder convs while the alignment stream is active: leaving ~1/6 of the SMs to the
+        # short PWC-Net launches is worth another 1-1.5 % per step on B200 (148 SMs -> 124; measured 9.39 -> 9.25 ms)
+        sms = torch.cuda.get_device_properties(self.device).multi_processor_count
+        self.encoder_grid_limit = sms - 24 if sms >= 96 else 0
         self.launches = 0
         self.layer_events = None   # when a dict (and timers is on): conv layer key -> [(events, flops, family, shape)]
         self.timers = None   # when a dict: family -> list of (start, end) CUDA events on the launching stream
@@ -629,7 +633,11 @@ class DBSREngine:
             self._side.wait_stream(cur)
             with torch.cuda.stream(self._side):
                 self.pwc_burst(ws, pwc_in, B, N, H, W, offsets, s2d0)
-            feat = self.encode(ws, enc_in)
+            ops.conv2d_tc_set_grid_limit(self.encoder_grid_limit)
+            try:
+                feat = self.encode(ws, enc_in)
+            finally:
+                ops.conv2d_tc_set_grid_limit(0)
             cur.wait_stream(self._side)
         else:
             self.prep_and_align(ws, burst, enc_in, offsets)

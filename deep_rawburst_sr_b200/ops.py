@@ -117,6 +117,11 @@ def conv2d_tc_predictor(x: Act, w: torch.Tensor, bias: Optional[torch.Tensor], y
     return pred
 
 
+def conv2d_tc_set_grid_limit(ctas: int) -> None:
+    """persistent-grid size of the following tensor-core conv launches (0 = one CTA per SM)"""
+    _lib.check(_lib.load_library().dbsr_conv2d_tc_set_grid_limit(int(ctas)), 'dbsr_conv2d_tc_set_grid_limit')
+
+
 def conv2d_tc_supported(x: Act, w: torch.Tensor, bias, y: Act, ksize: int, stride: int = 1, dilation: int = 1,
                         residual: Optional[Act] = None, shuffle_r: int = 0) -> bool:
     d = ConvDesc(x.view(), y.view(), residual.view() if residual is not None else _NULL_VIEW, w.data_ptr(),

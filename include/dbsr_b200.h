@@ -107,6 +107,10 @@ int dbsr_conv2d_direct(const dbsr_conv_t* p, void* stream);
  *   (dbsr_conv2d_tc_supported) and never falls back silently inside a call.                              */
 int dbsr_conv2d_tc(const dbsr_conv_t* p, void* stream);
 int dbsr_conv2d_tc_supported(const dbsr_conv_t* p);
+/* Persistent-grid size of the following dbsr_conv2d_tc launches of this process (0 = one CTA per SM, the default).  The engine
+ * lowers it for the encoder conv stack while PWC-Net runs on a second stream, so that the alignment kernels always find
+ * free SMs; launch-time state only (a captured CUDA graph keeps the grid it was captured with).  Not thread safe.        */
+int dbsr_conv2d_tc_set_grid_limit(int32_t ctas);
 /* The same convolution with the decoder's 1x1 predictor + ReLU (models/dbsr/decoders.py:52,61: conv_block(post_conv_dim, 3,
  * 1, activation) after the last post-res block) folded into the epilogue: every epilogue thread owns all (<= 32) output
  * channels of its pixel, so  pred[n, k, y, x] = relu(pred_b[k] + sum_c pred_w[k][c] * act(conv(x) + bias (+ residual))[c])
