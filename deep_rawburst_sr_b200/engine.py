@@ -517,8 +517,14 @@ class DBSREngine:
         self._conv('encoder.out_layer.0', cur, feat, ACT_RELU)
         return feat
 
+    def project(self, ws: dict, feat: Act) -> Act:
+        """q = W_p . feat (merging.py:75 without bias / ReLU, which follow the warp in `warp_proj`): depends on the
+        embeddings only, so the forward runs it before joining the alignment stream"""
+        q = self._buf(ws, 'proj_q', feat.n, feat.h, feat.w, self.proj_dim, self.act_dtype)
+        return self._conv('merging.feat_project_layer.0', feat, q, ACT_NONE, no_bias=True)
+
     def merge(self, ws: dict, feat: Act, offsets: torch.Tensor, B: int, N: int,
-              weights_out: Optional[torch.Tensor] = None, aligned: bool = False) -> Act:
+              weights_out: Optional[torch.Tensor] = None, aligned: bool = False, projected: bool = False) -> Act:
         """WeightedSum.forward (reference models/dbsr/merging.py:61-127) with the warp of encoders.py:80 folded in.
         `feat` [B*N, H, W, C]: the frame embeddings -- unwarped (aligned=False: the kernels gather through `offsets`
         on the fly, the warped 512-channel tensor is never materialised) or already aligned (aligned=True, the
@@ -529,7 +535,8 @@ class DBSREngine:
         gather = None if aligned else offsets
         # 1x1 projection commutes with the bilinear warp: project first (tensor cores), warp 64 channels instead of 512
         q = self._buf(ws, 'proj_q', F_, H, W, pd, dt)
-        self._conv('merging.feat_project_layer.0', feat, q, ACT_NONE, no_bias=True)
+        if not projected:
+            self.project(ws, feat)
         wp_in = self._buf(ws, 'wp_in', F_, H, W, 2 * pd + od, dt)
         self._run('warp_proj', ops.warp_proj, q, self.W['merging.feat_project_layer.0'].bias, wp_in, N, gather)
         offm = self._buf(ws, 'offm', F_, H, W, 8, dt)
@@ -636,16 +643,19 @@ class DBSREngine:
             ops.conv2d_tc_set_grid_limit(self.encoder_grid_limit)
             try:
                 feat = self.encode(ws, enc_in)
+                self.project(ws, feat)           # needs the embeddings only: before the join
             finally:
                 ops.conv2d_tc_set_grid_limit(0)
             cur.wait_stream(self._side)
+            projected = True
         else:
             self.prep_and_align(ws, burst, enc_in, offsets)
             feat = self.encode(ws, enc_in)
+            projected = False
         weights = None
         if return_weights:
             weights = torch.empty((B, N, self.feat_dim, H, W), dtype=torch.float32, device=self.device)
-        fused = self.merge(ws, feat, offsets, B, N, weights, aligned=False)
+        fused = self.merge(ws, feat, offsets, B, N, weights, aligned=False, projected=projected)
         pred = out.get('pred')
         if pred is None:
             pred = torch.empty((B, 3, H * self.up_r, W * self.up_r), dtype=torch.float32, device=self.device)
