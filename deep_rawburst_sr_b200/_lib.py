@@ -50,7 +50,8 @@ PROTOTYPES = {
     'dbsr_conv2d_tc': (_I, [_PC, _VP]),
     'dbsr_conv2d_tc_supported': (_I, [_PC]),
     'dbsr_conv2d_tc_set_grid_limit': (_I, [_I]),
-    'dbsr_conv2d_tc_predictor': (_I, [_PC, _VP, _VP, _I, _VP, _VP]),
+    'dbsr_conv2d_tc_predictor': (_I, [_PC, _VP, _VP, _I, _VP, _I, _VP]),
+    'dbsr_quantize_q14': (_I, [_VP, _VP, ctypes.c_int64, _VP]),
     'dbsr_conv2d_tc_geometry': (_I, [_I, _I, ctypes.POINTER(_I), ctypes.POINTER(_I), ctypes.POINTER(_I),
                                      ctypes.POINTER(_I)]),
     'dbsr_space_to_depth2': (_I, [_PV, _PV, _VP]),

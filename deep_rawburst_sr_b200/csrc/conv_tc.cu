@@ -250,7 +250,8 @@ struct ConvTcParams {
   // operand from the constant cache -- a first version that read them from shared memory added 1024 LDS wavefronts per
   // item to a kernel whose bottleneck is the shared-memory data pipe and was 100 us slower per launch.
   int tma_store;        // lean epilogue: the staged 32-pixel x GW-channel block of a warp leaves as ONE TMA tensor store
-  float* pred; int pred_c;
+  void* pred; int pred_c;
+  int pred_q14;         // 1: pred is int16 NCHW, value = (int16)(min(relu(.), 1) * 2^14)  (evaluation/*/compute_score.py:110)
   float pred_wb[4 * 32 + 4];   // [k][32] weights (zero beyond cout), then [k] biases
 };
 
@@ -925,7 +926,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
               v[j + 2] = apply_act(__uint_as_float(r[j + 2]) + b4.z, p.act); v[j + 3] = apply_act(__uint_as_float(r[j + 3]) + b4.w, p.act);
             }
             const long long plane = (long long)p.H * p.W;
-            float* dst = p.pred + img * p.pred_c * plane + (long long)y * p.W + x;
+            const long long o = img * p.pred_c * plane + (long long)y * p.W + x;
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
               if (k < p.pred_c) {
@@ -935,7 +936,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
                   s0 = fmaf(v[j], p.pred_wb[k * 32 + j], s0);
                   s1 = fmaf(v[j + 1], p.pred_wb[k * 32 + j + 1], s1);
                 }
-                dst[k * plane] = fmaxf(s0 + s1, 0.0f);
+                const float out = fmaxf(s0 + s1, 0.0f);
+                if (p.pred_q14) reinterpret_cast<short*>(p.pred)[o + k * plane] = (short)(fminf(out, 1.0f) * 16384.0f);
+                else reinterpret_cast<float*>(p.pred)[o + k * plane] = out;
               }
             }
           }
@@ -1282,7 +1285,7 @@ extern "C" int dbsr_conv2d_tc_supported(const dbsr_conv_t* c) {
 }
 
 static int conv2d_tc_impl(const dbsr_conv_t* c_in, void* stream, const float* pred_w, const float* pred_b, int pred_c,
-                          float* pred) {
+                          void* pred, int pred_q14) {
   TcConfig cfg;
   DBSR_REQUIRE(c_in != nullptr, "conv2d_tc: null descriptor");
   const dbsr_conv_t cc = centre_tap_form(c_in);
@@ -1390,7 +1393,7 @@ static int conv2d_tc_impl(const dbsr_conv_t* c_in, void* stream, const float* pr
   p.r_tx_bytes = TILE_H * TILE_W * cfg.mt * cfg.ck * 2;
   if (cfg.res_chunks > 0) p.res = nullptr;   // accumulated by the MMAs, nothing left for the epilogue
   p.bias = c->bias; p.act = c->act; p.shuffle_r = r;
-  p.pred = pred; p.pred_c = pred_c;
+  p.pred = pred; p.pred_c = pred_c; p.pred_q14 = pred_q14 ? 1 : 0;
   memset(p.pred_wb, 0, sizeof(p.pred_wb));
   if (pred != nullptr) {
     DBSR_REQUIRE(pred_w && pred_b && pred_c >= 1 && pred_c <= 4 && cfg.n_tile == 32 && cfg.cout_pad == 32 && !cfg.flat &&
@@ -1448,13 +1451,13 @@ static int conv2d_tc_impl(const dbsr_conv_t* c_in, void* stream, const float* pr
 }
 
 extern "C" int dbsr_conv2d_tc(const dbsr_conv_t* c, void* stream) {
-  return conv2d_tc_impl(c, stream, nullptr, nullptr, 0, nullptr);
+  return conv2d_tc_impl(c, stream, nullptr, nullptr, 0, nullptr, 0);
 }
 
 extern "C" int dbsr_conv2d_tc_predictor(const dbsr_conv_t* c, const float* pred_w, const float* pred_b, int32_t pred_c,
-                                        float* pred, void* stream) {
+                                        void* pred, int32_t pred_q14, void* stream) {
   DBSR_REQUIRE(pred != nullptr, "conv2d_tc_predictor: null output");
-  return conv2d_tc_impl(c, stream, pred_w, pred_b, pred_c, pred);
+  return conv2d_tc_impl(c, stream, pred_w, pred_b, pred_c, pred, pred_q14);
 }
 
 extern "C" int dbsr_conv2d_tc_set_grid_limit(int32_t ctas) {

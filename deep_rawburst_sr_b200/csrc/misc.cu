@@ -586,6 +586,21 @@ extern "C" int dbsr_prep_burst(const float* burst, int32_t frames, int32_t H, in
   return check_launch("prep_burst");
 }
 
+// evaluation/burstsr/compute_score.py:110-111: (pred.clamp(0, 1) * 2 ** 14).short()  (float -> int16 truncates toward zero)
+__global__ void quantize_q14_kernel(const float* __restrict__ src, short* __restrict__ dst, long long count) {
+  griddep_wait();
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (long long)gridDim.x * blockDim.x)
+    dst[i] = (short)(fminf(fmaxf(__ldg(src + i), 0.0f), 1.0f) * 16384.0f);
+}
+
+extern "C" int dbsr_quantize_q14(const float* src, int16_t* dst, int64_t count, void* stream) {
+  DBSR_REQUIRE(src && dst && count >= 0, "quantize_q14: bad arguments");
+  if (count == 0) return 0;
+  launch_pdl(quantize_q14_kernel, dim3(grid_for(count, 256)), dim3(256), 0, (cudaStream_t)stream, src, reinterpret_cast<short*>(dst),
+             (long long)count);
+  return check_launch("quantize_q14");
+}
+
 extern "C" int dbsr_prep_burst_s2d(const float* burst, int32_t frames, int32_t H, int32_t W, int32_t Hp, int32_t Wp,
                                    const dbsr_nhwc_t* enc_in, const dbsr_nhwc_t* pwc_s2d, void* stream) {
   DBSR_REQUIRE(burst && view_ok(enc_in) && view_ok(pwc_s2d), "prep_burst_s2d: bad arguments");

@@ -600,6 +600,13 @@ class DBSREngine:
                 return pred
             self._resblock(key, cur, ht, nxt)
             cur, nxt = nxt, cur
+        if pred.dtype == torch.int16:       # unfused path (fp32 precision): float prediction, then the 14-bit quantisation
+            pf = ws.get('pred_f32')
+            if pf is None or pf.shape != pred.shape:
+                pf = ws['pred_f32'] = torch.empty(pred.shape, dtype=torch.float32, device=self.device)
+            self._run('predictor', ops.predictor, cur, self.pred_w, self.pred_b, pf)
+            self._run('predictor', ops.quantize_q14, pf, pred)
+            return pred
         self._run('predictor', ops.predictor, cur, self.pred_w, self.pred_b, pred)
         return pred
 
@@ -612,7 +619,7 @@ class DBSREngine:
     # whole forward
     # ------------------------------------------------------------------------------------------------
     @torch.no_grad()
-    def forward(self, burst: torch.Tensor, return_weights: bool = False, out: Optional[dict] = None):
+    def forward(self, burst: torch.Tensor, return_weights: bool = False, out: Optional[dict] = None, quantize: bool = False):
         """DBSRNet.forward: burst [B, N, 4, H, W] fp32 CUDA -> pred [B, 3, 8H, 8W], offsets [B, N-1, 2, H, W],
         fusion_weights [B, N, C, H, W] (only when return_weights)."""
         assert burst.dim() == 5 and burst.shape[2] == 4, 'burst must be [B, N, 4, H, W]'
@@ -658,7 +665,9 @@ class DBSREngine:
         fused = self.merge(ws, feat, offsets, B, N, weights, aligned=False, projected=projected)
         pred = out.get('pred')
         if pred is None:
-            pred = torch.empty((B, 3, H * self.up_r, W * self.up_r), dtype=torch.float32, device=self.device)
+            # quantize: int16 = (pred.clamp(0, 1) * 2^14).short(), what the reference's evaluation / result writers store
+            pred = torch.empty((B, 3, H * self.up_r, W * self.up_r), dtype=torch.int16 if quantize else torch.float32,
+                               device=self.device)
         self.decode(ws, fused, pred)
         return pred, offsets.view(B, N - 1, 2, H, W), weights
 
@@ -666,12 +675,12 @@ class DBSREngine:
     # CUDA-graph replay of the whole forward (launch-bound at small batch: ~400 launches per forward)
     # ------------------------------------------------------------------------------------------------
     @torch.no_grad()
-    def forward_graphed(self, burst: torch.Tensor, return_weights: bool = False):
+    def forward_graphed(self, burst: torch.Tensor, return_weights: bool = False, quantize: bool = False):
         """Same as forward(), but the launch sequence is captured once per input shape into a CUDA graph and replayed.
         The returned tensors are the graph's static outputs: they are overwritten by the next call of the same shape."""
         ops.require_device(burst)
         burst = burst.contiguous().float()
-        key = (tuple(burst.shape), bool(return_weights))
+        key = (tuple(burst.shape), bool(return_weights), bool(quantize))
         entry = self._graphs.get(key)
         if entry is None:
             assert self.timers is None, 'per-kernel timers cannot be recorded inside a graph capture'
@@ -680,12 +689,12 @@ class DBSREngine:
             side = torch.cuda.Stream(device=self.device)
             side.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(side):          # warm-up outside capture: workspaces, smem attributes, tensor maps
-                self.forward(static_in, return_weights)
+                self.forward(static_in, return_weights, quantize=quantize)
             torch.cuda.current_stream().wait_stream(side)
             launches0 = self.launches
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph):
-                outs = self.forward(static_in, return_weights)
+                outs = self.forward(static_in, return_weights, quantize=quantize)
             entry = (graph, static_in, outs, self.launches - launches0)
             self._graphs[key] = entry
         graph, static_in, outs, n_launch = entry

@@ -33,6 +33,8 @@ class DBSRNet(nn.Module):
         self.logits_fp32 = False
         self.pwc_precision = None      # None: follow `precision`; 'fp32' keeps PWC-Net (flow) on the exact CUDA-core path
         self.return_fusion_weights = False
+        self.output_int16 = False      # True: pred is int16 = (pred.clamp(0, 1) * 2 ** 14).short(), the 14-bit form the reference's
+                                       # evaluation and result writers store (compute_score.py:110-111); halves D2H / gather bytes
         self.use_cuda_graph = False    # True: capture the launch sequence per input shape and replay it (outputs are
                                        # static buffers, overwritten by the next call with the same shape)
         self._engine = None
@@ -76,7 +78,7 @@ class DBSRNet(nn.Module):
         ops.require_device(im)
         eng = self.engine(im.device)
         run = eng.forward_graphed if (self.use_cuda_graph and eng.timers is None) else eng.forward
-        pred, offsets, weights = run(im, return_weights=self.return_fusion_weights)
+        pred, offsets, weights = run(im, return_weights=self.return_fusion_weights, quantize=self.output_int16)
         return pred, {'offsets': offsets, 'fusion_weights': weights}
 
 

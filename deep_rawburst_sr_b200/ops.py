@@ -97,8 +97,9 @@ def conv2d(x: Act, w: torch.Tensor, bias: Optional[torch.Tensor], y: Act, ksize:
 
 def conv2d_tc_predictor(x: Act, w: torch.Tensor, bias: Optional[torch.Tensor], y: Act, ksize: int, act: int,
                         residual: Optional[Act], pred_w, pred_b, pred: torch.Tensor) -> torch.Tensor:
-    """tcgen05 conv whose epilogue applies the 1x1 predictor + ReLU and writes `pred` [n, k, h, w] fp32 directly (the conv
-    output map `y` is not written; it only describes the geometry).  pred_w [k][Cout] / pred_b [k]: HOST values (CPU
+    """tcgen05 conv whose epilogue applies the 1x1 predictor + ReLU and writes `pred` [n, k, h, w] directly (the conv output
+    map `y` is not written; it only describes the geometry): fp32, or -- when `pred` is an int16 tensor -- the reference's
+    14-bit quantisation (min(value, 1) * 2^14, truncated).  pred_w [k][Cout] / pred_b [k]: HOST values (CPU
     tensors, lists or ctypes float arrays) -- they are copied into the kernel parameters."""
     if not isinstance(pred_w, ctypes.Array):
         pw = torch.as_tensor(pred_w, dtype=torch.float32).cpu().reshape(-1, y.c)
@@ -108,13 +109,23 @@ def conv2d_tc_predictor(x: Act, w: torch.Tensor, bias: Optional[torch.Tensor], y
         pred_b = (ctypes.c_float * pb.numel())(*pb.tolist())
     k = len(pred_b)
     assert len(pred_w) == k * y.c
-    assert pred.dtype == torch.float32 and pred.is_contiguous() and tuple(pred.shape) == (x.n, k, x.h, x.w)
+    assert pred.dtype in (torch.float32, torch.int16) and pred.is_contiguous() and tuple(pred.shape) == (x.n, k, x.h, x.w)
     d = ConvDesc(x.view(), y.view(), residual.view() if residual is not None else _NULL_VIEW, w.data_ptr(),
                  _ptr(bias), ksize, 1, 1, act, 0)
     _lib.check(_lib.load_library().dbsr_conv2d_tc_predictor(ctypes.byref(d), ctypes.cast(pred_w, ctypes.c_void_p),
                                                             ctypes.cast(pred_b, ctypes.c_void_p), k, pred.data_ptr(),
-                                                            _stream()), 'dbsr_conv2d_tc_predictor')
+                                                            1 if pred.dtype == torch.int16 else 0, _stream()),
+               'dbsr_conv2d_tc_predictor')
     return pred
+
+
+def quantize_q14(src: torch.Tensor, dst: torch.Tensor) -> torch.Tensor:
+    """dst = (src.clamp(0, 1) * 2 ** 14).short()  -- the reference's 14-bit output quantisation (compute_score.py:110-111)"""
+    require_device(src)
+    assert src.dtype == torch.float32 and dst.dtype == torch.int16 and src.is_contiguous() and dst.is_contiguous()
+    assert src.numel() == dst.numel()
+    _lib.check(_lib.load_library().dbsr_quantize_q14(src.data_ptr(), dst.data_ptr(), src.numel(), _stream()), 'dbsr_quantize_q14')
+    return dst
 
 
 def conv2d_tc_set_grid_limit(ctas: int) -> None:

@@ -117,9 +117,14 @@ int dbsr_conv2d_tc_set_grid_limit(int32_t ctas);
  * is computed in fp32 registers and stored as fp32 NCHW; the map y itself is NOT written (p->y only gives the geometry).
  *   Needs Cout <= 32 on a map wider than 8 pixels, a residual (if any) that the kernel accumulates on the tensor core
  *   (bf16, Cout == 32), 1 <= pred_c <= 4.  pred_w: fp32 [pred_c][Cout], pred_b: fp32 [pred_c] -- HOST arrays: the <= 132
- *   values are copied into the kernel parameters (constant bank), the only non-device pointers of this ABI.            */
-int dbsr_conv2d_tc_predictor(const dbsr_conv_t* p, const float* pred_w, const float* pred_b, int32_t pred_c, float* pred,
-                             void* stream);
+ *   values are copied into the kernel parameters (constant bank), the only non-device pointers of this ABI.
+ *   pred_q14 = 1: `pred` is an int16 [n, pred_c, h, w] buffer and receives (int16)(min(value, 1) * 2^14) -- the 14-bit
+ *   quantisation the reference's evaluation / result writers apply to the prediction (evaluation/burstsr/compute_score.py:
+ *   110-111, and the save_results.py writers), which halves the device-to-host / gather bytes.                            */
+int dbsr_conv2d_tc_predictor(const dbsr_conv_t* p, const float* pred_w, const float* pred_b, int32_t pred_c, void* pred,
+                             int32_t pred_q14, void* stream);
+/* the same quantisation as a stand-alone pass for the paths without the fused epilogue: dst[i] = (int16)(clamp(src[i],0,1)*2^14) */
+int dbsr_quantize_q14(const float* src, int16_t* dst, int64_t count, void* stream);
 /* tiling chosen for (Cin, Cout): K chunk (64 -> SWIZZLE_128B, 32 -> SWIZZLE_64B), padded K, UMMA N, padded Cout */
 int dbsr_conv2d_tc_geometry(int32_t cin, int32_t cout, int32_t* ck, int32_t* kpad, int32_t* n_tile,
                             int32_t* cout_pad);

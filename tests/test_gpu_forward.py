@@ -207,6 +207,32 @@ def test_alignment_encoder_overlap_is_bit_identical(dev):
                 assert torch.equal(p, p_ref) and torch.equal(aux['offsets'], o_ref)
 
 
+@pytest.mark.parametrize('precision', ['bf16', 'fp32'])
+def test_output_int16_is_the_reference_quantisation(dev, precision):
+    """net.output_int16: pred leaves as int16 = (pred.clamp(0, 1) * 2 ** 14).short() (evaluation/burstsr/compute_score.py:
+    110-111) -- written by the fused predictor epilogue on the bf16 path, by dbsr_quantize_q14 on the fp32 path -- and must
+    equal that expression applied to the float output bit for bit, eagerly, under graph replay and through HostPipeline"""
+    from deep_rawburst_sr_b200.pipeline import HostPipeline
+    sd = O.make_state_dict(0, dbsr_gain=3.0)      # larger decoder weights: part of the output saturates above 1
+    net = _net(sd, dev, precision)
+    net.return_fusion_weights = False
+    burst = O.make_burst(21, 2, 4, 24, 32)
+    pred_f, _ = net(burst.to(dev))
+    want = (pred_f.clamp(0.0, 1.0) * 2 ** 14).short()
+    assert int(want.max()) == 2 ** 14 or float(pred_f.max()) <= 1.0
+    net.output_int16 = True
+    for graph in (False, True):
+        net.use_cuda_graph = graph
+        for _ in range(2):
+            got, _ = net(burst.to(dev))
+        assert got.dtype == torch.int16 and torch.equal(got, want)
+    pipe = HostPipeline(net, depth=2)
+    hout = torch.empty(want.shape, dtype=torch.int16).pin_memory()
+    pipe.submit(burst.pin_memory(), hout).synchronize()
+    assert torch.equal(hout, want.cpu())
+    pipe.drain()
+
+
 def test_module_seams_match_fused_path(dev):
     """encoder -> merging -> decoder called one by one (NCHW dict seams of the reference) == fused engine path"""
     sd = O.make_state_dict(1)
