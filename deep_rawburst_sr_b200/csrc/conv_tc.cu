@@ -1413,7 +1413,7 @@ static int conv2d_tc_impl(const dbsr_conv_t* c_in, void* stream, const float* pr
   {
     const int gw = (cfg.n_tile % 64 == 0) ? 64 : (cfg.n_tile == 32 ? 32 : (cfg.n_tile == 16 ? 16 : 0));
     const size_t stg_off = (size_t)cfg.a_slots * cfg.a_bytes + (size_t)cfg.b_stages * cfg.b_bytes;
-    static const bool enabled = getenv("DBSR_TC_NO_TMA_STORE") == nullptr;
+    static const bool enabled = getenv("DBSR_TC_NO_TMA_STORE") == nullptr;     // A/B switch: =1 keeps the LDS + STG read-back
     // (an epilogue-side residual -- N tile 64 -- is prefetched into the same staging rows and is compatible)
     const bool ok = enabled && gw && pred == nullptr && !cfg.flat && p.bias_smem && cfg.vec_ok && c->y.dtype == DBSR_BF16 &&
                     (p.res == nullptr || cfg.n_tile == 64 || cfg.n_tile == 32 || cfg.n_tile == 16) && stg_off % 128 == 0;

@@ -14,6 +14,7 @@ aligned to 8 channels: [o5 32 | o4 64 | o3 96 | o2 128 | o1 128 | V 81(+7) | f1 
 """
 from __future__ import annotations
 
+import ctypes
 import math
 from typing import Dict, Optional
 
@@ -281,7 +282,6 @@ class DBSREngine:
             self.pred_w = sd['decoder.predictor.0.weight'].float().reshape(sd['decoder.predictor.0.weight'].shape[0], -1).contiguous()
             self.pred_b = sd['decoder.predictor.0.bias'].float().contiguous()
             # host copies for the fused predictor epilogue (its weights travel in the kernel parameters)
-            import ctypes
             self.pred_w_host = (ctypes.c_float * self.pred_w.numel())(*self.pred_w.reshape(-1).cpu().tolist())
             self.pred_b_host = (ctypes.c_float * self.pred_b.numel())(*self.pred_b.cpu().tolist())
             self.feat_dim = sd['decoder.init_layer.0.weight'].shape[1]
