@@ -31,11 +31,14 @@ __global__ void __launch_bounds__(128, 1) rate_kernel(int N, int iters, long lon
   uint8_t* sa = smem;               // 64 KB of A
   uint8_t* sb = smem + 65536;       // 64 KB of B
   __shared__ uint64_t bar;
+  __shared__ uint64_t bar2[2];
   __shared__ uint32_t tslot;
   for (int i = threadIdx.x; i < 131072 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u + i;
   const int warp = threadIdx.x >> 5;
   if (threadIdx.x == 0) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar)));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar2[0])));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar2[1])));
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -67,6 +70,30 @@ __global__ void __launch_bounds__(128, 1) rate_kernel(int N, int iters, long lon
           for (int j = 0; j < 8; ++j)
             umma(tbase + (uint32_t)((j >> 2) * N), ((uint64_t)hi << 32) | (a_lo + tap * 8u + (j >> 2) * 64u + 2u * (j & 3)),
                  ((uint64_t)hi << 32) | (b_lo + tap * 256u + 2u * (j & 3)), idesc, 1u);
+        }
+      } else if (MODE == 3 || MODE == 4) {
+        // the conv kernel's A operand: 8-pixel row groups of a 16x8 tile inside an 18-pixel-wide halo box (SBO = 18 rows of
+        // 128 B = 2304 B), tap (ky, kx) shifts the start by (ky * 18 + kx) rows (MODE 3) / no tap shift (MODE 4)
+        const uint32_t hi_halo = ((2304u >> 4) & 0x3FFFu) | (1u << 14) | (2u << 29);
+        for (int i = 0; i < iters; i += 8) {
+          const uint32_t tap = (uint32_t)(i >> 3) % 9u;
+          const uint32_t shift = (MODE == 3) ? ((tap / 3u) * 18u + (tap % 3u)) * 8u : 0u;
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            umma(tbase + (uint32_t)((j >> 2) * N), ((uint64_t)hi_halo << 32) | (a_lo + shift + (j >> 2) * 64u + 2u * (j & 3)),
+                 ((uint64_t)hi << 32) | (b_lo + tap * 256u + 2u * (j & 3)), idesc, 1u);
+        }
+      } else if (MODE >= 5) {
+        // the conv kernel's per-item structure: groups of G MMAs (G = 72: one 64 -> 64 item; 36: one 32 -> 32 item), the
+        // first MMAs of a group overwrite their accumulators, accumulators alternate between groups, and every group ends
+        // with tcgen05.commit to a barrier (MODE 5: one commit; MODE 6: two, as a_empty + tfull; MODE 7: none)
+        const int G = (N == 32) ? 36 : 72;
+        const uint64_t a = ((uint64_t)hi << 32) | a_lo, b = ((uint64_t)hi << 32) | b_lo;
+        for (int i = 0; i < iters; i += G) {
+          const uint32_t d = tbase + (uint32_t)(((i / G) & 1) * 2 * N);
+          for (int j = 0; j < G; ++j) umma(d + (uint32_t)(((j >> 2) & 1) * N), a, b, idesc, j < 8 ? 0u : 1u);
+          if (MODE == 5 || MODE == 6) commit(&bar2[0]);
+          if (MODE == 6) commit(&bar2[1]);
         }
       } else {                    // two alternating accumulators, constant descriptors
         const uint64_t a = ((uint64_t)hi << 32) | a_lo, b = ((uint64_t)hi << 32) | b_lo;
@@ -116,6 +143,9 @@ int main() {
     for (int N : Ns) run<0>(N, g, iters);
     for (int N : Ns) if (2 * N <= 512) run<1>(N, g, iters);
     for (int N : Ns) if (2 * N <= 512) run<2>(N, g, iters);
+    for (int N : Ns) if (2 * N <= 512) run<3>(N, g, iters);
+    for (int N : Ns) if (2 * N <= 512) run<4>(N, g, iters);
+    for (int N : {32, 64, 128}) { run<5>(N, g, 4032); run<6>(N, g, 4032); run<7>(N, g, 4032); }
   }
   return 0;
 }
