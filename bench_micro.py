@@ -4,7 +4,7 @@ microbench only: 14-frame 64-channel embeddings at 96x96 and 160x160 flow resolu
 
     python bench_micro.py [--iters K] [--warmup W] [--bursts B] [--out file.json]
 
-Four legs, every one through the C ABI (`ops.*` -> libdbsr_b200.so), one JSON line each (rank 0 / one GPU):
+Five legs, every one through the C ABI (`ops.*` -> libdbsr_b200.so), one JSON line each (rank 0 / one GPU):
 
 * `corr81`      cost volume (correlation.py:280-330 + the fused backwarp / LeakyReLU of pwcnet.py:161,169) at the five
                 pyramid level shapes of a 96^2 and a 160^2 frame, 13*B pairs: achieved HBM GB/s = algorithmic bytes
@@ -13,6 +13,7 @@ Four legs, every one through the C ABI (`ops.*` -> libdbsr_b200.so), one JSON li
                 C=64 at S=96,160 (the cfg-4 stress shape) and the network's real shape C=512 at S=48,80; flows
                 U(-4,4) px so that out-of-image taps occur.  Bytes: (28*C*s + 13*2*4)*S^2 + C*s*S^2 per burst.
 * `pwc_align`   the whole PWC-Net alignment of a burst batch (pwcnet.py:248-281) at 96^2 / 160^2: pairs/s.
+* `metrics`     SSIM / MS-SSIM / PSNR of a batch of predictions through the fused metric kernels.
 * `sca`         SpatialColorAlignment.forward (models/loss/spatial_color_alignment.py:85-108) at the BurstSR evaluation
                 shape (640^2 prediction / ground truth, 80^2 RAW burst): images/s.
 
@@ -67,7 +68,7 @@ def main():
     ap.add_argument('--iters', type=int, default=20)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--bursts', type=int, default=8, help='bursts per launch (13 pairs each)')
-    ap.add_argument('--legs', default='corr81,warp_fuse,pwc_align,sca')
+    ap.add_argument('--legs', default='corr81,warp_fuse,pwc_align,sca,metrics')
     ap.add_argument('--out', default='')
     args = ap.parse_args()
     from deep_rawburst_sr_b200 import ops
@@ -174,6 +175,33 @@ def main():
             med, mn = timer(lambda: sca(pred, gt, burst))
             emit({'leg': 'sca', 'images': nb, 'size': 640, 'alignment_net_precision': prec, 'ms': med, 'ms_min': mn,
                   'images_per_s': nb / med * 1e3})
+    if 'metrics' in legs:
+        # SSIM / MS-SSIM / PSNR of a batch of predictions (configs[1] / [2] output sizes), one launch
+        # chain per call, no host synchronisation.  SSIM: both images read once (8 B per pixel-channel) and 5 moments x
+        # 2 x 11 taps of separable window = 110 FMA per window position (+ halo) -> FP32-FMA-bound, reported as GFLOP/s of
+        # the algorithmic 2 x 110 FLOP per position next to the HBM figure; PSNR: 8 B per pixel-channel, HBM-bound.
+        from deep_rawburst_sr_b200.models.loss import msssim as ms
+        from deep_rawburst_sr_b200.models.loss.image_quality_v2 import PSNR
+        for nb, S in ((32, 384), (16, 640)):
+            gt = torch.rand(nb, 3, S, S, generator=g).to(dev)
+            pred = (gt + 0.02 * torch.randn(nb, 3, S, S, generator=g).to(dev)).clamp(0, 1)
+            px = nb * 3 * S * S
+            pos = nb * 3 * (S - 10) * (S - 10)
+            med, mn = timer(lambda: ms.ssim(pred, gt, size_average=False))
+            emit({'leg': 'metrics', 'op': 'ssim', 'images': nb, 'size': S, 'ms': med, 'ms_min': mn, 'images_per_s': nb / med * 1e3,
+                  'hbm_gbs': 8 * px / med / 1e6, 'hbm_frac': 8 * px / med / 1e6 / peak, 'fp32_gflops': 220 * pos / med / 1e6,
+                  'launches': 3})
+            med, mn = timer(lambda: ms.ssim(pred, gt, size_average=False, val_range=1.0))
+            emit({'leg': 'metrics', 'op': 'ssim_val_range_given', 'images': nb, 'size': S, 'ms': med, 'ms_min': mn,
+                  'images_per_s': nb / med * 1e3, 'fp32_gflops': 220 * pos / med / 1e6, 'launches': 2})
+            med, mn = timer(lambda: ms.msssim(pred, gt))
+            emit({'leg': 'metrics', 'op': 'msssim', 'images': nb, 'size': S, 'ms': med, 'ms_min': mn, 'images_per_s': nb / med * 1e3})
+            m = PSNR(boundary_ignore=40)
+            med, mn = timer(lambda: m.psnr_per_image(pred, gt))
+            cpx = nb * 3 * (S - 80) * (S - 80)
+            emit({'leg': 'metrics', 'op': 'psnr_per_image', 'images': nb, 'size': S, 'boundary_ignore': 40, 'ms': med, 'ms_min': mn,
+                  'images_per_s': nb / med * 1e3, 'hbm_gbs': 8 * cpx / med / 1e6, 'hbm_frac': 8 * cpx / med / 1e6 / peak})
+            del gt, pred
     if args.out:
         with open(args.out, 'w') as f:
             for d in lines:

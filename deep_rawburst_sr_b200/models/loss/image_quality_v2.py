@@ -1,12 +1,17 @@
 """Image-quality metrics of the DBSR path with the reference's interface (models/loss/image_quality_v2.py):
 `PixelWiseError` (:24-66), `PSNR` (:69-101) and `AlignedL2` (:166-191, the BurstSR loss / metric built on
-`SpatialColorAlignment`).  SSIM / LPIPS depend on packages outside this path and are not provided."""
+`SpatialColorAlignment`) and `SSIM` (:104-136, on the fused `dbsr_ssim` kernel of `msssim.py`).  On CUDA fp32 batches
+without a `valid` mask `PSNR` takes its per-image MSE from one `dbsr_mse_per_image` launch (boundary_ignore as index
+arithmetic) instead of a Python loop of sliced reductions.  LPIPS depends on a package outside this path (`lpips`, a
+pretrained AlexNet) and is not provided."""
 import math
 
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+from ... import ops
+from . import msssim
 from . import spatial_color_alignment as sca_utils
 
 
@@ -58,7 +63,19 @@ class PSNR(nn.Module):
             print('invalid psnr')
         return psnr
 
+    def psnr_per_image(self, pred, gt):
+        """[n] PSNR of every image of a CUDA fp32 batch from one fused launch, no host synchronisation (what a sharded
+        evaluation all-reduces instead of gathering images)."""
+        b = self.l2.boundary_ignore
+        mse = ops.mse_per_image(pred.contiguous(), gt.contiguous(), crop=0 if b is None else b)
+        return 20 * math.log10(getattr(self, 'max_value', 1.0)) - 10.0 * mse.log10()
+
     def forward(self, pred, gt, valid=None):
+        if valid is None and pred.is_cuda and pred.dim() == 4 and pred.dtype == torch.float32 and gt.dtype == torch.float32 \
+                and pred.shape == gt.shape and getattr(self, 'max_value', 1.0) is not None:
+            psnr = self.psnr_per_image(pred, gt)
+            ok = torch.isfinite(psnr)                      # the reference drops inf / nan images (:97), 0 if none is left
+            return torch.where(ok, psnr, torch.zeros_like(psnr)).sum() / ok.sum().clamp(min=1)
         if valid is None:
             psnr_all = [self.psnr(p.unsqueeze(0), g.unsqueeze(0)) for p, g in zip(pred, gt)]
         else:
@@ -67,6 +84,34 @@ class PSNR(nn.Module):
         if len(psnr_all) == 0:
             return 0
         return sum(psnr_all) / len(psnr_all)
+
+
+class SSIM(nn.Module):
+    def __init__(self, boundary_ignore=None, use_for_loss=True):
+        super().__init__()
+        self.ssim = msssim.SSIM(spatial_out=True)
+        self.boundary_ignore = boundary_ignore
+        self.use_for_loss = use_for_loss
+
+    def forward(self, pred, gt, valid=None):
+        crop = 0 if self.boundary_ignore is None else self.boundary_ignore
+        if valid is not None and crop:
+            valid = valid[..., crop:-crop, crop:-crop]
+        if pred.dim() == 3:
+            pred = pred.unsqueeze(0)
+            gt = gt.unsqueeze(0)
+        if valid is not None:
+            loss = self.ssim(pred, gt, crop=crop)          # the map itself is only needed under a mask
+            valid = valid[..., 5:-5, 5:-5]  # assume window size 11
+            eps = 1e-12
+            elem_ratio = loss.numel() / valid.numel()
+            loss = (loss * valid.float()).sum() / (valid.float().sum() * elem_ratio + eps)
+        else:
+            stats, _ = msssim._stats(pred, gt, self.ssim.window_size, None, None, want_map=False, crop=crop, fixed_window=True)
+            loss = stats[:, 0].mean()
+        if self.use_for_loss:
+            loss = 1.0 - loss
+        return loss
 
 
 class AlignedL2(nn.Module):

@@ -277,3 +277,57 @@ def predictor(x: Act, w: torch.Tensor, bias: Optional[torch.Tensor], pred: torch
     _lib.check(_lib.load_library().dbsr_predictor(ctypes.byref(v), w.data_ptr(), _ptr(bias), cout, pred.data_ptr(),
                                                   _stream()), 'dbsr_predictor')
     return pred
+
+
+# ---- evaluation metrics (include/dbsr_b200.h "evaluation metrics") ------------------------------------------------------
+def _check_image_pair(a: torch.Tensor, b: torch.Tensor) -> None:
+    require_device(a)
+    require_device(b)
+    if a.dim() != 4 or a.shape != b.shape:
+        raise ValueError(f'expected two [n, c, h, w] tensors of the same shape, got {tuple(a.shape)} / {tuple(b.shape)}')
+    if a.dtype != torch.float32 or b.dtype != torch.float32:
+        raise TypeError('the metric kernels take fp32 images')
+    assert a.is_contiguous() and b.is_contiguous()
+
+
+def ssim_stats(img1: torch.Tensor, img2: torch.Tensor, window1d, crop: int = 0, val_range: Optional[float] = None,
+               want_map: bool = False):
+    """Fused SSIM of two fp32 NCHW batches: returns (stats [n, 2] = per-image mean ssim / mean contrast term, map or None).
+    window1d: the 1-D Gaussian of msssim.gaussian (python floats, len 1..11); val_range None -> derived on the device."""
+    _check_image_pair(img1, img2)
+    n, c, h, w = img1.shape
+    k = len(window1d)
+    lib = _lib.load_library()
+    floats = lib.dbsr_ssim_workspace_floats(n, c, h, w, crop, k)
+    if floats < 0:
+        raise ValueError(f'ssim: image {h}x{w} with boundary_ignore {crop} and a {k}-tap window has no valid window position')
+    ws = torch.empty(floats, dtype=torch.float32, device=img1.device)
+    stats = torch.empty(n, 2, dtype=torch.float32, device=img1.device)
+    smap = torch.empty(n, c, h - 2 * crop - k + 1, w - 2 * crop - k + 1, dtype=torch.float32, device=img1.device) if want_map else None
+    arr = (ctypes.c_float * k)(*[float(v) for v in window1d])
+    _lib.check(lib.dbsr_ssim(img1.data_ptr(), img2.data_ptr(), n, c, h, w, crop, arr, k, float(val_range) if val_range else 0.0,
+                             ws.data_ptr(), stats.data_ptr(), _ptr(smap), _stream()), 'dbsr_ssim')
+    return stats, smap
+
+
+def avgpool2_pair(img1: torch.Tensor, img2: torch.Tensor):
+    """(F.avg_pool2d(img1, (2, 2)), F.avg_pool2d(img2, (2, 2))) in one launch (msssim.py:88-89)."""
+    _check_image_pair(img1, img2)
+    n, c, h, w = img1.shape
+    o1 = torch.empty(n, c, h // 2, w // 2, dtype=torch.float32, device=img1.device)
+    o2 = torch.empty_like(o1)
+    _lib.check(_lib.load_library().dbsr_avgpool2_pair(img1.data_ptr(), img2.data_ptr(), o1.data_ptr(), o2.data_ptr(), n * c, h, w,
+                                                      _stream()), 'dbsr_avgpool2_pair')
+    return o1, o2
+
+
+def mse_per_image(pred: torch.Tensor, gt: torch.Tensor, crop: int = 0) -> torch.Tensor:
+    """[n] mean squared error of each image over its interior (boundary_ignore = crop), one launch for the batch."""
+    _check_image_pair(pred, gt)
+    n, c, h, w = pred.shape
+    lib = _lib.load_library()
+    ws = torch.empty(lib.dbsr_mse_workspace_floats(n), dtype=torch.float32, device=pred.device)
+    out = torch.empty(n, dtype=torch.float32, device=pred.device)
+    _lib.check(lib.dbsr_mse_per_image(pred.data_ptr(), gt.data_ptr(), n, c, h, w, crop, ws.data_ptr(), out.data_ptr(), _stream()),
+               'dbsr_mse_per_image')
+    return out

@@ -200,6 +200,31 @@ int dbsr_blur3x3(const dbsr_nhwc_t* x, const dbsr_nhwc_t* y, const float* k9, vo
 int dbsr_predictor(const dbsr_nhwc_t* x, const float* w, const float* bias, int32_t cout, float* pred,
                    void* stream);
 
+/* -------------------------------------------------------------------------------------------------- */
+/* evaluation metrics: the multi-GPU run reduces scalars instead of gathering images  */
+/* -------------------------------------------------------------------------------------------------- */
+/* SSIM (models/loss/msssim.py:22-74 `ssim`, called by msssim.SSIM / MSSSIM and by image_quality_v2.SSIM :104-136).
+ *   img1, img2: fp32 NCHW [n, c, h, w], contiguous.  `crop` = boundary_ignore (image_quality_v2.py:112-114), applied as
+ *   index arithmetic.  window1d: `window` (1..11) HOST floats = msssim.gaussian(window, 1.5) (:10-12); the 2-D window of
+ *   create_window (:15-19) is its outer product and is applied separably, without padding (:44-45, padd = 0).
+ *   val_range > 0: L = val_range; <= 0: L is derived on the device from max / min of the cropped img1 (:24-35), no host
+ *   synchronisation.  stats: fp32 [n][2] = per-image mean of the ssim map and of the contrast term v1 / v2 (:59).
+ *   ssim_map: optional fp32 [n, c, h - 2 crop - window + 1, w - 2 crop - window + 1] (`spatial_out`), or NULL.
+ *   workspace: dbsr_ssim_workspace_floats(...) floats of device memory (per-CTA partial sums: the reduction order is
+ *   fixed, results are bit-identical from run to run).                                                         */
+int dbsr_ssim_workspace_floats(int32_t n, int32_t c, int32_t h, int32_t w, int32_t crop, int32_t window);
+int dbsr_ssim(const float* img1, const float* img2, int32_t n, int32_t c, int32_t h, int32_t w, int32_t crop,
+              const float* window1d, int32_t window, float val_range, float* workspace, float* stats, float* ssim_map,
+              void* stream);
+/* F.avg_pool2d(img, (2, 2)) of both images between two MS-SSIM levels (msssim.py:88-89): [planes, h, w] -> [planes, h/2, w/2] */
+int dbsr_avgpool2_pair(const float* img1, const float* img2, float* out1, float* out2, int32_t planes, int32_t h, int32_t w,
+                       void* stream);
+/* per-image mean squared error over the interior (image_quality_v2.py:47-66 with metric 'l2', valid = None), the quantity
+ * PSNR.psnr (:75-86) takes the log of.  pred, gt: fp32 NCHW [n, c, h, w]; mse: fp32 [n]; workspace: dbsr_mse_workspace_floats(n). */
+int dbsr_mse_workspace_floats(int32_t n);
+int dbsr_mse_per_image(const float* pred, const float* gt, int32_t n, int32_t c, int32_t h, int32_t w, int32_t crop,
+                       float* workspace, float* mse, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -116,3 +116,41 @@ def test_sca_oracle_matches_reference_golden(golden_dir, name):
     assert 0.02 < valid.float().mean() < 0.9          # the mask is neither empty nor full
     l2 = float(S.aligned_l2(pred, gt, burst, sd, boundary_ignore=16))
     assert abs(l2 - float(g['aligned_l2'][0])) <= 1e-4 * float(g['aligned_l2'][0])
+
+
+METRIC_CASES = ['metrics_rgb_b2_176', 'metrics_ragged_b3_97x131', 'metrics_gray_255_b1_200', 'metrics_signed_b2_180']
+
+
+@pytest.mark.parametrize('name', METRIC_CASES)
+def test_metrics_oracle_matches_reference_golden(golden_dir, name):
+    """oracle/metrics_oracle.py against the values the reference's own msssim.py / image_quality_v2.py produced
+    (oracle/make_golden_metrics.py): SSIM mean / per image / map, contrast term, MS-SSIM (incl. the small-map levels with
+    a min(11, h, w) window), the boundary_ignore + valid-mask SSIM metric, PSNR.  Tolerance 2e-6 abs on the means (summation
+    order of the 121-tap window), 10 x that on 0..255 images (E[x^2] - mu^2 cancels ~4 more digits there), 1e-4 dB on PSNR."""
+    from oracle import metrics_oracle as M
+    g = np.load(os.path.join(golden_dir, name + '.npz'))
+    seed, n, c, h, w, bi = [int(v) for v in g['meta']]
+    noise, scale, offset = [float(v) for v in g['gen']]
+    pred, gt = M.make_image_pair(seed, n, c, h, w, noise, scale, offset)
+    valid = torch.rand(n, 1, h, w, generator=torch.Generator().manual_seed(int(g['valid_seed']))) > 0.3
+    tol = 2e-6 if scale <= 2 else 2e-5
+    mtol = 10 * tol
+    s_mean, cs = M.ssim(pred, gt, full=True)
+    assert abs(float(s_mean) - float(g['ssim_mean'])) <= tol and abs(float(cs) - float(g['cs'])) <= tol
+    assert np.abs(M.ssim(pred, gt, size_average=False).numpy() - g['ssim_per_image']).max() <= tol
+    smap = M.ssim(pred, gt, spatial_out=True)
+    assert np.abs(smap[..., :24, :24].numpy() - g['ssim_map_corner']).max() <= mtol
+    assert np.abs(smap[..., -16:, -16:].numpy() - g['ssim_map_tail']).max() <= mtol
+    assert abs(float(M.ssim(pred, gt, val_range=1.0)) - float(g['ssim_val_range1'])) <= tol
+    assert abs(float(M.msssim(pred, gt)) - float(g['msssim'])) <= tol
+    assert abs(float(M.msssim(pred, gt, normalize=True)) - float(g['msssim_normalized'])) <= tol
+    assert float(g['ssim_class']) == float(g['ssim_mean']) and float(g['msssim_class']) == float(g['msssim'])
+    assert abs(float(M.ssim_metric(pred, gt, bi)) - float(g['iq_ssim_loss'])) <= tol
+    assert abs(float(M.ssim_metric(pred, gt, bi, use_for_loss=False)) - float(g['iq_ssim'])) <= tol
+    assert abs(float(M.ssim_metric(pred, gt, bi, use_for_loss=False, valid=valid)) - float(g['iq_ssim_valid'])) <= tol
+    assert abs(float(M.ssim_metric(pred[0], gt[0], None, use_for_loss=False)) - float(g['iq_ssim_single'])) <= tol
+    small = M.ssim(pred[..., :7, :9], gt[..., :7, :9], full=True)
+    assert abs(float(small[0]) - float(g['small_ssim'])) <= tol and abs(float(small[1]) - float(g['small_cs'])) <= tol
+    mv = max(scale, 1.0)
+    assert abs(float(M.psnr(pred, gt, bi, mv)) - float(g['psnr'])) <= 1e-4
+    assert np.abs(M.psnr_per_image(pred, gt, bi, mv).numpy() - g['psnr_per_image']).max() <= 1e-4
