@@ -15,7 +15,7 @@ constexpr int SS_IN_H = SS_TH + SS_MAXW - 1;   // 42 input rows / cols per tile
 constexpr int SS_IN_W = SS_TW + SS_MAXW - 1;
 constexpr int SS_PITCH = 45;          // input-tile row pitch: 4 rows x 8 strips of one warp hit 32 distinct banks
 constexpr int SS_THREADS = 256;
-constexpr int RANGE_BLOCKS = 64;      // per-CTA (max, min) partials of the data-dependent value range
+constexpr int RANGE_BLOCKS = 592;     // per-CTA (max, min) partials of the data-dependent value range (4 CTAs per SM)
 
 struct SsimParams {
   const float* a;          // img1 [planes, H, W]
@@ -82,24 +82,31 @@ __global__ void __launch_bounds__(SS_THREADS) ssim_tile_kernel(const SsimParams 
   const float* pb = p.b + ((long long)plane * p.H + p.crop) * p.W + p.crop;
 
   // C1 / C2 (msssim.py:54-55): python doubles, rounded to fp32 when they meet the tensors
-  if (tid < 32) {
-    float L = p.val_range;
-    if (L <= 0.0f) {
-      float mx = fmaxf(p.range_ws[2 * tid], p.range_ws[2 * (tid + 32)]);
-      float mn = fminf(p.range_ws[2 * tid + 1], p.range_ws[2 * (tid + 32) + 1]);
+  float L = p.val_range;
+  if (L <= 0.0f) {                                 // uniform branch: the whole CTA reduces the (max, min) partials
+    float mx = -INFINITY, mn = INFINITY;
+    for (int i = tid; i < RANGE_BLOCKS; i += SS_THREADS) {
+      mx = fmaxf(mx, p.range_ws[2 * i]);
+      mn = fminf(mn, p.range_ws[2 * i + 1]);
+    }
 #pragma unroll
-      for (int o = 16; o; o >>= 1) {
-        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-        mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
-      }
+    for (int o = 16; o; o >>= 1) {
+      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+      mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+    }
+    if ((tid & 31) == 0) { red[0][tid >> 5] = mx; red[1][tid >> 5] = mn; }
+    __syncthreads();
+    if (tid == 0) {
+      for (int i = 1; i < SS_THREADS / 32; ++i) { mx = fmaxf(mx, red[0][i]); mn = fminf(mn, red[1][i]); }
       L = (mx > 128.0f ? 255.0f : 1.0f) - (mn < -0.5f ? -1.0f : 0.0f);
     }
-    if (tid == 0) {
-      const double k1 = 0.01 * (double)L, k2 = 0.03 * (double)L;
-      s_c[0] = (float)(k1 * k1);
-      s_c[1] = (float)(k2 * k2);
-    }
   }
+  if (tid == 0) {
+    const double k1 = 0.01 * (double)L, k2 = 0.03 * (double)L;
+    s_c[0] = (float)(k1 * k1);
+    s_c[1] = (float)(k2 * k2);
+  }
+  __syncthreads();                                 // `red` is reused by the final reduction
 
   for (int i = tid; i < SS_IN_H * SS_IN_W; i += SS_THREADS) {
     const int r = i / SS_IN_W, c = i - r * SS_IN_W;
