@@ -38,6 +38,14 @@ def _worker(rank, world, port, total, out_dir):
     for rep in range(3):     # slots are recycled
         got, ev = gat.submit(_standin_forward(bursts[lo:hi]) + rep)
         assert ev is None and torch.equal(got, _standin_forward(bursts) + rep)
+    # metric scalars: one all_reduce of [sums | counts] instead of gathering images; inf / nan images are dropped
+    per_image = _standin_forward(bursts).flatten(1).mean(1)
+    per_image[0] = float('inf')
+    two = torch.stack([per_image, per_image * 2 + 1], dim=1)
+    mean1 = sharding.reduce_metric_means(per_image[lo:hi])
+    mean2 = sharding.reduce_metric_means(two[lo:hi])
+    assert torch.allclose(mean1, per_image[1:].mean(), rtol=1e-6, atol=0)
+    assert mean2.shape == (2,) and torch.allclose(mean2[0], mean1) and torch.allclose(mean2[1], two[1:, 1].mean(), rtol=1e-6, atol=0)
     torch.save({'full': full, 'mx': mx, 'range': sharding.shard_range(total, rank, world)}, os.path.join(out_dir, f'r{rank}.pt'))
     dist.destroy_process_group()
 
