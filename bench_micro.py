@@ -14,6 +14,7 @@ Five legs, every one through the C ABI (`ops.*` -> libdbsr_b200.so), one JSON li
                 U(-4,4) px so that out-of-image taps occur.  Bytes: (28*C*s + 13*2*4)*S^2 + C*s*S^2 per burst.
 * `pwc_align`   the whole PWC-Net alignment of a burst batch (pwcnet.py:248-281) at 96^2 / 160^2: pairs/s.
 * `metrics`     SSIM / MS-SSIM / PSNR of a batch of predictions through the fused metric kernels.
+* `eval`        (opt-in, --legs eval) the batched SyntheticBurst scoring loop end to end from host tensors (8(f) rank 2).
 * `sca`         SpatialColorAlignment.forward (models/loss/spatial_color_alignment.py:85-108) at the BurstSR evaluation
                 shape (640^2 prediction / ground truth, 80^2 RAW burst): images/s.
 
@@ -202,6 +203,24 @@ def main():
             emit({'leg': 'metrics', 'op': 'psnr_per_image', 'images': nb, 'size': S, 'boundary_ignore': 40, 'ms': med, 'ms_min': mn,
                   'images_per_s': nb / med * 1e3, 'hbm_gbs': 8 * cpx / med / 1e6, 'hbm_frac': 8 * cpx / med / 1e6 / peak})
             del gt, pred
+    if 'eval' in legs:
+        # the SyntheticBurst scoring protocol (forward -> 14-bit quantisation -> PSNR + SSIM with
+        # boundary_ignore 40 -> mean), batched: host bursts / ground truths in, one host read of the report at the end
+        import time
+        from deep_rawburst_sr_b200.evaluation.synburst.compute_score import TensorBurstSet, score_dataset
+        from deep_rawburst_sr_b200.models.dbsr.dbsrnet import dbsrnet_default_synthetic
+        torch.manual_seed(0)
+        net = dbsrnet_default_synthetic().to(dev).eval().set_precision('bf16')
+        net.use_cuda_graph = True
+        n = 256
+        data = TensorBurstSet(torch.rand(n, FRAMES, 4, 48, 48, generator=g).pin_memory(), torch.rand(n, 3, 384, 384, generator=g).pin_memory())
+        score_dataset(net, data, batch_size=32, device=dev)          # warm-up: graph capture, workspaces
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        rep = score_dataset(net, data, batch_size=32, device=dev)
+        dt = time.perf_counter() - t0                                 # the final report read synchronises
+        emit({'leg': 'eval', 'bursts': n, 'batch': 32, 'size': 48, 'precision': 'bf16', 's': dt, 'bursts_per_s': n / dt,
+              'report': rep, 'timing': 'host wall clock around score_dataset (ends with the host read of the report)'})
     if args.out:
         with open(args.out, 'w') as f:
             for d in lines:

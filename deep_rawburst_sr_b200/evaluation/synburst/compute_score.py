@@ -1,0 +1,100 @@
+"""Batched, burst-sharded scoring loop of the SyntheticBurst validation protocol.
+
+The reference's `compute_score` (evaluation/synburst/compute_score.py:35-126) walks the validation set one burst at a time:
+forward at batch 1, 14-bit quantisation `(pred.clamp(0, 1) * 2 ** 14).short().float() / 2 ** 14` (:110-111), then each metric
+with a `.cpu().item()` per image (:114) -- a host synchronisation per metric per burst.  `score_dataset` keeps the protocol
+(same quantisation, same per-image metrics `PSNR(boundary_ignore=40)` / `SSIM(boundary_ignore=40, use_for_loss=False)`
+averaged over the images, :47-60,122) and changes the schedule: bursts are stacked into batches, every rank scores a
+contiguous shard of the set (`sharding.shard_range`), the network writes the int16 form directly from the predictor
+epilogue (`net.output_int16`), the metrics come from the fused kernels without leaving the device, and the ranks exchange
+one all-reduce of `[sums | counts]` at the end (`sharding.reduce_metric_means`) -- the only host read is the final report.
+LPIPS (a pretrained AlexNet from the `lpips` package) is not on this path and is refused.  The on-disk dataset / experiment
+registry / PNG cache of the reference's driver are out of scope: `dataset` is any indexable of
+`(burst [N, 4, H, W], gt [3, 8H, 8W], meta_info)` items, the contract of `SyntheticBurstVal.__getitem__`
+(dataset/synthetic_burst_val_set.py:38-55)."""
+from __future__ import annotations
+
+from typing import Dict, Sequence
+
+import torch
+import torch.distributed as dist
+
+from ... import sharding
+from ...models.loss import msssim
+from ...models.loss.image_quality_v2 import PSNR
+
+
+class TensorBurstSet:
+    """In-memory stand-in with the item contract of `SyntheticBurstVal` (dataset/synthetic_burst_val_set.py:38-55)."""
+
+    def __init__(self, bursts: torch.Tensor, gts: torch.Tensor):
+        assert bursts.dim() == 5 and gts.dim() == 4 and bursts.shape[0] == gts.shape[0]
+        self.bursts, self.gts = bursts, gts
+
+    def __len__(self):
+        return self.bursts.shape[0]
+
+    def __getitem__(self, index):
+        return self.bursts[index], self.gts[index], {'burst_name': '{:04d}'.format(index)}
+
+
+def dequantize_q14(pred_q: torch.Tensor) -> torch.Tensor:
+    """int16 -> float, `net_pred_int.float() / (2 ** 14)` (compute_score.py:111); exact"""
+    return pred_q.float() / 2 ** 14
+
+
+@torch.no_grad()
+def score_dataset(net, dataset, metrics: Sequence[str] = ('psnr', 'ssim'), boundary_ignore: int = 40, batch_size: int = 32,
+                  device='cuda', burst_sz=None) -> Dict[str, float]:
+    """Mean per-image metrics of `net` over `dataset` (all ranks' shards), plus 'count'.  `net`: a `DBSRNet` of this package."""
+    for m in metrics:
+        if m not in ('psnr', 'ssim'):
+            raise NotImplementedError(f'metric {m!r} is not provided (psnr / ssim; lpips needs the `lpips` package)')
+    rank = dist.get_rank() if (dist.is_available() and dist.is_initialized()) else 0
+    world = dist.get_world_size() if (dist.is_available() and dist.is_initialized()) else 1
+    lo, hi = sharding.shard_range(len(dataset), rank, world)
+    device = torch.device(device)
+    psnr_fn = PSNR(boundary_ignore=boundary_ignore)
+    was_q = getattr(net, 'output_int16', False)
+    net.output_int16 = True
+    per_image = []
+    try:
+        for start in range(lo, hi, batch_size):
+            items = [dataset[i] for i in range(start, min(start + batch_size, hi))]
+            burst = torch.stack([it[0] for it in items]).to(device, non_blocking=True)
+            gt = torch.stack([it[1] for it in items]).to(device, non_blocking=True).float().contiguous()
+            if burst_sz is not None:
+                burst = burst[:, :burst_sz]
+            pred_q, _ = net(burst.float().contiguous())
+            pred = dequantize_q14(pred_q)
+            cols = []
+            for m in metrics:
+                if m == 'psnr':
+                    cols.append(psnr_fn.psnr_per_image(pred, gt))
+                else:   # image_quality_v2.SSIM(boundary_ignore, use_for_loss=False) per image: 11-tap window, data-derived range
+                    cols.append(msssim._stats(pred, gt, 11, None, None, crop=boundary_ignore or 0, fixed_window=True)[0][:, 0])
+            per_image.append(torch.stack(cols, dim=1))
+    finally:
+        net.output_int16 = was_q
+    local = torch.cat(per_image) if per_image else torch.zeros(0, len(metrics), device=device)
+    mean = sharding.reduce_metric_means(local)
+    out = {m: float(v) for m, v in zip(metrics, mean.cpu())}
+    out['count'] = len(dataset)
+    return out
+
+
+def generate_formatted_report(scores_all: Dict[str, Dict[str, float]], table_name: str = '') -> str:
+    """Text table `name | metric ... |` with three decimals (evaluation/common_utils/display_utils.py:15-41)."""
+    name_width = max([len(d) for d in scores_all] + [len(table_name)]) + 5
+    names = [k for k in next(iter(scores_all.values())) if k != 'count']
+    widths = [max(10, len(k) + 3) for k in names]
+    text = '\n{: <{w}} |'.format(table_name, w=name_width)
+    for k, w in zip(names, widths):
+        text += ' {: <{w}} |'.format(k, w=w)
+    text += '\n'
+    for net_name, scores in scores_all.items():
+        text += '{: <{w}} |'.format(net_name, w=name_width)
+        for k, w in zip(names, widths):
+            text += ' {: <{w}} |'.format('{:0.3f}'.format(scores[k]), w=w)
+        text += '\n'
+    return text
