@@ -219,7 +219,15 @@ def main():
         t0 = time.perf_counter()
         rep = score_dataset(net, data, batch_size=32, device=dev)
         dt = time.perf_counter() - t0                                 # the final report read synchronises
-        emit({'leg': 'eval', 'bursts': n, 'batch': 32, 'size': 48, 'precision': 'bf16', 's': dt, 'bursts_per_s': n / dt,
+        emit({'leg': 'eval', 'bursts': n, 'batch': 32, 'size': 48, 'precision': 'bf16', 's': dt, 'bursts_per_s': n / dt, 'dataset': 'contiguous pinned tensors',
+              'report': rep, 'timing': 'host wall clock around score_dataset (ends with the host read of the report)'})
+        items = [data[i] for i in range(n)]          # per-item datasets: stacked into pinned double buffers by the loop
+        score_dataset(net, items, batch_size=32, device=dev)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        rep = score_dataset(net, items, batch_size=32, device=dev)
+        dt = time.perf_counter() - t0
+        emit({'leg': 'eval', 'bursts': n, 'batch': 32, 'size': 48, 'precision': 'bf16', 's': dt, 'bursts_per_s': n / dt, 'dataset': 'per-item list',
               'report': rep, 'timing': 'host wall clock around score_dataset (ends with the host read of the report)'})
     if args.out:
         with open(args.out, 'w') as f:

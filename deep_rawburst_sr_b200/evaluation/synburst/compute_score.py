@@ -37,6 +37,37 @@ class TensorBurstSet:
     def __getitem__(self, index):
         return self.bursts[index], self.gts[index], {'burst_name': '{:04d}'.format(index)}
 
+    def batch(self, start: int, stop: int):
+        """contiguous items as two views (no per-item stacking); pinned storage makes the upload asynchronous"""
+        return self.bursts[start:stop], self.gts[start:stop]
+
+
+class _Stager:
+    """Stacks dataset items into two alternating pinned host buffers, so that the upload of batch i is asynchronous and the
+    host assembles batch i + 1 while the device works on batch i."""
+
+    def __init__(self):
+        self.slots = [{}, {}]
+        self.i = 0
+
+    def __call__(self, items, device):
+        slot = self.slots[self.i % 2]
+        self.i += 1
+        if 'event' in slot:
+            slot['event'].synchronize()              # the upload that last read this slot has finished
+        out = []
+        for k in (0, 1):
+            first = items[0][k]
+            shape = (len(items),) + tuple(first.shape)
+            buf = slot.get(k)
+            if buf is None or buf.shape[1:] != shape[1:] or buf.shape[0] < shape[0] or buf.dtype != first.dtype:
+                buf = slot[k] = torch.empty(shape, dtype=first.dtype).pin_memory()
+            torch.stack([it[k] for it in items], out=buf[:shape[0]])
+            out.append(buf[:shape[0]].to(device, non_blocking=True))
+        slot['event'] = torch.cuda.Event()
+        slot['event'].record()
+        return out
+
 
 def dequantize_q14(pred_q: torch.Tensor) -> torch.Tensor:
     """int16 -> float, `net_pred_int.float() / (2 ** 14)` (compute_score.py:111); exact"""
@@ -58,11 +89,15 @@ def score_dataset(net, dataset, metrics: Sequence[str] = ('psnr', 'ssim'), bound
     was_q = getattr(net, 'output_int16', False)
     net.output_int16 = True
     per_image = []
+    stage = _Stager()
     try:
         for start in range(lo, hi, batch_size):
-            items = [dataset[i] for i in range(start, min(start + batch_size, hi))]
-            burst = torch.stack([it[0] for it in items]).to(device, non_blocking=True)
-            gt = torch.stack([it[1] for it in items]).to(device, non_blocking=True).float().contiguous()
+            stop = min(start + batch_size, hi)
+            if hasattr(dataset, 'batch'):
+                burst, gt = (t.to(device, non_blocking=True) for t in dataset.batch(start, stop))
+            else:
+                burst, gt = stage([dataset[i] for i in range(start, stop)], device)
+            gt = gt.float().contiguous()
             if burst_sz is not None:
                 burst = burst[:, :burst_sz]
             pred_q, _ = net(burst.float().contiguous())

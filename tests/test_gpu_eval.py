@@ -47,6 +47,9 @@ def test_score_dataset_matches_per_image_protocol(dev):
             assert got['count'] == n and not net.output_int16
             assert abs(got['psnr'] - ref_psnr) <= tp, (precision, batch, got, ref_psnr)
             assert abs(got['ssim'] - ref_ssim) <= ts, (precision, batch, got, ref_ssim)
+    # a dataset without the contiguous-batch shortcut goes through the pinned double-buffered stager: same scores
+    items = [data[i] for i in range(n)]
+    assert score_dataset(net, items, batch_size=2, boundary_ignore=bi, device=dev) == score_dataset(net, data, batch_size=2, boundary_ignore=bi, device=dev)
     assert 'psnr' in generate_formatted_report({'dbsr': got})
     with pytest.raises(NotImplementedError):
         score_dataset(net, data, metrics=('lpips',), device=dev)
