@@ -292,6 +292,218 @@ __global__ void __launch_bounds__(CORR_THREADS, 2) corr81_kernel(const CorrParam
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// Tensor-core cost volume for bf16 feature maps (the `precision='bf16'` path), C in {32, 64, 96, 128}.
+// out[p, dy, dx] = sum_c f1[p, c] * f2[p + (dy, dx), c] is a BANDED product: for the 16 pixels of one tile row and the 24
+// halo pixels of row (y + dy), G = F1 (16 x C) * F2^T (C x 24) holds the 16 x 9 wanted values on its diagonals
+// (q - x = dx in 0..8), i.e. 37.5 % of G.  On CUDA cores the kernel above is instruction-bound (27.5 M warp instructions
+// for the level-2 shape, 41 % FFMA); here one warp = one dy computes G with 3 (n-tiles) x C/16 warp-level
+// mma.sync.m16n8k16 (bf16 in, fp32 accumulate) per tile row and scatters its accumulator fragments -- whose (row, column)
+// = (pixel, halo pixel) is known per lane -- straight into the displacement-major output staging tile; the vectorised
+// store epilogue is the one of corr81_kernel.  (tcgen05 would need the band extracted from TMEM, where a warp reads the
+// same columns for all 32 lanes: the register-fragment layout of mma.sync is what makes the diagonal scatter free.)
+// Both maps of the tile are staged ONCE for all channels as bf16 [pixel][C + 8] (pitch = 4 banks mod 32: the fragment
+// loads -- 8 pixels x 4 consecutive words per LDS.32 -- are conflict-free); the fused backwarp rounds the warped f2 tile
+// to bf16 (the operand type of the tensor core; same order as the bf16 rounding of the volume it produces).
+// ---------------------------------------------------------------------------------------------------------
+constexpr int OUT_PM = CT_H * CT_W + 4;
+template <int KS> struct CorrMma {
+  static constexpr int PITCH = KS * 16 + 8;                                  // bf16 elements per staged pixel
+  static constexpr int PW = PITCH / 2;                                       // 32-bit words per staged pixel
+  static constexpr int F2_BYTES = HALO_H * HALO_W * PITCH * 2;
+  static constexpr int F1_BYTES = CT_H * CT_W * PITCH * 2;
+  static constexpr int REC_BYTES = HALO_H * HALO_W * (int)sizeof(CorrRec);
+  static constexpr int OUT_BYTES = 81 * OUT_PM * (int)sizeof(float);
+  static constexpr int SMEM = F2_BYTES + F1_BYTES + REC_BYTES + OUT_BYTES;
+};
+
+template <int KS>
+__global__ void __launch_bounds__(CORR_THREADS, (CorrMma<KS>::SMEM <= 110 * 1024) ? 2 : 1) corr81_mma_kernel(const CorrParams p) {
+  using G = CorrMma<KS>;
+  griddep_wait();
+  extern __shared__ __align__(16) unsigned char smem_b[];
+  __nv_bfloat16* f2_s = reinterpret_cast<__nv_bfloat16*>(smem_b);                               // [HALO_H*HALO_W][PITCH]
+  __nv_bfloat16* f1_s = reinterpret_cast<__nv_bfloat16*>(smem_b + G::F2_BYTES);                 // [CT_H*CT_W][PITCH]
+  CorrRec* rec_s = reinterpret_cast<CorrRec*>(smem_b + G::F2_BYTES + G::F1_BYTES);              // [HALO_H*HALO_W]
+  float* out_s = reinterpret_cast<float*>(smem_b + G::F2_BYTES + G::F1_BYTES + G::REC_BYTES);   // [81][OUT_PM]
+
+  const int t = threadIdx.x;
+  const int lane = t & 31, dy = t >> 5;
+  const int pair = blockIdx.y;
+  const int ty0 = (blockIdx.x / p.tiles_x) * CT_H, tx0 = (blockIdx.x % p.tiles_x) * CT_W;
+  const int H = p.f1.h, W = p.f1.w, C = p.f1.c;
+  int i1 = pair, i2 = pair;
+  if (p.group > 0) {
+    const int b = pair / p.group;
+    i1 = b * (p.group + 1);
+    i2 = i1 + 1 + (pair - b * p.group);
+  }
+  const long long base1 = (long long)i1 * H * W, base2 = (long long)i2 * H * W, basef = (long long)pair * H * W;
+  const bool warp2 = p.flow.data != nullptr;
+  const float sxw = warp2 ? p.flow_scale * (float)W / (float)(W - 1) : 0.0f;
+  const float syh = warp2 ? p.flow_scale * (float)H / (float)(H - 1) : 0.0f;
+  const int th = min(CT_H, H - ty0);
+  const int hh = th + 8;
+
+  if (warp2) {      // backwarp records, as in corr81_kernel
+    for (int pix = t; pix < hh * HALO_W; pix += CORR_THREADS) {
+      const int y = ty0 - 4 + pix / HALO_W, x = tx0 - 4 + pix % HALO_W;
+      CorrRec r;
+      r.o[0] = r.o[1] = r.o[2] = r.o[3] = 0u;
+      r.w[0] = r.w[1] = r.w[2] = r.w[3] = 0.0f;
+      if (y >= 0 && y < H && x >= 0 && x < W) {
+        const long long fp = basef + (long long)y * W + x;
+        const float u = (float)x + view_ld(p.flow, fp, 0) * sxw;
+        const float w = (float)y + view_ld(p.flow, fp, 1) * syh;
+        const float fu = floorf(u), fv = floorf(w);
+        const float ax = u - fu, ay = w - fv;
+        const int xa = (int)fminf(fmaxf(fu, -2.0f), (float)W), ya = (int)fminf(fmaxf(fv, -2.0f), (float)H);
+        float m = 0.0f;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int xx = xa + (k & 1), yy = ya + (k >> 1);
+          const float wt = ((k & 1) ? ax : 1.0f - ax) * ((k >> 1) ? ay : 1.0f - ay);
+          if (xx >= 0 && xx < W && yy >= 0 && yy < H) {
+            r.o[k] = (uint32_t)(yy * W + xx) * (uint32_t)(p.f2.c_pitch * 2);
+            r.w[k] = wt;
+            m += wt;
+          }
+        }
+        if (!(m > 0.999f)) r.w[0] = r.w[1] = r.w[2] = r.w[3] = 0.0f;
+      }
+      rec_s[pix] = r;
+    }
+    __syncthreads();
+  }
+
+  // ---- staging: one task = one pixel x 8 channels = one 16-byte global load and one 16-byte shared store
+  constexpr int G8 = KS * 2;
+  // (C is a multiple of 16 here: no channel tail to mask; per-image offsets fit 32 bits, host-checked)
+  const __nv_bfloat16* b1 = reinterpret_cast<const __nv_bfloat16*>(p.f1.data) + p.f1.c_off + base1 * p.f1.c_pitch;
+  const __nv_bfloat16* b2 = reinterpret_cast<const __nv_bfloat16*>(p.f2.data) + p.f2.c_off + base2 * p.f2.c_pitch;
+  const unsigned char* b2b = reinterpret_cast<const unsigned char*>(b2);
+  for (int e = t; e < th * CT_W * G8; e += CORR_THREADS) {
+    const int g = e % G8, pix = e / G8;
+    const int y = ty0 + pix / CT_W, x = tx0 + pix % CT_W;
+    const int ch = g * 8;
+    uint4 q = make_uint4(0u, 0u, 0u, 0u);
+    if (x < W && ch < C) q = __ldg(reinterpret_cast<const uint4*>(b1 + (uint32_t)(y * W + x) * (uint32_t)p.f1.c_pitch + ch));
+    *reinterpret_cast<uint4*>(f1_s + pix * G::PITCH + ch) = q;
+  }
+  for (int e = t; e < hh * HALO_W * G8; e += CORR_THREADS) {
+    const int g = e % G8, pix = e / G8;
+    const int y = ty0 - 4 + pix / HALO_W, x = tx0 - 4 + pix % HALO_W;
+    const int ch = g * 8;
+    uint4 q = make_uint4(0u, 0u, 0u, 0u);
+    if (y >= 0 && y < H && x >= 0 && x < W && ch < C) {
+      if (!warp2) {
+        q = __ldg(reinterpret_cast<const uint4*>(b2 + (uint32_t)(y * W + x) * (uint32_t)p.f2.c_pitch + ch));
+      } else {
+        const uint4 ro = *reinterpret_cast<const uint4*>(rec_s[pix].o);
+        const float4 rw = *reinterpret_cast<const float4*>(rec_s[pix].w);
+        const uint32_t ok[4] = {ro.x, ro.y, ro.z, ro.w};
+        const float wk[4] = {rw.x, rw.y, rw.z, rw.w};
+        Vec8c v = vec8_zero();
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          if (wk[k] != 0.0f) {
+            const Vec8c a = vec8_ld<__nv_bfloat16>(reinterpret_cast<const __nv_bfloat16*>(b2b + ok[k]) + ch, 8);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v.v[i] = fmaf(a.v[i], wk[k], v.v[i]);
+          }
+        }
+        q = make_uint4(pack_bf16x2(v.v[0], v.v[1]), pack_bf16x2(v.v[2], v.v[3]), pack_bf16x2(v.v[4], v.v[5]), pack_bf16x2(v.v[6], v.v[7]));
+      }
+    }
+    *reinterpret_cast<uint4*>(f2_s + pix * G::PITCH + ch) = q;
+  }
+  __syncthreads();
+
+  // ---- banded product on the tensor cores: warp = dy, fragments straight from shared memory
+  const uint32_t* f1_w = reinterpret_cast<const uint32_t*>(f1_s);
+  const uint32_t* f2_w = reinterpret_cast<const uint32_t*>(f2_s);
+  const int gq = lane >> 2, tq = lane & 3;
+  // fragment element i of n-tile nt is (pixel x = gq + 8 (i >> 1), halo column q = 8 nt + 2 tq + (i & 1)): displacement
+  // dx = q - x, kept when 0 <= dx <= 8.  Offsets and the keep mask depend on the lane only, not on the tile row.
+  int sc_off[12];
+  uint32_t sc_keep = 0u;
+#pragma unroll
+  for (int nt = 0; nt < 3; ++nt)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int x = gq + 8 * (i >> 1);
+      const int dx = nt * 8 + 2 * tq + (i & 1) - x;
+      sc_off[nt * 4 + i] = (dy * 9 + dx) * OUT_PM + x;
+      if (dx >= 0 && dx <= 8) sc_keep |= 1u << (nt * 4 + i);
+    }
+  for (int row = 0; row < th; ++row) {
+    uint32_t a[KS][4];
+    const uint32_t* ap = f1_w + (row * CT_W + gq) * G::PW + tq;
+#pragma unroll
+    for (int ks = 0; ks < KS; ++ks) {
+      a[ks][0] = ap[ks * 8];
+      a[ks][1] = ap[8 * G::PW + ks * 8];
+      a[ks][2] = ap[ks * 8 + 4];
+      a[ks][3] = ap[8 * G::PW + ks * 8 + 4];
+    }
+#pragma unroll
+    for (int nt = 0; nt < 3; ++nt) {
+      float c0 = 0.0f, c1 = 0.0f, c2 = 0.0f, c3 = 0.0f;
+      const uint32_t* bp = f2_w + ((row + dy) * HALO_W + nt * 8 + gq) * G::PW + tq;
+#pragma unroll
+      for (int ks = 0; ks < KS; ++ks) {
+        const uint32_t b0 = bp[ks * 8], b1r = bp[ks * 8 + 4];
+        asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                     : "+f"(c0), "+f"(c1), "+f"(c2), "+f"(c3)
+                     : "r"(a[ks][0]), "r"(a[ks][1]), "r"(a[ks][2]), "r"(a[ks][3]), "r"(b0), "r"(b1r));
+      }
+      const float cv[4] = {c0, c1, c2, c3};
+      float* orow = out_s + row * CT_W;
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        if (sc_keep & (1u << (nt * 4 + i))) orow[sc_off[nt * 4 + i]] = cv[i];
+    }
+  }
+  __syncthreads();
+
+  // 1 / C and the activation are applied here, once per stored value: v > 0 ? v : slope * v
+  const float invC = 1.0f / (float)C;
+  const float slope = p.act == DBSR_ACT_LRELU ? 0.1f : (p.act == DBSR_ACT_RELU ? 0.0f : 1.0f);
+  if (p.vec_out) {
+    for (int e = t; e < 11 * CT_H * CT_W; e += CORR_THREADS) {
+      const int pix = e & (CT_H * CT_W - 1), g = e >> 7;
+      const int y = ty0 + pix / CT_W, x = tx0 + pix % CT_W;
+      if (y < H && x < W) {
+        float v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float r = (g * 8 + j < 81) ? out_s[(g * 8 + j) * OUT_PM + pix] * invC : 0.0f;
+          v[j] = r > 0.0f ? r : r * slope + 0.0f;          // (+ 0: ReLU of a negative value is +0, not -0)
+        }
+        const long long o = ((long long)pair * H * W + (long long)y * W + x) * p.out.c_pitch + p.out.c_off + g * 8;
+        if (p.out.dtype == DBSR_BF16) {
+          uint4 q;
+          q.x = pack_bf16x2(v[0], v[1]); q.y = pack_bf16x2(v[2], v[3]); q.z = pack_bf16x2(v[4], v[5]); q.w = pack_bf16x2(v[6], v[7]);
+          *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out.data) + o) = q;
+        } else {
+          float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out.data) + o);
+          dst[0] = make_float4(v[0], v[1], v[2], v[3]);
+          dst[1] = make_float4(v[4], v[5], v[6], v[7]);
+        }
+      }
+    }
+  } else {
+    for (int e = t; e < 81 * CT_H * CT_W; e += CORR_THREADS) {
+      const int pix = e & (CT_H * CT_W - 1), ch = e >> 7;
+      const int y = ty0 + pix / CT_W, x = tx0 + pix % CT_W;
+      if (y < H && x < W) {
+        const float r = out_s[ch * OUT_PM + pix] * invC;
+        view_st(p.out, (long long)pair * H * W + (long long)y * W + x, ch, r > 0.0f ? r : r * slope + 0.0f);
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // Small maps (H*W <= 64: pyramid levels 6..3 of the 48^2 .. 128^2 configs).  The tiled kernel above gives a 1x1 .. 8x8 map
 // one 8x16 tile of which a handful of threads own real pixels (9 threads for a 1x1 map: a serial latency chain).  Here
 // one CTA holds both whole maps of a pair in shared memory as [pixel][C] fp32 (the second one backwarped while it is
@@ -377,6 +589,12 @@ __global__ void __launch_bounds__(CORR_SMALL_THREADS) corr81_small_kernel(const 
 
 using namespace dbsr;
 
+static int g_corr_tensor_core = 1;
+extern "C" int dbsr_corr81_set_tensor_core(int32_t on) {
+  g_corr_tensor_core = on ? 1 : 0;
+  return 0;
+}
+
 extern "C" int dbsr_corr81(const dbsr_nhwc_t* f1, const dbsr_nhwc_t* f2, const dbsr_nhwc_t* flow, float flow_scale,
                            const dbsr_nhwc_t* out, int32_t pairs, int32_t group, int32_t act, void* stream) {
   DBSR_REQUIRE(view_ok(f1) && view_ok(f2) && view_ok(out), "corr81: bad views");
@@ -419,6 +637,28 @@ extern "C" int dbsr_corr81(const dbsr_nhwc_t* f1, const dbsr_nhwc_t* f2, const d
       configured[si] = small_smem;
     }
     launch_pdl(ks, dim3((unsigned)pairs), dim3(CORR_SMALL_THREADS), small_smem, (cudaStream_t)stream, p);
+    return check_launch("corr81");
+  }
+  // bf16 maps with C in {32, 64, 96, 128}: banded product on the tensor cores (mma.sync), see corr81_mma_kernel
+  if (vec && g_corr_tensor_core && f1->dtype == DBSR_BF16 && f1->c % 16 == 0 && f1->c >= 32 && f1->c <= 128 && f1->c != 48 &&
+      f1->c != 80 && f1->c != 112 && (long long)f1->h * f1->w * (f1->c_pitch > f2->c_pitch ? f1->c_pitch : f2->c_pitch) * 2 < (1ll << 31)) {
+    void (*km)(const CorrParams) = nullptr;
+    int smem = 0, ki = 0;
+    switch (f1->c / 16) {
+      case 2: km = corr81_mma_kernel<2>; smem = CorrMma<2>::SMEM; ki = 0; break;
+      case 4: km = corr81_mma_kernel<4>; smem = CorrMma<4>::SMEM; ki = 1; break;
+      case 6: km = corr81_mma_kernel<6>; smem = CorrMma<6>::SMEM; ki = 2; break;
+      default: km = corr81_mma_kernel<8>; smem = CorrMma<8>::SMEM; ki = 3; break;
+    }
+    static bool mma_attr[4] = {false, false, false, false};
+    if (!mma_attr[ki]) {
+      cudaError_t e = cudaFuncSetAttribute(km, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+      DBSR_REQUIRE(e == cudaSuccess, "corr81: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
+      e = cudaFuncSetAttribute(km, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+      DBSR_REQUIRE(e == cudaSuccess, "corr81: carve-out attribute failed: %s", cudaGetErrorString(e));
+      mma_attr[ki] = true;
+    }
+    launch_pdl(km, grid, dim3(CORR_THREADS), (size_t)smem, (cudaStream_t)stream, p);
     return check_launch("corr81");
   }
   void (*kern)(const CorrParams) = !vec ? corr81_kernel<false, float>

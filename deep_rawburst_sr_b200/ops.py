@@ -186,6 +186,11 @@ def corr81(f1: Act, f2: Act, out: Act, pairs: int, group: int = 0, flow: Optiona
     return out
 
 
+def corr81_set_tensor_core(on: bool) -> None:
+    """A/B switch of the bf16 cost volume: tensor-core banded product (default) vs the CUDA-core kernels"""
+    _lib.check(_lib.load_library().dbsr_corr81_set_tensor_core(1 if on else 0), 'dbsr_corr81_set_tensor_core')
+
+
 def copy_channels(src: Act, dst: Act, group: int = 0, src_group: int = 0, src_first: int = 0) -> Act:
     s, d = src.view(), dst.view()
     _lib.check(_lib.load_library().dbsr_copy_channels(ctypes.byref(s), ctypes.byref(d), group, src_group, src_first,

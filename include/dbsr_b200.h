@@ -159,6 +159,10 @@ int dbsr_deconv_col2im(const dbsr_nhwc_t* taps, const float* bias_t, const dbsr_
 /* -------------------------------------------------------------------------------------------------- */
 int dbsr_corr81(const dbsr_nhwc_t* f1, const dbsr_nhwc_t* f2, const dbsr_nhwc_t* flow, float flow_scale,
                 const dbsr_nhwc_t* out, int32_t pairs, int32_t group, int32_t act, void* stream);
+/* A/B switch (default 1): bf16 maps with C in {32, 64, 96, 128} larger than 8x8 run the banded product on the tensor cores
+ * (warp-level mma.sync, bf16 operands, fp32 accumulate; a fused backwarp rounds the warped map to bf16); 0 keeps every
+ * shape on the CUDA-core kernels (fp32 arithmetic on the bf16 inputs).                                              */
+int dbsr_corr81_set_tensor_core(int32_t on);
 
 /* flow head: replaces pwcnet.py:274-279.  flow4 [P, h4, w4, 2] fp32 -> offsets [P, 2, H, W] fp32 NCHW  */
 /*   offsets = 20 * bilinear_resize(flow4 -> (H, W)) * (W/Wp, H/Hp)                                     */

@@ -44,12 +44,13 @@ def test_missing_library_fails_loudly(tmp_path):
 
 def test_sass_has_blackwell_tensor_and_tma_instructions():
     """The built cubin must contain tcgen05 MMA (UTCHMMA), TMEM loads (LDTM), TMA loads (UTMALDG), the TMA tensor stores of the
-    conv epilogue (UTMASTG) and the asynchronous copies of the fused warp + softmax kernel (LDGSTS)."""
+    conv epilogue (UTMASTG), the asynchronous copies of the fused warp + softmax kernel (LDGSTS) and the warp-level bf16 MMA of the
+    banded cost-volume product (HMMA.16816)."""
     import shutil
     import subprocess
     cuobjdump = shutil.which('cuobjdump') or '/usr/local/cuda/bin/cuobjdump'
     if not os.path.exists(cuobjdump):
         pytest.skip('cuobjdump not available')
     sass = subprocess.run([cuobjdump, '-sass', build_library()], capture_output=True, text=True).stdout
-    for mnemonic in ('UTCHMMA', 'LDTM', 'UTMALDG', 'UTMASTG', 'LDGSTS'):
+    for mnemonic in ('UTCHMMA', 'LDTM', 'UTMALDG', 'UTMASTG', 'LDGSTS', 'HMMA.16816.F32.BF16'):
         assert mnemonic in sass, mnemonic

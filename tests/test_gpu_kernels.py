@@ -243,7 +243,66 @@ def test_corr81_bf16_vectorised_staging(dev, c, h, w, mag):
         ops.corr81(act_bf16(f1), act_bf16(f2), out, pairs=3, group=0, flow=_act_from(flow, dev), flow_scale=1.25,
                    act=ops.ACT_LRELU)
         err = (out.to_nchw().cpu() - ref).abs()
+        # tensor-core path (C in {32, 64, 96, 128}, map > 8x8): the warped map is rounded to bf16 (relative 2^-9 per value)
+        f2w = O.backwarp(f2, flow * 1.25)
+        bound = 5e-5 + 2.0 ** -9 * O.correlation81(f1.abs(), f2w.abs())
+        assert (err > bound).any(dim=1).float().mean() < 0.01, float(err.max())
+        ops.corr81_set_tensor_core(False)          # CUDA-core kernels: fp32 arithmetic on the bf16 inputs
+        try:
+            ops.corr81(act_bf16(f1), act_bf16(f2), out, pairs=3, group=0, flow=_act_from(flow, dev), flow_scale=1.25,
+                       act=ops.ACT_LRELU)
+        finally:
+            ops.corr81_set_tensor_core(True)
+        err = (out.to_nchw().cpu() - ref).abs()
         assert (err > 5e-5).any(dim=1).float().mean() < 0.01, float(err.max())
+
+
+@pytest.mark.parametrize('c,h,w,mag', [(32, 32, 24, 0.0), (32, 32, 24, 5.0), (64, 16, 16, 3.0), (96, 12, 12, 2.0), (128, 9, 9, 1.5),
+                                       (32, 13, 21, 8.0), (64, 48, 48, 0.0), (32, 10, 7, 0.0)])
+def test_corr81_tensor_core_banded_product(dev, c, h, w, mag):
+    """bf16 cost volume on the tensor cores (corr81_mma_kernel: mma.sync m16n8k16, diagonal scatter of the accumulator
+    fragments): full / ragged tiles, every supported channel count, burst pair -> image mapping, fused backwarp, bf16 volume
+    written into its concat slice.  Without a flow the products of bf16 values are exact and only the fp32 summation order
+    differs from the oracle (<= 2e-5); with a flow the warped map is rounded to bf16: |err| <= 2^-9 * mean_c |f1||f2w|."""
+    from deep_rawburst_sr_b200 import ops
+    g = _gen(c * 7 + h + w)
+    B, N = 2, 3
+    feats = torch.randn(B * N, c, h, w, generator=g).bfloat16().float()
+    f1 = feats.view(B, N, c, h, w)[:, :1].expand(-1, N - 1, -1, -1, -1).reshape(-1, c, h, w)
+    f2 = feats.view(B, N, c, h, w)[:, 1:].reshape(-1, c, h, w)
+    P = B * (N - 1)
+    buf = torch.full((B * N, h, w, c + 8), 7.0, dtype=torch.bfloat16, device=dev)          # poison behind the channels
+    buf[..., :c] = feats.permute(0, 2, 3, 1).to(dev).bfloat16()
+    fa = ops.Act(buf).slice(0, c)
+    out = ops.Act.empty(P, h, w, 88, torch.float32, dev, zero=True).slice(0, 81)
+    if mag > 0:
+        flow = (torch.rand(P, 2, h, w, generator=g) * 2 - 1) * mag
+        f2w = O.backwarp(f2, flow * 2.5)
+        ref = O.lrelu(O.correlation81(f1, f2w))
+        bound = 5e-5 + 2.0 ** -9 * O.correlation81(f1.abs(), f2w.abs())
+        kw = dict(flow=_act_from(flow, dev), flow_scale=2.5)
+    else:
+        ref = O.lrelu(O.correlation81(f1, f2))
+        bound = torch.full_like(ref, 2e-5)
+        kw = {}
+    ops.corr81(fa, fa, out, pairs=P, group=N - 1, act=ops.ACT_LRELU, **kw)
+    got = out.to_nchw().cpu()
+    err = (got - ref).abs()
+    assert (err > bound).any(dim=1).float().mean() < (0.01 if mag > 0 else 1e-9), float(err.max())
+    # A/B against the CUDA-core kernel on the same inputs
+    ops.corr81_set_tensor_core(False)
+    try:
+        out2 = ops.Act.empty(P, h, w, 88, torch.float32, dev, zero=True).slice(0, 81)
+        ops.corr81(fa, fa, out2, pairs=P, group=N - 1, act=ops.ACT_LRELU, **kw)
+    finally:
+        ops.corr81_set_tensor_core(True)
+    d = (out2.to_nchw().cpu() - got).abs()
+    assert (d > bound).any(dim=1).float().mean() < (0.01 if mag > 0 else 1e-9), float(d.max())
+    # bf16 volume into an 8-aligned concat slice: neighbours untouched, pad channels zeroed, deterministic
+    cat = torch.full((P, h, w, 104), 3.0, dtype=torch.bfloat16, device=dev)
+    ops.corr81(fa, fa, ops.Act(cat).slice(8, 81), pairs=P, group=N - 1, act=ops.ACT_LRELU, **kw)
+    assert torch.equal(cat[..., 8:89].float().permute(0, 3, 1, 2).cpu(), got.bfloat16().float())
+    assert (cat[..., :8] == 3.0).all() and (cat[..., 96:] == 3.0).all() and (cat[..., 89:96] == 0).all()
 
 
 def test_corr81_golden_reference_vector(dev, golden_dir):
