@@ -316,6 +316,12 @@ template <int KS> struct CorrMma {
   static constexpr int SMEM = F2_BYTES + F1_BYTES + REC_BYTES + OUT_BYTES;
 };
 
+__device__ __forceinline__ void cp_async16_zfill(void* dst_smem, const void* src, bool valid) {
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst_smem);
+  const int n = valid ? 16 : 0;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(src), "r"(n) : "memory");
+}
+
 template <int KS>
 __global__ void __launch_bounds__(CORR_THREADS, (CorrMma<KS>::SMEM <= 110 * 1024) ? 2 : 1) corr81_mma_kernel(const CorrParams p) {
   using G = CorrMma<KS>;
@@ -381,41 +387,47 @@ __global__ void __launch_bounds__(CORR_THREADS, (CorrMma<KS>::SMEM <= 110 * 1024
   const __nv_bfloat16* b1 = reinterpret_cast<const __nv_bfloat16*>(p.f1.data) + p.f1.c_off + base1 * p.f1.c_pitch;
   const __nv_bfloat16* b2 = reinterpret_cast<const __nv_bfloat16*>(p.f2.data) + p.f2.c_off + base2 * p.f2.c_pitch;
   const unsigned char* b2b = reinterpret_cast<const unsigned char*>(b2);
+  // plain copies go through cp.async (16 bytes, zero-filled when the pixel is outside the map: src-size 0), so that all
+  // of a thread's loads are in flight at once instead of one load -> store round trip per task
   for (int e = t; e < th * CT_W * G8; e += CORR_THREADS) {
     const int g = e % G8, pix = e / G8;
     const int y = ty0 + pix / CT_W, x = tx0 + pix % CT_W;
-    const int ch = g * 8;
-    uint4 q = make_uint4(0u, 0u, 0u, 0u);
-    if (x < W && ch < C) q = __ldg(reinterpret_cast<const uint4*>(b1 + (uint32_t)(y * W + x) * (uint32_t)p.f1.c_pitch + ch));
-    *reinterpret_cast<uint4*>(f1_s + pix * G::PITCH + ch) = q;
+    const bool in = x < W;
+    cp_async16_zfill(f1_s + pix * G::PITCH + g * 8, b1 + (in ? (uint32_t)(y * W + x) * (uint32_t)p.f1.c_pitch + g * 8 : 0u), in);
   }
-  for (int e = t; e < hh * HALO_W * G8; e += CORR_THREADS) {
-    const int g = e % G8, pix = e / G8;
-    const int y = ty0 - 4 + pix / HALO_W, x = tx0 - 4 + pix % HALO_W;
-    const int ch = g * 8;
-    uint4 q = make_uint4(0u, 0u, 0u, 0u);
-    if (y >= 0 && y < H && x >= 0 && x < W && ch < C) {
-      if (!warp2) {
-        q = __ldg(reinterpret_cast<const uint4*>(b2 + (uint32_t)(y * W + x) * (uint32_t)p.f2.c_pitch + ch));
-      } else {
-        const uint4 ro = *reinterpret_cast<const uint4*>(rec_s[pix].o);
-        const float4 rw = *reinterpret_cast<const float4*>(rec_s[pix].w);
-        const uint32_t ok[4] = {ro.x, ro.y, ro.z, ro.w};
-        const float wk[4] = {rw.x, rw.y, rw.z, rw.w};
-        Vec8c v = vec8_zero();
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          if (wk[k] != 0.0f) {
-            const Vec8c a = vec8_ld<__nv_bfloat16>(reinterpret_cast<const __nv_bfloat16*>(b2b + ok[k]) + ch, 8);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) v.v[i] = fmaf(a.v[i], wk[k], v.v[i]);
-          }
-        }
-        q = make_uint4(pack_bf16x2(v.v[0], v.v[1]), pack_bf16x2(v.v[2], v.v[3]), pack_bf16x2(v.v[4], v.v[5]), pack_bf16x2(v.v[6], v.v[7]));
-      }
+  if (!warp2) {
+    for (int e = t; e < hh * HALO_W * G8; e += CORR_THREADS) {
+      const int g = e % G8, pix = e / G8;
+      const int y = ty0 - 4 + pix / HALO_W, x = tx0 - 4 + pix % HALO_W;
+      const bool in = y >= 0 && y < H && x >= 0 && x < W;
+      cp_async16_zfill(f2_s + pix * G::PITCH + g * 8, b2 + (in ? (uint32_t)(y * W + x) * (uint32_t)p.f2.c_pitch + g * 8 : 0u), in);
     }
-    *reinterpret_cast<uint4*>(f2_s + pix * G::PITCH + ch) = q;
+  } else {
+    // fused backwarp: the four taps are loaded unconditionally (a zero-weight tap points at pixel 0 of the image), so
+    // the loads of a task -- and, unrolled by two, of the next one -- are issued back to back
+#pragma unroll 2
+    for (int e = t; e < hh * HALO_W * G8; e += CORR_THREADS) {
+      const int g = e % G8, pix = e / G8;
+      const uint4 ro = *reinterpret_cast<const uint4*>(rec_s[pix].o);
+      const float4 rw = *reinterpret_cast<const float4*>(rec_s[pix].w);
+      const unsigned char* src = b2b + g * 16;
+      const uint4 q0 = __ldg(reinterpret_cast<const uint4*>(src + ro.x)), q1 = __ldg(reinterpret_cast<const uint4*>(src + ro.y));
+      const uint4 q2 = __ldg(reinterpret_cast<const uint4*>(src + ro.z)), q3 = __ldg(reinterpret_cast<const uint4*>(src + ro.w));
+      const uint32_t w0[4] = {q0.x, q0.y, q0.z, q0.w}, w1[4] = {q1.x, q1.y, q1.z, q1.w};
+      const uint32_t w2[4] = {q2.x, q2.y, q2.z, q2.w}, w3[4] = {q3.x, q3.y, q3.z, q3.w};
+      uint32_t o[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        float lo = __uint_as_float(w0[i] << 16) * rw.x, hi = __uint_as_float(w0[i] & 0xFFFF0000u) * rw.x;
+        lo = fmaf(__uint_as_float(w1[i] << 16), rw.y, lo); hi = fmaf(__uint_as_float(w1[i] & 0xFFFF0000u), rw.y, hi);
+        lo = fmaf(__uint_as_float(w2[i] << 16), rw.z, lo); hi = fmaf(__uint_as_float(w2[i] & 0xFFFF0000u), rw.z, hi);
+        lo = fmaf(__uint_as_float(w3[i] << 16), rw.w, lo); hi = fmaf(__uint_as_float(w3[i] & 0xFFFF0000u), rw.w, hi);
+        o[i] = pack_bf16x2(lo, hi);
+      }
+      *reinterpret_cast<uint4*>(f2_s + pix * G::PITCH + g * 8) = make_uint4(o[0], o[1], o[2], o[3]);
+    }
   }
+  asm volatile("cp.async.commit_group;\n cp.async.wait_group 0;" ::: "memory");
   __syncthreads();
 
   // ---- banded product on the tensor cores: warp = dy, fragments straight from shared memory

@@ -22,7 +22,9 @@ f2 = padded(torch.randn(P, h, h, C, generator=g), dt)
 vol = Act.empty(P, h, h, 88, dt, dev, zero=True).slice(0, 81)
 flow = padded((torch.rand(P, h, h, 2, generator=g) * 2 - 1) * 0.5, torch.float32) if warp else None
 evs = []
+flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
 for i in range(5):
+    flush.zero_()      # ~100 us of queued GPU work: the host runs ahead, the events bracket the kernel and not the Python launch path
     s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     s.record(); ops.corr81(f1, f2, vol, P, 0, flow=flow, flow_scale=1.0 if warp else 0.0, act=ACT_LRELU); e.record(); evs.append((s, e))
 torch.cuda.synchronize()
