@@ -305,7 +305,8 @@ __global__ void __launch_bounds__(CORR_THREADS, 2) corr81_kernel(const CorrParam
 // loads -- 8 pixels x 4 consecutive words per LDS.32 -- are conflict-free); the fused backwarp rounds the warped f2 tile
 // to bf16 (the operand type of the tensor core; same order as the bf16 rounding of the volume it produces).
 // ---------------------------------------------------------------------------------------------------------
-constexpr int OUT_PM = CT_H * CT_W + 4;
+constexpr int MMA_ROWS = 4;                          // tile rows per output phase (two phases per 8-row tile)
+constexpr int OUT_PM = MMA_ROWS * CT_W + 4;          // displacement-major staging tile [81][OUT_PM] of one phase
 template <int KS> struct CorrMma {
   static constexpr int PITCH = KS * 16 + 8;                                  // bf16 elements per staged pixel
   static constexpr int PW = PITCH / 2;                                       // 32-bit words per staged pixel
@@ -313,7 +314,8 @@ template <int KS> struct CorrMma {
   static constexpr int F1_BYTES = CT_H * CT_W * PITCH * 2;
   static constexpr int REC_BYTES = HALO_H * HALO_W * (int)sizeof(CorrRec);
   static constexpr int OUT_BYTES = 81 * OUT_PM * (int)sizeof(float);
-  static constexpr int SMEM = F2_BYTES + F1_BYTES + REC_BYTES + OUT_BYTES;
+  // the output staging tile reuses the backwarp records' storage (the records are dead once the f2 tile is staged)
+  static constexpr int SMEM = F2_BYTES + F1_BYTES + (REC_BYTES > OUT_BYTES ? REC_BYTES : OUT_BYTES);
 };
 
 __device__ __forceinline__ void cp_async16_zfill(void* dst_smem, const void* src, bool valid) {
@@ -323,14 +325,14 @@ __device__ __forceinline__ void cp_async16_zfill(void* dst_smem, const void* src
 }
 
 template <int KS>
-__global__ void __launch_bounds__(CORR_THREADS, (CorrMma<KS>::SMEM <= 110 * 1024) ? 2 : 1) corr81_mma_kernel(const CorrParams p) {
+__global__ void __launch_bounds__(CORR_THREADS, (CorrMma<KS>::SMEM <= 74 * 1024) ? 3 : ((CorrMma<KS>::SMEM <= 110 * 1024) ? 2 : 1)) corr81_mma_kernel(const CorrParams p) {
   using G = CorrMma<KS>;
   griddep_wait();
   extern __shared__ __align__(16) unsigned char smem_b[];
   __nv_bfloat16* f2_s = reinterpret_cast<__nv_bfloat16*>(smem_b);                               // [HALO_H*HALO_W][PITCH]
   __nv_bfloat16* f1_s = reinterpret_cast<__nv_bfloat16*>(smem_b + G::F2_BYTES);                 // [CT_H*CT_W][PITCH]
   CorrRec* rec_s = reinterpret_cast<CorrRec*>(smem_b + G::F2_BYTES + G::F1_BYTES);              // [HALO_H*HALO_W]
-  float* out_s = reinterpret_cast<float*>(smem_b + G::F2_BYTES + G::F1_BYTES + G::REC_BYTES);   // [81][OUT_PM]
+  float* out_s = reinterpret_cast<float*>(rec_s);                                               // [81][OUT_PM], after staging
 
   const int t = threadIdx.x;
   const int lane = t & 31, dy = t >> 5;
@@ -447,71 +449,75 @@ __global__ void __launch_bounds__(CORR_THREADS, (CorrMma<KS>::SMEM <= 110 * 1024
       sc_off[nt * 4 + i] = (dy * 9 + dx) * OUT_PM + x;
       if (dx >= 0 && dx <= 8) sc_keep |= 1u << (nt * 4 + i);
     }
-  for (int row = 0; row < th; ++row) {
-    uint32_t a[KS][4];
-    const uint32_t* ap = f1_w + (row * CT_W + gq) * G::PW + tq;
-#pragma unroll
-    for (int ks = 0; ks < KS; ++ks) {
-      a[ks][0] = ap[ks * 8];
-      a[ks][1] = ap[8 * G::PW + ks * 8];
-      a[ks][2] = ap[ks * 8 + 4];
-      a[ks][3] = ap[8 * G::PW + ks * 8 + 4];
-    }
-#pragma unroll
-    for (int nt = 0; nt < 3; ++nt) {
-      float c0 = 0.0f, c1 = 0.0f, c2 = 0.0f, c3 = 0.0f;
-      const uint32_t* bp = f2_w + ((row + dy) * HALO_W + nt * 8 + gq) * G::PW + tq;
-#pragma unroll
-      for (int ks = 0; ks < KS; ++ks) {
-        const uint32_t b0 = bp[ks * 8], b1r = bp[ks * 8 + 4];
-        asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-                     : "+f"(c0), "+f"(c1), "+f"(c2), "+f"(c3)
-                     : "r"(a[ks][0]), "r"(a[ks][1]), "r"(a[ks][2]), "r"(a[ks][3]), "r"(b0), "r"(b1r));
-      }
-      const float cv[4] = {c0, c1, c2, c3};
-      float* orow = out_s + row * CT_W;
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-        if (sc_keep & (1u << (nt * 4 + i))) orow[sc_off[nt * 4 + i]] = cv[i];
-    }
-  }
-  __syncthreads();
-
-  // 1 / C and the activation are applied here, once per stored value: v > 0 ? v : slope * v
+  // 1 / C and the activation are applied in the store loop, once per stored value: v > 0 ? v : slope * v
   const float invC = 1.0f / (float)C;
   const float slope = p.act == DBSR_ACT_LRELU ? 0.1f : (p.act == DBSR_ACT_RELU ? 0.0f : 1.0f);
-  if (p.vec_out) {
-    for (int e = t; e < 11 * CT_H * CT_W; e += CORR_THREADS) {
-      const int pix = e & (CT_H * CT_W - 1), g = e >> 7;
-      const int y = ty0 + pix / CT_W, x = tx0 + pix % CT_W;
-      if (y < H && x < W) {
-        float v[8];
+  // two phases of MMA_ROWS tile rows: product + scatter into the staging tile, then the coalesced stores of those rows
+  for (int r0 = 0; r0 < th; r0 += MMA_ROWS) {
+    const int r1 = min(th, r0 + MMA_ROWS);
+    for (int row = r0; row < r1; ++row) {
+      uint32_t a[KS][4];
+      const uint32_t* ap = f1_w + (row * CT_W + gq) * G::PW + tq;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float r = (g * 8 + j < 81) ? out_s[(g * 8 + j) * OUT_PM + pix] * invC : 0.0f;
-          v[j] = r > 0.0f ? r : r * slope + 0.0f;          // (+ 0: ReLU of a negative value is +0, not -0)
+      for (int ks = 0; ks < KS; ++ks) {
+        a[ks][0] = ap[ks * 8];
+        a[ks][1] = ap[8 * G::PW + ks * 8];
+        a[ks][2] = ap[ks * 8 + 4];
+        a[ks][3] = ap[8 * G::PW + ks * 8 + 4];
+      }
+#pragma unroll
+      for (int nt = 0; nt < 3; ++nt) {
+        float c0 = 0.0f, c1 = 0.0f, c2 = 0.0f, c3 = 0.0f;
+        const uint32_t* bp = f2_w + ((row + dy) * HALO_W + nt * 8 + gq) * G::PW + tq;
+#pragma unroll
+        for (int ks = 0; ks < KS; ++ks) {
+          const uint32_t b0 = bp[ks * 8], b1r = bp[ks * 8 + 4];
+          asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                       : "+f"(c0), "+f"(c1), "+f"(c2), "+f"(c3)
+                       : "r"(a[ks][0]), "r"(a[ks][1]), "r"(a[ks][2]), "r"(a[ks][3]), "r"(b0), "r"(b1r));
         }
-        const long long o = ((long long)pair * H * W + (long long)y * W + x) * p.out.c_pitch + p.out.c_off + g * 8;
-        if (p.out.dtype == DBSR_BF16) {
-          uint4 q;
-          q.x = pack_bf16x2(v[0], v[1]); q.y = pack_bf16x2(v[2], v[3]); q.z = pack_bf16x2(v[4], v[5]); q.w = pack_bf16x2(v[6], v[7]);
-          *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out.data) + o) = q;
-        } else {
-          float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out.data) + o);
-          dst[0] = make_float4(v[0], v[1], v[2], v[3]);
-          dst[1] = make_float4(v[4], v[5], v[6], v[7]);
+        const float cv[4] = {c0, c1, c2, c3};
+        float* orow = out_s + (row - r0) * CT_W;
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          if (sc_keep & (1u << (nt * 4 + i))) orow[sc_off[nt * 4 + i]] = cv[i];
+      }
+    }
+    __syncthreads();
+    if (p.vec_out) {
+      for (int e = t; e < 11 * MMA_ROWS * CT_W; e += CORR_THREADS) {
+        const int pix = e & (MMA_ROWS * CT_W - 1), g = e / (MMA_ROWS * CT_W);
+        const int y = ty0 + r0 + pix / CT_W, x = tx0 + pix % CT_W;
+        if (y < H && x < W) {
+          float v[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float r = (g * 8 + j < 81) ? out_s[(g * 8 + j) * OUT_PM + pix] * invC : 0.0f;
+            v[j] = r > 0.0f ? r : r * slope + 0.0f;          // (+ 0: ReLU of a negative value is +0, not -0)
+          }
+          const long long o = ((long long)pair * H * W + (long long)y * W + x) * p.out.c_pitch + p.out.c_off + g * 8;
+          if (p.out.dtype == DBSR_BF16) {
+            uint4 q;
+            q.x = pack_bf16x2(v[0], v[1]); q.y = pack_bf16x2(v[2], v[3]); q.z = pack_bf16x2(v[4], v[5]); q.w = pack_bf16x2(v[6], v[7]);
+            *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out.data) + o) = q;
+          } else {
+            float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out.data) + o);
+            dst[0] = make_float4(v[0], v[1], v[2], v[3]);
+            dst[1] = make_float4(v[4], v[5], v[6], v[7]);
+          }
+        }
+      }
+    } else {
+      for (int e = t; e < 81 * MMA_ROWS * CT_W; e += CORR_THREADS) {
+        const int pix = e & (MMA_ROWS * CT_W - 1), ch = e / (MMA_ROWS * CT_W);
+        const int y = ty0 + r0 + pix / CT_W, x = tx0 + pix % CT_W;
+        if (y < H && x < W) {
+          const float r = out_s[ch * OUT_PM + pix] * invC;
+          view_st(p.out, (long long)pair * H * W + (long long)y * W + x, ch, r > 0.0f ? r : r * slope + 0.0f);
         }
       }
     }
-  } else {
-    for (int e = t; e < 81 * CT_H * CT_W; e += CORR_THREADS) {
-      const int pix = e & (CT_H * CT_W - 1), ch = e >> 7;
-      const int y = ty0 + pix / CT_W, x = tx0 + pix % CT_W;
-      if (y < H && x < W) {
-        const float r = out_s[ch * OUT_PM + pix] * invC;
-        view_st(p.out, (long long)pair * H * W + (long long)y * W + x, ch, r > 0.0f ? r : r * slope + 0.0f);
-      }
-    }
+    __syncthreads();                                // the staging tile is rewritten by the next phase
   }
 }
 
