@@ -449,9 +449,10 @@ __global__ void __launch_bounds__(CORR_THREADS, (CorrMma<KS>::SMEM <= 74 * 1024)
       sc_off[nt * 4 + i] = (dy * 9 + dx) * OUT_PM + x;
       if (dx >= 0 && dx <= 8) sc_keep |= 1u << (nt * 4 + i);
     }
-  // 1 / C and the activation are applied in the store loop, once per stored value: v > 0 ? v : slope * v
+  // 1 / C and the activation are applied in the store loop, once per stored value: max(v, slope * v) with slope <= 1
+  // (ReLU 0, LeakyReLU 0.1, none 1); the "+ 0" turns the -0 of 0 * negative into +0
   const float invC = 1.0f / (float)C;
-  const float slope = p.act == DBSR_ACT_LRELU ? 0.1f : (p.act == DBSR_ACT_RELU ? 0.0f : 1.0f);
+  const float invCs = invC * (p.act == DBSR_ACT_LRELU ? 0.1f : (p.act == DBSR_ACT_RELU ? 0.0f : 1.0f));
   // two phases of MMA_ROWS tile rows: product + scatter into the staging tile, then the coalesced stores of those rows
   for (int r0 = 0; r0 < th; r0 += MMA_ROWS) {
     const int r1 = min(th, r0 + MMA_ROWS);
@@ -492,8 +493,8 @@ __global__ void __launch_bounds__(CORR_THREADS, (CorrMma<KS>::SMEM <= 74 * 1024)
           float v[8];
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
-            const float r = (g * 8 + j < 81) ? out_s[(g * 8 + j) * OUT_PM + pix] * invC : 0.0f;
-            v[j] = r > 0.0f ? r : r * slope + 0.0f;          // (+ 0: ReLU of a negative value is +0, not -0)
+            const float r = (g * 8 + j < 81) ? out_s[(g * 8 + j) * OUT_PM + pix] : 0.0f;
+            v[j] = fmaxf(r * invC, fmaf(r, invCs, 0.0f));
           }
           const long long o = ((long long)pair * H * W + (long long)y * W + x) * p.out.c_pitch + p.out.c_off + g * 8;
           if (p.out.dtype == DBSR_BF16) {
@@ -512,8 +513,8 @@ __global__ void __launch_bounds__(CORR_THREADS, (CorrMma<KS>::SMEM <= 74 * 1024)
         const int pix = e & (MMA_ROWS * CT_W - 1), ch = e / (MMA_ROWS * CT_W);
         const int y = ty0 + r0 + pix / CT_W, x = tx0 + pix % CT_W;
         if (y < H && x < W) {
-          const float r = out_s[ch * OUT_PM + pix] * invC;
-          view_st(p.out, (long long)pair * H * W + (long long)y * W + x, ch, r > 0.0f ? r : r * slope + 0.0f);
+          const float r = out_s[ch * OUT_PM + pix];
+          view_st(p.out, (long long)pair * H * W + (long long)y * W + x, ch, fmaxf(r * invC, fmaf(r, invCs, 0.0f)));
         }
       }
     }
