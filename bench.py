@@ -145,7 +145,11 @@ def cpu_reference_arm(args, rank):
         'impl': 'reference', 'metric': 'bursts/sec (14-frame, 4x SR)', 'value': val, 'unit': 'bursts/s',
         'n_gpus': args.gpus, 'steps': steps, 'warmup': args.warmup, 'ms_per_step': dt * 1e3, 'higher_is_better': True,
         'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-        'config': {'workload': f'DBSRNet forward, bursts of {FRAMES}x4x{args.size}x{args.size} -> 3x{8 * args.size}x{8 * args.size}, random-init weights'},
+        # the product arm's config (same workload string); each step is a bounded sample of it: ONE of its bursts
+        'config': {'workload': f'DBSRNet forward, {args.batch} bursts/GPU of {FRAMES}x4x{args.size}x{args.size} packed RAW -> '
+                               f'3x{8 * args.size}x{8 * args.size}, random-init weights (BASELINE.json configs[1])',
+                   'global_batch': args.batch * args.gpus, 'parallelism': 'host CPU threads (torch intra-op), one burst per step',
+                   'sample': sample},
         'cpu_baseline': {'value': val, 'unit': 'bursts/s', 'cores': cores, 'kind': 'port', 'sample': sample},
         'e2e': {'value': val, 'unit': 'bursts/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
     }))
