@@ -68,10 +68,10 @@ PROTOTYPES = {
     'dbsr_blur3x3': (_I, [_PV, _PV, ctypes.POINTER(ctypes.c_float), _VP]),
     'dbsr_predictor': (_I, [_PV, _VP, _VP, _I, _VP, _VP]),
     'dbsr_ssim_workspace_floats': (_I, [_I, _I, _I, _I, _I, _I]),
-    'dbsr_ssim': (_I, [_VP, _VP, _I, _I, _I, _I, _I, ctypes.POINTER(ctypes.c_float), _I, _F, _VP, _VP, _VP, _VP]),
+    'dbsr_ssim': (_I, [_VP, _VP, _I, _I, _I, _I, _I, ctypes.POINTER(ctypes.c_float), _I, _F, _VP, _VP, _VP, _VP, _VP]),
     'dbsr_avgpool2_pair': (_I, [_VP, _VP, _VP, _VP, _I, _I, _I, _VP]),
     'dbsr_mse_workspace_floats': (_I, [_I]),
-    'dbsr_mse_per_image': (_I, [_VP, _VP, _I, _I, _I, _I, _I, _VP, _VP, _VP]),
+    'dbsr_mse_per_image': (_I, [_VP, _VP, _VP, _I, _I, _I, _I, _I, _VP, _VP, _VP]),
 }
 
 _lock = threading.Lock()

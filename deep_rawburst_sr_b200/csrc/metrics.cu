@@ -23,6 +23,8 @@ struct SsimParams {
   float* map;              // optional [planes, oh, ow] ssim map (spatial_out), may be null
   float* partial;          // [planes * tiles_y * tiles_x][2]  (sum ssim, sum cs) per CTA
   const float* range_ws;   // [RANGE_BLOCKS][2] (max, min) of img1, read when val_range <= 0
+  const unsigned char* valid;   // optional [n, 1, H, W] mask: sums become (sum ssim * valid, sum valid), see dbsr_ssim
+  int c;                   // channels per image (plane -> image for the mask)
   int H, W, crop, oh, ow;
   float val_range;
   float g[SS_MAXW];        // 1-D Gaussian (sigma 1.5, normalised), zero beyond the real window size
@@ -186,8 +188,14 @@ __global__ void __launch_bounds__(SS_THREADS) ssim_tile_kernel(const SsimParams 
       const float num = __fmul_rn(__fadd_rn(__fmul_rn(2.0f, mu12), C1), v1);
       const float den = __fmul_rn(__fadd_rn(__fadd_rn(mu1_sq, mu2_sq), C1), v2);
       const float ss = __fdiv_rn(num, den);
-      sum_ssim += ss;
-      sum_cs += cs;
+      if (p.valid) {      // image_quality_v2.py:127-131: the mask is cropped like the images, then by 5 (window 11)
+        const float m = p.valid[((long long)(plane / p.c) * p.H + p.crop + 5 + oy) * p.W + p.crop + 5 + ox] ? 1.0f : 0.0f;
+        sum_ssim += ss * m;
+        sum_cs += m;
+      } else {
+        sum_ssim += ss;
+        sum_cs += cs;
+      }
       if (p.map) p.map[((long long)plane * p.oh + oy) * p.ow + ox] = ss;
     }
   }
@@ -247,31 +255,43 @@ __global__ void __launch_bounds__(256) avgpool2_pair_kernel(const float* __restr
 }
 
 // per-image sum of squared differences over the cropped planes (image_quality_v2.py:47-66 with metric 'l2', valid=None)
-__global__ void __launch_bounds__(256) sq_err_kernel(const float* __restrict__ a, const float* __restrict__ b, int c, int H, int W, int crop,
-                                                     float* __restrict__ partial) {
+__global__ void __launch_bounds__(256) sq_err_kernel(const float* __restrict__ a, const float* __restrict__ b, const unsigned char* __restrict__ valid,
+                                                     int c, int H, int W, int crop, float* __restrict__ partial) {
   griddep_wait();
   const int hc = H - 2 * crop, wc = W - 2 * crop;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int image = blockIdx.y;
   const int rows = c * hc;
-  float acc = 0.0f;
+  float acc = 0.0f, cnt = 0.0f;
   for (int r = blockIdx.x * 8 + warp; r < rows; r += gridDim.x * 8) {
     const int pl = r / hc, y = r - pl * hc + crop;
     const long long off = (((long long)image * c + pl) * H + y) * W + crop;
+    const unsigned char* vrow = valid ? valid + ((long long)image * H + y) * W + crop : nullptr;
     for (int x = lane; x < wc; x += 32) {
       const float d = __ldg(a + off + x) - __ldg(b + off + x);
-      acc = fmaf(d, d, acc);
+      if (vrow) {
+        const float m = vrow[x] ? 1.0f : 0.0f;
+        acc = fmaf(d * d, m, acc);
+        cnt += m;
+      } else {
+        acc = fmaf(d, d, acc);
+      }
     }
   }
-  __shared__ float red[8];
+  __shared__ float red[2][8];
 #pragma unroll
-  for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-  if (lane == 0) red[warp] = acc;
+  for (int o = 16; o; o >>= 1) {
+    acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+  }
+  if (lane == 0) { red[0][warp] = acc; red[1][warp] = cnt; }
   __syncthreads();
   if (threadIdx.x == 0) {
-    float s = 0.0f;
-    for (int i = 0; i < 8; ++i) s += red[i];
-    partial[(long long)image * gridDim.x + blockIdx.x] = s;
+    float s = 0.0f, n = 0.0f;
+    for (int i = 0; i < 8; ++i) { s += red[0][i]; n += red[1][i]; }
+    const long long slot = (long long)image * gridDim.x + blockIdx.x;
+    if (valid) { partial[2 * slot] = s; partial[2 * slot + 1] = n; }
+    else partial[slot] = s;
   }
 }
 
@@ -289,13 +309,14 @@ extern "C" int dbsr_ssim_workspace_floats(int32_t n, int32_t c, int32_t h, int32
 }
 
 extern "C" int dbsr_ssim(const float* img1, const float* img2, int32_t n, int32_t c, int32_t h, int32_t w, int32_t crop,
-                         const float* window1d, int32_t window, float val_range, float* workspace, float* stats, float* ssim_map,
-                         void* stream) {
+                         const float* window1d, int32_t window, float val_range, const uint8_t* valid, float* workspace, float* stats,
+                         float* ssim_map, void* stream) {
   DBSR_REQUIRE(img1 && img2 && window1d && workspace && stats, "ssim: null argument");
   DBSR_REQUIRE(n > 0 && c > 0 && crop >= 0 && window >= 1 && window <= SS_MAXW, "ssim: bad geometry (window must be 1..11)");
   const int hc = h - 2 * crop, wc = w - 2 * crop;
   const int oh = hc - window + 1, ow = wc - window + 1;
   DBSR_REQUIRE(oh > 0 && ow > 0, "ssim: image %dx%d (crop %d) smaller than the %d-tap window", h, w, crop, window);
+  DBSR_REQUIRE(!valid || window == SS_MAXW, "ssim: a valid mask assumes the 11-tap window (the reference crops it by 5)");
   const int tx = ceil_div(ow, SS_TW), ty = ceil_div(oh, SS_TH);
   DBSR_REQUIRE((long long)n * c <= 65535 && ty <= 65535, "ssim: too many planes / tiles for one launch");
   cudaStream_t st = (cudaStream_t)stream;
@@ -305,11 +326,11 @@ extern "C" int dbsr_ssim(const float* img1, const float* img2, int32_t n, int32_
     launch_pdl(value_range_kernel, dim3(RANGE_BLOCKS), dim3(256), 0, st, img1, n * c, h, w, crop, range_ws);
   SsimParams p;
   p.a = img1; p.b = img2; p.map = ssim_map; p.partial = partial; p.range_ws = range_ws;
-  p.H = h; p.W = w; p.crop = crop; p.oh = oh; p.ow = ow; p.val_range = val_range;
+  p.H = h; p.W = w; p.crop = crop; p.oh = oh; p.ow = ow; p.val_range = val_range; p.valid = valid; p.c = c;
   for (int i = 0; i < SS_MAXW; ++i) p.g[i] = i < window ? window1d[i] : 0.0f;
   launch_pdl(ssim_tile_kernel, dim3(tx, ty, n * c), dim3(SS_THREADS), 0, st, p);
   launch_pdl(reduce_partials_kernel, dim3(n), dim3(256), 0, st, (const float*)partial, c * ty * tx, 2,
-             1.0 / ((double)c * oh * ow), stats);
+             valid ? 1.0 : 1.0 / ((double)c * oh * ow), stats);
   return check_launch("ssim");
 }
 
@@ -323,10 +344,10 @@ extern "C" int dbsr_avgpool2_pair(const float* img1, const float* img2, float* o
   return check_launch("avgpool2_pair");
 }
 
-extern "C" int dbsr_mse_workspace_floats(int32_t n) { return n > 0 ? n * 148 : -1; }
+extern "C" int dbsr_mse_workspace_floats(int32_t n) { return n > 0 ? n * 148 * 2 : -1; }
 
-extern "C" int dbsr_mse_per_image(const float* pred, const float* gt, int32_t n, int32_t c, int32_t h, int32_t w, int32_t crop,
-                                  float* workspace, float* mse, void* stream) {
+extern "C" int dbsr_mse_per_image(const float* pred, const float* gt, const uint8_t* valid, int32_t n, int32_t c, int32_t h, int32_t w,
+                                  int32_t crop, float* workspace, float* mse, void* stream) {
   DBSR_REQUIRE(pred && gt && workspace && mse && n > 0 && n <= 65535 && c > 0 && crop >= 0, "mse_per_image: bad arguments");
   const int hc = h - 2 * crop, wc = w - 2 * crop;
   DBSR_REQUIRE(hc > 0 && wc > 0, "mse_per_image: boundary_ignore %d leaves nothing of a %dx%d image", crop, h, w);
@@ -334,7 +355,10 @@ extern "C" int dbsr_mse_per_image(const float* pred, const float* gt, int32_t n,
   int per = ceil_div(rows, 8);
   if (per > 148) per = 148;
   cudaStream_t st = (cudaStream_t)stream;
-  launch_pdl(sq_err_kernel, dim3(per, n), dim3(256), 0, st, pred, gt, c, h, w, crop, workspace);
-  launch_pdl(reduce_partials_kernel, dim3(n), dim3(256), 0, st, (const float*)workspace, per, 1, 1.0 / ((double)c * hc * wc), mse);
+  launch_pdl(sq_err_kernel, dim3(per, n), dim3(256), 0, st, pred, gt, (const unsigned char*)valid, c, h, w, crop, workspace);
+  if (valid)      // mse[n][2] = (sum valid * err, sum valid over pixels and channels): the caller forms the reference's ratio
+    launch_pdl(reduce_partials_kernel, dim3(n), dim3(256), 0, st, (const float*)workspace, per, 2, 1.0, mse);
+  else
+    launch_pdl(reduce_partials_kernel, dim3(n), dim3(256), 0, st, (const float*)workspace, per, 1, 1.0 / ((double)c * hc * wc), mse);
   return check_launch("mse_per_image");
 }

@@ -63,17 +63,18 @@ class PSNR(nn.Module):
             print('invalid psnr')
         return psnr
 
-    def psnr_per_image(self, pred, gt):
+    def psnr_per_image(self, pred, gt, valid=None):
         """[n] PSNR of every image of a CUDA fp32 batch from one fused launch, no host synchronisation (what a sharded
-        evaluation all-reduces instead of gathering images)."""
+        evaluation all-reduces instead of gathering images).  valid: optional [n, 1, h, w] bool mask."""
         b = self.l2.boundary_ignore
-        mse = ops.mse_per_image(pred.contiguous(), gt.contiguous(), crop=0 if b is None else b)
+        mse = ops.mse_per_image(pred.contiguous(), gt.contiguous(), crop=0 if b is None else b, valid=valid)
         return 20 * math.log10(getattr(self, 'max_value', 1.0)) - 10.0 * mse.log10()
 
     def forward(self, pred, gt, valid=None):
-        if valid is None and pred.is_cuda and pred.dim() == 4 and pred.dtype == torch.float32 and gt.dtype == torch.float32 \
+        mask_ok = valid is None or (valid.dim() == 4 and valid.shape[1] == 1 and valid.dtype in (torch.bool, torch.uint8))
+        if mask_ok and pred.is_cuda and pred.dim() == 4 and pred.dtype == torch.float32 and gt.dtype == torch.float32 \
                 and pred.shape == gt.shape and getattr(self, 'max_value', 1.0) is not None:
-            psnr = self.psnr_per_image(pred, gt)
+            psnr = self.psnr_per_image(pred, gt, valid)
             ok = torch.isfinite(psnr)                      # the reference drops inf / nan images (:97), 0 if none is left
             return torch.where(ok, psnr, torch.zeros_like(psnr)).sum() / ok.sum().clamp(min=1)
         if valid is None:
@@ -95,20 +96,25 @@ class SSIM(nn.Module):
 
     def forward(self, pred, gt, valid=None):
         crop = 0 if self.boundary_ignore is None else self.boundary_ignore
-        if valid is not None and crop:
-            valid = valid[..., crop:-crop, crop:-crop]
         if pred.dim() == 3:
             pred = pred.unsqueeze(0)
             gt = gt.unsqueeze(0)
-        if valid is not None:
-            loss = self.ssim(pred, gt, crop=crop)          # the map itself is only needed under a mask
+        if valid is None:
+            stats, _ = msssim._stats(pred, gt, self.ssim.window_size, None, None, want_map=False, crop=crop, fixed_window=True)
+            loss = stats[:, 0].mean()
+        elif valid.dim() == 4 and valid.shape[1] == 1 and valid.dtype in (torch.bool, torch.uint8):
+            # masked mean inside the kernel, over the batch: (sum ssim * valid) / (sum valid * C + eps) (:127-131); the kernel
+            # crops the mask by index arithmetic exactly like the images (boundary_ignore, then 5 for the 11-tap window)
+            stats, _ = msssim._stats(pred, gt, self.ssim.window_size, None, None, crop=crop, fixed_window=True, valid=valid)
+            loss = stats[:, 0].sum() / (stats[:, 1].sum() + 1e-12)
+        else:                                              # other mask layouts: the map, then the reference's own torch ops
+            if crop:
+                valid = valid[..., crop:-crop, crop:-crop]
+            loss = self.ssim(pred, gt, crop=crop)
             valid = valid[..., 5:-5, 5:-5]  # assume window size 11
             eps = 1e-12
             elem_ratio = loss.numel() / valid.numel()
             loss = (loss * valid.float()).sum() / (valid.float().sum() * elem_ratio + eps)
-        else:
-            stats, _ = msssim._stats(pred, gt, self.ssim.window_size, None, None, want_map=False, crop=crop, fixed_window=True)
-            loss = stats[:, 0].mean()
         if self.use_for_loss:
             loss = 1.0 - loss
         return loss

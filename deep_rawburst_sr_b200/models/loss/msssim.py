@@ -47,7 +47,7 @@ def _window_taps(window, window_size, height, width):
     return gaussian(k, 1.5).tolist()
 
 
-def _stats(img1, img2, window_size, window, val_range, want_map=False, crop=0, fixed_window=False):
+def _stats(img1, img2, window_size, window, val_range, want_map=False, crop=0, fixed_window=False, valid=None):
     if img1.dim() != 4:
         raise ValueError('ssim expects [n, c, h, w] tensors')
     if fixed_window:      # the SSIM class always convolves with its window_size window (:121-130), never min(11, h, w)
@@ -56,7 +56,7 @@ def _stats(img1, img2, window_size, window, val_range, want_map=False, crop=0, f
         taps = gaussian(window_size, 1.5).tolist()
     else:
         taps = _window_taps(window, window_size, img1.shape[2] - 2 * crop, img1.shape[3] - 2 * crop)
-    return ops.ssim_stats(img1.contiguous(), img2.contiguous(), taps, crop=crop, val_range=val_range, want_map=want_map)
+    return ops.ssim_stats(img1.contiguous(), img2.contiguous(), taps, crop=crop, val_range=val_range, want_map=want_map, valid=valid)
 
 
 def ssim(img1, img2, window_size=11, window=None, size_average=True, full=False, val_range=None, spatial_out=False):

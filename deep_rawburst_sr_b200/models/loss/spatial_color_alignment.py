@@ -58,6 +58,10 @@ class SpatialColorAlignment(nn.Module):
         self.sr_factor = sr_factor
         self.alignment_net = alignment_net
         self.gauss_kernel, self.ksz = get_gaussian_kernel(sd=1.5)
+        # extension: normalise every image of a batch by ITS OWN maximum before the alignment net, so that a batch is
+        # aligned exactly as the reference's batch-1 evaluation loop aligns its images one by one (False: the reference
+        # expression, one maximum over the whole batch, spatial_color_alignment.py:88)
+        self.per_image_norm = False
 
     def to(self, device):
         """ Move the network to device (reference signature: returns None, spatial_color_alignment.py:80-87) """
@@ -68,7 +72,11 @@ class SpatialColorAlignment(nn.Module):
     def forward(self, pred, gt, burst_input):
         ops.require_device(pred)
         # flow between the prediction and the ground truth: PWC-Net at the output resolution on the sm_100a kernels
-        flow = self.alignment_net(pred / (pred.max() + 1e-6), gt / (gt.max() + 1e-6))
+        if getattr(self, 'per_image_norm', False):
+            flow = self.alignment_net(pred / (pred.amax(dim=(1, 2, 3), keepdim=True) + 1e-6),
+                                      gt / (gt.amax(dim=(1, 2, 3), keepdim=True) + 1e-6))
+        else:
+            flow = self.alignment_net(pred / (pred.max() + 1e-6), gt / (gt.max() + 1e-6))
         pred_warped = lispr_warp.warp(pred, flow)
         sr_factor = self.sr_factor
         ds_factor = 1.0 / float(2.0 * sr_factor)

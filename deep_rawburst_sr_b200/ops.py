@@ -295,11 +295,24 @@ def _check_image_pair(a: torch.Tensor, b: torch.Tensor) -> None:
     assert a.is_contiguous() and b.is_contiguous()
 
 
+def _mask_bytes(valid: Optional[torch.Tensor], like: torch.Tensor) -> Optional[torch.Tensor]:
+    """[n, 1, h, w] bool / uint8 mask -> contiguous uint8 view for the metric kernels"""
+    if valid is None:
+        return None
+    require_device(valid)
+    n, _, h, w = like.shape
+    if tuple(valid.shape) != (n, 1, h, w) or valid.dtype not in (torch.bool, torch.uint8):
+        raise ValueError(f'valid mask must be a bool / uint8 [n, 1, h, w] tensor, got {valid.dtype} {tuple(valid.shape)}')
+    return valid.contiguous().view(torch.uint8)
+
+
 def ssim_stats(img1: torch.Tensor, img2: torch.Tensor, window1d, crop: int = 0, val_range: Optional[float] = None,
-               want_map: bool = False):
+               want_map: bool = False, valid: Optional[torch.Tensor] = None):
     """Fused SSIM of two fp32 NCHW batches: returns (stats [n, 2] = per-image mean ssim / mean contrast term, map or None).
-    window1d: the 1-D Gaussian of msssim.gaussian (python floats, len 1..11); val_range None -> derived on the device."""
+    window1d: the 1-D Gaussian of msssim.gaussian (python floats, len 1..11); val_range None -> derived on the device.
+    valid ([n, 1, h, w] mask, window 11): stats become (sum ssim * valid, sum valid) per image, un-normalised."""
     _check_image_pair(img1, img2)
+    vb = _mask_bytes(valid, img1)
     n, c, h, w = img1.shape
     k = len(window1d)
     lib = _lib.load_library()
@@ -311,7 +324,7 @@ def ssim_stats(img1: torch.Tensor, img2: torch.Tensor, window1d, crop: int = 0, 
     smap = torch.empty(n, c, h - 2 * crop - k + 1, w - 2 * crop - k + 1, dtype=torch.float32, device=img1.device) if want_map else None
     arr = (ctypes.c_float * k)(*[float(v) for v in window1d])
     _lib.check(lib.dbsr_ssim(img1.data_ptr(), img2.data_ptr(), n, c, h, w, crop, arr, k, float(val_range) if val_range else 0.0,
-                             ws.data_ptr(), stats.data_ptr(), _ptr(smap), _stream()), 'dbsr_ssim')
+                             _ptr(vb), ws.data_ptr(), stats.data_ptr(), _ptr(smap), _stream()), 'dbsr_ssim')
     return stats, smap
 
 
@@ -326,13 +339,15 @@ def avgpool2_pair(img1: torch.Tensor, img2: torch.Tensor):
     return o1, o2
 
 
-def mse_per_image(pred: torch.Tensor, gt: torch.Tensor, crop: int = 0) -> torch.Tensor:
-    """[n] mean squared error of each image over its interior (boundary_ignore = crop), one launch for the batch."""
+def mse_per_image(pred: torch.Tensor, gt: torch.Tensor, crop: int = 0, valid: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """[n] mean squared error of each image over its interior (boundary_ignore = crop), one launch for the batch.
+    valid ([n, 1, h, w] mask): the masked form (err * valid).sum() / (valid.sum() * C + 1e-12) of image_quality_v2.py:60-64."""
     _check_image_pair(pred, gt)
+    vb = _mask_bytes(valid, pred)
     n, c, h, w = pred.shape
     lib = _lib.load_library()
     ws = torch.empty(lib.dbsr_mse_workspace_floats(n), dtype=torch.float32, device=pred.device)
-    out = torch.empty(n, dtype=torch.float32, device=pred.device)
-    _lib.check(lib.dbsr_mse_per_image(pred.data_ptr(), gt.data_ptr(), n, c, h, w, crop, ws.data_ptr(), out.data_ptr(), _stream()),
-               'dbsr_mse_per_image')
-    return out
+    out = torch.empty((n, 2) if vb is not None else (n,), dtype=torch.float32, device=pred.device)
+    _lib.check(lib.dbsr_mse_per_image(pred.data_ptr(), gt.data_ptr(), _ptr(vb), n, c, h, w, crop, ws.data_ptr(), out.data_ptr(),
+                                      _stream()), 'dbsr_mse_per_image')
+    return out if vb is None else out[:, 0] / (out[:, 1] + 1e-12)

@@ -215,19 +215,24 @@ int dbsr_predictor(const dbsr_nhwc_t* x, const float* w, const float* bias, int3
  *   synchronisation.  stats: fp32 [n][2] = per-image mean of the ssim map and of the contrast term v1 / v2 (:59).
  *   ssim_map: optional fp32 [n, c, h - 2 crop - window + 1, w - 2 crop - window + 1] (`spatial_out`), or NULL.
  *   workspace: dbsr_ssim_workspace_floats(...) floats of device memory (per-CTA partial sums: the reduction order is
- *   fixed, results are bit-identical from run to run).                                                         */
+ *   fixed, results are bit-identical from run to run).
+ *   valid: optional [n, 1, h, w] bytes (non-zero = valid pixel), the mask of image_quality_v2.SSIM.forward (:127-131: cropped
+ *   like the images, then by 5 on each side -- window 11 only); with a mask stats[n] = (sum ssim * valid, sum valid) over the
+ *   positions of all channels, un-normalised, so that the caller forms `sum / (count + eps)` per image or per batch.   */
 int dbsr_ssim_workspace_floats(int32_t n, int32_t c, int32_t h, int32_t w, int32_t crop, int32_t window);
 int dbsr_ssim(const float* img1, const float* img2, int32_t n, int32_t c, int32_t h, int32_t w, int32_t crop,
-              const float* window1d, int32_t window, float val_range, float* workspace, float* stats, float* ssim_map,
-              void* stream);
+              const float* window1d, int32_t window, float val_range, const uint8_t* valid, float* workspace, float* stats,
+              float* ssim_map, void* stream);
 /* F.avg_pool2d(img, (2, 2)) of both images between two MS-SSIM levels (msssim.py:88-89): [planes, h, w] -> [planes, h/2, w/2] */
 int dbsr_avgpool2_pair(const float* img1, const float* img2, float* out1, float* out2, int32_t planes, int32_t h, int32_t w,
                        void* stream);
 /* per-image mean squared error over the interior (image_quality_v2.py:47-66 with metric 'l2', valid = None), the quantity
- * PSNR.psnr (:75-86) takes the log of.  pred, gt: fp32 NCHW [n, c, h, w]; mse: fp32 [n]; workspace: dbsr_mse_workspace_floats(n). */
+ * PSNR.psnr (:75-86) takes the log of.  pred, gt: fp32 NCHW [n, c, h, w]; mse: fp32 [n]; workspace: dbsr_mse_workspace_floats(n).
+ * valid (optional, [n, 1, h, w] bytes): mse becomes fp32 [n][2] = (sum valid * err^2, sum valid over pixels and channels), the two
+ * sums of the masked form `(err * valid).sum() / (valid.sum() * elem_ratio + eps)` (:60-64).                                */
 int dbsr_mse_workspace_floats(int32_t n);
-int dbsr_mse_per_image(const float* pred, const float* gt, int32_t n, int32_t c, int32_t h, int32_t w, int32_t crop,
-                       float* workspace, float* mse, void* stream);
+int dbsr_mse_per_image(const float* pred, const float* gt, const uint8_t* valid, int32_t n, int32_t c, int32_t h, int32_t w,
+                       int32_t crop, float* workspace, float* mse, void* stream);
 
 #ifdef __cplusplus
 }

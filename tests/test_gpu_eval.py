@@ -53,3 +53,57 @@ def test_score_dataset_matches_per_image_protocol(dev):
     assert 'psnr' in generate_formatted_report({'dbsr': got})
     with pytest.raises(NotImplementedError):
         score_dataset(net, data, metrics=('lpips',), device=dev)
+
+
+class _LookupNet:
+    """Stand-in for the SR network of the BurstSR loop test: returns a prepared prediction per burst (matched by the burst's
+    content), honouring `output_int16` like DBSRNet.  The real network inside a scoring loop is covered by the SyntheticBurst
+    test above; here the prediction must RESEMBLE the ground truth, or the colour-error mask invalidates nearly every pixel."""
+
+    def __init__(self, bursts, preds):
+        self.keys, self.preds, self.output_int16 = bursts.flatten(1)[:, :64].clone(), preds, False
+
+    def __call__(self, burst):
+        idx = torch.cdist(burst.flatten(1)[:, :64].cpu(), self.keys).argmin(dim=1)
+        pred = self.preds[idx].to(burst.device)
+        if self.output_int16:
+            pred = (pred.clamp(0.0, 1.0) * 2 ** 14).short()
+        return pred, {}
+
+
+def test_burstsr_score_dataset_matches_batch1_loop(dev):
+    """BurstSR protocol (evaluation/burstsr/compute_score.py:97-128): the batched loop (per-image normalisation inside the
+    alignment, masked PSNR / SSIM from the fused kernels, one reduction) against the reference's schedule -- one burst at a
+    time through the drop-in modules: forward, quantise, SpatialColorAlignment, PSNR / SSIM with `valid`, python mean."""
+    from deep_rawburst_sr_b200.evaluation.burstsr.compute_score import score_dataset
+    from deep_rawburst_sr_b200.models.alignment.pwcnet import PWCNet
+    from deep_rawburst_sr_b200.models.loss.image_quality_v2 import PSNR, SSIM
+    from deep_rawburst_sr_b200.models.loss.spatial_color_alignment import SpatialColorAlignment
+    from oracle import sca_oracle as S
+    n, bi = 5, 8
+    preds, gts, bursts = S.make_sca_inputs(0, n, 192)
+    scale = torch.linspace(0.5, 1.0, n).view(n, 1, 1, 1)           # different maxima: per-image normalisation matters
+    preds, gts, bursts = preds * scale, gts * scale, bursts * scale.view(n, 1, 1, 1, 1)
+    net = _LookupNet(bursts, preds)
+    pwc = PWCNet(load_pretrained=False)
+    pwc.load_state_dict(S.pwc_state_dict(0, 1.0), strict=True)
+    pwc = pwc.to(dev).eval()
+    data = [{'burst': b, 'frame_gt': g, 'burst_name': str(i)} for i, (b, g) in enumerate(zip(bursts, gts))]
+    sca = SpatialColorAlignment(pwc, sr_factor=4)
+    sca.to(dev)
+    psnr_fn, ssim_fn = PSNR(boundary_ignore=bi), SSIM(boundary_ignore=bi, use_for_loss=False)
+    ps, ss, vf = [], [], []
+    for it in data:
+        burst, gt = it['burst'].unsqueeze(0).to(dev), it['frame_gt'].unsqueeze(0).to(dev)
+        pred, _ = net(burst)
+        pred = (pred.clamp(0.0, 1.0) * 2 ** 14).short().float() / 2 ** 14
+        pm, valid = sca(pred, gt, burst)
+        vf.append(float(valid.float().mean()))
+        ps.append(psnr_fn(pm, gt, valid=valid).cpu().item())
+        ss.append(ssim_fn(pm, gt, valid=valid).cpu().item())
+    assert 0.05 < sum(vf) / n < 1.0, vf                           # a real mask: some, not all, pixels valid (cf. the goldens: 6-21 %)
+    for batch in (2, 8):
+        got = score_dataset(net, data, pwc, boundary_ignore=bi, batch_size=batch, device=dev)
+        assert got['count'] == n and not net.output_int16
+        assert abs(got['psnr'] - sum(ps) / n) <= 1e-3, (got, ps)
+        assert abs(got['ssim'] - sum(ss) / n) <= 1e-5, (got, ss)
