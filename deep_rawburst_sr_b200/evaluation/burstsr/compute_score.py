@@ -25,13 +25,15 @@ from ..synburst.compute_score import dequantize_q14, generate_formatted_report  
 
 @torch.no_grad()
 def score_dataset(net, dataset, alignment_net, metrics: Sequence[str] = ('psnr', 'ssim'), boundary_ignore: int = 40,
-                  batch_size: int = 16, device='cuda', burst_sz=None, sr_factor: int = 4) -> Dict[str, float]:
+                  batch_size: int = 16, device='cuda', burst_sz=None, sr_factor: int = 4, shard: bool = True) -> Dict[str, float]:
     """Mean per-image aligned metrics of `net` over `dataset` (all ranks' shards), plus 'count'."""
     for m in metrics:
         if m not in ('psnr', 'ssim'):
             raise NotImplementedError(f'metric {m!r} is not provided (psnr / ssim; lpips needs the `lpips` package)')
-    rank = dist.get_rank() if (dist.is_available() and dist.is_initialized()) else 0
-    world = dist.get_world_size() if (dist.is_available() and dist.is_initialized()) else 1
+    # shard=False: this rank scores the whole set on its own (no collective), e.g. to cross-check a sharded run
+    distributed = shard and dist.is_available() and dist.is_initialized()
+    rank = dist.get_rank() if distributed else 0
+    world = dist.get_world_size() if distributed else 1
     lo, hi = sharding.shard_range(len(dataset), rank, world)
     device = torch.device(device)
     sca = SpatialColorAlignment(alignment_net.eval(), sr_factor=sr_factor)
@@ -62,7 +64,7 @@ def score_dataset(net, dataset, alignment_net, metrics: Sequence[str] = ('psnr',
     finally:
         net.output_int16 = was_q
     local = torch.cat(per_image) if per_image else torch.zeros(0, len(metrics), device=device)
-    mean = sharding.reduce_metric_means(local)
+    mean = sharding.reduce_metric_means(local, collective=distributed)
     out = {m: float(v) for m, v in zip(metrics, mean.cpu())}
     out['count'] = len(dataset)
     return out

@@ -76,13 +76,15 @@ def dequantize_q14(pred_q: torch.Tensor) -> torch.Tensor:
 
 @torch.no_grad()
 def score_dataset(net, dataset, metrics: Sequence[str] = ('psnr', 'ssim'), boundary_ignore: int = 40, batch_size: int = 32,
-                  device='cuda', burst_sz=None) -> Dict[str, float]:
+                  device='cuda', burst_sz=None, shard: bool = True) -> Dict[str, float]:
     """Mean per-image metrics of `net` over `dataset` (all ranks' shards), plus 'count'.  `net`: a `DBSRNet` of this package."""
     for m in metrics:
         if m not in ('psnr', 'ssim'):
             raise NotImplementedError(f'metric {m!r} is not provided (psnr / ssim; lpips needs the `lpips` package)')
-    rank = dist.get_rank() if (dist.is_available() and dist.is_initialized()) else 0
-    world = dist.get_world_size() if (dist.is_available() and dist.is_initialized()) else 1
+    # shard=False: this rank scores the whole set on its own (no collective), e.g. to cross-check a sharded run
+    distributed = shard and dist.is_available() and dist.is_initialized()
+    rank = dist.get_rank() if distributed else 0
+    world = dist.get_world_size() if distributed else 1
     lo, hi = sharding.shard_range(len(dataset), rank, world)
     device = torch.device(device)
     psnr_fn = PSNR(boundary_ignore=boundary_ignore)
@@ -112,7 +114,7 @@ def score_dataset(net, dataset, metrics: Sequence[str] = ('psnr', 'ssim'), bound
     finally:
         net.output_int16 = was_q
     local = torch.cat(per_image) if per_image else torch.zeros(0, len(metrics), device=device)
-    mean = sharding.reduce_metric_means(local)
+    mean = sharding.reduce_metric_means(local, collective=distributed)
     out = {m: float(v) for m, v in zip(metrics, mean.cpu())}
     out['count'] = len(dataset)
     return out

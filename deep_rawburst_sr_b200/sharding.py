@@ -53,7 +53,7 @@ def max_over_ranks(value: float, device) -> float:
     return float(t.item())
 
 
-def reduce_metric_means(per_image: torch.Tensor) -> torch.Tensor:
+def reduce_metric_means(per_image: torch.Tensor, collective: bool = True) -> torch.Tensor:
     """Mean over ALL ranks' images of per-image metric values [b_local] or [b_local, k] (e.g. the outputs of
     `PSNR.psnr_per_image` / `msssim.ssim(size_average=False)`), with one all_reduce(SUM) of `[sums | counts]` instead of a
     gather of the images ("plus one all_reduce(SUM) of [sum psnr, count]").  Non-finite values are dropped per
@@ -62,7 +62,7 @@ def reduce_metric_means(per_image: torch.Tensor) -> torch.Tensor:
     v = per_image if per_image.dim() == 2 else per_image.unsqueeze(1)
     ok = torch.isfinite(v)
     acc = torch.cat([torch.where(ok, v, torch.zeros_like(v)).double().sum(0), ok.double().sum(0)])
-    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+    if collective and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
         dist.all_reduce(acc, op=dist.ReduceOp.SUM)
     k = v.shape[1]
     mean = (acc[:k] / acc[k:].clamp(min=1)).to(per_image.dtype)
