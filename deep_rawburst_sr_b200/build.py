@@ -15,7 +15,7 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 LIB = os.path.join(CSRC, 'libdbsr_b200.so')
-SOURCES = ['misc.cu', 'conv_direct.cu', 'corr.cu', 'fusion.cu', 'metrics.cu', 'conv_tc.cu']
+SOURCES = ['misc.cu', 'conv_direct.cu', 'corr.cu', 'fusion.cu', 'metrics.cu', 'camera.cu', 'conv_tc.cu']
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17',
               '-Xcompiler', '-fPIC', '-Xptxas', '-v']
 

@@ -351,3 +351,33 @@ def mse_per_image(pred: torch.Tensor, gt: torch.Tensor, crop: int = 0, valid: Op
     _lib.check(lib.dbsr_mse_per_image(pred.data_ptr(), gt.data_ptr(), _ptr(vb), n, c, h, w, crop, ws.data_ptr(), out.data_ptr(),
                                       _stream()), 'dbsr_mse_per_image')
     return out if vb is None else out[:, 0] / (out[:, 1] + 1e-12)
+
+
+# ---- synthetic burst generation: inverse camera pipeline (include/dbsr_b200.h) ------------------------------------------------
+def unprocess_rgb(image: torch.Tensor, rgb2cam: torch.Tensor, gains3, smoothstep: bool = True, gamma: bool = True) -> torch.Tensor:
+    """sRGB [3, h, w] / [b, 3, h, w] -> clamped linear camera RGB (inverse tone curve, gamma, CCM, safe gain inversion), one pass"""
+    require_device(image)
+    assert image.dtype == torch.float32 and image.dim() in (3, 4) and image.shape[-3] == 3
+    x = image.contiguous()
+    out = torch.empty_like(x)
+    b = 1 if x.dim() == 3 else x.shape[0]
+    ccm = (ctypes.c_float * 9)(*[float(v) for v in rgb2cam.detach().float().cpu().flatten().tolist()])
+    g3 = (ctypes.c_float * 3)(*[float(v) for v in gains3])
+    _lib.check(_lib.load_library().dbsr_unprocess_rgb(x.data_ptr(), out.data_ptr(), b, x.shape[-2], x.shape[-1], ccm, g3,
+                                                      1 if smoothstep else 0, 1 if gamma else 0, _stream()), 'dbsr_unprocess_rgb')
+    return out
+
+
+def mosaic_noise(rgb: torch.Tensor, shot_noise: float = 0.0, read_noise: float = 0.0, noise: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """RGB burst [n, 3, h, w] -> clamped noisy RGGB burst [n, 4, h/2, w/2]; `noise`: standard-normal tensor of that shape or None"""
+    require_device(rgb)
+    assert rgb.dtype == torch.float32 and rgb.dim() == 4 and rgb.shape[1] == 3
+    x = rgb.contiguous()
+    n, _, h, w = x.shape
+    raw = torch.empty(n, 4, h // 2, w // 2, dtype=torch.float32, device=x.device)
+    if noise is not None:
+        require_device(noise)
+        assert noise.dtype == torch.float32 and tuple(noise.shape) == tuple(raw.shape) and noise.is_contiguous()
+    _lib.check(_lib.load_library().dbsr_mosaic_noise(x.data_ptr(), _ptr(noise), raw.data_ptr(), n, h, w, float(shot_noise),
+                                                     float(read_noise), _stream()), 'dbsr_mosaic_noise')
+    return raw

@@ -234,6 +234,21 @@ int dbsr_mse_workspace_floats(int32_t n);
 int dbsr_mse_per_image(const float* pred, const float* gt, const uint8_t* valid, int32_t n, int32_t c, int32_t h, int32_t w,
                        int32_t crop, float* workspace, float* mse, void* stream);
 
+/* -------------------------------------------------------------------------------------------------- */
+/* synthetic burst generation, inverse camera pipeline (the parameter-deterministic part)  */
+/* -------------------------------------------------------------------------------------------------- */
+/* data/synthetic_burst_generation.py:59-79 in one pass: invert_smoothstep (camera_pipeline.py:78-81, if `smoothstep`) ->
+ * gamma_expansion (:84-87, if `gamma`) -> apply_ccm(rgb2cam) (:96-107) -> safe_invert_gains (:121-136) -> clamp(0, 1).
+ *   image, out: fp32 [batch, 3, h, w]; rgb2cam9: 9 HOST floats (row-major); gains3: 3 HOST floats =
+ *   [1 / red_gain, 1, 1 / blue_gain] / rgb_gain as the reference forms them in fp32 (:125).                         */
+int dbsr_unprocess_rgb(const float* image, float* out, int32_t batch, int32_t h, int32_t w, const float* rgb2cam9,
+                       const float* gains3, int32_t smoothstep, int32_t gamma, void* stream);
+/* synthetic_burst_generation.py:88-99: mosaic (camera_pipeline.py:139-150, 'rggb') -> add_noise (:178-183) -> clamp(0, 1).
+ *   rgb: fp32 [n, 3, h, w] (h, w even); raw: fp32 [n, 4, h/2, w/2]; noise: standard-normal fp32 of raw's shape drawn by the
+ *   caller (the reference draws it on the host inside add_noise), or NULL for no noise.                              */
+int dbsr_mosaic_noise(const float* rgb, const float* noise, float* raw, int32_t n, int32_t h, int32_t w, float shot_noise,
+                      float read_noise, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

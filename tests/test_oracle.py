@@ -154,3 +154,19 @@ def test_metrics_oracle_matches_reference_golden(golden_dir, name):
     mv = max(scale, 1.0)
     assert abs(float(M.psnr(pred, gt, bi, mv)) - float(g['psnr'])) <= 1e-4
     assert np.abs(M.psnr_per_image(pred, gt, bi, mv).numpy() - g['psnr_per_image']).max() <= 1e-4
+
+
+@pytest.mark.parametrize('name', ['camera_s0_64x96', 'camera_s1_48x40'])
+def test_camera_oracle_matches_reference_golden(golden_dir, name):
+    """oracle/camera_oracle.py against the reference's own data/camera_pipeline.py functions (oracle/make_golden_camera.py):
+    the inverse pipeline within 1e-6 (torch.mm vs explicit sums), mosaic and the noisy burst bit for bit."""
+    from oracle import camera_oracle as C
+    g = np.load(os.path.join(golden_dir, name + '.npz'))
+    seed, h, w, n = [int(v) for v in g['meta']]
+    image, rgb2cam, gains, burst_rgb, (shot, read) = C.make_inputs(seed, h, w, n)
+    assert np.abs(C.unprocess(image, rgb2cam, *gains).numpy() - g['linear']).max() <= 1e-6
+    assert np.abs(C.unprocess(image, rgb2cam, *gains, gamma=False).numpy() - g['linear_nogamma']).max() <= 1e-6
+    assert np.array_equal(C.mosaic(burst_rgb).numpy(), g['raw'])
+    torch.manual_seed(500 + seed)
+    z = torch.FloatTensor(*g['raw'].shape).normal_()
+    assert np.array_equal(C.mosaic_add_noise(burst_rgb, shot, read, z).numpy(), g['noisy'])
