@@ -99,3 +99,121 @@ extern "C" int dbsr_mosaic_noise(const float* rgb, const float* noise, float* ra
              read_noise);
   return check_launch("mosaic_noise");
 }
+
+// ---------------------------------------------------------------------------------------------------------
+// single2lrburst (data/synthetic_burst_generation.py:131-246) for given frame transforms: uint8 quantisation of the image,
+// cv2.warpAffine (8-bit, INTER_LINEAR, BORDER_CONSTANT), border crop, cv2.resize by 1 / factor (8-bit, INTER_LINEAR), / 255 --
+// fused: only the warped pixels the resize reads are ever computed (2 x 2 of every factor x factor block for an even factor),
+// straight from the fp32 image.  Byte / integer work: BIT-EXACT against OpenCV's fixed-point scheme (restated in
+// oracle/lrburst_oracle.py: inverse map in 1/1024 px with separately rounded column / row terms + 16, reduced to 1/32 px; tap
+// weights (32 - fx)(32 - fy) * 32 ..., (sum + 2^14) >> 15; resize (sum of the 2 x 2 block + 2) >> 2).  The flow vectors
+// (sampling-position maps, :214-218, 229-246) are fp32.
+// ---------------------------------------------------------------------------------------------------------
+namespace dbsr {
+
+struct LrBurstParams {
+  const float* image;      // [3, H, W]
+  const double* inv;       // [n][6] inverse affine maps (double, as cv::warpAffine inverts them)
+  const float* pos;        // [n][6] fp32 inverse of the 3x3 forward matrix, rows 0..1 (torch .inverse(), :215)
+  float* burst;            // [n, 3, h, w]
+  float* flow;             // [n, 2, h, w] or null
+  int H, W, n, f, crop, h, w, normalize;
+};
+
+__device__ __forceinline__ int warped_u8x3(const LrBurstParams& p, const double* M, int x, int y, int out[3]) {
+  // cv::warpAffine: X0 = round((M1 y + M2) 1024) + 16, adelta = round(M0 x 1024); 1/32 px after >> 5
+  // (explicit IEEE mul / add: an FMA contraction would round the half-way cases differently from the host code)
+  const double dx = (double)x, dy = (double)y;
+  const long long X = (__double2ll_rn(__dmul_rn(__dadd_rn(__dmul_rn(M[1], dy), M[2]), 1024.0)) + 16 +
+                       __double2ll_rn(__dmul_rn(__dmul_rn(M[0], dx), 1024.0))) >> 5;
+  const long long Y = (__double2ll_rn(__dmul_rn(__dadd_rn(__dmul_rn(M[4], dy), M[5]), 1024.0)) + 16 +
+                       __double2ll_rn(__dmul_rn(__dmul_rn(M[3], dx), 1024.0))) >> 5;
+  long long sxl = X >> 5, syl = Y >> 5;
+  sxl = sxl < -32768 ? -32768 : (sxl > 32767 ? 32767 : sxl);        // saturate_cast<short>
+  syl = syl < -32768 ? -32768 : (syl > 32767 ? 32767 : syl);
+  const int sx = (int)sxl, sy = (int)syl, fx = (int)(X & 31), fy = (int)(Y & 31);
+  const int w00 = (32 - fx) * (32 - fy) * 32, w01 = fx * (32 - fy) * 32, w10 = (32 - fx) * fy * 32, w11 = fx * fy * 32;
+  const bool x0 = sx >= 0 && sx < p.W, x1 = sx + 1 >= 0 && sx + 1 < p.W, y0 = sy >= 0 && sy < p.H, y1 = sy + 1 >= 0 && sy + 1 < p.H;
+  const long long plane = (long long)p.H * p.W;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const float* im = p.image + c * plane;
+    auto q = [&](bool ok, int yy, int xx) -> int {       // (image * 255).astype(uint8): fp32 product, truncation
+      if (!ok) return 0;
+      float v = __ldg(im + (long long)yy * p.W + xx);
+      if (p.normalize) v = __fmul_rn(v, 255.0f);
+      return (int)fminf(fmaxf(v, 0.0f), 255.0f);
+    };
+    const int acc = q(y0 && x0, sy, sx) * w00 + q(y0 && x1, sy, sx + 1) * w01 + q(y1 && x0, sy + 1, sx) * w10 + q(y1 && x1, sy + 1, sx + 1) * w11;
+    out[c] = (acc + 16384) >> 15;
+  }
+  return 0;
+}
+
+__global__ void __launch_bounds__(256) lrburst_kernel(const LrBurstParams p) {
+  griddep_wait();
+  const long long total = (long long)p.n * p.h * p.w;
+  const int k = (p.f & 1) ? 1 : 2, o = (p.f & 1) ? (p.f - 1) / 2 : p.f / 2 - 1;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int ox = (int)(i % p.w);
+    const long long t = i / p.w;
+    const int oy = (int)(t % p.h), frame = (int)(t / p.h);
+    const double* M = p.inv + 6 * frame;
+    const int bx = p.crop + p.f * ox + o, by = p.crop + p.f * oy + o;
+    int s[3] = {0, 0, 0};
+    for (int dy = 0; dy < k; ++dy)
+      for (int dx = 0; dx < k; ++dx) {
+        int v[3];
+        warped_u8x3(p, M, bx + dx, by + dy, v);
+        s[0] += v[0]; s[1] += v[1]; s[2] += v[2];
+      }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const int v = k == 2 ? (s[c] + 2) >> 2 : s[c];
+      const float fv = (float)v;
+      p.burst[(((long long)frame * 3 + c) * p.h + oy) * p.w + ox] = p.normalize ? __fdiv_rn(fv, 255.0f) : fv;
+    }
+    if (p.flow) {
+      float d[2];
+#pragma unroll
+      for (int a = 0; a < 2; ++a) {
+        float pos[2];
+#pragma unroll
+        for (int which = 0; which < 2; ++which) {          // this frame, frame 0
+          const float* T = p.pos + 6 * (which == 0 ? frame : 0) + 3 * a;
+          auto at = [&](int xx, int yy) { return __fadd_rn(__fadd_rn(__fmul_rn((float)xx, T[0]), __fmul_rn((float)yy, T[1])), T[2]); };
+          float r;
+          if (k == 2) {
+            const float h0 = __fadd_rn(__fmul_rn(at(bx, by), 0.5f), __fmul_rn(at(bx + 1, by), 0.5f));
+            const float h1 = __fadd_rn(__fmul_rn(at(bx, by + 1), 0.5f), __fmul_rn(at(bx + 1, by + 1), 0.5f));
+            r = __fadd_rn(__fmul_rn(h0, 0.5f), __fmul_rn(h1, 0.5f));
+          } else {
+            r = at(bx, by);
+          }
+          pos[which] = __fdiv_rn(r, (float)p.f);
+        }
+        d[a] = __fsub_rn(pos[0], pos[1]);
+      }
+      p.flow[(((long long)frame * 2 + 0) * p.h + oy) * p.w + ox] = d[0];
+      p.flow[(((long long)frame * 2 + 1) * p.h + oy) * p.w + ox] = d[1];
+    }
+  }
+}
+
+}  // namespace dbsr
+
+extern "C" int dbsr_single2lrburst(const float* image, int32_t H, int32_t W, const double* inverse_maps, const float* position_maps,
+                                   int32_t n, int32_t factor, int32_t border_crop, int32_t normalize, float* burst, float* flow,
+                                   void* stream) {
+  DBSR_REQUIRE(image && inverse_maps && burst && H > 0 && W > 0 && n > 0 && factor >= 1 && border_crop >= 0, "single2lrburst: bad arguments");
+  DBSR_REQUIRE(!flow || position_maps, "single2lrburst: flow vectors need the fp32 position maps");
+  const int hc = H - 2 * border_crop, wc = W - 2 * border_crop;
+  DBSR_REQUIRE(hc > 0 && wc > 0 && hc % factor == 0 && wc % factor == 0,
+               "single2lrburst: the cropped image (%d x %d) must be a multiple of the down-sampling factor %d", hc, wc, factor);
+  LrBurstParams p;
+  p.image = image; p.inv = inverse_maps; p.pos = position_maps; p.burst = burst; p.flow = flow;
+  p.H = H; p.W = W; p.n = n; p.f = factor; p.crop = border_crop; p.h = hc / factor; p.w = wc / factor; p.normalize = normalize;
+  const long long total = (long long)n * p.h * p.w;
+  launch_pdl(lrburst_kernel, dim3(grid_for_cam(total)), dim3(256), 0, (cudaStream_t)stream, p);
+  return check_launch("single2lrburst");
+}

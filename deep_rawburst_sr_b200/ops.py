@@ -381,3 +381,25 @@ def mosaic_noise(rgb: torch.Tensor, shot_noise: float = 0.0, read_noise: float =
     _lib.check(_lib.load_library().dbsr_mosaic_noise(x.data_ptr(), _ptr(noise), raw.data_ptr(), n, h, w, float(shot_noise),
                                                      float(read_noise), _stream()), 'dbsr_mosaic_noise')
     return raw
+
+
+def single2lrburst(image: torch.Tensor, inverse_maps: torch.Tensor, position_maps: torch.Tensor, factor: int, border_crop: int = 0,
+                   normalize: bool = True, want_flow: bool = True):
+    """image [3, H, W] fp32 -> (burst [n, 3, h, w], flow [n, 2, h, w] or None): quantise, warp, crop, down-sample (OpenCV-exact)"""
+    require_device(image)
+    assert image.dtype == torch.float32 and image.dim() == 3 and image.shape[0] == 3
+    x = image.contiguous()
+    n = inverse_maps.shape[0]
+    inv = inverse_maps.to(device=x.device, dtype=torch.float64).contiguous()
+    pos = position_maps.to(device=x.device, dtype=torch.float32).contiguous()
+    assert tuple(inv.shape) == (n, 6) and tuple(pos.shape) == (n, 6)
+    _, H, W = x.shape
+    hc, wc = H - 2 * border_crop, W - 2 * border_crop
+    if hc <= 0 or wc <= 0 or hc % factor or wc % factor:
+        raise ValueError(f'single2lrburst: cropped size {hc}x{wc} must be a positive multiple of the down-sampling factor {factor}')
+    burst = torch.empty(n, 3, hc // factor, wc // factor, dtype=torch.float32, device=x.device)
+    flow = torch.empty(n, 2, hc // factor, wc // factor, dtype=torch.float32, device=x.device) if want_flow else None
+    _lib.check(_lib.load_library().dbsr_single2lrburst(x.data_ptr(), H, W, inv.data_ptr(), pos.data_ptr(), n, factor, border_crop,
+                                                       1 if normalize else 0, burst.data_ptr(), _ptr(flow), _stream()),
+               'dbsr_single2lrburst')
+    return burst, flow

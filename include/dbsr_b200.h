@@ -248,6 +248,15 @@ int dbsr_unprocess_rgb(const float* image, float* out, int32_t batch, int32_t h,
  *   caller (the reference draws it on the host inside add_noise), or NULL for no noise.                              */
 int dbsr_mosaic_noise(const float* rgb, const float* noise, float* raw, int32_t n, int32_t h, int32_t w, float shot_noise,
                       float read_noise, void* stream);
+/* single2lrburst (data/synthetic_burst_generation.py:131-246) for given frame transforms, fused: (image * 255).astype(uint8)
+ * -> cv2.warpAffine (8-bit, INTER_LINEAR, BORDER_CONSTANT, :211-212) -> border crop (:220-224) -> cv2.resize by 1 / factor (8-bit,
+ * INTER_LINEAR, :227-228) -> / 255 (:236); BIT-EXACT against OpenCV's fixed-point arithmetic (restated in oracle/lrburst_oracle.py).
+ *   image: fp32 [3, H, W]; inverse_maps: DEVICE doubles [n][6], the inverse of each 2x3 forward matrix as cv::warpAffine forms it;
+ *   position_maps: DEVICE floats [n][6], rows 0..1 of the fp32 inverse of the 3x3 matrix (:214-215), needed for `flow`;
+ *   burst: fp32 [n, 3, h, w], h = (H - 2 crop) / factor (must divide); flow (optional): fp32 [n, 2, h, w] flow vectors to frame 0
+ *   (:229-246); normalize = 1: the image is in [0, 1] (the reference tests image.max() < 2, :154).                       */
+int dbsr_single2lrburst(const float* image, int32_t H, int32_t W, const double* inverse_maps, const float* position_maps,
+                        int32_t n, int32_t factor, int32_t border_crop, int32_t normalize, float* burst, float* flow, void* stream);
 
 #ifdef __cplusplus
 }

