@@ -14,6 +14,7 @@ Five legs, every one through the C ABI (`ops.*` -> libdbsr_b200.so), one JSON li
                 U(-4,4) px so that out-of-image taps occur.  Bytes: (28*C*s + 13*2*4)*S^2 + C*s*S^2 per burst.
 * `pwc_align`   the whole PWC-Net alignment of a burst batch (pwcnet.py:248-281) at 96^2 / 160^2: pairs/s.
 * `metrics`     SSIM / MS-SSIM / PSNR of a batch of predictions through the fused metric kernels.
+* `generator`   (opt-in) the synthetic burst generator: its three kernels, and `rgb2rawburst` as called (8(f) rank 4).
 * `eval`        (opt-in, --legs eval) the batched SyntheticBurst scoring loop end to end from host tensors (8(f) rank 2).
 * `sca`         SpatialColorAlignment.forward (models/loss/spatial_color_alignment.py:85-108) at the BurstSR evaluation
                 shape (640^2 prediction / ground truth, 80^2 RAW burst): images/s.
@@ -229,6 +230,35 @@ def main():
         dt = time.perf_counter() - t0
         emit({'leg': 'eval', 'bursts': n, 'batch': 32, 'size': 48, 'precision': 'bf16', 's': dt, 'bursts_per_s': n / dt, 'dataset': 'per-item list',
               'report': rep, 'timing': 'host wall clock around score_dataset (ends with the host read of the report)'})
+    if 'generator' in legs:
+        # the synthetic burst generator (default_synthetic.py settings) -- the three kernels alone with the
+        # frame transforms prepared once (CUDA events), and `rgb2rawburst` as called (host RNG + sampling per burst, wall clock)
+        import time
+        from deep_rawburst_sr_b200.data import camera_pipeline as cp
+        from deep_rawburst_sr_b200.data import synthetic_burst_generation as G
+        params = {'max_translation': 24.0, 'max_rotation': 1.0, 'max_shear': 0.0, 'max_scale': 0.0, 'border_crop': 24}
+        img = torch.rand(3, 432, 432, generator=g).to(dev)
+        rgb2cam, gains = cp.random_ccm(), cp.random_gains()
+        t_mats = G.sample_transforms((432, 432), FRAMES, 4, params)
+        z = torch.randn(FRAMES, 4, 48, 48, generator=g).to(dev)
+
+        def kernels_only():
+            lin = cp.unprocess(img, rgb2cam, *gains)
+            rgb, _ = G.lrburst_from_transforms(lin, t_mats, 4, 24, normalize=True)
+            return cp.mosaic_add_noise(rgb, 0.004, 0.0003, z)
+        med, mn = timer(kernels_only)
+        emit({'leg': 'generator', 'op': 'unprocess + single2lrburst + mosaic_noise (transforms given; includes the per-call upload of '
+                                        'the 14 matrices)', 'ms': med, 'ms_min': mn, 'bursts_per_s': 1e3 / med})
+        for _ in range(3):
+            G.rgb2rawburst(img, FRAMES, 4, dict(params))
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(50):
+            G.rgb2rawburst(img, FRAMES, 4, dict(params))
+        torch.cuda.synchronize()
+        dt = (time.perf_counter() - t0) / 50
+        emit({'leg': 'generator', 'op': 'rgb2rawburst as called (host RNG, transform sampling, noise draw + upload)', 'ms': dt * 1e3,
+              'bursts_per_s': 1.0 / dt, 'timing': 'host wall clock over 50 bursts'})
     if args.out:
         with open(args.out, 'w') as f:
             for d in lines:
