@@ -83,11 +83,12 @@ def lrburst_from_transforms(image, t_mats, downsample_factor=1, border_crop=None
     if normalize is None:
         normalize = bool(image.max() < 2.0)                 # the reference's data-dependent test (:154), one host read
     inv = torch.from_numpy(np.stack([_inverse_map(m) for m in t_mats]))
-    pos = []
-    for m in t_mats:
-        t3 = torch.cat((torch.from_numpy(np.asarray(m)).float(), torch.tensor([0.0, 0.0, 1.0]).view(1, 3)), dim=0)
-        pos.append(t3.inverse()[:2, :].contiguous().view(6))
-    return ops.single2lrburst(image, inv, torch.stack(pos), int(downsample_factor), int(border_crop or 0), normalize)
+    # fp32 inverse of the 3x3 forward matrices (:214-215), all frames in one batched call
+    t3 = torch.zeros(len(t_mats), 3, 3)
+    t3[:, :2, :] = torch.from_numpy(np.stack([np.asarray(m) for m in t_mats])).float()
+    t3[:, 2, 2] = 1.0
+    pos = torch.linalg.inv(t3)[:, :2, :].reshape(len(t_mats), 6)
+    return ops.single2lrburst(image, inv, pos, int(downsample_factor), int(border_crop or 0), normalize)
 
 
 def single2lrburst(image, burst_size, downsample_factor=1, transformation_params=None, interpolation_type='bilinear'):
@@ -113,9 +114,12 @@ def rgb2rawburst(image, burst_size, downsample_factor=1, burst_transformation_pa
     rgb_gain, red_gain, blue_gain = rgb2raw.random_gains() if image_processing_params['random_gains'] else (1.0, 1.0, 1.0)
     use_smoothstep, use_gamma = image_processing_params['smoothstep'], image_processing_params['gamma']
     image = rgb2raw.unprocess(image, rgb2cam, rgb_gain, red_gain, blue_gain, use_smoothstep, use_gamma)
-    image_burst_rgb, flow_vectors = single2lrburst(image, burst_size=burst_size, downsample_factor=downsample_factor,
-                                                   transformation_params=burst_transformation_params,
-                                                   interpolation_type=interpolation_type)
+    if interpolation_type != 'bilinear':
+        raise NotImplementedError("only interpolation_type='bilinear' (cv2.INTER_LINEAR) is implemented")
+    # single2lrburst, with its `image.max() < 2` test (:154) known to hold: the image was just clamped to [0, 1] (no host read)
+    tp = burst_transformation_params or {}
+    t_mats = sample_transforms(tuple(image.shape[-2:]), burst_size, downsample_factor, tp)
+    image_burst_rgb, flow_vectors = lrburst_from_transforms(image, t_mats, downsample_factor, tp.get('border_crop'), normalize=True)
     if image_processing_params['add_noise']:
         shot_noise_level, read_noise_level = rgb2raw.random_noise_levels()
         n, _, h, w = image_burst_rgb.shape
