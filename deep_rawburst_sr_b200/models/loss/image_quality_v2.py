@@ -8,43 +8,50 @@ import math
 
 import torch
 import torch.nn as nn
-import torch.nn.functional as F
 
 from ... import ops
 from . import msssim
 from . import spatial_color_alignment as sca_utils
 
 
+def _interior(b, *tensors):
+    """drop `b` boundary pixels on every side of the last two dimensions (boundary_ignore); None entries pass through"""
+    if b is None:
+        return tensors
+    return tuple(t if t is None else t[..., b:-b, b:-b] for t in tensors)
+
+
+def _masked_mean(err, valid):
+    """mean of `err` over the valid pixels; a one-channel mask counts once per channel (image_quality_v2.py:60-64)"""
+    mask = valid.float()
+    per_mask_elem = err.numel() / valid.numel()
+    return (err * mask).sum() / (mask.sum() * per_mask_elem + 1e-12)
+
+
+_ELEMENTWISE = {'l1': lambda d: d.abs(), 'l2': lambda d: d * d}
+_REDUCED = {'l2_sqrt': lambda d: (d * d).sum(dim=-3).sqrt().mean(),
+            'charbonnier': lambda d: (d * d + 1e-3 ** 2).sqrt().mean()}
+
+
 class PixelWiseError(nn.Module):
-    """ Computes pixel-wise error using the specified metric. Optionally boundary pixels are ignored during error
-        calculation """
+    """Pixel-wise error ('l1' | 'l2' | 'l2_sqrt' | 'charbonnier'), optionally ignoring `boundary_ignore` boundary pixels and,
+    for 'l1' / 'l2', restricted to a validity mask (reference :24-66; there too the other two metrics take no mask)."""
     def __init__(self, metric='l1', boundary_ignore=None):
         super().__init__()
-        self.boundary_ignore = boundary_ignore
-        if metric == 'l1':
-            self.loss_fn = F.l1_loss
-        elif metric == 'l2':
-            self.loss_fn = F.mse_loss
-        elif metric == 'l2_sqrt':
-            self.loss_fn = lambda pred, gt: (((pred - gt) ** 2).sum(dim=-3)).sqrt().mean()
-        elif metric == 'charbonnier':
-            self.loss_fn = lambda pred, gt: ((pred - gt) ** 2 + 1e-3 ** 2).sqrt().mean()
-        else:
+        if metric not in _ELEMENTWISE and metric not in _REDUCED:
             raise Exception
+        self.metric = metric
+        self.boundary_ignore = boundary_ignore
 
     def forward(self, pred, gt, valid=None):
-        if self.boundary_ignore is not None:
-            b = self.boundary_ignore
-            pred = pred[..., b:-b, b:-b]
-            gt = gt[..., b:-b, b:-b]
+        pred, gt, valid = _interior(self.boundary_ignore, pred, gt, valid)
+        diff = pred - gt
+        if self.metric in _REDUCED:
             if valid is not None:
-                valid = valid[..., b:-b, b:-b]
-        if valid is None:
-            return self.loss_fn(pred, gt)
-        err = self.loss_fn(pred, gt, reduction='none')
-        eps = 1e-12
-        elem_ratio = err.numel() / valid.numel()
-        return (err * valid.float()).sum() / (valid.float().sum() * elem_ratio + eps)
+                raise TypeError(f"metric {self.metric!r} does not take a validity mask")
+            return _REDUCED[self.metric](diff)
+        err = _ELEMENTWISE[self.metric](diff)
+        return err.mean() if valid is None else _masked_mean(err, valid)
 
 
 class PSNR(nn.Module):
@@ -121,20 +128,14 @@ class SSIM(nn.Module):
 
 
 class AlignedL2(nn.Module):
-    """ Computes L2 error after performing spatial and color alignment of the input image to GT"""
+    """L2 error after spatial and colour alignment of the prediction to the ground truth (reference :166-191), over the valid
+    pixels of the whole batch; the two masked sums come from one fused launch (`dbsr_mse_per_image` with the mask)."""
     def __init__(self, alignment_net, sr_factor=4, boundary_ignore=None):
         super().__init__()
         self.sca = sca_utils.SpatialColorAlignment(alignment_net, sr_factor)
         self.boundary_ignore = boundary_ignore
 
     def forward(self, pred, gt, burst_input):
-        pred_warped_m, valid = self.sca(pred, gt, burst_input)
-        if self.boundary_ignore is not None:
-            b = self.boundary_ignore
-            pred_warped_m = pred_warped_m[..., b:-b, b:-b]
-            gt = gt[..., b:-b, b:-b]
-            valid = valid[..., b:-b, b:-b]
-        mse = F.mse_loss(pred_warped_m, gt, reduction='none')
-        eps = 1e-12
-        elem_ratio = mse.numel() / valid.numel()
-        return (mse * valid.float()).sum() / (valid.float().sum() * elem_ratio + eps)
+        aligned, valid = self.sca(pred, gt, burst_input)
+        sums = ops.mse_per_image(aligned.contiguous(), gt.contiguous(), crop=self.boundary_ignore or 0, valid=valid, raw=True)
+        return sums[:, 0].sum() / (sums[:, 1].sum() + 1e-12)

@@ -24,32 +24,37 @@ def _color_apply(im, c_mat):
     return (im.unsqueeze(2) * c_mat.unsqueeze(-1).unsqueeze(-1)).sum(dim=1)
 
 
+_COLOR_ERR_THRESHOLD = 20      # on the 0..255 scale (:48-50)
+_TRIM = 5                      # pixels dropped on every side after the 7x7 blur (:27-31)
+
+
+def _fit_color_matrix(src, dst):
+    """Per image, the 3x3 matrix X minimising || src^T X - dst^T || over the pixels (src, dst: [B, 3, h, w]) -- what the
+    reference obtains from `torch.lstsq(dst.t(), src.t())` (:40-42; removed from torch 2.x).  Solved for the whole batch as
+    fp64 normal equations of the [P, 3] systems: exact enough, and no host round trip."""
+    A = src.flatten(2).transpose(1, 2).double()
+    Bm = dst.flatten(2).transpose(1, 2).double()
+    At = A.transpose(1, 2)
+    return torch.linalg.solve(At @ A, At @ Bm).float()
+
+
 def match_colors(im_ref, im_q, im_test, ksz, gauss_kernel):
-    """Estimates a colour transformation matrix between im_ref and im_q and applies it to im_test
-    (spatial_color_alignment.py:23-69)."""
+    """Estimates a colour transformation matrix between im_ref and im_q and applies it to im_test; also returns the mask of
+    pixels whose blurred colours agree after the transformation (spatial_color_alignment.py:23-69)."""
     ops.require_device(im_ref)
-    gauss_kernel = gauss_kernel.to(im_ref.device)
-    bi = 5
-    im_ref_mean = apply_kernel(im_ref, ksz, gauss_kernel)[:, :, bi:-bi, bi:-bi].contiguous()
-    im_q_mean = apply_kernel(im_q, ksz, gauss_kernel)[:, :, bi:-bi, bi:-bi].contiguous()
-    im_ref_mean_re = im_ref_mean.view(*im_ref_mean.shape[:2], -1)
-    im_q_mean_re = im_q_mean.view(*im_q_mean.shape[:2], -1)
-    # least squares per image: argmin_X || iq^T X - ir^T ||  (the reference's removed torch.lstsq(ir.t(), iq.t()), :40-42),
-    # batched over the images; fp64 normal equations of a [P, 3] system are exact enough and need no host round trip
-    A = im_q_mean_re.permute(0, 2, 1).double()
-    Bm = im_ref_mean_re.permute(0, 2, 1).double()
-    c_mat = torch.linalg.solve(A.transpose(1, 2) @ A, A.transpose(1, 2) @ Bm).float()
-    im_q_mean_conv = _color_apply(im_q_mean, c_mat)
-    err = ((im_q_mean_conv - im_ref_mean) * 255.0).norm(dim=1)
-    thresh = 20
-    valid = err < thresh
-    pad = (im_q.shape[-1] - valid.shape[-1]) // 2
-    valid = F.pad(valid, [pad, pad, pad, pad])
-    upsample_factor = im_test.shape[-1] / valid.shape[-1]
-    valid = F.interpolate(valid.unsqueeze(1).float(), scale_factor=upsample_factor, mode='bilinear')
-    valid = valid > 0.9
-    im_t_conv = _color_apply(im_test, c_mat)
-    return im_t_conv, valid
+    kernel = gauss_kernel.to(im_ref.device)
+    t = _TRIM
+    ref_blur = apply_kernel(im_ref, ksz, kernel)[:, :, t:-t, t:-t].contiguous()
+    qry_blur = apply_kernel(im_q, ksz, kernel)[:, :, t:-t, t:-t].contiguous()
+    c_mat = _fit_color_matrix(qry_blur, ref_blur)
+    # colour error of the fit, as a mask at the resolution of im_test
+    residual = (_color_apply(qry_blur, c_mat) - ref_blur) * 255.0
+    agree = residual.norm(dim=1) < _COLOR_ERR_THRESHOLD
+    border = (im_q.shape[-1] - agree.shape[-1]) // 2
+    agree = F.pad(agree, [border] * 4)
+    scale = im_test.shape[-1] / agree.shape[-1]
+    valid = F.interpolate(agree.unsqueeze(1).float(), scale_factor=scale, mode='bilinear') > 0.9
+    return _color_apply(im_test, c_mat), valid
 
 
 class SpatialColorAlignment(nn.Module):

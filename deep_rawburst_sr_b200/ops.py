@@ -339,9 +339,10 @@ def avgpool2_pair(img1: torch.Tensor, img2: torch.Tensor):
     return o1, o2
 
 
-def mse_per_image(pred: torch.Tensor, gt: torch.Tensor, crop: int = 0, valid: Optional[torch.Tensor] = None) -> torch.Tensor:
+def mse_per_image(pred: torch.Tensor, gt: torch.Tensor, crop: int = 0, valid: Optional[torch.Tensor] = None, raw: bool = False) -> torch.Tensor:
     """[n] mean squared error of each image over its interior (boundary_ignore = crop), one launch for the batch.
-    valid ([n, 1, h, w] mask): the masked form (err * valid).sum() / (valid.sum() * C + 1e-12) of image_quality_v2.py:60-64."""
+    valid ([n, 1, h, w] mask): the masked form (err * valid).sum() / (valid.sum() * C + 1e-12) of image_quality_v2.py:60-64;
+    raw=True returns its two sums per image, [n, 2], for a batch-wide ratio."""
     _check_image_pair(pred, gt)
     vb = _mask_bytes(valid, pred)
     n, c, h, w = pred.shape
@@ -350,7 +351,9 @@ def mse_per_image(pred: torch.Tensor, gt: torch.Tensor, crop: int = 0, valid: Op
     out = torch.empty((n, 2) if vb is not None else (n,), dtype=torch.float32, device=pred.device)
     _lib.check(lib.dbsr_mse_per_image(pred.data_ptr(), gt.data_ptr(), _ptr(vb), n, c, h, w, crop, ws.data_ptr(), out.data_ptr(),
                                       _stream()), 'dbsr_mse_per_image')
-    return out if vb is None else out[:, 0] / (out[:, 1] + 1e-12)
+    if vb is None or raw:
+        return out
+    return out[:, 0] / (out[:, 1] + 1e-12)
 
 
 # ---- synthetic burst generation: inverse camera pipeline (include/dbsr_b200.h) ------------------------------------------------
