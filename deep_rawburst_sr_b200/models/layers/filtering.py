@@ -5,22 +5,23 @@ import torch
 
 
 def gauss_1d(sz, sigma, center, end_pad=0, density=False):
-    k = torch.arange(-(sz - 1) / 2, (sz + 1) / 2 + end_pad).reshape(1, -1)
-    gauss = torch.exp(-1.0 / (2 * sigma ** 2) * (k - center.reshape(-1, 1)) ** 2)
-    if density:
-        gauss /= math.sqrt(2 * math.pi) * sigma
-    return gauss
+    """rows of exp(-(k - c)^2 / (2 sigma^2)) on the symmetric grid k = -(sz-1)/2 ... (sz-1)/2 (+ end_pad), one per centre c"""
+    half = (sz - 1) / 2
+    grid = torch.arange(-half, half + 1 + end_pad).reshape(1, -1)
+    values = torch.exp((grid - center.reshape(-1, 1)) ** 2 * (-1.0 / (2 * sigma ** 2)))
+    return values / (math.sqrt(2 * math.pi) * sigma) if density else values
 
 
 def gauss_2d(sz, sigma, center, end_pad=(0, 0), density=False):
-    if isinstance(sigma, (float, int)):
-        sigma = (sigma, sigma)
-    if isinstance(sz, int):
-        sz = (sz, sz)
+    """outer product of two 1-D Gaussians per centre: [n_centres, sz_y (+pad), sz_x (+pad)]"""
+    sigma = (sigma, sigma) if isinstance(sigma, (float, int)) else sigma
+    sz = (sz, sz) if isinstance(sz, int) else sz
     if isinstance(center, (list, tuple)):
         center = torch.tensor(center).view(1, 2)
-    return gauss_1d(sz[0], sigma[0], center[:, 0], end_pad[0], density).reshape(center.shape[0], 1, -1) * \
-        gauss_1d(sz[1], sigma[1], center[:, 1], end_pad[1], density).reshape(center.shape[0], -1, 1)
+    n = center.shape[0]
+    along_x = gauss_1d(sz[0], sigma[0], center[:, 0], end_pad[0], density).reshape(n, 1, -1)
+    along_y = gauss_1d(sz[1], sigma[1], center[:, 1], end_pad[1], density).reshape(n, -1, 1)
+    return along_x * along_y
 
 
 def get_gaussian_kernel(sd, ksz=None):
