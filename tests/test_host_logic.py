@@ -123,3 +123,43 @@ def test_gaussian_filter_glue_matches_oracle():
     assert (K[0, 0] - Ko).abs().max() < 1e-7 and abs(float(K.sum()) - 1.0) < 1e-6
     x = torch.rand(2, 3, 11, 9, generator=torch.Generator().manual_seed(3))
     assert (apply_kernel(x, ksz, K) - S.apply_kernel(x, ksz, Ko)).abs().max() < 1e-6
+
+
+def test_generator_transform_sampling_matches_reference_draws(golden_dir):
+    """host logic of the burst generator: under the same `random` seed, `sample_transforms` / `get_tmat` (with
+    cv2.getRotationMatrix2D written out) reproduce the matrices the reference's `single2lrburst` drew (recorded by
+    oracle/make_golden_lrburst.py) to the last bits, frame 0 being the pure half-pixel shift."""
+    import os
+    import random
+    import numpy as np
+    from deep_rawburst_sr_b200.data import synthetic_burst_generation as G
+    from oracle.make_golden_lrburst import CASES
+    for name, seed, H, W, n, f, crop, params in CASES:
+        g = np.load(os.path.join(golden_dir, name + '.npz'))
+        random.seed(seed)
+        t_mats = np.stack(G.sample_transforms((H, W), n, f, dict(params)))
+        assert t_mats.shape == g['t_mats'].shape and np.abs(t_mats - g['t_mats']).max() <= 1e-12
+        shift = f / 2.0 - 0.5
+        assert np.array_equal(t_mats[0], np.array([[1.0, 0.0, shift], [0.0, 1.0, shift]]))
+    # the inverse map handed to the kernel is the exact inverse of the forward matrix
+    M = G._inverse_map(t_mats[1])
+    fwd = np.vstack([t_mats[1], [0, 0, 1]])
+    inv = np.vstack([M.reshape(2, 3), [0, 0, 1]])
+    assert np.abs(fwd @ inv - np.eye(3)).max() <= 1e-9
+
+
+def test_scoring_loops_refuse_unknown_metrics_and_format_like_the_reference():
+    from deep_rawburst_sr_b200.evaluation.burstsr import compute_score as burstsr
+    from deep_rawburst_sr_b200.evaluation.synburst import compute_score as synburst
+    import pytest
+    with pytest.raises(NotImplementedError):
+        synburst.score_dataset(None, [], metrics=('psnr', 'lpips'))
+    with pytest.raises(NotImplementedError):
+        burstsr.score_dataset(None, [], None, metrics=('lpips',))
+    text = synburst.generate_formatted_report({'DBSR': {'psnr': 39.0912, 'ssim': 0.9512, 'count': 300}})
+    assert text == '\n          | psnr       | ssim       |\nDBSR      | 39.091     | 0.951      |\n'
+    data = synburst.TensorBurstSet(torch.zeros(3, 2, 4, 8, 8), torch.zeros(3, 3, 64, 64))
+    burst, gt, meta = data[1]
+    assert len(data) == 3 and burst.shape == (2, 4, 8, 8) and gt.shape == (3, 64, 64) and meta['burst_name'] == '0001'
+    b, g = data.batch(1, 3)
+    assert b.shape[0] == 2 and g.shape[0] == 2
