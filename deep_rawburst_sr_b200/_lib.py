@@ -14,6 +14,7 @@ LIB_PATH = os.path.join(_HERE, 'csrc', 'libdbsr_b200.so')
 
 DBSR_F32, DBSR_BF16 = 0, 1
 ACT_NONE, ACT_RELU, ACT_LRELU = 0, 1, 2
+CORR_AUTO, CORR_CUDA_CORES = 0, 1
 
 
 class NhwcView(ctypes.Structure):
@@ -27,7 +28,8 @@ class ConvDesc(ctypes.Structure):
     """struct dbsr_conv (include/dbsr_b200.h)."""
     _fields_ = [('x', NhwcView), ('y', NhwcView), ('residual', NhwcView), ('w', ctypes.c_void_p),
                 ('bias', ctypes.c_void_p), ('ksize', ctypes.c_int32), ('stride', ctypes.c_int32),
-                ('dilation', ctypes.c_int32), ('act', ctypes.c_int32), ('shuffle_r', ctypes.c_int32)]
+                ('dilation', ctypes.c_int32), ('act', ctypes.c_int32), ('shuffle_r', ctypes.c_int32),
+                ('grid_limit', ctypes.c_int32)]
 
 
 _VP = ctypes.c_void_p
@@ -49,7 +51,6 @@ PROTOTYPES = {
     'dbsr_conv2d_direct': (_I, [_PC, _VP]),
     'dbsr_conv2d_tc': (_I, [_PC, _VP]),
     'dbsr_conv2d_tc_supported': (_I, [_PC]),
-    'dbsr_conv2d_tc_set_grid_limit': (_I, [_I]),
     'dbsr_conv2d_tc_predictor': (_I, [_PC, _VP, _VP, _I, _VP, _I, _VP]),
     'dbsr_quantize_q14': (_I, [_VP, _VP, ctypes.c_int64, _VP]),
     'dbsr_conv2d_tc_geometry': (_I, [_I, _I, ctypes.POINTER(_I), ctypes.POINTER(_I), ctypes.POINTER(_I),
@@ -57,8 +58,7 @@ PROTOTYPES = {
     'dbsr_space_to_depth2': (_I, [_PV, _PV, _VP]),
     'dbsr_deconv4x4s2': (_I, [_PV, _VP, _VP, _PV, _PV, _VP]),
     'dbsr_deconv_col2im': (_I, [_PV, _VP, _PV, _PV, _VP, _VP, _PV, _PV, _VP]),
-    'dbsr_corr81': (_I, [_PV, _PV, _PV, _F, _PV, _I, _I, _I, _VP]),
-    'dbsr_corr81_set_tensor_core': (_I, [_I]),
+    'dbsr_corr81': (_I, [_PV, _PV, _PV, _F, _PV, _I, _I, _I, _I, _VP]),
     'dbsr_flow_head': (_I, [_PV, _VP, _I, _I, _I, _I, _VP]),
     'dbsr_warp': (_I, [_PV, _VP, _PV, _I, _VP]),
     'dbsr_offsets_mod': (_I, [_VP, _PV, _I, _I, _F, _VP]),

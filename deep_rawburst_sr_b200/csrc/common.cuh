@@ -96,4 +96,13 @@ inline void launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t sme
 
 inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
 
+// Host-side caches (function attributes already set, SM counts, identity tiles) are kept PER DEVICE: a process may drive
+// several GPUs (nn.DataParallel style), and cudaFuncSetAttribute / cudaMalloc act on the current device only.
+constexpr int MAX_DEVICES = 64;
+inline int current_device_slot() {
+  int d = 0;
+  if (cudaGetDevice(&d) != cudaSuccess || d < 0 || d >= MAX_DEVICES) d = 0;
+  return d;
+}
+
 }  // namespace dbsr

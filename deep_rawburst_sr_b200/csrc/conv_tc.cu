@@ -28,6 +28,9 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <mutex>
+#include <vector>
+
 namespace dbsr {
 
 // ---------------------------------------------------------------------------------------------------------
@@ -1063,24 +1066,28 @@ static void tc_geometry(int cin, int cout, int* ck, int* kpad, int* n_tile, int*
   *cout_pad = round_up(cout, nt);
 }
 
-__global__ void fill_identity_kernel(__nv_bfloat16* w, int n) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n * n) w[i] = __float2bfloat16_rn((i / n) == (i % n) ? 1.0f : 0.0f);
-}
-
-// [n][n] bf16 identity ("weights" of the residual K chunks), created once per n and kept for the process lifetime
+// [n][n] bf16 identity ("weights" of the residual K chunks), created once per (device, n) and kept for the process
+// lifetime.  Creation is synchronous (cudaMalloc + blocking cudaMemcpy) so that the tile is complete before ANY stream of
+// the device can read it; it therefore cannot happen inside a stream capture (the engine always runs a layer eagerly before
+// capturing it).
 static const void* identity_weights(int n, cudaStream_t st) {
-  static void* cache[17] = {nullptr};
+  static std::mutex mu;
+  static void* cache[MAX_DEVICES][17] = {};
   const int slot = n / 16;
   if (slot < 1 || slot > 16) return nullptr;
-  if (!cache[slot]) {
+  std::lock_guard<std::mutex> lock(mu);
+  void*& entry = cache[current_device_slot()][slot];
+  if (!entry) {
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(st, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) { cudaGetLastError(); return nullptr; }
+    std::vector<__nv_bfloat16> host((size_t)n * n, __float2bfloat16_rn(0.0f));
+    for (int i = 0; i < n; ++i) host[(size_t)i * n + i] = __float2bfloat16_rn(1.0f);
     void* ptr = nullptr;
     if (cudaMalloc(&ptr, (size_t)n * n * 2) != cudaSuccess) { cudaGetLastError(); return nullptr; }
-    fill_identity_kernel<<<(n * n + 255) / 256, 256, 0, st>>>(reinterpret_cast<__nv_bfloat16*>(ptr), n);
-    if (cudaGetLastError() != cudaSuccess) return nullptr;
-    cache[slot] = ptr;
+    if (cudaMemcpy(ptr, host.data(), (size_t)n * n * 2, cudaMemcpyHostToDevice) != cudaSuccess) { cudaGetLastError(); cudaFree(ptr); return nullptr; }
+    entry = ptr;
   }
-  return cache[slot];
+  return entry;
 }
 
 struct TcConfig {
@@ -1229,11 +1236,12 @@ static dbsr_conv_t centre_tap_form(const dbsr_conv_t* c) {
   return cc;
 }
 
-static int g_grid_limit = 0;     // dbsr_conv2d_tc_set_grid_limit: CTAs per launch (0 = one per SM)
 template <int CK, bool RESIDENT>
 static int launch_tc(const CUtensorMap& mx, const CUtensorMap& mw, const CUtensorMap& mr, const CUtensorMap& mi,
-                     const CUtensorMap& my, const ConvTcParams& p, int smem, cudaStream_t st) {
-  static int configured_smem = 0;
+                     const CUtensorMap& my, const ConvTcParams& p, int smem, int grid_limit, cudaStream_t st) {
+  const int dev_slot = current_device_slot();
+  static int configured_smem_dev[MAX_DEVICES] = {};
+  int& configured_smem = configured_smem_dev[dev_slot];
   if (smem > configured_smem) {
     cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<CK, RESIDENT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) {
@@ -1242,14 +1250,15 @@ static int launch_tc(const CUtensorMap& mx, const CUtensorMap& mw, const CUtenso
     }
     configured_smem = smem;
   }
-  static int num_sms = 0;
+  static int num_sms_dev[MAX_DEVICES] = {};
+  int& num_sms = num_sms_dev[dev_slot];
   if (!num_sms) {
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
   }
   int grid = (int)(p.total_items < num_sms ? p.total_items : num_sms);
-  if (g_grid_limit > 0 && grid > g_grid_limit) grid = g_grid_limit;
+  if (grid_limit > 0 && grid > grid_limit) grid = grid_limit;
   // programmatic dependent launch: CTAs may be scheduled (barrier init, tensor-map prefetch, TMEM allocation) as soon as
   // the SMs of the preceding kernel drain; the kernel calls griddepcontrol.wait before its first global access
   static const bool pdl = getenv("DBSR_TC_NO_PDL") == nullptr;     // A/B switch: DBSR_TC_NO_PDL=1 launches normally
@@ -1341,7 +1350,7 @@ static int conv2d_tc_impl(const dbsr_conv_t* c_in, void* stream, const float* pr
     }
     {
       const void* eye = identity_weights(cfg.n_tile, (cudaStream_t)stream);
-      DBSR_REQUIRE(eye != nullptr, "conv2d_tc: could not create the identity weight tile (cudaMalloc inside a graph capture?)");
+      DBSR_REQUIRE(eye != nullptr, "conv2d_tc: could not create the identity weight tile (first call of this N tile inside a stream capture? run the layer once eagerly)");
       cuuint64_t dims[2] = {(cuuint64_t)cfg.n_tile, (cuuint64_t)cfg.n_tile};
       cuuint64_t strides[1] = {(cuuint64_t)cfg.n_tile * 2};
       cuuint32_t box[2] = {(cuuint32_t)cfg.ck, (cuuint32_t)cfg.n_tile};
@@ -1444,10 +1453,11 @@ static int conv2d_tc_impl(const dbsr_conv_t* c_in, void* stream, const float* pr
     }
   }
   cudaStream_t st = (cudaStream_t)stream;
-  if (cfg.ck == 64) return cfg.b_resident ? launch_tc<64, true>(mx, mw, mr, mi, my, p, cfg.smem_bytes, st)
-                                          : launch_tc<64, false>(mx, mw, mr, mi, my, p, cfg.smem_bytes, st);
-  return cfg.b_resident ? launch_tc<32, true>(mx, mw, mr, mi, my, p, cfg.smem_bytes, st)
-                        : launch_tc<32, false>(mx, mw, mr, mi, my, p, cfg.smem_bytes, st);
+  const int gl = c_in->grid_limit;
+  if (cfg.ck == 64) return cfg.b_resident ? launch_tc<64, true>(mx, mw, mr, mi, my, p, cfg.smem_bytes, gl, st)
+                                          : launch_tc<64, false>(mx, mw, mr, mi, my, p, cfg.smem_bytes, gl, st);
+  return cfg.b_resident ? launch_tc<32, true>(mx, mw, mr, mi, my, p, cfg.smem_bytes, gl, st)
+                        : launch_tc<32, false>(mx, mw, mr, mi, my, p, cfg.smem_bytes, gl, st);
 }
 
 extern "C" int dbsr_conv2d_tc(const dbsr_conv_t* c, void* stream) {
@@ -1460,7 +1470,3 @@ extern "C" int dbsr_conv2d_tc_predictor(const dbsr_conv_t* c, const float* pred_
   return conv2d_tc_impl(c, stream, pred_w, pred_b, pred_c, pred, pred_q14);
 }
 
-extern "C" int dbsr_conv2d_tc_set_grid_limit(int32_t ctas) {
-  g_grid_limit = ctas > 0 ? ctas : 0;
-  return 0;
-}

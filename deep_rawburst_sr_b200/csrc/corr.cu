@@ -608,14 +608,8 @@ __global__ void __launch_bounds__(CORR_SMALL_THREADS) corr81_small_kernel(const 
 
 using namespace dbsr;
 
-static int g_corr_tensor_core = 1;
-extern "C" int dbsr_corr81_set_tensor_core(int32_t on) {
-  g_corr_tensor_core = on ? 1 : 0;
-  return 0;
-}
-
 extern "C" int dbsr_corr81(const dbsr_nhwc_t* f1, const dbsr_nhwc_t* f2, const dbsr_nhwc_t* flow, float flow_scale,
-                           const dbsr_nhwc_t* out, int32_t pairs, int32_t group, int32_t act, void* stream) {
+                           const dbsr_nhwc_t* out, int32_t pairs, int32_t group, int32_t act, int32_t mode, void* stream) {
   DBSR_REQUIRE(view_ok(f1) && view_ok(f2) && view_ok(out), "corr81: bad views");
   DBSR_REQUIRE(f1->h == f2->h && f1->w == f2->w && f1->c == f2->c && out->h == f1->h && out->w == f1->w &&
                    out->c == 81 && out->n == pairs, "corr81: geometry mismatch");
@@ -648,7 +642,8 @@ extern "C" int dbsr_corr81(const dbsr_nhwc_t* f1, const dbsr_nhwc_t* f2, const d
   const size_t small_smem = (size_t)2 * f1->h * f1->w * cp_small * sizeof(float);
   if (vec && f1->h * f1->w <= 64 && small_smem <= 160 * 1024) {
     void (*ks)(const CorrParams) = f1->dtype == DBSR_BF16 ? corr81_small_kernel<__nv_bfloat16> : corr81_small_kernel<float>;
-    static size_t configured[2] = {0, 0};
+    static size_t configured_dev[MAX_DEVICES][2] = {};
+    size_t* configured = configured_dev[current_device_slot()];
     const int si = f1->dtype == DBSR_BF16 ? 0 : 1;
     if (small_smem > 48 * 1024 && small_smem > configured[si]) {
       cudaError_t e = cudaFuncSetAttribute(ks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)small_smem);
@@ -659,7 +654,7 @@ extern "C" int dbsr_corr81(const dbsr_nhwc_t* f1, const dbsr_nhwc_t* f2, const d
     return check_launch("corr81");
   }
   // bf16 maps with C in {32, 64, 96, 128}: banded product on the tensor cores (mma.sync), see corr81_mma_kernel
-  if (vec && g_corr_tensor_core && f1->dtype == DBSR_BF16 && f1->c % 16 == 0 && f1->c >= 32 && f1->c <= 128 && f1->c != 48 &&
+  if (vec && mode != DBSR_CORR_CUDA_CORES && f1->dtype == DBSR_BF16 && f1->c % 16 == 0 && f1->c >= 32 && f1->c <= 128 && f1->c != 48 &&
       f1->c != 80 && f1->c != 112 && (long long)f1->h * f1->w * (f1->c_pitch > f2->c_pitch ? f1->c_pitch : f2->c_pitch) * 2 < (1ll << 31)) {
     void (*km)(const CorrParams) = nullptr;
     int smem = 0, ki = 0;
@@ -669,7 +664,8 @@ extern "C" int dbsr_corr81(const dbsr_nhwc_t* f1, const dbsr_nhwc_t* f2, const d
       case 6: km = corr81_mma_kernel<6>; smem = CorrMma<6>::SMEM; ki = 2; break;
       default: km = corr81_mma_kernel<8>; smem = CorrMma<8>::SMEM; ki = 3; break;
     }
-    static bool mma_attr[4] = {false, false, false, false};
+    static bool mma_attr_dev[MAX_DEVICES][4] = {};
+    bool* mma_attr = mma_attr_dev[current_device_slot()];
     if (!mma_attr[ki]) {
       cudaError_t e = cudaFuncSetAttribute(km, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
       DBSR_REQUIRE(e == cudaSuccess, "corr81: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
@@ -682,7 +678,8 @@ extern "C" int dbsr_corr81(const dbsr_nhwc_t* f1, const dbsr_nhwc_t* f2, const d
   }
   void (*kern)(const CorrParams) = !vec ? corr81_kernel<false, float>
                                    : (f1->dtype == DBSR_BF16 ? corr81_kernel<true, __nv_bfloat16> : corr81_kernel<true, float>);
-  static bool attr_set[3] = {false, false, false};
+  static bool attr_set_dev[MAX_DEVICES][3] = {};
+  bool* attr_set = attr_set_dev[current_device_slot()];
   const int ki = !vec ? 0 : (f1->dtype == DBSR_BF16 ? 1 : 2);
   if (!attr_set[ki]) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, CORR_SMEM);

@@ -708,7 +708,8 @@ extern "C" int dbsr_softmax_wsum(const dbsr_nhwc_t* feat, const dbsr_nhwc_t* log
     // records hold 32-bit byte offsets inside one image and at most WSP_MAX_OTHERS non-reference frames
     if (key == 7 && offsets != nullptr && frames >= 2 && frames - 1 <= WSP_MAX_OTHERS &&
         (long long)fused->h * fused->w * feat->c_pitch * 2 < (1ll << 32)) {
-      static bool attr_set = false;
+      static bool attr_set_dev[MAX_DEVICES] = {};
+      bool& attr_set = attr_set_dev[current_device_slot()];
       if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(softmax_wsum8_pair_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, WSP_SMEM);
         DBSR_REQUIRE(e == cudaSuccess, "softmax_wsum: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));

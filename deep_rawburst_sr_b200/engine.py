@@ -62,39 +62,50 @@ class PwcLayout:
         return cm, start, self.total - start
 
 
-def pack_direct(w: torch.Tensor, chmap=None, cin_buf: Optional[int] = None) -> torch.Tensor:
-    """[Cout, Cin, k, k] -> fp32 [k*k, Cin_buf, Cout] (rows of padded channels are zero)."""
+# Weight packing runs on the HOST (CPU tensors in, one H2D copy per packed tensor out): building an engine issues no
+# device kernels, so a profiler's launch list of a forward starts with the forward's own kernels.
+def _host(t: torch.Tensor) -> torch.Tensor:
+    return t.detach().to('cpu', torch.float32)
+
+
+def pack_direct(w: torch.Tensor, chmap=None, cin_buf: Optional[int] = None, device=None) -> torch.Tensor:
+    """[Cout, Cin, k, k] -> fp32 [k*k, Cin_buf, Cout] (rows of padded channels are zero).  Packed on the host; the result
+    lands on `device` (default: the device of `w`)."""
+    device = w.device if device is None else device
+    w = _host(w)
     cout, cin, kh, kw = w.shape
     cin_buf = cin if cin_buf is None else cin_buf
-    out = torch.zeros((kh * kw, cin_buf, cout), dtype=torch.float32, device=w.device)
-    src = w.float().permute(2, 3, 1, 0).reshape(kh * kw, cin, cout)
+    out = torch.zeros((kh * kw, cin_buf, cout), dtype=torch.float32)
+    src = w.permute(2, 3, 1, 0).reshape(kh * kw, cin, cout)
     if chmap is None:
         out[:, :cin] = src
     else:
-        out[:, torch.as_tensor(chmap, device=w.device)] = src
-    return out.contiguous()
+        out[:, torch.as_tensor(chmap)] = src
+    return out.contiguous().to(device)
 
 
-def pack_tc(w: torch.Tensor, shuffle_r: int = 0, chmap=None, cin_buf: Optional[int] = None) -> torch.Tensor:
+def pack_tc(w: torch.Tensor, shuffle_r: int = 0, chmap=None, cin_buf: Optional[int] = None, device=None) -> torch.Tensor:
     """[Cout, Cin, k, k] -> bf16 [k*k, cout_pad, kpad] K-major for dbsr_conv2d_tc; (kpad, cout_pad) come from the
     kernel's own tiling rule (dbsr_conv2d_tc_geometry).  Padded rows / columns are zero.  `chmap`/`cin_buf`: input
     channel -> position inside a padded concat slice.  shuffle_r = 8: rows permuted to (i, j, c) order so that an N
     tile is contiguous in the pixel-shuffled output (nn.PixelShuffle: co = c*r*r + i*r + j)."""
+    device = w.device if device is None else device
+    w = _host(w)
     cout, cin, kh, kw = w.shape
     cin_buf = cin if cin_buf is None else cin_buf
     _ck, kpad, _nt, cout_pad = ops.conv2d_tc_geometry(cin_buf, cout)
-    src = w.float()
+    src = w
     if shuffle_r and shuffle_r > 1:
         r = shuffle_r
         c = cout // (r * r)
         src = src.view(c, r, r, cin, kh, kw).permute(1, 2, 0, 3, 4, 5).reshape(cout, cin, kh, kw)
-    out = torch.zeros((kh * kw, cout_pad, kpad), dtype=torch.float32, device=w.device)
+    out = torch.zeros((kh * kw, cout_pad, kpad), dtype=torch.float32)
     src = src.permute(2, 3, 0, 1).reshape(kh * kw, cout, cin)
     if chmap is None:
         out[:, :cout, :cin] = src
     else:
-        out[:, :cout, torch.as_tensor(chmap, device=w.device)] = src
-    return out.to(torch.bfloat16).contiguous()
+        out[:, :cout, torch.as_tensor(chmap)] = src
+    return out.to(torch.bfloat16).contiguous().to(device)
 
 
 def permute_shuffle_rows(t: torch.Tensor, r: int) -> torch.Tensor:
@@ -118,17 +129,19 @@ def pack_s2d_weight(w: torch.Tensor) -> torch.Tensor:
     return out
 
 
-def pack_deconv(w: torch.Tensor, chmap=None, cin_buf: Optional[int] = None) -> torch.Tensor:
+def pack_deconv(w: torch.Tensor, chmap=None, cin_buf: Optional[int] = None, device=None) -> torch.Tensor:
     """ConvTranspose2d weight [Cin, 2, 4, 4] -> fp32 [4, 4, 2, Cin_buf]."""
+    device = w.device if device is None else device
+    w = _host(w)
     cin = w.shape[0]
     cin_buf = cin if cin_buf is None else cin_buf
-    out = torch.zeros((4, 4, 2, cin_buf), dtype=torch.float32, device=w.device)
-    src = w.float().permute(2, 3, 1, 0)
+    out = torch.zeros((4, 4, 2, cin_buf), dtype=torch.float32)
+    src = w.permute(2, 3, 1, 0)
     if chmap is None:
         out[..., :cin] = src
     else:
-        out[..., torch.as_tensor(chmap, device=w.device)] = src
-    return out.contiguous()
+        out[..., torch.as_tensor(chmap)] = src
+    return out.contiguous().to(device)
 
 
 class ConvW:
@@ -139,7 +152,7 @@ class ConvW:
             direct, tc, bias, ksize, cout, cin, shuffle_r
         self.bias_tc = bias
         if bias is not None and shuffle_r and shuffle_r > 1:   # the tensor-core path stores in (i, j, c) row order
-            self.bias_tc = permute_shuffle_rows(bias, shuffle_r)
+            self.bias_tc = permute_shuffle_rows(bias.cpu(), shuffle_r).to(bias.device)
 
 
 class DBSREngine:
@@ -174,7 +187,7 @@ class DBSREngine:
         self.timers = None   # when a dict: family -> list of (start, end) CUDA events on the launching stream
         self.flops = {}      # family -> algorithmic FLOPs (2*MAC, real channel counts) launched since reset
         self.hbm_bytes = {}  # family -> algorithmic HBM bytes (input + output + residual maps, once each) since reset
-        sd = {k: v.detach().to(self.device) for k, v in state_dict.items()}
+        sd = {k: _host(v) for k, v in state_dict.items()}      # packing happens on the host, see pack_*
         if 'pwc' in parts:
             self._pack_pwc(sd)
         if 'encoder' in parts or 'merging' in parts or 'decoder' in parts:
@@ -192,10 +205,10 @@ class DBSREngine:
     # weight packing
     # ------------------------------------------------------------------------------------------------
     def _add(self, key, w, b, tc=False, chmap=None, cin_buf=None, shuffle_r=0):
-        direct = pack_direct(w, chmap, cin_buf)
-        tcw = pack_tc(w, shuffle_r, chmap, cin_buf) if tc else None
-        self.W[key] = ConvW(direct, tcw, None if b is None else b.float().contiguous(), w.shape[2], w.shape[0], w.shape[1],
-                             shuffle_r)
+        direct = pack_direct(w, chmap, cin_buf, self.device)
+        tcw = pack_tc(w, shuffle_r, chmap, cin_buf, self.device) if tc else None
+        self.W[key] = ConvW(direct, tcw, None if b is None else b.float().contiguous().to(self.device), w.shape[2], w.shape[0],
+                             w.shape[1], shuffle_r)
 
     def _pack_pwc(self, sd):
         pre = self.pwc_prefix
@@ -219,12 +232,12 @@ class DBSREngine:
                 prev = self.pwc_layouts[lvl + 1]
                 cm, _s, length = prev.chmap_from('o5')
                 k = f'{pre}net{lname}.netUpfeat'
-                self.D[k] = (pack_deconv(sd[k + '.weight'], cm, length), sd[k + '.bias'].float().contiguous())
+                self.D[k] = (pack_deconv(sd[k + '.weight'], cm, length, self.device), sd[k + '.bias'].float().contiguous().to(self.device))
                 # the same transposed conv as a 1x1 conv Cin -> 32 planes (ky, kx, oc) + a scatter (ops.deconv_col2im)
                 w1 = sd[k + '.weight'].permute(2, 3, 1, 0).reshape(32, -1, 1, 1).contiguous()
                 self._add(k + '.taps', w1, None, tc=ptc, chmap=cm, cin_buf=length)
                 k = f'{pre}net{lname}.netUpflow'
-                self.D[k] = (pack_deconv(sd[k + '.weight']), sd[k + '.bias'].float().contiguous())
+                self.D[k] = (pack_deconv(sd[k + '.weight'], device=self.device), sd[k + '.bias'].float().contiguous().to(self.device))
         cm, _s, length = self.pwc_layouts[2].chmap_from('o5')
         for j in range(7):
             k = f'{pre}netRefiner.netMain.{2 * j}'
@@ -279,11 +292,12 @@ class DBSREngine:
             for i in range(self.dec_post):
                 add(f'decoder.post_res_layers.{i}.conv1.0')
                 add(f'decoder.post_res_layers.{i}.conv2.0')
-            self.pred_w = sd['decoder.predictor.0.weight'].float().reshape(sd['decoder.predictor.0.weight'].shape[0], -1).contiguous()
-            self.pred_b = sd['decoder.predictor.0.bias'].float().contiguous()
+            pw = sd['decoder.predictor.0.weight'].float().reshape(sd['decoder.predictor.0.weight'].shape[0], -1).contiguous()
+            pb = sd['decoder.predictor.0.bias'].float().contiguous()
             # host copies for the fused predictor epilogue (its weights travel in the kernel parameters)
-            self.pred_w_host = (ctypes.c_float * self.pred_w.numel())(*self.pred_w.reshape(-1).cpu().tolist())
-            self.pred_b_host = (ctypes.c_float * self.pred_b.numel())(*self.pred_b.cpu().tolist())
+            self.pred_w_host = (ctypes.c_float * pw.numel())(*pw.reshape(-1).tolist())
+            self.pred_b_host = (ctypes.c_float * pb.numel())(*pb.tolist())
+            self.pred_w, self.pred_b = pw.to(self.device), pb.to(self.device)
             self.feat_dim = sd['decoder.init_layer.0.weight'].shape[1]
 
     # ------------------------------------------------------------------------------------------------
@@ -291,7 +305,7 @@ class DBSREngine:
     # ------------------------------------------------------------------------------------------------
     def _conv(self, key: str, x: Act, y: Act, act: int, stride: int = 1, dilation: int = 1,
               residual: Optional[Act] = None, force_direct: bool = False, no_bias: bool = False,
-              real_cin: Optional[int] = None, pred: Optional[torch.Tensor] = None) -> Act:
+              real_cin: Optional[int] = None, pred: Optional[torch.Tensor] = None, grid_limit: int = 0) -> Act:
         cw = self.W[key]
         cin_alg = cw.cin if real_cin is None else real_cin       # algorithmic input channels for the FLOP count
         bias, bias_tc = (None, None) if no_bias else (cw.bias, cw.bias_tc)
@@ -316,9 +330,11 @@ class DBSREngine:
         if pred is not None:
             assert use_tc, 'the fused predictor epilogue exists on the tensor-core path only'
             self.flops[fam] += 2 * x.n * ho * wo * self.pred_w.shape[0] * cw.cout
-            ops.conv2d_tc_predictor(x, cw.tc, bias_tc, y, cw.ksize, act, residual, self.pred_w_host, self.pred_b_host, pred)
+            ops.conv2d_tc_predictor(x, cw.tc, bias_tc, y, cw.ksize, act, residual, self.pred_w_host, self.pred_b_host, pred,
+                                    grid_limit=grid_limit)
         elif use_tc:
-            ops.conv2d(x, cw.tc, bias_tc, y, cw.ksize, stride, dilation, act, residual, cw.shuffle_r, tensor_core=True)
+            ops.conv2d(x, cw.tc, bias_tc, y, cw.ksize, stride, dilation, act, residual, cw.shuffle_r, tensor_core=True,
+                       grid_limit=grid_limit)
         else:
             ops.conv2d(x, cw.direct, bias, y, cw.ksize, stride, dilation, act, residual, cw.shuffle_r)
         self._toc(ev)
@@ -362,10 +378,10 @@ class DBSREngine:
             out[fam] = (sum(a.elapsed_time(b) for a, b in evs), len(evs))
         return out
 
-    def _resblock(self, key: str, x: Act, tmp: Act, y: Act) -> Act:
+    def _resblock(self, key: str, x: Act, tmp: Act, y: Act, grid_limit: int = 0) -> Act:
         """reference models/layers/blocks.py:84-96: relu(x + conv2(relu(conv1(x))))"""
-        self._conv(key + '.conv1.0', x, tmp, ACT_RELU)
-        return self._conv(key + '.conv2.0', tmp, y, ACT_RELU, residual=x)
+        self._conv(key + '.conv1.0', x, tmp, ACT_RELU, grid_limit=grid_limit)
+        return self._conv(key + '.conv2.0', tmp, y, ACT_RELU, residual=x, grid_limit=grid_limit)
 
     def _buf(self, ws: dict, name: str, n, h, w, c, dtype, zero=False) -> Act:
         """workspace buffer; the pixel pitch is rounded up to 8 channels (16-byte rows for TMA / vector access)"""
@@ -501,27 +517,28 @@ class DBSREngine:
     # ------------------------------------------------------------------------------------------------
     # DBSR stages
     # ------------------------------------------------------------------------------------------------
-    def encode(self, ws: dict, enc_in: Act) -> Act:
-        """conv stack of ResEncoderWarpAlignnet (reference models/dbsr/encoders.py:66-72) on all B*N frames."""
+    def encode(self, ws: dict, enc_in: Act, grid_limit: int = 0) -> Act:
+        """conv stack of ResEncoderWarpAlignnet (reference models/dbsr/encoders.py:66-72) on all B*N frames.
+        grid_limit: persistent-grid cap of these launches (per call; > 0 while PWC-Net shares the GPU on a second stream)."""
         F_, H, W = enc_in.n, enc_in.h, enc_in.w
         dt = self.act_dtype
         xa = self._buf(ws, 'enc_a', F_, H, W, self.enc_dim, dt)
         xb = self._buf(ws, 'enc_b', F_, H, W, self.enc_dim, dt)
         xt = self._buf(ws, 'enc_t', F_, H, W, self.enc_dim, dt)
         feat = self._buf(ws, 'feat', F_, H, W, self.feat_dim, dt)
-        self._conv('encoder.init_layer.0', enc_in.slice(0, 4), xa, ACT_RELU)
+        self._conv('encoder.init_layer.0', enc_in.slice(0, 4), xa, ACT_RELU, grid_limit=grid_limit)
         cur, nxt = xa, xb
         for i in range(self.enc_res):
-            self._resblock(f'encoder.res_layers.{i}', cur, xt, nxt)
+            self._resblock(f'encoder.res_layers.{i}', cur, xt, nxt, grid_limit=grid_limit)
             cur, nxt = nxt, cur
-        self._conv('encoder.out_layer.0', cur, feat, ACT_RELU)
+        self._conv('encoder.out_layer.0', cur, feat, ACT_RELU, grid_limit=grid_limit)
         return feat
 
-    def project(self, ws: dict, feat: Act) -> Act:
+    def project(self, ws: dict, feat: Act, grid_limit: int = 0) -> Act:
         """q = W_p . feat (merging.py:75 without bias / ReLU, which follow the warp in `warp_proj`): depends on the
         embeddings only, so the forward runs it before joining the alignment stream"""
         q = self._buf(ws, 'proj_q', feat.n, feat.h, feat.w, self.proj_dim, self.act_dtype)
-        return self._conv('merging.feat_project_layer.0', feat, q, ACT_NONE, no_bias=True)
+        return self._conv('merging.feat_project_layer.0', feat, q, ACT_NONE, no_bias=True, grid_limit=grid_limit)
 
     def merge(self, ws: dict, feat: Act, offsets: torch.Tensor, B: int, N: int,
               weights_out: Optional[torch.Tensor] = None, aligned: bool = False, projected: bool = False) -> Act:
@@ -621,7 +638,8 @@ class DBSREngine:
     @torch.no_grad()
     def forward(self, burst: torch.Tensor, return_weights: bool = False, out: Optional[dict] = None, quantize: bool = False):
         """DBSRNet.forward: burst [B, N, 4, H, W] fp32 CUDA -> pred [B, 3, 8H, 8W], offsets [B, N-1, 2, H, W],
-        fusion_weights [B, N, C, H, W] (only when return_weights)."""
+        fusion_weights [B, N, C, H, W] (only when return_weights).  `out` (optional): preallocated 'pred' / 'offsets' to
+        write into, and 'offsets_in': flows to use INSTEAD of running PWC-Net."""
         assert burst.dim() == 5 and burst.shape[2] == 4, 'burst must be [B, N, 4, H, W]'
         ops.require_device(burst)
         burst = burst.contiguous().float()
@@ -636,7 +654,15 @@ class DBSREngine:
         offsets = out.get('offsets')
         if offsets is None:
             offsets = torch.empty((B * (N - 1), 2, H, W), dtype=torch.float32, device=self.device)
-        if self.overlap_alignment and self.timers is None:
+        given = out.get('offsets_in')      # precomputed flows [B, N-1, 2, H, W]: the alignment network is skipped
+        if given is not None:
+            ops.require_device(given)
+            assert given.numel() == offsets.numel(), 'offsets_in must be [B, N-1, 2, H, W]'
+            offsets.copy_(given.reshape(offsets.shape).float())
+            self.prep(ws, burst, enc_in)
+            feat = self.encode(ws, enc_in)
+            projected = False
+        elif self.overlap_alignment and self.timers is None:
             # PWC-Net (many short launches, most of them on 50-75 of the 148 SMs) and the encoder conv stack (persistent
             # full-grid launches) are independent until the fusion: run them on two streams so that encoder CTAs fill
             # the SMs the small alignment kernels leave idle.  Inside a CUDA-graph capture this becomes a fork / join.
@@ -647,12 +673,8 @@ class DBSREngine:
             self._side.wait_stream(cur)
             with torch.cuda.stream(self._side):
                 self.pwc_burst(ws, pwc_in, B, N, H, W, offsets, s2d0)
-            ops.conv2d_tc_set_grid_limit(self.encoder_grid_limit)
-            try:
-                feat = self.encode(ws, enc_in)
-                self.project(ws, feat)           # needs the embeddings only: before the join
-            finally:
-                ops.conv2d_tc_set_grid_limit(0)
+            feat = self.encode(ws, enc_in, grid_limit=self.encoder_grid_limit)
+            self.project(ws, feat, grid_limit=self.encoder_grid_limit)           # needs the embeddings only: before the join
             cur.wait_stream(self._side)
             projected = True
         else:
@@ -674,21 +696,20 @@ class DBSREngine:
     # ------------------------------------------------------------------------------------------------
     # CUDA-graph replay of the whole forward (launch-bound at small batch: ~400 launches per forward)
     # ------------------------------------------------------------------------------------------------
-    @torch.no_grad()
-    def forward_graphed(self, burst: torch.Tensor, return_weights: bool = False, quantize: bool = False):
-        """Same as forward(), but the launch sequence is captured once per input shape into a CUDA graph and replayed.
-        The returned tensors are the graph's static outputs: they are overwritten by the next call of the same shape."""
-        ops.require_device(burst)
-        burst = burst.contiguous().float()
-        key = (tuple(burst.shape), bool(return_weights), bool(quantize))
+    def graph_entry(self, shape, return_weights: bool = False, quantize: bool = False, slot: int = 0):
+        """(graph, static_in, outs, launches) of the CUDA graph that runs forward() on `static_in` [B, N, 4, H, W] and leaves
+        (pred, offsets, weights) in `outs`; captured on first use.  `slot` selects one of several independent graphs of the
+        same shape, each with its own static input / output buffers (workspaces are shared: graphs of one engine must be
+        replayed on one stream) -- HostPipeline double-buffers with it so that host copies go straight into / out of the
+        graph's buffers."""
+        key = (tuple(shape), bool(return_weights), bool(quantize), int(slot))
         entry = self._graphs.get(key)
         if entry is None:
             assert self.timers is None, 'per-kernel timers cannot be recorded inside a graph capture'
-            static_in = torch.empty_like(burst)
-            static_in.copy_(burst)
+            static_in = torch.zeros(tuple(shape), dtype=torch.float32, device=self.device)
             side = torch.cuda.Stream(device=self.device)
             side.wait_stream(torch.cuda.current_stream())
-            with torch.cuda.stream(side):          # warm-up outside capture: workspaces, smem attributes, tensor maps
+            with torch.cuda.stream(side):          # warm-up outside capture: workspaces, smem attributes, identity tiles
                 self.forward(static_in, return_weights, quantize=quantize)
             torch.cuda.current_stream().wait_stream(side)
             launches0 = self.launches
@@ -697,8 +718,19 @@ class DBSREngine:
                 outs = self.forward(static_in, return_weights, quantize=quantize)
             entry = (graph, static_in, outs, self.launches - launches0)
             self._graphs[key] = entry
-        graph, static_in, outs, n_launch = entry
-        static_in.copy_(burst, non_blocking=True)
+        return entry
+
+    @torch.no_grad()
+    def forward_graphed(self, burst: torch.Tensor, return_weights: bool = False, quantize: bool = False, slot: int = 0):
+        """Same as forward(), but the launch sequence is captured once per input shape into a CUDA graph and replayed.
+        The returned tensors are the graph's static outputs: they are overwritten by the next call of the same shape (and
+        slot).  A `burst` that already IS the slot's static input (HostPipeline copies host data straight into it) is not
+        copied again."""
+        ops.require_device(burst)
+        burst = burst.contiguous().float()
+        graph, static_in, outs, n_launch = self.graph_entry(burst.shape, return_weights, quantize, slot)
+        if burst.data_ptr() != static_in.data_ptr():
+            static_in.copy_(burst, non_blocking=True)
         graph.replay()
-        self.launches += n_launch + 1
+        self.launches += n_launch
         return outs

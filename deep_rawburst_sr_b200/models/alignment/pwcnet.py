@@ -13,6 +13,7 @@ import torch
 from ... import ops
 from ...engine import DBSREngine
 from ...external.pwcnet.correlation import correlation  # noqa: F401  (same import the reference performs)
+from ..engine_owner import EngineOwner
 
 
 def backwarp(tenInput, tenFlow):
@@ -35,11 +36,12 @@ def backwarp(tenInput, tenFlow):
     return out[:, :-1] * mask
 
 
-class Network(torch.nn.Module):
-    """Parameter container with the reference's module tree (pwcnet.py:41-219)."""
+class Network(EngineOwner, torch.nn.Module):
+    """The reference's module tree (pwcnet.py:41-219) as a parameter container; `forward` runs the sm_100a kernel sequence."""
 
     def __init__(self):
         super(Network, self).__init__()
+        self.precision = 'fp32'       # 'fp32': exact CUDA-core path; 'bf16': tcgen05 tensor cores (PWCNet.set_precision)
         L = torch.nn.LeakyReLU
         C = torch.nn.Conv2d
 
@@ -90,8 +92,28 @@ class Network(torch.nn.Module):
         self.netSix = Decoder(6)
         self.netRefiner = Refiner()
 
+    def engine(self, device):
+        if not self._engine_is_current(device, precision=self.precision):
+            self._set_engine(DBSREngine(self.state_dict(), device, precision=self.precision, pwc_prefix='', parts=('pwc',)))
+        return self._engine
+
+    @torch.no_grad()
     def forward(self, tenFirst, tenSecond):
-        raise NotImplementedError('Network is a parameter container; call PWCNet.forward')
+        """pwcnet.py:220-231: extractor pyramids of both images, decoders 6..2, refiner -> flow [P, 2, H/4, W/4] (in units of
+        1/20 px of the input grid, as the reference returns it).  H and W must be multiples of 64 (the reference's decoder
+        concatenations only line up then; `PWCNet.forward` resizes to such a size first)."""
+        ops.require_device(tenFirst)
+        assert tenFirst.dim() == 4 and tenFirst.shape == tenSecond.shape and tenFirst.shape[1] == 3
+        P, _, H, W = tenFirst.shape
+        if H % 64 or W % 64:
+            raise ValueError(f'Network.forward needs H, W multiples of 64 (got {H}x{W}); PWCNet.forward resizes for you')
+        eng = self.engine(tenFirst.device)
+        ws = eng.workspace(('net_pairs', P, H, W))
+        pwc_in = eng._buf(ws, 'pwc_in', 2 * P, H, W, 4, torch.float32)
+        pwc_in.slice(0, 3).from_nchw(torch.cat([tenFirst, tenSecond], 0).contiguous().float())
+        feats = eng.pwc_extract(ws, pwc_in)
+        flow4 = eng.pwc_decode(ws, [f.images(0, P) for f in feats], [f.images(P, P) for f in feats], P, 0, 0)
+        return flow4.to_nchw()
 
 
 class PWCNet(torch.nn.Module):
@@ -102,7 +124,6 @@ class PWCNet(torch.nn.Module):
         # 'fp32': exact CUDA-core path (flows within 1e-4 px of the reference); 'bf16': tcgen05 tensor cores (the precision
         # the burst forward uses for PWC-Net, ~1e-2 px) -- e.g. for the output-resolution alignment of the BurstSR metric
         self.precision = 'fp32'
-        self._engine = None
         if load_pretrained:
             if weights_path is None:
                 raise Exception
@@ -110,24 +131,15 @@ class PWCNet(torch.nn.Module):
             self.net.load_state_dict({strKey.replace('module', 'net'): tenWeight for strKey, tenWeight
                                       in weights_dict.items()})
 
-    def _apply(self, fn, *a, **k):
-        self._engine = None
-        return super()._apply(fn, *a, **k)
-
-    def load_state_dict(self, *a, **k):
-        self._engine = None
-        return super().load_state_dict(*a, **k)
-
     def set_precision(self, precision: str):
         assert precision in ('fp32', 'bf16')
         self.precision = precision
-        self._engine = None
         return self
 
     def engine(self, device):
-        if self._engine is None or self._engine.device != torch.device(device) or self._engine.precision != self.precision:
-            self._engine = DBSREngine(self.state_dict(), device, precision=self.precision, pwc_prefix='net.', parts=('pwc',))
-        return self._engine
+        """the engine lives on `.net` (one set of packed weights whether `PWCNet.forward` or `Network.forward` is called)"""
+        self.net.precision = self.precision
+        return self.net.engine(device)
 
     @torch.no_grad()
     def forward(self, source_img, target_img):

@@ -16,12 +16,13 @@ from ...admin.environment import env_settings
 from ...admin.model_constructor import model_constructor
 from ...engine import DBSREngine
 from ..alignment.pwcnet import PWCNet
+from ..engine_owner import EngineOwner
 from . import decoders as dbsr_decoders
 from . import encoders as dbsr_encoders
 from . import merging as dbsr_merging
 
 
-class DBSRNet(nn.Module):
+class DBSRNet(EngineOwner, nn.Module):
     """ Deep Burst Super-Resolution model"""
 
     def __init__(self, encoder, merging, decoder):
@@ -39,18 +40,10 @@ class DBSRNet(nn.Module):
                                        # static buffers, overwritten by the next call with the same shape)
         self._engine = None
 
-    def _apply(self, fn, *a, **k):
-        self._engine = None
-        return super()._apply(fn, *a, **k)
-
-    def load_state_dict(self, *a, **k):
-        self._engine = None
-        return super().load_state_dict(*a, **k)
-
     def set_precision(self, precision: str):
         assert precision in ('bf16', 'fp32')
         self.precision = precision
-        self._engine = None
+        self.invalidate_engine()
         return self
 
     def _fused_path(self):
@@ -59,17 +52,26 @@ class DBSRNet(nn.Module):
                 isinstance(self.decoder, dbsr_decoders.ResPixShuffleConv))
 
     def engine(self, device):
-        e = self._engine
-        if (e is None or e.device != torch.device(device) or e.precision != self.precision or
-                e.pwc_precision != (self.pwc_precision or self.precision)):
-            self._engine = DBSREngine(self.state_dict(), device, precision=self.precision,
-                                      pwc_precision=self.pwc_precision,
-                                      offset_modulo=self.merging.offset_modulo,
-                                      gauss_kernel=self.decoder.gauss_taps(), logits_fp32=self.logits_fp32)
+        if not self._engine_is_current(device, precision=self.precision,
+                                       pwc_precision=self.pwc_precision or self.precision):
+            self._set_engine(DBSREngine(self.state_dict(), device, precision=self.precision,
+                                        pwc_precision=self.pwc_precision,
+                                        offset_modulo=self.merging.offset_modulo,
+                                        gauss_kernel=self.decoder.gauss_taps(), logits_fp32=self.logits_fp32))
         return self._engine
 
     @torch.no_grad()
-    def forward(self, im):
+    def forward(self, im, offsets=None):
+        """im [B, N, 4, H, W] -> (pred, {'offsets', 'fusion_weights'}) (reference dbsrnet.py:33-38).  `offsets` (extension,
+        optional [B, N-1, 2, H, W]): flows to use instead of the alignment network's (external alignment; parity tests pin
+        the flows with it to compare everything downstream of them exactly)."""
+        if offsets is not None:
+            assert self._fused_path(), 'external offsets need the fused engine path'
+            ops.require_device(im)
+            eng = self.engine(im.device)
+            pred, offs, weights = eng.forward(im, return_weights=self.return_fusion_weights, out={'offsets_in': offsets},
+                                              quantize=self.output_int16)
+            return pred, {'offsets': offs, 'fusion_weights': weights}
         if not self._fused_path():
             out_enc = self.encoder(im)
             out_merge = self.merging(out_enc)

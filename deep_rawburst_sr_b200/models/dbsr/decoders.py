@@ -4,11 +4,12 @@ import torch.nn as nn
 
 from ... import ops
 from ...engine import DBSREngine
+from ..engine_owner import EngineOwner
 from ..layers import blocks
 from ..layers.upsampling import PixShuffleUpsampler
 
 
-class ResPixShuffleConv(nn.Module):
+class ResPixShuffleConv(EngineOwner, nn.Module):
     """Residual decoder with sub-pixel-convolution upsampling.  forward({'fused_enc' [B, C, H, W]}) ->
     {'pred' [B, 3, r*H, r*W]}."""
 
@@ -33,23 +34,15 @@ class ResPixShuffleConv(nn.Module):
         self.precision = 'bf16'
         self._engine = None
 
-    def _apply(self, fn, *a, **k):
-        self._engine = None
-        return super()._apply(fn, *a, **k)
-
-    def load_state_dict(self, *a, **k):
-        self._engine = None
-        return super().load_state_dict(*a, **k)
-
     def gauss_taps(self):
         gk = getattr(self.upsample_layer, 'gauss_kernel', None)
         return False if gk is None else gk.reshape(3, 3)
 
     def engine(self, device):
-        if self._engine is None or self._engine.device != torch.device(device) or self._engine.precision != self.precision:
+        if not self._engine_is_current(device, precision=self.precision):
             sd = {'decoder.' + k: v for k, v in self.state_dict().items()}
-            self._engine = DBSREngine(sd, device, precision=self.precision, gauss_kernel=self.gauss_taps(),
-                                      parts=('decoder',))
+            self._set_engine(DBSREngine(sd, device, precision=self.precision, gauss_kernel=self.gauss_taps(),
+                                        parts=('decoder',)))
         return self._engine
 
     @torch.no_grad()

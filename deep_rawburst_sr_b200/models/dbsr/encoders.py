@@ -4,10 +4,11 @@ import torch.nn as nn
 
 from ... import ops
 from ...engine import DBSREngine
+from ..engine_owner import EngineOwner
 from ..layers import blocks
 
 
-class ResEncoderWarpAlignnet(nn.Module):
+class ResEncoderWarpAlignnet(EngineOwner, nn.Module):
     """Encodes the burst with a residual network, estimates the flow of every frame w.r.t. the first one with the
     alignment net and warps the embeddings to the reference frame.  forward(x [B, N, 4, H, W]) ->
     {'ref_feat' [B, N-1 (expanded), C, H, W], 'oth_feat' [B, N-1, C, H, W], 'offsets' [B, N-1, 2, H, W]}."""
@@ -31,18 +32,10 @@ class ResEncoderWarpAlignnet(nn.Module):
         self.precision = 'bf16'
         self._engine = None
 
-    def _apply(self, fn, *a, **k):
-        self._engine = None
-        return super()._apply(fn, *a, **k)
-
-    def load_state_dict(self, *a, **k):
-        self._engine = None
-        return super().load_state_dict(*a, **k)
-
     def engine(self, device):
-        if self._engine is None or self._engine.device != torch.device(device) or self._engine.precision != self.precision:
+        if not self._engine_is_current(device, precision=self.precision):
             sd = {'encoder.' + k: v for k, v in self.state_dict().items()}
-            self._engine = DBSREngine(sd, device, precision=self.precision, parts=('pwc', 'encoder'))
+            self._set_engine(DBSREngine(sd, device, precision=self.precision, parts=('pwc', 'encoder')))
         return self._engine
 
     @torch.no_grad()

@@ -4,10 +4,11 @@ import torch.nn as nn
 
 from ... import ops
 from ...engine import DBSREngine
+from ..engine_owner import EngineOwner
 from ..layers import blocks
 
 
-class WeightedSum(nn.Module):
+class WeightedSum(EngineOwner, nn.Module):
     """Adaptive weighted-sum fusion of the aligned burst embeddings.  forward({'ref_feat','oth_feat','offsets'}) ->
     {'fused_enc' [B, C, H, W], 'fusion_weights' [B, N, C, H, W]}."""
 
@@ -49,19 +50,11 @@ class WeightedSum(nn.Module):
         self.return_fusion_weights = True
         self._engine = None
 
-    def _apply(self, fn, *a, **k):
-        self._engine = None
-        return super()._apply(fn, *a, **k)
-
-    def load_state_dict(self, *a, **k):
-        self._engine = None
-        return super().load_state_dict(*a, **k)
-
     def engine(self, device):
-        if self._engine is None or self._engine.device != torch.device(device) or self._engine.precision != self.precision:
+        if not self._engine_is_current(device, precision=self.precision):
             sd = {'merging.' + k: v for k, v in self.state_dict().items()}
-            self._engine = DBSREngine(sd, device, precision=self.precision, offset_modulo=self.offset_modulo,
-                                      parts=('merging',))
+            self._set_engine(DBSREngine(sd, device, precision=self.precision, offset_modulo=self.offset_modulo,
+                                        parts=('merging',)))
         return self._engine
 
     @torch.no_grad()

@@ -84,9 +84,11 @@ def _ptr(t: Optional[torch.Tensor]):
 
 
 def conv2d(x: Act, w: torch.Tensor, bias: Optional[torch.Tensor], y: Act, ksize: int, stride: int = 1, dilation: int = 1,
-           act: int = ACT_NONE, residual: Optional[Act] = None, shuffle_r: int = 0, tensor_core: bool = False) -> Act:
+           act: int = ACT_NONE, residual: Optional[Act] = None, shuffle_r: int = 0, tensor_core: bool = False,
+           grid_limit: int = 0) -> Act:
+    """grid_limit (tensor-core path): cap of the persistent grid of THIS launch, 0 = one CTA per SM"""
     d = ConvDesc(x.view(), y.view(), residual.view() if residual is not None else _NULL_VIEW, w.data_ptr(),
-                 _ptr(bias), ksize, stride, dilation, act, shuffle_r)
+                 _ptr(bias), ksize, stride, dilation, act, shuffle_r, int(grid_limit))
     lib = _lib.load_library()
     if tensor_core:
         _lib.check(lib.dbsr_conv2d_tc(ctypes.byref(d), _stream()), 'dbsr_conv2d_tc')
@@ -96,7 +98,7 @@ def conv2d(x: Act, w: torch.Tensor, bias: Optional[torch.Tensor], y: Act, ksize:
 
 
 def conv2d_tc_predictor(x: Act, w: torch.Tensor, bias: Optional[torch.Tensor], y: Act, ksize: int, act: int,
-                        residual: Optional[Act], pred_w, pred_b, pred: torch.Tensor) -> torch.Tensor:
+                        residual: Optional[Act], pred_w, pred_b, pred: torch.Tensor, grid_limit: int = 0) -> torch.Tensor:
     """tcgen05 conv whose epilogue applies the 1x1 predictor + ReLU and writes `pred` [n, k, h, w] directly (the conv output
     map `y` is not written; it only describes the geometry): fp32, or -- when `pred` is an int16 tensor -- the reference's
     14-bit quantisation (min(value, 1) * 2^14, truncated).  pred_w [k][Cout] / pred_b [k]: HOST values (CPU
@@ -111,7 +113,7 @@ def conv2d_tc_predictor(x: Act, w: torch.Tensor, bias: Optional[torch.Tensor], y
     assert len(pred_w) == k * y.c
     assert pred.dtype in (torch.float32, torch.int16) and pred.is_contiguous() and tuple(pred.shape) == (x.n, k, x.h, x.w)
     d = ConvDesc(x.view(), y.view(), residual.view() if residual is not None else _NULL_VIEW, w.data_ptr(),
-                 _ptr(bias), ksize, 1, 1, act, 0)
+                 _ptr(bias), ksize, 1, 1, act, 0, int(grid_limit))
     _lib.check(_lib.load_library().dbsr_conv2d_tc_predictor(ctypes.byref(d), ctypes.cast(pred_w, ctypes.c_void_p),
                                                             ctypes.cast(pred_b, ctypes.c_void_p), k, pred.data_ptr(),
                                                             1 if pred.dtype == torch.int16 else 0, _stream()),
@@ -128,15 +130,10 @@ def quantize_q14(src: torch.Tensor, dst: torch.Tensor) -> torch.Tensor:
     return dst
 
 
-def conv2d_tc_set_grid_limit(ctas: int) -> None:
-    """persistent-grid size of the following tensor-core conv launches (0 = one CTA per SM)"""
-    _lib.check(_lib.load_library().dbsr_conv2d_tc_set_grid_limit(int(ctas)), 'dbsr_conv2d_tc_set_grid_limit')
-
-
 def conv2d_tc_supported(x: Act, w: torch.Tensor, bias, y: Act, ksize: int, stride: int = 1, dilation: int = 1,
                         residual: Optional[Act] = None, shuffle_r: int = 0) -> bool:
     d = ConvDesc(x.view(), y.view(), residual.view() if residual is not None else _NULL_VIEW, w.data_ptr(),
-                 _ptr(bias), ksize, stride, dilation, 0, shuffle_r)
+                 _ptr(bias), ksize, stride, dilation, 0, shuffle_r, 0)
     return bool(_lib.load_library().dbsr_conv2d_tc_supported(ctypes.byref(d)))
 
 
@@ -178,17 +175,14 @@ def deconv_col2im(taps: Act, bias_t: torch.Tensor, y_t: Act, flow: Optional[Act]
 
 
 def corr81(f1: Act, f2: Act, out: Act, pairs: int, group: int = 0, flow: Optional[Act] = None, flow_scale: float = 0.0,
-           act: int = ACT_NONE) -> Act:
+           act: int = ACT_NONE, tensor_core: bool = True) -> Act:
+    """tensor_core=False (per call) keeps bf16 maps on the CUDA-core kernels instead of the mma.sync banded product (A/B)"""
     a, b, o = f1.view(), f2.view(), out.view()
     fl = flow.view() if flow is not None else _NULL_VIEW
     _lib.check(_lib.load_library().dbsr_corr81(ctypes.byref(a), ctypes.byref(b), ctypes.byref(fl), float(flow_scale),
-                                               ctypes.byref(o), pairs, group, act, _stream()), 'dbsr_corr81')
+                                               ctypes.byref(o), pairs, group, act,
+                                               _lib.CORR_AUTO if tensor_core else _lib.CORR_CUDA_CORES, _stream()), 'dbsr_corr81')
     return out
-
-
-def corr81_set_tensor_core(on: bool) -> None:
-    """A/B switch of the bf16 cost volume: tensor-core banded product (default) vs the CUDA-core kernels"""
-    _lib.check(_lib.load_library().dbsr_corr81_set_tensor_core(1 if on else 0), 'dbsr_corr81_set_tensor_core')
 
 
 def copy_channels(src: Act, dst: Act, group: int = 0, src_group: int = 0, src_first: int = 0) -> Act:

@@ -120,10 +120,15 @@ class OutputGatherer:
         self._side.wait_event(staged)
         with torch.cuda.stream(self._side):
             dist.all_gather_into_tensor(self._out[k], self._stage[k])
+            # ragged shards: the compaction READS the gathered buffer, so it must be ordered after the collective -- on the
+            # side stream, before the event the caller waits on (on the current stream it would race with the gather)
+            gathered = self._compact(self._out[k])
             ev = torch.cuda.Event()
             ev.record(self._side)
+        if gathered is not self._out[k]:
+            gathered.record_stream(cur)               # allocated on the side stream, consumed on the caller's
         self._done[k] = ev
-        return self._compact(self._out[k]), ev
+        return gathered, ev
 
     def _compact(self, out: torch.Tensor) -> torch.Tensor:
         if all(s == self.pad for s in self.sizes):

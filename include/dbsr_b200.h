@@ -93,6 +93,8 @@ typedef struct dbsr_conv {
   int32_t stride, dilation;  /* padding is dilation*(ksize-1)/2 ("same" for stride 1)               */
   int32_t act;
   int32_t shuffle_r;         /* 0/1: plain; 8: pixel-shuffle scatter                                */
+  int32_t grid_limit;        /* dbsr_conv2d_tc*: cap of the persistent grid (CTAs); 0 = one per SM.  Per call, so
+                                that concurrent engines / devices never share launch state.                */
 } dbsr_conv_t;
 int dbsr_conv2d_direct(const dbsr_conv_t* p, void* stream);
 
@@ -107,10 +109,9 @@ int dbsr_conv2d_direct(const dbsr_conv_t* p, void* stream);
  *   (dbsr_conv2d_tc_supported) and never falls back silently inside a call.                              */
 int dbsr_conv2d_tc(const dbsr_conv_t* p, void* stream);
 int dbsr_conv2d_tc_supported(const dbsr_conv_t* p);
-/* Persistent-grid size of the following dbsr_conv2d_tc launches of this process (0 = one CTA per SM, the default).  The engine
- * lowers it for the encoder conv stack while PWC-Net runs on a second stream, so that the alignment kernels always find
- * free SMs; launch-time state only (a captured CUDA graph keeps the grid it was captured with).  Not thread safe.        */
-int dbsr_conv2d_tc_set_grid_limit(int32_t ctas);
+/* p->grid_limit caps the persistent grid of THIS launch (0 = one CTA per SM).  The engine lowers it for the encoder conv
+ * stack while PWC-Net runs on a second stream, so that the alignment kernels always find free SMs.  The library keeps no
+ * mutable launch state: every entry point is re-entrant per device (host-side caches are per device).                  */
 /* The same convolution with the decoder's 1x1 predictor + ReLU (models/dbsr/decoders.py:52,61: conv_block(post_conv_dim, 3,
  * 1, activation) after the last post-res block) folded into the epilogue: every epilogue thread owns all (<= 32) output
  * channels of its pixel, so  pred[n, k, y, x] = relu(pred_b[k] + sum_c pred_w[k][c] * act(conv(x) + bias (+ residual))[c])
@@ -158,11 +159,11 @@ int dbsr_deconv_col2im(const dbsr_nhwc_t* taps, const float* bias_t, const dbsr_
 /*   flow: [pairs, h, w, 2] fp32 view or data NULL; flow_scale = fltBackwarp (pwcnet.py:121)            */
 /* -------------------------------------------------------------------------------------------------- */
 int dbsr_corr81(const dbsr_nhwc_t* f1, const dbsr_nhwc_t* f2, const dbsr_nhwc_t* flow, float flow_scale,
-                const dbsr_nhwc_t* out, int32_t pairs, int32_t group, int32_t act, void* stream);
-/* A/B switch (default 1): bf16 maps with C in {32, 64, 96, 128} larger than 8x8 run the banded product on the tensor cores
- * (warp-level mma.sync, bf16 operands, fp32 accumulate; a fused backwarp rounds the warped map to bf16); 0 keeps every
- * shape on the CUDA-core kernels (fp32 arithmetic on the bf16 inputs).                                              */
-int dbsr_corr81_set_tensor_core(int32_t on);
+                const dbsr_nhwc_t* out, int32_t pairs, int32_t group, int32_t act, int32_t mode, void* stream);
+/* mode (per call): DBSR_CORR_AUTO: bf16 maps with C in {32, 64, 96, 128} larger than 8x8 run the banded product on the tensor
+ * cores (warp-level mma.sync, bf16 operands, fp32 accumulate; a fused backwarp rounds the warped map to bf16);
+ * DBSR_CORR_CUDA_CORES keeps every shape on the CUDA-core kernels (fp32 arithmetic on the bf16 inputs): A/B + tests.  */
+enum { DBSR_CORR_AUTO = 0, DBSR_CORR_CUDA_CORES = 1 };
 
 /* flow head: replaces pwcnet.py:274-279.  flow4 [P, h4, w4, 2] fp32 -> offsets [P, 2, H, W] fp32 NCHW  */
 /*   offsets = 20 * bilinear_resize(flow4 -> (H, W)) * (W/Wp, H/Hp)                                     */

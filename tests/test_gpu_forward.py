@@ -68,6 +68,59 @@ def test_fp32_path_stress_flows_against_oracle(dev):
     assert err.mean().item() < 1e-5 and (err > 1e-4).float().mean().item() < 2e-3, (err.max().item(), err.mean().item())
 
 
+def test_fp32_stress_golden_flows_pinned(dev, golden_dir):
+    """The reference-generated stress golden (4.5 px flows, PWC weights x2.2) on the fp32 path, with NO outlier allowance on
+    the output.  The path has two discontinuous functions of the flow -- backwarp's `mask > 0.999` inside PWC-Net
+    (pwcnet.py:34-36) and `offsets % 1.0` (merging.py:97) -- so a flow that differs from the reference's in the last bits
+    can flip a pixel.  That is separated by construction: (1) the flows themselves agree with the golden ones to 1e-4 px on
+    >= 99 % of the pixels (the rest: pixels downstream of a flipped backwarp mask, bounded by 2e-2 px); (2) with the flows
+    pinned to the golden ones (`net(burst, offsets=...)`: PWC-Net skipped, everything else -- encoder, warp, modulo, weight
+    predictor, softmax fusion, decoder -- unchanged) EVERY output element is within 1e-4 of the reference's, fusion weights
+    included.  The outliers of the un-pinned forward are therefore exactly the flow-discontinuity pixels."""
+    g = np.load(os.path.join(golden_dir, 'stress_b1n5_32x32.npz'))
+    wseed, bseed, B, N, H, W = [int(v) for v in g['meta']]
+    sd = O.make_state_dict(wseed, pwc_gain=float(g['pwc_gain'][0]))
+    net = _net(sd, dev, 'fp32')
+    burst = O.make_burst(bseed, B, N, H, W).to(dev)
+    gold_off = torch.from_numpy(g['offsets'])
+    assert float(gold_off.abs().max()) > 4.0
+    pred, aux = net(burst)
+    ferr = (aux['offsets'].cpu() - gold_off).abs()
+    assert ferr.max().item() < 2e-2 and (ferr > 1e-4).float().mean().item() < 1e-2, (ferr.max().item(), (ferr > 1e-4).float().mean().item())
+    pinned, aux_p = net(burst, offsets=gold_off.to(dev))
+    assert torch.equal(aux_p['offsets'].cpu(), gold_off)
+    err = np.abs(pinned.cpu().numpy() - g['pred'])
+    assert err.max() <= 1e-4, err.max()
+    fw = aux_p['fusion_weights'].cpu()
+    assert np.abs(fw[:, :, ::37, ::3, ::3].numpy() - g['fusion_weights_sub']).max() < 1e-4
+    free = np.abs(pred.cpu().numpy() - g['pred'])
+    print(f'stress golden: flow err max {ferr.max().item():.2e} px, {100 * (ferr > 1e-4).float().mean().item():.3f} % of flow values '
+          f'> 1e-4 px; pinned-flow pred err max {err.max():.2e}; free-running pred err max {free.max():.2e}, '
+          f'{100 * (free > 1e-4).mean():.3f} % > 1e-4')
+
+
+def test_bf16_full_range_output_with_large_flows(dev):
+    """bf16 tolerance at a REALISTIC output range and multi-pixel flows: the default-scale weights of the other bf16 tests
+    give pred in [0, 0.12]; here the DBSR weights are scaled by 1.5 (pred spans [0, 1.17], std 0.34 -- a larger gain compounds
+    over the ~40 layers: x3 gives pred ~ 7e5) and the PWC-Net weights by 2.2 (flows up to 14 px: out-of-bounds taps, mask and
+    modulo flips), on a full 14-frame 48x48 burst.  Bar = north_star: >= 95 % of the output within 1e-2 and |dPSNR| <= 0.02 dB."""
+    sd = O.make_state_dict(4, pwc_gain=2.2, dbsr_gain=1.5)
+    burst = O.make_burst(9, 1, 14, 48, 48)
+    ref_pred, ref_aux = O.dbsr_forward_fast(burst, sd)
+    assert float(ref_pred.max()) > 1.0 and float(ref_pred.std()) > 0.3 and float(ref_aux['offsets'].abs().max()) > 8.0
+    net = _net(sd, dev, 'bf16')
+    net.return_fusion_weights = False
+    pred, aux = net(burst.to(dev))
+    err = (pred.cpu() - ref_pred).abs()
+    frac = (err <= 1e-2).float().mean().item()
+    gt = torch.rand(ref_pred.shape, generator=torch.Generator().manual_seed(17))
+    d_psnr = abs(O.psnr(pred.cpu(), gt, 40) - O.psnr(ref_pred, gt, 40))
+    print(f'bf16 full-range: max_abs={err.max().item():.3e} mean={err.mean().item():.3e} frac<=1e-2={frac:.4f} dPSNR={d_psnr:.4f} '
+          f'pred max {float(ref_pred.max()):.2f} max|flow| {float(ref_aux["offsets"].abs().max()):.1f}')
+    assert frac >= 0.95, frac
+    assert d_psnr <= 0.02, d_psnr
+
+
 @pytest.mark.parametrize('pwc_precision', [None, 'fp32'])
 @pytest.mark.parametrize('shape', [(1, 14, 48, 48), (2, 5, 16, 24), (1, 2, 24, 24), (1, 3, 30, 46), (1, 18, 16, 16)])
 def test_bf16_path_tolerance(dev, shape, pwc_precision):
@@ -139,11 +192,10 @@ def test_batch_invariance_and_reuse(dev):
 
 @pytest.mark.parametrize('B,N,S', [(32, 14, 48), (16, 14, 80)])
 def test_full_size_configs_burst_independence(dev, B, N, S):
-    """BASELINE.json configs[1] / configs[2] at full size (where the oracle takes minutes): size-independent properties.
-    Bursts are independent on this path, so (a) every burst of the full batch is bit-identical to the same burst run in a
-    batch of 2 (different tile packing, pair / flat grouping and item counts in every kernel), (b) CUDA-graph replay equals
-    eager, (c) one burst of the batch agrees with the CPU oracle's fp32 forward within the bf16 tolerance, (d) the
-    offsets of the reference frame pairs are finite and the output is finite everywhere."""
+    """BASELINE.json configs[1] / configs[2] at full size: (a) every burst of the full batch is bit-identical to the same
+    burst run in a batch of 2 (different tile packing, pair / flat grouping and item counts in every kernel), (b) CUDA-graph
+    replay equals eager, (c) the offsets and the output are finite everywhere.  The oracle comparison of EVERY burst of both
+    configs is test_full_size_configs_every_burst_against_oracle."""
     sd = O.make_state_dict(0)
     net = _net(sd, dev, 'bf16')
     net.return_fusion_weights = False
@@ -159,11 +211,37 @@ def test_full_size_configs_burst_independence(dev, B, N, S):
     for _ in range(2):
         p_g, _ = net(burst.to(dev))
     assert torch.equal(p_g, p_all)
-    if S == 48:      # one burst against the oracle's library-op forward (a second of CPU)
-        ref = O.dbsr_forward_fast(burst[B - 1:B], sd)
-        ref = ref[0] if isinstance(ref, (tuple, list)) else ref
-        err = (p_all[B - 1:B].cpu() - ref).abs().max().item()
-        assert err <= 1e-2, err
+
+
+@pytest.mark.parametrize('B,N,S', [(32, 14, 48), (16, 14, 80)])
+def test_full_size_configs_every_burst_against_oracle(dev, B, N, S):
+    """BASELINE.json configs[1] (32 x 14x4x48x48 -> 3x384x384) and configs[2] (16 x 14x4x80x80 -> 3x640x640, the shapes of
+    /root/reference/evaluation/burstsr/compute_score.py:100-117), bf16 path, ONE forward of the full batch (CUDA-graph
+    replay, as bench.py runs it): EVERY burst is compared with the CPU oracle's fp32 forward (`dbsr_forward_fast`, the
+    reference's own op sequence).  north_star bar per burst: max-abs <= 1e-2 on pred, |dPSNR| <= 0.02 dB against a seeded
+    pseudo ground truth (boundary_ignore 40); the fraction of bursts within tolerance must be >= 95 % (it is 100 %)."""
+    sd = O.make_state_dict(0)
+    net = _net(sd, dev, 'bf16')
+    net.return_fusion_weights = False
+    net.use_cuda_graph = True
+    burst = O.make_burst(77, B, N, S, S)
+    for _ in range(2):
+        pred, aux = net(burst.to(dev))
+    pred, offs = pred.cpu(), aux['offsets'].cpu()
+    gt_gen = torch.Generator().manual_seed(99)
+    worst, worst_dpsnr, worst_flow, ok = 0.0, 0.0, 0.0, 0
+    for i in range(B):
+        ref, ref_aux = O.dbsr_forward_fast(burst[i:i + 1], sd)
+        gt = torch.rand(ref.shape, generator=gt_gen)
+        e = (pred[i:i + 1] - ref).abs().max().item()
+        d = abs(O.psnr(pred[i:i + 1], gt, 40) - O.psnr(ref, gt, 40))
+        f = (offs[i:i + 1] - ref_aux['offsets']).abs().max().item()
+        worst, worst_dpsnr, worst_flow = max(worst, e), max(worst_dpsnr, d), max(worst_flow, f)
+        ok += int(e <= 1e-2 and d <= 0.02)
+    print(f'cfg {B}x{N}x4x{S}x{S}: bursts within tolerance {ok}/{B}; worst max-abs {worst:.3e}, worst dPSNR {worst_dpsnr:.4f} dB, '
+          f'worst flow err {worst_flow:.3e} px')
+    assert ok / B >= 0.95, (ok, B)
+    assert worst <= 1e-2 and worst_dpsnr <= 0.02, (worst, worst_dpsnr)      # in fact every burst passes
 
 
 def test_large_crop_256(dev):
@@ -299,3 +377,60 @@ def test_host_pipeline_matches_direct_forward(dev):
         pipe.drain()
         with pytest.raises(ValueError):
             pipe.submit(bursts[0].to(dev), hout[0])
+
+
+def test_network_and_upsampler_seams(dev):
+    """`Network.forward` (pwcnet.py:220-231: raw flow at 1/4 resolution of a x64-sized pair) and `PixShuffleUpsampler.forward`
+    (upsampling.py:51-66) are callable like the reference's and agree with the oracle"""
+    import torch.nn.functional as F
+    sd = O.make_state_dict(1)
+    net = _net(sd, dev, 'fp32')
+    g = torch.Generator().manual_seed(3)
+    first, second = torch.rand(2, 3, 64, 128, generator=g), torch.rand(2, 3, 64, 128, generator=g)
+    pre = 'encoder.alignment_net.net.'
+    ref = O.pwc_network(first, second, sd, pre)
+    got = net.encoder.alignment_net.net(first.to(dev), second.to(dev))
+    assert tuple(got.shape) == (2, 2, 16, 32) and (got.cpu() - ref).abs().max().item() < 1e-5
+    with pytest.raises(ValueError):
+        net.encoder.alignment_net.net(first[..., :48, :48].to(dev), second[..., :48, :48].to(dev))
+    # PWCNet.forward shares the packed weights of .net and still matches
+    flow = net.encoder.alignment_net(second[..., :48, :80].contiguous().to(dev), first[..., :48, :80].contiguous().to(dev))
+    ref_flow = O.pwcnet_forward(second[..., :48, :80].contiguous(), first[..., :48, :80].contiguous(), sd)
+    assert (flow.cpu() - ref_flow).abs().max().item() < 1e-4
+    up = net.decoder.upsample_layer
+    x = torch.rand(2, 64, 9, 13, generator=g)
+    w = sd['decoder.upsample_layer.conv_layer.0.weight']
+    want = F.pixel_shuffle(torch.relu(F.conv2d(x, w)), 8)
+    want = F.conv2d(want.reshape(-1, 1, 72, 104), O.gauss_kernel3().view(1, 1, 3, 3), padding=1).view(2, 32, 72, 104)
+    got = up(x.to(dev))
+    assert tuple(got.shape) == (2, 32, 72, 104) and (got.cpu() - want).abs().max().item() < 1e-5
+
+
+def test_engine_follows_weight_updates(dev):
+    """the packed-weight engine (and its CUDA graphs) is rebuilt when parameters change through a CHILD module or in place:
+    `net.decoder.load_state_dict`, `net.encoder.alignment_net.load_state_dict`, `p.mul_()` -- none of which passes through
+    DBSRNet._apply / DBSRNet.load_state_dict -- and by `invalidate_engine()` after a write through `p.data`"""
+    sd_a, sd_b = O.make_state_dict(0), O.make_state_dict(5)
+    burst = O.make_burst(1, 1, 3, 16, 16).to(dev)
+    net_a, net_b = _net(sd_a, dev, 'bf16'), _net(sd_b, dev, 'bf16')
+    for n in (net_a, net_b):
+        n.return_fusion_weights = False
+        n.use_cuda_graph = True
+    want_b = net_b(burst)[0].clone()
+    first = net_a(burst)[0].clone()
+    first = net_a(burst)[0].clone()                 # graph captured and replayed
+    assert not torch.equal(first, want_b)
+    # every weight of B loaded through the three child modules only
+    for name in ('encoder', 'merging', 'decoder'):
+        getattr(net_a, name).load_state_dict({k[len(name) + 1:]: v for k, v in sd_b.items() if k.startswith(name + '.')})
+    assert torch.equal(net_a(burst)[0], want_b)
+    # in-place update of one parameter
+    with torch.no_grad():
+        net_a.decoder.predictor[0].bias.add_(0.25)
+    shifted = net_a(burst)[0].clone()
+    assert (shifted - want_b).abs().max().item() > 0.1
+    # a write through .data is invisible to the version counters: invalidate_engine() is the documented way
+    net_a.decoder.predictor[0].bias.data.sub_(0.25)
+    assert torch.equal(net_a(burst)[0], shifted)
+    net_a.invalidate_engine()
+    assert (net_a(burst)[0] - want_b).abs().max().item() < 1e-6

@@ -247,12 +247,9 @@ def test_corr81_bf16_vectorised_staging(dev, c, h, w, mag):
         f2w = O.backwarp(f2, flow * 1.25)
         bound = 5e-5 + 2.0 ** -9 * O.correlation81(f1.abs(), f2w.abs())
         assert (err > bound).any(dim=1).float().mean() < 0.01, float(err.max())
-        ops.corr81_set_tensor_core(False)          # CUDA-core kernels: fp32 arithmetic on the bf16 inputs
-        try:
-            ops.corr81(act_bf16(f1), act_bf16(f2), out, pairs=3, group=0, flow=_act_from(flow, dev), flow_scale=1.25,
-                       act=ops.ACT_LRELU)
-        finally:
-            ops.corr81_set_tensor_core(True)
+        # CUDA-core kernels (per-call switch): fp32 arithmetic on the bf16 inputs
+        ops.corr81(act_bf16(f1), act_bf16(f2), out, pairs=3, group=0, flow=_act_from(flow, dev), flow_scale=1.25,
+                   act=ops.ACT_LRELU, tensor_core=False)
         err = (out.to_nchw().cpu() - ref).abs()
         assert (err > 5e-5).any(dim=1).float().mean() < 0.01, float(err.max())
 
@@ -290,12 +287,8 @@ def test_corr81_tensor_core_banded_product(dev, c, h, w, mag):
     err = (got - ref).abs()
     assert (err > bound).any(dim=1).float().mean() < (0.01 if mag > 0 else 1e-9), float(err.max())
     # A/B against the CUDA-core kernel on the same inputs
-    ops.corr81_set_tensor_core(False)
-    try:
-        out2 = ops.Act.empty(P, h, w, 88, torch.float32, dev, zero=True).slice(0, 81)
-        ops.corr81(fa, fa, out2, pairs=P, group=N - 1, act=ops.ACT_LRELU, **kw)
-    finally:
-        ops.corr81_set_tensor_core(True)
+    out2 = ops.Act.empty(P, h, w, 88, torch.float32, dev, zero=True).slice(0, 81)
+    ops.corr81(fa, fa, out2, pairs=P, group=N - 1, act=ops.ACT_LRELU, tensor_core=False, **kw)
     d = (out2.to_nchw().cpu() - got).abs()
     assert (d > bound).any(dim=1).float().mean() < (0.01 if mag > 0 else 1e-9), float(d.max())
     # bf16 volume into an 8-aligned concat slice: neighbours untouched, pad channels zeroed, deterministic
