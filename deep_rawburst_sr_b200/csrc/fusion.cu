@@ -7,6 +7,10 @@
 //                        weights are materialised.  Per (burst, pixel, 4-channel group) one thread streams the N
 //                        logits and the N (gathered) embeddings once, with an online softmax in fp32.
 #include "common.cuh"
+#include "tma.cuh"
+
+#include <stdlib.h>
+#include <string.h>
 
 namespace dbsr {
 
@@ -409,33 +413,79 @@ __device__ __forceinline__ Vec8 unpack_bf16x8(const uint4& q) {
 struct __align__(16) WsRec { uint32_t o[4]; float w[4]; };
 constexpr int WSP_MAX_OTHERS = 16;
 constexpr int WSP_SMEM = 2 * 2 * 5 * 256 * 16;           // ring: [2 stages][2 frames][5 loads][256 threads] x 16 bytes
+// TMA variant: [2 stages][2 frames][4 taps][256 threads] x 16 B gathered taps (cp.async) | per warp [2 stages][2 frames] 512 B
+// logit boxes | per warp 2 x 512 B reference-frame boxes (embedding, logits) | per warp 3 mbarriers
+constexpr int WST_TAPS = 2 * 2 * 4 * 256 * 16;
+constexpr int WST_LOGITS = 8 * 2 * 2 * 512;
+constexpr int WST_REF = 8 * 2 * 512;
+constexpr int WST_SMEM = WST_TAPS + WST_LOGITS + WST_REF + 8 * 3 * 8 + 128 /* alignment slack */;
 __device__ __forceinline__ float ex2f(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
-template <typename TO>
+
+// TMA = true (north_star: "TMA staging of the reference-frame tiles"): everything REGULAR in this kernel -- the unwarped
+// reference-frame embedding tile and the 14 logit tiles, 15 of the 28 tile streams of a block -- is staged by the TMA engine
+// (cp.async.bulk.tensor boxes {64 channels, 4 pixels, 1 row} = the 512 bytes one warp consumes, issued by one elected lane per
+// warp, completion on a per-warp mbarrier: no block-wide synchronisation enters the loop); only the 13 x 4 flow-dependent
+// bilinear taps stay per-thread cp.async gathers.  Out-of-image pixels / channels of ragged tiles are zero-filled by the
+// tensor map instead of clamped by address arithmetic.
+template <typename TO, bool TMA>
 __global__ void __launch_bounds__(256, 2)
-softmax_wsum8_pair_kernel(View feat, View logits, const float* __restrict__ offsets, View fused, int frames) {
-  griddep_wait();
-  extern __shared__ __align__(16) uint4 ring[];
+softmax_wsum8_pair_kernel(const __grid_constant__ CUtensorMap tmap_feat, const __grid_constant__ CUtensorMap tmap_logits,
+                          View feat, View logits, const float* __restrict__ offsets, View fused, int frames) {
+  extern __shared__ __align__(128) uint4 ring[];
   __shared__ WsRec rec_s[32][WSP_MAX_OTHERS];
   const int H = fused.h, W = fused.w;
   const int HW = H * W;
+  const int tiles_x = (W + WS_TW - 1) / WS_TW;
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5, lane = tid & 31;
+  const int g = tid & 7, pix = tid >> 3, px = pix & 7, py = pix >> 3;
+  const int b = blockIdx.z;
+  const int ty0 = (blockIdx.x / tiles_x) * WS_TH, tx0 = (blockIdx.x % tiles_x) * WS_TW;
+  constexpr int TAPS = TMA ? 4 : 5;                       // 16-byte ring slots per thread and frame
+  constexpr uint32_t FRAME_BYTES = TAPS * 4096u, STAGE_BYTES = 2u * FRAME_BYTES;
+  // per-warp TMA staging (TMA variant): 128-byte aligned boxes behind the tap ring
+  const uint32_t ring_base = (uint32_t)__cvta_generic_to_shared(ring);
+  const uint32_t lg_s = ((ring_base + (uint32_t)WST_TAPS + 127u) & ~127u) + (uint32_t)warp * 2048u;      // [stage][frame] 512 B
+  const uint32_t ref_s = ((ring_base + (uint32_t)WST_TAPS + 127u) & ~127u) + (uint32_t)WST_LOGITS + (uint32_t)warp * 1024u;
+  const uint32_t bar_s = ((ring_base + (uint32_t)WST_TAPS + 127u) & ~127u) + (uint32_t)(WST_LOGITS + WST_REF) + (uint32_t)warp * 24u;
+  // this warp's 4 pixels: tile row warp / 2, columns (warp & 1) * 4 .. + 3
+  const int wy = ty0 + (warp >> 1), wx = tx0 + (warp & 1) * 4;
+  if (TMA) {
+    if (lane == 0) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_s));
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_s + 8u));
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_s + 16u));
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncwarp();
+  }
+  griddep_wait();
   const __nv_bfloat16* fbase = reinterpret_cast<const __nv_bfloat16*>(feat.data) + feat.c_off;
   const __nv_bfloat16* lbase = reinterpret_cast<const __nv_bfloat16*>(logits.data) + logits.c_off;
   TO* obase = reinterpret_cast<TO*>(fused.data) + fused.c_off;
-  const int tiles_x = (W + WS_TW - 1) / WS_TW;
-  const int tid = threadIdx.x;
-  const int g = tid & 7, pix = tid >> 3, px = pix & 7, py = pix >> 3;
-  const int b = blockIdx.z;
   const int ch_raw = blockIdx.y * 64 + g * 8;
   const int ch = min(ch_raw, fused.c - 8);   // clamped for the loads; the store is predicated on `live`
-  const int y_raw = (blockIdx.x / tiles_x) * WS_TH + py, x_raw = (blockIdx.x % tiles_x) * WS_TW + px;
+  const int y_raw = ty0 + py, x_raw = tx0 + px;
   const bool live = y_raw < H && x_raw < W && ch_raw < fused.c;
   const int y = min(y_raw, H - 1), x = min(x_raw, W - 1);
   const int rem = y * W + x;
   const int others = frames - 1;
+  auto tma_box = [&](const CUtensorMap* map, uint32_t bar, uint32_t dst, int img) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"((int)blockIdx.y * 64), "r"(wx), "r"(wy), "r"(img)
+        : "memory");
+  };
+  if (TMA && lane == 0) {     // reference frame of this burst: embedding tile + logit tile -> ref_s, completion on bar 2
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_s + 16u), "r"(1024u) : "memory");
+    tma_box(&tmap_feat, bar_s + 16u, ref_s, b * frames);
+    tma_box(&tmap_logits, bar_s + 16u, ref_s + 512u, b * frames);
+  }
   // ---- per (pixel, frame) gather records, computed by the 8 channel-group threads of the pixel (2 frames each)
 #pragma unroll
   for (int q = 0; q < 2; ++q) {
@@ -461,37 +511,67 @@ softmax_wsum8_pair_kernel(View feat, View logits, const float* __restrict__ offs
     }
   }
   __syncwarp();     // a pixel's 8 threads are in one warp
-  const uint32_t ring_s = (uint32_t)__cvta_generic_to_shared(ring) + (uint32_t)tid * 16u;
+  const uint32_t ring_s = ring_base + (uint32_t)tid * 16u;
   const size_t lstride = (size_t)HW * logits.c_pitch * 2, fstride = (size_t)HW * feat.c_pitch * 2;
   const char* l0 = reinterpret_cast<const char*>(lbase + ((long long)b * frames * HW + rem) * logits.c_pitch + ch);
   const char* f0 = reinterpret_cast<const char*>(fbase + (long long)b * frames * HW * feat.c_pitch + ch);
   const char* lq = l0 + lstride;        // next frame to issue (frame 1)
   const char* fq = f0 + fstride;
   int nq = 1;
-  auto issue_pair = [&](uint32_t dst) {   // the next two frames -> ring stage at dst (skips frames past the burst)
+  auto issue_pair = [&](int stage) {   // the next two frames -> ring stage (skips frames past the burst)
+    const uint32_t dst = ring_s + (uint32_t)stage * STAGE_BYTES;
+    if (TMA) {
+      // the warp has consumed this stage's logit boxes (values are in registers; __syncwarp by the caller): re-arm + refill
+      if (lane == 0 && nq < frames) {
+        const int nf = min(2, frames - nq);
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_s + (uint32_t)stage * 8u), "r"((uint32_t)nf * 512u) : "memory");
+        tma_box(&tmap_logits, bar_s + (uint32_t)stage * 8u, lg_s + (uint32_t)stage * 1024u, b * frames + nq);
+        if (nf == 2) tma_box(&tmap_logits, bar_s + (uint32_t)stage * 8u, lg_s + (uint32_t)stage * 1024u + 512u, b * frames + nq + 1);
+      }
+    }
 #pragma unroll
     for (int f = 0; f < 2; ++f) {
       if (nq < frames) {
-        const uint32_t d = dst + (uint32_t)(f * 5 * 4096);
-        cp_async_16(d, lq, 16u);
+        const uint32_t d = dst + (uint32_t)f * FRAME_BYTES;
+        if (!TMA) cp_async_16(d, lq, 16u);
+        const uint32_t t0 = TMA ? 0u : 4096u;
         const uint4 o = *reinterpret_cast<const uint4*>(rec_s[pix][nq - 1].o);
-        cp_async_16(d + 4096u, fq + o.x, 16u);
-        cp_async_16(d + 8192u, fq + o.y, 16u);
-        cp_async_16(d + 12288u, fq + o.z, 16u);
-        cp_async_16(d + 16384u, fq + o.w, 16u);
+        cp_async_16(d + t0, fq + o.x, 16u);
+        cp_async_16(d + t0 + 4096u, fq + o.y, 16u);
+        cp_async_16(d + t0 + 8192u, fq + o.z, 16u);
+        cp_async_16(d + t0 + 12288u, fq + o.w, 16u);
         lq += lstride; fq += fstride; ++nq;
       }
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
   };
-  issue_pair(ring_s);
-  issue_pair(ring_s + 2u * 5u * 4096u);
-  // reference frame (never warped): plain loads while the ring fills.  The running maximum m is kept in log2 units.
+  auto bar_wait = [&](uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    do {
+      asm volatile(
+          "{\n\t.reg .pred p;\n\t"
+          "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+          "selp.u32 %0, 1, 0, p;\n\t}"
+          : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    } while (!ok);
+  };
+  issue_pair(0);
+  issue_pair(1);
+  // reference frame (never warped).  The running maximum m is kept in log2 units.
   constexpr float LOG2E = 1.4426950408889634f;
   float m[8], s[8], acc[8];
   {
-    const Vec8 l = ld8<__nv_bfloat16>(reinterpret_cast<const __nv_bfloat16*>(l0));
-    const Vec8 a = ld8<__nv_bfloat16>(reinterpret_cast<const __nv_bfloat16*>(f0 + (size_t)rem * feat.c_pitch * 2));
+    Vec8 l, a;
+    if (TMA) {
+      bar_wait(bar_s + 16u, 0u);
+      uint4 qa, ql;
+      asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(qa.x), "=r"(qa.y), "=r"(qa.z), "=r"(qa.w) : "r"(ref_s + (uint32_t)lane * 16u));
+      asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(ql.x), "=r"(ql.y), "=r"(ql.z), "=r"(ql.w) : "r"(ref_s + 512u + (uint32_t)lane * 16u));
+      a = unpack_bf16x8(qa); l = unpack_bf16x8(ql);
+    } else {
+      l = ld8<__nv_bfloat16>(reinterpret_cast<const __nv_bfloat16*>(l0));
+      a = ld8<__nv_bfloat16>(reinterpret_cast<const __nv_bfloat16*>(f0 + (size_t)rem * feat.c_pitch * 2));
+    }
 #pragma unroll
     for (int k = 0; k < 8; ++k) { m[k] = l.v[k] * LOG2E; s[k] = 1.0f; acc[k] = a.v[k]; }
   }
@@ -499,30 +579,45 @@ softmax_wsum8_pair_kernel(View feat, View logits, const float* __restrict__ offs
   for (int pp = 0; pp < npairs; ++pp) {
     asm volatile("cp.async.wait_group 1;" ::: "memory");
     const int stg = pp & 1;
-    const uint4* st = ring + stg * (2 * 5 * 256) + tid;
+    const uint4* st = ring + stg * (2 * TAPS * 256) + tid;
     const int n0 = 2 * pp;                     // index of the pair's first frame among the others
     const bool has2 = n0 + 1 < others;
     Vec8 lA, lB, aA, aB;
-    auto interp = [&](const uint4* sf, const WsRec& rc, Vec8& a) {
+    auto interp = [&](const uint4* sf, const WsRec& rc, Vec8& a) {      // sf: the frame's first TAP slot of this thread
       const float4 w = *reinterpret_cast<const float4*>(rc.w);
-      const Vec8 t0 = unpack_bf16x8(sf[256]), t1 = unpack_bf16x8(sf[512]);
+      const Vec8 t0 = unpack_bf16x8(sf[0]), t1 = unpack_bf16x8(sf[256]);
 #pragma unroll
       for (int k = 0; k < 8; ++k) a.v[k] = fmaf(t1.v[k], w.y, t0.v[k] * w.x);
-      const Vec8 t2 = unpack_bf16x8(sf[768]), t3 = unpack_bf16x8(sf[1024]);
+      const Vec8 t2 = unpack_bf16x8(sf[512]), t3 = unpack_bf16x8(sf[768]);
 #pragma unroll
       for (int k = 0; k < 8; ++k) a.v[k] = fmaf(t3.v[k], w.w, fmaf(t2.v[k], w.z, a.v[k]));
     };
-    lA = unpack_bf16x8(st[0]);
-    interp(st, rec_s[pix][n0], aA);
+    constexpr int T0 = TMA ? 0 : 256;          // first tap slot behind the logit slot of the cp.async-only ring
+    if (TMA) {
+      bar_wait(bar_s + (uint32_t)stg * 8u, (uint32_t)(pp >> 1) & 1u);
+      uint4 q;
+      asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(q.x), "=r"(q.y), "=r"(q.z), "=r"(q.w) : "r"(lg_s + (uint32_t)stg * 1024u + (uint32_t)lane * 16u));
+      lA = unpack_bf16x8(q);
+    } else {
+      lA = unpack_bf16x8(st[0]);
+    }
+    interp(st + T0, rec_s[pix][n0], aA);
     if (has2) {
-      lB = unpack_bf16x8(st[5 * 256]);
-      interp(st + 5 * 256, rec_s[pix][n0 + 1], aB);
+      if (TMA) {
+        uint4 q;
+        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(q.x), "=r"(q.y), "=r"(q.z), "=r"(q.w) : "r"(lg_s + (uint32_t)stg * 1024u + 512u + (uint32_t)lane * 16u));
+        lB = unpack_bf16x8(q);
+      } else {
+        lB = unpack_bf16x8(st[TAPS * 256]);
+      }
+      interp(st + TAPS * 256 + T0, rec_s[pix][n0 + 1], aB);
     } else {
 #pragma unroll
       for (int k = 0; k < 8; ++k) { lB.v[k] = -INFINITY; aB.v[k] = 0.0f; }
     }
     // this stage's slots are consumed (values are in registers): refill it with the pair after next
-    issue_pair(ring_s + (uint32_t)(stg * 2 * 5 * 4096));
+    if (TMA) __syncwarp();
+    issue_pair(stg);
     // online softmax, one rescale per pair: 3 exponentials per 2 frames and element
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
@@ -708,14 +803,37 @@ extern "C" int dbsr_softmax_wsum(const dbsr_nhwc_t* feat, const dbsr_nhwc_t* log
     // records hold 32-bit byte offsets inside one image and at most WSP_MAX_OTHERS non-reference frames
     if (key == 7 && offsets != nullptr && frames >= 2 && frames - 1 <= WSP_MAX_OTHERS &&
         (long long)fused->h * fused->w * feat->c_pitch * 2 < (1ll << 32)) {
-      static bool attr_set_dev[MAX_DEVICES] = {};
-      bool& attr_set = attr_set_dev[current_device_slot()];
+      // TMA staging of the regular streams (reference-frame tile + all logit tiles); DBSR_WSUM_NO_TMA=1 keeps them on
+      // per-thread cp.async (A/B switch, identical results)
+      static const bool use_tma = getenv("DBSR_WSUM_NO_TMA") == nullptr;
+      EncodeTiledFn encode = use_tma ? get_encode() : nullptr;
+      alignas(64) CUtensorMap mf, ml;
+      memset(&mf, 0, sizeof(mf)); memset(&ml, 0, sizeof(ml));
+      bool tma = encode != nullptr;
+      if (tma) {
+        const dbsr_nhwc_t* vs[2] = {feat, logits};
+        CUtensorMap* ms[2] = {&mf, &ml};
+        for (int i = 0; i < 2 && tma; ++i) {
+          const dbsr_nhwc_t* v = vs[i];
+          cuuint64_t dims[4] = {(cuuint64_t)v->c, (cuuint64_t)v->w, (cuuint64_t)v->h, (cuuint64_t)v->n};
+          cuuint64_t strides[3] = {(cuuint64_t)v->c_pitch * 2, (cuuint64_t)v->w * v->c_pitch * 2, (cuuint64_t)v->h * v->w * v->c_pitch * 2};
+          cuuint32_t box[4] = {64u, 4u, 1u, 1u};
+          cuuint32_t es[4] = {1, 1, 1, 1};
+          void* base = reinterpret_cast<__nv_bfloat16*>(v->data) + v->c_off;
+          tma = encode(ms[i], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                       CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+        }
+      }
+      static bool attr_set_dev[MAX_DEVICES][2] = {};
+      bool& attr_set = attr_set_dev[current_device_slot()][tma ? 1 : 0];
       if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(softmax_wsum8_pair_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, WSP_SMEM);
+        cudaError_t e = tma ? cudaFuncSetAttribute(softmax_wsum8_pair_kernel<__nv_bfloat16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, WST_SMEM)
+                            : cudaFuncSetAttribute(softmax_wsum8_pair_kernel<__nv_bfloat16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, WSP_SMEM);
         DBSR_REQUIRE(e == cudaSuccess, "softmax_wsum: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
         attr_set = true;
       }
-      launch_pdl(softmax_wsum8_pair_kernel<__nv_bfloat16>, dim3(grid8), dim3(256), (size_t)WSP_SMEM, st, f, l, offsets, o, frames);
+      if (tma) launch_pdl(softmax_wsum8_pair_kernel<__nv_bfloat16, true>, dim3(grid8), dim3(256), (size_t)WST_SMEM, st, mf, ml, f, l, offsets, o, frames);
+      else launch_pdl(softmax_wsum8_pair_kernel<__nv_bfloat16, false>, dim3(grid8), dim3(256), (size_t)WSP_SMEM, st, mf, ml, f, l, offsets, o, frames);
     }
     else if (key == 0) softmax_wsum8_kernel<float, float, float><<<grid8, 256, 0, st>>>(f, l, offsets, o, frames);
     else if (key == 7) softmax_wsum8_kernel<__nv_bfloat16, __nv_bfloat16, __nv_bfloat16><<<grid8, 256, 0, st>>>(f, l, offsets, o, frames);
