@@ -32,11 +32,20 @@ class ConvDesc(ctypes.Structure):
                 ('grid_limit', ctypes.c_int32)]
 
 
+class ResBlockDesc(ctypes.Structure):
+    """struct dbsr_resblock (include/dbsr_b200.h)."""
+    _fields_ = [('x', NhwcView), ('y', NhwcView), ('w1', ctypes.c_void_p), ('b1', ctypes.c_void_p), ('w2', ctypes.c_void_p),
+                ('b2', ctypes.c_void_p), ('pred_w', ctypes.c_void_p), ('pred_b', ctypes.c_void_p), ('pred', ctypes.c_void_p),
+                ('pred_c', ctypes.c_int32), ('pred_q14', ctypes.c_int32), ('grid_limit', ctypes.c_int32),
+                ('reserved', ctypes.c_int32)]
+
+
 _VP = ctypes.c_void_p
 _I = ctypes.c_int32
 _F = ctypes.c_float
 _PV = ctypes.POINTER(NhwcView)
 _PC = ctypes.POINTER(ConvDesc)
+_PR = ctypes.POINTER(ResBlockDesc)
 
 # name -> (restype, argtypes); must list every symbol of include/dbsr_b200.h (tests check this)
 PROTOTYPES = {
@@ -52,6 +61,8 @@ PROTOTYPES = {
     'dbsr_conv2d_tc': (_I, [_PC, _VP]),
     'dbsr_conv2d_tc_supported': (_I, [_PC]),
     'dbsr_conv2d_tc_predictor': (_I, [_PC, _VP, _VP, _I, _VP, _I, _VP]),
+    'dbsr_resblock32_tc': (_I, [_PR, _VP]),
+    'dbsr_resblock32_tc_supported': (_I, [_PR]),
     'dbsr_quantize_q14': (_I, [_VP, _VP, ctypes.c_int64, _VP]),
     'dbsr_conv2d_tc_geometry': (_I, [_I, _I, ctypes.POINTER(_I), ctypes.POINTER(_I), ctypes.POINTER(_I),
                                      ctypes.POINTER(_I)]),

@@ -15,7 +15,7 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 LIB = os.path.join(CSRC, 'libdbsr_b200.so')
-SOURCES = ['misc.cu', 'conv_direct.cu', 'corr.cu', 'fusion.cu', 'metrics.cu', 'camera.cu', 'conv_tc.cu']
+SOURCES = ['misc.cu', 'conv_direct.cu', 'corr.cu', 'fusion.cu', 'metrics.cu', 'camera.cu', 'conv_tc.cu', 'resblock_tc.cu']
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17',
               '-Xcompiler', '-fPIC', '-Xptxas', '-v']
 
@@ -31,7 +31,7 @@ def _stale():
     if not os.path.exists(LIB):
         return True
     t = os.path.getmtime(LIB)
-    deps = [os.path.join(CSRC, s) for s in SOURCES] + [os.path.join(CSRC, 'common.cuh'),
+    deps = [os.path.join(CSRC, s) for s in SOURCES] + [os.path.join(CSRC, 'common.cuh'), os.path.join(CSRC, 'tma.cuh'), os.path.join(CSRC, 'tcgen05.cuh'),
                                                        os.path.join(HERE, '..', 'include', 'dbsr_b200.h')]
     return any(os.path.getmtime(d) > t for d in deps)
 

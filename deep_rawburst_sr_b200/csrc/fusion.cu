@@ -413,25 +413,30 @@ __device__ __forceinline__ Vec8 unpack_bf16x8(const uint4& q) {
 struct __align__(16) WsRec { uint32_t o[4]; float w[4]; };
 constexpr int WSP_MAX_OTHERS = 16;
 constexpr int WSP_SMEM = 2 * 2 * 5 * 256 * 16;           // ring: [2 stages][2 frames][5 loads][256 threads] x 16 bytes
-// TMA variant: [2 stages][2 frames][4 taps][256 threads] x 16 B gathered taps (cp.async) | per warp [2 stages][2 frames] 512 B
-// logit boxes | per warp 2 x 512 B reference-frame boxes (embedding, logits) | per warp 3 mbarriers
+// TMA modes.  1 (default): the reference-frame tiles (embedding + logits of frame 0) are staged by TMA, ring as above.
+// 2 (A/B, DBSR_WSUM_TMA=2): additionally all logit tiles: ring [2 stages][2 frames][4 taps][256 threads] x 16 B of gathered taps
+// (cp.async) | per warp [2 stages][2 frames] 512 B logit boxes.  Behind the ring in both modes: per warp 2 x 512 B
+// reference-frame boxes | per warp 3 mbarriers.
 constexpr int WST_TAPS = 2 * 2 * 4 * 256 * 16;
 constexpr int WST_LOGITS = 8 * 2 * 2 * 512;
 constexpr int WST_REF = 8 * 2 * 512;
-constexpr int WST_SMEM = WST_TAPS + WST_LOGITS + WST_REF + 8 * 3 * 8 + 128 /* alignment slack */;
+constexpr int WST_SMEM2 = WST_TAPS + WST_LOGITS + WST_REF + 8 * 3 * 8 + 128 /* alignment slack */;
+constexpr int WST_SMEM1 = WSP_SMEM + WST_REF + 8 * 3 * 8 + 128;
 __device__ __forceinline__ float ex2f(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
 
-// TMA = true (north_star: "TMA staging of the reference-frame tiles"): everything REGULAR in this kernel -- the unwarped
-// reference-frame embedding tile and the 14 logit tiles, 15 of the 28 tile streams of a block -- is staged by the TMA engine
-// (cp.async.bulk.tensor boxes {64 channels, 4 pixels, 1 row} = the 512 bytes one warp consumes, issued by one elected lane per
-// warp, completion on a per-warp mbarrier: no block-wide synchronisation enters the loop); only the 13 x 4 flow-dependent
-// bilinear taps stay per-thread cp.async gathers.  Out-of-image pixels / channels of ragged tiles are zero-filled by the
-// tensor map instead of clamped by address arithmetic.
-template <typename TO, bool TMA>
+// MODE >= 1 (north_star: "TMA staging of the reference-frame tiles"): the unwarped reference-frame tiles (embedding and logits
+// of frame 0) are staged by the TMA engine: cp.async.bulk.tensor boxes {64 channels, 4 pixels, 1 row} = the 512 bytes one
+// warp consumes, issued by one elected lane per warp before the gather records are computed, completion on a per-warp
+// mbarrier (no block-wide synchronisation); out-of-image pixels / channels of ragged tiles are zero-filled by the tensor map.
+// MODE == 2 stages ALL 14 logit tiles that way (15 of the 28 tile streams of a block; only the 13 x 4 flow-dependent bilinear
+// taps stay per-thread cp.async gathers).  Measured on B200 (B = 32, 48^2, profiles/r02_wsum_tma_ncu_summary.txt): the kernel
+// is bound by instruction issue, not by the copy mechanism, and the per-pair mbarrier wait / re-arm / box issue costs more
+// warp instructions (467 M vs 418 M) than the two cp.async it removes: 554 us against 527 us.  So MODE 1 is the default.
+template <typename TO, int MODE>
 __global__ void __launch_bounds__(256, 2)
 softmax_wsum8_pair_kernel(const __grid_constant__ CUtensorMap tmap_feat, const __grid_constant__ CUtensorMap tmap_logits,
                           View feat, View logits, const float* __restrict__ offsets, View fused, int frames) {
@@ -445,16 +450,20 @@ softmax_wsum8_pair_kernel(const __grid_constant__ CUtensorMap tmap_feat, const _
   const int g = tid & 7, pix = tid >> 3, px = pix & 7, py = pix >> 3;
   const int b = blockIdx.z;
   const int ty0 = (blockIdx.x / tiles_x) * WS_TH, tx0 = (blockIdx.x % tiles_x) * WS_TW;
+  constexpr bool TMA = MODE == 2;                         // logits through TMA boxes
+  constexpr bool TMA_REF = MODE >= 1;                     // reference-frame tiles through TMA boxes
+  constexpr int RING_BYTES = TMA ? WST_TAPS : WSP_SMEM;
+  constexpr int LOGIT_BYTES = TMA ? WST_LOGITS : 0;
   constexpr int TAPS = TMA ? 4 : 5;                       // 16-byte ring slots per thread and frame
   constexpr uint32_t FRAME_BYTES = TAPS * 4096u, STAGE_BYTES = 2u * FRAME_BYTES;
   // per-warp TMA staging (TMA variant): 128-byte aligned boxes behind the tap ring
   const uint32_t ring_base = (uint32_t)__cvta_generic_to_shared(ring);
-  const uint32_t lg_s = ((ring_base + (uint32_t)WST_TAPS + 127u) & ~127u) + (uint32_t)warp * 2048u;      // [stage][frame] 512 B
-  const uint32_t ref_s = ((ring_base + (uint32_t)WST_TAPS + 127u) & ~127u) + (uint32_t)WST_LOGITS + (uint32_t)warp * 1024u;
-  const uint32_t bar_s = ((ring_base + (uint32_t)WST_TAPS + 127u) & ~127u) + (uint32_t)(WST_LOGITS + WST_REF) + (uint32_t)warp * 24u;
+  const uint32_t lg_s = ((ring_base + (uint32_t)RING_BYTES + 127u) & ~127u) + (uint32_t)warp * 2048u;      // [stage][frame] 512 B
+  const uint32_t ref_s = ((ring_base + (uint32_t)RING_BYTES + 127u) & ~127u) + (uint32_t)LOGIT_BYTES + (uint32_t)warp * 1024u;
+  const uint32_t bar_s = ((ring_base + (uint32_t)RING_BYTES + 127u) & ~127u) + (uint32_t)(LOGIT_BYTES + WST_REF) + (uint32_t)warp * 24u;
   // this warp's 4 pixels: tile row warp / 2, columns (warp & 1) * 4 .. + 3
   const int wy = ty0 + (warp >> 1), wx = tx0 + (warp & 1) * 4;
-  if (TMA) {
+  if (TMA_REF) {
     if (lane == 0) {
       asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_s));
       asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_s + 8u));
@@ -481,7 +490,7 @@ softmax_wsum8_pair_kernel(const __grid_constant__ CUtensorMap tmap_feat, const _
         ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"((int)blockIdx.y * 64), "r"(wx), "r"(wy), "r"(img)
         : "memory");
   };
-  if (TMA && lane == 0) {     // reference frame of this burst: embedding tile + logit tile -> ref_s, completion on bar 2
+  if (TMA_REF && lane == 0) {     // reference frame of this burst: embedding tile + logit tile -> ref_s, completion on bar 2
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_s + 16u), "r"(1024u) : "memory");
     tma_box(&tmap_feat, bar_s + 16u, ref_s, b * frames);
     tma_box(&tmap_logits, bar_s + 16u, ref_s + 512u, b * frames);
@@ -562,7 +571,7 @@ softmax_wsum8_pair_kernel(const __grid_constant__ CUtensorMap tmap_feat, const _
   float m[8], s[8], acc[8];
   {
     Vec8 l, a;
-    if (TMA) {
+    if (TMA_REF) {
       bar_wait(bar_s + 16u, 0u);
       uint4 qa, ql;
       asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(qa.x), "=r"(qa.y), "=r"(qa.z), "=r"(qa.w) : "r"(ref_s + (uint32_t)lane * 16u));
@@ -803,37 +812,39 @@ extern "C" int dbsr_softmax_wsum(const dbsr_nhwc_t* feat, const dbsr_nhwc_t* log
     // records hold 32-bit byte offsets inside one image and at most WSP_MAX_OTHERS non-reference frames
     if (key == 7 && offsets != nullptr && frames >= 2 && frames - 1 <= WSP_MAX_OTHERS &&
         (long long)fused->h * fused->w * feat->c_pitch * 2 < (1ll << 32)) {
-      // TMA staging of the regular streams (reference-frame tile + all logit tiles); DBSR_WSUM_NO_TMA=1 keeps them on
-      // per-thread cp.async (A/B switch, identical results)
-      static const bool use_tma = getenv("DBSR_WSUM_NO_TMA") == nullptr;
-      EncodeTiledFn encode = use_tma ? get_encode() : nullptr;
+      // TMA mode (see the kernel): 1 = reference-frame tiles (default), 2 = + all logit tiles, 0 = none (A/B: DBSR_WSUM_TMA)
+      static const int want_mode = getenv("DBSR_WSUM_TMA") ? atoi(getenv("DBSR_WSUM_TMA")) : 1;
+      EncodeTiledFn encode = want_mode > 0 ? get_encode() : nullptr;
       alignas(64) CUtensorMap mf, ml;
       memset(&mf, 0, sizeof(mf)); memset(&ml, 0, sizeof(ml));
-      bool tma = encode != nullptr;
-      if (tma) {
+      int mode = encode != nullptr ? (want_mode >= 2 ? 2 : 1) : 0;
+      if (mode) {
         const dbsr_nhwc_t* vs[2] = {feat, logits};
         CUtensorMap* ms[2] = {&mf, &ml};
-        for (int i = 0; i < 2 && tma; ++i) {
+        for (int i = 0; i < 2 && mode; ++i) {
           const dbsr_nhwc_t* v = vs[i];
           cuuint64_t dims[4] = {(cuuint64_t)v->c, (cuuint64_t)v->w, (cuuint64_t)v->h, (cuuint64_t)v->n};
           cuuint64_t strides[3] = {(cuuint64_t)v->c_pitch * 2, (cuuint64_t)v->w * v->c_pitch * 2, (cuuint64_t)v->h * v->w * v->c_pitch * 2};
           cuuint32_t box[4] = {64u, 4u, 1u, 1u};
           cuuint32_t es[4] = {1, 1, 1, 1};
           void* base = reinterpret_cast<__nv_bfloat16*>(v->data) + v->c_off;
-          tma = encode(ms[i], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                       CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+          if (encode(ms[i], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+            mode = 0;
         }
       }
-      static bool attr_set_dev[MAX_DEVICES][2] = {};
-      bool& attr_set = attr_set_dev[current_device_slot()][tma ? 1 : 0];
+      typedef void (*WsKernel)(const CUtensorMap, const CUtensorMap, View, View, const float*, View, int);
+      const WsKernel kern = mode == 2 ? softmax_wsum8_pair_kernel<__nv_bfloat16, 2>
+                            : (mode == 1 ? softmax_wsum8_pair_kernel<__nv_bfloat16, 1> : softmax_wsum8_pair_kernel<__nv_bfloat16, 0>);
+      const int smem = mode == 2 ? WST_SMEM2 : (mode == 1 ? WST_SMEM1 : WSP_SMEM);
+      static bool attr_set_dev[MAX_DEVICES][3] = {};
+      bool& attr_set = attr_set_dev[current_device_slot()][mode];
       if (!attr_set) {
-        cudaError_t e = tma ? cudaFuncSetAttribute(softmax_wsum8_pair_kernel<__nv_bfloat16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, WST_SMEM)
-                            : cudaFuncSetAttribute(softmax_wsum8_pair_kernel<__nv_bfloat16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, WSP_SMEM);
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         DBSR_REQUIRE(e == cudaSuccess, "softmax_wsum: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
         attr_set = true;
       }
-      if (tma) launch_pdl(softmax_wsum8_pair_kernel<__nv_bfloat16, true>, dim3(grid8), dim3(256), (size_t)WST_SMEM, st, mf, ml, f, l, offsets, o, frames);
-      else launch_pdl(softmax_wsum8_pair_kernel<__nv_bfloat16, false>, dim3(grid8), dim3(256), (size_t)WSP_SMEM, st, mf, ml, f, l, offsets, o, frames);
+      launch_pdl(kern, dim3(grid8), dim3(256), (size_t)smem, st, mf, ml, f, l, offsets, o, frames);
     }
     else if (key == 0) softmax_wsum8_kernel<float, float, float><<<grid8, 256, 0, st>>>(f, l, offsets, o, frames);
     else if (key == 7) softmax_wsum8_kernel<__nv_bfloat16, __nv_bfloat16, __nv_bfloat16><<<grid8, 256, 0, st>>>(f, l, offsets, o, frames);

@@ -178,6 +178,9 @@ class DBSREngine:
         self._graphs: Dict[tuple, tuple] = {}
         self._side = None                 # second stream of the alignment / encoder overlap
         self.overlap_alignment = True
+        # decoder post-res blocks (32 channels at 8H x 8W): one fused launch per block (csrc/resblock_tc.cu) instead of two
+        # conv launches; bit-identical results.  False = A/B against the two-launch path.
+        self.fuse_hr_resblocks = True
         # persistent-grid size of the encoder convs while the alignment stream is active: leaving ~1/6 of the SMs to the
         # short PWC-Net launches is worth another 1-1.5 % per step on B200 (148 SMs -> 124; measured 9.39 -> 9.25 ms)
         sms = torch.cuda.get_device_properties(self.device).multi_processor_count
@@ -609,7 +612,17 @@ class DBSREngine:
             cur, nxt = ha, hb
         for i in range(self.dec_post):
             key = f'decoder.post_res_layers.{i}'
-            if i == self.dec_post - 1 and self._fuse_predictor(key + '.conv2.0', ht, nxt, cur):
+            last = i == self.dec_post - 1
+            if self._fused_resblock_ok(key, cur, nxt):
+                # relu(x + conv2(relu(conv1(x)))) in ONE launch, the intermediate map stays on the SM; the last block also
+                # applies the 1x1 predictor + ReLU (decoders.py:52,61) in its epilogue and writes `pred` directly
+                fuse_pred = last and self.pred_w.shape[0] <= 4
+                self._resblock_fused(key, cur, nxt, pred if fuse_pred else None)
+                if fuse_pred:
+                    return pred
+                cur, nxt = nxt, cur
+                continue
+            if last and self._fuse_predictor(key + '.conv2.0', ht, nxt, cur):
                 # last block: relu(x + conv2(relu(conv1(x)))) never goes to HBM -- the tcgen05 epilogue applies the 1x1
                 # predictor + ReLU (decoders.py:52,61) to the 32 channels each thread holds and writes `pred` directly
                 self._conv(key + '.conv1.0', cur, ht, ACT_RELU)
@@ -626,6 +639,35 @@ class DBSREngine:
             return pred
         self._run('predictor', ops.predictor, cur, self.pred_w, self.pred_b, pred)
         return pred
+
+    def _fused_resblock_ok(self, key: str, x: Act, y: Act) -> bool:
+        c1, c2 = self.W.get(key + '.conv1.0'), self.W.get(key + '.conv2.0')
+        if not (self.fuse_hr_resblocks and c1 is not None and c2 is not None and c1.tc is not None and c2.tc is not None):
+            return False
+        if not (x.dtype == torch.bfloat16 and c1.cin == 32 and c1.cout == 32 and c2.cin == 32 and c2.cout == 32 and
+                c1.ksize == 3 and c2.ksize == 3 and c1.bias is not None and c2.bias is not None):
+            return False
+        return ops.resblock32_tc_supported(x, y, c1.tc, c1.bias, c2.tc, c2.bias)
+
+    def _resblock_fused(self, key: str, x: Act, y: Act, pred: Optional[torch.Tensor]) -> None:
+        c1, c2 = self.W[key + '.conv1.0'], self.W[key + '.conv2.0']
+        fam = 'resblock_tc'
+        fl = 2 * 2 * x.n * x.h * x.w * 32 * 32 * 9
+        nbytes = 2 * x.n * x.h * x.w * 32 * 2
+        if pred is not None:
+            fl += 2 * x.n * x.h * x.w * self.pred_w.shape[0] * 32
+            nbytes += pred.numel() * pred.element_size() - x.n * x.h * x.w * 32 * 2
+        self.flops[fam] = self.flops.get(fam, 0) + fl
+        self.hbm_bytes[fam] = self.hbm_bytes.get(fam, 0) + nbytes
+        self.launches += 1
+        ev = self._tic(fam)
+        if ev is not None and self.layer_events is not None:
+            self.layer_events.setdefault(key, []).append((self.timers[fam][-1], fl, fam, (x.n, x.h, x.w, 32, 32)))
+        if pred is not None:
+            ops.resblock32_tc(x, None, c1.tc, c1.bias, c2.tc, c2.bias, self.pred_w_host, self.pred_b_host, pred)
+        else:
+            ops.resblock32_tc(x, y, c1.tc, c1.bias, c2.tc, c2.bias)
+        self._toc(ev)
 
     def _fuse_predictor(self, key: str, x: Act, y: Act, residual: Act) -> bool:
         cw = self.W[key]

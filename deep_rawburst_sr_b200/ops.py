@@ -10,7 +10,7 @@ from typing import Optional
 import torch
 
 from . import _lib
-from ._lib import ACT_LRELU, ACT_NONE, ACT_RELU, DBSR_BF16, DBSR_F32, ConvDesc, NhwcView  # noqa: F401
+from ._lib import ACT_LRELU, ACT_NONE, ACT_RELU, DBSR_BF16, DBSR_F32, ConvDesc, NhwcView, ResBlockDesc  # noqa: F401
 
 _checked_devices = set()
 
@@ -119,6 +119,51 @@ def conv2d_tc_predictor(x: Act, w: torch.Tensor, bias: Optional[torch.Tensor], y
                                                             1 if pred.dtype == torch.int16 else 0, _stream()),
                'dbsr_conv2d_tc_predictor')
     return pred
+
+
+def _host_floats(v, n=None):
+    if isinstance(v, ctypes.Array):
+        return v
+    t = torch.as_tensor(v, dtype=torch.float32).cpu().reshape(-1)
+    assert n is None or t.numel() == n
+    return (ctypes.c_float * t.numel())(*t.tolist())
+
+
+def _resblock_desc(x: Act, y: Optional[Act], w1, b1, w2, b2, pred_w=None, pred_b=None, pred=None, grid_limit=0):
+    keep = []
+    pw = pb = None
+    k = 0
+    if pred is not None:
+        pb = _host_floats(pred_b)
+        k = len(pb)
+        pw = _host_floats(pred_w, k * 32)
+        keep = [pw, pb]
+        assert pred.dtype in (torch.float32, torch.int16) and pred.is_contiguous() and tuple(pred.shape) == (x.n, k, x.h, x.w)
+    d = ResBlockDesc(x.view(), y.view() if y is not None else _NULL_VIEW, w1.data_ptr(), b1.data_ptr(), w2.data_ptr(), b2.data_ptr(),
+                     ctypes.cast(pw, ctypes.c_void_p) if pw is not None else None,
+                     ctypes.cast(pb, ctypes.c_void_p) if pb is not None else None,
+                     None if pred is None else pred.data_ptr(), k, 1 if (pred is not None and pred.dtype == torch.int16) else 0,
+                     int(grid_limit), 0)
+    return d, keep
+
+
+def resblock32_tc(x: Act, y: Optional[Act], w1: torch.Tensor, b1: torch.Tensor, w2: torch.Tensor, b2: torch.Tensor,
+                  pred_w=None, pred_b=None, pred: Optional[torch.Tensor] = None, grid_limit: int = 0):
+    """y = relu(x + conv2(relu(conv1(x) + b1)) + b2) for 32-channel bf16 maps in one tcgen05 launch (the intermediate map stays
+    on the SM); w1 / w2: packed like `conv2d(..., tensor_core=True)` weights.  With `pred` (fp32 or int16 [n, k, h, w]) the 1x1
+    predictor + ReLU is applied in the epilogue and `y` is not written."""
+    d, _keep = _resblock_desc(x, y, w1, b1, w2, b2, pred_w, pred_b, pred, grid_limit)
+    _lib.check(_lib.load_library().dbsr_resblock32_tc(ctypes.byref(d), _stream()), 'dbsr_resblock32_tc')
+    return pred if pred is not None else y
+
+
+def resblock32_tc_supported(x: Act, y: Optional[Act], w1, b1, w2, b2, with_pred: bool = False) -> bool:
+    d = ResBlockDesc(x.view(), y.view() if y is not None else _NULL_VIEW, w1.data_ptr(), b1.data_ptr(), w2.data_ptr(), b2.data_ptr(),
+                     None, None, None, 0, 0, 0, 0)
+    if with_pred:      # geometry / alignment only: the predictor arguments are checked by the call itself
+        d.y = _NULL_VIEW
+        d.pred, d.pred_w, d.pred_b, d.pred_c = 1, 1, 1, 3
+    return bool(_lib.load_library().dbsr_resblock32_tc_supported(ctypes.byref(d)))
 
 
 def quantize_q14(src: torch.Tensor, dst: torch.Tensor) -> torch.Tensor:

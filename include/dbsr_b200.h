@@ -124,6 +124,33 @@ int dbsr_conv2d_tc_supported(const dbsr_conv_t* p);
  *   110-111, and the save_results.py writers), which halves the device-to-host / gather bytes.                            */
 int dbsr_conv2d_tc_predictor(const dbsr_conv_t* p, const float* pred_w, const float* pred_b, int32_t pred_c, void* pred,
                              int32_t pred_q14, void* stream);
+/* Fused residual block of the decoder's high-resolution stage (models/layers/blocks.py:84-96 as used by the four
+ * `post_res_layers` of ResPixShuffleConv, models/dbsr/decoders.py:45-50, 59):
+ *     y = relu(x + conv2(relu(conv1(x) + b1)) + b2),  3x3 / stride 1 / zero padding, 32 -> 32 channels
+ * in ONE launch: the intermediate map stays in shared memory (bf16, rounded exactly where the two-launch path rounds it),
+ * so the block reads x once and writes y once.  Results are bit-identical to dbsr_conv2d_tc(conv1) + dbsr_conv2d_tc(conv2,
+ * residual = x).
+ *   x, y: bf16 NHWC views of 32 channels (c_off, c_pitch multiples of 8, 16-byte aligned), same geometry, NOT aliased.
+ *   w1, w2: bf16 [9][32][32] as dbsr_conv2d_tc packs a 32 -> 32 3x3 kernel; b1, b2: fp32 [32], 16-byte aligned.
+ *   pred != NULL: the decoder's 1x1 predictor + ReLU (decoders.py:52, 61) is applied in the epilogue as in
+ *   dbsr_conv2d_tc_predictor (pred_w [pred_c][32], pred_b [pred_c]: HOST arrays; pred: fp32 or, with pred_q14, int16
+ *   [n, pred_c, h, w]); y is then not written and may be empty.                                                       */
+typedef struct dbsr_resblock {
+  dbsr_nhwc_t x, y;
+  const void*  w1;
+  const float* b1;
+  const void*  w2;
+  const float* b2;
+  const float* pred_w;
+  const float* pred_b;
+  void*        pred;
+  int32_t      pred_c;
+  int32_t      pred_q14;
+  int32_t      grid_limit;   /* cap of the persistent grid (CTAs); 0 = one per SM */
+  int32_t      reserved;
+} dbsr_resblock_t;
+int dbsr_resblock32_tc(const dbsr_resblock_t* p, void* stream);
+int dbsr_resblock32_tc_supported(const dbsr_resblock_t* p);
 /* the same quantisation as a stand-alone pass for the paths without the fused epilogue: dst[i] = (int16)(clamp(src[i],0,1)*2^14) */
 int dbsr_quantize_q14(const float* src, int16_t* dst, int64_t count, void* stream);
 /* tiling chosen for (Cin, Cout): K chunk (64 -> SWIZZLE_128B, 32 -> SWIZZLE_64B), padded K, UMMA N, padded Cout */

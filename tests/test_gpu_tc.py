@@ -143,6 +143,64 @@ def test_conv2d_tc_fused_predictor(n, h, w, use_res, k):
     assert (ya.buf == 5.0).all()        # the conv's output map is not written in this mode
 
 
+@pytest.mark.parametrize('n,h,w,with_pred', [(2, 48, 48, False), (1, 16, 24, False), (3, 37, 53, False), (1, 80, 20, False),
+                                             (2, 5, 7, False), (2, 48, 48, True), (1, 33, 50, True), (5, 64, 96, False)])
+def test_resblock32_fused(n, h, w, with_pred):
+    """dbsr_resblock32_tc: relu(x + conv2(relu(conv1(x) + b1)) + b2) in one launch (the intermediate map lives in shared
+    memory) -- (a) BIT-IDENTICAL to the two-launch tcgen05 path (dbsr_conv2d_tc x 2, residual on the tensor core), incl.
+    ragged tiles (37x53: tiles of 16x24), maps smaller than one tile, several items per CTA pipeline stage; (b) within
+    bf16 rounding of the fp32 reference of the same bf16-rounded operands with the intermediate map rounded to bf16;
+    (c) with the fused predictor: equal to dbsr_conv2d_tc_predictor on the same intermediate (fp32, 1e-6) and y untouched;
+    poison around the input view must not leak (x is a channel slice of a wider buffer)."""
+    if not torch.cuda.is_available():
+        pytest.skip('needs a CUDA device')
+    from deep_rawburst_sr_b200 import ops
+    from deep_rawburst_sr_b200.engine import pack_tc
+    dev = torch.device('cuda:0')
+    g = torch.Generator().manual_seed(n * 7919 + h * 31 + w)
+    x = torch.randn(n, 32, h, w, generator=g).bfloat16().float()
+    w1 = (torch.randn(32, 32, 3, 3, generator=g) / 288 ** 0.5).bfloat16().float()
+    w2 = (torch.randn(32, 32, 3, 3, generator=g) / 288 ** 0.5).bfloat16().float()
+    b1, b2 = torch.randn(32, generator=g) * 0.2, torch.randn(32, generator=g) * 0.2
+    pw = torch.randn(3, 32, generator=g) / 32 ** 0.5
+    pb = torch.randn(3, generator=g) * 0.1
+    t_ref = torch.relu(F.conv2d(x, w1, b1, padding=1)).bfloat16().float()
+    mid = torch.relu(x + F.conv2d(t_ref, w2, b2, padding=1))
+    xbuf = torch.full((n, h, w, 48), 9.0, dtype=torch.bfloat16, device=dev)       # poison on both sides of the view
+    xa = ops.Act(xbuf).slice(8, 32).from_nchw(x.to(dev))
+    w1p, w2p, b1d, b2d = pack_tc(w1.to(dev)), pack_tc(w2.to(dev)), b1.to(dev), b2.to(dev)
+    # two-launch path
+    ta = ops.Act.empty(n, h, w, 32, torch.bfloat16, dev)
+    y2 = ops.Act.empty(n, h, w, 32, torch.bfloat16, dev)
+    ops.conv2d(xa, w1p, b1d, ta, 3, 1, 1, ops.ACT_RELU, None, tensor_core=True)
+    if with_pred:
+        pred2 = torch.full((n, 3, h, w), -1.0, device=dev)
+        ops.conv2d_tc_predictor(ta, w2p, b2d, y2, 3, ops.ACT_RELU, xa, pw, pb, pred2)
+        pred = torch.full((n, 3, h, w), -2.0, device=dev)
+        assert ops.resblock32_tc_supported(xa, None, w1p, b1d, w2p, b2d, with_pred=True)
+        ops.resblock32_tc(xa, None, w1p, b1d, w2p, b2d, pw, pb, pred)
+        torch.cuda.synchronize()
+        assert (pred - pred2).abs().max().item() <= 1e-6, (pred - pred2).abs().max().item()
+        ref = torch.relu(F.conv2d(mid, pw.view(3, 32, 1, 1), pb))
+        assert (pred.cpu() - ref).abs().max().item() <= 2e-2 * max(1.0, ref.abs().max().item())
+        q = torch.zeros((n, 3, h, w), dtype=torch.int16, device=dev)
+        ops.resblock32_tc(xa, None, w1p, b1d, w2p, b2d, pw, pb, q)
+        assert torch.equal(q, (pred.clamp(0.0, 1.0) * 2 ** 14).short())
+        return
+    ops.conv2d(ta, w2p, b2d, y2, 3, 1, 1, ops.ACT_RELU, xa, tensor_core=True)
+    ybuf = torch.full((n, h, w, 40), 5.0, dtype=torch.bfloat16, device=dev)
+    ya = ops.Act(ybuf).slice(8, 32)
+    assert ops.resblock32_tc_supported(xa, ya, w1p, b1d, w2p, b2d)
+    for _ in range(2):
+        ops.resblock32_tc(xa, ya, w1p, b1d, w2p, b2d)
+    torch.cuda.synchronize()
+    assert torch.equal(ybuf[..., 8:], y2.buf), (ybuf[..., 8:].float() - y2.buf.float()).abs().max().item()
+    assert (ybuf[..., :8] == 5.0).all() and (xbuf[..., :8] == 9.0).all() and (xbuf[..., 40:] == 9.0).all()
+    got = ya.to_nchw().cpu()
+    scale = max(1.0, mid.abs().max().item())
+    assert (got - mid).abs().max().item() <= scale * 2.0 ** -7
+
+
 if __name__ == '__main__':
     # probe mode: `python tests/test_gpu_tc.py <case>` prints the error of one case (one process per case so a
     # device fault in one variant does not hide the others)
