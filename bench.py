@@ -41,6 +41,8 @@ def parse():
     ap.add_argument('--one-forward', action='store_true', help='profiling aid: warm up, run ONE eager forward, exit')
     ap.add_argument('--no-graph', action='store_true', help='launch eagerly instead of replaying a CUDA graph')
     ap.add_argument('--no-overlap', action='store_true', help='run PWC-Net and the encoder on ONE stream (default: two, fork / join)')
+    ap.add_argument('--no-extra-configs', action='store_true',
+                    help='skip the extra BASELINE.json configs reported next to the headline (cfg_80, cfg_256, strong_cfg2, cfg_256_gather)')
     return ap.parse_args()
 
 
@@ -132,9 +134,12 @@ def cpu_reference_arm(args, rank):
     torch.set_num_threads(cores)
     sd = O.make_state_dict(0)
     burst = O.make_burst(0, 1, FRAMES, args.size, args.size)
-    for _ in range(max(1, min(args.warmup, 2))):
+    t_w = time.perf_counter()
+    for _ in range(max(1, min(args.warmup, 3))):
         O.dbsr_forward_fast(burst, sd)
-    steps = max(1, min(args.steps, 10))
+    per = (time.perf_counter() - t_w) / max(1, min(args.warmup, 3))
+    # the same number of timed steps as the product arm, unless that would run for more than ~2.5 minutes on this host
+    steps = max(1, min(args.steps, int(150.0 / max(per, 1e-3))))
     t0 = time.perf_counter()
     for _ in range(steps):
         O.dbsr_forward_fast(burst, sd)
@@ -307,6 +312,80 @@ def main():
         sampler.stop_flag = True
         sampler.join(timeout=3)
 
+    # ---- the other BASELINE.json configurations the driver never asks for, as extra keys of the same line
+    extras = {}
+    if not args.no_extra_configs and args.precision == 'bf16' and S == 48 and B == 32:
+        net.use_cuda_graph = not args.no_graph
+
+        def time_config(b, s, steps, int16=False, gather_total=0):
+            """bursts/s of `steps` forwards of b bursts of 14x4xsxs per GPU (CUDA-graph replay, inputs resident); with
+            gather_total > 0 every forward is followed by the NCCL all-gather of the (int16) predictions on a side stream"""
+            g2 = torch.Generator().manual_seed(2000 + rank)
+            x = torch.rand(b, FRAMES, 4, s, s, generator=g2).to(dev)
+            net.output_int16 = int16
+            gat = None
+            if gather_total:
+                from deep_rawburst_sr_b200.sharding import OutputGatherer
+                gat = OutputGatherer(gather_total, depth=2)
+            gev, full = None, None
+            for _ in range(3):
+                p_, _a = net(x)
+                if gat is not None:
+                    full, gev = gat.submit(p_)
+            barrier()
+            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a0.record()
+            for _ in range(steps):
+                p_, _a = net(x)
+                if gat is not None:
+                    full, gev = gat.submit(p_)
+            if gev is not None:
+                torch.cuda.current_stream().wait_event(gev)
+            a1.record()
+            barrier()
+            ms = max_over_ranks(a0.elapsed_time(a1))
+            net.output_int16 = False
+            out = {'bursts_per_gpu': b, 'size': s, 'steps': steps, 'ms_per_step': ms / steps,
+                   'value': world * b * steps / (ms / 1e3), 'unit': 'bursts/s'}
+            if gat is not None:
+                out['gathered_shape'] = list(full.shape)
+                out['gathered_dtype'] = str(full.dtype).replace('torch.', '')
+                out['bytes_gathered_per_rank_per_step'] = int(full.numel() * full.element_size())
+            gf80 = CONV_GFLOP_PER_BURST.get(s)
+            if gf80:
+                out['model_tflops_per_gpu'] = gf80 * out['value'] / 1e3 / world
+                out['frac_of_conv_roofline'] = out['model_tflops_per_gpu'] / peaks()['tflops']
+            return out
+
+        try:
+            if world == 1:
+                # BASELINE configs[2] on ONE GPU (16 bursts of 14x4x80x80 -> 3x640x640): the 1-GPU point of its strong-scaling curve
+                extras['cfg_80'] = dict(time_config(16, 80, max(5, args.steps // 2)),
+                                        workload='BASELINE.json configs[2] on 1 GPU: 16 bursts of 14x4x80x80 -> 3x640x640')
+                # BASELINE configs[4], the share of one GPU: one 14x4x256x256 burst -> 3x2048x2048 (untiled: it fits)
+                extras['cfg_256'] = dict(time_config(1, 256, max(5, args.steps // 2)),
+                                         workload='BASELINE.json configs[4], one rank\'s share: 1 burst of 14x4x256x256 -> 3x2048x2048, '
+                                                  'untiled (the whole crop fits one GPU: tiling would only add halo recompute)')
+                # small-batch (latency) regime: what the reference's batch-1 evaluation loops and 8-GPU configs[2] run per GPU
+                extras['cfg_48_b2'] = time_config(2, 48, max(10, args.steps))
+                extras['cfg_48_b1'] = time_config(1, 48, max(10, args.steps))
+            elif 16 % world == 0:
+                # STRONG scaling of BASELINE configs[2]: the same 16 bursts of 80x80 split over the ranks, int16 predictions
+                # (the reference writers' 14-bit form) all-gathered over NVLink behind the next forward
+                extras['strong_cfg2'] = dict(time_config(16 // world, 80, max(5, args.steps // 2), int16=True, gather_total=16),
+                                             scaling='strong', global_batch=16,
+                                             workload=f'BASELINE.json configs[2]: 16 bursts of 14x4x80x80 split {16 // world} per GPU over '
+                                                      f'{world} GPUs, int16 output gather (NCCL all_gather on a side stream)')
+                extras['strong_cfg2_no_gather'] = dict(time_config(16 // world, 80, max(5, args.steps // 2)), scaling='strong',
+                                                       global_batch=16)
+                if world == 8:
+                    extras['cfg_256_gather'] = dict(time_config(1, 256, max(5, args.steps // 2), int16=True, gather_total=8),
+                                                    workload='BASELINE.json configs[4]: 8 bursts of 14x4x256x256 -> 3x2048x2048, one per GPU '
+                                                             '(untiled), int16 NCCL output gather')
+        except Exception as ex:      # extras never fail the headline measurement
+            extras['error'] = repr(ex)[:300]
+        barrier()
+
     # ---- instrumented pass (same K steps, eager launches bracketed by CUDA events on the launching stream): per
     #      kernel-family device time for the roofline; kept out of the timed regions above because creating ~800 events
     #      per step makes the step CPU-bound
@@ -335,27 +414,47 @@ def main():
         return
 
     pk = peaks()
-    # dominant kernel family by measured device time inside the timed region
-    dom = max(fam.items(), key=lambda kv: kv[1][0])[0] if fam else None
+    # dominant kernel family by measured device time inside the timed region.  The tcgen05 implicit-GEMM convolutions are ONE
+    # family for the roofline whether a layer runs as a single conv launch (conv_tc_kernel) or as a fused residual block
+    # (resblock32_tc_kernel: two convs per launch) -- moving the slow N = 32 layers into their own row must not flatter it.
+    tensor_fams = [k for k in ('conv_tc', 'resblock_tc') if k in fam]
+    if tensor_fams:
+        fam_tc = (sum(fam[k][0] for k in tensor_fams), sum(fam[k][1] for k in tensor_fams))
+        flops['tensor_conv'] = sum(flops.get(k, 0) for k in tensor_fams)
+        alg_bytes['tensor_conv'] = sum(alg_bytes.get(k, 0) for k in tensor_fams)
+    rank_by = {k: v for k, v in fam.items() if k not in tensor_fams}
+    if tensor_fams:
+        rank_by['tensor_conv'] = fam_tc
+    dom = max(rank_by.items(), key=lambda kv: kv[1][0])[0] if rank_by else None
     roofline = None
-    if dom in ('conv_tc', 'conv_direct'):
-        ms, n = fam[dom]
+    if dom in ('tensor_conv', 'conv_direct'):
+        ms, n = rank_by[dom]
         ach = flops.get(dom, 0) / (ms / 1e3) / 1e12
         # measured DRAM traffic of the same launches (ncu dram__bytes_read/write.sum of one forward at this config,
         # committed under profiles/ by tools/gpu_ncu_traffic.sh + tools/traffic_table.py), per launch like `achieved`
-        traffic = None
-        tpath = os.path.join(ROOT, 'profiles', f'r01_traffic_b{B}.json')
+        traffic, traffic_note = None, None
+        tpath = os.path.join(ROOT, 'profiles', f'r02_traffic_b{B}.json')
         if S == 48 and args.precision == 'bf16' and os.path.exists(tpath):
-            tf = json.load(open(tpath))['families'].get(dom)
-            if tf:
-                traffic = (tf['dram_read_bytes'] + tf['dram_write_bytes']) / tf['launches']
-        roofline = {'kernel': dom, 'bound': 'tensor', 'achieved': ach, 'peak': pk['tflops'], 'unit': 'TFLOP/s',
-                    'frac': ach / pk['tflops'], 'traffic': traffic, 'peak_source': pk['src'],
+            tfile = json.load(open(tpath))
+            # the capture must describe THIS launch sequence: same kernel families, same launches per family per forward
+            mine = {k: int(round(v[1] / args.steps)) for k, v in fam.items()}
+            theirs = {k: int(v['launches']) for k, v in tfile['families'].items()}
+            if mine == theirs:
+                tfs = [tfile['families'][k] for k in (tensor_fams if dom == 'tensor_conv' else [dom])]
+                traffic = sum(t['dram_read_bytes'] + t['dram_write_bytes'] for t in tfs) / sum(t['launches'] for t in tfs)
+                traffic_note = f'ncu dram__bytes_read+write.sum of one forward at this config ({os.path.basename(tpath)}), per launch'
+            else:
+                traffic_note = (f'{os.path.basename(tpath)} does not match this run (launches per family {theirs} vs {mine}): '
+                                'regenerate with tools/gpu_ncu_traffic.sh + tools/traffic_table.py')
+        roofline = {'kernel': 'conv_tc_kernel + resblock32_tc_kernel (tcgen05 implicit-GEMM convolutions)' if dom == 'tensor_conv' else dom,
+                    'bound': 'tensor', 'achieved': ach, 'peak': pk['tflops'], 'unit': 'TFLOP/s',
+                    'frac': ach / pk['tflops'], 'traffic': traffic, 'traffic_source': traffic_note, 'peak_source': pk['src'],
                     'launches': n, 'kernel_ms_per_step': ms / args.steps,
                     'flops_per_launch': flops.get(dom, 0) / max(n, 1), 'us_per_launch': ms * 1e3 / max(n, 1),
                     'algorithmic_bytes_per_launch': alg_bytes.get(dom, 0) / max(n, 1),
-                    'note': 'family of ~111 implicit-GEMM conv launches per step (Cout 2..512); SS-mode tcgen05 operand '
-                            'fetch (128 B/clk/SM shared memory) bounds N<128 layers below the tensor peak, see DESIGN.md 4.1'}
+                    'note': 'family of ~107 implicit-GEMM conv launches per step (Cout 2..512; the four HR residual blocks are one '
+                            'fused launch each); SS-mode tcgen05 operand fetch (128 B/clk/SM shared memory) bounds N<128 layers '
+                            'below the tensor peak, see DESIGN.md 4.1'}
     elif dom is not None:
         ms, n = fam[dom]
         roofline = {'kernel': dom, 'bound': 'hbm', 'achieved': None, 'peak': pk['hbm_gbs'], 'unit': 'GB/s', 'frac': None,
@@ -378,7 +477,7 @@ def main():
     for k in families:
         if families[k]['hbm_gbs'] is not None:
             families[k]['hbm_frac'] = families[k]['hbm_gbs'] / pk['hbm_gbs']
-        if families[k]['tflops'] is not None and k == 'conv_tc':
+        if families[k]['tflops'] is not None and k in ('conv_tc', 'resblock_tc'):
             families[k]['tensor_frac'] = families[k]['tflops'] / pk['tflops']
 
     cpu = None
@@ -422,6 +521,7 @@ def main():
         'cpu_baseline': cpu,
         'clocks': sampler.summary(),
         'model_tflops': (gf * value / 1e3) if gf else None,
+        'extra_configs': extras or None,
     }
     print(json.dumps(line))
     if world > 1:

@@ -31,7 +31,7 @@ def gather_bursts(local: torch.Tensor, total: int) -> torch.Tensor:
     buf = local.new_zeros((pad,) + tuple(local.shape[1:]))
     buf[:local.shape[0]] = local
     out = [torch.empty_like(buf) for _ in range(world)]
-    dist.all_gather(out, buf)
+    dist.all_gather([o.view(torch.uint8) for o in out], buf.view(torch.uint8))      # byte views: NCCL has no int16
     return torch.cat([o[:s] for o, s in zip(out, sizes)], dim=0)
 
 
@@ -111,7 +111,7 @@ class OutputGatherer:
                 ev.record(cur)
             return self._stage[k][:self.total], ev
         if not cuda:
-            dist.all_gather_into_tensor(self._out[k], self._stage[k])
+            dist.all_gather_into_tensor(self._bytes(self._out[k]), self._bytes(self._stage[k]))
             return self._compact(self._out[k]), None
         if self._side is None:
             self._side = torch.cuda.Stream(device=local.device)
@@ -119,7 +119,7 @@ class OutputGatherer:
         staged.record(cur)
         self._side.wait_event(staged)
         with torch.cuda.stream(self._side):
-            dist.all_gather_into_tensor(self._out[k], self._stage[k])
+            dist.all_gather_into_tensor(self._bytes(self._out[k]), self._bytes(self._stage[k]))
             # ragged shards: the compaction READS the gathered buffer, so it must be ordered after the collective -- on the
             # side stream, before the event the caller waits on (on the current stream it would race with the gather)
             gathered = self._compact(self._out[k])
@@ -129,6 +129,12 @@ class OutputGatherer:
             gathered.record_stream(cur)               # allocated on the side stream, consumed on the caller's
         self._done[k] = ev
         return gathered, ev
+
+    @staticmethod
+    def _bytes(t: torch.Tensor) -> torch.Tensor:
+        """the gather is pure data movement: hand the collective a byte view, so that every element type works (NCCL has no
+        int16, the 14-bit quantised prediction format)"""
+        return t.view(torch.uint8)
 
     def _compact(self, out: torch.Tensor) -> torch.Tensor:
         if all(s == self.pad for s in self.sizes):

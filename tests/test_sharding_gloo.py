@@ -38,6 +38,11 @@ def _worker(rank, world, port, total, out_dir):
     for rep in range(3):     # slots are recycled
         got, ev = gat.submit(_standin_forward(bursts[lo:hi]) + rep)
         assert ev is None and torch.equal(got, _standin_forward(bursts) + rep)
+    # int16 predictions (the 14-bit quantised output format; NCCL has no int16 -> the gatherer moves bytes)
+    gat16 = sharding.OutputGatherer(total, depth=1)
+    q = (_standin_forward(bursts) * 1000).short()
+    got16, _ = gat16.submit(q[lo:hi])
+    assert got16.dtype == torch.int16 and torch.equal(got16, q)
     # metric scalars: one all_reduce of [sums | counts] instead of gathering images; inf / nan images are dropped
     per_image = _standin_forward(bursts).flatten(1).mean(1)
     per_image[0] = float('inf')
