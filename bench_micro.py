@@ -259,6 +259,20 @@ def main():
         dt = (time.perf_counter() - t0) / 50
         emit({'leg': 'generator', 'op': 'rgb2rawburst as called (host RNG, transform sampling, noise draw + upload)', 'ms': dt * 1e3,
               'bursts_per_s': 1.0 / dt, 'timing': 'host wall clock over 50 bursts'})
+        # batched front end: parameters of 32 bursts sampled up front, one upload per table, three launches per batch
+        imgs = torch.rand(32, 3, 432, 432, generator=g).to(dev)
+        for mode in ('device', 'host'):
+            for _ in range(2):
+                G.rgb2rawburst_batch(imgs, FRAMES, 4, dict(params), noise=mode)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            reps = 10
+            for _ in range(reps):
+                out = G.rgb2rawburst_batch(imgs, FRAMES, 4, dict(params), noise=mode)
+            torch.cuda.synchronize()
+            dt = (time.perf_counter() - t0) / (reps * 32)
+            emit({'leg': 'generator', 'op': f'rgb2rawburst_batch, 32 bursts per call, noise={mode!r}', 'ms_per_burst': dt * 1e3,
+                  'bursts_per_s': 1.0 / dt, 'timing': f'host wall clock over {reps} batches of 32', 'burst_shape': list(out[0].shape[1:])})
     if args.out:
         with open(args.out, 'w') as f:
             for d in lines:

@@ -84,6 +84,9 @@ PROTOTYPES = {
     'dbsr_unprocess_rgb': (_I, [_VP, _VP, _I, _I, _I, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_float), _I, _I, _VP]),
     'dbsr_mosaic_noise': (_I, [_VP, _VP, _VP, _I, _I, _I, _F, _F, _VP]),
     'dbsr_single2lrburst': (_I, [_VP, _I, _I, _VP, _VP, _I, _I, _I, _I, _VP, _VP, _VP]),
+    'dbsr_unprocess_rgb_batch': (_I, [_VP, _VP, _I, _I, _I, _VP, _I, _I, _VP]),
+    'dbsr_single2lrburst_batch': (_I, [_VP, _I, _I, _I, _VP, _VP, _I, _I, _I, _I, _VP, _VP, _VP]),
+    'dbsr_mosaic_noise_batch': (_I, [_VP, _VP, _VP, _I, _I, _I, _VP, _I, _VP]),
     'dbsr_mse_workspace_floats': (_I, [_I]),
     'dbsr_mse_per_image': (_I, [_VP, _VP, _VP, _I, _I, _I, _I, _I, _VP, _VP, _VP]),
 }

@@ -7,6 +7,8 @@
 // in the reference and stay out of scope.
 #include "common.cuh"
 
+#include <string.h>
+
 namespace dbsr {
 
 struct UnprocessParams {
@@ -15,11 +17,17 @@ struct UnprocessParams {
   int smoothstep, gamma;
 };
 
+// per_image (optional, device): [batch][12] = rgb2cam (9, row-major) + gains (3) of every image; else the launch-wide p.ccm / p.gains
 __global__ void __launch_bounds__(256) unprocess_kernel(const float* __restrict__ img, float* __restrict__ out, long long plane,
-                                                        long long total, const UnprocessParams p) {
+                                                        long long total, const UnprocessParams p, const float* __restrict__ per_image) {
   griddep_wait();
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const long long b = i / plane, px = i - b * plane;
+    float ccm[9], gains[3];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) ccm[k] = per_image ? __ldg(per_image + b * 12 + k) : p.ccm[k];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) gains[k] = per_image ? __ldg(per_image + b * 12 + 9 + k) : p.gains[k];
     const float* src = img + b * 3 * plane + px;
     float v[3];
 #pragma unroll
@@ -35,7 +43,7 @@ __global__ void __launch_bounds__(256) unprocess_kernel(const float* __restrict_
     float cam[3];
 #pragma unroll
     for (int c = 0; c < 3; ++c)                              // :96-107 (torch.mm, k ascending)
-      cam[c] = __fadd_rn(__fadd_rn(__fmul_rn(p.ccm[3 * c], v[0]), __fmul_rn(p.ccm[3 * c + 1], v[1])), __fmul_rn(p.ccm[3 * c + 2], v[2]));
+      cam[c] = __fadd_rn(__fadd_rn(__fmul_rn(ccm[3 * c], v[0]), __fmul_rn(ccm[3 * c + 1], v[1])), __fmul_rn(ccm[3 * c + 2], v[2]));
     // :121-136: gains masked near white so that saturated pixels are not dimmed
     const float gray = __fdiv_rn(__fadd_rn(__fadd_rn(cam[0], cam[1]), cam[2]), 3.0f);
     const float m0 = __fdiv_rn(fmaxf(__fsub_rn(gray, 0.9f), 0.0f), (float)(1.0 - 0.9));
@@ -43,7 +51,7 @@ __global__ void __launch_bounds__(256) unprocess_kernel(const float* __restrict_
     float* dst = out + b * 3 * plane + px;
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
-      const float g = p.gains[c];
+      const float g = gains[c];
       const float safe = fmaxf(__fadd_rn(mask, __fmul_rn(__fsub_rn(1.0f, mask), g)), g);
       dst[c * plane] = fminf(fmaxf(__fmul_rn(cam[c], safe), 0.0f), 1.0f);       // synthetic_burst_generation.py:79
     }
@@ -52,7 +60,9 @@ __global__ void __launch_bounds__(256) unprocess_kernel(const float* __restrict_
 
 // rgb [n, 3, h, w] -> raw [n, 4, h/2, w/2] = (R(0,0), G(0,1), G(1,0), B(1,1)) (+ z * sqrt(raw * shot + read)), clamped to [0, 1]
 __global__ void __launch_bounds__(256) mosaic_noise_kernel(const float* __restrict__ rgb, const float* __restrict__ z, float* __restrict__ raw,
-                                                           int h, int w, long long total, float shot, float read) {
+                                                           int h, int w, long long total, float shot, float read,
+                                                           const float* __restrict__ levels, int per) {
+  // levels (optional, device): [bursts][2] = (shot, read) noise level of every burst of `per` frames; else the launch-wide pair
   griddep_wait();
   const int h2 = h / 2, w2 = w / 2;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -65,6 +75,7 @@ __global__ void __launch_bounds__(256) mosaic_noise_kernel(const float* __restri
     const int src_c = ch == 0 ? 0 : (ch == 3 ? 2 : 1);
     const int sy = 2 * y + (ch >> 1), sx = 2 * x + (ch & 1);
     float v = __ldg(rgb + ((n * 3 + src_c) * h + sy) * (long long)w + sx);
+    if (levels) { shot = __ldg(levels + 2 * (n / per)); read = __ldg(levels + 2 * (n / per) + 1); }
     if (z) v = __fadd_rn(v, __fmul_rn(__ldg(z + i), sqrtf(__fadd_rn(__fmul_rn(v, shot), read))));    // camera_pipeline.py:178-183
     raw[i] = fminf(fmaxf(v, 0.0f), 1.0f);
   }
@@ -87,8 +98,19 @@ extern "C" int dbsr_unprocess_rgb(const float* image, float* out, int32_t batch,
   for (int i = 0; i < 3; ++i) p.gains[i] = gains3[i];
   p.smoothstep = smoothstep; p.gamma = gamma;
   const long long plane = (long long)h * w, total = plane * batch;
-  launch_pdl(unprocess_kernel, dim3(grid_for_cam(total)), dim3(256), 0, (cudaStream_t)stream, image, out, plane, total, p);
+  launch_pdl(unprocess_kernel, dim3(grid_for_cam(total)), dim3(256), 0, (cudaStream_t)stream, image, out, plane, total, p, (const float*)nullptr);
   return check_launch("unprocess_rgb");
+}
+
+extern "C" int dbsr_unprocess_rgb_batch(const float* image, float* out, int32_t batch, int32_t h, int32_t w, const float* params12,
+                                        int32_t smoothstep, int32_t gamma, void* stream) {
+  DBSR_REQUIRE(image && out && params12 && batch > 0 && h > 0 && w > 0, "unprocess_rgb_batch: bad arguments");
+  UnprocessParams p;
+  memset(&p, 0, sizeof(p));
+  p.smoothstep = smoothstep; p.gamma = gamma;
+  const long long plane = (long long)h * w, total = plane * batch;
+  launch_pdl(unprocess_kernel, dim3(grid_for_cam(total)), dim3(256), 0, (cudaStream_t)stream, image, out, plane, total, p, params12);
+  return check_launch("unprocess_rgb_batch");
 }
 
 extern "C" int dbsr_mosaic_noise(const float* rgb, const float* noise, float* raw, int32_t n, int32_t h, int32_t w, float shot_noise,
@@ -96,8 +118,18 @@ extern "C" int dbsr_mosaic_noise(const float* rgb, const float* noise, float* ra
   DBSR_REQUIRE(rgb && raw && n > 0 && h >= 2 && w >= 2 && h % 2 == 0 && w % 2 == 0, "mosaic_noise: needs even image sizes");
   const long long total = (long long)n * 4 * (h / 2) * (w / 2);
   launch_pdl(mosaic_noise_kernel, dim3(grid_for_cam(total)), dim3(256), 0, (cudaStream_t)stream, rgb, noise, raw, h, w, total, shot_noise,
-             read_noise);
+             read_noise, (const float*)nullptr, 1);
   return check_launch("mosaic_noise");
+}
+
+extern "C" int dbsr_mosaic_noise_batch(const float* rgb, const float* noise, float* raw, int32_t n, int32_t h, int32_t w,
+                                       const float* levels, int32_t frames_per_burst, void* stream) {
+  DBSR_REQUIRE(rgb && raw && levels && n > 0 && frames_per_burst > 0 && n % frames_per_burst == 0 && h >= 2 && w >= 2 && h % 2 == 0 &&
+                   w % 2 == 0, "mosaic_noise_batch: needs even image sizes and n = bursts * frames_per_burst");
+  const long long total = (long long)n * 4 * (h / 2) * (w / 2);
+  launch_pdl(mosaic_noise_kernel, dim3(grid_for_cam(total)), dim3(256), 0, (cudaStream_t)stream, rgb, noise, raw, h, w, total, 0.0f, 0.0f,
+             levels, (int)frames_per_burst);
+  return check_launch("mosaic_noise_batch");
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -118,6 +150,7 @@ struct LrBurstParams {
   float* burst;            // [n, 3, h, w]
   float* flow;             // [n, 2, h, w] or null
   int H, W, n, f, crop, h, w, normalize;
+  int per;                 // frames per source image: frame k warps image k / per, flows are relative to frame (k / per) * per
 };
 
 __device__ __forceinline__ int warped_u8x3(const LrBurstParams& p, const double* M, int x, int y, int out[3]) {
@@ -137,7 +170,7 @@ __device__ __forceinline__ int warped_u8x3(const LrBurstParams& p, const double*
   const long long plane = (long long)p.H * p.W;
 #pragma unroll
   for (int c = 0; c < 3; ++c) {
-    const float* im = p.image + c * plane;
+    const float* im = p.image + c * plane;      // p.image: this frame's source image (set by the caller)
     auto q = [&](bool ok, int yy, int xx) -> int {       // (image * 255).astype(uint8): fp32 product, truncation
       if (!ok) return 0;
       float v = __ldg(im + (long long)yy * p.W + xx);
@@ -159,12 +192,14 @@ __global__ void __launch_bounds__(256) lrburst_kernel(const LrBurstParams p) {
     const long long t = i / p.w;
     const int oy = (int)(t % p.h), frame = (int)(t / p.h);
     const double* M = p.inv + 6 * frame;
+    LrBurstParams q = p;
+    q.image = p.image + (long long)(frame / p.per) * 3 * p.H * p.W;
     const int bx = p.crop + p.f * ox + o, by = p.crop + p.f * oy + o;
     int s[3] = {0, 0, 0};
     for (int dy = 0; dy < k; ++dy)
       for (int dx = 0; dx < k; ++dx) {
         int v[3];
-        warped_u8x3(p, M, bx + dx, by + dy, v);
+        warped_u8x3(q, M, bx + dx, by + dy, v);
         s[0] += v[0]; s[1] += v[1]; s[2] += v[2];
       }
 #pragma unroll
@@ -180,7 +215,7 @@ __global__ void __launch_bounds__(256) lrburst_kernel(const LrBurstParams p) {
         float pos[2];
 #pragma unroll
         for (int which = 0; which < 2; ++which) {          // this frame, frame 0
-          const float* T = p.pos + 6 * (which == 0 ? frame : 0) + 3 * a;
+          const float* T = p.pos + 6 * (which == 0 ? frame : (frame / p.per) * p.per) + 3 * a;
           auto at = [&](int xx, int yy) { return __fadd_rn(__fadd_rn(__fmul_rn((float)xx, T[0]), __fmul_rn((float)yy, T[1])), T[2]); };
           float r;
           if (k == 2) {
@@ -213,7 +248,26 @@ extern "C" int dbsr_single2lrburst(const float* image, int32_t H, int32_t W, con
   LrBurstParams p;
   p.image = image; p.inv = inverse_maps; p.pos = position_maps; p.burst = burst; p.flow = flow;
   p.H = H; p.W = W; p.n = n; p.f = factor; p.crop = border_crop; p.h = hc / factor; p.w = wc / factor; p.normalize = normalize;
+  p.per = n;
   const long long total = (long long)n * p.h * p.w;
   launch_pdl(lrburst_kernel, dim3(grid_for_cam(total)), dim3(256), 0, (cudaStream_t)stream, p);
   return check_launch("single2lrburst");
+}
+
+extern "C" int dbsr_single2lrburst_batch(const float* images, int32_t batch, int32_t H, int32_t W, const double* inverse_maps,
+                                         const float* position_maps, int32_t frames_per_image, int32_t factor, int32_t border_crop,
+                                         int32_t normalize, float* burst, float* flow, void* stream) {
+  DBSR_REQUIRE(images && inverse_maps && burst && batch > 0 && H > 0 && W > 0 && frames_per_image > 0 && factor >= 1 && border_crop >= 0,
+               "single2lrburst_batch: bad arguments");
+  DBSR_REQUIRE(!flow || position_maps, "single2lrburst_batch: flow vectors need the fp32 position maps");
+  const int hc = H - 2 * border_crop, wc = W - 2 * border_crop;
+  DBSR_REQUIRE(hc > 0 && wc > 0 && hc % factor == 0 && wc % factor == 0,
+               "single2lrburst_batch: the cropped image (%d x %d) must be a multiple of the down-sampling factor %d", hc, wc, factor);
+  LrBurstParams p;
+  p.image = images; p.inv = inverse_maps; p.pos = position_maps; p.burst = burst; p.flow = flow;
+  p.H = H; p.W = W; p.n = batch * frames_per_image; p.f = factor; p.crop = border_crop; p.h = hc / factor; p.w = wc / factor;
+  p.normalize = normalize; p.per = frames_per_image;
+  const long long total = (long long)p.n * p.h * p.w;
+  launch_pdl(lrburst_kernel, dim3(grid_for_cam(total)), dim3(256), 0, (cudaStream_t)stream, p);
+  return check_launch("single2lrburst_batch");
 }

@@ -8,13 +8,16 @@ averaged over the images, :47-60,122) and changes the schedule: bursts are stack
 contiguous shard of the set (`sharding.shard_range`), the network writes the int16 form directly from the predictor
 epilogue (`net.output_int16`), the metrics come from the fused kernels without leaving the device, and the ranks exchange
 one all-reduce of `[sums | counts]` at the end (`sharding.reduce_metric_means`) -- the only host read is the final report.
-LPIPS (a pretrained AlexNet from the `lpips` package) is not on this path and is refused.  The on-disk dataset / experiment
-registry / PNG cache of the reference's driver are out of scope: `dataset` is any indexable of
+LPIPS (a pretrained AlexNet from the `lpips` package) is not on this path and is refused.  `saved_dir` reproduces the
+`load_saved` branch (:78-88, 100-104): when the directory holds one `<burst_name>.png` per burst (written by
+`save_results.save_results` here or by the reference's own script), the predictions are read from the files instead of
+running the network.  The on-disk dataset / experiment registry of the reference's driver are out of scope: `dataset` is any indexable of
 `(burst [N, 4, H, W], gt [3, 8H, 8W], meta_info)` items, the contract of `SyntheticBurstVal.__getitem__`
 (dataset/synthetic_burst_val_set.py:38-55)."""
 from __future__ import annotations
 
-from typing import Dict, Sequence
+import os
+from typing import Dict, Optional, Sequence
 
 import torch
 import torch.distributed as dist
@@ -76,11 +79,16 @@ def dequantize_q14(pred_q: torch.Tensor) -> torch.Tensor:
 
 @torch.no_grad()
 def score_dataset(net, dataset, metrics: Sequence[str] = ('psnr', 'ssim'), boundary_ignore: int = 40, batch_size: int = 32,
-                  device='cuda', burst_sz=None, shard: bool = True) -> Dict[str, float]:
-    """Mean per-image metrics of `net` over `dataset` (all ranks' shards), plus 'count'.  `net`: a `DBSRNet` of this package."""
+                  device='cuda', burst_sz=None, shard: bool = True, saved_dir: Optional[str] = None) -> Dict[str, float]:
+    """Mean per-image metrics of `net` over `dataset` (all ranks' shards), plus 'count' and 'using_saved_results'.
+    `net`: a `DBSRNet` of this package (may be None when `saved_dir` holds a complete set of saved predictions)."""
     for m in metrics:
         if m not in ('psnr', 'ssim'):
             raise NotImplementedError(f'metric {m!r} is not provided (psnr / ssim; lpips needs the `lpips` package)')
+    from .save_results import load_prediction, saved_results_complete
+    using_saved = saved_dir is not None and saved_results_complete(saved_dir, dataset)
+    if not using_saved and net is None:
+        raise ValueError('no network given and no complete set of saved results to read')
     # shard=False: this rank scores the whole set on its own (no collective), e.g. to cross-check a sharded run
     distributed = shard and dist.is_available() and dist.is_initialized()
     rank = dist.get_rank() if distributed else 0
@@ -89,21 +97,28 @@ def score_dataset(net, dataset, metrics: Sequence[str] = ('psnr', 'ssim'), bound
     device = torch.device(device)
     psnr_fn = PSNR(boundary_ignore=boundary_ignore)
     was_q = getattr(net, 'output_int16', False)
-    net.output_int16 = True
+    if not using_saved:
+        net.output_int16 = True
     per_image = []
     stage = _Stager()
     try:
         for start in range(lo, hi, batch_size):
             stop = min(start + batch_size, hi)
-            if hasattr(dataset, 'batch'):
+            if using_saved:
+                items = [dataset[i] for i in range(start, stop)]
+                gt = torch.stack([it[1] for it in items]).to(device).float().contiguous()
+                pred = torch.cat([load_prediction(os.path.join(saved_dir, it[2]['burst_name'] + '.png'), device) for it in items])
+                burst = None
+            elif hasattr(dataset, 'batch'):
                 burst, gt = (t.to(device, non_blocking=True) for t in dataset.batch(start, stop))
             else:
                 burst, gt = stage([dataset[i] for i in range(start, stop)], device)
-            gt = gt.float().contiguous()
-            if burst_sz is not None:
-                burst = burst[:, :burst_sz]
-            pred_q, _ = net(burst.float().contiguous())
-            pred = dequantize_q14(pred_q)
+            if not using_saved:
+                gt = gt.float().contiguous()
+                if burst_sz is not None:
+                    burst = burst[:, :burst_sz]
+                pred_q, _ = net(burst.float().contiguous())
+                pred = dequantize_q14(pred_q)
             cols = []
             for m in metrics:
                 if m == 'psnr':
@@ -112,11 +127,13 @@ def score_dataset(net, dataset, metrics: Sequence[str] = ('psnr', 'ssim'), bound
                     cols.append(msssim._stats(pred, gt, 11, None, None, crop=boundary_ignore or 0, fixed_window=True)[0][:, 0])
             per_image.append(torch.stack(cols, dim=1))
     finally:
-        net.output_int16 = was_q
+        if not using_saved:
+            net.output_int16 = was_q
     local = torch.cat(per_image) if per_image else torch.zeros(0, len(metrics), device=device)
     mean = sharding.reduce_metric_means(local, collective=distributed)
     out = {m: float(v) for m, v in zip(metrics, mean.cpu())}
     out['count'] = len(dataset)
+    out['using_saved_results'] = bool(using_saved)
     return out
 
 

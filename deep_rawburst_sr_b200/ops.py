@@ -445,3 +445,51 @@ def single2lrburst(image: torch.Tensor, inverse_maps: torch.Tensor, position_map
                                                        1 if normalize else 0, burst.data_ptr(), _ptr(flow), _stream()),
                'dbsr_single2lrburst')
     return burst, flow
+
+
+# ---- batched generator kernels: per-burst parameters live in device memory (one upload per batch) --------------------------------
+def unprocess_rgb_batch(images: torch.Tensor, params12: torch.Tensor, smoothstep: bool = True, gamma: bool = True) -> torch.Tensor:
+    """images [b, 3, h, w]; params12 [b, 12] device fp32 = rgb2cam (row-major) + [1 / red, 1, 1 / blue] / rgb_gain per image"""
+    require_device(images)
+    assert images.dtype == torch.float32 and images.dim() == 4 and images.shape[1] == 3
+    x = images.contiguous()
+    assert params12.is_cuda and params12.dtype == torch.float32 and tuple(params12.shape) == (x.shape[0], 12) and params12.is_contiguous()
+    out = torch.empty_like(x)
+    _lib.check(_lib.load_library().dbsr_unprocess_rgb_batch(x.data_ptr(), out.data_ptr(), x.shape[0], x.shape[2], x.shape[3],
+                                                            params12.data_ptr(), 1 if smoothstep else 0, 1 if gamma else 0, _stream()),
+               'dbsr_unprocess_rgb_batch')
+    return out
+
+
+def single2lrburst_batch(images: torch.Tensor, inverse_maps: torch.Tensor, position_maps: torch.Tensor, frames: int, factor: int,
+                         border_crop: int = 0, normalize: bool = True, want_flow: bool = True):
+    """images [b, 3, H, W] -> (burst [b * frames, 3, h, w], flow [b * frames, 2, h, w] or None); maps: DEVICE [b * frames, 6]"""
+    require_device(images)
+    assert images.dtype == torch.float32 and images.dim() == 4 and images.shape[1] == 3
+    x = images.contiguous()
+    b, _, H, W = x.shape
+    assert inverse_maps.is_cuda and inverse_maps.dtype == torch.float64 and tuple(inverse_maps.shape) == (b * frames, 6)
+    assert position_maps.is_cuda and position_maps.dtype == torch.float32 and tuple(position_maps.shape) == (b * frames, 6)
+    hc, wc = H - 2 * border_crop, W - 2 * border_crop
+    if hc <= 0 or wc <= 0 or hc % factor or wc % factor:
+        raise ValueError(f'single2lrburst: cropped size {hc}x{wc} must be a positive multiple of the down-sampling factor {factor}')
+    burst = torch.empty(b * frames, 3, hc // factor, wc // factor, dtype=torch.float32, device=x.device)
+    flow = torch.empty(b * frames, 2, hc // factor, wc // factor, dtype=torch.float32, device=x.device) if want_flow else None
+    _lib.check(_lib.load_library().dbsr_single2lrburst_batch(x.data_ptr(), b, H, W, inverse_maps.contiguous().data_ptr(),
+                                                             position_maps.contiguous().data_ptr(), frames, factor, border_crop,
+                                                             1 if normalize else 0, burst.data_ptr(), _ptr(flow), _stream()),
+               'dbsr_single2lrburst_batch')
+    return burst, flow
+
+
+def mosaic_noise_batch(rgb: torch.Tensor, levels: torch.Tensor, frames_per_burst: int, noise: torch.Tensor) -> torch.Tensor:
+    """rgb [n, 3, h, w] -> noisy RGGB [n, 4, h/2, w/2]; levels [n / frames_per_burst, 2] device fp32 = (shot, read) per burst"""
+    require_device(rgb)
+    x = rgb.contiguous()
+    n, _, h, w = x.shape
+    raw = torch.empty(n, 4, h // 2, w // 2, dtype=torch.float32, device=x.device)
+    assert levels.is_cuda and levels.dtype == torch.float32 and tuple(levels.shape) == (n // frames_per_burst, 2) and levels.is_contiguous()
+    assert noise.is_cuda and noise.dtype == torch.float32 and tuple(noise.shape) == tuple(raw.shape) and noise.is_contiguous()
+    _lib.check(_lib.load_library().dbsr_mosaic_noise_batch(x.data_ptr(), noise.data_ptr(), raw.data_ptr(), n, h, w, levels.data_ptr(),
+                                                           frames_per_burst, _stream()), 'dbsr_mosaic_noise_batch')
+    return raw

@@ -286,6 +286,20 @@ int dbsr_mosaic_noise(const float* rgb, const float* noise, float* raw, int32_t 
 int dbsr_single2lrburst(const float* image, int32_t H, int32_t W, const double* inverse_maps, const float* position_maps,
                         int32_t n, int32_t factor, int32_t border_crop, int32_t normalize, float* burst, float* flow, void* stream);
 
+/* Batched forms of the three generator kernels (one launch for `batch` bursts with their OWN random parameters, all in device
+ * memory, so that a generator front end samples the parameters of many bursts on the host and uploads them once):
+ *   params12: fp32 [batch][12] = rgb2cam (9, row-major) + gains (3) per image;
+ *   images [batch, 3, H, W]; inverse_maps [batch * frames_per_image][6] / position_maps likewise: frame k warps image
+ *   k / frames_per_image and its flow is relative to the first frame of that image; burst [batch * frames_per_image, 3, h, w];
+ *   levels: fp32 [n / frames_per_burst][2] = (shot, read) noise level per burst.  Same arithmetic as the single forms.     */
+int dbsr_unprocess_rgb_batch(const float* image, float* out, int32_t batch, int32_t h, int32_t w, const float* params12,
+                             int32_t smoothstep, int32_t gamma, void* stream);
+int dbsr_single2lrburst_batch(const float* images, int32_t batch, int32_t H, int32_t W, const double* inverse_maps,
+                              const float* position_maps, int32_t frames_per_image, int32_t factor, int32_t border_crop,
+                              int32_t normalize, float* burst, float* flow, void* stream);
+int dbsr_mosaic_noise_batch(const float* rgb, const float* noise, float* raw, int32_t n, int32_t h, int32_t w, const float* levels,
+                            int32_t frames_per_burst, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -119,3 +119,32 @@ def test_rgb2rawburst_end_to_end(dev):
     z = torch.FloatTensor(14, 4, 48, 48).normal_()
     d = (raw.cpu() - C.mosaic_add_noise(ref_rgb, shot, read, z)).abs()
     assert float(d.max()) <= 1.2e-7
+
+
+def test_rgb2rawburst_batch_equals_per_burst_calls(dev):
+    """rgb2rawburst_batch (one launch per kernel for the whole batch, parameters sampled for all bursts up front and uploaded
+    once) under the same `random` / torch seeds == `rgb2rawburst` called burst after burst (the reference's schedule,
+    data/synthetic_burst_generation.py:23-103): every output bit for bit with noise='host'; with noise='device' everything
+    but the noise realisation is identical and the noisy burst has the same statistics."""
+    import random
+    from deep_rawburst_sr_b200.data import synthetic_burst_generation as G
+    g = torch.Generator().manual_seed(2)
+    images = torch.rand(3, 3, 240, 208, generator=g).to(dev)
+    tp = {'max_translation': 24.0, 'max_rotation': 1.0, 'max_shear': 0.0, 'max_scale': 0.0, 'border_crop': 24}
+    random.seed(77); torch.manual_seed(77)
+    per = [G.rgb2rawburst(images[i], 5, 4, dict(tp), None) for i in range(3)]
+    random.seed(77); torch.manual_seed(77)
+    raw, lin, rgb, flow, metas = G.rgb2rawburst_batch(images, 5, 4, dict(tp), None, noise='host')
+    assert tuple(raw.shape) == (3, 5, 4, 24, 20) and tuple(rgb.shape) == (3, 5, 3, 48, 40) and tuple(flow.shape) == (3, 5, 2, 48, 40)
+    for i, (p_raw, p_lin, p_rgb, p_flow, p_meta) in enumerate(per):
+        assert torch.equal(lin[i], p_lin) and torch.equal(rgb[i], p_rgb) and torch.equal(flow[i], p_flow), i
+        assert torch.equal(raw[i], p_raw), i
+        assert torch.equal(metas[i]['rgb2cam'], p_meta['rgb2cam']) and metas[i]['shot_noise_level'] == p_meta['shot_noise_level']
+        assert metas[i]['red_gain'] == p_meta['red_gain'] and metas[i]['read_noise_level'] == p_meta['read_noise_level']
+    # device-side noise: the host stream no longer contains the normal_ draws, so only burst 0 shares its parameters
+    random.seed(77); torch.manual_seed(77)
+    raw_d, lin_d, rgb_d, flow_d, _ = G.rgb2rawburst_batch(images, 5, 4, dict(tp), None, noise='device')
+    assert torch.equal(lin_d[0], lin[0]) and torch.equal(rgb_d[0], rgb[0]) and torch.equal(flow_d, flow)
+    assert float(raw_d.min()) >= 0.0 and float(raw_d.max()) <= 1.0 and abs(float(raw_d[0].mean()) - float(raw[0].mean())) < 5e-3
+    with pytest.raises(NotImplementedError):
+        G.rgb2rawburst_batch(images.cpu(), 5, 4, dict(tp), None)

@@ -2,6 +2,8 @@
 against the same protocol walked image by image on the CPU oracle: forward -> 14-bit quantisation -> PSNR / SSIM with
 boundary_ignore -> mean over the set.  fp32 path: PSNR within 1e-3 dB, SSIM within 1e-5 (a prediction within 1.5e-7 of the
 oracle's can flip single 14-bit codes); bf16 tensor-core path: PSNR within 0.02 dB (north_star), SSIM within 1e-3."""
+import os
+
 import pytest
 import torch
 
@@ -107,3 +109,33 @@ def test_burstsr_score_dataset_matches_batch1_loop(dev):
         assert got['count'] == n and not net.output_int16
         assert abs(got['psnr'] - sum(ps) / n) <= 1e-3, (got, ps)
         assert abs(got['ssim'] - sum(ss) / n) <= 1e-5, (got, ss)
+
+
+def test_save_results_and_score_from_saved_pngs(dev, tmp_path):
+    """save_results.py:52-68 + compute_score.py:78-104: the batched writer stores, per burst, the PNG the reference's batch-1
+    loop would store (pixel for pixel: the int16 epilogue IS (pred.clamp(0, 1) * 2 ** 14)), and scoring from the saved files
+    (`using_saved_results`) gives the same report as scoring the network directly."""
+    import numpy as np
+    from deep_rawburst_sr_b200.evaluation.synburst.compute_score import TensorBurstSet, score_dataset
+    from deep_rawburst_sr_b200.evaluation.synburst.save_results import read_png16, save_results
+    from deep_rawburst_sr_b200.models.dbsr.dbsrnet import dbsrnet_default_synthetic
+    from oracle import dbsr_oracle as O
+    sd = O.make_state_dict(0, dbsr_gain=1.5)
+    net = dbsrnet_default_synthetic()
+    net.load_state_dict(sd, strict=True)
+    net = net.to(dev).eval().set_precision('bf16')
+    g = torch.Generator().manual_seed(11)
+    data = TensorBurstSet(torch.rand(5, 4, 4, 24, 24, generator=g), torch.rand(5, 3, 192, 192, generator=g))
+    out_dir = str(tmp_path / 'synburst' / 'net0')
+    for graph in (False, True):
+        net.use_cuda_graph = graph
+        assert save_results(net, data, out_dir, batch_size=2, device=dev) == 5
+        for i in range(5):
+            pred, _ = net(data.bursts[i:i + 1].to(dev))
+            want = (pred.squeeze(0).permute(1, 2, 0).clamp(0.0, 1.0) * 2 ** 14).cpu().numpy().astype(np.uint16)
+            assert np.array_equal(read_png16(os.path.join(out_dir, '{:04d}.png'.format(i))), want), (graph, i)
+    net.use_cuda_graph = False
+    live = score_dataset(net, data, batch_size=2, device=dev, boundary_ignore=8)
+    saved = score_dataset(None, data, batch_size=2, device=dev, boundary_ignore=8, saved_dir=out_dir)
+    assert saved['using_saved_results'] and not live['using_saved_results']
+    assert abs(saved['psnr'] - live['psnr']) < 1e-5 and abs(saved['ssim'] - live['ssim']) < 1e-6

@@ -1,5 +1,6 @@
 """CPU: host-side logic of the package -- interface / state_dict contract of the drop-in modules, weight packing
 (checked numerically against torch convs of the original weights), unsupported-flag and CPU-input behaviour."""
+import os
 import pytest
 import torch
 import torch.nn.functional as F
@@ -163,3 +164,71 @@ def test_scoring_loops_refuse_unknown_metrics_and_format_like_the_reference():
     assert len(data) == 3 and burst.shape == (2, 4, 8, 8) and gt.shape == (3, 64, 64) and meta['burst_name'] == '0001'
     b, g = data.batch(1, 3)
     assert b.shape[0] == 2 and g.shape[0] == 2
+
+
+def test_png16_codec_matches_the_reference_writer(tmp_path, golden_dir):
+    """save_results.py:65-68 / compute_score.py:100-104: 16-bit BGR-ordered PNGs.  (a) a file written by the reference's own
+    call (`cv2.imwrite`, committed by oracle/make_golden_png.py) decodes to the array that was written; (b) write -> read is
+    the identity; (c) every PNG filter type decodes (OpenCV picks them adaptively); (d) the saved-results criterion and the
+    float form `value / 2 ** 14` of the `using_saved_results` branch."""
+    import struct
+    import zlib
+    import numpy as np
+    from oracle.make_golden_png import golden_image
+    from deep_rawburst_sr_b200.evaluation.synburst import save_results as SR
+    img = golden_image()
+    assert np.array_equal(SR.read_png16(os.path.join(golden_dir, 'pred_u16_cv2.png')), img)
+    p = str(tmp_path / '0000.png')
+    SR.write_png16(p, img)
+    assert np.array_equal(SR.read_png16(p), img)
+    with pytest.raises(ValueError):
+        SR.write_png16(p, img.astype(np.uint8))
+    # hand-encode the same image once per filter type (encoder side of the PNG spec, section 9)
+    h, w, _ = img.shape
+    rgb = np.ascontiguousarray(img[:, :, ::-1]).astype('>u2').view(np.uint8).reshape(h, w * 6).astype(np.int32)
+    left = np.zeros_like(rgb); left[:, 6:] = rgb[:, :-6]
+    up = np.zeros_like(rgb); up[1:] = rgb[:-1]
+    ul = np.zeros_like(rgb); ul[1:, 6:] = rgb[:-1, :-6]
+    pa, pb, pc = np.abs(up - ul), np.abs(left - ul), np.abs(left + up - 2 * ul)
+    paeth = np.where((pa <= pb) & (pa <= pc), left, np.where(pb <= pc, up, ul))
+    for ft, pred in ((0, 0), (1, left), (2, up), (3, (left + up) >> 1), (4, paeth)):
+        rows = np.concatenate([np.full((h, 1), ft, np.uint8), ((rgb - pred) & 255).astype(np.uint8)], axis=1)
+        blob = SR._PNG_SIG + SR._chunk(b'IHDR', struct.pack('>IIBBBBB', w, h, 16, 2, 0, 0, 0)) + \
+            SR._chunk(b'IDAT', zlib.compress(rows.tobytes())) + SR._chunk(b'IEND', b'')
+        q = str(tmp_path / f'f{ft}.png')
+        open(q, 'wb').write(blob)
+        assert np.array_equal(SR.read_png16(q), img), ft
+    t = SR.load_prediction(p)
+    assert tuple(t.shape) == (1, 3, h, w) and t.dtype == torch.float32
+    assert torch.equal(t[0], torch.from_numpy(img.astype(np.float32) / 2 ** 14).permute(2, 0, 1))
+    q14 = torch.from_numpy(img.astype(np.int16)).permute(2, 0, 1).contiguous()
+    assert np.array_equal(SR.prediction_to_array(q14), img)
+    only = tmp_path / 'only'
+    only.mkdir()
+    SR.write_png16(str(only / '0000.png'), img)
+    assert SR.saved_results_complete(str(only), [0]) and not SR.saved_results_complete(str(only), [0, 1])
+
+
+def test_batched_transform_sampling_is_bit_identical_to_the_per_burst_path():
+    """rgb2rawburst_batch's host front end: the same `random` stream gives the same transform parameters, and the stacked
+    matrix products / inversions equal the per-frame functions bit for bit"""
+    import random
+    import numpy as np
+    from deep_rawburst_sr_b200.data import synthetic_burst_generation as G
+    tp = {'max_translation': 24.0, 'max_rotation': 1.0, 'max_shear': 0.02, 'max_scale': 0.05, 'max_ar_factor': 0.03, 'border_crop': 24}
+    random.seed(123)
+    per = [G.sample_transforms((432, 400), 14, 4, tp) for _ in range(3)]
+    random.seed(123)
+    params = []
+    for _ in range(3):
+        params += G.sample_transform_params(14, 4, tp)
+    bat = G.get_tmat_batch((432, 400), params)
+    flat = np.stack([m for burst in per for m in burst])
+    assert bat.shape == (42, 2, 3) and np.array_equal(bat, flat)
+    assert np.array_equal(G._inverse_map_batch(bat), np.stack([G._inverse_map(m) for m in flat]))
+    # identity case (max_translation <= 0.01 -> fixed shift) draws the same number of values
+    random.seed(5)
+    a = G.sample_transforms((64, 64), 3, 2, {'max_rotation': 2.0})
+    random.seed(5)
+    b = G.get_tmat_batch((64, 64), G.sample_transform_params(3, 2, {'max_rotation': 2.0}))
+    assert np.array_equal(np.stack(a), b)

@@ -118,6 +118,102 @@ __global__ void __launch_bounds__(128, 1) rate_kernel(int N, int iters, long lon
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------
+// cta_group::2: a CTA pair (cluster of 2) executes ONE MMA of M = 256: each CTA supplies its own 128 A rows and HALF of the
+// B rows (N / 2) from its own shared memory, the leader CTA's thread issues.  Per SM and MMA the operand fetch is
+// 4096 + 16 N bytes instead of 4096 + 32 N.
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_rank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void umma2(uint32_t d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+               ::"r"(d), "l"(a), "l"(b), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void commit2(uint64_t* bar) {      // arrives on the barrier at this offset in BOTH CTAs
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1) rate2_kernel(int N, int iters, long long* out) {
+  extern __shared__ __align__(1024) uint8_t raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* sa = smem;
+  uint8_t* sb = smem + 65536;
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tslot;
+  for (int i = threadIdx.x; i < 131072 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u + i;
+  const int warp = threadIdx.x >> 5;
+  const uint32_t rank = cluster_rank();
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar)));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&tslot)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  cluster_sync_all();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tbase = tslot;
+  if (warp == 1 && rank == 0) {
+    if (elect_one()) {
+      // M = 256 (field M >> 4 = 16), N columns
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((256u >> 4) << 24);
+      const uint32_t hi = ((1024u >> 4) & 0x3FFFu) | (1u << 14) | (2u << 29);
+      const uint32_t a_lo = ((smem_u32(sa) >> 4) & 0x3FFFu) | 0x10000u;
+      const uint32_t b_lo = ((smem_u32(sb) >> 4) & 0x3FFFu) | 0x10000u;
+      const long long t0 = clock64();
+      for (int i = 0; i < iters; i += 8) {
+        const uint32_t tap = (uint32_t)(i >> 3) % 9u;
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          umma2(tbase + (uint32_t)((j >> 2) * N), ((uint64_t)hi << 32) | (a_lo + tap * 8u + (j >> 2) * 64u + 2u * (j & 3)),
+                ((uint64_t)hi << 32) | (b_lo + tap * 128u + 2u * (j & 3)), idesc, 1u);
+      }
+      const long long t1 = clock64();
+      commit2(&bar);
+      while (!try_wait(&bar, 0)) {}
+      const long long t2 = clock64();
+      out[(blockIdx.x >> 1) * 2] = t1 - t0;
+      out[(blockIdx.x >> 1) * 2 + 1] = t2 - t0;
+    }
+  } else if (warp == 1 && rank == 1) {
+    while (!try_wait(&bar, 0)) {}        // the multicast commit also completes the peer's barrier
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 0) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, 512;" ::"r"(tbase) : "memory");
+  }
+}
+
+static void run2(int N, int grid, int iters) {
+  long long* d;
+  cudaMalloc(&d, grid * sizeof(long long));
+  const int smem = 131072 + 1024;
+  cudaFuncSetAttribute(rate2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  for (int rep = 0; rep < 2; ++rep) rate2_kernel<<<grid, 128, smem>>>(N, iters, d);
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) { printf("cta_group::2 N %d: %s\n", N, cudaGetErrorString(e)); exit(1); }
+  const int pairs = grid / 2;
+  long long* h = new long long[pairs * 2];
+  cudaMemcpy(h, d, pairs * 2 * sizeof(long long), cudaMemcpyDeviceToHost);
+  double issue = 0, total = 0;
+  for (int i = 0; i < pairs; ++i) { issue += h[2 * i]; total += h[2 * i + 1]; }
+  printf("cta_group::2 M=256 N=%3d grid=%3d : issue %.1f clk/MMA   complete %.1f clk/MMA   (math floor %d, operand bytes/SM %d -> %d clk)\n",
+         N, grid, issue / pairs / iters, total / pairs / iters, N / 2, 4096 + 16 * N, (4096 + 16 * N) / 128);
+  delete[] h; cudaFree(d);
+}
+
 template <int MODE>
 static void run(int N, int grid, int iters) {
   long long* d;
@@ -136,8 +232,12 @@ static void run(int N, int grid, int iters) {
   delete[] h; cudaFree(d);
 }
 
-int main() {
+int main(int argc, char** argv) {
   const int iters = 4096;
+  if (argc > 1 && argv[1][0] == '2') {          // `mma_rate.bin 2`: only the cta_group::2 table
+    for (int g : {2, 148}) for (int N : {32, 64, 128, 256}) run2(N, g, iters);
+    return 0;
+  }
   const int Ns[5] = {32, 64, 128, 192, 256};
   for (int g : {1, 148}) {
     for (int N : Ns) run<0>(N, g, iters);
