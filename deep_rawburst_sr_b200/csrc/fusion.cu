@@ -395,6 +395,41 @@ __device__ __forceinline__ Vec8 unpack_bf16x8(const uint4& q) {
   return r;
 }
 
+// Packed fp32 pairs (Blackwell FFMA2: fma / mul / add .f32x2 operate on two IEEE fp32 values per instruction -- the same
+// results as two scalar instructions, half the issue slots).  lo = element 2j, hi = element 2j + 1 of a Vec8.
+typedef unsigned long long f32x2_t;
+__device__ __forceinline__ f32x2_t f2_pack(float lo, float hi) {
+  f32x2_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void f2_unpack(f32x2_t v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ f32x2_t f2_fma(f32x2_t a, f32x2_t b, f32x2_t c) {
+  f32x2_t r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ f32x2_t f2_mul(f32x2_t a, f32x2_t b) {
+  f32x2_t r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ f32x2_t f2_add(f32x2_t a, f32x2_t b) {
+  f32x2_t r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+struct Vec8p { f32x2_t p[4]; };
+// 8 bf16 -> 4 packed fp32 pairs (a bf16 is the high half of its fp32)
+__device__ __forceinline__ Vec8p unpack_bf16x8_p(const uint4& q) {
+  Vec8p r;
+  r.p[0] = f2_pack(__uint_as_float(q.x << 16), __uint_as_float(q.x & 0xFFFF0000u));
+  r.p[1] = f2_pack(__uint_as_float(q.y << 16), __uint_as_float(q.y & 0xFFFF0000u));
+  r.p[2] = f2_pack(__uint_as_float(q.z << 16), __uint_as_float(q.z & 0xFFFF0000u));
+  r.p[3] = f2_pack(__uint_as_float(q.w << 16), __uint_as_float(q.w & 0xFFFF0000u));
+  return r;
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // Asynchronously prefetched, pair-pipelined kernel (bf16 embeddings and logits, warp on the fly).
 // History (profiles/): the register-resident kernel above is latency bound (6 warps per scheduler, each waiting on 5
@@ -568,21 +603,23 @@ softmax_wsum8_pair_kernel(const __grid_constant__ CUtensorMap tmap_feat, const _
   issue_pair(1);
   // reference frame (never warped).  The running maximum m is kept in log2 units.
   constexpr float LOG2E = 1.4426950408889634f;
-  float m[8], s[8], acc[8];
+  // the online-softmax state of the thread's 8 channels as 4 packed fp32 pairs (FFMA2: half the fp32 issue slots)
+  const f32x2_t LOG2E2 = f2_pack(LOG2E, LOG2E), NEG1 = f2_pack(-1.0f, -1.0f);
+  f32x2_t m[4], s[4], acc[4];
   {
-    Vec8 l, a;
+    Vec8p l, a;
     if (TMA_REF) {
       bar_wait(bar_s + 16u, 0u);
       uint4 qa, ql;
       asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(qa.x), "=r"(qa.y), "=r"(qa.z), "=r"(qa.w) : "r"(ref_s + (uint32_t)lane * 16u));
       asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(ql.x), "=r"(ql.y), "=r"(ql.z), "=r"(ql.w) : "r"(ref_s + 512u + (uint32_t)lane * 16u));
-      a = unpack_bf16x8(qa); l = unpack_bf16x8(ql);
+      a = unpack_bf16x8_p(qa); l = unpack_bf16x8_p(ql);
     } else {
-      l = ld8<__nv_bfloat16>(reinterpret_cast<const __nv_bfloat16*>(l0));
-      a = ld8<__nv_bfloat16>(reinterpret_cast<const __nv_bfloat16*>(f0 + (size_t)rem * feat.c_pitch * 2));
+      l = unpack_bf16x8_p(__ldg(reinterpret_cast<const uint4*>(l0)));
+      a = unpack_bf16x8_p(__ldg(reinterpret_cast<const uint4*>(f0 + (size_t)rem * feat.c_pitch * 2)));
     }
 #pragma unroll
-    for (int k = 0; k < 8; ++k) { m[k] = l.v[k] * LOG2E; s[k] = 1.0f; acc[k] = a.v[k]; }
+    for (int k = 0; k < 4; ++k) { m[k] = f2_mul(l.p[k], LOG2E2); s[k] = f2_pack(1.0f, 1.0f); acc[k] = a.p[k]; }
   }
   const int npairs = (others + 1) >> 1;
   for (int pp = 0; pp < npairs; ++pp) {
@@ -591,56 +628,66 @@ softmax_wsum8_pair_kernel(const __grid_constant__ CUtensorMap tmap_feat, const _
     const uint4* st = ring + stg * (2 * TAPS * 256) + tid;
     const int n0 = 2 * pp;                     // index of the pair's first frame among the others
     const bool has2 = n0 + 1 < others;
-    Vec8 lA, lB, aA, aB;
-    auto interp = [&](const uint4* sf, const WsRec& rc, Vec8& a) {      // sf: the frame's first TAP slot of this thread
+    Vec8p lA, lB, aA, aB;
+    auto interp = [&](const uint4* sf, const WsRec& rc, Vec8p& a) {      // sf: the frame's first TAP slot of this thread
       const float4 w = *reinterpret_cast<const float4*>(rc.w);
-      const Vec8 t0 = unpack_bf16x8(sf[0]), t1 = unpack_bf16x8(sf[256]);
+      const f32x2_t w0 = f2_pack(w.x, w.x), w1 = f2_pack(w.y, w.y), w2 = f2_pack(w.z, w.z), w3 = f2_pack(w.w, w.w);
+      const Vec8p t0 = unpack_bf16x8_p(sf[0]), t1 = unpack_bf16x8_p(sf[256]);
 #pragma unroll
-      for (int k = 0; k < 8; ++k) a.v[k] = fmaf(t1.v[k], w.y, t0.v[k] * w.x);
-      const Vec8 t2 = unpack_bf16x8(sf[512]), t3 = unpack_bf16x8(sf[768]);
+      for (int k = 0; k < 4; ++k) a.p[k] = f2_fma(t1.p[k], w1, f2_mul(t0.p[k], w0));
+      const Vec8p t2 = unpack_bf16x8_p(sf[512]), t3 = unpack_bf16x8_p(sf[768]);
 #pragma unroll
-      for (int k = 0; k < 8; ++k) a.v[k] = fmaf(t3.v[k], w.w, fmaf(t2.v[k], w.z, a.v[k]));
+      for (int k = 0; k < 4; ++k) a.p[k] = f2_fma(t3.p[k], w3, f2_fma(t2.p[k], w2, a.p[k]));
     };
     constexpr int T0 = TMA ? 0 : 256;          // first tap slot behind the logit slot of the cp.async-only ring
     if (TMA) {
       bar_wait(bar_s + (uint32_t)stg * 8u, (uint32_t)(pp >> 1) & 1u);
       uint4 q;
       asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(q.x), "=r"(q.y), "=r"(q.z), "=r"(q.w) : "r"(lg_s + (uint32_t)stg * 1024u + (uint32_t)lane * 16u));
-      lA = unpack_bf16x8(q);
+      lA = unpack_bf16x8_p(q);
     } else {
-      lA = unpack_bf16x8(st[0]);
+      lA = unpack_bf16x8_p(st[0]);
     }
     interp(st + T0, rec_s[pix][n0], aA);
     if (has2) {
       if (TMA) {
         uint4 q;
         asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(q.x), "=r"(q.y), "=r"(q.z), "=r"(q.w) : "r"(lg_s + (uint32_t)stg * 1024u + 512u + (uint32_t)lane * 16u));
-        lB = unpack_bf16x8(q);
+        lB = unpack_bf16x8_p(q);
       } else {
-        lB = unpack_bf16x8(st[TAPS * 256]);
+        lB = unpack_bf16x8_p(st[TAPS * 256]);
       }
       interp(st + TAPS * 256 + T0, rec_s[pix][n0 + 1], aB);
     } else {
 #pragma unroll
-      for (int k = 0; k < 8; ++k) { lB.v[k] = -INFINITY; aB.v[k] = 0.0f; }
+      for (int k = 0; k < 4; ++k) { lB.p[k] = f2_pack(-INFINITY, -INFINITY); aB.p[k] = f2_pack(0.0f, 0.0f); }
     }
     // this stage's slots are consumed (values are in registers): refill it with the pair after next
     if (TMA) __syncwarp();
     issue_pair(stg);
     // online softmax, one rescale per pair: 3 exponentials per 2 frames and element
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      const float la = lA.v[k] * LOG2E, lb = lB.v[k] * LOG2E;
-      const float mn = fmaxf(m[k], fmaxf(la, lb));
-      const float sc = ex2f(m[k] - mn), ea = ex2f(la - mn), eb = ex2f(lb - mn);
-      s[k] = fmaf(s[k], sc, ea + eb);
-      acc[k] = fmaf(acc[k], sc, fmaf(aA.v[k], ea, aB.v[k] * eb));
+    for (int k = 0; k < 4; ++k) {
+      const f32x2_t la = f2_mul(lA.p[k], LOG2E2), lb = f2_mul(lB.p[k], LOG2E2);
+      float m0, m1, a0, a1, b0, b1;
+      f2_unpack(m[k], m0, m1); f2_unpack(la, a0, a1); f2_unpack(lb, b0, b1);
+      const f32x2_t mn = f2_pack(fmaxf(m0, fmaxf(a0, b0)), fmaxf(m1, fmaxf(a1, b1)));
+      // x - mn as fma(mn, -1, x): the product is exact, so this is the scalar subtraction bit for bit
+      float d0, d1, e0, e1, g0, g1;
+      f2_unpack(f2_fma(mn, NEG1, m[k]), d0, d1); f2_unpack(f2_fma(mn, NEG1, la), e0, e1); f2_unpack(f2_fma(mn, NEG1, lb), g0, g1);
+      const f32x2_t sc = f2_pack(ex2f(d0), ex2f(d1)), ea = f2_pack(ex2f(e0), ex2f(e1)), eb = f2_pack(ex2f(g0), ex2f(g1));
+      s[k] = f2_fma(s[k], sc, f2_add(ea, eb));
+      acc[k] = f2_fma(acc[k], sc, f2_fma(aA.p[k], ea, f2_mul(aB.p[k], eb)));
       m[k] = mn;
     }
   }
   Vec8 r;
 #pragma unroll
-  for (int k = 0; k < 8; ++k) r.v[k] = __fdividef(acc[k], s[k]);
+  for (int k = 0; k < 4; ++k) {
+    float a0, a1, s0, s1;
+    f2_unpack(acc[k], a0, a1); f2_unpack(s[k], s0, s1);
+    r.v[2 * k] = __fdividef(a0, s0); r.v[2 * k + 1] = __fdividef(a1, s1);
+  }
   if (live) st8<TO>(obase + ((long long)b * HW + rem) * fused.c_pitch + ch, r);
 }
 

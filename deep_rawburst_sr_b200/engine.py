@@ -16,6 +16,7 @@ from __future__ import annotations
 
 import ctypes
 import math
+import os
 from typing import Dict, Optional
 
 import torch
@@ -185,6 +186,8 @@ class DBSREngine:
         # short PWC-Net launches is worth another 1-1.5 % per step on B200 (148 SMs -> 124; measured 9.39 -> 9.25 ms)
         sms = torch.cuda.get_device_properties(self.device).multi_processor_count
         self.encoder_grid_limit = sms - 24 if sms >= 96 else 0
+        if os.environ.get('DBSR_ENC_GRID_LIMIT'):          # tuning aid: A/B other splits of the SMs between the two streams
+            self.encoder_grid_limit = int(os.environ['DBSR_ENC_GRID_LIMIT'])
         self.launches = 0
         self.layer_events = None   # when a dict (and timers is on): conv layer key -> [(events, flops, family, shape)]
         self.timers = None   # when a dict: family -> list of (start, end) CUDA events on the launching stream
