@@ -86,6 +86,9 @@ struct ConvTcParams {
   // item to a kernel whose bottleneck is the shared-memory data pipe and was 100 us slower per launch.
   int tma_store;        // lean epilogue: the staged 32-pixel x GW-channel block of a warp leaves as ONE TMA tensor store
   void* pred; int pred_c;
+  int pair_cta;         // 1: launched as clusters of two CTAs that execute every MMA together (tcgen05 cta_group::2, M = 256):
+                        //    CTA rank r of pair q works on tile index 2 * (q / ntiles_n) + r of N tile q % ntiles_n; total_items
+                        //    counts PAIR items; b_bytes is the half weight tile (n_tile / 2 rows) each CTA holds
   int pred_q14;         // 1: pred is int16 NCHW, value = (int16)(min(relu(.), 1) * 2^14)  (evaluation/*/compute_score.py:110)
   float pred_wb[4 * 32 + 4];   // [k][32] weights (zero beyond cout), then [k] biases
 };
@@ -282,11 +285,13 @@ struct ItemCoord { int nt, img, y0, x0; };
 __device__ __forceinline__ unsigned fast_div(unsigned n, unsigned d, unsigned mul, unsigned one, int fast) {
   return fast ? __umulhi(n, mul) + (n & one) : n / d;
 }
-__device__ __forceinline__ ItemCoord decode_item(const ConvTcParams& p, long long item64) {
+__device__ __forceinline__ ItemCoord decode_item(const ConvTcParams& p, long long item64, unsigned pair_rank = 0u) {
   ItemCoord c;
   const unsigned item = (unsigned)item64;            // item counts fit 32 bits (64-bit div/mod costs ~100 instr each)
-  const unsigned tm = fast_div(item, (unsigned)p.ntiles_n, p.md_nt, p.one_nt, p.fastdiv);
+  unsigned tm = fast_div(item, (unsigned)p.ntiles_n, p.md_nt, p.one_nt, p.fastdiv);
   c.nt = (int)(item - tm * (unsigned)p.ntiles_n);
+  if (p.pair_cta) tm = 2u * tm + pair_rank;          // the two CTAs of a pair take neighbouring tiles of the SAME N tile (a tile index
+                                                     // past the end decodes to an image past the batch: loads zero-fill, stores are skipped)
   if (p.flat) {   // item = imgs_per_item consecutive images
     c.img = (int)tm * p.imgs_per_item; c.y0 = 0; c.x0 = 0;
     return c;
@@ -422,7 +427,7 @@ __device__ __forceinline__ void lean_prefetch_res(uint32_t stg_s, int lane, cons
   }
 }
 
-template <int CK, bool RESIDENT>
+template <int CK, bool RESIDENT, bool PAIR>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
                const __grid_constant__ CUtensorMap tmap_r, const __grid_constant__ CUtensorMap tmap_i,
@@ -443,10 +448,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
   float* bias_tab = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + BAR_BYTES);   // [cout_pad] when p.bias_smem
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // PAIR: cluster of two CTAs; rank 0 (the leader) issues every MMA for both, each CTA loads its own activation boxes and its
+  // half of every weight tile and runs the epilogue of its own 128 accumulator lanes
+  const uint32_t pair_rank = PAIR ? cluster_ctarank() : 0u;
+  const long long item_first = PAIR ? (long long)(blockIdx.x >> 1) : (long long)blockIdx.x;
+  const long long item_step = PAIR ? (long long)(gridDim.x >> 1) : (long long)gridDim.x;
   constexpr uint32_t ROW_BYTES = CK * 2;                 // bytes per pixel of a K chunk
   constexpr uint32_t LAYOUT = (CK == 64) ? 2u : 4u;
   // cute::UMMA::InstrDescriptor: c_format F32 [4,6) | a,b format BF16 [7,10),[10,13) | K-major | N>>3 [17,23) | M>>4 [24,29)
-  const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.n_tile >> 3) << 17) | ((128u >> 4) << 24);
+  const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.n_tile >> 3) << 17) | (((PAIR ? 256u : 128u) >> 4) << 24);
   const int NT = p.n_tile;
   const int taps = p.ksize * p.ksize;
   const int pad = (p.ksize == 3) ? p.dil : 0;
@@ -454,7 +464,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.a_slots; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
     for (int s = 0; s < p.b_stages; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], 8); }
+    // PAIR: the leader's issuer waits for the epilogue warps of BOTH CTAs before it reuses an accumulator stage
+    for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], PAIR ? 16 : 8); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     tma_prefetch_desc(&tmap_x);
@@ -462,7 +473,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
     if (p.res_chunks) { tma_prefetch_desc(&tmap_r); tma_prefetch_desc(&tmap_i); }
     if (p.tma_store) tma_prefetch_desc(&tmap_y);
   }
-  if (warp == WARP_MMA) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+  if (warp == WARP_MMA) { if (PAIR) tmem_alloc_pair(tmem_slot, (uint32_t)p.tmem_cols); else tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols); }
   // Programmatic dependent launch: everything above touches only on-chip state and the kernel parameters, so it may run
   // while the preceding kernel of the stream is still draining; all global-memory traffic (activations, residual, y,
   // and -- because a caller may have produced them just before -- weights and bias) comes after this wait.
@@ -471,6 +482,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
     for (int i = threadIdx.x; i < p.cout_pad; i += 256) bias_tab[i] = p.bias ? __ldg(p.bias + i) : 0.0f;
   tc_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync_all();          // both CTAs' barriers are initialised before any cross-CTA arrive / TMA completion
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -478,19 +490,29 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
     // ===================== A producer: one halo box per (item, K chunk), then the residual boxes =====================
     if (elect_one()) {
       int slot = 0; uint32_t phase = 0;
-      for (long long item = blockIdx.x; item < p.total_items; item += gridDim.x) {
-        const ItemCoord c = decode_item(p, item);
+      for (long long item = item_first; item < p.total_items; item += item_step) {
+        const ItemCoord c = decode_item(p, item, pair_rank);
         for (int ch = 0; ch < p.nchunks; ++ch) {
           mbar_wait(&a_empty[slot], phase ^ 1, 100 + slot);
-          mbar_arrive_expect_tx(&a_full[slot], (uint32_t)p.a_tx_bytes);
-          tma_load_4d(&tmap_x, &a_full[slot], smem_a + (size_t)slot * p.a_bytes, ch * CK, c.x0 - pad, c.y0 - pad, c.img);   // flat: (-1, -1, first image)
+          if (PAIR) {     // both boxes complete on the LEADER's barrier; only the leader arms it (for the bytes of both)
+            if (pair_rank == 0) mbar_arrive_expect_tx(&a_full[slot], 2u * (uint32_t)p.a_tx_bytes);
+            tma_load_4d_pair(&tmap_x, &a_full[slot], smem_a + (size_t)slot * p.a_bytes, ch * CK, c.x0 - pad, c.y0 - pad, c.img);
+          } else {
+            mbar_arrive_expect_tx(&a_full[slot], (uint32_t)p.a_tx_bytes);
+            tma_load_4d(&tmap_x, &a_full[slot], smem_a + (size_t)slot * p.a_bytes, ch * CK, c.x0 - pad, c.y0 - pad, c.img);   // flat: (-1, -1, first image)
+          }
           if (++slot == p.a_slots) { slot = 0; phase ^= 1; }
         }
         // residual of this N tile as extra K chunks: plain (no halo) box of the residual tensor
         for (int rc = 0; rc < p.res_chunks; ++rc) {
           mbar_wait(&a_empty[slot], phase ^ 1, 120 + slot);
-          mbar_arrive_expect_tx(&a_full[slot], (uint32_t)p.r_tx_bytes);
-          tma_load_4d(&tmap_r, &a_full[slot], smem_a + (size_t)slot * p.a_bytes, c.nt * NT + rc * CK, c.x0, c.y0, c.img);
+          if (PAIR) {
+            if (pair_rank == 0) mbar_arrive_expect_tx(&a_full[slot], 2u * (uint32_t)p.r_tx_bytes);
+            tma_load_4d_pair(&tmap_r, &a_full[slot], smem_a + (size_t)slot * p.a_bytes, c.nt * NT + rc * CK, c.x0, c.y0, c.img);
+          } else {
+            mbar_arrive_expect_tx(&a_full[slot], (uint32_t)p.r_tx_bytes);
+            tma_load_4d(&tmap_r, &a_full[slot], smem_a + (size_t)slot * p.a_bytes, c.nt * NT + rc * CK, c.x0, c.y0, c.img);
+          }
           if (++slot == p.a_slots) { slot = 0; phase ^= 1; }
         }
       }
@@ -501,29 +523,45 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
       if (RESIDENT) {
         // every item uses the same tiles (one N tile): load each (chunk, tap) tile once, they all signal b_full[0]
         const int n_main = p.nchunks * taps;
-        mbar_arrive_expect_tx(&b_full[0], (uint32_t)((n_main + p.res_chunks) * p.b_bytes));
+        // PAIR: each CTA holds rows [rank * NT / 2, (rank + 1) * NT / 2) of every weight tile (b_bytes is that half)
+        const int row0 = PAIR ? (int)pair_rank * (NT >> 1) : 0;
+        if (!PAIR || pair_rank == 0) mbar_arrive_expect_tx(&b_full[0], (uint32_t)((PAIR ? 2 : 1) * (n_main + p.res_chunks) * p.b_bytes));
         for (int t = 0; t < n_main; ++t) {
           const int ch = t / taps, tap = t - ch * taps;
-          tma_load_2d(&tmap_w, &b_full[0], smem_b + (size_t)t * p.b_bytes, ch * CK, tap * p.cout_pad);
+          if (PAIR) tma_load_2d_pair(&tmap_w, &b_full[0], smem_b + (size_t)t * p.b_bytes, ch * CK, tap * p.cout_pad + row0);
+          else tma_load_2d(&tmap_w, &b_full[0], smem_b + (size_t)t * p.b_bytes, ch * CK, tap * p.cout_pad);
         }
-        for (int rc = 0; rc < p.res_chunks; ++rc)     // identity tiles of the residual chunks
-          tma_load_2d(&tmap_i, &b_full[0], smem_b + (size_t)(n_main + rc) * p.b_bytes, rc * CK, 0);
+        for (int rc = 0; rc < p.res_chunks; ++rc) {   // identity tiles of the residual chunks
+          if (PAIR) tma_load_2d_pair(&tmap_i, &b_full[0], smem_b + (size_t)(n_main + rc) * p.b_bytes, rc * CK, row0);
+          else tma_load_2d(&tmap_i, &b_full[0], smem_b + (size_t)(n_main + rc) * p.b_bytes, rc * CK, 0);
+        }
       } else {
         int stage = 0; uint32_t phase = 0;
-        for (long long item = blockIdx.x; item < p.total_items; item += gridDim.x) {
+        const int row0 = PAIR ? (int)pair_rank * (NT >> 1) : 0;
+        for (long long item = item_first; item < p.total_items; item += item_step) {
           const int nt = (int)((unsigned)item % (unsigned)p.ntiles_n);
           for (int ch = 0; ch < p.nchunks; ++ch) {
             for (int tap = 0; tap < taps; ++tap) {
               mbar_wait(&b_empty[stage], phase ^ 1, 150 + stage);
-              mbar_arrive_expect_tx(&b_full[stage], (uint32_t)p.b_bytes);
-              tma_load_2d(&tmap_w, &b_full[stage], smem_b + (size_t)stage * p.b_bytes, ch * CK, tap * p.cout_pad + nt * NT);
+              if (PAIR) {
+                if (pair_rank == 0) mbar_arrive_expect_tx(&b_full[stage], 2u * (uint32_t)p.b_bytes);
+                tma_load_2d_pair(&tmap_w, &b_full[stage], smem_b + (size_t)stage * p.b_bytes, ch * CK, tap * p.cout_pad + nt * NT + row0);
+              } else {
+                mbar_arrive_expect_tx(&b_full[stage], (uint32_t)p.b_bytes);
+                tma_load_2d(&tmap_w, &b_full[stage], smem_b + (size_t)stage * p.b_bytes, ch * CK, tap * p.cout_pad + nt * NT);
+              }
               if (++stage == p.b_stages) { stage = 0; phase ^= 1; }
             }
           }
           for (int rc = 0; rc < p.res_chunks; ++rc) {
             mbar_wait(&b_empty[stage], phase ^ 1, 170 + stage);
-            mbar_arrive_expect_tx(&b_full[stage], (uint32_t)p.b_bytes);
-            tma_load_2d(&tmap_i, &b_full[stage], smem_b + (size_t)stage * p.b_bytes, rc * CK, 0);
+            if (PAIR) {
+              if (pair_rank == 0) mbar_arrive_expect_tx(&b_full[stage], 2u * (uint32_t)p.b_bytes);
+              tma_load_2d_pair(&tmap_i, &b_full[stage], smem_b + (size_t)stage * p.b_bytes, rc * CK, row0);
+            } else {
+              mbar_arrive_expect_tx(&b_full[stage], (uint32_t)p.b_bytes);
+              tma_load_2d(&tmap_i, &b_full[stage], smem_b + (size_t)stage * p.b_bytes, rc * CK, 0);
+            }
             if (++stage == p.b_stages) { stage = 0; phase ^= 1; }
           }
         }
@@ -533,7 +571,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
     // ===================== MMA issuer =====================
     // One in-order instruction stream: everything that is not an MMA, a barrier wait or a commit is hoisted out of the
     // per-tap path (descriptor high words, tap offsets, weight-tile addresses are plain adds on the low word).
-    if (elect_one()) {
+    if ((!PAIR || pair_rank == 0) && elect_one()) {
       int aslot = 0; uint32_t aphase = 0;
       int bstage = 0; uint32_t bphase = 0;
       int acc = 0; uint32_t acc_phase = 0;
@@ -561,17 +599,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
       auto mma_pair = [&](uint32_t a_lo, uint32_t a_hi_w, uint32_t b_lo, uint32_t d0, uint32_t first_acc) {
 #pragma unroll
         for (int k16 = 0; k16 < CK / 16; ++k16)
-          umma_bf16(d0, ((uint64_t)a_hi_w << 32) | (uint64_t)(a_lo + 2u * k16), ((uint64_t)b_hi << 32) | (uint64_t)(b_lo + 2u * k16),
-                    idesc, k16 == 0 ? first_acc : 1u);
+          umma_bf16_t<PAIR>(d0, ((uint64_t)a_hi_w << 32) | (uint64_t)(a_lo + 2u * k16), ((uint64_t)b_hi << 32) | (uint64_t)(b_lo + 2u * k16),
+                            idesc, k16 == 0 ? first_acc : 1u);
         if (two_tiles) {
 #pragma unroll
           for (int k16 = 0; k16 < CK / 16; ++k16)
-            umma_bf16(d0 + (uint32_t)NT, ((uint64_t)a_hi_w << 32) | (uint64_t)(a_lo + tile_step + 2u * k16),
-                      ((uint64_t)b_hi << 32) | (uint64_t)(b_lo + 2u * k16), idesc, k16 == 0 ? first_acc : 1u);
+            umma_bf16_t<PAIR>(d0 + (uint32_t)NT, ((uint64_t)a_hi_w << 32) | (uint64_t)(a_lo + tile_step + 2u * k16),
+                              ((uint64_t)b_hi << 32) | (uint64_t)(b_lo + 2u * k16), idesc, k16 == 0 ? first_acc : 1u);
         }
       };
 
-      for (long long item = blockIdx.x; item < p.total_items; item += gridDim.x) {
+      for (long long item = item_first; item < p.total_items; item += item_step) {
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1, 200 + acc);
         tc_fence_after();
         const uint32_t d0 = tmem_base + (uint32_t)(acc * p.mt * NT);
@@ -592,7 +630,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
               }
               mma_pair(a_lo0 + tap_off[tap], a_hi, b_lo, d0, (tap == 0 && ch == 0) ? 0u : 1u);
               if (!RESIDENT) {
-                umma_commit(&b_empty[bstage]);   // weight stage free once these MMAs retire
+                umma_commit_t<PAIR>(&b_empty[bstage]);   // weight stage free once these MMAs retire
                 if (++bstage == p.b_stages) { bstage = 0; bphase ^= 1; }
               }
             }
@@ -606,11 +644,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
             }
             mma_pair(a_lo0, a_hi, b_lo, d0, ch == 0 ? 0u : 1u);
             if (!RESIDENT) {
-              umma_commit(&b_empty[bstage]);
+              umma_commit_t<PAIR>(&b_empty[bstage]);
               if (++bstage == p.b_stages) { bstage = 0; bphase ^= 1; }
             }
           }
-          umma_commit(&a_empty[aslot]);          // halo box free once every tap of this chunk retired
+          umma_commit_t<PAIR>(&a_empty[aslot]);          // halo box free once every tap of this chunk retired
           if (++aslot == p.a_slots) { aslot = 0; aphase ^= 1; }
         }
         // residual: D += R * I  (exact: identity weights, fp32 accumulation) -- the epilogue never touches it
@@ -626,13 +664,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
           }
           mma_pair(a_base + (uint32_t)aslot * a_step, r_hi, b_lo, d0, 1u);
           if (!RESIDENT) {
-            umma_commit(&b_empty[bstage]);
+            umma_commit_t<PAIR>(&b_empty[bstage]);
             if (++bstage == p.b_stages) { bstage = 0; bphase ^= 1; }
           }
-          umma_commit(&a_empty[aslot]);
+          umma_commit_t<PAIR>(&a_empty[aslot]);
           if (++aslot == p.a_slots) { aslot = 0; aphase ^= 1; }
         }
-        umma_commit(&tfull_bar[acc]);            // accumulators ready for the epilogue
+        umma_commit_t<PAIR>(&tfull_bar[acc]);    // accumulators ready for the epilogue (PAIR: of both CTAs)
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
@@ -665,8 +703,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
       const long long r_row = (long long)p.yW * p.r_pitch, r_col = (long long)p.r_pitch;
       const __nv_bfloat16* const rbase = reinterpret_cast<const __nv_bfloat16*>(p.res) + p.r_coff + (long long)(quarter * 4) * r_row;
       const bool my_group = (p.mt == 2) || group == 0;      // NT <= 64 is one group: with mt == 1 warps 4..7 have no columns
-      for (long long item = blockIdx.x; item < p.total_items; item += gridDim.x) {
-        const ItemCoord c = decode_item(p, item);
+      for (long long item = item_first; item < p.total_items; item += item_step) {
+        const ItemCoord c = decode_item(p, item, pair_rank);
         const int co0 = c.nt * NT;
         const int tx0 = c.x0 + t * p.t1_dx;
         const int img_t = c.img + t * p.t1_dimg;             // narrow maps: the second tile is the next image
@@ -713,12 +751,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+        if (lane == 0) { if (PAIR) mbar_arrive_leader(&tempty_bar[acc]); else mbar_arrive(&tempty_bar[acc]); }
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     } else
-    for (long long item = blockIdx.x; item < p.total_items; item += gridDim.x) {
-      const ItemCoord c = decode_item(p, item);
+    for (long long item = item_first; item < p.total_items; item += item_step) {
+      const ItemCoord c = decode_item(p, item, pair_rank);
       const int co0 = c.nt * NT;
       const int t = (p.mt == 2) ? group : 0;
       const uint32_t tbase = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)((acc * p.mt + t) * NT);
@@ -824,7 +862,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
       // all TMEM reads of this warp are complete (tcgen05.wait::ld inside the loads): release the accumulators
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      if (lane == 0) { if (PAIR) mbar_arrive_leader(&tempty_bar[acc]); else mbar_arrive(&tempty_bar[acc]); }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   }
@@ -832,9 +870,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
   if (p.tma_store && warp < 8 && lane == 0) tma_store_wait_all();     // this warp's tensor stores have been written
   tc_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync_all();          // neither CTA leaves (or frees TMEM) while the peer may still signal its barriers
   if (warp == WARP_MMA) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+    if (PAIR) tmem_dealloc_pair(tmem_base, (uint32_t)p.tmem_cols); else tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
   }
 }
 
@@ -892,9 +931,10 @@ struct TcConfig {
   int pair_img;    // narrow maps (one tile column): the two M tiles of an item are two consecutive images
   int n_tile, ck, nchunks, cout, cout_pad, mt, halo_w, rows, a_slots, b_stages, b_resident, a_bytes, a_tx_bytes, b_bytes,
       smem_bytes, tmem_cols, vec_ok, align_ok;
+  int pair_cta;    // CTA pairs (cta_group::2): b_bytes is then the HALF weight tile one CTA holds
 };
 
-static int tc_plan(const dbsr_conv_t* c, TcConfig* cfg, bool set_err) {
+static int tc_plan(const dbsr_conv_t* c, TcConfig* cfg, bool set_err, bool allow_pair = true) {
 #define TC_REQ(cond, ...) do { if (!(cond)) { if (set_err) set_error(__VA_ARGS__); return 1; } } while (0)
   TC_REQ(c && view_ok(&c->x) && view_ok(&c->y) && c->w, "conv2d_tc: bad descriptor");
   TC_REQ(c->x.dtype == DBSR_BF16, "conv2d_tc: input must be bf16");
@@ -934,7 +974,16 @@ static int tc_plan(const dbsr_conv_t* c, TcConfig* cfg, bool set_err) {
   const int pad = (c->ksize == 3) ? c->dilation : 0;
   const int budget = 227 * 1024 - (1024 + BAR_BYTES + BIAS_TAB_BYTES) - 8 * STG_WARP_BYTES;
   const int taps = c->ksize * c->ksize;
-  cfg->b_bytes = nt * ck * 2;
+  // CTA pairs (tcgen05 cta_group::2): the large N = 64 / 128 layers run as clusters of two CTAs that execute every MMA together
+  // (M = 256): each CTA fetches its own activations but only HALF of the weight rows, so the per-SM operand fetch of an MMA
+  // drops from 4096 + 32 N to 4096 + 16 N bytes (tools/micro/mma_rate.cu: 48 -> 43 clk at N = 64) and the weight tiles take
+  // half the shared memory.  Needs two-tile items of a map at least 16 pixels wide and enough of them for every pair.
+  static const bool pair_enabled = getenv("DBSR_TC_NO_PAIR") == nullptr;       // A/B switch
+  const long long tm_items2 = (long long)c->x.n * ceil_div(c->x.w, 2 * TILE_W) * ceil_div(c->x.h, TILE_H);
+  const bool want_pair = allow_pair && pair_enabled && (nt == 64 || nt == 128) && tiles_x >= 2 && r == 1 && tm_items2 >= 4 * 148 &&
+                         !(c->ksize == 3 && c->dilation == 1 && c->x.h <= 8 && c->x.w <= 8);
+  cfg->pair_cta = want_pair ? 1 : 0;
+  cfg->b_bytes = (want_pair ? nt / 2 : nt) * ck * 2;
   TC_REQ(cfg->b_bytes % 1024 == 0, "conv2d_tc: internal: unaligned weight stage");
   cfg->rows = TILE_H + 2 * pad;
   // small maps: pack several whole images (with their zero borders) into one M = 128 tile -- "flat" mode
@@ -991,6 +1040,7 @@ static int tc_plan(const dbsr_conv_t* c, TcConfig* cfg, bool set_err) {
     }
   }
   TC_REQ(found, "conv2d_tc: activation halo box does not fit in shared memory (dilation %d)", c->dilation);
+  if (want_pair && !(cfg->mt == 2 && !cfg->pair_img && !cfg->flat)) return tc_plan(c, cfg, set_err, false);   // pairs need two-tile items
   int tc = 32;
   while (tc < 2 * cfg->mt * nt) tc <<= 1;
   cfg->tmem_cols = tc;
@@ -1043,14 +1093,14 @@ static dbsr_conv_t centre_tap_form(const dbsr_conv_t* c) {
   return cc;
 }
 
-template <int CK, bool RESIDENT>
+template <int CK, bool RESIDENT, bool PAIR>
 static int launch_tc(const CUtensorMap& mx, const CUtensorMap& mw, const CUtensorMap& mr, const CUtensorMap& mi,
                      const CUtensorMap& my, const ConvTcParams& p, int smem, int grid_limit, cudaStream_t st) {
   const int dev_slot = current_device_slot();
   static int configured_smem_dev[MAX_DEVICES] = {};
   int& configured_smem = configured_smem_dev[dev_slot];
   if (smem > configured_smem) {
-    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<CK, RESIDENT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<CK, RESIDENT, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) {
       set_error("conv2d_tc: cudaFuncSetAttribute(%d) failed: %s", smem, cudaGetErrorString(e));
       return 2;
@@ -1066,16 +1116,29 @@ static int launch_tc(const CUtensorMap& mx, const CUtensorMap& mw, const CUtenso
   }
   int grid = (int)(p.total_items < num_sms ? p.total_items : num_sms);
   if (grid_limit > 0 && grid > grid_limit) grid = grid_limit;
+  if (PAIR) {      // clusters of two CTAs, one PAIR item at a time per cluster
+    const int pairs_max = (grid_limit > 0 && grid_limit < num_sms ? grid_limit : num_sms) / 2;
+    grid = 2 * (int)(p.total_items < pairs_max ? p.total_items : pairs_max);
+  }
   // programmatic dependent launch: CTAs may be scheduled (barrier init, tensor-map prefetch, TMEM allocation) as soon as
   // the SMs of the preceding kernel drain; the kernel calls griddepcontrol.wait before its first global access
   static const bool pdl = getenv("DBSR_TC_NO_PDL") == nullptr;     // A/B switch: DBSR_TC_NO_PDL=1 launches normally
   cudaLaunchConfig_t lc = {};
   lc.gridDim = dim3((unsigned)grid); lc.blockDim = dim3(TC_THREADS); lc.dynamicSmemBytes = (size_t)smem; lc.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
-  lc.attrs = attr; lc.numAttrs = pdl ? 1 : 0;
-  cudaError_t le = cudaLaunchKernelEx(&lc, conv_tc_kernel<CK, RESIDENT>, mx, mw, mr, mi, my, p);
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  if (PAIR) {
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = 2; attr[na].val.clusterDim.y = 1; attr[na].val.clusterDim.z = 1;
+    ++na;
+  }
+  if (pdl) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  lc.attrs = attr; lc.numAttrs = na;
+  cudaError_t le = cudaLaunchKernelEx(&lc, conv_tc_kernel<CK, RESIDENT, PAIR>, mx, mw, mr, mi, my, p);
   if (le != cudaSuccess) { set_error("conv2d_tc: launch failed: %s", cudaGetErrorString(le)); return 2; }
   return check_launch("conv2d_tc");
 }
@@ -1132,7 +1195,7 @@ static int conv2d_tc_impl(const dbsr_conv_t* c_in, void* stream, const float* pr
     const int kpad = cfg.nchunks * cfg.ck;
     cuuint64_t dims[2] = {(cuuint64_t)kpad, (cuuint64_t)taps * cfg.cout_pad};
     cuuint64_t strides[1] = {(cuuint64_t)kpad * 2};
-    cuuint32_t box[2] = {(cuuint32_t)cfg.ck, (cuuint32_t)cfg.n_tile};
+    cuuint32_t box[2] = {(cuuint32_t)cfg.ck, (cuuint32_t)(cfg.pair_cta ? cfg.n_tile / 2 : cfg.n_tile)};
     cuuint32_t es[2] = {1, 1};
     CUresult rc = encode(&mw, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(c->w), dims, strides, box, es,
                          CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -1160,7 +1223,7 @@ static int conv2d_tc_impl(const dbsr_conv_t* c_in, void* stream, const float* pr
       DBSR_REQUIRE(eye != nullptr, "conv2d_tc: could not create the identity weight tile (first call of this N tile inside a stream capture? run the layer once eagerly)");
       cuuint64_t dims[2] = {(cuuint64_t)cfg.n_tile, (cuuint64_t)cfg.n_tile};
       cuuint64_t strides[1] = {(cuuint64_t)cfg.n_tile * 2};
-      cuuint32_t box[2] = {(cuuint32_t)cfg.ck, (cuuint32_t)cfg.n_tile};
+      cuuint32_t box[2] = {(cuuint32_t)cfg.ck, (cuuint32_t)(cfg.pair_cta ? cfg.n_tile / 2 : cfg.n_tile)};
       cuuint32_t es[2] = {1, 1};
       CUresult rc = encode(&mi, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(eye), dims, strides, box, es,
                            CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -1182,7 +1245,9 @@ static int conv2d_tc_impl(const dbsr_conv_t* c_in, void* stream, const float* pr
   if (cfg.flat) { p.t1_step16 = cfg.flat_ni * cfg.flat_s * row16; p.t1_dimg = cfg.flat_ni; p.t1_dx = 0; }
   else if (cfg.pair_img) { p.t1_step16 = cfg.rows * cfg.halo_w * row16; p.t1_dimg = 1; p.t1_dx = 0; }
   else { p.t1_step16 = TILE_W * row16; p.t1_dimg = 0; p.t1_dx = TILE_W; }
-  p.total_items = (long long)ceil_div(p.n, p.imgs_per_item) * (cfg.flat ? 1 : p.items_x * p.tiles_y) * p.ntiles_n;
+  const long long tm_items = (long long)ceil_div(p.n, p.imgs_per_item) * (cfg.flat ? 1 : p.items_x * p.tiles_y);      // per N tile
+  p.pair_cta = cfg.pair_cta;
+  p.total_items = (cfg.pair_cta ? (tm_items + 1) / 2 : tm_items) * p.ntiles_n;                  // pair_cta: PAIR items
   DBSR_REQUIRE(p.total_items < (1LL << 31) && (long long)c->y.n * c->y.h * c->y.w < (1LL << 31),
                "conv2d_tc: more than 2^31 work items / output pixels");
   {
@@ -1197,7 +1262,8 @@ static int conv2d_tc_impl(const dbsr_conv_t* c_in, void* stream, const float* pr
     }
     p.md_nt = mul[0]; p.md_img = mul[1]; p.md_x = mul[2];
     p.one_nt = one[0]; p.one_img = one[1]; p.one_x = one[2];
-    p.fastdiv = ((unsigned long long)p.total_items * dmax < (1ULL << 32)) ? 1 : 0;
+    const unsigned long long nmax = (unsigned long long)(p.total_items > tm_items + 2 ? p.total_items : tm_items + 2);   // pairs decode tile indices up to tm_items + 1
+    p.fastdiv = (nmax * dmax < (1ULL << 32)) ? 1 : 0;
   }
   p.bias_smem = (cfg.cout_pad * 4 <= BIAS_TAB_BYTES) ? 1 : 0;
   p.a_slots = cfg.a_slots; p.b_stages = cfg.b_stages; p.b_resident = cfg.b_resident;
@@ -1261,10 +1327,16 @@ static int conv2d_tc_impl(const dbsr_conv_t* c_in, void* stream, const float* pr
   }
   cudaStream_t st = (cudaStream_t)stream;
   const int gl = c_in->grid_limit;
-  if (cfg.ck == 64) return cfg.b_resident ? launch_tc<64, true>(mx, mw, mr, mi, my, p, cfg.smem_bytes, gl, st)
-                                          : launch_tc<64, false>(mx, mw, mr, mi, my, p, cfg.smem_bytes, gl, st);
-  return cfg.b_resident ? launch_tc<32, true>(mx, mw, mr, mi, my, p, cfg.smem_bytes, gl, st)
-                        : launch_tc<32, false>(mx, mw, mr, mi, my, p, cfg.smem_bytes, gl, st);
+  if (cfg.pair_cta) {
+    if (cfg.ck == 64) return cfg.b_resident ? launch_tc<64, true, true>(mx, mw, mr, mi, my, p, cfg.smem_bytes, gl, st)
+                                            : launch_tc<64, false, true>(mx, mw, mr, mi, my, p, cfg.smem_bytes, gl, st);
+    return cfg.b_resident ? launch_tc<32, true, true>(mx, mw, mr, mi, my, p, cfg.smem_bytes, gl, st)
+                          : launch_tc<32, false, true>(mx, mw, mr, mi, my, p, cfg.smem_bytes, gl, st);
+  }
+  if (cfg.ck == 64) return cfg.b_resident ? launch_tc<64, true, false>(mx, mw, mr, mi, my, p, cfg.smem_bytes, gl, st)
+                                          : launch_tc<64, false, false>(mx, mw, mr, mi, my, p, cfg.smem_bytes, gl, st);
+  return cfg.b_resident ? launch_tc<32, true, false>(mx, mw, mr, mi, my, p, cfg.smem_bytes, gl, st)
+                        : launch_tc<32, false, false>(mx, mw, mr, mi, my, p, cfg.smem_bytes, gl, st);
 }
 
 extern "C" int dbsr_conv2d_tc(const dbsr_conv_t* c, void* stream) {

@@ -50,6 +50,15 @@ TC_CASES = {
     'narrow_8x8_pair_136x128_n301': (136, 128, 3, 1, 301, 8, 8, 2, False, False, 0),
     'narrow_8x5_pair_64x64_n297_k1': (64, 64, 1, 1, 297, 8, 5, 1, False, False, 0),
     'narrow_20x8_pair_32x32_n300': (32, 32, 3, 1, 300, 20, 8, 1, False, False, 0),
+    # CTA pairs (tcgen05 cta_group::2, M = 256 over two CTAs that share every weight tile): large N = 64 / 128 layers with at
+    # least 592 two-tile items.  Odd tile counts (the last pair has one idle half), ragged tiles, resident and streamed weights,
+    # tensor-core and epilogue-side residuals, several N tiles, 1x1 kernels, fp32 outputs.
+    'cta_pair_64x64_res_n67': (64, 64, 3, 1, 67, 48, 48, 1, True, False, 0),
+    'cta_pair_128x128_res_n70_ragged': (128, 128, 3, 1, 70, 40, 44, 1, True, False, 0),
+    'cta_pair_64x512_n99': (64, 512, 3, 1, 99, 32, 48, 1, False, False, 0),
+    'cta_pair_192x128_n67': (192, 128, 3, 1, 67, 48, 48, 1, False, False, 0),
+    'cta_pair_1x1_512x64_n67': (512, 64, 1, 1, 67, 48, 48, 0, False, False, 0),
+    'cta_pair_128x128_f32_n67': (128, 128, 3, 1, 67, 48, 48, 2, False, True, 0),
     # 1x1 maps, image count a multiple of 8: centre tap only, the n maps viewed as one (n/8) x 8 image
     'centre_1x1_196x196_n448': (196, 196, 3, 1, 448, 1, 1, 2, False, False, 0),
     'centre_1x1_512x196_n448_res': (512, 192, 3, 1, 448, 1, 1, 1, True, False, 0),
