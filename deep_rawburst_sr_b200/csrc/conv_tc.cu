@@ -51,7 +51,8 @@ struct ConvTcParams {
   int cout;             // real output channels (stores are masked beyond it)
   int n_tile;           // UMMA N (multiple of 16, <= 128)
   int mt;               // 16x8 tiles per item (1 or 2, side by side along x)
-  int tmem_cols;        // power of two >= max(32, 2 * mt * n_tile)
+  int tmem_cols;        // power of two >= max(32, acc_stages * mt * n_tile)
+  int acc_stages;       // accumulator stages in TMEM (2 or 4): how many items the MMA issuer may run ahead of the epilogue
   int vec_ok;           // 1: aligned fast path (16-byte accesses, every 32-column chunk fully inside cout)
   int align_ok;         // 1: y / residual / bias allow 16-byte accesses (chunks that end inside cout use them per thread)
   int ntiles_n;         // cout_pad / n_tile
@@ -443,8 +444,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
   uint64_t* b_full = a_empty + p.a_slots;
   uint64_t* b_empty = b_full + p.b_stages;
   uint64_t* tfull_bar = b_empty + p.b_stages;
-  uint64_t* tempty_bar = tfull_bar + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  uint64_t* tempty_bar = tfull_bar + 4;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 4);
   float* bias_tab = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + BAR_BYTES);   // [cout_pad] when p.bias_smem
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -465,7 +466,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
     for (int s = 0; s < p.a_slots; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
     for (int s = 0; s < p.b_stages; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
     // PAIR: the leader's issuer waits for the epilogue warps of BOTH CTAs before it reuses an accumulator stage
-    for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], PAIR ? 16 : 8); }
+    for (int a = 0; a < p.acc_stages; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], PAIR ? 16 : 8); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     tma_prefetch_desc(&tmap_x);
@@ -671,7 +672,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
           if (++aslot == p.a_slots) { aslot = 0; aphase ^= 1; }
         }
         umma_commit_t<PAIR>(&tfull_bar[acc]);    // accumulators ready for the epilogue (PAIR: of both CTAs)
-        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        if (++acc == p.acc_stages) { acc = 0; acc_phase ^= 1; }
       }
     }
   } else if (warp < 8) {
@@ -752,7 +753,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
         tc_fence_before();
         __syncwarp();
         if (lane == 0) { if (PAIR) mbar_arrive_leader(&tempty_bar[acc]); else mbar_arrive(&tempty_bar[acc]); }
-        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        if (++acc == p.acc_stages) { acc = 0; acc_phase ^= 1; }
       }
     } else
     for (long long item = item_first; item < p.total_items; item += item_step) {
@@ -863,7 +864,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
       tc_fence_before();
       __syncwarp();
       if (lane == 0) { if (PAIR) mbar_arrive_leader(&tempty_bar[acc]); else mbar_arrive(&tempty_bar[acc]); }
-      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      if (++acc == p.acc_stages) { acc = 0; acc_phase ^= 1; }
     }
   }
 
@@ -930,7 +931,7 @@ struct TcConfig {
   int flat, flat_s, flat_ni, res_chunks;
   int pair_img;    // narrow maps (one tile column): the two M tiles of an item are two consecutive images
   int n_tile, ck, nchunks, cout, cout_pad, mt, halo_w, rows, a_slots, b_stages, b_resident, a_bytes, a_tx_bytes, b_bytes,
-      smem_bytes, tmem_cols, vec_ok, align_ok;
+      smem_bytes, tmem_cols, vec_ok, align_ok, acc_stages;
   int pair_cta;    // CTA pairs (cta_group::2): b_bytes is then the HALF weight tile one CTA holds
 };
 
@@ -978,9 +979,13 @@ static int tc_plan(const dbsr_conv_t* c, TcConfig* cfg, bool set_err, bool allow
   // (M = 256): each CTA fetches its own activations but only HALF of the weight rows, so the per-SM operand fetch of an MMA
   // drops from 4096 + 32 N to 4096 + 16 N bytes (tools/micro/mma_rate.cu: 48 -> 43 clk at N = 64) and the weight tiles take
   // half the shared memory.  Needs two-tile items of a map at least 16 pixels wide and enough of them for every pair.
-  static const bool pair_enabled = getenv("DBSR_TC_NO_PAIR") == nullptr;       // A/B switch
+  // Measured on B200 (profiles/r02_cta_pair_ab.txt): layers with >= 128 input channels (two K chunks, 144 MMAs per item) gain
+  // 5-7 %; 64-channel layers (72 MMAs per item) lose to the cross-CTA round trips per item, so pairs are used for K >= 128 only.
+  // DBSR_TC_PAIR = 0 / 1 / 2: never / K >= 128 (default) / every eligible layer (A/B switch).
+  static const int pair_mode = getenv("DBSR_TC_PAIR") ? atoi(getenv("DBSR_TC_PAIR")) : 1;
   const long long tm_items2 = (long long)c->x.n * ceil_div(c->x.w, 2 * TILE_W) * ceil_div(c->x.h, TILE_H);
-  const bool want_pair = allow_pair && pair_enabled && (nt == 64 || nt == 128) && tiles_x >= 2 && r == 1 && tm_items2 >= 4 * 148 &&
+  const bool want_pair = allow_pair && (pair_mode >= 2 || (pair_mode == 1 && kpad / ck >= 2)) && (nt == 64 || nt == 128) &&
+                         tiles_x >= 2 && r == 1 && tm_items2 >= 4 * 148 &&
                          !(c->ksize == 3 && c->dilation == 1 && c->x.h <= 8 && c->x.w <= 8);
   cfg->pair_cta = want_pair ? 1 : 0;
   cfg->b_bytes = (want_pair ? nt / 2 : nt) * ck * 2;
@@ -1041,8 +1046,13 @@ static int tc_plan(const dbsr_conv_t* c, TcConfig* cfg, bool set_err, bool allow
   }
   TC_REQ(found, "conv2d_tc: activation halo box does not fit in shared memory (dilation %d)", c->dilation);
   if (want_pair && !(cfg->mt == 2 && !cfg->pair_img && !cfg->flat)) return tc_plan(c, cfg, set_err, false);   // pairs need two-tile items
+  // accumulator stages: four when they fit the 512 TMEM columns (N tile <= 64 with two-tile items), else two.  With four the
+  // issuer runs up to three items ahead of the epilogue warps -- what a CTA pair needs to hide the cross-CTA round trip of
+  // "both epilogues have drained this stage", and slack for the epilogue-bound small-N layers in general.
+  static const int max_acc_stages = getenv("DBSR_TC_ACC_STAGES") ? atoi(getenv("DBSR_TC_ACC_STAGES")) : 4;      // A/B switch
+  cfg->acc_stages = (max_acc_stages >= 4 && 4 * cfg->mt * nt <= 512) ? 4 : 2;
   int tc = 32;
-  while (tc < 2 * cfg->mt * nt) tc <<= 1;
+  while (tc < cfg->acc_stages * cfg->mt * nt) tc <<= 1;
   cfg->tmem_cols = tc;
   // residual on the tensor core: extra K chunks with identity weights (bf16 residual, aligned, same channel chunking)
   cfg->res_chunks = 0;
@@ -1236,7 +1246,7 @@ static int conv2d_tc_impl(const dbsr_conv_t* c_in, void* stream, const float* pr
   p.n = c->x.n; p.H = c->x.h; p.W = c->x.w;
   p.ksize = c->ksize; p.dil = c->dilation;
   p.nchunks = cfg.nchunks; p.cout_pad = cfg.cout_pad; p.cout = cfg.cout; p.n_tile = cfg.n_tile; p.mt = cfg.mt;
-  p.tmem_cols = cfg.tmem_cols; p.vec_ok = cfg.vec_ok; p.align_ok = cfg.align_ok;
+  p.tmem_cols = cfg.tmem_cols; p.acc_stages = cfg.acc_stages; p.vec_ok = cfg.vec_ok; p.align_ok = cfg.align_ok;
   p.ntiles_n = cfg.cout_pad / cfg.n_tile;
   p.items_x = cfg.pair_img ? 1 : ceil_div(p.W, TILE_W * cfg.mt); p.tiles_y = ceil_div(p.H, TILE_H);
   p.flat = cfg.flat; p.flat_s = cfg.flat_s; p.flat_ni = cfg.flat_ni;

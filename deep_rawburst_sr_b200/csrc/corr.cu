@@ -640,7 +640,13 @@ extern "C" int dbsr_corr81(const dbsr_nhwc_t* f1, const dbsr_nhwc_t* f2, const d
   // small maps: both maps of a pair in shared memory, outputs spread over the threads
   const int cp_small = ((f1->c + 7) & ~7) + 4;
   const size_t small_smem = (size_t)2 * f1->h * f1->w * cp_small * sizeof(float);
-  if (vec && f1->h * f1->w <= 64 && small_smem <= 160 * 1024) {
+  // bf16 maps with C in {32, 64, 96, 128}: banded product on the tensor cores (mma.sync), see corr81_mma_kernel
+  const bool mma_ok = vec && mode != DBSR_CORR_CUDA_CORES && f1->dtype == DBSR_BF16 && f1->c % 16 == 0 && f1->c >= 32 && f1->c <= 128 &&
+                      f1->c != 48 && f1->c != 80 && f1->c != 112 &&
+                      (long long)f1->h * f1->w * (f1->c_pitch > f2->c_pitch ? f1->c_pitch : f2->c_pitch) * 2 < (1ll << 31);
+  // 8x8 maps (level 3 of a 48^2 burst, level 4 of an 80^2 one) go to the tensor-core kernel when it covers them: the small-map
+  // kernel is bound by its shared-memory loads there (2 LDS per FMA: 34 us for 416 pairs of 64 channels against ~14 us)
+  if (vec && f1->h * f1->w <= 64 && small_smem <= 160 * 1024 && !(mma_ok && f1->h * f1->w >= 64)) {
     void (*ks)(const CorrParams) = f1->dtype == DBSR_BF16 ? corr81_small_kernel<__nv_bfloat16> : corr81_small_kernel<float>;
     static size_t configured_dev[MAX_DEVICES][2] = {};
     size_t* configured = configured_dev[current_device_slot()];
@@ -653,9 +659,7 @@ extern "C" int dbsr_corr81(const dbsr_nhwc_t* f1, const dbsr_nhwc_t* f2, const d
     launch_pdl(ks, dim3((unsigned)pairs), dim3(CORR_SMALL_THREADS), small_smem, (cudaStream_t)stream, p);
     return check_launch("corr81");
   }
-  // bf16 maps with C in {32, 64, 96, 128}: banded product on the tensor cores (mma.sync), see corr81_mma_kernel
-  if (vec && mode != DBSR_CORR_CUDA_CORES && f1->dtype == DBSR_BF16 && f1->c % 16 == 0 && f1->c >= 32 && f1->c <= 128 && f1->c != 48 &&
-      f1->c != 80 && f1->c != 112 && (long long)f1->h * f1->w * (f1->c_pitch > f2->c_pitch ? f1->c_pitch : f2->c_pitch) * 2 < (1ll << 31)) {
+  if (mma_ok) {
     void (*km)(const CorrParams) = nullptr;
     int smem = 0, ki = 0;
     switch (f1->c / 16) {
