@@ -980,7 +980,8 @@ static int tc_plan(const dbsr_conv_t* c, TcConfig* cfg, bool set_err, bool allow
   // drops from 4096 + 32 N to 4096 + 16 N bytes (tools/micro/mma_rate.cu: 48 -> 43 clk at N = 64) and the weight tiles take
   // half the shared memory.  Needs two-tile items of a map at least 16 pixels wide and enough of them for every pair.
   // Measured on B200 (profiles/r02_cta_pair_ab.txt): layers with >= 128 input channels (two K chunks, 144 MMAs per item) gain
-  // 5-7 %; 64-channel layers (72 MMAs per item) lose to the cross-CTA round trips per item, so pairs are used for K >= 128 only.
+  // 5-7 % (128->128 + residual 240 -> 226 us, 128->512 767 -> 716 us); 64-channel layers (72 MMAs per item) LOSE (64->64 80 -> 86 us,
+  // 64->512 412 -> 441 us): the cross-CTA round trips per item are not amortised.  So pairs are used for K >= 128 only.
   // DBSR_TC_PAIR = 0 / 1 / 2: never / K >= 128 (default) / every eligible layer (A/B switch).
   static const int pair_mode = getenv("DBSR_TC_PAIR") ? atoi(getenv("DBSR_TC_PAIR")) : 1;
   const long long tm_items2 = (long long)c->x.n * ceil_div(c->x.w, 2 * TILE_W) * ceil_div(c->x.h, TILE_H);
@@ -1046,10 +1047,10 @@ static int tc_plan(const dbsr_conv_t* c, TcConfig* cfg, bool set_err, bool allow
   }
   TC_REQ(found, "conv2d_tc: activation halo box does not fit in shared memory (dilation %d)", c->dilation);
   if (want_pair && !(cfg->mt == 2 && !cfg->pair_img && !cfg->flat)) return tc_plan(c, cfg, set_err, false);   // pairs need two-tile items
-  // accumulator stages: four when they fit the 512 TMEM columns (N tile <= 64 with two-tile items), else two.  With four the
-  // issuer runs up to three items ahead of the epilogue warps -- what a CTA pair needs to hide the cross-CTA round trip of
-  // "both epilogues have drained this stage", and slack for the epilogue-bound small-N layers in general.
-  static const int max_acc_stages = getenv("DBSR_TC_ACC_STAGES") ? atoi(getenv("DBSR_TC_ACC_STAGES")) : 4;      // A/B switch
+  // accumulator stages: two (double buffering).  DBSR_TC_ACC_STAGES=4 uses four where they fit the 512 TMEM columns (N tile
+  // <= 64 with two-tile items): measured on B200 it changes nothing -- neither single CTAs nor CTA pairs wait for a free
+  // accumulator stage (profiles/r02_cta_pair_ab.txt) -- so it stays an A/B switch.
+  static const int max_acc_stages = getenv("DBSR_TC_ACC_STAGES") ? atoi(getenv("DBSR_TC_ACC_STAGES")) : 2;
   cfg->acc_stages = (max_acc_stages >= 4 && 4 * cfg->mt * nt <= 512) ? 4 : 2;
   int tc = 32;
   while (tc < cfg->acc_stages * cfg->mt * nt) tc <<= 1;
