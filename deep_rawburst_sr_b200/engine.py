@@ -156,6 +156,20 @@ class ConvW:
             self.bias_tc = permute_shuffle_rows(bias.cpu(), shuffle_r).to(bias.device)
 
 
+def on_engine_device(fn):
+    """run a DBSREngine method with the engine's device current: the ctypes layer launches on `torch.cuda.current_stream()` of
+    the CURRENT device and the library keeps per-device caches, so a model on cuda:1 must not launch while cuda:0 is current"""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapper(self, *a, **k):
+        if torch.cuda.current_device() == (self.device.index if self.device.index is not None else torch.cuda.current_device()):
+            return fn(self, *a, **k)
+        with torch.cuda.device(self.device):
+            return fn(self, *a, **k)
+    return wrapper
+
+
 class DBSREngine:
     def __init__(self, state_dict: Dict[str, torch.Tensor], device, precision: str = 'bf16', offset_modulo: float = 1.0,
                  gauss_kernel=None, logits_fp32: bool = False, pwc_precision: Optional[str] = None,
@@ -408,6 +422,7 @@ class DBSREngine:
     # ------------------------------------------------------------------------------------------------
     # PWC-Net  (reference models/alignment/pwcnet.py)
     # ------------------------------------------------------------------------------------------------
+    @on_engine_device
     def pwc_extract(self, ws: dict, pwc_in: Optional[Act], s2d0: Optional[Act] = None) -> list:
         """Extractor pyramid (pwcnet.py:45-111) on every image of `pwc_in` [n, Hp, Wp, >=3] -- or, on the bf16 path, of
         `s2d0` [n, Hp/2, Wp/2, 12]: the same images already in the space-to-depth layout of the first stride-2 conv
@@ -442,6 +457,7 @@ class DBSREngine:
             x = f
         return feats
 
+    @on_engine_device
     def pwc_decode(self, ws: dict, first: list, second: list, pairs: int, group: int, src_group: int) -> Act:
         """Decoders 6..2 + refiner (pwcnet.py:113-231).  `first`/`second`: per-level feature Acts.  group > 0: burst
         mode (both lists are the same per-frame pyramid, frame 0 of each burst is the reference)."""
@@ -489,6 +505,7 @@ class DBSREngine:
         self._conv(f'{pre}netRefiner.netMain.12', x, flow4, ACT_NONE, dilation=1, residual=prev_flow)
         return flow4
 
+    @on_engine_device
     def pwc_burst(self, ws: dict, pwc_in: Optional[Act], B: int, N: int, H: int, W: int, offsets: torch.Tensor,
                   s2d0: Optional[Act] = None) -> torch.Tensor:
         """PWCNet.forward (pwcnet.py:248-281) for a burst batch: frame 0 of every burst is the target; the pyramid of
@@ -499,6 +516,7 @@ class DBSREngine:
         self._run('flow_head', ops.flow_head, flow4, offsets, H, W, Hp, Wp)
         return offsets
 
+    @on_engine_device
     def prep_and_align(self, ws: dict, burst: torch.Tensor, enc_in: Act, offsets: torch.Tensor) -> torch.Tensor:
         """burst [B, N, 4, H, W] fp32 -> `enc_in` (channels-last packed RAW for the encoder) and the flows `offsets`
         [B*(N-1), 2, H, W] of every frame towards frame 0 (encoders.py:52-61 + PWCNet.forward)."""
@@ -506,6 +524,7 @@ class DBSREngine:
         s2d0, pwc_in = self.prep(ws, burst, enc_in)
         return self.pwc_burst(ws, pwc_in, B, N, H, W, offsets, s2d0)
 
+    @on_engine_device
     def prep(self, ws: dict, burst: torch.Tensor, enc_in: Act):
         """burst -> `enc_in` + the PWC-Net input: (s2d0, None) on the bf16 path (RGGB->RGB + resize written straight into
         the space-to-depth layout of the extractor's first stride-2 conv), (None, pwc_in) on the fp32 path."""
@@ -523,6 +542,7 @@ class DBSREngine:
     # ------------------------------------------------------------------------------------------------
     # DBSR stages
     # ------------------------------------------------------------------------------------------------
+    @on_engine_device
     def encode(self, ws: dict, enc_in: Act, grid_limit: int = 0) -> Act:
         """conv stack of ResEncoderWarpAlignnet (reference models/dbsr/encoders.py:66-72) on all B*N frames.
         grid_limit: persistent-grid cap of these launches (per call; > 0 while PWC-Net shares the GPU on a second stream)."""
@@ -540,12 +560,14 @@ class DBSREngine:
         self._conv('encoder.out_layer.0', cur, feat, ACT_RELU, grid_limit=grid_limit)
         return feat
 
+    @on_engine_device
     def project(self, ws: dict, feat: Act, grid_limit: int = 0) -> Act:
         """q = W_p . feat (merging.py:75 without bias / ReLU, which follow the warp in `warp_proj`): depends on the
         embeddings only, so the forward runs it before joining the alignment stream"""
         q = self._buf(ws, 'proj_q', feat.n, feat.h, feat.w, self.proj_dim, self.act_dtype)
         return self._conv('merging.feat_project_layer.0', feat, q, ACT_NONE, no_bias=True, grid_limit=grid_limit)
 
+    @on_engine_device
     def merge(self, ws: dict, feat: Act, offsets: torch.Tensor, B: int, N: int,
               weights_out: Optional[torch.Tensor] = None, aligned: bool = False, projected: bool = False) -> Act:
         """WeightedSum.forward (reference models/dbsr/merging.py:61-127) with the warp of encoders.py:80 folded in.
@@ -591,6 +613,7 @@ class DBSREngine:
         self.launches += (1 if weights_out is not None else 0)
         return fused
 
+    @on_engine_device
     def decode(self, ws: dict, fused: Act, pred: torch.Tensor) -> torch.Tensor:
         """ResPixShuffleConv.forward (reference models/dbsr/decoders.py:54-62, models/layers/upsampling.py:51-66)."""
         B, H, W = fused.n, fused.h, fused.w
@@ -681,6 +704,7 @@ class DBSREngine:
     # whole forward
     # ------------------------------------------------------------------------------------------------
     @torch.no_grad()
+    @on_engine_device
     def forward(self, burst: torch.Tensor, return_weights: bool = False, out: Optional[dict] = None, quantize: bool = False):
         """DBSRNet.forward: burst [B, N, 4, H, W] fp32 CUDA -> pred [B, 3, 8H, 8W], offsets [B, N-1, 2, H, W],
         fusion_weights [B, N, C, H, W] (only when return_weights).  `out` (optional): preallocated 'pred' / 'offsets' to
@@ -741,6 +765,7 @@ class DBSREngine:
     # ------------------------------------------------------------------------------------------------
     # CUDA-graph replay of the whole forward (launch-bound at small batch: ~400 launches per forward)
     # ------------------------------------------------------------------------------------------------
+    @on_engine_device
     def graph_entry(self, shape, return_weights: bool = False, quantize: bool = False, slot: int = 0):
         """(graph, static_in, outs, launches) of the CUDA graph that runs forward() on `static_in` [B, N, 4, H, W] and leaves
         (pred, offsets, weights) in `outs`; captured on first use.  `slot` selects one of several independent graphs of the
@@ -766,6 +791,7 @@ class DBSREngine:
         return entry
 
     @torch.no_grad()
+    @on_engine_device
     def forward_graphed(self, burst: torch.Tensor, return_weights: bool = False, quantize: bool = False, slot: int = 0):
         """Same as forward(), but the launch sequence is captured once per input shape into a CUDA graph and replayed.
         The returned tensors are the graph's static outputs: they are overwritten by the next call of the same shape (and

@@ -97,6 +97,7 @@ class Network(EngineOwner, torch.nn.Module):
             self._set_engine(DBSREngine(self.state_dict(), device, precision=self.precision, pwc_prefix='', parts=('pwc',)))
         return self._engine
 
+    @ops.tensor_device_guard
     @torch.no_grad()
     def forward(self, tenFirst, tenSecond):
         """pwcnet.py:220-231: extractor pyramids of both images, decoders 6..2, refiner -> flow [P, 2, H/4, W/4] (in units of
@@ -141,6 +142,7 @@ class PWCNet(torch.nn.Module):
         self.net.precision = self.precision
         return self.net.engine(device)
 
+    @ops.tensor_device_guard
     @torch.no_grad()
     def forward(self, source_img, target_img):
         assert (source_img.shape[-1] == target_img.shape[-1])

@@ -60,6 +60,7 @@ class DBSRNet(EngineOwner, nn.Module):
                                         gauss_kernel=self.decoder.gauss_taps(), logits_fp32=self.logits_fp32))
         return self._engine
 
+    @ops.tensor_device_guard
     @torch.no_grad()
     def forward(self, im, offsets=None):
         """im [B, N, 4, H, W] -> (pred, {'offsets', 'fusion_weights'}) (reference dbsrnet.py:33-38).  `offsets` (extension,

@@ -45,6 +45,7 @@ class ResPixShuffleConv(EngineOwner, nn.Module):
                                         parts=('decoder',)))
         return self._engine
 
+    @ops.tensor_device_guard
     @torch.no_grad()
     def forward(self, x):
         feat = x['fused_enc']

@@ -38,6 +38,7 @@ class ResEncoderWarpAlignnet(EngineOwner, nn.Module):
             self._set_engine(DBSREngine(sd, device, precision=self.precision, parts=('pwc', 'encoder')))
         return self._engine
 
+    @ops.tensor_device_guard
     @torch.no_grad()
     def forward(self, x):
         assert x.dim() == 5

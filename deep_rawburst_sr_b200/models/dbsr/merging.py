@@ -57,6 +57,7 @@ class WeightedSum(EngineOwner, nn.Module):
                                         parts=('merging',)))
         return self._engine
 
+    @ops.tensor_device_guard
     @torch.no_grad()
     def forward(self, x):
         ref_feat, oth_feat, offsets = x['ref_feat'], x['oth_feat'], x['offsets']

@@ -34,6 +34,7 @@ class PixShuffleUpsampler(nn.Module):
         self.gauss_kernel = None if gauss_blur_sd is None else self._get_gaussian_kernel(gauss_ksz, gauss_blur_sd).unsqueeze(0)
         self.pix_shuffle = nn.PixelShuffle(upsample_factor)
 
+    @ops.tensor_device_guard
     @torch.no_grad()
     def forward(self, x):
         """upsampling.py:51-66 standalone (NCHW fp32 seam): 1x1 conv (+ bias) + activation with the PixelShuffle folded into the

@@ -73,8 +73,16 @@ class SpatialColorAlignment(nn.Module):
         self.alignment_net.to(device)
         self.gauss_kernel = self.gauss_kernel.to(device)
 
+    @ops.tensor_device_guard
     @torch.no_grad()
     def forward(self, pred, gt, burst_input):
+        """METRIC-ONLY (inference path): the whole alignment runs without autograd.  The reference disables gradients for the
+        flow estimate only and keeps warp / colour matching differentiable w.r.t. `pred` because `AlignedL2` is also its
+        BurstSR TRAINING loss (spatial_color_alignment.py:88-90); the backward pass is out of this tier's scope, so a
+        prediction that requires grad is refused instead of silently returning a tensor without a graph."""
+        if torch.is_tensor(pred) and pred.requires_grad:
+            raise NotImplementedError('SpatialColorAlignment / AlignedL2 of deep_rawburst_sr_b200 are metric-only (no autograd '
+                                      'through the sm_100a kernels): detach the prediction, or use the reference for training')
         ops.require_device(pred)
         # flow between the prediction and the ground truth: PWC-Net at the output resolution on the sm_100a kernels
         if getattr(self, 'per_image_norm', False):

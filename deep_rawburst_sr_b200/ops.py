@@ -19,12 +19,44 @@ def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
 
+def _first_cuda_tensor(args):
+    for a in args:
+        if torch.is_tensor(a):
+            if a.is_cuda:
+                return a
+        elif isinstance(a, dict):
+            t = _first_cuda_tensor(a.values())
+            if t is not None:
+                return t
+    return None
+
+
+def tensor_device_guard(fn):
+    """decorator of the module `forward`s: run with the device of the first CUDA tensor argument current.  Every launch of
+    this package goes to `torch.cuda.current_stream()` of the CURRENT device and the library caches per current device, so a
+    module living on cuda:1 must not run while cuda:0 is current (multi-GPU in one process, nn.DataParallel style)."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapper(*args, **kwargs):
+        t = _first_cuda_tensor(args) or _first_cuda_tensor(kwargs.values())
+        if t is None or t.device.index == torch.cuda.current_device():
+            return fn(*args, **kwargs)
+        with torch.cuda.device(t.device):
+            return fn(*args, **kwargs)
+    return wrapper
+
+
 def require_device(t: torch.Tensor) -> None:
     """Fail loudly on anything but a CUDA tensor on an sm_100 device (reference behaviour for the cost volume on
     CPU input is NotImplementedError, external/pwcnet/correlation/correlation.py:324-325)."""
     if not t.is_cuda:
         raise NotImplementedError('deep_rawburst_sr_b200 runs on CUDA (sm_100a) tensors only; there is no CPU path')
     idx = t.device.index if t.device.index is not None else torch.cuda.current_device()
+    if idx != torch.cuda.current_device():
+        raise RuntimeError(f'tensor on cuda:{idx} but cuda:{torch.cuda.current_device()} is the current device: launches of this '
+                           'package go to the current device\'s stream (run under `torch.cuda.device(tensor.device)`; the module '
+                           'forwards do that themselves)')
     if idx not in _checked_devices:
         _lib.check(_lib.load_library().dbsr_device_check(idx), 'dbsr_device_check')
         _checked_devices.add(idx)

@@ -44,6 +44,10 @@ class HostPipeline:
         return None
 
     def submit(self, host_in: torch.Tensor, host_out: torch.Tensor) -> torch.cuda.Event:
+        with torch.cuda.device(self.device):
+            return self._submit(host_in, host_out)
+
+    def _submit(self, host_in: torch.Tensor, host_out: torch.Tensor) -> torch.cuda.Event:
         """host_in: [B, N, 4, H, W] fp32 host tensor (pinned for a truly asynchronous copy); host_out: [B, 3, 8H, 8W] host
         tensor that receives `pred` -- fp32, or int16 when `net.output_int16` is set (the dtype must match the output).
         Returns the event to wait on before reading host_out."""
