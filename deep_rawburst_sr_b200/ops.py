@@ -39,7 +39,9 @@ def tensor_device_guard(fn):
 
     @functools.wraps(fn)
     def wrapper(*args, **kwargs):
-        t = _first_cuda_tensor(args) or _first_cuda_tensor(kwargs.values())
+        t = _first_cuda_tensor(args)
+        if t is None:
+            t = _first_cuda_tensor(kwargs.values())
         if t is None or t.device.index == torch.cuda.current_device():
             return fn(*args, **kwargs)
         with torch.cuda.device(t.device):
