@@ -7,8 +7,14 @@ import sys
 path = sys.argv[1]
 with open(path) as f:
     lines = [l for l in f if not l.startswith('==')]
-rows = [(x['Kernel Name'], float(x['Metric Value'].replace(',', '')), x.get('Grid Size', ''))
-        for x in csv.DictReader(lines)]
+def _us(x):      # gpu__time_duration.sum in the CSV's unit -> ns (the table below prints us)
+    v = float(x['Metric Value'].replace(',', ''))
+    return v * {'ns': 1.0, 'nsecond': 1.0, 'us': 1e3, 'usecond': 1e3, 'ms': 1e6, 'msecond': 1e6}.get(x.get('Metric Unit', 'ns'), 1.0)
+
+
+# a CSV may carry several metrics per launch (tools/gpu_r2_profiles.sh adds the DRAM byte counters): keep the durations
+rows = [(x['Kernel Name'], _us(x), x.get('Grid Size', ''))
+        for x in csv.DictReader(lines) if x.get('Metric Name', 'gpu__time_duration.sum') == 'gpu__time_duration.sum']
 starts = [i for i, x in enumerate(rows) if 'prep_burst' in x[0]]
 fw = rows[starts[-1]:]
 out = []
