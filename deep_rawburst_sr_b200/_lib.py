@@ -29,7 +29,7 @@ class ConvDesc(ctypes.Structure):
     _fields_ = [('x', NhwcView), ('y', NhwcView), ('residual', NhwcView), ('w', ctypes.c_void_p),
                 ('bias', ctypes.c_void_p), ('ksize', ctypes.c_int32), ('stride', ctypes.c_int32),
                 ('dilation', ctypes.c_int32), ('act', ctypes.c_int32), ('shuffle_r', ctypes.c_int32),
-                ('grid_limit', ctypes.c_int32)]
+                ('grid_limit', ctypes.c_int32), ('residual_group', ctypes.c_int32)]
 
 
 class ResBlockDesc(ctypes.Structure):
@@ -75,6 +75,7 @@ PROTOTYPES = {
     'dbsr_offsets_mod': (_I, [_VP, _PV, _I, _I, _F, _VP]),
     'dbsr_build_wp_input': (_I, [_PV, _PV, _I, _VP]),
     'dbsr_warp_proj': (_I, [_PV, _VP, _VP, _PV, _I, _VP]),
+    'dbsr_warp_proj_split': (_I, [_PV, _VP, _VP, _PV, _PV, _I, _VP]),
     'dbsr_softmax_wsum': (_I, [_PV, _PV, _VP, _PV, _VP, _I, _VP]),
     'dbsr_blur3x3': (_I, [_PV, _PV, ctypes.POINTER(ctypes.c_float), _VP]),
     'dbsr_predictor': (_I, [_PV, _VP, _VP, _I, _VP, _VP]),

@@ -194,6 +194,7 @@ extern "C" int dbsr_conv2d_direct(const dbsr_conv_t* c, void* stream) {
   DBSR_REQUIRE(c != nullptr, "conv2d_direct: null descriptor");
   DBSR_REQUIRE(view_ok(&c->x) && view_ok(&c->y), "conv2d_direct: bad x/y view");
   DBSR_REQUIRE(c->w != nullptr, "conv2d_direct: null weights");
+  DBSR_REQUIRE(c->residual_group <= 1, "conv2d_direct: residual_group is a feature of the tensor-core path");
   DBSR_REQUIRE(c->ksize == 1 || c->ksize == 3, "conv2d_direct: ksize %d unsupported", c->ksize);
   DBSR_REQUIRE(c->stride >= 1 && c->dilation >= 1, "conv2d_direct: bad stride/dilation");
   ConvDirectParams p;

@@ -67,6 +67,7 @@ struct ConvTcParams {
   int halo_w;           // pixels per row of the A box
   int res_chunks;       // > 0: the residual is accumulated on the tensor core as res_chunks extra K chunks (identity weights)
   int r_tx_bytes;       // bytes of one residual box {CK, 8*mt px, 16 rows}
+  int res_group;        // >= 1: output image i takes residual image i / res_group (a per-burst map broadcast over the frames)
   int flat;             // small-map mode: the A box holds flat_ni whole zero-bordered images, M rows = flat slots
   int flat_s, flat_ni;  // slots per image (H+2)*(W+2); images per M tile
   // second M tile of an item (mt == 2): offset of its A rows inside the box (16-byte units), image and column offset.
@@ -509,10 +510,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
           mbar_wait(&a_empty[slot], phase ^ 1, 120 + slot);
           if (PAIR) {
             if (pair_rank == 0) mbar_arrive_expect_tx(&a_full[slot], 2u * (uint32_t)p.r_tx_bytes);
-            tma_load_4d_pair(&tmap_r, &a_full[slot], smem_a + (size_t)slot * p.a_bytes, c.nt * NT + rc * CK, c.x0, c.y0, c.img);
+            tma_load_4d_pair(&tmap_r, &a_full[slot], smem_a + (size_t)slot * p.a_bytes, c.nt * NT + rc * CK, c.x0, c.y0, c.img / p.res_group);
           } else {
             mbar_arrive_expect_tx(&a_full[slot], (uint32_t)p.r_tx_bytes);
-            tma_load_4d(&tmap_r, &a_full[slot], smem_a + (size_t)slot * p.a_bytes, c.nt * NT + rc * CK, c.x0, c.y0, c.img);
+            tma_load_4d(&tmap_r, &a_full[slot], smem_a + (size_t)slot * p.a_bytes, c.nt * NT + rc * CK, c.x0, c.y0, c.img / p.res_group);
           }
           if (++slot == p.a_slots) { slot = 0; phase ^= 1; }
         }
@@ -956,9 +957,10 @@ static int tc_plan(const dbsr_conv_t* c, TcConfig* cfg, bool set_err, bool allow
   // fast path: no channel padding (every accumulator chunk lies inside cout) and 16-byte aligned rows
   bool vec = ((c->y.c_off * yes) % 16) == 0 && ((c->y.c_pitch * yes) % 16) == 0 && ((uintptr_t)c->y.data % 16) == 0;
   if (c->residual.data) {
-    TC_REQ(r == 1 && view_ok(&c->residual) && c->residual.n == c->y.n && c->residual.h == c->y.h &&
+    const int rg = c->residual_group > 1 ? c->residual_group : 1;
+    TC_REQ(r == 1 && view_ok(&c->residual) && (long long)c->residual.n * rg >= c->y.n && c->residual.h == c->y.h &&
                c->residual.w == c->y.w && c->residual.c == c->y.c,
-           "conv2d_tc: residual must have the geometry of y");
+           "conv2d_tc: residual must have the geometry of y (residual_group images of y per residual image)");
     vec = vec && c->residual.dtype == DBSR_BF16 && (c->residual.c_off % 8) == 0 && (c->residual.c_pitch % 8) == 0 &&
           ((uintptr_t)c->residual.data % 16) == 0;
   }
@@ -1063,6 +1065,9 @@ static int tc_plan(const dbsr_conv_t* c, TcConfig* cfg, bool set_err, bool allow
     cfg->res_chunks = nt / ck;       // N tile 64 takes the residual in the (prefetching) lean epilogue instead: there the extra
                                      // K chunk costs a whole halo slot of the A ring; at N = 32 the epilogue is the bottleneck and at
                                      // N = 128 the staging area holds half a pixel row, so both keep the tensor-core residual
+  // a broadcast residual (one map per group of output images) exists on the tensor-core residual path only
+  TC_REQ(!(c->residual.data && c->residual_group > 1) || cfg->res_chunks > 0,
+         "conv2d_tc: residual_group needs the tensor-core residual (bf16, 16-byte aligned, N tile 32 or 128)");
   const int b_total = (cfg->nchunks * taps + cfg->res_chunks) * cfg->b_bytes;
   if (cpad == nt && cfg->a_slots * cfg->a_bytes + b_total <= budget && cfg->nchunks * taps + cfg->res_chunks <= 64) {
     cfg->b_resident = 1;
@@ -1283,6 +1288,7 @@ static int conv2d_tc_impl(const dbsr_conv_t* c_in, void* stream, const float* pr
   p.yH = c->y.h; p.yW = c->y.w;
   p.res = c->residual.data; p.r_dtype = c->residual.dtype; p.r_pitch = c->residual.c_pitch; p.r_coff = c->residual.c_off;
   p.res_chunks = cfg.res_chunks;
+  p.res_group = c->residual_group > 1 ? c->residual_group : 1;
   p.r_tx_bytes = TILE_H * TILE_W * cfg.mt * cfg.ck * 2;
   if (cfg.res_chunks > 0) p.res = nullptr;   // accumulated by the MMAs, nothing left for the epilogue
   p.bias = c->bias; p.act = c->act; p.shuffle_r = r;

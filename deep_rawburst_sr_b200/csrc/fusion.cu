@@ -246,9 +246,11 @@ __device__ __forceinline__ Vec8 gather8(const T* img_base, int c_pitch, const Ta
 // ---------------------------------------------------------------------------------------------------------
 // Grid: x covers (pixel, 8-channel group) of one frame in 32-bit arithmetic, y walks the frames (the first version
 // decoded a 64-bit linear index with three 64-bit divisions per thread and was instruction bound at 2.1 TB/s).
-template <typename TQ, typename TO>
+// SPLIT: the weight predictor's first conv is split into a per-frame and a per-burst part (engine.merge): this kernel then
+// writes wp_in[:, 0:C] = p_n for every frame and the base frame's p_0 once per burst into `p0out` [bursts, H, W, C].
+template <typename TQ, typename TO, bool SPLIT>
 __global__ void __launch_bounds__(256)
-warp_proj_kernel(View q, const float* __restrict__ bias, const float* __restrict__ offsets, View wp_in, int frames) {
+warp_proj_kernel(View q, const float* __restrict__ bias, const float* __restrict__ offsets, View wp_in, int frames, View p0out) {
   griddep_wait();
   const int H = q.h, W = q.w, C = q.c, C8 = C >> 3;
   const int HW = H * W;
@@ -263,6 +265,23 @@ warp_proj_kernel(View q, const float* __restrict__ bias, const float* __restrict
   for (int f = blockIdx.y; f < q.n; f += gridDim.y) {
     const int b = f / frames, n = f - b * frames;
     const long long pix = (long long)f * HW + rem;
+    if (SPLIT) {
+      Vec8 pn;
+      if (n > 0 && offsets != nullptr) {
+        const long long pr = (long long)b * (frames - 1) + (n - 1);
+        const float fx = __ldg(offsets + (pr * 2 + 0) * HW + rem);
+        const float fy = __ldg(offsets + (pr * 2 + 1) * HW + rem);
+        const Taps t = make_taps((float)x + fx, (float)y + fy, H, W);
+        pn = gather8<TQ>(qbase + (long long)f * HW * q.c_pitch, q.c_pitch, t, ch);
+      } else {
+        pn = ld8<TQ>(qbase + pix * q.c_pitch + ch);
+      }
+#pragma unroll
+      for (int k = 0; k < 8; ++k) pn.v[k] = fmaxf(pn.v[k] + bv.v[k], 0.0f);
+      st8<TO>(obase + pix * wp_in.c_pitch + ch, pn);
+      if (n == 0) st8<TO>(reinterpret_cast<TO*>(p0out.data) + p0out.c_off + ((long long)b * HW + rem) * p0out.c_pitch + ch, pn);
+      continue;
+    }
     Vec8 p0 = ld8<TQ>(qbase + ((long long)b * frames * HW + rem) * q.c_pitch + ch);
 #pragma unroll
     for (int k = 0; k < 8; ++k) p0.v[k] = fmaxf(p0.v[k] + bv.v[k], 0.0f);
@@ -928,9 +947,26 @@ extern "C" int dbsr_warp_proj(const dbsr_nhwc_t* q, const float* bias, const flo
   DBSR_REQUIRE(per_frame < (1ll << 31), "warp_proj: more than 2^31 (pixel, channel group) items per frame");
   const dim3 g((unsigned)ceil_div(per_frame, 256), (unsigned)(q->n < 65535 ? q->n : 65535));
   cudaStream_t st = (cudaStream_t)stream;
-  if (q->dtype == DBSR_F32) launch_pdl(warp_proj_kernel<float, float>, dim3(g), dim3(256), 0, st, make_view(q), bias, offsets, make_view(wp_in), frames);
-  else launch_pdl(warp_proj_kernel<__nv_bfloat16, __nv_bfloat16>, dim3(g), dim3(256), 0, st, make_view(q), bias, offsets, make_view(wp_in), frames);
+  const View none = make_view(nullptr);
+  if (q->dtype == DBSR_F32) launch_pdl(warp_proj_kernel<float, float, false>, dim3(g), dim3(256), 0, st, make_view(q), bias, offsets, make_view(wp_in), frames, none);
+  else launch_pdl(warp_proj_kernel<__nv_bfloat16, __nv_bfloat16, false>, dim3(g), dim3(256), 0, st, make_view(q), bias, offsets, make_view(wp_in), frames, none);
   return check_launch("warp_proj");
+}
+
+extern "C" int dbsr_warp_proj_split(const dbsr_nhwc_t* q, const float* bias, const float* offsets, const dbsr_nhwc_t* wp_in,
+                                    const dbsr_nhwc_t* p0, int32_t frames, void* stream) {
+  DBSR_REQUIRE(view_ok(q) && view_ok(wp_in) && view_ok(p0) && bias && frames >= 2, "warp_proj_split: bad arguments");
+  DBSR_REQUIRE(q->n == wp_in->n && q->h == wp_in->h && q->w == wp_in->w && wp_in->c >= q->c && q->n % frames == 0 &&
+                   p0->n == q->n / frames && p0->h == q->h && p0->w == q->w && p0->c == q->c, "warp_proj_split: geometry mismatch");
+  DBSR_REQUIRE(vec8_ok(q) && vec8_ok(wp_in) && vec8_ok(p0) && ((uintptr_t)bias % 16) == 0 && q->dtype == wp_in->dtype &&
+                   q->dtype == p0->dtype, "warp_proj_split: channels must be multiples of 8, 16-byte aligned, same dtype in and out");
+  const long long per_frame = (long long)q->h * q->w * (q->c / 8);
+  DBSR_REQUIRE(per_frame < (1ll << 31), "warp_proj_split: more than 2^31 (pixel, channel group) items per frame");
+  const dim3 g((unsigned)ceil_div(per_frame, 256), (unsigned)(q->n < 65535 ? q->n : 65535));
+  cudaStream_t st = (cudaStream_t)stream;
+  if (q->dtype == DBSR_F32) launch_pdl(warp_proj_kernel<float, float, true>, dim3(g), dim3(256), 0, st, make_view(q), bias, offsets, make_view(wp_in), frames, make_view(p0));
+  else launch_pdl(warp_proj_kernel<__nv_bfloat16, __nv_bfloat16, true>, dim3(g), dim3(256), 0, st, make_view(q), bias, offsets, make_view(wp_in), frames, make_view(p0));
+  return check_launch("warp_proj_split");
 }
 
 extern "C" int dbsr_blur3x3(const dbsr_nhwc_t* x, const dbsr_nhwc_t* y, const float* k9, void* stream) {

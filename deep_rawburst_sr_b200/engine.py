@@ -224,8 +224,8 @@ class DBSREngine:
     # ------------------------------------------------------------------------------------------------
     # weight packing
     # ------------------------------------------------------------------------------------------------
-    def _add(self, key, w, b, tc=False, chmap=None, cin_buf=None, shuffle_r=0):
-        direct = pack_direct(w, chmap, cin_buf, self.device)
+    def _add(self, key, w, b, tc=False, chmap=None, cin_buf=None, shuffle_r=0, direct_too=True):
+        direct = pack_direct(w, chmap, cin_buf, self.device) if direct_too else None
         tcw = pack_tc(w, shuffle_r, chmap, cin_buf, self.device) if tc else None
         self.W[key] = ConvW(direct, tcw, None if b is None else b.float().contiguous().to(self.device), w.shape[2], w.shape[0],
                              w.shape[1], shuffle_r)
@@ -293,6 +293,20 @@ class DBSREngine:
                 add(f'merging.weight_predictor.{i + 1}.conv2.0')
             add(f'merging.weight_predictor.{self.wp_res + 1}.0')
             self.proj_dim = sd['merging.feat_project_layer.0.weight'].shape[0]
+            # The first conv of the weight predictor sees [p_0 | p_n - p_0 | e_n] (merging.py:108-112).  It is linear, so
+            #   W [p_0 | p_n - p_0 | e_n] = W_d p_n + W_o e_n + (W_b - W_d) p_0 :
+            # the last term depends on the burst only.  On the tensor-core path it is computed ONCE per burst (a 64 -> 128 conv
+            # over B maps instead of B * N) and added as a broadcast residual; the per-frame conv contracts 128 instead of 192
+            # channels and the warp kernel writes p_n only (no replicated p_0, no difference).
+            pd_ = self.proj_dim
+            w0 = sd['merging.weight_predictor.0.0.weight']
+            self.split_wp0 = bool(self.bf16 and w0.shape[1] == 2 * pd_ + sd['merging.offset_feat_extractor.0.0.weight'].shape[0]
+                                  and os.environ.get('DBSR_NO_SPLIT_WP0') is None)
+            if self.split_wp0:
+                self._add('merging.weight_predictor.0.0.frame', torch.cat([w0[:, pd_:2 * pd_], w0[:, 2 * pd_:]], dim=1).contiguous(),
+                          None, tc=True, direct_too=False)
+                self._add('merging.weight_predictor.0.0.burst', (w0[:, :pd_] - w0[:, pd_:2 * pd_]).contiguous(),
+                          sd['merging.weight_predictor.0.0.bias'], tc=True, direct_too=False)
             self.offf_dim = sd['merging.offset_feat_extractor.0.0.weight'].shape[0]
             self.wp_dim = sd['merging.weight_predictor.0.0.weight'].shape[0]
             self.feat_dim = sd['merging.feat_project_layer.0.weight'].shape[1]
@@ -325,21 +339,24 @@ class DBSREngine:
     # ------------------------------------------------------------------------------------------------
     def _conv(self, key: str, x: Act, y: Act, act: int, stride: int = 1, dilation: int = 1,
               residual: Optional[Act] = None, force_direct: bool = False, no_bias: bool = False,
-              real_cin: Optional[int] = None, pred: Optional[torch.Tensor] = None, grid_limit: int = 0) -> Act:
+              real_cin: Optional[int] = None, pred: Optional[torch.Tensor] = None, grid_limit: int = 0,
+              residual_group: int = 0) -> Act:
         cw = self.W[key]
         cin_alg = cw.cin if real_cin is None else real_cin       # algorithmic input channels for the FLOP count
         bias, bias_tc = (None, None) if no_bias else (cw.bias, cw.bias_tc)
         use_tc = (cw.tc is not None and not force_direct and x.dtype == torch.bfloat16 and stride == 1)
         if use_tc:
-            use_tc = ops.conv2d_tc_supported(x, cw.tc, bias_tc, y, cw.ksize, stride, dilation, residual, cw.shuffle_r)
+            use_tc = ops.conv2d_tc_supported(x, cw.tc, bias_tc, y, cw.ksize, stride, dilation, residual, cw.shuffle_r,
+                                             residual_group)
+        assert use_tc or residual_group <= 1, 'a broadcast residual exists on the tensor-core path only'
         self.launches += 1
         fam = 'conv_tc' if use_tc else 'conv_direct'
         ho, wo = (y.h, y.w) if cw.shuffle_r <= 1 else (y.h // cw.shuffle_r, y.w // cw.shuffle_r)
         self.flops[fam] = self.flops.get(fam, 0) + 2 * x.n * ho * wo * cw.cout * cin_alg * cw.ksize * cw.ksize
         es_in, es_out = x.buf.element_size(), y.buf.element_size()
         nbytes = x.n * x.h * x.w * cin_alg * es_in + y.n * y.h * y.w * y.c * es_out
-        if residual is not None:
-            nbytes += residual.n * residual.h * residual.w * residual.c * residual.buf.element_size()
+        if residual is not None:     # (a broadcast residual is still read once per output tile: count it per output image)
+            nbytes += y.n * residual.h * residual.w * residual.c * residual.buf.element_size()
         if pred is not None:     # the output map is replaced by the fp32 prediction
             nbytes += pred.numel() * 4 - y.n * y.h * y.w * y.c * es_out
         self.hbm_bytes[fam] = self.hbm_bytes.get(fam, 0) + nbytes
@@ -354,7 +371,7 @@ class DBSREngine:
                                     grid_limit=grid_limit)
         elif use_tc:
             ops.conv2d(x, cw.tc, bias_tc, y, cw.ksize, stride, dilation, act, residual, cw.shuffle_r, tensor_core=True,
-                       grid_limit=grid_limit)
+                       grid_limit=grid_limit, residual_group=residual_group)
         else:
             ops.conv2d(x, cw.direct, bias, y, cw.ksize, stride, dilation, act, residual, cw.shuffle_r)
         self._toc(ev)
@@ -582,8 +599,16 @@ class DBSREngine:
         q = self._buf(ws, 'proj_q', F_, H, W, pd, dt)
         if not projected:
             self.project(ws, feat)
-        wp_in = self._buf(ws, 'wp_in', F_, H, W, 2 * pd + od, dt)
-        self._run('warp_proj', ops.warp_proj, q, self.W['merging.feat_project_layer.0'].bias, wp_in, N, gather)
+        split = getattr(self, 'split_wp0', False)
+        if split:
+            wp_in = self._buf(ws, 'wp_in_split', F_, H, W, pd + od, dt)        # [p_n | e_n]
+            p0 = self._buf(ws, 'proj_p0', B, H, W, pd, dt)
+            self._run('warp_proj', ops.warp_proj_split, q, self.W['merging.feat_project_layer.0'].bias, wp_in, p0, N, gather)
+            e_off = pd
+        else:
+            wp_in = self._buf(ws, 'wp_in', F_, H, W, 2 * pd + od, dt)          # [p_0 | p_n - p_0 | e_n]
+            self._run('warp_proj', ops.warp_proj, q, self.W['merging.feat_project_layer.0'].bias, wp_in, N, gather)
+            e_off = 2 * pd
         offm = self._buf(ws, 'offm', F_, H, W, 8, dt)
         self._run('offsets_mod', ops.offsets_mod, offsets, offm, B, N, self.offset_modulo)
         oa = self._buf(ws, 'off_a', F_, H, W, od, dt)
@@ -593,15 +618,20 @@ class DBSREngine:
         cur, nxt = oa, ob
         for i in range(self.off_res):
             last = i == self.off_res - 1
-            dst = wp_in.slice(2 * pd, od) if last else nxt
+            dst = wp_in.slice(e_off, od) if last else nxt
             self._resblock(f'merging.offset_feat_extractor.{i + 1}', cur, ot, dst)
             cur, nxt = dst, cur
         if self.off_res == 0:
-            self._run('copy', ops.copy_channels, oa, wp_in.slice(2 * pd, od))
+            self._run('copy', ops.copy_channels, oa, wp_in.slice(e_off, od))
         wa = self._buf(ws, 'wp_a', F_, H, W, wd, dt)
         wb = self._buf(ws, 'wp_b', F_, H, W, wd, dt)
         wt = self._buf(ws, 'wp_t', F_, H, W, wd, dt)
-        self._conv('merging.weight_predictor.0.0', wp_in, wa, ACT_RELU)
+        if split:
+            base = self._buf(ws, 'wp_base', B, H, W, wd, dt)                   # (W_b - W_d) p_0 + bias, one map per burst
+            self._conv('merging.weight_predictor.0.0.burst', p0, base, ACT_NONE)
+            self._conv('merging.weight_predictor.0.0.frame', wp_in, wa, ACT_RELU, residual=base, residual_group=N)
+        else:
+            self._conv('merging.weight_predictor.0.0', wp_in, wa, ACT_RELU)
         cur, nxt = wa, wb
         for i in range(self.wp_res):
             self._resblock(f'merging.weight_predictor.{i + 1}', cur, wt, nxt)

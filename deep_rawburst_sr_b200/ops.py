@@ -119,10 +119,11 @@ def _ptr(t: Optional[torch.Tensor]):
 
 def conv2d(x: Act, w: torch.Tensor, bias: Optional[torch.Tensor], y: Act, ksize: int, stride: int = 1, dilation: int = 1,
            act: int = ACT_NONE, residual: Optional[Act] = None, shuffle_r: int = 0, tensor_core: bool = False,
-           grid_limit: int = 0) -> Act:
-    """grid_limit (tensor-core path): cap of the persistent grid of THIS launch, 0 = one CTA per SM"""
+           grid_limit: int = 0, residual_group: int = 0) -> Act:
+    """grid_limit (tensor-core path): cap of the persistent grid of THIS launch, 0 = one CTA per SM.
+    residual_group g > 1 (tensor-core path): output image i adds residual image i // g (a per-burst map broadcast over frames)"""
     d = ConvDesc(x.view(), y.view(), residual.view() if residual is not None else _NULL_VIEW, w.data_ptr(),
-                 _ptr(bias), ksize, stride, dilation, act, shuffle_r, int(grid_limit))
+                 _ptr(bias), ksize, stride, dilation, act, shuffle_r, int(grid_limit), int(residual_group))
     lib = _lib.load_library()
     if tensor_core:
         _lib.check(lib.dbsr_conv2d_tc(ctypes.byref(d), _stream()), 'dbsr_conv2d_tc')
@@ -147,7 +148,7 @@ def conv2d_tc_predictor(x: Act, w: torch.Tensor, bias: Optional[torch.Tensor], y
     assert len(pred_w) == k * y.c
     assert pred.dtype in (torch.float32, torch.int16) and pred.is_contiguous() and tuple(pred.shape) == (x.n, k, x.h, x.w)
     d = ConvDesc(x.view(), y.view(), residual.view() if residual is not None else _NULL_VIEW, w.data_ptr(),
-                 _ptr(bias), ksize, 1, 1, act, 0, int(grid_limit))
+                 _ptr(bias), ksize, 1, 1, act, 0, int(grid_limit), 0)
     _lib.check(_lib.load_library().dbsr_conv2d_tc_predictor(ctypes.byref(d), ctypes.cast(pred_w, ctypes.c_void_p),
                                                             ctypes.cast(pred_b, ctypes.c_void_p), k, pred.data_ptr(),
                                                             1 if pred.dtype == torch.int16 else 0, _stream()),
@@ -210,9 +211,9 @@ def quantize_q14(src: torch.Tensor, dst: torch.Tensor) -> torch.Tensor:
 
 
 def conv2d_tc_supported(x: Act, w: torch.Tensor, bias, y: Act, ksize: int, stride: int = 1, dilation: int = 1,
-                        residual: Optional[Act] = None, shuffle_r: int = 0) -> bool:
+                        residual: Optional[Act] = None, shuffle_r: int = 0, residual_group: int = 0) -> bool:
     d = ConvDesc(x.view(), y.view(), residual.view() if residual is not None else _NULL_VIEW, w.data_ptr(),
-                 _ptr(bias), ksize, stride, dilation, 0, shuffle_r, 0)
+                 _ptr(bias), ksize, stride, dilation, 0, shuffle_r, 0, int(residual_group))
     return bool(_lib.load_library().dbsr_conv2d_tc_supported(ctypes.byref(d)))
 
 
@@ -326,6 +327,16 @@ def warp_proj(q: Act, bias: torch.Tensor, wp_in: Act, frames: int, offsets: Opti
     qv, wv = q.view(), wp_in.view()
     _lib.check(_lib.load_library().dbsr_warp_proj(ctypes.byref(qv), bias.data_ptr(), _ptr(offsets), ctypes.byref(wv),
                                                   frames, _stream()), 'dbsr_warp_proj')
+    return wp_in
+
+
+def warp_proj_split(q: Act, bias: torch.Tensor, wp_in: Act, p0: Act, frames: int, offsets: Optional[torch.Tensor] = None) -> Act:
+    """wp_in[:, 0:C] = p_n = relu(warp(q_n) + bias) for every frame, p0[b] = p_0 of every burst (split weight predictor input)"""
+    if offsets is not None:
+        assert offsets.dtype == torch.float32 and offsets.is_contiguous()
+    qv, wv, pv = q.view(), wp_in.view(), p0.view()
+    _lib.check(_lib.load_library().dbsr_warp_proj_split(ctypes.byref(qv), bias.data_ptr(), _ptr(offsets), ctypes.byref(wv),
+                                                        ctypes.byref(pv), frames, _stream()), 'dbsr_warp_proj_split')
     return wp_in
 
 

@@ -95,6 +95,9 @@ typedef struct dbsr_conv {
   int32_t shuffle_r;         /* 0/1: plain; 8: pixel-shuffle scatter                                */
   int32_t grid_limit;        /* dbsr_conv2d_tc*: cap of the persistent grid (CTAs); 0 = one per SM.  Per call, so
                                 that concurrent engines / devices never share launch state.                */
+  int32_t residual_group;    /* dbsr_conv2d_tc: 0 / 1: residual image i belongs to output image i; g > 1: output image i
+                                takes residual image i / g (one map per burst broadcast over its g frames: the
+                                per-burst term of the fusion weight predictor's first conv, merging.py:108-112)  */
 } dbsr_conv_t;
 int dbsr_conv2d_direct(const dbsr_conv_t* p, void* stream);
 
@@ -216,6 +219,12 @@ int dbsr_build_wp_input(const dbsr_nhwc_t* proj, const dbsr_nhwc_t* wp_in, int32
  * offsets == NULL: q is already aligned (WeightedSum called on pre-warped embeddings).                           */
 int dbsr_warp_proj(const dbsr_nhwc_t* q, const float* bias, const float* offsets, const dbsr_nhwc_t* wp_in,
                    int32_t frames, void* stream);
+/* The same with the weight predictor's first convolution SPLIT into a per-frame and a per-burst part:
+ *   W [p_0 | p_n - p_0 | e_n] = W_d p_n + W_o e_n + (W_b - W_d) p_0      (merging.py:108-112: the last term is per burst)
+ * so this form writes wp_in[:, 0:C] = p_n for every frame (frame 0: p_0) and p0[b] = p_0 of every burst ([B, H, W, C]); the
+ * engine convolves p0 once per burst and adds the result as a broadcast residual (dbsr_conv_t.residual_group).          */
+int dbsr_warp_proj_split(const dbsr_nhwc_t* q, const float* bias, const float* offsets, const dbsr_nhwc_t* wp_in,
+                         const dbsr_nhwc_t* p0, int32_t frames, void* stream);
 /* merging.py:117-124 fused with the warp: fused[b] = sum_n softmax_n(logits[b,n]) * A[b,n] where
  *   A[b,0] = feat[b*N], A[b,n>0] = bilinear(feat[b*N+n], (x,y) + offsets[b*(N-1)+n-1]) gathered on the fly
  *   (offsets == NULL: `feat` already holds the aligned maps).  weights_out (optional, may be NULL):

@@ -152,6 +152,35 @@ def test_conv2d_tc_fused_predictor(n, h, w, use_res, k):
     assert (ya.buf == 5.0).all()        # the conv's output map is not written in this mode
 
 
+@pytest.mark.parametrize('bursts,frames,h,w', [(3, 5, 24, 40), (48, 14, 48, 48)])
+def test_conv2d_tc_broadcast_residual(bursts, frames, h, w):
+    """dbsr_conv_t.residual_group: output image i adds residual image i // group -- one map per burst broadcast over its
+    frames (the per-burst term of the split weight-predictor conv), accumulated on the tensor core; single CTAs (small case)
+    and CTA pairs (672 images)"""
+    if not torch.cuda.is_available():
+        pytest.skip('needs a CUDA device')
+    from deep_rawburst_sr_b200 import ops
+    from deep_rawburst_sr_b200.engine import pack_tc
+    dev = torch.device('cuda:0')
+    g = torch.Generator().manual_seed(bursts * 100 + frames)
+    n = bursts * frames
+    x = torch.randn(n, 128, h, w, generator=g).bfloat16().float()
+    wt = (torch.randn(128, 128, 3, 3, generator=g) / (128 * 9) ** 0.5).bfloat16().float()
+    res = torch.randn(bursts, 128, h, w, generator=g).bfloat16().float()
+    xa = ops.Act.empty(n, h, w, 128, torch.bfloat16, dev).from_nchw(x.to(dev))
+    ra = ops.Act.empty(bursts, h, w, 128, torch.bfloat16, dev).from_nchw(res.to(dev))
+    ya = ops.Act.empty(n, h, w, 128, torch.bfloat16, dev)
+    wp = pack_tc(wt.to(dev))
+    assert ops.conv2d_tc_supported(xa, wp, None, ya, 3, 1, 1, ra, 0, residual_group=frames)
+    ops.conv2d(xa, wp, None, ya, 3, 1, 1, ops.ACT_RELU, ra, 0, tensor_core=True, residual_group=frames)
+    torch.cuda.synchronize()
+    got = ya.to_nchw().cpu()
+    for b in (0, bursts // 2, bursts - 1):          # the CPU reference of a few bursts is enough
+        sl = slice(b * frames, (b + 1) * frames)
+        ref = torch.relu(F.conv2d(x[sl], wt, padding=1) + res[b:b + 1])
+        assert (got[sl] - ref).abs().max().item() <= max(1.0, ref.abs().max().item()) * 2.0 ** -8, b
+
+
 @pytest.mark.parametrize('n,h,w,with_pred', [(2, 48, 48, False), (1, 16, 24, False), (3, 37, 53, False), (1, 80, 20, False),
                                              (2, 5, 7, False), (2, 48, 48, True), (1, 33, 50, True), (5, 64, 96, False)])
 def test_resblock32_fused(n, h, w, with_pred):
