@@ -61,7 +61,8 @@ struct ConvTcParams {
   // exact division by multiply-high for item -> (N tile, image, tile row, tile column): q = umulhi(n, mul) + (n & one)
   // (host proves exactness for every n < total_items, else fastdiv = 0 and the kernel divides)
   unsigned md_nt, md_img, md_x, one_nt, one_img, one_x; int fastdiv;
-  int bias_smem;        // bias table of cout_pad floats staged in shared memory (lean epilogue)
+  int bias_smem;        // the lean epilogue may run: its bias table (cout_pad floats) fits shared memory, or there is no bias at all
+  int bias_fill;        // the table fits and is filled (zeros without a bias)
   int a_slots, b_stages, b_resident;
   int a_bytes, a_tx_bytes, b_bytes;
   int halo_w;           // pixels per row of the A box
@@ -480,7 +481,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
   // while the preceding kernel of the stream is still draining; all global-memory traffic (activations, residual, y,
   // and -- because a caller may have produced them just before -- weights and bias) comes after this wait.
   griddep_wait();
-  if (p.bias_smem && warp < 8)
+  if (p.bias_fill && warp < 8)
     for (int i = threadIdx.x; i < p.cout_pad; i += 256) bias_tab[i] = p.bias ? __ldg(p.bias + i) : 0.0f;
   tc_fence_before();
   __syncthreads();
@@ -1281,7 +1282,11 @@ static int conv2d_tc_impl(const dbsr_conv_t* c_in, void* stream, const float* pr
     const unsigned long long nmax = (unsigned long long)(p.total_items > tm_items + 2 ? p.total_items : tm_items + 2);   // pairs decode tile indices up to tm_items + 1
     p.fastdiv = (nmax * dmax < (1ULL << 32)) ? 1 : 0;
   }
-  p.bias_smem = (cfg.cout_pad * 4 <= BIAS_TAB_BYTES) ? 1 : 0;
+  // the lean (coalesced, TMA-store) epilogue reads its bias from a shared-memory table.  A layer WITHOUT bias needs no table
+  // however wide it is: the decoder's 64 -> 2048 upsampling conv (no bias under ICNR init) fell back to the per-thread
+  // store path in round 1 because its 8 KB table did not fit (146 us; ncu: predicated STG.E.128 at the top of the stall list).
+  p.bias_fill = (cfg.cout_pad * 4 <= BIAS_TAB_BYTES) ? 1 : 0;
+  p.bias_smem = (p.bias_fill || c->bias == nullptr) ? 1 : 0;
   p.a_slots = cfg.a_slots; p.b_stages = cfg.b_stages; p.b_resident = cfg.b_resident;
   p.a_bytes = cfg.a_bytes; p.a_tx_bytes = cfg.a_tx_bytes; p.b_bytes = cfg.b_bytes; p.halo_w = cfg.halo_w;
   p.y = c->y.data; p.y_dtype = c->y.dtype; p.y_pitch = c->y.c_pitch; p.y_coff = c->y.c_off;
@@ -1296,7 +1301,7 @@ static int conv2d_tc_impl(const dbsr_conv_t* c_in, void* stream, const float* pr
   memset(p.pred_wb, 0, sizeof(p.pred_wb));
   if (pred != nullptr) {
     DBSR_REQUIRE(pred_w && pred_b && pred_c >= 1 && pred_c <= 4 && cfg.n_tile == 32 && cfg.cout_pad == 32 && !cfg.flat &&
-                     r == 1 && p.bias_smem && (cfg.res_chunks > 0 || c->residual.data == nullptr),
+                     r == 1 && p.bias_fill && (cfg.res_chunks > 0 || c->residual.data == nullptr),
                  "conv2d_tc_predictor: needs a 3x3 / 1x1 conv with <= 32 output channels on maps larger than 8x8, "
                  "residual (if any) accumulated on the tensor core, and 1..4 predictor channels");
     for (int k = 0; k < pred_c; ++k) {
