@@ -122,7 +122,7 @@ def test_bf16_full_range_output_with_large_flows(dev):
 
 
 @pytest.mark.parametrize('pwc_precision', [None, 'fp32'])
-@pytest.mark.parametrize('shape', [(1, 14, 48, 48), (2, 5, 16, 24), (1, 2, 24, 24), (1, 3, 30, 46), (1, 18, 16, 16)])
+@pytest.mark.parametrize('shape', [(1, 14, 48, 48), (2, 5, 16, 24), (1, 2, 24, 24), (1, 3, 30, 46), (1, 18, 16, 16), (2, 8, 48, 80)])
 def test_bf16_path_tolerance(dev, shape, pwc_precision):
     B, N, H, W = shape
     sd = O.make_state_dict(0)
