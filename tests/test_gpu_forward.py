@@ -94,6 +94,7 @@ def test_fp32_stress_golden_flows_pinned(dev, golden_dir):
     fw = aux_p['fusion_weights'].cpu()
     assert np.abs(fw[:, :, ::37, ::3, ::3].numpy() - g['fusion_weights_sub']).max() < 1e-4
     free = np.abs(pred.cpu().numpy() - g['pred'])
+    assert free.max() <= 1e-4, free.max()       # measured on B200: the un-pinned forward also lands within 1.5e-7 on this golden
     print(f'stress golden: flow err max {ferr.max().item():.2e} px, {100 * (ferr > 1e-4).float().mean().item():.3f} % of flow values '
           f'> 1e-4 px; pinned-flow pred err max {err.max():.2e}; free-running pred err max {free.max():.2e}, '
           f'{100 * (free > 1e-4).mean():.3f} % > 1e-4')
