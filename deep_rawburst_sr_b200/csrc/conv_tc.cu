@@ -988,7 +988,8 @@ static int tc_plan(const dbsr_conv_t* c, TcConfig* cfg, bool set_err, bool allow
   // DBSR_TC_PAIR = 0 / 1 / 2: never / K >= 128 (default) / every eligible layer (A/B switch).
   static const int pair_mode = getenv("DBSR_TC_PAIR") ? atoi(getenv("DBSR_TC_PAIR")) : 1;
   const long long tm_items2 = (long long)c->x.n * ceil_div(c->x.w, 2 * TILE_W) * ceil_div(c->x.h, TILE_H);
-  const bool want_pair = allow_pair && (pair_mode >= 2 || (pair_mode == 1 && kpad / ck >= 2)) && (nt == 64 || nt == 128) &&
+  // (1x1 layers with K >= 128 -- the 512 -> 64 projection -- are HBM-bound passes: 187 us paired vs 183 us, left unpaired)
+  const bool want_pair = allow_pair && (pair_mode >= 2 || (pair_mode == 1 && kpad / ck >= 2 && c->ksize == 3)) && (nt == 64 || nt == 128) &&
                          tiles_x >= 2 && r == 1 && tm_items2 >= 4 * 148 &&
                          !(c->ksize == 3 && c->dilation == 1 && c->x.h <= 8 && c->x.w <= 8);
   cfg->pair_cta = want_pair ? 1 : 0;

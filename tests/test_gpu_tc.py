@@ -152,6 +152,59 @@ def test_conv2d_tc_fused_predictor(n, h, w, use_res, k):
     assert (ya.buf == 5.0).all()        # the conv's output map is not written in this mode
 
 
+def _fuzz_cases():
+    """seeded random conv shapes around the decision boundaries of the tcgen05 planner: CTA pairs on / off (>= 592 two-tile
+    items, K >= 128, N tile 64 / 128), ragged tiles in both directions, odd image counts (idle half of the last pair), 1x1
+    and 3x3 kernels, with / without bias and residual, channel counts that need padded K chunks / masked N tiles"""
+    import random
+    rnd = random.Random(20260)
+    cases = []
+    for i in range(28):
+        cin = rnd.choice([64, 128, 128, 192, 136, 256])
+        cout = rnd.choice([64, 64, 128, 128, 96, 256])
+        k = rnd.choice([3, 3, 3, 1])
+        h, w = rnd.choice([(16, 16), (20, 24), (32, 48), (17, 33), (48, 40), (9, 31)])
+        tiles2 = ((w + 15) // 16) * ((h + 15) // 16)
+        n = rnd.choice([3, max(2, 592 // tiles2 + rnd.choice([-1, 0, 1, 2])), max(2, 700 // tiles2 + 1)])
+        cases.append((i, cin, cout, k, n, h, w, rnd.choice([0, 1, 2]), rnd.random() < 0.4, rnd.random() < 0.8))
+    return cases
+
+
+@pytest.mark.parametrize('case', _fuzz_cases(), ids=lambda c: 'fuzz%d_%dx%d_k%d_n%d_%dx%d' % c[:7])
+def test_conv2d_tc_fuzz(case):
+    if not torch.cuda.is_available():
+        pytest.skip('needs a CUDA device')
+    from deep_rawburst_sr_b200 import ops
+    from deep_rawburst_sr_b200.engine import pack_tc
+    i, cin, cout, k, n, h, w, act, use_res, use_bias = case
+    dev = torch.device('cuda:0')
+    g = torch.Generator().manual_seed(1000 + i)
+    x = torch.randn(n, cin, h, w, generator=g).bfloat16().float()
+    wt = (torch.randn(cout, cin, k, k, generator=g) / (cin * k * k) ** 0.5).bfloat16().float()
+    b = torch.randn(cout, generator=g) if use_bias else None
+    res = torch.randn(n, cout, h, w, generator=g).bfloat16().float() if use_res else None
+    pitch = (cin + 7) // 8 * 8
+    xa = ops.Act(torch.full((n, h, w, pitch + 8), 7.0, dtype=torch.bfloat16, device=dev)).slice(8, cin).from_nchw(x.to(dev))
+    ya = ops.Act(torch.full((n, h, w, cout + 8), 3.0, dtype=torch.bfloat16, device=dev)).slice(0, cout)
+    ra = ops.Act.empty(n, h, w, cout, torch.bfloat16, dev).from_nchw(res.to(dev)) if use_res else None
+    wp = pack_tc(wt.to(dev))
+    bd = b.to(dev) if use_bias else None
+    assert ops.conv2d_tc_supported(xa, wp, bd, ya, k, 1, 1, ra, 0)
+    ops.conv2d(xa, wp, bd, ya, k, 1, 1, act, ra, 0, tensor_core=True)
+    torch.cuda.synchronize()
+    assert (ya.buf[..., cout:] == 3.0).all(), 'pad channels behind the output view were written'
+    got = ya.to_nchw().cpu()
+    # CPU reference of the first, a middle and the last images (the last ones sit in the half-empty pair / ragged items)
+    for lo in sorted({0, max(0, n // 2 - 1), max(0, n - 3)}):
+        sl = slice(lo, min(n, lo + 3))
+        ref = F.conv2d(x[sl], wt, b, padding=(k - 1) // 2)
+        if use_res:
+            ref = ref + res[sl]
+        ref = torch.relu(ref) if act == 1 else (O.lrelu(ref) if act == 2 else ref)
+        err = (got[sl] - ref).abs().max().item()
+        assert err <= max(1.0, ref.abs().max().item()) * 2.0 ** -8, (case, lo, err)
+
+
 @pytest.mark.parametrize('bursts,frames,h,w', [(3, 5, 24, 40), (48, 14, 48, 48)])
 def test_conv2d_tc_broadcast_residual(bursts, frames, h, w):
     """dbsr_conv_t.residual_group: output image i adds residual image i // group -- one map per burst broadcast over its
