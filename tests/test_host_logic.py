@@ -232,3 +232,27 @@ def test_batched_transform_sampling_is_bit_identical_to_the_per_burst_path():
     random.seed(5)
     b = G.get_tmat_batch((64, 64), G.sample_transform_params(3, 2, {'max_rotation': 2.0}))
     assert np.array_equal(np.stack(a), b)
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the CPU arm the driver runs beside the product arm) prints ONE JSON line with the contract
+    keys, the same metric / unit / workload string as the product arm, `impl: reference`, a `cpu_baseline` describing itself and an
+    `e2e` equal to its own value with zero copy bytes; it runs the asked number of steps (no silent cap)."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, 'bench.py'), '--impl', 'reference', '--steps', '2', '--warmup', '1',
+                          '--size', '16'], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.strip().split('\n') if l.startswith('{')]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for k in ('metric', 'value', 'unit', 'n_gpus', 'steps', 'warmup', 'ms_per_step', 'higher_is_better', 'scaling', 'vs_baseline',
+              'dtype', 'data', 'config', 'cpu_baseline', 'e2e', 'impl'):
+        assert k in d, k
+    assert d['impl'] == 'reference' and d['unit'] == 'bursts/s' and d['higher_is_better'] is True and d['steps'] == 2
+    assert d['metric'] == 'bursts/sec (14-frame, 4x SR)' and 'workload' in d['config'] and d['vs_baseline'] is None
+    assert d['cpu_baseline']['kind'] == 'port' and d['cpu_baseline']['cores'] >= 1 and d['cpu_baseline']['value'] == d['value']
+    assert d['e2e'] == {'value': d['value'], 'unit': 'bursts/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}
+    assert abs(d['value'] - 1e3 / d['ms_per_step']) < 1e-6 * d['value']
