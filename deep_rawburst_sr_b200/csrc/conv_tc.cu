@@ -937,7 +937,7 @@ struct TcConfig {
   int pair_cta;    // CTA pairs (cta_group::2): b_bytes is then the HALF weight tile one CTA holds
 };
 
-static int tc_plan(const dbsr_conv_t* c, TcConfig* cfg, bool set_err, bool allow_pair = true) {
+static int tc_plan(const dbsr_conv_t* c, TcConfig* cfg, bool set_err, bool allow_pair = true, int n_split = 1, bool allow_split = true) {
 #define TC_REQ(cond, ...) do { if (!(cond)) { if (set_err) set_error(__VA_ARGS__); return 1; } } while (0)
   TC_REQ(c && view_ok(&c->x) && view_ok(&c->y) && c->w, "conv2d_tc: bad descriptor");
   TC_REQ(c->x.dtype == DBSR_BF16, "conv2d_tc: input must be bf16");
@@ -951,6 +951,9 @@ static int tc_plan(const dbsr_conv_t* c, TcConfig* cfg, bool set_err, bool allow
          "conv2d_tc: input view must be 16-byte aligned (c_off, c_pitch multiples of 8)");
   int ck, kpad, nt, cpad;
   tc_geometry(c->x.c, cout, &ck, &kpad, &nt, &cpad);
+  // n_split > 1 (chosen at the end of this function for launches that would occupy a fraction of the SMs): the same packed
+  // weights, N tiles n_split times narrower, so that n_split times as many CTAs share the work
+  nt /= n_split;
   if (r > 1)
     TC_REQ(r == 8 && c->y.c == 32 && c->y.c_pitch == 32 && c->y.c_off == 0 && nt == 128,
            "conv2d_tc: pixel-shuffle mode needs r=8 and a dense 32-channel output map");
@@ -1050,7 +1053,7 @@ static int tc_plan(const dbsr_conv_t* c, TcConfig* cfg, bool set_err, bool allow
     }
   }
   TC_REQ(found, "conv2d_tc: activation halo box does not fit in shared memory (dilation %d)", c->dilation);
-  if (want_pair && !(cfg->mt == 2 && !cfg->pair_img && !cfg->flat)) return tc_plan(c, cfg, set_err, false);   // pairs need two-tile items
+  if (want_pair && !(cfg->mt == 2 && !cfg->pair_img && !cfg->flat)) return tc_plan(c, cfg, set_err, false, n_split, allow_split);   // pairs need two-tile items
   // accumulator stages: two (double buffering).  DBSR_TC_ACC_STAGES=4 uses four where they fit the 512 TMEM columns (N tile
   // <= 64 with two-tile items): measured on B200 it changes nothing -- neither single CTAs nor CTA pairs wait for a free
   // accumulator stage (profiles/r02_cta_pair_ab.txt) -- so it stays an A/B switch.
@@ -1085,6 +1088,17 @@ static int tc_plan(const dbsr_conv_t* c, TcConfig* cfg, bool set_err, bool allow
   // a CTA that owns more than half of TMEM must be alone on its SM: make its smem footprint exclusive too
   if (cfg->tmem_cols > 256 && smem < 120 * 1024) smem = 120 * 1024;
   cfg->smem_bytes = smem;
+  // Small grids: PWC-Net's pyramid levels 3..6 of a few bursts are a handful of items (26 pairs of 2x2 maps in flat mode: FOUR),
+  // each streaming the layer's whole weight set (up to 1.5 MB) through one SM while 140 SMs idle -- 25-40 us per launch on the
+  // critical path of the small-batch regime (profiles/r02_launches_b2.txt).  When the launch would fill less than half of the
+  // SMs, the N tile is halved (same packed weights, narrower weight-tile boxes; >= 16 columns) until it does.
+  static const bool split_enabled = getenv("DBSR_TC_NO_NSPLIT") == nullptr;      // A/B switch
+  if (split_enabled && allow_split && r == 1 && !cfg->pair_cta && !(c->residual.data && c->residual_group > 1)) {
+    const int imgs_per_item = cfg->flat ? cfg->flat_ni * cfg->mt : (cfg->pair_img ? 2 : 1);
+    const long long tiles = cfg->flat ? 1 : (long long)(cfg->pair_img ? 1 : ceil_div(c->x.w, TILE_W * cfg->mt)) * ceil_div(c->x.h, TILE_H);
+    const long long items = (long long)ceil_div(c->x.n, imgs_per_item) * tiles * (cpad / nt);
+    if (items * 2 <= 148 && nt % 32 == 0 && n_split < 8) return tc_plan(c, cfg, set_err, allow_pair, n_split * 2, allow_split);
+  }
   return 0;
 #undef TC_REQ
 }
@@ -1187,7 +1201,7 @@ static int conv2d_tc_impl(const dbsr_conv_t* c_in, void* stream, const float* pr
   DBSR_REQUIRE(c_in != nullptr, "conv2d_tc: null descriptor");
   const dbsr_conv_t cc = centre_tap_form(c_in);
   const dbsr_conv_t* c = &cc;
-  if (tc_plan(c, &cfg, true)) return 1;
+  if (tc_plan(c, &cfg, true, true, 1, /*allow_split=*/pred == nullptr)) return 1;      // the fused predictor needs all 32 channels in one N tile
   EncodeTiledFn encode = get_encode();
   DBSR_REQUIRE(encode != nullptr, "conv2d_tc: cuTensorMapEncodeTiled entry point not available");
 
