@@ -285,7 +285,11 @@ def test_resblock32_fused(n, h, w, with_pred):
     for _ in range(2):
         ops.resblock32_tc(xa, ya, w1p, b1d, w2p, b2d)
     torch.cuda.synchronize()
-    assert torch.equal(ybuf[..., 8:], y2.buf), (ybuf[..., 8:].float() - y2.buf.float()).abs().max().item()
+    # bit-identical whenever the two-launch path also accumulates the residual on the tensor core; launches of a few items
+    # split their N tile (32 -> 16 columns) and then add the residual in the epilogue: one fp32 rounding order apart
+    small = n * ((h + 15) // 16) * ((w + 15) // 16) * 2 <= 148
+    d = (ybuf[..., 8:].float() - y2.buf.float()).abs().max().item()
+    assert torch.equal(ybuf[..., 8:], y2.buf) or (small and d <= max(1.0, y2.buf.float().abs().max().item()) * 2.0 ** -7), d
     assert (ybuf[..., :8] == 5.0).all() and (xbuf[..., :8] == 9.0).all() and (xbuf[..., 40:] == 9.0).all()
     got = ya.to_nchw().cpu()
     scale = max(1.0, mid.abs().max().item())
