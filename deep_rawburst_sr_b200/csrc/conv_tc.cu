@@ -65,6 +65,8 @@ struct ConvTcParams {
   int bias_fill;        // the table fits and is filled (zeros without a bias)
   int a_slots, b_stages, b_resident;
   int a_bytes, a_tx_bytes, b_bytes;
+  int b_taps;           // streamed weights: taps of one (chunk, N tile) that share a ring stage, ONE TMA box and one barrier pair (1, 3 or 9)
+  int b_stage_bytes;    // b_taps * b_bytes (resident: b_bytes)
   int halo_w;           // pixels per row of the A box
   int res_chunks;       // > 0: the residual is accumulated on the tensor core as res_chunks extra K chunks (identity weights)
   int r_tx_bytes;       // bytes of one residual box {CK, 8*mt px, 16 rows}
@@ -439,7 +441,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* smem_a = smem;                                         // [a_slots][a_bytes]
   uint8_t* smem_b = smem + (size_t)p.a_slots * p.a_bytes;         // [b_stages][b_bytes]
-  uint8_t* smem_stg = smem_b + (size_t)p.b_stages * p.b_bytes;    // [8 epilogue warps][STG_WARP_BYTES]
+  uint8_t* smem_stg = smem_b + (size_t)p.b_stages * p.b_stage_bytes;    // [8 epilogue warps][STG_WARP_BYTES]
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_stg + 8 * STG_WARP_BYTES);
   uint64_t* a_full = bars;
   uint64_t* a_empty = a_full + p.a_slots;
@@ -531,8 +533,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
         if (!PAIR || pair_rank == 0) mbar_arrive_expect_tx(&b_full[0], (uint32_t)((PAIR ? 2 : 1) * (n_main + p.res_chunks) * p.b_bytes));
         for (int t = 0; t < n_main; ++t) {
           const int ch = t / taps, tap = t - ch * taps;
-          if (PAIR) tma_load_2d_pair(&tmap_w, &b_full[0], smem_b + (size_t)t * p.b_bytes, ch * CK, tap * p.cout_pad + row0);
-          else tma_load_2d(&tmap_w, &b_full[0], smem_b + (size_t)t * p.b_bytes, ch * CK, tap * p.cout_pad);
+          if (PAIR) tma_load_3d_pair(&tmap_w, &b_full[0], smem_b + (size_t)t * p.b_bytes, ch * CK, row0, tap);
+          else tma_load_3d(&tmap_w, &b_full[0], smem_b + (size_t)t * p.b_bytes, ch * CK, 0, tap);
         }
         for (int rc = 0; rc < p.res_chunks; ++rc) {   // identity tiles of the residual chunks
           if (PAIR) tma_load_2d_pair(&tmap_i, &b_full[0], smem_b + (size_t)(n_main + rc) * p.b_bytes, rc * CK, row0);
@@ -544,14 +546,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
         for (long long item = item_first; item < p.total_items; item += item_step) {
           const int nt = (int)((unsigned)item % (unsigned)p.ntiles_n);
           for (int ch = 0; ch < p.nchunks; ++ch) {
-            for (int tap = 0; tap < taps; ++tap) {
+            for (int tap = 0; tap < taps; tap += p.b_taps) {      // one box {CK, N tile rows, b_taps taps} per stage
               mbar_wait(&b_empty[stage], phase ^ 1, 150 + stage);
               if (PAIR) {
-                if (pair_rank == 0) mbar_arrive_expect_tx(&b_full[stage], 2u * (uint32_t)p.b_bytes);
-                tma_load_2d_pair(&tmap_w, &b_full[stage], smem_b + (size_t)stage * p.b_bytes, ch * CK, tap * p.cout_pad + nt * NT + row0);
+                if (pair_rank == 0) mbar_arrive_expect_tx(&b_full[stage], 2u * (uint32_t)p.b_stage_bytes);
+                tma_load_3d_pair(&tmap_w, &b_full[stage], smem_b + (size_t)stage * p.b_stage_bytes, ch * CK, nt * NT + row0, tap);
               } else {
-                mbar_arrive_expect_tx(&b_full[stage], (uint32_t)p.b_bytes);
-                tma_load_2d(&tmap_w, &b_full[stage], smem_b + (size_t)stage * p.b_bytes, ch * CK, tap * p.cout_pad + nt * NT);
+                mbar_arrive_expect_tx(&b_full[stage], (uint32_t)p.b_stage_bytes);
+                tma_load_3d(&tmap_w, &b_full[stage], smem_b + (size_t)stage * p.b_stage_bytes, ch * CK, nt * NT, tap);
               }
               if (++stage == p.b_stages) { stage = 0; phase ^= 1; }
             }
@@ -560,10 +562,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
             mbar_wait(&b_empty[stage], phase ^ 1, 170 + stage);
             if (PAIR) {
               if (pair_rank == 0) mbar_arrive_expect_tx(&b_full[stage], 2u * (uint32_t)p.b_bytes);
-              tma_load_2d_pair(&tmap_i, &b_full[stage], smem_b + (size_t)stage * p.b_bytes, rc * CK, row0);
+              tma_load_2d_pair(&tmap_i, &b_full[stage], smem_b + (size_t)stage * p.b_stage_bytes, rc * CK, row0);
             } else {
               mbar_arrive_expect_tx(&b_full[stage], (uint32_t)p.b_bytes);
-              tma_load_2d(&tmap_i, &b_full[stage], smem_b + (size_t)stage * p.b_bytes, rc * CK, 0);
+              tma_load_2d(&tmap_i, &b_full[stage], smem_b + (size_t)stage * p.b_stage_bytes, rc * CK, 0);
             }
             if (++stage == p.b_stages) { stage = 0; phase ^= 1; }
           }
@@ -594,6 +596,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
       const uint32_t tile_step = (uint32_t)p.t1_step16;                  // second M tile of the item
       const bool two_tiles = p.mt == 2;
       const uint32_t b_step = (uint32_t)p.b_bytes >> 4;
+      const uint32_t b_stage_step = (uint32_t)p.b_stage_bytes >> 4;
+      const int b_taps = p.b_taps;
       const uint32_t a_step = (uint32_t)p.a_bytes >> 4;
       const uint32_t a_base = ((smem_u32(smem_a) >> 4) & 0x3FFFu) | 0x10000u;
       const uint32_t b_base = ((smem_u32(smem_b) >> 4) & 0x3FFFu) | 0x10000u;
@@ -622,19 +626,25 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
           tc_fence_after();
           const uint32_t a_lo0 = a_base + (uint32_t)aslot * a_step;
           if (taps == 9) {
+            int tis = 0;                           // tap within the current weight stage
 #pragma unroll
             for (int tap = 0; tap < 9; ++tap) {
               uint32_t b_lo;
               if (RESIDENT) { b_lo = b_lo_res; b_lo_res += b_step; }
               else {
-                mbar_wait(&b_full[bstage], bphase, 350 + bstage);
-                tc_fence_after();
-                b_lo = b_base + (uint32_t)bstage * b_step;
+                if (tis == 0) {
+                  mbar_wait(&b_full[bstage], bphase, 350 + bstage);
+                  tc_fence_after();
+                }
+                b_lo = b_base + (uint32_t)bstage * b_stage_step + (uint32_t)tis * b_step;
               }
               mma_pair(a_lo0 + tap_off[tap], a_hi, b_lo, d0, (tap == 0 && ch == 0) ? 0u : 1u);
               if (!RESIDENT) {
-                umma_commit_t<PAIR>(&b_empty[bstage]);   // weight stage free once these MMAs retire
-                if (++bstage == p.b_stages) { bstage = 0; bphase ^= 1; }
+                if (++tis == b_taps) {
+                  tis = 0;
+                  umma_commit_t<PAIR>(&b_empty[bstage]);   // weight stage free once these MMAs retire
+                  if (++bstage == p.b_stages) { bstage = 0; bphase ^= 1; }
+                }
               }
             }
           } else {
@@ -643,7 +653,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
             else {
               mbar_wait(&b_full[bstage], bphase, 350 + bstage);
               tc_fence_after();
-              b_lo = b_base + (uint32_t)bstage * b_step;
+              b_lo = b_base + (uint32_t)bstage * b_stage_step;
             }
             mma_pair(a_lo0, a_hi, b_lo, d0, ch == 0 ? 0u : 1u);
             if (!RESIDENT) {
@@ -663,7 +673,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
           else {
             mbar_wait(&b_full[bstage], bphase, 370 + bstage);
             tc_fence_after();
-            b_lo = b_base + (uint32_t)bstage * b_step;
+            b_lo = b_base + (uint32_t)bstage * b_stage_step;
           }
           mma_pair(a_base + (uint32_t)aslot * a_step, r_hi, b_lo, d0, 1u);
           if (!RESIDENT) {
@@ -933,7 +943,7 @@ struct TcConfig {
   int flat, flat_s, flat_ni, res_chunks;
   int pair_img;    // narrow maps (one tile column): the two M tiles of an item are two consecutive images
   int n_tile, ck, nchunks, cout, cout_pad, mt, halo_w, rows, a_slots, b_stages, b_resident, a_bytes, a_tx_bytes, b_bytes,
-      smem_bytes, tmem_cols, vec_ok, align_ok, acc_stages;
+      b_taps, b_stage_bytes, smem_bytes, tmem_cols, vec_ok, align_ok, acc_stages;
   int pair_cta;    // CTA pairs (cta_group::2): b_bytes is then the HALF weight tile one CTA holds
 };
 
@@ -1076,17 +1086,26 @@ static int tc_plan(const dbsr_conv_t* c, TcConfig* cfg, bool set_err, bool allow
   const int b_total = (cfg->nchunks * taps + cfg->res_chunks) * cfg->b_bytes;
   if (cpad == nt && cfg->a_slots * cfg->a_bytes + b_total <= budget && cfg->nchunks * taps + cfg->res_chunks <= 64) {
     cfg->b_resident = 1;
+    cfg->b_taps = 1; cfg->b_stage_bytes = cfg->b_bytes;
     cfg->b_stages = cfg->nchunks * taps + cfg->res_chunks;
   } else {
     cfg->b_resident = 0;
     // depth of the weight ring: a (tap, chunk) step is one TMA round trip (~2 us from L2 when few CTAs run) divided by the
     // stages in flight; with 12 stages the small PWC-Net launches spent 0.35 us per step against 0.1 us of MMAs
-    int st = (budget - cfg->a_slots * cfg->a_bytes) / cfg->b_bytes;
+    // and taps per stage: every ring step costs the single issuing thread a barrier wait + a commit and the producer thread
+    // a wait + expect_tx + TMA issue (~0.3 us per step measured on the PWC-Net launches whatever the tile width), so the
+    // taps of one (chunk, N tile) share a stage, one 3-D TMA box and one barrier pair while the stage stays <= 24 KB
+    static const int stage_cap = getenv("DBSR_TC_BSTAGE_KB") ? atoi(getenv("DBSR_TC_BSTAGE_KB")) * 1024 : 24 * 1024;
+    cfg->b_taps = 1;
+    for (int t : {9, 3})
+      if (taps % t == 0 && t * cfg->b_bytes <= stage_cap && (budget - cfg->a_slots * cfg->a_bytes) / (t * cfg->b_bytes) >= 3) { cfg->b_taps = t; break; }
+    cfg->b_stage_bytes = cfg->b_taps * cfg->b_bytes;
+    int st = (budget - cfg->a_slots * cfg->a_bytes) / cfg->b_stage_bytes;
     if (st > 32) st = 32;
     TC_REQ(st >= 2, "conv2d_tc: no room for the weight pipeline");
     cfg->b_stages = st;
   }
-  int smem = cfg->a_slots * cfg->a_bytes + cfg->b_stages * cfg->b_bytes + 8 * STG_WARP_BYTES + 1024 /*align slack*/ + BAR_BYTES + BIAS_TAB_BYTES;
+  int smem = cfg->a_slots * cfg->a_bytes + cfg->b_stages * cfg->b_stage_bytes + 8 * STG_WARP_BYTES + 1024 /*align slack*/ + BAR_BYTES + BIAS_TAB_BYTES;
   // a CTA that owns more than half of TMEM must be alone on its SM: make its smem footprint exclusive too
   if (cfg->tmem_cols > 256 && smem < 120 * 1024) smem = 120 * 1024;
   cfg->smem_bytes = smem;
@@ -1227,11 +1246,12 @@ static int conv2d_tc_impl(const dbsr_conv_t* c_in, void* stream, const float* pr
   {
     const int taps = c->ksize * c->ksize;
     const int kpad = cfg.nchunks * cfg.ck;
-    cuuint64_t dims[2] = {(cuuint64_t)kpad, (cuuint64_t)taps * cfg.cout_pad};
-    cuuint64_t strides[1] = {(cuuint64_t)kpad * 2};
-    cuuint32_t box[2] = {(cuuint32_t)cfg.ck, (cuuint32_t)(cfg.pair_cta ? cfg.n_tile / 2 : cfg.n_tile)};
-    cuuint32_t es[2] = {1, 1};
-    CUresult rc = encode(&mw, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(c->w), dims, strides, box, es,
+    // packed weights [tap][cout_pad][kpad] as a 3-D tensor: one box = b_taps taps of one (K chunk, N tile)
+    cuuint64_t dims[3] = {(cuuint64_t)kpad, (cuuint64_t)cfg.cout_pad, (cuuint64_t)taps};
+    cuuint64_t strides[2] = {(cuuint64_t)kpad * 2, (cuuint64_t)cfg.cout_pad * kpad * 2};
+    cuuint32_t box[3] = {(cuuint32_t)cfg.ck, (cuuint32_t)(cfg.pair_cta ? cfg.n_tile / 2 : cfg.n_tile), (cuuint32_t)cfg.b_taps};
+    cuuint32_t es[3] = {1, 1, 1};
+    CUresult rc = encode(&mw, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(c->w), dims, strides, box, es,
                          CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     DBSR_REQUIRE(rc == CUDA_SUCCESS, "conv2d_tc: cuTensorMapEncodeTiled(w) failed with %d", (int)rc);
@@ -1305,7 +1325,7 @@ static int conv2d_tc_impl(const dbsr_conv_t* c_in, void* stream, const float* pr
   p.bias_fill = (cfg.cout_pad * 4 <= BIAS_TAB_BYTES) ? 1 : 0;
   p.bias_smem = (p.bias_fill || c->bias == nullptr) ? 1 : 0;
   p.a_slots = cfg.a_slots; p.b_stages = cfg.b_stages; p.b_resident = cfg.b_resident;
-  p.a_bytes = cfg.a_bytes; p.a_tx_bytes = cfg.a_tx_bytes; p.b_bytes = cfg.b_bytes; p.halo_w = cfg.halo_w;
+  p.a_bytes = cfg.a_bytes; p.a_tx_bytes = cfg.a_tx_bytes; p.b_bytes = cfg.b_bytes; p.b_taps = cfg.b_taps; p.b_stage_bytes = cfg.b_stage_bytes; p.halo_w = cfg.halo_w;
   p.y = c->y.data; p.y_dtype = c->y.dtype; p.y_pitch = c->y.c_pitch; p.y_coff = c->y.c_off;
   p.yH = c->y.h; p.yW = c->y.w;
   p.res = c->residual.data; p.r_dtype = c->residual.dtype; p.r_pitch = c->residual.c_pitch; p.r_coff = c->residual.c_off;
@@ -1333,7 +1353,7 @@ static int conv2d_tc_impl(const dbsr_conv_t* c_in, void* stream, const float* pr
   p.tma_store = 0;
   {
     const int gw = (cfg.n_tile % 64 == 0) ? 64 : (cfg.n_tile == 32 ? 32 : (cfg.n_tile == 16 ? 16 : 0));
-    const size_t stg_off = (size_t)cfg.a_slots * cfg.a_bytes + (size_t)cfg.b_stages * cfg.b_bytes;
+    const size_t stg_off = (size_t)cfg.a_slots * cfg.a_bytes + (size_t)cfg.b_stages * cfg.b_stage_bytes;
     static const bool enabled = getenv("DBSR_TC_NO_TMA_STORE") == nullptr;     // A/B switch: =1 keeps the LDS + STG read-back
     // (an epilogue-side residual -- N tile 64 -- is prefetched into the same staging rows and is compatible)
     const bool ok = enabled && gw && pred == nullptr && !cfg.flat && p.bias_smem && cfg.vec_ok && c->y.dtype == DBSR_BF16 &&
