@@ -29,7 +29,7 @@ class ConvDesc(ctypes.Structure):
     _fields_ = [('x', NhwcView), ('y', NhwcView), ('residual', NhwcView), ('w', ctypes.c_void_p),
                 ('bias', ctypes.c_void_p), ('ksize', ctypes.c_int32), ('stride', ctypes.c_int32),
                 ('dilation', ctypes.c_int32), ('act', ctypes.c_int32), ('shuffle_r', ctypes.c_int32),
-                ('grid_limit', ctypes.c_int32), ('residual_group', ctypes.c_int32)]
+                ('grid_limit', ctypes.c_int32), ('residual_group', ctypes.c_int32), ('flags', ctypes.c_int32)]
 
 
 class ResBlockDesc(ctypes.Structure):
@@ -37,7 +37,7 @@ class ResBlockDesc(ctypes.Structure):
     _fields_ = [('x', NhwcView), ('y', NhwcView), ('w1', ctypes.c_void_p), ('b1', ctypes.c_void_p), ('w2', ctypes.c_void_p),
                 ('b2', ctypes.c_void_p), ('pred_w', ctypes.c_void_p), ('pred_b', ctypes.c_void_p), ('pred', ctypes.c_void_p),
                 ('pred_c', ctypes.c_int32), ('pred_q14', ctypes.c_int32), ('grid_limit', ctypes.c_int32),
-                ('reserved', ctypes.c_int32)]
+                ('flags', ctypes.c_int32)]
 
 
 _VP = ctypes.c_void_p

@@ -20,6 +20,7 @@ struct UnprocessParams {
 // per_image (optional, device): [batch][12] = rgb2cam (9, row-major) + gains (3) of every image; else the launch-wide p.ccm / p.gains
 __global__ void __launch_bounds__(256) unprocess_kernel(const float* __restrict__ img, float* __restrict__ out, long long plane,
                                                         long long total, const UnprocessParams p, const float* __restrict__ per_image) {
+  griddep_launch_dependents_if_small();
   griddep_wait();
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const long long b = i / plane, px = i - b * plane;
@@ -63,6 +64,7 @@ __global__ void __launch_bounds__(256) mosaic_noise_kernel(const float* __restri
                                                            int h, int w, long long total, float shot, float read,
                                                            const float* __restrict__ levels, int per) {
   // levels (optional, device): [bursts][2] = (shot, read) noise level of every burst of `per` frames; else the launch-wide pair
+  griddep_launch_dependents_if_small();
   griddep_wait();
   const int h2 = h / 2, w2 = w / 2;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -184,6 +186,7 @@ __device__ __forceinline__ int warped_u8x3(const LrBurstParams& p, const double*
 }
 
 __global__ void __launch_bounds__(256) lrburst_kernel(const LrBurstParams p) {
+  griddep_launch_dependents_if_small();
   griddep_wait();
   const long long total = (long long)p.n * p.h * p.w;
   const int k = (p.f & 1) ? 1 : 2, o = (p.f & 1) ? (p.f - 1) / 2 : p.f / 2 - 1;

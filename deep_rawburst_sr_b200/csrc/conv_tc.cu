@@ -65,6 +65,8 @@ struct ConvTcParams {
   int bias_fill;        // the table fits and is filled (zeros without a bias)
   int a_slots, b_stages, b_resident;
   int a_bytes, a_tx_bytes, b_bytes;
+  int early_trigger;    // griddepcontrol.launch_dependents at the top (the launch leaves at least half of the SMs idle)
+  int static_w;         // DBSR_CONV_STATIC_WEIGHTS: weights / bias may be fetched before griddepcontrol.wait
   int b_taps;           // streamed weights: taps of one (chunk, N tile) that share a ring stage, ONE TMA box and one barrier pair (1, 3 or 9)
   int b_stage_bytes;    // b_taps * b_bytes (resident: b_bytes)
   int halo_w;           // pixels per row of the A box
@@ -482,13 +484,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
   // Programmatic dependent launch: everything above touches only on-chip state and the kernel parameters, so it may run
   // while the preceding kernel of the stream is still draining; all global-memory traffic (activations, residual, y,
   // and -- because a caller may have produced them just before -- weights and bias) comes after this wait.
-  griddep_wait();
+  // With static weights (constants of the caller) only the threads that read activations or write the output wait; the
+  // weight producer starts right away, so the weight ring / the resident tiles fill while the preceding kernel still runs.
+  if (p.early_trigger) griddep_launch_dependents();
+  if (!p.static_w) griddep_wait();
   if (p.bias_fill && warp < 8)
     for (int i = threadIdx.x; i < p.cout_pad; i += 256) bias_tab[i] = p.bias ? __ldg(p.bias + i) : 0.0f;
   tc_fence_before();
   __syncthreads();
   if (PAIR) cluster_sync_all();          // both CTAs' barriers are initialised before any cross-CTA arrive / TMA completion
   tc_fence_after();
+  if (p.static_w && warp != WARP_B && warp != WARP_MMA) griddep_wait();   // A producer, epilogue warps (residual loads, stores)
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == WARP_A) {
@@ -1191,7 +1197,11 @@ static int launch_tc(const CUtensorMap& mx, const CUtensorMap& mw, const CUtenso
     ++na;
   }
   lc.attrs = attr; lc.numAttrs = na;
-  cudaError_t le = cudaLaunchKernelEx(&lc, conv_tc_kernel<CK, RESIDENT, PAIR>, mx, mw, mr, mi, my, p);
+  // early trigger of the dependent launch (see common.cuh): 0 never, 1 always, default: when half of the SMs stay idle
+  static const int early_mode = getenv("DBSR_EARLY_TRIGGER") ? atoi(getenv("DBSR_EARLY_TRIGGER")) : 2;
+  ConvTcParams pp = p;
+  pp.early_trigger = early_mode == 1 || (early_mode == 2 && grid * 2 <= num_sms);
+  cudaError_t le = cudaLaunchKernelEx(&lc, conv_tc_kernel<CK, RESIDENT, PAIR>, mx, mw, mr, mi, my, pp);
   if (le != cudaSuccess) { set_error("conv2d_tc: launch failed: %s", cudaGetErrorString(le)); return 2; }
   return check_launch("conv2d_tc");
 }
@@ -1325,7 +1335,8 @@ static int conv2d_tc_impl(const dbsr_conv_t* c_in, void* stream, const float* pr
   p.bias_fill = (cfg.cout_pad * 4 <= BIAS_TAB_BYTES) ? 1 : 0;
   p.bias_smem = (p.bias_fill || c->bias == nullptr) ? 1 : 0;
   p.a_slots = cfg.a_slots; p.b_stages = cfg.b_stages; p.b_resident = cfg.b_resident;
-  p.a_bytes = cfg.a_bytes; p.a_tx_bytes = cfg.a_tx_bytes; p.b_bytes = cfg.b_bytes; p.b_taps = cfg.b_taps; p.b_stage_bytes = cfg.b_stage_bytes; p.halo_w = cfg.halo_w;
+  p.a_bytes = cfg.a_bytes; p.a_tx_bytes = cfg.a_tx_bytes; p.static_w = (c->flags & DBSR_CONV_STATIC_WEIGHTS) ? 1 : 0;
+  p.b_bytes = cfg.b_bytes; p.b_taps = cfg.b_taps; p.b_stage_bytes = cfg.b_stage_bytes; p.halo_w = cfg.halo_w;
   p.y = c->y.data; p.y_dtype = c->y.dtype; p.y_pitch = c->y.c_pitch; p.y_coff = c->y.c_off;
   p.yH = c->y.h; p.yW = c->y.w;
   p.res = c->residual.data; p.r_dtype = c->residual.dtype; p.r_pitch = c->residual.c_pitch; p.r_coff = c->residual.c_off;

@@ -71,6 +71,7 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
 
 template <bool VEC, typename T>
 __global__ void __launch_bounds__(CORR_THREADS, 2) corr81_kernel(const CorrParams p) {
+  griddep_launch_dependents_if_small();
   griddep_wait();
   extern __shared__ __align__(16) float smem[];
   float* f2_s = smem;                                // [HALO_H*HALO_W][32]
@@ -327,6 +328,7 @@ __device__ __forceinline__ void cp_async16_zfill(void* dst_smem, const void* src
 template <int KS>
 __global__ void __launch_bounds__(CORR_THREADS, (CorrMma<KS>::SMEM <= 74 * 1024) ? 3 : ((CorrMma<KS>::SMEM <= 110 * 1024) ? 2 : 1)) corr81_mma_kernel(const CorrParams p) {
   using G = CorrMma<KS>;
+  griddep_launch_dependents_if_small();
   griddep_wait();
   extern __shared__ __align__(16) unsigned char smem_b[];
   __nv_bfloat16* f2_s = reinterpret_cast<__nv_bfloat16*>(smem_b);                               // [HALO_H*HALO_W][PITCH]
@@ -531,6 +533,7 @@ __global__ void __launch_bounds__(CORR_THREADS, (CorrMma<KS>::SMEM <= 74 * 1024)
 constexpr int CORR_SMALL_THREADS = 256;
 template <typename T>
 __global__ void __launch_bounds__(CORR_SMALL_THREADS) corr81_small_kernel(const CorrParams p) {
+  griddep_launch_dependents_if_small();
   griddep_wait();
   extern __shared__ __align__(16) float smem[];
   const int H = p.f1.h, W = p.f1.w, C = p.f1.c, HW = H * W;

@@ -251,6 +251,7 @@ __device__ __forceinline__ Vec8 gather8(const T* img_base, int c_pitch, const Ta
 template <typename TQ, typename TO, bool SPLIT>
 __global__ void __launch_bounds__(256)
 warp_proj_kernel(View q, const float* __restrict__ bias, const float* __restrict__ offsets, View wp_in, int frames, View p0out) {
+  griddep_launch_dependents_if_small();
   griddep_wait();
   const int H = q.h, W = q.w, C = q.c, C8 = C >> 3;
   const int HW = H * W;
@@ -527,6 +528,7 @@ softmax_wsum8_pair_kernel(const __grid_constant__ CUtensorMap tmap_feat, const _
     }
     __syncwarp();
   }
+  griddep_launch_dependents_if_small();
   griddep_wait();
   const __nv_bfloat16* fbase = reinterpret_cast<const __nv_bfloat16*>(feat.data) + feat.c_off;
   const __nv_bfloat16* lbase = reinterpret_cast<const __nv_bfloat16*>(logits.data) + logits.c_off;
@@ -720,6 +722,7 @@ constexpr int BLUR_ROWS = 16;
 template <typename T>
 __global__ void __launch_bounds__(256) blur3x3_rows_kernel(View x, View y, float k0, float k1, float k2, float k3, float k4,
                                                            float k5, float k6, float k7, float k8) {
+  griddep_launch_dependents_if_small();
   griddep_wait();
   const float kk[9] = {k0, k1, k2, k3, k4, k5, k6, k7, k8};
   const int H = x.h, W = x.w, C8 = x.c >> 3;
@@ -773,6 +776,7 @@ __global__ void __launch_bounds__(256) blur3x3_rows_kernel(View x, View y, float
 constexpr int BLUR_SEP_ROWS = 32;
 template <typename T>
 __global__ void __launch_bounds__(256) blur3x3_sep_kernel(View x, View y, float a0, float a1, float a2, float b0, float b1, float b2) {
+  griddep_launch_dependents_if_small();
   griddep_wait();
   const int H = x.h, W = x.w, C8 = x.c >> 3;
   const int col = blockIdx.x * blockDim.x + threadIdx.x;       // (pixel column, channel group)

@@ -33,6 +33,7 @@ struct SsimParams {
 // msssim.py:24-35: L = (255 if max(img1) > 128 else 1) - (-1 if min(img1) < -0.5 else 0), over the CROPPED img1
 __global__ void __launch_bounds__(256) value_range_kernel(const float* __restrict__ a, int planes, int H, int W, int crop,
                                                           float* __restrict__ range_ws) {
+  griddep_launch_dependents_if_small();
   griddep_wait();
   const int hc = H - 2 * crop, wc = W - 2 * crop;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -75,6 +76,7 @@ __global__ void __launch_bounds__(SS_THREADS) ssim_tile_kernel(const SsimParams 
   __shared__ float red[2][SS_THREADS / 32];
   __shared__ float s_c[2];
 
+  griddep_launch_dependents_if_small();
   griddep_wait();
   const int tid = threadIdx.x;
   const int plane = blockIdx.z;
@@ -218,6 +220,7 @@ __global__ void __launch_bounds__(SS_THREADS) ssim_tile_kernel(const SsimParams 
 // second stage of every metric reduction: out[image][v] = scale * sum_i partial[image][i][v], fixed order, fp64
 __global__ void __launch_bounds__(256) reduce_partials_kernel(const float* __restrict__ partial, int per_image, int k, double scale,
                                                               float* __restrict__ out) {
+  griddep_launch_dependents_if_small();
   griddep_wait();
   __shared__ double sm[256];
   const float* base = partial + (long long)blockIdx.x * per_image * k;
@@ -238,6 +241,7 @@ __global__ void __launch_bounds__(256) reduce_partials_kernel(const float* __res
 // F.avg_pool2d(img, (2, 2)) of both images between the MS-SSIM levels (msssim.py:88-89); floor output size
 __global__ void __launch_bounds__(256) avgpool2_pair_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ oa,
                                                             float* __restrict__ ob, int planes, int H, int W) {
+  griddep_launch_dependents_if_small();
   griddep_wait();
   const int oh = H / 2, ow = W / 2;
   const long long total = (long long)planes * oh * ow;
@@ -257,6 +261,7 @@ __global__ void __launch_bounds__(256) avgpool2_pair_kernel(const float* __restr
 // per-image sum of squared differences over the cropped planes (image_quality_v2.py:47-66 with metric 'l2', valid=None)
 __global__ void __launch_bounds__(256) sq_err_kernel(const float* __restrict__ a, const float* __restrict__ b, const unsigned char* __restrict__ valid,
                                                      int c, int H, int W, int crop, float* __restrict__ partial) {
+  griddep_launch_dependents_if_small();
   griddep_wait();
   const int hc = H - 2 * crop, wc = W - 2 * crop;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;

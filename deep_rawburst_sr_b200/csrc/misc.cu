@@ -60,6 +60,7 @@ __global__ void nhwc_to_nchw_kernel(View src, float* __restrict__ dst) {
 }
 
 __global__ void copy_channels_kernel(View src, View dst, int group, int src_group, int src_first) {
+  griddep_launch_dependents_if_small();
   griddep_wait();
   const long long total = (long long)dst.n * dst.h * dst.w * dst.c;
   const int HW = dst.h * dst.w;
@@ -78,6 +79,7 @@ __global__ void copy_channels_kernel(View src, View dst, int group, int src_grou
 // bytes; grid.y walks the images so that the per-thread decode is 32-bit (the generic kernel above spends its time in
 // 64-bit divisions and per-element dtype dispatch)
 __global__ void copy_channels_v8_kernel(View src, View dst, int group, int src_group, int src_first) {
+  griddep_launch_dependents_if_small();
   griddep_wait();
   const int HW = dst.h * dst.w, C8 = dst.c >> 3;
   const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
@@ -99,6 +101,7 @@ __global__ void copy_channels_v8_kernel(View src, View dst, int group, int src_g
 // stride-2 layers (pwcnet.py:49-97) reach the tensor-core kernel.  Converts dtype on the way.
 // -------------------------------------------------------------------------------------------------------
 __global__ void space_to_depth2_kernel(View x, View y) {
+  griddep_launch_dependents_if_small();
   griddep_wait();
   const int C = x.c, C4 = 4 * C;
   const long long total = (long long)y.n * y.h * y.w * C4;
@@ -117,6 +120,7 @@ __global__ void space_to_depth2_kernel(View x, View y) {
 }
 // bf16 -> bf16 with C % 8 == 0 and 16-byte aligned views: one thread moves 8 channels (16 bytes)
 __global__ void space_to_depth2_v8_kernel(View x, View y) {
+  griddep_launch_dependents_if_small();
   griddep_wait();
   const int C8 = x.c >> 3, G = 4 * C8;
   const long long total = (long long)y.n * y.h * y.w * G;
@@ -143,6 +147,7 @@ __global__ void space_to_depth2_v8_kernel(View x, View y) {
 //           (pwcnet.py:266-271): src = (dst + 0.5) * in/out - 0.5, clamped at 0, neighbour clamped.
 // -------------------------------------------------------------------------------------------------------
 __global__ void prep_burst_kernel(const float* __restrict__ burst, int H, int W, View enc_in, View pwc_in) {
+  griddep_launch_dependents_if_small();
   griddep_wait();
   const int HW = H * W;
   const long long n_enc = (long long)enc_in.n * HW;
@@ -222,6 +227,7 @@ __device__ __forceinline__ uint32_t bf16x2_bits(float lo, float hi) {
 }
 __global__ void __launch_bounds__(256) prep_burst_s2d_kernel(const float* __restrict__ burst, int H, int W, int Hp, int Wp,
                                                              View enc_in, View pwc_s2d) {
+  griddep_launch_dependents_if_small();
   griddep_wait();
   const int HW = H * W, H2 = Hp >> 1, W2 = Wp >> 1;
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
@@ -321,6 +327,7 @@ __global__ void deconv4x4s2_kernel(View x, const float* __restrict__ w, const fl
 // -------------------------------------------------------------------------------------------------------
 __global__ void deconv_col2im_kernel(View taps, const float* __restrict__ bias_t, View y_t, View flow,
                                      const float* __restrict__ wf, const float* __restrict__ bias_f, View y_f, View y_f2) {
+  griddep_launch_dependents_if_small();
   griddep_wait();
   const int h = taps.h, w = taps.w, Ho = 2 * h, Wo = 2 * w;
   const long long total = (long long)taps.n * Ho * Wo;
@@ -367,6 +374,7 @@ __global__ void deconv_col2im_kernel(View taps, const float* __restrict__ bias_t
 // align_corners=False, x20, x(W/Wp, H/Hp).  Output NCHW fp32 (the public `offsets`).
 // -------------------------------------------------------------------------------------------------------
 __global__ void flow_head_kernel(View f4, float* __restrict__ offsets, int H, int W, float mulx, float muly) {
+  griddep_launch_dependents_if_small();
   griddep_wait();
   const long long total = (long long)f4.n * H * W;
   const int h4 = f4.h, w4 = f4.w;
@@ -396,6 +404,7 @@ __global__ void flow_head_kernel(View f4, float* __restrict__ offsets, int H, in
 
 // merging.py:91-105: zeros for the reference frame, floor-mod for the others
 __global__ void offsets_mod_kernel(const float* __restrict__ offsets, View out, int frames, float modulo) {
+  griddep_launch_dependents_if_small();
   griddep_wait();
   const int HW = out.h * out.w;
   const int rem = blockIdx.x * blockDim.x + threadIdx.x;
@@ -453,6 +462,7 @@ __global__ void build_wp_input_kernel(View proj, View wp_in, int frames) {
 template <typename T, bool VEC>
 __global__ void __launch_bounds__(256) predictor_kernel(View x, const float* __restrict__ w, const float* __restrict__ bias,
                                                         int cout, float* __restrict__ pred) {
+  griddep_launch_dependents_if_small();
   griddep_wait();
   extern __shared__ float ws[];  // [cout][C] + [cout]
   const int C = x.c;
@@ -588,6 +598,7 @@ extern "C" int dbsr_prep_burst(const float* burst, int32_t frames, int32_t H, in
 
 // evaluation/burstsr/compute_score.py:110-111: (pred.clamp(0, 1) * 2 ** 14).short()  (float -> int16 truncates toward zero)
 __global__ void quantize_q14_kernel(const float* __restrict__ src, short* __restrict__ dst, long long count) {
+  griddep_launch_dependents_if_small();
   griddep_wait();
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (long long)gridDim.x * blockDim.x)
     dst[i] = (short)(fminf(fmaxf(__ldg(src + i), 0.0f), 1.0f) * 16384.0f);

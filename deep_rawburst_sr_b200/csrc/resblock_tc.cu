@@ -52,6 +52,8 @@ struct RbParams {
   int n, H, W;
   int tiles_x, tiles_y;
   int total_items;
+  int early_trigger;  // launch_dependents at the top: only when the grid leaves at least half of the SMs idle
+  int static_w;     // DBSR_CONV_STATIC_WEIGHTS: weights and biases may be fetched before griddepcontrol.wait
   const float* b1;
   const float* b2;
   // fused 1x1 predictor (last block): y is NOT written; pred[n, k, y, x] = relu(pb[k] + sum_c pw[k][c] * block(x)[c])
@@ -107,11 +109,15 @@ resblock32_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
     if (p.pred == nullptr) tma_prefetch_desc(&tmap_y);
   }
   if (warp == RB_WARP_MMA) tmem_alloc(tmem_slot, 512u);
-  griddep_wait();      // programmatic dependent launch: everything above touches on-chip state only
+  // programmatic dependent launch: everything above touches on-chip state only.  With static weights the 19 resident weight
+  // tiles and the biases are fetched before the wait (while the preceding kernel drains); X loads and stores come after it.
+  if (p.early_trigger) griddep_launch_dependents();
+  if (!p.static_w) griddep_wait();
   if (threadIdx.x < 64) bias_tab[threadIdx.x] = __ldg((threadIdx.x < 32 ? p.b1 : p.b2 - 32) + threadIdx.x);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  if (p.static_w && warp != RB_WARP_PROD && warp != RB_WARP_MMA) griddep_wait();
   const uint32_t tmem_base = *tmem_slot;
   const int n_local = (p.total_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
 
@@ -122,6 +128,7 @@ resblock32_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
       for (int t = 0; t < 9; ++t) tma_load_2d(&tmap_w1, w_full, smem_w + t * RB_W_TILE, 0, t * 32);
       for (int t = 0; t < 9; ++t) tma_load_2d(&tmap_w2, w_full, smem_w + (9 + t) * RB_W_TILE, 0, t * 32);
       tma_load_2d(&tmap_i, w_full, smem_w + 18 * RB_W_TILE, 0, 0);
+      if (p.static_w) griddep_wait();
       int item = blockIdx.x;
       for (int k = 0; k < n_local; ++k, item += gridDim.x) {
         int img, y0, x0;
@@ -399,6 +406,7 @@ extern "C" int dbsr_resblock32_tc(const dbsr_resblock_t* b, void* stream) {
   p.n = b->x.n; p.H = b->x.h; p.W = b->x.w;
   p.tiles_x = ceil_div(p.W, RB_OW); p.tiles_y = ceil_div(p.H, RB_OH);
   p.total_items = p.n * p.tiles_x * p.tiles_y;
+  p.static_w = (b->flags & DBSR_CONV_STATIC_WEIGHTS) ? 1 : 0;
   p.b1 = b->b1; p.b2 = b->b2;
   p.pred = b->pred; p.pred_c = b->pred_c; p.pred_q14 = b->pred_q14 ? 1 : 0;
   memset(p.pred_wb, 0, sizeof(p.pred_wb));
@@ -421,6 +429,7 @@ extern "C" int dbsr_resblock32_tc(const dbsr_resblock_t* b, void* stream) {
   }
   int grid = p.total_items < sms_dev[dev_slot] ? p.total_items : sms_dev[dev_slot];
   if (b->grid_limit > 0 && grid > b->grid_limit) grid = b->grid_limit;
+  p.early_trigger = grid * 2 <= sms_dev[dev_slot];
   launch_pdl(resblock32_tc_kernel, dim3((unsigned)grid), dim3(RB_THREADS), (size_t)RB_SMEM, st, mx, mw1, mw2, mi, my, p);
   return check_launch("resblock32_tc");
 }

@@ -200,6 +200,9 @@ class DBSREngine:
         # short PWC-Net launches is worth another 1-1.5 % per step on B200 (148 SMs -> 124; measured 9.39 -> 9.25 ms)
         sms = torch.cuda.get_device_properties(self.device).multi_processor_count
         self.encoder_grid_limit = sms - 24 if sms >= 96 else 0
+        # the packed weights are constants of this engine (uploaded at construction, never written by a kernel): the tensor-core
+        # kernels fetch them before their programmatic-dependent-launch wait.  DBSR_NO_EARLY_WEIGHTS=1: A/B switch
+        self.static_weights = os.environ.get('DBSR_NO_EARLY_WEIGHTS', '0') != '1'
         if os.environ.get('DBSR_ENC_GRID_LIMIT'):          # tuning aid: A/B other splits of the SMs between the two streams
             self.encoder_grid_limit = int(os.environ['DBSR_ENC_GRID_LIMIT'])
         self.launches = 0
@@ -368,10 +371,10 @@ class DBSREngine:
             assert use_tc, 'the fused predictor epilogue exists on the tensor-core path only'
             self.flops[fam] += 2 * x.n * ho * wo * self.pred_w.shape[0] * cw.cout
             ops.conv2d_tc_predictor(x, cw.tc, bias_tc, y, cw.ksize, act, residual, self.pred_w_host, self.pred_b_host, pred,
-                                    grid_limit=grid_limit)
+                                    grid_limit=grid_limit, static_weights=self.static_weights)
         elif use_tc:
             ops.conv2d(x, cw.tc, bias_tc, y, cw.ksize, stride, dilation, act, residual, cw.shuffle_r, tensor_core=True,
-                       grid_limit=grid_limit, residual_group=residual_group)
+                       grid_limit=grid_limit, residual_group=residual_group, static_weights=self.static_weights)
         else:
             ops.conv2d(x, cw.direct, bias, y, cw.ksize, stride, dilation, act, residual, cw.shuffle_r)
         self._toc(ev)
@@ -720,9 +723,9 @@ class DBSREngine:
         if ev is not None and self.layer_events is not None:
             self.layer_events.setdefault(key, []).append((self.timers[fam][-1], fl, fam, (x.n, x.h, x.w, 32, 32)))
         if pred is not None:
-            ops.resblock32_tc(x, None, c1.tc, c1.bias, c2.tc, c2.bias, self.pred_w_host, self.pred_b_host, pred)
+            ops.resblock32_tc(x, None, c1.tc, c1.bias, c2.tc, c2.bias, self.pred_w_host, self.pred_b_host, pred, static_weights=self.static_weights)
         else:
-            ops.resblock32_tc(x, y, c1.tc, c1.bias, c2.tc, c2.bias)
+            ops.resblock32_tc(x, y, c1.tc, c1.bias, c2.tc, c2.bias, static_weights=self.static_weights)
         self._toc(ev)
 
     def _fuse_predictor(self, key: str, x: Act, y: Act, residual: Act) -> bool:

@@ -119,11 +119,14 @@ def _ptr(t: Optional[torch.Tensor]):
 
 def conv2d(x: Act, w: torch.Tensor, bias: Optional[torch.Tensor], y: Act, ksize: int, stride: int = 1, dilation: int = 1,
            act: int = ACT_NONE, residual: Optional[Act] = None, shuffle_r: int = 0, tensor_core: bool = False,
-           grid_limit: int = 0, residual_group: int = 0) -> Act:
+           grid_limit: int = 0, residual_group: int = 0, static_weights: bool = False) -> Act:
     """grid_limit (tensor-core path): cap of the persistent grid of THIS launch, 0 = one CTA per SM.
+    static_weights (tensor-core path): w / bias were uploaded earlier and no kernel queued before this call writes them, so
+    the kernel may fetch them while the preceding kernel still runs (DBSR_CONV_STATIC_WEIGHTS).  Default off: safe for callers
+    that pack weights on the device right before the call.
     residual_group g > 1 (tensor-core path): output image i adds residual image i // g (a per-burst map broadcast over frames)"""
     d = ConvDesc(x.view(), y.view(), residual.view() if residual is not None else _NULL_VIEW, w.data_ptr(),
-                 _ptr(bias), ksize, stride, dilation, act, shuffle_r, int(grid_limit), int(residual_group))
+                 _ptr(bias), ksize, stride, dilation, act, shuffle_r, int(grid_limit), int(residual_group), 1 if static_weights else 0)
     lib = _lib.load_library()
     if tensor_core:
         _lib.check(lib.dbsr_conv2d_tc(ctypes.byref(d), _stream()), 'dbsr_conv2d_tc')
@@ -133,7 +136,8 @@ def conv2d(x: Act, w: torch.Tensor, bias: Optional[torch.Tensor], y: Act, ksize:
 
 
 def conv2d_tc_predictor(x: Act, w: torch.Tensor, bias: Optional[torch.Tensor], y: Act, ksize: int, act: int,
-                        residual: Optional[Act], pred_w, pred_b, pred: torch.Tensor, grid_limit: int = 0) -> torch.Tensor:
+                        residual: Optional[Act], pred_w, pred_b, pred: torch.Tensor, grid_limit: int = 0,
+                        static_weights: bool = False) -> torch.Tensor:
     """tcgen05 conv whose epilogue applies the 1x1 predictor + ReLU and writes `pred` [n, k, h, w] directly (the conv output
     map `y` is not written; it only describes the geometry): fp32, or -- when `pred` is an int16 tensor -- the reference's
     14-bit quantisation (min(value, 1) * 2^14, truncated).  pred_w [k][Cout] / pred_b [k]: HOST values (CPU
@@ -148,7 +152,7 @@ def conv2d_tc_predictor(x: Act, w: torch.Tensor, bias: Optional[torch.Tensor], y
     assert len(pred_w) == k * y.c
     assert pred.dtype in (torch.float32, torch.int16) and pred.is_contiguous() and tuple(pred.shape) == (x.n, k, x.h, x.w)
     d = ConvDesc(x.view(), y.view(), residual.view() if residual is not None else _NULL_VIEW, w.data_ptr(),
-                 _ptr(bias), ksize, 1, 1, act, 0, int(grid_limit), 0)
+                 _ptr(bias), ksize, 1, 1, act, 0, int(grid_limit), 0, 1 if static_weights else 0)
     _lib.check(_lib.load_library().dbsr_conv2d_tc_predictor(ctypes.byref(d), ctypes.cast(pred_w, ctypes.c_void_p),
                                                             ctypes.cast(pred_b, ctypes.c_void_p), k, pred.data_ptr(),
                                                             1 if pred.dtype == torch.int16 else 0, _stream()),
@@ -164,7 +168,7 @@ def _host_floats(v, n=None):
     return (ctypes.c_float * t.numel())(*t.tolist())
 
 
-def _resblock_desc(x: Act, y: Optional[Act], w1, b1, w2, b2, pred_w=None, pred_b=None, pred=None, grid_limit=0):
+def _resblock_desc(x: Act, y: Optional[Act], w1, b1, w2, b2, pred_w=None, pred_b=None, pred=None, grid_limit=0, static_weights=False):
     keep = []
     pw = pb = None
     k = 0
@@ -178,16 +182,17 @@ def _resblock_desc(x: Act, y: Optional[Act], w1, b1, w2, b2, pred_w=None, pred_b
                      ctypes.cast(pw, ctypes.c_void_p) if pw is not None else None,
                      ctypes.cast(pb, ctypes.c_void_p) if pb is not None else None,
                      None if pred is None else pred.data_ptr(), k, 1 if (pred is not None and pred.dtype == torch.int16) else 0,
-                     int(grid_limit), 0)
+                     int(grid_limit), 1 if static_weights else 0)
     return d, keep
 
 
 def resblock32_tc(x: Act, y: Optional[Act], w1: torch.Tensor, b1: torch.Tensor, w2: torch.Tensor, b2: torch.Tensor,
-                  pred_w=None, pred_b=None, pred: Optional[torch.Tensor] = None, grid_limit: int = 0):
+                  pred_w=None, pred_b=None, pred: Optional[torch.Tensor] = None, grid_limit: int = 0,
+                  static_weights: bool = False):
     """y = relu(x + conv2(relu(conv1(x) + b1)) + b2) for 32-channel bf16 maps in one tcgen05 launch (the intermediate map stays
     on the SM); w1 / w2: packed like `conv2d(..., tensor_core=True)` weights.  With `pred` (fp32 or int16 [n, k, h, w]) the 1x1
     predictor + ReLU is applied in the epilogue and `y` is not written."""
-    d, _keep = _resblock_desc(x, y, w1, b1, w2, b2, pred_w, pred_b, pred, grid_limit)
+    d, _keep = _resblock_desc(x, y, w1, b1, w2, b2, pred_w, pred_b, pred, grid_limit, static_weights)
     _lib.check(_lib.load_library().dbsr_resblock32_tc(ctypes.byref(d), _stream()), 'dbsr_resblock32_tc')
     return pred if pred is not None else y
 
@@ -213,7 +218,7 @@ def quantize_q14(src: torch.Tensor, dst: torch.Tensor) -> torch.Tensor:
 def conv2d_tc_supported(x: Act, w: torch.Tensor, bias, y: Act, ksize: int, stride: int = 1, dilation: int = 1,
                         residual: Optional[Act] = None, shuffle_r: int = 0, residual_group: int = 0) -> bool:
     d = ConvDesc(x.view(), y.view(), residual.view() if residual is not None else _NULL_VIEW, w.data_ptr(),
-                 _ptr(bias), ksize, stride, dilation, 0, shuffle_r, 0, int(residual_group))
+                 _ptr(bias), ksize, stride, dilation, 0, shuffle_r, 0, int(residual_group), 0)
     return bool(_lib.load_library().dbsr_conv2d_tc_supported(ctypes.byref(d)))
 
 

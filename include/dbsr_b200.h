@@ -98,7 +98,13 @@ typedef struct dbsr_conv {
   int32_t residual_group;    /* dbsr_conv2d_tc: 0 / 1: residual image i belongs to output image i; g > 1: output image i
                                 takes residual image i / g (one map per burst broadcast over its g frames: the
                                 per-burst term of the fusion weight predictor's first conv, merging.py:108-112)  */
+  int32_t flags;             /* DBSR_CONV_* bits                                                     */
 } dbsr_conv_t;
+/* flags: w and bias are constants of the caller (uploaded before, never written by a kernel that precedes this launch on the
+ * stream).  The tensor-core kernels then start fetching weights while the PRECEDING kernel is still running (programmatic
+ * dependent launch: only the activation loads and the stores wait for it).  Leave it clear when a kernel of the same stream
+ * produced the weights (the reference has no such layer; the parity tests pack weights right before a call).            */
+enum { DBSR_CONV_STATIC_WEIGHTS = 1 };
 int dbsr_conv2d_direct(const dbsr_conv_t* p, void* stream);
 
 /* tcgen05 / TMEM implicit-GEMM path (bf16 operands, fp32 accumulate in tensor memory), stride 1.
@@ -150,7 +156,7 @@ typedef struct dbsr_resblock {
   int32_t      pred_c;
   int32_t      pred_q14;
   int32_t      grid_limit;   /* cap of the persistent grid (CTAs); 0 = one per SM */
-  int32_t      reserved;
+  int32_t      flags;        /* DBSR_CONV_STATIC_WEIGHTS: w1, b1, w2, b2 are constants of the caller */
 } dbsr_resblock_t;
 int dbsr_resblock32_tc(const dbsr_resblock_t* p, void* stream);
 int dbsr_resblock32_tc_supported(const dbsr_resblock_t* p);

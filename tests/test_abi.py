@@ -34,7 +34,7 @@ def test_probes_without_gpu():
     assert lib.dbsr_version() == 100
     # struct layout must match the header (8-byte pointer + 7 int32, padded to 40 bytes)
     assert ctypes.sizeof(_lib.NhwcView) == 40
-    assert ctypes.sizeof(_lib.ConvDesc) == 3 * 40 + 8 + 8 + 7 * 4 + 4
+    assert ctypes.sizeof(_lib.ConvDesc) == 3 * 40 + 8 + 8 + 8 * 4
 
 
 def test_missing_library_fails_loudly(tmp_path):
