@@ -70,6 +70,7 @@ PROTOTYPES = {
     'dbsr_deconv4x4s2': (_I, [_PV, _VP, _VP, _PV, _PV, _VP]),
     'dbsr_deconv_col2im': (_I, [_PV, _VP, _PV, _PV, _VP, _VP, _PV, _PV, _VP]),
     'dbsr_corr81': (_I, [_PV, _PV, _PV, _F, _PV, _I, _I, _I, _I, _VP]),
+    'dbsr_corr81_copy': (_I, [_PV, _PV, _PV, _F, _PV, _PV, _I, _I, _I, _I, _VP]),
     'dbsr_flow_head': (_I, [_PV, _VP, _I, _I, _I, _I, _VP]),
     'dbsr_warp': (_I, [_PV, _VP, _PV, _I, _VP]),
     'dbsr_offsets_mod': (_I, [_VP, _PV, _I, _I, _F, _VP]),

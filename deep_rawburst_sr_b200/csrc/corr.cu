@@ -63,10 +63,32 @@ struct CorrParams {
   int group, act;
   int tiles_x;
   int vec_out;      // 1: the 81-channel volume is stored as 11 groups of 8 channels (the 7 pad channels are zeroed)
+  View f1_copy;     // data != NULL: f1_copy[p] = f1[i1(p)] (the first map's slice of the decoder's concat buffer, pwcnet.py:173)
+                    // written from the tile this kernel stages anyway (tensor-core and small-map kernels)
 };
+// 8 consecutive channels to global memory (16-byte aligned address, host-checked); channels >= valid are not written
+template <typename T> __device__ __forceinline__ void vec8_stg(T* dst, const Vec8c& v, int valid);
+template <> __device__ __forceinline__ void vec8_stg<float>(float* dst, const Vec8c& v, int valid) {
+  if (valid >= 8) {
+    *reinterpret_cast<float4*>(dst) = make_float4(v.v[0], v.v[1], v.v[2], v.v[3]);
+    *reinterpret_cast<float4*>(dst + 4) = make_float4(v.v[4], v.v[5], v.v[6], v.v[7]);
+  } else {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) if (i < valid) dst[i] = v.v[i];
+  }
+}
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   const __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<const uint32_t*>(&h);
+}
+template <> __device__ __forceinline__ void vec8_stg<__nv_bfloat16>(__nv_bfloat16* dst, const Vec8c& v, int valid) {
+  if (valid >= 8) {     // the values came from bf16: the rounding is exact
+    *reinterpret_cast<uint4*>(dst) = make_uint4(pack_bf16x2(v.v[0], v.v[1]), pack_bf16x2(v.v[2], v.v[3]),
+                                                pack_bf16x2(v.v[4], v.v[5]), pack_bf16x2(v.v[6], v.v[7]));
+  } else {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) if (i < valid) dst[i] = __float2bfloat16_rn(v.v[i]);
+  }
 }
 
 template <bool VEC, typename T>
@@ -433,6 +455,16 @@ __global__ void __launch_bounds__(CORR_THREADS, (CorrMma<KS>::SMEM <= 74 * 1024)
   }
   asm volatile("cp.async.commit_group;\n cp.async.wait_group 0;" ::: "memory");
   __syncthreads();
+  if (p.f1_copy.data) {     // the staged f1 tile also goes to the concat slice (16-byte rows; alignment host-checked)
+    __nv_bfloat16* d = reinterpret_cast<__nv_bfloat16*>(p.f1_copy.data) + p.f1_copy.c_off + basef * p.f1_copy.c_pitch;
+    for (int e = t; e < th * CT_W * G8; e += CORR_THREADS) {
+      const int g = e % G8, pix = e / G8;
+      const int y = ty0 + pix / CT_W, x = tx0 + pix % CT_W;
+      if (x < W)
+        *reinterpret_cast<uint4*>(d + (long long)(y * W + x) * p.f1_copy.c_pitch + g * 8) =
+            *reinterpret_cast<const uint4*>(f1_s + pix * G::PITCH + g * 8);
+    }
+  }
 
   // ---- banded product on the tensor cores: warp = dy, fragments straight from shared memory
   const uint32_t* f1_w = reinterpret_cast<const uint32_t*>(f1_s);
@@ -557,7 +589,10 @@ __global__ void __launch_bounds__(CORR_SMALL_THREADS) corr81_small_kernel(const 
   for (int e = t; e < HW * G; e += CORR_SMALL_THREADS) {
     const int g = e % G, pix = e / G;
     const int ch = g * 8;
-    vec8_sts(&f1_s[pix * Cp + ch], vec8_ld<T>(b1 + (base1 + pix) * p.f1.c_pitch + ch, C - ch));
+    const Vec8c a1 = vec8_ld<T>(b1 + (base1 + pix) * p.f1.c_pitch + ch, C - ch);
+    vec8_sts(&f1_s[pix * Cp + ch], a1);
+    if (p.f1_copy.data)
+      vec8_stg<T>(reinterpret_cast<T*>(p.f1_copy.data) + p.f1_copy.c_off + (basef + pix) * p.f1_copy.c_pitch + ch, a1, C - ch);
     Vec8c v = vec8_zero();
     if (!warp2) {
       v = vec8_ld<T>(b2 + (base2 + pix) * p.f2.c_pitch + ch, C - ch);
@@ -613,6 +648,12 @@ using namespace dbsr;
 
 extern "C" int dbsr_corr81(const dbsr_nhwc_t* f1, const dbsr_nhwc_t* f2, const dbsr_nhwc_t* flow, float flow_scale,
                            const dbsr_nhwc_t* out, int32_t pairs, int32_t group, int32_t act, int32_t mode, void* stream) {
+  return dbsr_corr81_copy(f1, f2, flow, flow_scale, out, nullptr, pairs, group, act, mode, stream);
+}
+
+extern "C" int dbsr_corr81_copy(const dbsr_nhwc_t* f1, const dbsr_nhwc_t* f2, const dbsr_nhwc_t* flow, float flow_scale,
+                                const dbsr_nhwc_t* out, const dbsr_nhwc_t* f1_copy, int32_t pairs, int32_t group, int32_t act,
+                                int32_t mode, void* stream) {
   DBSR_REQUIRE(view_ok(f1) && view_ok(f2) && view_ok(out), "corr81: bad views");
   DBSR_REQUIRE(f1->h == f2->h && f1->w == f2->w && f1->c == f2->c && out->h == f1->h && out->w == f1->w &&
                    out->c == 81 && out->n == pairs, "corr81: geometry mismatch");
@@ -630,6 +671,19 @@ extern "C" int dbsr_corr81(const dbsr_nhwc_t* f1, const dbsr_nhwc_t* f2, const d
   CorrParams p;
   p.f1 = make_view(f1); p.f2 = make_view(f2); p.flow = make_view(has_flow ? flow : nullptr); p.out = make_view(out);
   p.flow_scale = flow_scale; p.group = group; p.act = act;
+  const bool want_copy = f1_copy && f1_copy->data;
+  p.f1_copy = make_view(nullptr);
+  if (want_copy) {
+    DBSR_REQUIRE(view_ok(f1_copy) && f1_copy->n == pairs && f1_copy->h == f1->h && f1_copy->w == f1->w && f1_copy->c == f1->c &&
+                     f1_copy->dtype == f1->dtype, "corr81: f1_copy must be a [pairs, h, w, C] view of the dtype of f1");
+  }
+  // the kernels that stage whole 8-channel groups write the copy themselves; every other path launches dbsr_copy_channels
+  const int copy_es = f1->dtype == DBSR_BF16 ? 2 : 4;
+  const bool copy_vec = want_copy && f1_copy->c_off % 8 == 0 && f1_copy->c_pitch % 8 == 0 &&
+                        ((uintptr_t)f1_copy->data + (size_t)f1_copy->c_off * copy_es) % 32 == 0;
+  auto copy_separately = [&]() -> int {
+    return want_copy ? dbsr_copy_channels(f1, f1_copy, group, group > 0 ? group + 1 : 0, 0, stream) : 0;
+  };
   p.tiles_x = ceil_div(f1->w, CT_W);
   const int out_es = out->dtype == DBSR_BF16 ? 2 : 4;
   p.vec_out = out->c_off % 8 == 0 && out->c_pitch % 8 == 0 && out->c_off + 88 <= out->c_pitch &&
@@ -659,6 +713,8 @@ extern "C" int dbsr_corr81(const dbsr_nhwc_t* f1, const dbsr_nhwc_t* f2, const d
       DBSR_REQUIRE(e == cudaSuccess, "corr81: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
       configured[si] = small_smem;
     }
+    if (copy_vec) p.f1_copy = make_view(f1_copy);
+    else if (int rc = copy_separately()) return rc;
     launch_pdl(ks, dim3((unsigned)pairs), dim3(CORR_SMALL_THREADS), small_smem, (cudaStream_t)stream, p);
     return check_launch("corr81");
   }
@@ -680,6 +736,8 @@ extern "C" int dbsr_corr81(const dbsr_nhwc_t* f1, const dbsr_nhwc_t* f2, const d
       DBSR_REQUIRE(e == cudaSuccess, "corr81: carve-out attribute failed: %s", cudaGetErrorString(e));
       mma_attr[ki] = true;
     }
+    if (copy_vec) p.f1_copy = make_view(f1_copy);
+    else if (int rc = copy_separately()) return rc;
     launch_pdl(km, grid, dim3(CORR_THREADS), (size_t)smem, (cudaStream_t)stream, p);
     return check_launch("corr81");
   }
@@ -697,6 +755,7 @@ extern "C" int dbsr_corr81(const dbsr_nhwc_t* f1, const dbsr_nhwc_t* f2, const d
     DBSR_REQUIRE(e == cudaSuccess, "corr81: carve-out attribute failed: %s", cudaGetErrorString(e));
     attr_set[ki] = true;
   }
+  if (int rc = copy_separately()) return rc;
   launch_pdl(kern, grid, dim3(CORR_THREADS), (size_t)CORR_SMEM, (cudaStream_t)stream, p);
   return check_launch("corr81");
 }

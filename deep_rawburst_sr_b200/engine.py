@@ -503,9 +503,10 @@ class DBSREngine:
                 self._conv(f'{pre}net{lname}.netUpfeat.taps', prev_cat, taps, ACT_NONE)
                 self._run('deconv', ops.deconv_col2im, taps, bt, cat.slice(lay.off['upfeat'], 2), prev_flow, wf, bf,
                           cat.slice(lay.off['upflow'], 2), upflow)
-                self._run('copy', ops.copy_channels, f1, cat.slice(lay.off['f1'], lay.sizes['f1']), group, src_group, 0)
+                # the first map's slice of the concat buffer is written by the cost-volume launch (it stages that tile anyway)
+                assert group == 0 or src_group == group + 1
                 self._run('corr81', ops.corr81, f1, f2, vol, pairs, group, flow=upflow, flow_scale=PWC_BACKWARP[lvl],
-                          act=ACT_LRELU)
+                          act=ACT_LRELU, f1_copy=cat.slice(lay.off['f1'], lay.sizes['f1']))
             for j, sub in enumerate(PWC_NAMES[:5]):
                 _cm, start, length = lay.chmap_from(segs[j])
                 out_name = 'o%d' % (j + 1)

@@ -260,13 +260,17 @@ def deconv_col2im(taps: Act, bias_t: torch.Tensor, y_t: Act, flow: Optional[Act]
 
 
 def corr81(f1: Act, f2: Act, out: Act, pairs: int, group: int = 0, flow: Optional[Act] = None, flow_scale: float = 0.0,
-           act: int = ACT_NONE, tensor_core: bool = True) -> Act:
-    """tensor_core=False (per call) keeps bf16 maps on the CUDA-core kernels instead of the mma.sync banded product (A/B)"""
+           act: int = ACT_NONE, tensor_core: bool = True, f1_copy: Optional[Act] = None) -> Act:
+    """tensor_core=False (per call) keeps bf16 maps on the CUDA-core kernels instead of the mma.sync banded product (A/B).
+    f1_copy: [pairs, h, w, C] view that also receives the first map of every pair (the `tenFirst` slice of the decoder's concat
+    buffer, pwcnet.py:173) -- written by the same launch where the kernel stages whole channel groups"""
     a, b, o = f1.view(), f2.view(), out.view()
     fl = flow.view() if flow is not None else _NULL_VIEW
-    _lib.check(_lib.load_library().dbsr_corr81(ctypes.byref(a), ctypes.byref(b), ctypes.byref(fl), float(flow_scale),
-                                               ctypes.byref(o), pairs, group, act,
-                                               _lib.CORR_AUTO if tensor_core else _lib.CORR_CUDA_CORES, _stream()), 'dbsr_corr81')
+    cp = f1_copy.view() if f1_copy is not None else _NULL_VIEW
+    _lib.check(_lib.load_library().dbsr_corr81_copy(ctypes.byref(a), ctypes.byref(b), ctypes.byref(fl), float(flow_scale),
+                                                    ctypes.byref(o), ctypes.byref(cp), pairs, group, act,
+                                                    _lib.CORR_AUTO if tensor_core else _lib.CORR_CUDA_CORES, _stream()),
+               'dbsr_corr81_copy')
     return out
 
 

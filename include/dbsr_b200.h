@@ -200,6 +200,13 @@ int dbsr_corr81(const dbsr_nhwc_t* f1, const dbsr_nhwc_t* f2, const dbsr_nhwc_t*
  * cores (warp-level mma.sync, bf16 operands, fp32 accumulate; a fused backwarp rounds the warped map to bf16);
  * DBSR_CORR_CUDA_CORES keeps every shape on the CUDA-core kernels (fp32 arithmetic on the bf16 inputs): A/B + tests.  */
 enum { DBSR_CORR_AUTO = 0, DBSR_CORR_CUDA_CORES = 1 };
+/* The same call with the first map also written into a second view: f1_copy[p] = f1[i1(p)], [pairs, h, w, C] of f1's dtype --
+ * the `tenFirst` slice of the decoder's concat buffer (torch.cat([tenVolume, tenFirst, tenFlow, tenFeat], 1), pwcnet.py:173).
+ * The tensor-core and small-map kernels store it from the tile they stage anyway (one launch less per pyramid level); the
+ * other paths run dbsr_copy_channels on the same stream.  f1_copy == NULL or data == NULL: dbsr_corr81.                  */
+int dbsr_corr81_copy(const dbsr_nhwc_t* f1, const dbsr_nhwc_t* f2, const dbsr_nhwc_t* flow, float flow_scale,
+                     const dbsr_nhwc_t* out, const dbsr_nhwc_t* f1_copy, int32_t pairs, int32_t group, int32_t act,
+                     int32_t mode, void* stream);
 
 /* flow head: replaces pwcnet.py:274-279.  flow4 [P, h4, w4, 2] fp32 -> offsets [P, 2, H, W] fp32 NCHW  */
 /*   offsets = 20 * bilinear_resize(flow4 -> (H, W)) * (W/Wp, H/Hp)                                     */

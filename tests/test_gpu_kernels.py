@@ -334,6 +334,39 @@ def test_corr81_backwarp_burst_mapping(dev, c, h, w, mag):
     assert bad < 0.01, float(err.max())
 
 
+@pytest.mark.parametrize('c,h,w,dtype,coff', [(32, 16, 16, torch.bfloat16, 88), (64, 8, 8, torch.bfloat16, 88), (128, 2, 2, torch.bfloat16, 88),
+                                              (96, 4, 4, torch.bfloat16, 88), (32, 20, 24, torch.bfloat16, 88), (64, 8, 8, torch.float32, 88),
+                                              (96, 4, 4, torch.float32, 88), (32, 16, 16, torch.float32, 88), (32, 16, 16, torch.bfloat16, 92)])
+def test_corr81_writes_first_map_into_concat_slice(dev, c, h, w, dtype, coff):
+    """dbsr_corr81_copy: the launch that builds the cost volume also writes the first map of every pair into the `tenFirst` slice
+    of the decoder's concat buffer (pwcnet.py:173), with the burst pair->image mapping -- bit for bit what dbsr_copy_channels writes
+    (tensor-core kernel, small-map kernel, and the paths that run the separate copy: fp32 tiled kernel, unaligned slice)"""
+    from deep_rawburst_sr_b200 import ops
+    g = _gen(c * h + w)
+    B, N = 2, 4
+    P = B * (N - 1)
+    feats = torch.randn(B * N, c, h, w, generator=g)
+    flow = (torch.rand(P, 2, h, w, generator=g) * 2 - 1) * 2.0
+    fa = _act_from(feats, dev, dtype=dtype)
+    fl = _act_from(flow, dev)
+    pitch = 88 + c + 16
+    cat_a = ops.Act(torch.zeros((P, h, w, pitch), dtype=dtype, device=dev))
+    cat_b = ops.Act(torch.zeros((P, h, w, pitch), dtype=dtype, device=dev))
+    ops.corr81(fa, fa, cat_a.slice(0, 81), pairs=P, group=N - 1, flow=fl, flow_scale=1.25, act=ops.ACT_LRELU,
+               f1_copy=cat_a.slice(coff, c))
+    ops.corr81(fa, fa, cat_b.slice(0, 81), pairs=P, group=N - 1, flow=fl, flow_scale=1.25, act=ops.ACT_LRELU)
+    ops.copy_channels(fa, cat_b.slice(coff, c), N - 1, N, 0)
+    torch.cuda.synchronize()
+    assert torch.equal(cat_a.buf, cat_b.buf)
+    want = feats.view(B, N, c, h, w)[:, :1].expand(-1, N - 1, -1, -1, -1).reshape(P, c, h, w).to(dtype).float()
+    assert torch.equal(cat_a.slice(coff, c).to_nchw().cpu().float(), want)
+    # pair mode (group 0): image p -> pair p
+    cat_c = ops.Act(torch.zeros((P, h, w, pitch), dtype=dtype, device=dev))
+    ops.corr81(fa.images(0, P), fa.images(1, P), cat_c.slice(0, 81), pairs=P, group=0, flow=fl, flow_scale=1.25, act=ops.ACT_LRELU,
+               f1_copy=cat_c.slice(coff, c))
+    assert torch.equal(cat_c.slice(coff, c).to_nchw().cpu().float(), feats[:P].to(dtype).float())
+
+
 def test_prep_burst_and_flow_head(dev):
     from deep_rawburst_sr_b200 import ops
     g = _gen(11)
