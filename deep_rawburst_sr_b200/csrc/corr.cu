@@ -680,7 +680,8 @@ extern "C" int dbsr_corr81_copy(const dbsr_nhwc_t* f1, const dbsr_nhwc_t* f2, co
   // the kernels that stage whole 8-channel groups write the copy themselves; every other path launches dbsr_copy_channels
   const int copy_es = f1->dtype == DBSR_BF16 ? 2 : 4;
   const bool copy_vec = want_copy && f1_copy->c_off % 8 == 0 && f1_copy->c_pitch % 8 == 0 &&
-                        ((uintptr_t)f1_copy->data + (size_t)f1_copy->c_off * copy_es) % 32 == 0;
+                        ((uintptr_t)f1_copy->data + (size_t)f1_copy->c_off * copy_es) % 16 == 0 &&
+                        ((size_t)f1_copy->c_pitch * copy_es) % 16 == 0;
   auto copy_separately = [&]() -> int {
     return want_copy ? dbsr_copy_channels(f1, f1_copy, group, group > 0 ? group + 1 : 0, 0, stream) : 0;
   };

@@ -775,21 +775,21 @@ __global__ void __launch_bounds__(256) blur3x3_rows_kernel(View x, View y, float
 // rows per thread (6 % halo re-reads instead of 12 %).
 constexpr int BLUR_SEP_ROWS = 32;
 template <typename T>
-__global__ void __launch_bounds__(256) blur3x3_sep_kernel(View x, View y, float a0, float a1, float a2, float b0, float b1, float b2) {
+__global__ void __launch_bounds__(256) blur3x3_sep_kernel(View x, View y, float a0, float a1, float a2, float b0, float b1, float b2, int rows) {
   griddep_launch_dependents_if_small();
   griddep_wait();
   const int H = x.h, W = x.w, C8 = x.c >> 3;
   const int col = blockIdx.x * blockDim.x + threadIdx.x;       // (pixel column, channel group)
   if (col >= W * C8) return;
   const int px = col / C8, c8 = col - px * C8;
-  const int y0 = blockIdx.y * BLUR_SEP_ROWS, n = blockIdx.z;
+  const int y0 = blockIdx.y * rows, n = blockIdx.z;
   const T* xb = reinterpret_cast<const T*>(x.data) + x.c_off + c8 * 8;
   T* yb = reinterpret_cast<T*>(y.data) + y.c_off + c8 * 8;
   const bool has_l = px > 0, has_r = px + 1 < W;
   Vec8 hm2, hm1;       // horizontal sums of rows r-2 and r-1
 #pragma unroll
   for (int k = 0; k < 8; ++k) { hm2.v[k] = 0.0f; hm1.v[k] = 0.0f; }
-  const int r_end = min(y0 + BLUR_SEP_ROWS, H);
+  const int r_end = min(y0 + rows, H);
 #pragma unroll 4
   for (int r = y0 - 1; r <= r_end; ++r) {
     Vec8 h;
@@ -990,11 +990,18 @@ extern "C" int dbsr_blur3x3(const dbsr_nhwc_t* x, const dbsr_nhwc_t* y, const fl
       for (int i = 0; i < 3; ++i) b[i] = k9[i * 3 + pc] / k9[pi];
       for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) dev = fmaxf(dev, fabsf(k9[i * 3 + j] - b[i] * a[j]));
       if (dev <= 1e-7f * kmax) {
-        dim3 gs((unsigned)ceil_div((long long)x->w * (x->c / 8), 256), (unsigned)ceil_div(x->h, BLUR_SEP_ROWS), (unsigned)x->n);
+        // rows per thread: 32 (6 % halo re-reads) when that still gives every SM several CTAs, fewer for a few images
+        // (2 x 384^2 x 32 channels at 32 rows is 144 CTAs of serial row loops: 35 us for 19 MB)
+        static const int rows_env = getenv("DBSR_BLUR_ROWS") ? atoi(getenv("DBSR_BLUR_ROWS")) : 0;
+        const long long cols = ceil_div((long long)x->w * (x->c / 8), 256);
+        int rows = BLUR_SEP_ROWS;
+        while (rows > 4 && cols * ceil_div(x->h, rows) * x->n < 148LL * 3) rows >>= 1;
+        if (rows_env > 0) rows = rows_env;
+        dim3 gs((unsigned)cols, (unsigned)ceil_div(x->h, rows), (unsigned)x->n);
         if (x->dtype == DBSR_F32)
-          launch_pdl(blur3x3_sep_kernel<float>, dim3(gs), dim3(256), 0, st, make_view(x), make_view(y), a[0], a[1], a[2], b[0], b[1], b[2]);
+          launch_pdl(blur3x3_sep_kernel<float>, dim3(gs), dim3(256), 0, st, make_view(x), make_view(y), a[0], a[1], a[2], b[0], b[1], b[2], rows);
         else
-          launch_pdl(blur3x3_sep_kernel<__nv_bfloat16>, dim3(gs), dim3(256), 0, st, make_view(x), make_view(y), a[0], a[1], a[2], b[0], b[1], b[2]);
+          launch_pdl(blur3x3_sep_kernel<__nv_bfloat16>, dim3(gs), dim3(256), 0, st, make_view(x), make_view(y), a[0], a[1], a[2], b[0], b[1], b[2], rows);
         return check_launch("blur3x3");
       }
     }
