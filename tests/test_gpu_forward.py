@@ -340,6 +340,28 @@ def test_cpu_input_is_refused(dev):
         net(O.make_burst(0, 1, 2, 16, 16))
 
 
+def test_early_weight_fetch_is_bit_identical(dev):
+    """DBSR_CONV_STATIC_WEIGHTS: the tensor-core kernels fetch the engine's constant weights before their programmatic-dependent-
+    launch wait, and small launches trigger their dependents early.  Ordering of DATA must not change: the flag on and off give
+    the same bits, eagerly and under CUDA-graph replay, at a shape whose small launches leave most SMs idle (the early-trigger
+    case) and for repeated back-to-back replays (a dependent that read activations too early would show up here)."""
+    sd = O.make_state_dict(0)
+    net = _net(sd, dev, 'bf16')
+    net.return_fusion_weights = False
+    eng = net.engine(dev)
+    bursts = [O.make_burst(70 + i, 2, 5, 24, 32).to(dev) for i in range(3)]
+    assert eng.static_weights
+    eng.static_weights = False
+    want = [(net(b)[0].clone(), net(b)[1]['offsets'].clone()) for b in bursts]
+    eng.static_weights = True
+    for graph in (False, True):
+        net.use_cuda_graph = graph
+        for rep in range(3):
+            for b, (p_ref, o_ref) in zip(bursts, want):
+                p, aux = net(b)
+                assert torch.equal(p, p_ref) and torch.equal(aux['offsets'], o_ref)
+
+
 def test_cuda_graph_replay_matches_eager(dev):
     sd = O.make_state_dict(0)
     net = _net(sd, dev, 'bf16')

@@ -367,6 +367,47 @@ def test_corr81_writes_first_map_into_concat_slice(dev, c, h, w, dtype, coff):
     assert torch.equal(cat_c.slice(coff, c).to_nchw().cpu().float(), feats[:P].to(dtype).float())
 
 
+def _guarded(n, h, w, pitch, dtype, dev, fill):
+    """an Act over the MIDDLE images of a larger allocation whose first and last image are a sentinel: an out-of-bounds store of
+    a kernel (before or after the view, or into channels outside its slice) changes a sentinel value"""
+    from deep_rawburst_sr_b200 import ops
+    big = torch.full((n + 2, h, w, pitch), fill, dtype=dtype, device=dev)
+    return big, ops.Act(big[1:n + 1])
+
+
+@pytest.mark.parametrize('n,h,w', [(1, 5, 7), (2, 37, 9), (3, 70, 24), (1, 384, 48)])
+def test_store_paths_stay_inside_their_views(dev, n, h, w):
+    """guard bands around the outputs of the kernels whose store loops changed in round 2: blur3x3 with every rows-per-thread
+    choice (1..3 images, ragged last row block), the cost volume with the folded first-map copy (tensor-core and small-map
+    kernels), a tensor-core conv with the halved N tile.  Sentinel images before / after the view and the channels outside the
+    written slices must keep their value; the written values are checked by the parity tests."""
+    from deep_rawburst_sr_b200 import ops
+    g = _gen(n * h + w)
+    S = 7.0
+    # blur: bf16 [n, h, w, 32] inside a 48-channel pitch at offset 8
+    x = _act_from(torch.rand(n, 32, h, w, generator=g), dev, dtype=torch.bfloat16)
+    big, ya = _guarded(n, h, w, 48, torch.bfloat16, dev, S)
+    ops.blur3x3(x, ya.slice(8, 32), O.gauss_kernel3().reshape(-1).tolist())
+    torch.cuda.synchronize()
+    assert bool((big[0] == S).all()) and bool((big[-1] == S).all())
+    assert bool((big[1:-1, :, :, :8] == S).all()) and bool((big[1:-1, :, :, 40:] == S).all())
+    assert not bool((big[1:-1, :, :, 8:40] == S).any())
+    if h <= 70:
+        # cost volume + first-map copy into a concat buffer [V 81 (+7) | f1 C | rest]
+        for c in (32, 64):
+            feats = _act_from(torch.randn(2 * n, c, h, w, generator=g), dev, dtype=torch.bfloat16)
+            flow = _act_from((torch.rand(n, 2, h, w, generator=g) * 2 - 1) * 3, dev)
+            pitch = 88 + c + 8
+            big, cat = _guarded(n, h, w, pitch, torch.bfloat16, dev, S)
+            if h > 1 and w > 1:
+                ops.corr81(feats.images(0, n), feats.images(n, n), cat.slice(0, 81), pairs=n, flow=flow, flow_scale=1.0,
+                           act=ops.ACT_LRELU, f1_copy=cat.slice(88, c))
+                torch.cuda.synchronize()
+                assert bool((big[0] == S).all()) and bool((big[-1] == S).all())
+                assert bool((big[1:-1, :, :, 88 + c:] == S).all())
+                assert torch.equal(cat.slice(88, c).to_nchw(), feats.images(0, n).to_nchw())
+
+
 def test_prep_burst_and_flow_head(dev):
     from deep_rawburst_sr_b200 import ops
     g = _gen(11)
