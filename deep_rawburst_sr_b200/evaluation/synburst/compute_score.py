@@ -11,11 +11,12 @@ one all-reduce of `[sums | counts]` at the end (`sharding.reduce_metric_means`) 
 LPIPS (a pretrained AlexNet from the `lpips` package) is not on this path and is refused.  `saved_dir` reproduces the
 `load_saved` branch (:78-88, 100-104): when the directory holds one `<burst_name>.png` per burst (written by
 `save_results.save_results` here or by the reference's own script), the predictions are read from the files instead of
-running the network.  The on-disk dataset / experiment registry of the reference's driver are out of scope: `dataset` is any indexable of
-`(burst [N, 4, H, W], gt [3, 8H, 8W], meta_info)` items, the contract of `SyntheticBurstVal.__getitem__`
-(dataset/synthetic_burst_val_set.py:38-55)."""
+running the network.  `dataset` is any indexable of `(burst [N, 4, H, W], gt [3, 8H, 8W], meta_info)` items, the contract of
+`SyntheticBurstVal.__getitem__` (dataset/synthetic_burst_val_set.py:38-55).  `compute_score(setting_name, load_saved)` is the
+reference's driver on top of it: experiment file -> list of `NetworkParam` -> one row of the report per network."""
 from __future__ import annotations
 
+import importlib
 import os
 from typing import Dict, Optional, Sequence
 
@@ -152,3 +153,49 @@ def generate_formatted_report(scores_all: Dict[str, Dict[str, float]], table_nam
             text += ' {: <{w}} |'.format('{:0.3f}'.format(scores[k]), w=w)
         text += '\n'
     return text
+
+
+def load_experiment(setting_name: str, dataset_name: str = 'synburst'):
+    """list of `NetworkParam` of an experiment: `evaluation/<dataset>/experiments/<setting_name>.py::main()` of this package
+    (compute_score.py:41-43), or -- a dotted name -- any importable module with a `main()`"""
+    mod = setting_name if '.' in setting_name else '{}.evaluation.{}.experiments.{}'.format(__name__.split('.')[0], dataset_name, setting_name)
+    return getattr(importlib.import_module(mod), 'main')()
+
+
+def compute_score(setting_name, load_saved=False, dataset=None, metrics: Sequence[str] = ('psnr', 'ssim'), batch_size: int = 32,
+                  device='cuda', verbose: bool = True) -> Dict[str, Dict[str, float]]:
+    """The reference's `compute_score(setting_name, load_saved=False)` (evaluation/synburst/compute_score.py:36-122): scores every
+    network of the experiment on the SyntheticBurst validation set and prints the report.  Predictions are looked up /
+    expected under `<save_data_path>/synburst/<unique_name>`; with `load_saved` a complete set of saved files replaces the
+    network run (a `NetworkParam` with only `unique_name` is scored from downloaded predictions that way).  Returns
+    {display name: {metric: mean}}.  `dataset` defaults to `SyntheticBurstVal()`; LPIPS is not provided (see `score_dataset`)."""
+    from ...admin.environment import env_settings
+    from .save_results import saved_results_complete
+    if dataset is None:
+        from ...dataset.synthetic_burst_val_set import SyntheticBurstVal
+        dataset = SyntheticBurstVal()
+    base_results_dir = env_settings().save_data_path
+    scores_all = {}
+    for n in load_experiment(setting_name, 'synburst'):
+        out_dir = '{}/synburst/{}'.format(base_results_dir, n.get_unique_name())
+        using_saved = bool(load_saved) and saved_results_complete(out_dir, dataset)
+        net = None
+        if not using_saved:
+            net = n.load_net()
+            net.to(device).train(False)
+        s = score_dataset(net, dataset, metrics=metrics, boundary_ignore=40, batch_size=batch_size, device=device,
+                          burst_sz=n.burst_sz, saved_dir=out_dir if using_saved else None)
+        scores_all[n.get_display_name()] = {m: s[m] for m in metrics}
+    if verbose:
+        print(generate_formatted_report(scores_all))
+    return scores_all
+
+
+if __name__ == '__main__':
+    import argparse
+    parser = argparse.ArgumentParser(description='Compute scores on the SyntheticBurst validation set. With --load_saved, '
+                                                 'saved predictions are used whenever a complete set exists.')
+    parser.add_argument('setting', type=str, help='Name of experiment setting')
+    parser.add_argument('--load_saved', dest='load_saved', action='store_true', default=False)
+    args = parser.parse_args()
+    compute_score(args.setting, args.load_saved)

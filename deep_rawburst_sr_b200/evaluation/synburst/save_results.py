@@ -32,22 +32,29 @@ def _chunk(tag: bytes, data: bytes) -> bytes:
     return struct.pack('>I', len(data)) + tag + data + struct.pack('>I', zlib.crc32(tag + data) & 0xFFFFFFFF)
 
 
+def _file_order(channels: int):
+    """OpenCV arrays are B, G, R (, A); PNG stores R, G, B (, A)"""
+    return [2, 1, 0] if channels == 3 else [2, 1, 0, 3]
+
+
 def write_png16(path: str, image: np.ndarray, level: int = 3) -> None:
-    """image: uint16 [H, W, 3] in the array order the reference hands to `cv2.imwrite` (channel 0 -> file BLUE plane).
-    16-bit samples are stored big-endian; every scanline uses the `Up` filter (vectorised; smooth rows compress well)."""
+    """image: uint16 [H, W, 3] or [H, W, 4] in the array order the reference hands to `cv2.imwrite` (channel 0 -> file BLUE
+    plane; a fourth channel is the file's alpha plane -- the packed RGGB burst frames of the SyntheticBurst validation set are
+    stored that way, dataset/synthetic_burst_val_set.py:44).  16-bit samples are stored big-endian; every scanline uses the `Up`
+    filter (vectorised; smooth rows compress well)."""
     a = np.ascontiguousarray(image)
-    if a.dtype != np.uint16 or a.ndim != 3 or a.shape[2] != 3:
-        raise ValueError(f'write_png16 takes a uint16 [H, W, 3] array, got {a.dtype} {a.shape}')
-    h, w, _ = a.shape
-    rgb = np.ascontiguousarray(a[:, :, ::-1]).astype('>u2').view(np.uint8).reshape(h, w * 6)      # file order R, G, B; big-endian
+    if a.dtype != np.uint16 or a.ndim != 3 or a.shape[2] not in (3, 4):
+        raise ValueError(f'write_png16 takes a uint16 [H, W, 3 or 4] array, got {a.dtype} {a.shape}')
+    h, w, ch = a.shape
+    rgb = np.ascontiguousarray(a[:, :, _file_order(ch)]).astype('>u2').view(np.uint8).reshape(h, w * 2 * ch)   # big-endian
     up = rgb.copy()
     up[1:] = rgb[1:] - rgb[:-1]                                                 # filter type 2 (Up), modulo 256
-    rows = np.empty((h, 1 + w * 6), dtype=np.uint8)
+    rows = np.empty((h, 1 + w * 2 * ch), dtype=np.uint8)
     rows[:, 0] = 2
     rows[0, 0] = 0                                                              # first row: no filter (nothing above it)
     rows[:, 1:] = up
     rows[0, 1:] = rgb[0]
-    ihdr = struct.pack('>IIBBBBB', w, h, 16, 2, 0, 0, 0)                        # 16 bit, colour type 2 (RGB), no interlace
+    ihdr = struct.pack('>IIBBBBB', w, h, 16, 2 if ch == 3 else 6, 0, 0, 0)      # 16 bit, colour type 2 (RGB) / 6 (RGBA), no interlace
     blob = _PNG_SIG + _chunk(b'IHDR', ihdr) + _chunk(b'IDAT', zlib.compress(rows.tobytes(), level)) + _chunk(b'IEND', b'')
     tmp = path + '.tmp'
     with open(tmp, 'wb') as f:
@@ -91,8 +98,9 @@ def _unfilter(raw: np.ndarray, h: int, stride: int, bpp: int) -> np.ndarray:
 
 
 def read_png16(path: str) -> np.ndarray:
-    """-> uint16 [H, W, 3] in `cv2.imread(path, cv2.IMREAD_UNCHANGED)` order (channel 0 = file BLUE plane).  Reads 16-bit,
-    non-interlaced RGB PNGs (what `write_png16` and `cv2.imwrite` of a uint16 HxWx3 array produce)."""
+    """-> uint16 [H, W, 3] (or [H, W, 4] for an RGBA file) in `cv2.imread(path, cv2.IMREAD_UNCHANGED)` order (channel 0 = file
+    BLUE plane, channel 3 = alpha).  Reads 16-bit, non-interlaced RGB / RGBA PNGs (what `write_png16` and `cv2.imwrite` of a
+    uint16 HxWx3 / HxWx4 array produce)."""
     with open(path, 'rb') as f:
         blob = f.read()
     if blob[:8] != _PNG_SIG:
@@ -111,12 +119,13 @@ def read_png16(path: str) -> np.ndarray:
     if hdr is None:
         raise ValueError(f'{path}: no IHDR chunk')
     w, h, depth, ctype, _comp, _filt, interlace = hdr
-    if depth != 16 or ctype != 2 or interlace != 0:
-        raise ValueError(f'{path}: expected a 16-bit non-interlaced RGB PNG (got depth {depth}, colour type {ctype}, interlace {interlace})')
-    stride = w * 6
+    if depth != 16 or ctype not in (2, 6) or interlace != 0:
+        raise ValueError(f'{path}: expected a 16-bit non-interlaced RGB(A) PNG (got depth {depth}, colour type {ctype}, interlace {interlace})')
+    ch = 3 if ctype == 2 else 4
+    stride = w * 2 * ch
     raw = np.frombuffer(zlib.decompress(b''.join(idat)), dtype=np.uint8).reshape(h, 1 + stride)
-    rgb = np.ascontiguousarray(_unfilter(raw, h, stride, 6)).view('>u2').reshape(h, w, 3)
-    return np.ascontiguousarray(rgb[:, :, ::-1]).astype(np.uint16)
+    rgb = np.ascontiguousarray(_unfilter(raw, h, stride, 2 * ch)).view('>u2').reshape(h, w, ch)
+    return np.ascontiguousarray(rgb[:, :, _file_order(ch)]).astype(np.uint16)
 
 
 def prediction_to_array(pred_q: torch.Tensor) -> np.ndarray:
@@ -136,11 +145,35 @@ def saved_results_complete(out_dir: str, dataset) -> bool:
     return os.path.isdir(out_dir) and len([r for r in os.listdir(out_dir) if r[-3:] == 'png']) == len(dataset)
 
 
+def save_results_for_setting(setting_name: str, dataset=None, batch_size: int = 32, device='cuda') -> dict:
+    """The reference's `save_results(setting_name)` (evaluation/synburst/save_results.py:33-69): for every network of the
+    experiment, write the predictions of the whole validation set to `<save_data_path>/synburst/<unique_name>/<burst_name>.png`.
+    -> {unique name: files written}"""
+    from ...admin.environment import env_settings
+    from .compute_score import load_experiment
+    if dataset is None:
+        from ...dataset.synthetic_burst_val_set import SyntheticBurstVal
+        dataset = SyntheticBurstVal()
+    base_results_dir = env_settings().save_data_path
+    written = {}
+    for n in load_experiment(setting_name, 'synburst'):
+        net = n.load_net()
+        net.to(device).train(False)
+        out_dir = '{}/synburst/{}'.format(base_results_dir, n.get_unique_name())
+        written[n.get_unique_name()] = save_results(net, dataset, out_dir, batch_size=batch_size, device=device, burst_sz=n.burst_sz)
+    return written
+
+
 @torch.no_grad()
-def save_results(net, dataset, out_dir: str, batch_size: int = 32, device='cuda', burst_sz: Optional[int] = None,
-                 workers: int = 8) -> int:
+def save_results(net, dataset=None, out_dir: Optional[str] = None, batch_size: int = 32, device='cuda', burst_sz: Optional[int] = None,
+                 workers: int = 8):
     """Run `net` over `dataset` (items `(burst [N, 4, H, W], gt, meta_info)`, the contract of `SyntheticBurstVal`) and write one
-    `<burst_name>.png` per burst into `out_dir` -- the files of reference save_results.py:52-68.  Returns the number written."""
+    `<burst_name>.png` per burst into `out_dir` -- the files of reference save_results.py:52-68.  Returns the number written.
+    Called with an experiment NAME as the only argument it is the reference's `save_results(setting_name)` driver
+    (`save_results_for_setting`)."""
+    if isinstance(net, str):
+        return save_results_for_setting(net, dataset, batch_size=batch_size, device=device)
+    assert dataset is not None and out_dir is not None
     from ...pipeline import HostPipeline
     os.makedirs(out_dir, exist_ok=True)
     device = torch.device(device)
@@ -181,3 +214,10 @@ def save_results(net, dataset, out_dir: str, batch_size: int = 32, device='cuda'
         pool.shutdown(wait=True)
         net.output_int16 = was_q
     return len(jobs)
+
+
+if __name__ == '__main__':
+    import argparse
+    parser = argparse.ArgumentParser(description='Save network predictions on the SyntheticBurst validation set')
+    parser.add_argument('setting', type=str, help='Name of experiment setting')
+    save_results_for_setting(parser.parse_args().setting)

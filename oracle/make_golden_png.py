@@ -7,7 +7,6 @@ exactly that call, so the tests can check `read_png16` against a file the refere
 """
 import os
 
-import cv2
 import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -21,10 +20,27 @@ def golden_image(h=40, w=56):
     return img.astype(np.uint16)
 
 
+def golden_image4(h=24, w=32):
+    """deterministic 14-bit four-channel frame (R, G, G, B planes of a packed mosaic)"""
+    base = golden_image(h, w).astype(np.int64)
+    yy, xx = np.mgrid[0:h, 0:w].astype(np.int64)
+    fourth = (yy * 613 + xx * 389 + (yy ^ xx) * 17) % 16385
+    return np.concatenate([base, fourth[:, :, None]], axis=-1).astype(np.uint16)
+
+
 if __name__ == '__main__':
+    import cv2          # only the generator needs OpenCV; the tests import golden_image / golden_image4
     out = os.path.join(ROOT, 'tests', 'golden', 'pred_u16_cv2.png')
     img = golden_image()
     assert cv2.imwrite(out, img)
     back = cv2.imread(out, cv2.IMREAD_UNCHANGED)
     assert back.dtype == np.uint16 and np.array_equal(back, img)
     print('wrote', out, os.path.getsize(out), 'bytes')
+    # a packed RGGB burst frame as the SyntheticBurst validation set stores it: uint16 HxWx4 through the same cv2.imwrite
+    # (dataset/synthetic_burst_val_set.py:44 reads it back with cv2.IMREAD_UNCHANGED)
+    out4 = os.path.join(ROOT, 'tests', 'golden', 'burst_u16x4_cv2.png')
+    img4 = golden_image4()
+    assert cv2.imwrite(out4, img4)
+    back4 = cv2.imread(out4, cv2.IMREAD_UNCHANGED)
+    assert back4.dtype == np.uint16 and np.array_equal(back4, img4)
+    print('wrote', out4, os.path.getsize(out4), 'bytes')

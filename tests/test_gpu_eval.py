@@ -139,3 +139,55 @@ def test_save_results_and_score_from_saved_pngs(dev, tmp_path):
     saved = score_dataset(None, data, batch_size=2, device=dev, boundary_ignore=8, saved_dir=out_dir)
     assert saved['using_saved_results'] and not live['using_saved_results']
     assert abs(saved['psnr'] - live['psnr']) < 1e-5 and abs(saved['ssim'] - live['ssim']) < 1e-6
+
+
+def test_experiment_drivers_on_a_miniature_validation_set(dev, tmp_path, monkeypatch, capsys):
+    """The reference's two command-line drivers end to end (evaluation/synburst/save_results.py:33-69, compute_score.py:36-122):
+    experiment file -> NetworkParam -> checkpoint (admin/loading.py) -> SyntheticBurstVal files on disk -> predictions under
+    <save_data_path>/synburst/<unique_name> -> report; `load_saved` scores the saved files instead of running the network and
+    must print the same numbers; `burst_sz` truncates the bursts; a NetworkParam with only a unique_name scores downloaded
+    predictions."""
+    import sys
+    from deep_rawburst_sr_b200.dataset.synthetic_burst_val_set import SyntheticBurstVal, write_burst
+    from deep_rawburst_sr_b200.evaluation.synburst.compute_score import compute_score, score_dataset
+    from deep_rawburst_sr_b200.evaluation.synburst.save_results import save_results
+    from deep_rawburst_sr_b200.models.dbsr.dbsrnet import dbsrnet_default_synthetic
+    sd = O.make_state_dict(0, dbsr_gain=1.5)
+    net = dbsrnet_default_synthetic()
+    net.load_state_dict(sd, strict=True)
+    ck = tmp_path / 'nets' / 'tiny_net.pth'
+    ck.parent.mkdir()
+    torch.save({'net': net.state_dict(), 'constructor': net.constructor, 'net_info': None}, str(ck))
+    g = torch.Generator().manual_seed(21)
+    root = str(tmp_path / 'val')
+    for i in range(3):
+        write_burst(root, i, torch.rand(6, 4, 48, 48, generator=g), torch.rand(3, 384, 384, generator=g), {'gamma': True})
+    data = SyntheticBurstVal(root=root, num_bursts=3, burst_size=6)
+    exp = tmp_path / 'exp_pkg'
+    exp.mkdir()
+    (exp / '__init__.py').write_text('')
+    (exp / 'tiny.py').write_text(
+        'from deep_rawburst_sr_b200.evaluation.common_utils.network_param import NetworkParam\n'
+        'def main():\n'
+        "    return [NetworkParam(network_path='tiny_net.pth', unique_name='TINY'),\n"
+        "            NetworkParam(network_path='tiny_net.pth', unique_name='TINY4', burst_sz=4, display_name='four frames')]\n")
+    (exp / 'downloaded.py').write_text(
+        'from deep_rawburst_sr_b200.evaluation.common_utils.network_param import NetworkParam\n'
+        'def main():\n'
+        "    return [NetworkParam(unique_name='TINY')]\n")
+    monkeypatch.syspath_prepend(str(tmp_path))
+    monkeypatch.setenv('DBSR_PRETRAINED_NETS_DIR', str(ck.parent))
+    monkeypatch.setenv('DBSR_SAVE_DATA_PATH', str(tmp_path / 'results'))
+    live = compute_score('exp_pkg.tiny', load_saved=True, dataset=data, batch_size=2, device=dev)   # nothing saved yet: runs the nets
+    assert set(live) == {'TINY', 'four frames'} and 'four frames' in capsys.readouterr().out
+    assert save_results('exp_pkg.tiny', data, batch_size=2, device=dev) == {'TINY': 3, 'TINY4': 3}
+    assert sorted(os.listdir(str(tmp_path / 'results' / 'synburst' / 'TINY4'))) == ['0000.png', '0001.png', '0002.png']
+    saved = compute_score('exp_pkg.tiny', load_saved=True, dataset=data, batch_size=2, device=dev)
+    for name in live:
+        for m in ('psnr', 'ssim'):
+            assert abs(live[name][m] - saved[name][m]) < 1e-5, (name, m)
+    assert abs(live['TINY']['psnr'] - live['four frames']['psnr']) > 1e-4                 # burst_sz = 4 is a different run
+    down = compute_score('exp_pkg.downloaded', load_saved=True, dataset=data, batch_size=2, device=dev, verbose=False)
+    assert abs(down['TINY']['psnr'] - live['TINY']['psnr']) < 1e-5
+    direct = score_dataset(net.to(dev).eval(), data, batch_size=2, device=dev)
+    assert abs(direct['psnr'] - live['TINY']['psnr']) < 1e-5 and abs(direct['ssim'] - live['TINY']['ssim']) < 1e-6

@@ -209,6 +209,117 @@ def test_png16_codec_matches_the_reference_writer(tmp_path, golden_dir):
     assert SR.saved_results_complete(str(only), [0]) and not SR.saved_results_complete(str(only), [0, 1])
 
 
+def test_png16_four_channel_frames_and_val_set_layout(tmp_path, golden_dir):
+    """dataset/synthetic_burst_val_set.py:42-55: burst frames are 16-bit FOUR-channel PNGs written / read through OpenCV (array
+    channels B, G, R, A <-> file planes R, G, B, A).  (a) a 4-channel file written by `cv2.imwrite` (oracle/make_golden_png.py)
+    decodes to the array that was written, and write -> read is the identity; (b) a miniature validation set written in the
+    reference's directory layout reads back through `SyntheticBurstVal` with the reference's item contract."""
+    import numpy as np
+    from oracle.make_golden_png import golden_image4
+    from deep_rawburst_sr_b200.evaluation.synburst import save_results as SR
+    from deep_rawburst_sr_b200.dataset.synthetic_burst_val_set import SyntheticBurstVal, write_burst
+    img = golden_image4()
+    assert np.array_equal(SR.read_png16(os.path.join(golden_dir, 'burst_u16x4_cv2.png')), img)
+    p = str(tmp_path / 'f.png')
+    SR.write_png16(p, img)
+    assert np.array_equal(SR.read_png16(p), img)
+    g = torch.Generator().manual_seed(5)
+    root = str(tmp_path / 'val')
+    items = []
+    for i in range(2):
+        burst = (torch.rand(3, 4, 12, 16, generator=g) * 2 ** 14).round() / 2 ** 14       # 14-bit values: stored exactly
+        gt = (torch.rand(3, 96, 128, generator=g) * 2 ** 14).round() / 2 ** 14
+        meta = {'rgb2cam': torch.eye(3), 'gamma': True, 'smoothstep': True}
+        write_burst(root, i, burst, gt, meta)
+        items.append((burst, gt))
+    ds = SyntheticBurstVal(root=root, num_bursts=2, burst_size=3)
+    assert len(ds) == 2 and len(SyntheticBurstVal(root=root)) == 300 and SyntheticBurstVal(root=root).burst_size == 14
+    for i, (burst, gt) in enumerate(items):
+        b, t, meta = ds[i]
+        assert torch.equal(b, burst) and torch.equal(t, gt) and b.dtype == torch.float32
+        assert meta['burst_name'] == '%04d' % i and meta['gamma'] is True and torch.equal(meta['rgb2cam'], torch.eye(3))
+    assert sorted(os.listdir(os.path.join(root, 'bursts', '0001'))) == ['im_raw_00.png', 'im_raw_01.png', 'im_raw_02.png']
+    assert sorted(os.listdir(os.path.join(root, 'gt', '0001'))) == ['im_rgb.png', 'meta_info.pkl']
+
+
+def test_network_param_and_experiment_registry():
+    """evaluation/common_utils/network_param.py:64-111 and evaluation/synburst/experiments/dbsr_default.py: constructor
+    constraints, generated names, the shipped experiment"""
+    from deep_rawburst_sr_b200.evaluation.common_utils.network_param import NetworkParam
+    from deep_rawburst_sr_b200.evaluation.synburst.compute_score import load_experiment
+    n = NetworkParam(module='dbsr', parameter='default_synthetic')
+    assert n.get_unique_name() == 'dbsr_default_synthetic' and n.get_display_name() == 'dbsr_default_synthetic'
+    assert NetworkParam(module='dbsr', parameter='x', epoch=7).get_unique_name() == 'dbsr_x_ep0007'
+    assert NetworkParam(module='dbsr', parameter='x', epoch=7, burst_sz=4).get_unique_name() == 'dbsr_x_ep0007_bsz04'
+    assert NetworkParam(module='dbsr', parameter='x', burst_sz=12, display_name='short').get_display_name() == 'short'
+    assert NetworkParam(unique_name='DBSR_results').get_unique_name() == 'DBSR_results'
+    with pytest.raises(AssertionError):
+        NetworkParam(network_path='a.pth')                                  # a downloaded checkpoint needs a unique_name
+    with pytest.raises(AssertionError):
+        NetworkParam(network_path='a.pth', unique_name='A', module='dbsr')   # ... and excludes module / parameter / epoch
+    nets = load_experiment('dbsr_default')
+    assert len(nets) == 1 and nets[0].network_path == 'dbsr_synthetic_default.pth' and nets[0].get_unique_name() == 'DBSR_syn'
+
+
+def test_checkpoint_loading_incl_reference_format(tmp_path, monkeypatch, capsys):
+    """admin/loading.py:24-100, utils/loading.py:6-19: checkpoint selection (file / latest of a directory / epoch), constructor
+    keyword overrides, and a checkpoint whose pickle names the REFERENCE's modules (`admin.model_constructor.NetConstructor`,
+    factory module `models.dbsr.dbsrnet`) -- what the published `dbsr_synthetic_default.pth` contains -- rebuilt with this
+    package's classes"""
+    import sys
+    import types
+    from deep_rawburst_sr_b200.admin import loading
+    from deep_rawburst_sr_b200.utils.loading import load_network
+    from deep_rawburst_sr_b200.evaluation.common_utils.network_param import NetworkParam
+    from deep_rawburst_sr_b200.models.dbsr.dbsrnet import dbsrnet_default_synthetic, DBSRNet
+    torch.manual_seed(3)
+    net = dbsrnet_default_synthetic()
+    sd = {k: v.clone() for k, v in net.state_dict().items()}
+    ws = tmp_path / 'ws'
+    d = ws / 'checkpoints' / 'dbsr' / 'default_synthetic'
+    d.mkdir(parents=True)
+    for ep in (3, 5):
+        torch.save({'epoch': ep, 'net': {k: v + ep for k, v in sd.items()}, 'constructor': net.constructor, 'net_info': {'e': ep}},
+                   str(d / ('DBSRNet_ep%04d.pth.tar' % ep)))
+    monkeypatch.setenv('DBSR_WORKSPACE_DIR', str(ws))
+    key = next(iter(sd))
+    latest = NetworkParam(module='dbsr', parameter='default_synthetic').load_net()
+    assert isinstance(latest, DBSRNet) and torch.equal(latest.state_dict()[key], sd[key] + 5) and latest.info == {'e': 5}
+    ep3 = NetworkParam(module='dbsr', parameter='default_synthetic', epoch=3).load_net()
+    assert torch.equal(ep3.state_dict()[key], sd[key] + 3)
+    with pytest.raises(Exception, match='No matching checkpoint'):
+        NetworkParam(module='dbsr', parameter='default_synthetic', epoch=4).load_net()
+    with pytest.raises(Exception, match='No matching checkpoint'):
+        load_network('dbsr/nothing_here')
+    # keyword overrides of constructor arguments: known ones replace the saved value, unknown ones are reported
+    n2, ck = load_network(str(d / 'DBSRNet_ep0003.pth.tar'), return_dict=True, not_an_argument=1)
+    assert ck['epoch'] == 3 and 'not_an_argument' in capsys.readouterr().out
+    # a checkpoint pickled inside the reference's module layout
+    ref_admin, ref_mc = types.ModuleType('admin'), types.ModuleType('admin.model_constructor')
+
+    class NetConstructor:
+        def __init__(self, fun_name, fun_module, args, kwds):
+            self.fun_name, self.fun_module, self.args, self.kwds = fun_name, fun_module, args, kwds
+    NetConstructor.__module__ = 'admin.model_constructor'
+    NetConstructor.__qualname__ = 'NetConstructor'
+    ref_mc.NetConstructor = NetConstructor
+    ref_admin.model_constructor = ref_mc
+    monkeypatch.setitem(sys.modules, 'admin', ref_admin)
+    monkeypatch.setitem(sys.modules, 'admin.model_constructor', ref_mc)
+    c = net.constructor
+    ref_ck = tmp_path / 'dbsr_synthetic_default.pth'
+    torch.save({'net': sd, 'constructor': NetConstructor(c.fun_name, 'models.dbsr.dbsrnet', c.args, dict(c.kwds)), 'net_info': None},
+               str(ref_ck))
+    monkeypatch.delitem(sys.modules, 'admin')
+    monkeypatch.delitem(sys.modules, 'admin.model_constructor')
+    monkeypatch.setenv('DBSR_PRETRAINED_NETS_DIR', str(tmp_path))
+    got = NetworkParam(network_path='dbsr_synthetic_default.pth', unique_name='DBSR_syn').load_net()
+    assert isinstance(got, DBSRNet) and type(got.constructor).__module__ == 'deep_rawburst_sr_b200.admin.model_constructor'
+    assert got.constructor.fun_module == 'deep_rawburst_sr_b200.models.dbsr.dbsrnet'
+    assert all(torch.equal(v, sd[k]) for k, v in got.state_dict().items())
+    assert loading.package_module('numpy.core') == 'numpy.core' and loading.package_module('models.x') == 'deep_rawburst_sr_b200.models.x'
+
+
 def test_batched_transform_sampling_is_bit_identical_to_the_per_burst_path():
     """rgb2rawburst_batch's host front end: the same `random` stream gives the same transform parameters, and the stacked
     matrix products / inversions equal the per-frame functions bit for bit"""
