@@ -194,8 +194,10 @@ def save_results(net, dataset=None, out_dir: Optional[str] = None, batch_size: i
         r = getattr(getattr(getattr(net, 'decoder', None), 'upsample_layer', None), 'upsample_factor', 8)
         for bi, start in enumerate(range(0, len(dataset), batch_size)):
             items = [dataset[i] for i in range(start, min(start + batch_size, len(dataset)))]
-            bursts = torch.stack([it[0][:burst_sz] if burst_sz is not None else it[0] for it in items]).float()
-            names = [it[2]['burst_name'] for it in items]
+            # tuples (burst, gt, meta_info) of SyntheticBurstVal, or the dicts of the BurstSR sampler
+            raw = [it['burst'] if isinstance(it, dict) else it[0] for it in items]
+            names = [it['burst_name'] if isinstance(it, dict) else it[2]['burst_name'] for it in items]
+            bursts = torch.stack([b[:burst_sz] if burst_sz is not None else b for b in raw]).float()
             b, _n, _c, h, w = bursts.shape
             if len(pending) >= 2:
                 flush(pending.pop(0))            # batch bi - 2 used the slot that is reused now: drain it first

@@ -191,3 +191,43 @@ def test_experiment_drivers_on_a_miniature_validation_set(dev, tmp_path, monkeyp
     assert abs(down['TINY']['psnr'] - live['TINY']['psnr']) < 1e-5
     direct = score_dataset(net.to(dev).eval(), data, batch_size=2, device=dev)
     assert abs(direct['psnr'] - live['TINY']['psnr']) < 1e-5 and abs(direct['ssim'] - live['TINY']['ssim']) < 1e-6
+
+
+def test_burstsr_drivers_save_and_score_by_experiment_name(dev, tmp_path, monkeypatch):
+    """evaluation/burstsr/{save_results,compute_score}.py by experiment name: predictions go to <save_data_path>/burstsr/<name>,
+    `load_saved` scores the files (criterion: at least one PNG per burst) and agrees with the live run"""
+    from deep_rawburst_sr_b200.evaluation.burstsr.compute_score import compute_score
+    from deep_rawburst_sr_b200.evaluation.burstsr.save_results import save_results
+    from deep_rawburst_sr_b200.evaluation.synburst.compute_score import load_experiment
+    from deep_rawburst_sr_b200.models.alignment.pwcnet import PWCNet
+    from deep_rawburst_sr_b200.models.dbsr.dbsrnet import dbsrnet_default_synthetic
+    from oracle import sca_oracle as S
+    assert load_experiment('dbsr_default', 'burstsr')[0].get_unique_name() == 'DBSR_burstsr'
+    net = dbsrnet_default_synthetic()
+    net.load_state_dict(O.make_state_dict(0, dbsr_gain=1.5), strict=True)
+    ck = tmp_path / 'nets' / 'real_net.pth'
+    ck.parent.mkdir()
+    torch.save({'net': net.state_dict(), 'constructor': net.constructor, 'net_info': None}, str(ck))
+    pwc = PWCNet(load_pretrained=False)
+    pwc.load_state_dict(S.pwc_state_dict(0, 1.0), strict=True)
+    pwc = pwc.to(dev).eval()
+    g = torch.Generator().manual_seed(31)
+    data = [{'burst': torch.rand(5, 4, 48, 48, generator=g), 'frame_gt': torch.rand(3, 384, 384, generator=g) * 0.5,
+             'burst_name': 'seq%02d' % i} for i in range(3)]
+    exp = tmp_path / 'exp_real'
+    exp.mkdir()
+    (exp / '__init__.py').write_text('')
+    (exp / 'one.py').write_text(
+        'from deep_rawburst_sr_b200.evaluation.common_utils.network_param import NetworkParam\n'
+        'def main():\n'
+        "    return [NetworkParam(network_path='real_net.pth', unique_name='REAL')]\n")
+    monkeypatch.syspath_prepend(str(tmp_path))
+    monkeypatch.setenv('DBSR_PRETRAINED_NETS_DIR', str(ck.parent))
+    monkeypatch.setenv('DBSR_SAVE_DATA_PATH', str(tmp_path / 'results'))
+    with pytest.raises(ValueError):
+        compute_score('exp_real.one')                      # the BurstSR RAW dataset classes are not part of the package
+    live = compute_score('exp_real.one', dataset=data, alignment_net=pwc, batch_size=2, device=dev, verbose=False)
+    assert save_results('exp_real.one', data, batch_size=2, device=dev) == {'REAL': 3}
+    assert sorted(os.listdir(str(tmp_path / 'results' / 'burstsr' / 'REAL'))) == ['seq00.png', 'seq01.png', 'seq02.png']
+    saved = compute_score('exp_real.one', load_saved=True, dataset=data, alignment_net=pwc, batch_size=2, device=dev, verbose=False)
+    assert abs(live['REAL']['psnr'] - saved['REAL']['psnr']) < 1e-4 and abs(live['REAL']['ssim'] - saved['REAL']['ssim']) < 1e-5
