@@ -69,6 +69,8 @@ PROTOTYPES = {
     'dbsr_space_to_depth2': (_I, [_PV, _PV, _VP]),
     'dbsr_deconv4x4s2': (_I, [_PV, _VP, _VP, _PV, _PV, _VP]),
     'dbsr_deconv_col2im': (_I, [_PV, _VP, _PV, _PV, _VP, _VP, _PV, _PV, _VP]),
+    'dbsr_deconv_col2im_ftaps': (_I, [_PV, _VP, _PV, _PV, _PV, _VP, _VP, _VP, _PV, _PV, _VP]),
+    'dbsr_flow_from_taps': (_I, [_PV, _VP, _PV, _VP]),
     'dbsr_corr81': (_I, [_PV, _PV, _PV, _F, _PV, _I, _I, _I, _I, _VP]),
     'dbsr_corr81_copy': (_I, [_PV, _PV, _PV, _F, _PV, _PV, _I, _I, _I, _I, _VP]),
     'dbsr_flow_head': (_I, [_PV, _VP, _I, _I, _I, _I, _VP]),

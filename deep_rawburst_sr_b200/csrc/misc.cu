@@ -325,8 +325,47 @@ __global__ void deconv4x4s2_kernel(View x, const float* __restrict__ w, const fl
 // The 2-channel flow deconvolution of the same level (netUpflow) is computed directly in the same pass.
 // One thread per output pixel.
 // -------------------------------------------------------------------------------------------------------
+// A 3x3 convolution with TWO output channels whose channel contraction ran as a 1x1 convolution Cin -> 18 planes
+//   ftaps[n, y, x, (ky*3 + kx)*2 + oc] = sum_ic x[n, y, x, ic] * w[oc, ic, ky, kx]
+// (the flow heads of PWC-Net's decoders, pwcnet.py:150: nine N = 16 tensor-core MMAs per K step become one):
+//   out[n, y, x, oc] = b[oc] + sum over the taps inside the map of ftaps[n, y + ky - 1, x + kx - 1, (ky*3 + kx)*2 + oc]
+__device__ __forceinline__ void flow_from_taps(const View& ftaps, const float* __restrict__ bias6, int n, int h, int w, int y,
+                                               int x, float& u, float& v) {
+  u = bias6[0]; v = bias6[1];
+#pragma unroll
+  for (int ky = 0; ky < 3; ++ky) {
+    const int yy = y + ky - 1;
+    if (yy < 0 || yy >= h) continue;
+#pragma unroll
+    for (int kx = 0; kx < 3; ++kx) {
+      const int xx = x + kx - 1;
+      if (xx < 0 || xx >= w) continue;
+      const long long q = ((long long)n * h + yy) * w + xx;
+      u += view_ld(ftaps, q, (ky * 3 + kx) * 2 + 0);
+      v += view_ld(ftaps, q, (ky * 3 + kx) * 2 + 1);
+    }
+  }
+}
+
+__global__ void flow_from_taps_kernel(View ftaps, const float* __restrict__ bias6, View y) {
+  griddep_launch_dependents_if_small();
+  griddep_wait();
+  const int h = ftaps.h, w = ftaps.w;
+  const long long total = (long long)ftaps.n * h * w;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int n = (int)(i / ((long long)h * w));
+    const int rem = (int)(i - (long long)n * h * w);
+    float u, v;
+    flow_from_taps(ftaps, bias6, n, h, w, rem / w, rem % w, u, v);
+    view_st(y, i, 0, u); view_st(y, i, 1, v);
+  }
+}
+
+// ftaps.data != NULL: the flow is not read from `flow` but summed from the 18 tap planes of its convolution on the fly
+// (the flow map of the coarser level is then never written)
 __global__ void deconv_col2im_kernel(View taps, const float* __restrict__ bias_t, View y_t, View flow,
-                                     const float* __restrict__ wf, const float* __restrict__ bias_f, View y_f, View y_f2) {
+                                     const float* __restrict__ wf, const float* __restrict__ bias_f, View y_f, View y_f2,
+                                     View ftaps, const float* __restrict__ bias6) {
   griddep_launch_dependents_if_small();
   griddep_wait();
   const int h = taps.h, w = taps.w, Ho = 2 * h, Wo = 2 * w;
@@ -337,7 +376,8 @@ __global__ void deconv_col2im_kernel(View taps, const float* __restrict__ bias_t
     const int oy = rem / Wo, ox = rem - oy * Wo;
     float t0 = bias_t[0], t1 = bias_t[1];
     float f0 = 0.0f, f1 = 0.0f;
-    const bool has_flow = flow.data != nullptr;
+    const bool from_taps = ftaps.data != nullptr;
+    const bool has_flow = flow.data != nullptr || from_taps;
     if (has_flow) { f0 = bias_f[0]; f1 = bias_f[1]; }
 #pragma unroll
     for (int a = 0; a < 2; ++a) {
@@ -354,7 +394,9 @@ __global__ void deconv_col2im_kernel(View taps, const float* __restrict__ bias_t
         t0 += view_ld(taps, pix, tap * 2 + 0);
         t1 += view_ld(taps, pix, tap * 2 + 1);
         if (has_flow) {
-          const float u = view_ld(flow, pix, 0), v = view_ld(flow, pix, 1);
+          float u, v;
+          if (from_taps) flow_from_taps(ftaps, bias6, n, h, w, iy2 >> 1, ix2 >> 1, u, v);
+          else { u = view_ld(flow, pix, 0); v = view_ld(flow, pix, 1); }
           const float* q = wf + tap * 4;      // [ky][kx][oc][ic]
           f0 = fmaf(u, __ldg(q + 0), fmaf(v, __ldg(q + 1), f0));
           f1 = fmaf(u, __ldg(q + 2), fmaf(v, __ldg(q + 3), f1));
@@ -643,13 +685,35 @@ extern "C" int dbsr_deconv4x4s2(const dbsr_nhwc_t* x, const float* w, const floa
   return check_launch("deconv4x4s2");
 }
 
+extern "C" int dbsr_flow_from_taps(const dbsr_nhwc_t* ftaps, const float* bias, const dbsr_nhwc_t* y, void* stream) {
+  DBSR_REQUIRE(view_ok(ftaps) && bias && view_ok(y) && ftaps->c == 18 && y->c == 2 && y->n == ftaps->n && y->h == ftaps->h &&
+                   y->w == ftaps->w, "flow_from_taps: ftaps must be [n, h, w, 18], y [n, h, w, 2]");
+  const long long total = (long long)y->n * y->h * y->w;
+  launch_pdl(flow_from_taps_kernel, dim3(grid_for(total, 256)), dim3(256), 0, (cudaStream_t)stream, make_view(ftaps), bias,
+             make_view(y));
+  return check_launch("flow_from_taps");
+}
+
 extern "C" int dbsr_deconv_col2im(const dbsr_nhwc_t* taps, const float* bias_t, const dbsr_nhwc_t* y_t,
                                   const dbsr_nhwc_t* flow, const float* wf, const float* bias_f, const dbsr_nhwc_t* y_f,
                                   const dbsr_nhwc_t* y_f2, void* stream) {
+  return dbsr_deconv_col2im_ftaps(taps, bias_t, y_t, flow, nullptr, nullptr, wf, bias_f, y_f, y_f2, stream);
+}
+
+extern "C" int dbsr_deconv_col2im_ftaps(const dbsr_nhwc_t* taps, const float* bias_t, const dbsr_nhwc_t* y_t,
+                                        const dbsr_nhwc_t* flow, const dbsr_nhwc_t* ftaps, const float* bias6, const float* wf,
+                                        const float* bias_f, const dbsr_nhwc_t* y_f, const dbsr_nhwc_t* y_f2, void* stream) {
   DBSR_REQUIRE(view_ok(taps) && bias_t && view_ok(y_t) && taps->c == 32 && y_t->c == 2 && y_t->n == taps->n &&
                    y_t->h == 2 * taps->h && y_t->w == 2 * taps->w, "deconv_col2im: bad tap / output geometry");
-  const bool has_flow = flow && flow->data;
-  if (has_flow)
+  const bool from_taps = ftaps && ftaps->data;
+  if (from_taps) {
+    DBSR_REQUIRE(!(flow && flow->data), "deconv_col2im: give the flow either as a map or as its 18 tap planes, not both");
+    DBSR_REQUIRE(view_ok(ftaps) && bias6 && wf && bias_f && view_ok(y_f) && ftaps->c == 18 && ftaps->n == taps->n &&
+                     ftaps->h == taps->h && ftaps->w == taps->w && y_f->c == 2 && y_f->n == y_t->n && y_f->h == y_t->h &&
+                     y_f->w == y_t->w, "deconv_col2im: bad flow-tap geometry");
+  }
+  const bool has_flow = (flow && flow->data) || from_taps;
+  if (has_flow && !from_taps)
     DBSR_REQUIRE(view_ok(flow) && wf && bias_f && view_ok(y_f) && flow->c == 2 && flow->n == taps->n && flow->h == taps->h &&
                      flow->w == taps->w && y_f->c == 2 && y_f->n == y_t->n && y_f->h == y_t->h && y_f->w == y_t->w,
                  "deconv_col2im: bad flow geometry");
@@ -658,8 +722,8 @@ extern "C" int dbsr_deconv_col2im(const dbsr_nhwc_t* taps, const float* bias_t, 
                          "deconv_col2im: second flow output geometry");
   const long long total = (long long)y_t->n * y_t->h * y_t->w;
   launch_pdl(deconv_col2im_kernel, dim3(grid_for(total, 256)), dim3(256), 0, (cudaStream_t)stream, 
-      make_view(taps), bias_t, make_view(y_t), make_view(has_flow ? flow : nullptr), wf, bias_f,
-      make_view(has_flow ? y_f : nullptr), make_view(has2 ? y_f2 : nullptr));
+      make_view(taps), bias_t, make_view(y_t), make_view(has_flow && !from_taps ? flow : nullptr), wf, bias_f,
+      make_view(has_flow ? y_f : nullptr), make_view(has2 ? y_f2 : nullptr), make_view(from_taps ? ftaps : nullptr), bias6);
   return check_launch("deconv_col2im");
 }
 

@@ -261,6 +261,24 @@ class DBSREngine:
                 self._add(k + '.taps', w1, None, tc=ptc, chmap=cm, cin_buf=length)
                 k = f'{pre}net{lname}.netUpflow'
                 self.D[k] = (pack_deconv(sd[k + '.weight'], device=self.device), sd[k + '.bias'].float().contiguous().to(self.device))
+        # Tensor-core path: the flow head of level L (netSix: 3x3, ~600 -> 2 channels) is nine N = 16 MMAs per K step that
+        # each fetch the whole activation tile from shared memory.  Its channel contraction is run as a 1x1 convolution to 18
+        # (tap, oc) planes instead -- one MMA per K step -- in the SAME launch as the 32 planes of the next level's netUpfeat
+        # (a transposed conv over the same concat buffer); the taps are summed by deconv_col2im / flow_from_taps.
+        #   rows [0, 32): netUpfeat of level L - 1 (levels 6..3), then 18 rows (ky*3 + kx)*2 + oc of netSix
+        self.pwc_flow_taps = ptc and os.environ.get('DBSR_NO_FLOW_TAPS', '0') != '1'
+        if self.pwc_flow_taps:
+            for lvl in (6, 5, 4, 3, 2):
+                lname = PWC_NAMES[lvl - 1]
+                cm, _s, length = self.pwc_layouts[lvl].chmap_from('o5')
+                w6 = _host(sd[f'{pre}net{lname}.netSix.0.weight'])                      # [2, K, 3, 3]
+                rows = [w6.permute(2, 3, 0, 1).reshape(18, -1)]
+                if lvl > 2:
+                    wu = _host(sd[f'{pre}net{PWC_NAMES[lvl - 2]}.netUpfeat.weight'])     # [K, 2, 4, 4]
+                    rows.insert(0, wu.permute(2, 3, 1, 0).reshape(32, -1))
+                wm = torch.cat(rows, 0)
+                self._add(f'{pre}net{lname}.netSix.taps', wm.reshape(wm.shape[0], -1, 1, 1).contiguous(), None, tc=True, chmap=cm,
+                          cin_buf=length, direct_too=False)
         cm, _s, length = self.pwc_layouts[2].chmap_from('o5')
         for j in range(7):
             k = f'{pre}netRefiner.netMain.{2 * j}'
@@ -485,13 +503,16 @@ class DBSREngine:
         segs = ['V', 'o1', 'o2', 'o3', 'o4', 'o5']
         prev_cat = None
         prev_flow = None
+        prev_taps = None          # tensor-core path: [pairs, h, w, 64] fp32, [0, 32) netUpfeat planes, [32, 50) flow-head planes
+        prev_b6 = None
+        ftaps = getattr(self, 'pwc_flow_taps', False)
         for lvl in (6, 5, 4, 3, 2):
             lay = self.pwc_layouts[lvl]
             lname = PWC_NAMES[lvl - 1]
             f1, f2 = first[lvl - 1], second[lvl - 1]
             h, w = f1.h, f1.w
             cat = self._buf(ws, f'cat{lvl}', pairs, h, w, lay.total, self.pwc_dtype, zero=True)
-            flow = self._buf(ws, f'flow{lvl}', pairs, h, w, 2, torch.float32)
+            flow = None if (ftaps and lvl > 2) else self._buf(ws, f'flow{lvl}', pairs, h, w, 2, torch.float32)
             vol = cat.slice(lay.off['V'], 81)
             if prev_cat is None:
                 self._run('corr81', ops.corr81, f1, f2, vol, pairs, group, act=ACT_LRELU)
@@ -499,10 +520,14 @@ class DBSREngine:
                 upflow = self._buf(ws, f'upflow{lvl}', pairs, h, w, 2, torch.float32)
                 wf, bf = self.D[f'{pre}net{lname}.netUpflow']
                 _wt, bt = self.D[f'{pre}net{lname}.netUpfeat']
-                taps = self._buf(ws, f'taps{lvl}', pairs, prev_cat.h, prev_cat.w, 32, torch.float32)
-                self._conv(f'{pre}net{lname}.netUpfeat.taps', prev_cat, taps, ACT_NONE)
-                self._run('deconv', ops.deconv_col2im, taps, bt, cat.slice(lay.off['upfeat'], 2), prev_flow, wf, bf,
-                          cat.slice(lay.off['upflow'], 2), upflow)
+                if ftaps:
+                    self._run('deconv', ops.deconv_col2im, prev_taps.slice(0, 32), bt, cat.slice(lay.off['upfeat'], 2), None, wf, bf,
+                              cat.slice(lay.off['upflow'], 2), upflow, flow_taps=prev_taps.slice(32, 18), flow_bias=prev_b6)
+                else:
+                    taps = self._buf(ws, f'taps{lvl}', pairs, prev_cat.h, prev_cat.w, 32, torch.float32)
+                    self._conv(f'{pre}net{lname}.netUpfeat.taps', prev_cat, taps, ACT_NONE)
+                    self._run('deconv', ops.deconv_col2im, taps, bt, cat.slice(lay.off['upfeat'], 2), prev_flow, wf, bf,
+                              cat.slice(lay.off['upflow'], 2), upflow)
                 # the first map's slice of the concat buffer is written by the cost-volume launch (it stages that tile anyway)
                 assert group == 0 or src_group == group + 1
                 self._run('corr81', ops.corr81, f1, f2, vol, pairs, group, flow=upflow, flow_scale=PWC_BACKWARP[lvl],
@@ -512,7 +537,17 @@ class DBSREngine:
                 out_name = 'o%d' % (j + 1)
                 self._conv(f'{pre}net{lname}.net{sub}.0', cat.slice(start, length),
                            cat.slice(lay.off[out_name], lay.sizes[out_name]), ACT_LRELU)
-            self._conv(f'{pre}net{lname}.netSix.0', cat, flow, ACT_NONE)
+            if ftaps:
+                mt = self._buf(ws, f'mtaps{lvl}', pairs, h, w, 64, torch.float32)
+                b6 = self.W[f'{pre}net{lname}.netSix.0'].bias
+                if lvl > 2:
+                    self._conv(f'{pre}net{lname}.netSix.taps', cat, mt.slice(0, 50), ACT_NONE)
+                    prev_taps, prev_b6 = mt, b6
+                else:       # the finest level's flow is a map: the refiner adds its output to it (pwcnet.py:231)
+                    self._conv(f'{pre}net{lname}.netSix.taps', cat, mt.slice(0, 18), ACT_NONE)
+                    self._run('deconv', ops.flow_from_taps, mt.slice(0, 18), b6, flow)
+            else:
+                self._conv(f'{pre}net{lname}.netSix.0', cat, flow, ACT_NONE)
             prev_cat, prev_flow = cat, flow
         # refiner (dilated convs), result added to the level-2 flow (pwcnet.py:231)
         h, w = prev_cat.h, prev_cat.w

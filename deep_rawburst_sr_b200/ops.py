@@ -246,17 +246,30 @@ def deconv4x4s2(x: Act, w: torch.Tensor, bias: torch.Tensor, y: Act, y2: Optiona
 
 
 def deconv_col2im(taps: Act, bias_t: torch.Tensor, y_t: Act, flow: Optional[Act] = None, wf: Optional[torch.Tensor] = None,
-                  bias_f: Optional[torch.Tensor] = None, y_f: Optional[Act] = None, y_f2: Optional[Act] = None) -> Act:
+                  bias_f: Optional[torch.Tensor] = None, y_f: Optional[Act] = None, y_f2: Optional[Act] = None,
+                  flow_taps: Optional[Act] = None, flow_bias: Optional[torch.Tensor] = None) -> Act:
     """scatter half of ConvTranspose2d(4, 2, 1) after a 1x1 conv produced the 32 (tap, oc) planes (+ the 2-channel
-    flow deconvolution of the same level when `flow` is given)"""
+    flow deconvolution of the same level when `flow` is given -- or `flow_taps` [n, h, w, 18] + `flow_bias`: the coarser
+    flow as the tap planes of its 3x3 convolution, summed on the fly)"""
     tv, yv = taps.view(), y_t.view()
     fv = flow.view() if flow is not None else _NULL_VIEW
+    ftv = flow_taps.view() if flow_taps is not None else _NULL_VIEW
     yfv = y_f.view() if y_f is not None else _NULL_VIEW
     yf2v = y_f2.view() if y_f2 is not None else _NULL_VIEW
-    _lib.check(_lib.load_library().dbsr_deconv_col2im(ctypes.byref(tv), bias_t.data_ptr(), ctypes.byref(yv), ctypes.byref(fv),
-                                                      _ptr(wf), _ptr(bias_f), ctypes.byref(yfv), ctypes.byref(yf2v),
-                                                      _stream()), 'dbsr_deconv_col2im')
+    _lib.check(_lib.load_library().dbsr_deconv_col2im_ftaps(ctypes.byref(tv), bias_t.data_ptr(), ctypes.byref(yv), ctypes.byref(fv),
+                                                            ctypes.byref(ftv), _ptr(flow_bias), _ptr(wf), _ptr(bias_f),
+                                                            ctypes.byref(yfv), ctypes.byref(yf2v), _stream()),
+               'dbsr_deconv_col2im_ftaps')
     return y_t
+
+
+def flow_from_taps(flow_taps: Act, bias: torch.Tensor, y: Act) -> Act:
+    """y[n, y, x, oc] = bias[oc] + sum_taps flow_taps[n, y + ky - 1, x + kx - 1, (ky * 3 + kx) * 2 + oc] (zero outside the map):
+    the second half of a 3x3 convolution with two output channels whose channel contraction ran as a 1x1 convolution"""
+    fv, yv = flow_taps.view(), y.view()
+    _lib.check(_lib.load_library().dbsr_flow_from_taps(ctypes.byref(fv), bias.data_ptr(), ctypes.byref(yv), _stream()),
+               'dbsr_flow_from_taps')
+    return y
 
 
 def corr81(f1: Act, f2: Act, out: Act, pairs: int, group: int = 0, flow: Optional[Act] = None, flow_scale: float = 0.0,

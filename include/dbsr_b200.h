@@ -184,6 +184,17 @@ int dbsr_deconv4x4s2(const dbsr_nhwc_t* x, const float* w, const float* bias, co
 int dbsr_deconv_col2im(const dbsr_nhwc_t* taps, const float* bias_t, const dbsr_nhwc_t* y_t, const dbsr_nhwc_t* flow,
                        const float* wf, const float* bias_f, const dbsr_nhwc_t* y_f, const dbsr_nhwc_t* y_f2,
                        void* stream);
+/* The decoders' flow heads (netSix: 3x3, Cin ~ 600 -> 2, pwcnet.py:150) in the same split form: the channel contraction runs
+ * as a 1x1 convolution Cin -> 18 planes, ftaps[n, y, x, (ky*3 + kx)*2 + oc] = sum_ic x[n, y, x, ic] * w[oc, ic, ky, kx] (ONE
+ * N = 32 tensor-core MMA per K step instead of nine N = 16 ones; it shares its launch with netUpfeat's 32 planes, which read
+ * the same concat buffer), and
+ *   dbsr_flow_from_taps       y[n, y, x, oc] = bias[oc] + sum of the taps inside the map  (the level-2 flow, fp32 [n, h, w, 2]);
+ *   dbsr_deconv_col2im_ftaps  dbsr_deconv_col2im with the coarser flow given as its 18 tap planes `ftaps` + `bias6` instead of
+ *                             a map (`flow` NULL): netUpflow sums the taps on the fly, the coarser flow map is never written. */
+int dbsr_flow_from_taps(const dbsr_nhwc_t* ftaps, const float* bias, const dbsr_nhwc_t* y, void* stream);
+int dbsr_deconv_col2im_ftaps(const dbsr_nhwc_t* taps, const float* bias_t, const dbsr_nhwc_t* y_t, const dbsr_nhwc_t* flow,
+                             const dbsr_nhwc_t* ftaps, const float* bias6, const float* wf, const float* bias_f,
+                             const dbsr_nhwc_t* y_f, const dbsr_nhwc_t* y_f2, void* stream);
 
 /* -------------------------------------------------------------------------------------------------- */
 /* PWC-Net cost volume: replaces correlation.FunctionCorrelation (correlation.py:280-330, 3 launches +  */

@@ -7,7 +7,7 @@ import sys
 
 FAMILY = [('resblock32_tc', 'resblock_tc'), ('conv_tc', 'conv_tc'), ('softmax_wsum', 'softmax_wsum'), ('corr81', 'corr81'), ('blur3x3', 'blur3x3'),
           ('warp_proj', 'warp_proj'), ('predictor', 'predictor'), ('space_to_depth', 'copy'), ('copy_channels', 'copy'),
-          ('deconv', 'deconv'), ('prep_burst', 'prep_burst'), ('offsets_mod', 'offsets_mod'), ('flow_head', 'flow_head'),
+          ('deconv', 'deconv'), ('flow_from_taps', 'deconv'), ('prep_burst', 'prep_burst'), ('offsets_mod', 'offsets_mod'), ('flow_head', 'flow_head'),
           ('conv_direct', 'conv_direct')]
 
 
