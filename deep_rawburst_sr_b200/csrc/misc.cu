@@ -332,6 +332,9 @@ __global__ void deconv4x4s2_kernel(View x, const float* __restrict__ w, const fl
 __device__ __forceinline__ void flow_from_taps(const View& ftaps, const float* __restrict__ bias6, int n, int h, int w, int y,
                                                int x, float& u, float& v) {
   u = bias6[0]; v = bias6[1];
+  // fp32 planes whose (oc = 0, 1) pair is 8-byte aligned (the engine's layout): one 8-byte load per tap
+  const bool pair_ld = ftaps.dtype == DBSR_F32 && ((ftaps.c_off | ftaps.c_pitch) & 1) == 0 &&
+                       (reinterpret_cast<uintptr_t>(ftaps.data) & 7) == 0;
 #pragma unroll
   for (int ky = 0; ky < 3; ++ky) {
     const int yy = y + ky - 1;
@@ -341,8 +344,14 @@ __device__ __forceinline__ void flow_from_taps(const View& ftaps, const float* _
       const int xx = x + kx - 1;
       if (xx < 0 || xx >= w) continue;
       const long long q = ((long long)n * h + yy) * w + xx;
-      u += view_ld(ftaps, q, (ky * 3 + kx) * 2 + 0);
-      v += view_ld(ftaps, q, (ky * 3 + kx) * 2 + 1);
+      if (pair_ld) {
+        const float2 t = __ldg(reinterpret_cast<const float2*>(reinterpret_cast<const float*>(ftaps.data) + q * ftaps.c_pitch +
+                                                                ftaps.c_off + (ky * 3 + kx) * 2));
+        u += t.x; v += t.y;
+      } else {
+        u += view_ld(ftaps, q, (ky * 3 + kx) * 2 + 0);
+        v += view_ld(ftaps, q, (ky * 3 + kx) * 2 + 1);
+      }
     }
   }
 }

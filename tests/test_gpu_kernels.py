@@ -408,8 +408,9 @@ def test_store_paths_stay_inside_their_views(dev, n, h, w):
                 assert torch.equal(cat.slice(88, c).to_nchw(), feats.images(0, n).to_nchw())
 
 
+@pytest.mark.parametrize('coff', [32, 33])          # 8-byte aligned (oc pair in one load) / odd offset (scalar loads)
 @pytest.mark.parametrize('n,h,w', [(3, 1, 1), (2, 2, 2), (2, 4, 5), (1, 8, 8), (2, 16, 16)])
-def test_flow_head_as_tap_planes(dev, n, h, w):
+def test_flow_head_as_tap_planes(dev, n, h, w, coff):
     """pwcnet.py:150 (netSix: Conv2d(Cin, 2, 3, 1, 1)) split into a 1x1 channel contraction to 18 (tap, oc) planes and a tap sum:
     (a) `flow_from_taps` of the planes of a reference conv equals that conv; (b) `deconv_col2im` fed with the planes (+ bias)
     gives bit for bit what it gives when fed with the flow map those planes sum to."""
@@ -425,9 +426,9 @@ def test_flow_head_as_tap_planes(dev, n, h, w):
     taps32 = torch.randn(n, 32, h, w, generator=g)
     buf = ops.Act(torch.zeros((n, h, w, 64), dtype=torch.float32, device=dev))
     buf.slice(0, 32).from_nchw(taps32.to(dev).contiguous())
-    buf.slice(32, 18).from_nchw(planes.to(dev).contiguous())
+    buf.slice(coff, 18).from_nchw(planes.to(dev).contiguous())
     flow = ops.Act.empty(n, h, w, 2, torch.float32, dev)
-    ops.flow_from_taps(buf.slice(32, 18), b6.to(dev), flow)
+    ops.flow_from_taps(buf.slice(coff, 18), b6.to(dev), flow)
     assert (flow.to_nchw().cpu() - ref).abs().max() < 1e-5
     wf = torch.randn(4, 4, 2, 2, generator=g).to(dev)
     bf, bt = torch.randn(2, generator=g).to(dev), torch.randn(2, generator=g).to(dev)
@@ -437,14 +438,14 @@ def test_flow_head_as_tap_planes(dev, n, h, w):
         y_f = ops.Act.empty(n, 2 * h, 2 * w, 2, torch.float32, dev)
         y_f2 = ops.Act.empty(n, 2 * h, 2 * w, 2, torch.float32, dev)
         if from_planes:
-            ops.deconv_col2im(buf.slice(0, 32), bt, y_t, None, wf, bf, y_f, y_f2, flow_taps=buf.slice(32, 18), flow_bias=b6.to(dev))
+            ops.deconv_col2im(buf.slice(0, 32), bt, y_t, None, wf, bf, y_f, y_f2, flow_taps=buf.slice(coff, 18), flow_bias=b6.to(dev))
         else:
             ops.deconv_col2im(buf.slice(0, 32), bt, y_t, flow, wf, bf, y_f, y_f2)
         outs.append((y_t.buf.clone(), y_f.buf.clone(), y_f2.buf.clone()))
     for a_, b_ in zip(*outs):
         assert torch.equal(a_, b_)
     with pytest.raises(Exception):
-        ops.deconv_col2im(buf.slice(0, 32), bt, y_t, flow, wf, bf, y_f, None, flow_taps=buf.slice(32, 18), flow_bias=b6.to(dev))
+        ops.deconv_col2im(buf.slice(0, 32), bt, y_t, flow, wf, bf, y_f, None, flow_taps=buf.slice(coff, 18), flow_bias=b6.to(dev))
 
 
 def test_prep_burst_and_flow_head(dev):
