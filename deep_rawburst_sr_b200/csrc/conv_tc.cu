@@ -1017,9 +1017,14 @@ static int tc_plan(const dbsr_conv_t* c, TcConfig* cfg, bool set_err, bool allow
   cfg->rows = TILE_H + 2 * pad;
   // small maps: pack several whole images (with their zero borders) into one M = 128 tile -- "flat" mode
   cfg->flat = 0; cfg->flat_s = 0; cfg->flat_ni = 1;
-  if (c->ksize == 3 && c->dilation == 1 && r == 1 && c->x.h <= 8 && c->x.w <= 8) {
-    const int S = (c->x.h + 2) * (c->x.w + 2);
-    const int last = (c->x.h - 1) * (c->x.w + 2) + (c->x.w - 1);
+  // (1x1 kernels need no border: the slots are the pixels themselves, 128 / (h*w) images per tile -- the tap GEMMs of PWC-Net's
+  //  flow heads on 1x1 .. 8x8 maps use 100 % of their M rows instead of 1 .. 50 %)
+  const int bord = c->ksize == 3 ? 2 : 0;
+  static const bool flat_k1 = getenv("DBSR_TC_NO_FLAT_K1") == nullptr;      // A/B switch
+  // (only for many images: with a few dozen, one image per tile keeps more CTAs busy -- 2 bursts: 1 503 vs 1 470 bursts/s)
+  if (((c->ksize == 3 && c->dilation == 1) || (c->ksize == 1 && flat_k1 && c->x.n >= 2 * 148)) && r == 1 && c->x.h <= 8 && c->x.w <= 8) {
+    const int S = (c->x.h + bord) * (c->x.w + bord);
+    const int last = (c->x.h - 1) * (c->x.w + bord) + (c->x.w - 1);
     const int ni = (127 - last) / S + 1;
     if (ni >= 2) { cfg->flat = 1; cfg->flat_s = S; cfg->flat_ni = ni; }
   }
@@ -1029,10 +1034,10 @@ static int tc_plan(const dbsr_conv_t* c, TcConfig* cfg, bool set_err, bool allow
     // two M tiles (2 * ni images) per item share every weight tile when that still leaves work for half the SMs: the
     // CTAs of these tiny-M layers are bound by streaming the whole weight set from L2 once per item
     cfg->mt = (ceil_div(c->x.n, cfg->flat_ni) >= 100 && 2 * 2 * nt <= 512) ? 2 : 1;
-    cfg->halo_w = c->x.w + 2; cfg->rows = c->x.h + 2;
+    cfg->halo_w = c->x.w + bord; cfg->rows = c->x.h + bord;
     cfg->a_tx_bytes = cfg->mt * cfg->flat_ni * cfg->flat_s * ck * 2;
     // the MMA reads up to slot 127 + 2*halo_w + 2 of its tile (garbage rows beyond the box only feed masked outputs)
-    const int a_read = ((cfg->mt - 1) * cfg->flat_ni * cfg->flat_s + 128 + 2 * cfg->halo_w + 2) * ck * 2;
+    const int a_read = ((cfg->mt - 1) * cfg->flat_ni * cfg->flat_s + 128 + (bord ? 2 * cfg->halo_w + 2 : 0)) * ck * 2;
     cfg->a_bytes = round_up(a_read > cfg->a_tx_bytes ? a_read : cfg->a_tx_bytes, 1024);
     cfg->a_slots = 4;
     while (cfg->a_slots > 1 && cfg->a_slots * cfg->a_bytes + 4 * cfg->b_bytes > budget) cfg->a_slots--;

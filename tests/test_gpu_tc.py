@@ -43,6 +43,13 @@ TC_CASES = {
     'flat_4x4_437x96_n11': (437, 96, 3, 1, 11, 4, 4, 2, False, False, 0),
     'flat_4x4_629x2_f32': (629, 2, 3, 1, 7, 4, 4, 0, True, True, 0),
     'flat_2x3_128x128': (128, 128, 3, 1, 9, 2, 3, 1, True, False, 0),
+    # 1x1 kernels on small maps: flat mode without a border (128 / (h*w) images per tile): the tap GEMMs of the flow heads
+    'flat_k1_1x1_529x50_n326_f32': (529, 50, 1, 1, 326, 1, 1, 0, False, True, 0),
+    'flat_k1_1x1_196x64_n300': (196, 64, 1, 1, 300, 1, 1, 2, False, False, 0),
+    'flat_k1_2x2_661x50_n337_f32': (661, 50, 1, 1, 337, 2, 2, 0, False, True, 0),
+    'flat_k1_4x4_629x50_n416_f32': (629, 50, 1, 1, 416, 4, 4, 0, False, True, 0),
+    'flat_k1_8x8_597x50_n297_f32': (597, 50, 1, 1, 297, 8, 8, 0, False, True, 0),
+    'flat_k1_3x5_64x32_res': (64, 32, 1, 1, 319, 3, 5, 1, True, False, 0),
     # many small images: an item holds TWO M tiles that share every weight tile -- flat mode (2 x ni images, odd image count
     # so the last item is half empty) and narrow regular maps (two consecutive 8x8 / 8x5 images per item)
     'flat_4x4_pair_209x128_n331': (209, 128, 3, 1, 331, 4, 4, 2, False, False, 0),
