@@ -787,10 +787,52 @@ __global__ void __launch_bounds__(256) blur3x3_sep_kernel(View x, View y, float 
   const T* xb = reinterpret_cast<const T*>(x.data) + x.c_off + c8 * 8;
   T* yb = reinterpret_cast<T*>(y.data) + y.c_off + c8 * 8;
   const bool has_l = px > 0, has_r = px + 1 < W;
+  const int r_end = min(y0 + rows, H);
+  if constexpr (sizeof(T) == 2) {
+    // bf16 maps: the same operations in the same order on packed fp32 pairs (FFMA2: half the arithmetic issue slots -- ncu
+    // had this kernel at 54 % issue-slot utilisation and 42 % of the DRAM peak, i.e. instruction bound); results are
+    // bit-identical to the scalar form below
+    const f32x2_t A0 = f2_pack(a0, a0), A1 = f2_pack(a1, a1), A2 = f2_pack(a2, a2);
+    const f32x2_t B0 = f2_pack(b0, b0), B1 = f2_pack(b1, b1), B2 = f2_pack(b2, b2), Z = f2_pack(0.0f, 0.0f);
+    f32x2_t hm2[4] = {Z, Z, Z, Z}, hm1[4] = {Z, Z, Z, Z};
+#pragma unroll 4
+    for (int r = y0 - 1; r <= r_end; ++r) {
+      f32x2_t h[4] = {Z, Z, Z, Z};
+      if (r >= 0 && r < H) {
+        const T* row = xb + (((long long)n * H + r) * W + px) * x.c_pitch;
+        const Vec8p c = unpack_bf16x8_p(__ldg(reinterpret_cast<const uint4*>(row)));
+#pragma unroll
+        for (int k = 0; k < 4; ++k) h[k] = f2_mul(c.p[k], A1);
+        if (has_l) {
+          const Vec8p l = unpack_bf16x8_p(__ldg(reinterpret_cast<const uint4*>(row - x.c_pitch)));
+#pragma unroll
+          for (int k = 0; k < 4; ++k) h[k] = f2_fma(l.p[k], A0, h[k]);
+        }
+        if (has_r) {
+          const Vec8p rr = unpack_bf16x8_p(__ldg(reinterpret_cast<const uint4*>(row + x.c_pitch)));
+#pragma unroll
+          for (int k = 0; k < 4; ++k) h[k] = f2_fma(rr.p[k], A2, h[k]);
+        }
+      }
+      if (r - 1 >= y0 && r - 1 < r_end) {
+        uint32_t o[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          float lo, hi;
+          f2_unpack(f2_fma(h[k], B2, f2_fma(hm1[k], B1, f2_mul(hm2[k], B0))), lo, hi);
+          const __nv_bfloat162 pk = __floats2bfloat162_rn(lo, hi);
+          o[k] = *reinterpret_cast<const uint32_t*>(&pk);
+        }
+        *reinterpret_cast<uint4*>(yb + (((long long)n * H + (r - 1)) * W + px) * y.c_pitch) = make_uint4(o[0], o[1], o[2], o[3]);
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) { hm2[k] = hm1[k]; hm1[k] = h[k]; }
+    }
+    return;
+  }
   Vec8 hm2, hm1;       // horizontal sums of rows r-2 and r-1
 #pragma unroll
   for (int k = 0; k < 8; ++k) { hm2.v[k] = 0.0f; hm1.v[k] = 0.0f; }
-  const int r_end = min(y0 + rows, H);
 #pragma unroll 4
   for (int r = y0 - 1; r <= r_end; ++r) {
     Vec8 h;

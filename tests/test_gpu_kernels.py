@@ -611,6 +611,15 @@ def test_blur_and_predictor(dev):
         yt = ops.Act.empty(1, 70, 9, 8, torch.float32, dev)
         ops.blur3x3(_act_from(xt, dev), yt, kk.reshape(-1).tolist())
         assert (yt.to_nchw().cpu() - reft).abs().max() < 1e-6
+    # bf16 maps take a packed-fp32 (two values per instruction) form of the separable kernel: same operations, same order --
+    # its output must be the bf16 rounding of what the fp32 kernel computes from the same bf16-rounded input, bit for bit
+    for (nn, hh, ww) in ((2, 70, 9), (1, 33, 40)):
+        xb = torch.rand(nn, 32, hh, ww, generator=g).bfloat16().float()
+        y32 = ops.Act.empty(nn, hh, ww, 32, torch.float32, dev)
+        ops.blur3x3(_act_from(xb, dev), y32, K.reshape(-1).tolist())
+        y16 = ops.Act.empty(nn, hh, ww, 32, torch.bfloat16, dev)
+        ops.blur3x3(_act_from(xb, dev, dtype=torch.bfloat16), y16, K.reshape(-1).tolist())
+        assert torch.equal(y16.buf, y32.buf.bfloat16())
     wt = torch.randn(3, 32, generator=g)
     b = torch.randn(3, generator=g)
     pred = torch.empty(2, 3, 16, 24, device=dev)
