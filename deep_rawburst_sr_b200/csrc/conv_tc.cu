@@ -704,7 +704,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
     uint8_t* stg = smem_stg + (size_t)warp * STG_WARP_BYTES;
     int acc = 0; uint32_t acc_phase = 0;
     if (p.pred == nullptr && !p.flat && p.bias_smem && p.vec_ok && p.y_dtype == DBSR_BF16 &&
-        (p.res == nullptr || NT == 64 || NT == 32 || NT == 16)) {
+        (p.res == nullptr || NT == 128 || NT == 64 || NT == 32 || NT == 16)) {
       // ---------- lean coalesced path (every bf16 layer of the encoder / fusion / decoder trunks) ----------
       const uint32_t stg_s = smem_u32(stg);
       const uint32_t bias_s0 = smem_u32(bias_tab);
@@ -721,7 +721,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
       const bool has_res = p.res != nullptr;
       const long long r_row = (long long)p.yW * p.r_pitch, r_col = (long long)p.r_pitch;
       const __nv_bfloat16* const rbase = reinterpret_cast<const __nv_bfloat16*>(p.res) + p.r_coff + (long long)(quarter * 4) * r_row;
-      const bool my_group = (p.mt == 2) || group == 0;      // NT <= 64 is one group: with mt == 1 warps 4..7 have no columns
+      // NT <= 64 is one group: with mt == 1 warps 4..7 have no columns; NT == 128 with mt == 1: warps 4..7 own the second group
+      const bool my_group = (p.mt == 2) || group == 0 || NT == 128;
+      const int first_g0 = (p.mt == 2 || NT != 128) ? 0 : group * 64;
       for (long long item = item_first; item < p.total_items; item += item_step) {
         const ItemCoord c = decode_item(p, item, pair_rank);
         const int co0 = c.nt * NT;
@@ -745,8 +747,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
             if (lane == 0) tma_store_wait_read();
             __syncwarp();
           }
-          const __nv_bfloat16* rwarp = rbase + ((long long)(img_t * p.yH + c.y0) * p.yW + tx0) * p.r_pitch + co0;
-          if (NT == 64) lean_prefetch_res<64>(stg_s, lane, rwarp, r_row, r_col, rows_left, cols_in, p.res);
+          const __nv_bfloat16* rwarp = rbase + ((long long)(img_t * p.yH + c.y0) * p.yW + tx0) * p.r_pitch + co0 + first_g0;
+          if (NT >= 64) lean_prefetch_res<64>(stg_s, lane, rwarp, r_row, r_col, rows_left, cols_in, p.res);
           else if (NT == 32) lean_prefetch_res<32>(stg_s, lane, rwarp, r_row, r_col, rows_left, cols_in, p.res);
           else lean_prefetch_res<16>(stg_s, lane, rwarp, r_row, r_col, rows_left, cols_in, p.res);
         }
@@ -757,6 +759,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
           const int rem = NT - g0;
           const int gw = rem >= 64 ? 64 : (rem >= 32 ? 32 : 16);
           if (p.mt == 2 || (gi & 1) == group) {
+            if (has_res && g0 > first_g0) {     // second 64-channel group of an N = 128 tile: its residual rows, once the store
+              if (p.tma_store) {                // of the first group has finished reading the staging rows
+                if (lane == 0) tma_store_wait_read();
+              }
+              __syncwarp();
+              const __nv_bfloat16* rwarp = rbase + ((long long)(img_t * p.yH + c.y0) * p.yW + tx0) * p.r_pitch + co0 + g0;
+              lean_prefetch_res<64>(stg_s, lane, rwarp, r_row, r_col, rows_left, cols_in, p.res);
+            }
             const CUtensorMap* ty_map = p.tma_store ? &tmap_y : nullptr;
             const int sy = c.y0 + quarter * 4;
             // pixel shuffle: packed channel co' = i*256 + j*32 + c -> store coordinates ((j, c) = co' % 256, i = co' / 256)
@@ -1084,10 +1094,14 @@ static int tc_plan(const dbsr_conv_t* c, TcConfig* cfg, bool set_err, bool allow
   while (tc < cfg->acc_stages * cfg->mt * nt) tc <<= 1;
   cfg->tmem_cols = tc;
   // residual on the tensor core: extra K chunks with identity weights (bf16 residual, aligned, same channel chunking)
+  // DBSR_TC_RES128_EPI=1: N tile 128 also takes it in the lean epilogue (two 64-channel groups per warp; the second group's
+  // rows are prefetched after the first group's store has drained the staging rows)
+  static const bool res128_epilogue = getenv("DBSR_TC_RES128_EPI") != nullptr && atoi(getenv("DBSR_TC_RES128_EPI")) != 0;
   cfg->res_chunks = 0;
   if (c->residual.data && !cfg->flat && c->residual.dtype == DBSR_BF16 && (c->residual.c_off % 8) == 0 &&
       (c->residual.c_pitch % 8) == 0 && ((uintptr_t)c->residual.data % 16) == 0 && nt % ck == 0 &&
-      !(vec && c->y.dtype == DBSR_BF16 && nt == 64 && cpad * 4 <= BIAS_TAB_BYTES))
+      !(vec && c->y.dtype == DBSR_BF16 && (nt == 64 || (nt == 128 && res128_epilogue && c->residual_group <= 1)) &&
+        cpad * 4 <= BIAS_TAB_BYTES))
     cfg->res_chunks = nt / ck;       // N tile 64 takes the residual in the (prefetching) lean epilogue instead: there the extra
                                      // K chunk costs a whole halo slot of the A ring; at N = 32 the epilogue is the bottleneck and at
                                      // N = 128 the staging area holds half a pixel row, so both keep the tensor-core residual
