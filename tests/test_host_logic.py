@@ -320,6 +320,44 @@ def test_checkpoint_loading_incl_reference_format(tmp_path, monkeypatch, capsys)
     assert loading.package_module('numpy.core') == 'numpy.core' and loading.package_module('models.x') == 'deep_rawburst_sr_b200.models.x'
 
 
+def test_flow_head_and_upfeat_as_one_tap_gemm_algebra():
+    """The algebra behind `engine._pack_pwc`'s merged weight (DESIGN.md 4.1 "flow heads as tap planes"): one 1x1 contraction of
+    the decoder's concat features with the rows [netUpfeat planes (ky*4+kx)*2+oc | netSix planes (ky*3+kx)*2+oc], followed by
+    (a) the 9-tap sum `flow_from_taps` implements = Conv2d(K, 2, 3, 1, 1) (pwcnet.py:150), and (b) the <= 4-tap scatter
+    `deconv_col2im` implements = ConvTranspose2d(K, 2, 4, 2, 1) (pwcnet.py:120).  Plain torch on the CPU, fp64."""
+    import torch.nn.functional as F
+    g = torch.Generator().manual_seed(9)
+    n, K, h, w = 2, 37, 5, 6
+    x = torch.randn(n, K, h, w, generator=g, dtype=torch.float64)
+    w6 = torch.randn(2, K, 3, 3, generator=g, dtype=torch.float64)
+    b6 = torch.randn(2, generator=g, dtype=torch.float64)
+    wu = torch.randn(K, 2, 4, 4, generator=g, dtype=torch.float64)           # ConvTranspose2d weight: [in, out, kh, kw]
+    bu = torch.randn(2, generator=g, dtype=torch.float64)
+    rows = torch.cat([wu.permute(2, 3, 1, 0).reshape(32, K), w6.permute(2, 3, 0, 1).reshape(18, K)], 0)   # as the engine packs them
+    planes = torch.einsum('nkhw,rk->nrhw', x, rows)                           # the one 1x1 GEMM, 50 output planes
+    up_planes, flow_planes = planes[:, :32], planes[:, 32:]
+    # (a) flow head
+    flow = b6.view(1, 2, 1, 1).expand(n, 2, h, w).clone()
+    pad = F.pad(flow_planes, (1, 1, 1, 1))
+    for ky in range(3):
+        for kx in range(3):
+            t = (ky * 3 + kx) * 2
+            flow += pad[:, t:t + 2, ky:ky + h, kx:kx + w]
+    assert torch.allclose(flow, F.conv2d(x, w6, b6, padding=1), atol=1e-10)
+    # (b) transposed conv: out[oy, ox] = b + sum over (ky, kx) with iy = (oy + 1 - ky) / 2, ix = (ox + 1 - kx) / 2 integral and inside
+    up = bu.view(1, 2, 1, 1).expand(n, 2, 2 * h, 2 * w).clone()
+    for oy in range(2 * h):
+        for ox in range(2 * w):
+            for ky in range(4):
+                for kx in range(4):
+                    iy2, ix2 = oy + 1 - ky, ox + 1 - kx
+                    if iy2 % 2 or ix2 % 2 or not (0 <= iy2 // 2 < h) or not (0 <= ix2 // 2 < w):
+                        continue
+                    t = (ky * 4 + kx) * 2
+                    up[:, :, oy, ox] += up_planes[:, t:t + 2, iy2 // 2, ix2 // 2]
+    assert torch.allclose(up, F.conv_transpose2d(x, wu, bu, stride=2, padding=1), atol=1e-10)
+
+
 def test_batched_transform_sampling_is_bit_identical_to_the_per_burst_path():
     """rgb2rawburst_batch's host front end: the same `random` stream gives the same transform parameters, and the stacked
     matrix products / inversions equal the per-frame functions bit for bit"""
